@@ -1,0 +1,123 @@
+/* mcba.h — C-ABI of the B200 bundle-adjustment engine (libmcba.so).
+ *
+ * Drop-in boundary for ONE numeric seam of the reference (multical):
+ *     scipy.optimize.least_squares(evaluate, self.param_vec, jac_sparsity=..., x_scale='jac',
+ *                                  f_scale=..., ftol=..., max_nfev=..., method='trf', loss=...)
+ *     -- multical/optimization/calibration.py:209-210 (inside Calibration.bundle_adjust, 199-212)
+ * plus the residual closure it drives (calibration.py:204-206) and the reprojection-error /
+ * outlier statistics that bracket every call (calibration.py:134-141, 240-252; tables.py:244-249).
+ *
+ * Plain C types only: opaque handle, host pointers + sizes, integer status (0 = ok; message via
+ * mcba_last_error).  All host arrays are borrowed for the duration of the call and copied.
+ * There is no CPU fallback: every entry point fails with MCBA_ERR_CUDA if no sm_100 device works.
+ *
+ * Index contract (bit-exact with the reference): packed corner k corresponds to row k of
+ * np.argwhere(calib.inliers) = (camera, frame, board, point) in row-major order of the dense
+ * [C,F,B,P] table (calibration.py:206 boolean-mask order); residual vector element 2k is u, 2k+1 is v.
+ * Parameter vector layout = reference order (calibration.py:146-153, parameters.py:104-106):
+ *   [camera_poses 6C][board_poses 6B][motion 6F][cameras (5+nd)C]   (enabled blocks only)
+ *   pose = [rx ry rz tx ty tz] (transform/rtvec.py:16-27), camera = [fx fy cx cy skew dist...]
+ *   (camera.py:144-155).
+ */
+#ifndef MCBA_H
+#define MCBA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcba_ctx mcba_ctx;
+
+enum { MCBA_OK = 0, MCBA_ERR_ARG = 1, MCBA_ERR_CUDA = 2, MCBA_ERR_STATE = 3, MCBA_ERR_NCCL = 4,
+       MCBA_ERR_NONFINITE = 5, MCBA_ERR_UNSUPPORTED = 6 };
+
+/* camera models: camera.py:43-48 (cv2.projectPoints, 5/8/12 coefficients) and
+ * camera_fisheye.py:113-117 (cv2.fisheye.projectPoints, 4 coefficients) */
+enum { MCBA_MODEL_STANDARD = 0, MCBA_MODEL_RATIONAL = 1, MCBA_MODEL_THIN_PRISM = 2, MCBA_MODEL_FISHEYE = 3 };
+
+/* loss names of scipy.optimize.least_squares (config/arguments.py:59) */
+enum { MCBA_LOSS_LINEAR = 0, MCBA_LOSS_SOFT_L1 = 1, MCBA_LOSS_HUBER = 2, MCBA_LOSS_CAUCHY = 3, MCBA_LOSS_ARCTAN = 4 };
+
+/* which parameter blocks are free: Calibration.optimize (calibration.py:28-35,155-161) */
+enum { MCBA_OPT_CAMERA_POSES = 1, MCBA_OPT_BOARD_POSES = 2, MCBA_OPT_MOTION = 4, MCBA_OPT_CAMERAS = 8,
+       MCBA_OPT_FIX_ASPECT = 256 /* camera.py:147-148,159-160 */ };
+
+typedef struct {
+  int32_t C, F, B, P;       /* Calibration.size (calibration.py:64-67); F = frames held by THIS rank   */
+  int32_t model;            /* MCBA_MODEL_*                                                            */
+  int32_t optimize;         /* bitmask MCBA_OPT_*                                                      */
+  int64_t N;                /* packed inlier corners held by this rank                                 */
+} mcba_problem_desc;
+
+typedef struct {
+  double ftol, xtol, gtol;  /* scipy defaults 1e-8; the reference passes ftol=tolerance (1e-4)         */
+  double f_scale;           /* least_squares f_scale                                                   */
+  int32_t max_nfev;         /* max_iterations -> max_nfev (calibration.py:199,210)                     */
+  int32_t loss;             /* MCBA_LOSS_*                                                             */
+} mcba_solve_opts;
+
+typedef struct {            /* one row of scipy's verbose=2 table (calibration.py:208)                 */
+  int32_t iteration, nfev;
+  double cost, cost_reduction, step_norm, optimality;
+} mcba_log_row;
+
+typedef struct {
+  double cost, initial_cost, optimality;
+  int32_t nfev, njev, status;   /* scipy termination status -1,0,1,2,3,4 (_lsq/common.py:705-717)      */
+  int32_t n_log;                /* rows written to the log buffer                                      */
+  double device_ms;             /* CUDA-event time of the solve on the context stream                  */
+  int32_t kernel_launches;      /* kernels launched by this solve                                      */
+  int32_t chol_retries;
+} mcba_solve_result;
+
+/* -- context ------------------------------------------------------------------------------------ */
+int  mcba_create(int device_ordinal, mcba_ctx** out);
+void mcba_destroy(mcba_ctx* ctx);
+const char* mcba_last_error(const mcba_ctx* ctx);   /* ctx may be NULL: returns the creation error     */
+int  mcba_set_stream(mcba_ctx* ctx, void* cuda_stream);   /* e.g. torch.cuda.current_stream().cuda_stream */
+int  mcba_version(void);
+
+/* -- multi-GPU: one context per process/GPU; frames are sharded across ranks ---- */
+int  mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]);      /* rank 0, then broadcast by the host   */
+int  mcba_comm_init(mcba_ctx* ctx, const char id[128], int rank, int world);
+
+/* -- problem upload: replaces what `evaluate` closes over (calibration.py:204-206) --------------
+ * cam/frame/board/point: int32[N] rows of np.argwhere(inliers) (frame ids local to this rank);
+ * obs: f64[N][2] = point_table.points[inliers] (calibration.py:206);
+ * board_points: f64[B][P][3] = tables.stack_boards(boards).points (tables.py:385-394).            */
+int  mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc,
+                 const int32_t* cam, const int32_t* frame, const int32_t* board, const int32_t* point,
+                 const double* obs, const double* board_points);
+
+/* full parameter state (also the values of disabled/fixed blocks):
+ * cam_rt f64[C][6], board_rt f64[B][6], frame_rt f64[F][6] (PoseSet.params, pose_set.py:51-53),
+ * intrinsics f64[C][5+nd] (Camera.params, camera.py:144-155)                                      */
+int  mcba_set_params(mcba_ctx* ctx, const double* cam_rt, const double* board_rt,
+                     const double* frame_rt, const double* intrinsics);
+int  mcba_get_params(mcba_ctx* ctx, double* cam_rt, double* board_rt, double* frame_rt, double* intrinsics);
+int  mcba_num_params(mcba_ctx* ctx, int64_t* n);      /* length of param_vec for the enabled blocks    */
+int  mcba_get_param_vec(mcba_ctx* ctx, double* x);    /* Parameters.param_vec (parameters.py:44-46)    */
+int  mcba_set_param_vec(mcba_ctx* ctx, const double* x);   /* with_param_vec (parameters.py:48-50)     */
+
+/* -- parity hooks -------------------------------------------------------------------------------
+ * residuals: r f64[2N] = evaluate(x) (calibration.py:204-206); cost = 0.5*sum(rho) as scipy.       */
+int  mcba_residuals(mcba_ctx* ctx, const double* x /*NULL = current params*/, double* r, double* cost);
+/* linearize at x: dense J^T J (f64[n][n], row-major, parameter order of param_vec) and J^T r (f64[n])
+ * of the (loss-scaled) residual -- what scipy's FD Jacobian + compute_grad produce (trf.py).       */
+int  mcba_linearize(mcba_ctx* ctx, const double* x, double* JtJ, double* Jtr, double* cost);
+/* per-corner reprojection error norm, f64[N] (tables.py:244-249 restricted to the packed corners)  */
+int  mcba_reprojection_error(mcba_ctx* ctx, double* err);
+
+/* -- the solve: replaces scipy.optimize.least_squares(...) at calibration.py:209-210 ------------ */
+int  mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* result,
+                mcba_log_row* log, int32_t log_capacity);
+
+/* -- measurement hooks (bench.py): launch one kernel family on the context stream -------------- */
+enum { MCBA_BENCH_LINEARIZE = 0, MCBA_BENCH_RESIDUAL = 1, MCBA_BENCH_COST = 2 };
+int  mcba_bench_launch(mcba_ctx* ctx, int which, int repeats);
+int  mcba_bench_info(mcba_ctx* ctx, int which, int64_t* corners, int64_t* bytes_per_launch, int32_t* launches_per_call);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,316 @@
+"""`Calibration` with the reference's public surface (multical/optimization/calibration.py:43-300)
+whose `bundle_adjust()` runs on a B200 through libmcba.so instead of
+`scipy.optimize.least_squares` over numpy + cv2 (calibration.py:199-212).
+
+Constructor signature, method names, argument meanings, logging and error behaviour follow the
+reference so that callers (`Workspace.calibrate`, workspace.py:228-247) can swap the class in.
+The objects passed in may be this package's mirrors (camera.py, pose_set.py, board.py) or the
+reference's own `Camera`, `PoseSet`, `StaticFrames`, `ParamList`, `Table`: only attributes that both
+expose are touched (duck typing)."""
+import os
+from functools import cached_property
+from numbers import Integral
+
+import numpy as np
+
+from . import rtvec
+from ._native import OPT_BITS, OPT_FIX_ASPECT
+from .board import stack_boards
+from .camera import engine_model_of
+from .engine import Engine, format_log, pack_corners
+from .log import info
+from .parameters import Parameters
+from .structs import Table, struct
+
+default_optimize = struct(cameras=False, boards=False, camera_poses=True, board_poses=True, motion=True)
+
+
+def select_threshold(quantile=0.75, factor=5.0):
+  """calibration.py:37-40"""
+  def f(reprojection_error):
+    return np.quantile(reprojection_error, quantile) * factor
+  return f
+
+
+_engines = {}
+
+
+def default_device():
+  return int(os.environ.get("MCBA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def get_engine(device=None):
+  """One C-ABI context per (process, GPU); the caller is single threaded like the reference."""
+  device = default_device() if device is None else device
+  if device not in _engines:
+    _engines[device] = Engine(device)
+  return _engines[device]
+
+
+def _mk_table(like, **arrays):
+  """Build a points/valid table of the same kind the caller handed us (reference Table or ours)."""
+  create = getattr(type(like), "create", None)
+  return create(**arrays) if create is not None else Table.create(**arrays)
+
+
+class Calibration(Parameters):
+  def __init__(self, cameras, boards, point_table, camera_poses, board_poses, motion,
+               inlier_mask=None, optimize=default_optimize):
+    self.cameras = cameras
+    self.boards = boards
+    self.point_table = point_table
+    self.camera_poses = camera_poses
+    self.board_poses = board_poses
+    self.motion = motion
+    self.optimize = optimize
+    self.inlier_mask = inlier_mask
+    assert len(self.cameras) == self.size.cameras
+    assert camera_poses.size == self.size.cameras
+    assert board_poses.size == self.size.boards
+
+  # ---- shapes and masks (calibration.py:64-81) --------------------------------------------------
+  @cached_property
+  def size(self):
+    cameras, rig_poses, boards, points = np.shape(self.point_table.valid)
+    return struct(cameras=cameras, rig_poses=rig_poses, boards=boards, points=points)
+
+  @cached_property
+  def pose_valid(self):
+    return (np.asarray(self.camera_poses.valid)[:, None, None] & np.asarray(self.motion.valid)[None, :, None]
+            & np.asarray(self.board_poses.valid)[None, None, :])
+
+  @cached_property
+  def valid(self):
+    return np.asarray(self.point_table.valid) & self.pose_valid[..., None]
+
+  @cached_property
+  def inliers(self):
+    return self.valid if self.inlier_mask is None else self.inlier_mask
+
+  @cached_property
+  def board_points(self):
+    pts, valid = stack_boards(self.boards)
+    return Table.create(points=pts, valid=valid)
+
+  @cached_property
+  def world_points(self):
+    """calibration.py:87-90 (host utility for viewers; the solver recomputes this on the GPU)."""
+    T = np.asarray(self.board_poses.poses)
+    bp = self.board_points
+    pts = np.einsum("bij,bpj->bpi", T[:, :3, :3], bp.points) + T[:, None, :3, 3]
+    return Table.create(points=pts, valid=np.asarray(self.board_poses.valid)[:, None] & bp.valid)
+
+  @cached_property
+  def pose_estimates(self):
+    return struct(camera=self.camera_poses.pose_table, board=self.board_poses.pose_table, times=self.motion.frame_poses)
+
+  def with_master(self, camera):
+    if isinstance(camera, str): camera = self.camera_poses.names.index(camera)
+    assert isinstance(camera, Integral)
+    return self.transform_views(self.camera_poses.poses[camera])
+
+  def transform_views(self, t):
+    """calibration.py:107-112: cameras by t^-1, frame poses by t (projection unchanged)."""
+    return self.copy(camera_poses=self.camera_poses.post_transform(np.linalg.inv(t)), motion=self.motion.pre_transform(t))
+
+  # ---- GPU problem ------------------------------------------------------------------------------
+  @cached_property
+  def engine_model(self):
+    models = {engine_model_of(c) for c in self.cameras}
+    assert len(models) == 1, f"all cameras must share one model, got {models}"
+    return models.pop()
+
+  def _optimize_bits(self):
+    if self.optimize["boards"] is True:
+      raise NotImplementedError("boards=True (board points as parameters) is not implemented on the GPU path yet")
+    bits = sum(bit for k, bit in OPT_BITS.items() if self.optimize[k] is True)
+    fix = {bool(getattr(c, "fix_aspect", False)) for c in self.cameras}
+    assert len(fix) == 1, "fix_aspect must agree across cameras"
+    return bits | (OPT_FIX_ASPECT if fix.pop() else 0)
+
+  def _state_arrays(self):
+    cam_rt = rtvec.from_matrix(np.asarray(self.camera_poses.poses))
+    board_rt = rtvec.from_matrix(np.asarray(self.board_poses.poses))
+    frame_rt = rtvec.from_matrix(np.asarray(self.motion.poses))
+    intr = np.stack([np.asarray(c.param_vec, np.float64) for c in self.cameras])
+    return cam_rt, board_rt, frame_rt, intr
+
+  def _upload(self, mask, points=None, device=None):
+    eng = get_engine(device)
+    pts = np.asarray(self.point_table.points) if points is None else points
+    idx, obs = pack_corners(mask, pts)
+    s = self.size
+    eng.upload(self.engine_model, self._optimize_bits(), (s.cameras, s.rig_poses, s.boards, s.points),
+               idx, obs, self.board_points.points)
+    eng.set_params(*self._state_arrays())
+    return eng
+
+  # ---- projection / errors (calibration.py:115-141, tables.py:239-249) ---------------------------
+  def _project(self, mask):
+    """Dense [C,F,B,P,2] projections of the points selected by `mask` (zeros elsewhere)."""
+    out = np.zeros((*mask.shape, 2))
+    if mask.any():
+      eng = self._upload(mask, points=np.zeros((*mask.shape, 2)))
+      out[mask] = eng.residuals().reshape(-1, 2)        # projected - 0
+    return out
+
+  @cached_property
+  def projected(self):
+    ok = self.pose_valid[..., None] & self.board_points.valid[None, None]
+    return _mk_table(self.point_table, points=self._project(ok), valid=ok)
+
+  @cached_property
+  def reprojected(self):
+    return self.projected          # static frames: the measured points do not change the projection
+
+  @cached_property
+  def _valid_errors(self):
+    """Per-corner pixel error over `valid`, in boolean-mask order (tables.py:244-249)."""
+    if not self.valid.any(): return np.zeros(0)
+    return self._upload(self.valid).reprojection_error()
+
+  @cached_property
+  def reprojection_error(self):
+    return self._valid_errors
+
+  @cached_property
+  def reprojection_inliers(self):
+    return self._valid_errors[self.inliers[self.valid]]
+
+  # ---- parameters (calibration.py:144-171) ------------------------------------------------------
+  @cached_property
+  def param_objects(self):
+    return struct(camera_poses=self.camera_poses, board_poses=self.board_poses, motion=self.motion,
+                  cameras=self.cameras, boards=self.boards)
+
+  @cached_property
+  def params(self):
+    return struct(**{k: p.param_vec for k, p in self.param_objects.items() if self.optimize[k] is True})
+
+  def with_params(self, params):
+    updated = {k: self.param_objects[k].with_param_vec(v) for k, v in params.items()}
+    return self.copy(**updated)
+
+  @cached_property
+  def sparsity_matrix(self):
+    """Jacobian sparsity as the reference builds it for scipy (calibration.py:173-196).  The GPU solver
+    uses analytic block Jacobians and never needs it; kept for API compatibility."""
+    from scipy.sparse import csr_matrix
+    idx = np.argwhere(self.inliers)
+    N = idx.shape[0]
+    rows2 = np.arange(2 * N).reshape(N, 2)
+    rr, cc, col0 = [], [], 0
+    def add(block_of_corner, nper, enabled):
+      nonlocal col0
+      on = enabled[block_of_corner]
+      base = col0 + block_of_corner[on] * nper
+      for j in range(nper):
+        for comp in range(2):
+          cc.append(base + j); rr.append(rows2[on][:, comp])
+      col0 += enabled.size * nper
+    if self.optimize["camera_poses"] is True: add(idx[:, 0], 6, np.asarray(self.camera_poses.valid))
+    if self.optimize["board_poses"] is True: add(idx[:, 2], 6, np.asarray(self.board_poses.valid))
+    if self.optimize["motion"] is True: add(idx[:, 1], 6, np.asarray(self.motion.valid))
+    if self.optimize["cameras"] is True:
+      add(idx[:, 0], self.cameras.param_vec.size // self.size.cameras, np.ones(self.size.cameras, bool))
+    if self.optimize["boards"] is True:
+      for board in self.boards:
+        add(idx[:, 3].clip(max=board.num_points - 1), 3, np.ones(board.num_points, bool))
+    if not cc: return csr_matrix((2 * N, col0), dtype=np.int16)
+    S = csr_matrix((np.ones(sum(c.size for c in cc), np.int16), (np.concatenate(rr), np.concatenate(cc))), shape=(2 * N, col0))
+    S.data[:] = 1
+    return S
+
+  # ---- the hot path -----------------------------------------------------------------------------
+  def bundle_adjust(self, tolerance=1e-4, f_scale=1.0, max_iterations=100, loss="linear", xtol=1e-8, gtol=1e-8):
+    """Non-linear least squares on point reprojection error (calibration.py:199-212), solved on the GPU
+    with scipy-TRF semantics: ftol=tolerance, max_nfev=max_iterations, x_scale='jac', robust `loss`."""
+    eng = self._upload(self.inliers)
+    res = eng.solve(ftol=tolerance, xtol=xtol, gtol=gtol, f_scale=f_scale, max_nfev=max_iterations, loss=loss)
+    for line in format_log(res.log): info(line)
+    info(res.message)
+    info(f"Function evaluations {res.nfev}, initial cost {res.initial_cost:.4e}, final cost {res.cost:.4e}, "
+         f"first-order optimality {res.optimality:.2e}.")
+    out = self.with_param_vec(eng.param_vec)
+    out.__dict__["last_solve"] = res
+    return out
+
+  def enable(self, **flags):
+    for k in flags.keys():
+      assert k in self.optimize, f"unknown option {k}, options are {list(self.optimize.keys())}"
+    return self.copy(optimize=self.optimize._extend(**flags))
+
+  def __getstate__(self):
+    attrs = ["cameras", "boards", "point_table", "camera_poses", "board_poses", "motion", "inlier_mask", "optimize"]
+    return {k: self.__dict__[k] for k in attrs}
+
+  def __setstate__(self, d): self.__dict__.update(d)
+
+  def copy(self, **k):
+    d = self.__getstate__(); d.update(k)
+    return Calibration(**d)
+
+  # ---- outliers (calibration.py:234-268) --------------------------------------------------------
+  def reject_outliers_quantile(self, quantile=0.95, factor=1.0):
+    threshold = np.quantile(self.reprojection_error, quantile)
+    return self.reject_outliers(threshold=threshold * factor)
+
+  def reject_outliers(self, threshold):
+    valid = self.valid
+    inliers = np.zeros_like(valid)
+    inliers[valid] = self._valid_errors < threshold
+    num_outliers = valid.sum() - inliers.sum()
+    inlier_percent = 100.0 * inliers.sum() / valid.sum()
+    info(f"Rejecting {num_outliers} outliers with error > {threshold:.2f} pixels, "
+         f"keeping {inliers.sum()} / {valid.sum()} inliers, ({inlier_percent:.2f}%)")
+    return self.copy(inlier_mask=inliers)
+
+  def adjust_outliers(self, num_adjustments=3, select_scale=None, select_outliers=None, **kwargs):
+    info(f"Beginning adjustments ({num_adjustments}) enabled: {self.optimize}, options: {kwargs}")
+    for i in range(num_adjustments):
+      self.report(f"Adjust_outliers {i}:")
+      f_scale = (None if select_scale is None else select_scale(self.reprojection_error)) or 1.0
+      if select_scale is not None:
+        info(f"Auto scaling for outliers influence at {f_scale:.2f} pixels")
+      if select_outliers is not None:
+        self = self.reject_outliers(select_outliers(self.reprojection_error))
+      self = self.bundle_adjust(f_scale=f_scale, **kwargs)
+    self.report("Adjust_outliers end:")
+    return self
+
+  def report(self, stage=""):
+    overall = error_stats(self.reprojection_error)
+    inliers = error_stats(self.reprojection_inliers)
+    if self.inlier_mask is not None:
+      info(f"{stage} reprojection RMS={inliers.rms:.3f} ({overall.rms:.3f}), "
+           f"n={inliers.n} ({overall.n}), quantiles={overall.quantiles}")
+    else:
+      info(f"{stage} reprojection RMS={overall.rms:.3f}, n={overall.n}, quantiles={overall.quantiles}")
+
+
+def error_stats(errors):
+  """calibration.py:303-310"""
+  errors = np.asarray(errors)
+  if len(errors) == 0: errors = np.zeros((1, 1), np.float32)
+  mse = np.square(errors).mean()
+  quantiles = np.array([np.quantile(errors, n) for n in [0, 0.25, 0.5, 0.75, 1]])
+  return struct(mse=mse, rms=np.sqrt(mse), quantiles=quantiles, n=errors.size)
+
+
+def from_scene(scene, guess=True, **kwargs):
+  """Calibration over a multical_b200.synthetic scene (plain numpy) using this package's mirror classes."""
+  from .board import Board
+  from .camera import Camera, CameraFisheye
+  from .parameters import ParamList
+  from .pose_set import PoseSet, StaticFrames, pose_table
+  src = scene["init"] if guess else scene["gt"]
+  fisheye = scene["model"] == "fisheye"
+  cams = [(CameraFisheye(scene["image_size"], src["K"][i], src["dist"][i]) if fisheye else
+           Camera(scene["image_size"], src["K"][i], src["dist"][i], model=scene["model"])) for i in range(scene["C"])]
+  names = [f"cam{i}" for i in range(scene["C"])]
+  bnames = [f"board{i}" for i in range(scene["B"])]
+  return Calibration(ParamList(cams, names), ParamList([Board(p) for p in scene["board_points"]], bnames),
+                     Table.create(points=scene["points"], valid=scene["valid"]),
+                     PoseSet(pose_table(src["cam_poses"], scene["cam_valid"]), names),
+                     PoseSet(pose_table(src["board_poses"], scene["board_valid"]), bnames),
+                     StaticFrames(pose_table(src["frame_poses"], scene["frame_valid"])), **kwargs)

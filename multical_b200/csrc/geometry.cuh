@@ -1,0 +1,191 @@
+// geometry.cuh — SE(3) pose chain and camera models, device side (fp64).
+//
+// Replaces, per corner, what the reference evaluates densely on the CPU:
+//   pose chain   x_cam = T_cam[c] T_frame[f] T_board[b] X   motion/static_frames.py:16-25, tables.py:284-304,400-405
+//   pinhole      cv2.projectPoints(rvec=0,tvec=0,K,dist)    camera.py:124-128   (5/8/12 coefficients, camera.py:43-48)
+//   fisheye      cv2.fisheye.projectPoints(...)             camera_fisheye.py:113-117
+// plus the analytic derivatives that scipy obtains by 2-point finite differences (calibration.py:209-210).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mcba {
+
+enum { MODEL_STANDARD = 0, MODEL_RATIONAL = 1, MODEL_THIN_PRISM = 2, MODEL_FISHEYE = 3 };
+
+__host__ __device__ constexpr int model_nd(int model) {
+  return model == MODEL_STANDARD ? 5 : model == MODEL_RATIONAL ? 8 : model == MODEL_THIN_PRISM ? 12 : 4;
+}
+// local Jacobian layout of one residual row: [omega(3) v(3) fx fy cx cy dist(nd)]  (skew has no effect:
+// cv2 ignores K[0,1]) -> D = 10 + nd
+__host__ __device__ constexpr int model_D(int model) { return 10 + model_nd(model); }
+
+// per-pose table entry built once per parameter vector: R, t and the SO(3) left Jacobian of the rotvec
+struct PoseT {
+  double R[9];
+  double t[3];
+  double JL[9];
+  double pad[3];
+};
+
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+      C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mat3_vec(const double* A, const double* x, double* y) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) y[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
+}
+
+// rotvec -> R (transform/rtvec.py:24-27, scipy Rotation.from_rotvec) and left Jacobian JL with
+//   R(r + dr) ~= exp([JL dr]x) R(r)
+__device__ inline void rodrigues(const double* r, double* R, double* JL) {
+  const double x = r[0], y = r[1], z = r[2];
+  const double th2 = x * x + y * y + z * z;
+  double A, B, Cc;            // sin(th)/th, (1-cos th)/th^2, (th - sin th)/th^3
+  if (th2 < 1e-6) {
+    const double th4 = th2 * th2;
+    A = 1.0 - th2 / 6.0 + th4 / 120.0;
+    B = 0.5 - th2 / 24.0 + th4 / 720.0;
+    Cc = 1.0 / 6.0 - th2 / 120.0 + th4 / 5040.0;
+  } else {
+    const double th = sqrt(th2);
+    double s, c;
+    sincos(th, &s, &c);
+    A = s / th;
+    B = (1.0 - c) / th2;
+    Cc = (th - s) / (th2 * th);
+  }
+  // K = [r]x ; K^2 = r r^T - th2 I
+  const double K[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+  const double K2[9] = {x * x - th2, x * y, x * z, x * y, y * y - th2, y * z, x * z, y * z, z * z - th2};
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
+    R[i] = I + A * K[i] + B * K2[i];
+    JL[i] = I + B * K[i] + Cc * K2[i];
+  }
+}
+
+// 6x6 map from a pose-parameter increment (dr, dt) to the camera-frame twist (omega, v) it induces on
+// x_cam.  With Rl, tl = rotation / translation of everything LEFT of the perturbed pose in the chain
+// (identity for the camera pose) and tcur = translation of the chain up to and including this pose:
+//   omega = Rl JL dr ,   v = [tcur]x Rl JL dr + Rl dt
+__device__ __forceinline__ void twist_map(const double* Rl, const double* JL, const double* tcur, double* A /*6x6 row-major*/) {
+  double RJ[9];
+  mat3_mul(Rl, JL, RJ);
+  const double tx = tcur[0], ty = tcur[1], tz = tcur[2];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const double a0 = RJ[j], a1 = RJ[3 + j], a2 = RJ[6 + j];
+    A[0 * 6 + j] = a0; A[1 * 6 + j] = a1; A[2 * 6 + j] = a2;
+    A[3 * 6 + j] = ty * a2 - tz * a1;       // (t x a)
+    A[4 * 6 + j] = tz * a0 - tx * a2;
+    A[5 * 6 + j] = tx * a1 - ty * a0;
+    A[0 * 6 + 3 + j] = 0; A[1 * 6 + 3 + j] = 0; A[2 * 6 + 3 + j] = 0;
+    A[3 * 6 + 3 + j] = Rl[j]; A[4 * 6 + 3 + j] = Rl[3 + j]; A[5 * 6 + 3 + j] = Rl[6 + j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Camera models.  k points at [fx fy cx cy skew dist...] (camera.py:144-155).  Outputs u,v; when JAC:
+//   Ju,Jv = d(u,v)/dX_cam (3 each);  ku,kv = d(u,v)/d[fx fy cx cy dist...] (4+nd each; fy,cy of ku and
+//   fx,cx of kv are structurally zero and not written)
+template <int MODEL, bool JAC>
+__device__ __forceinline__ void project(const double* X, const double* __restrict__ k, double& u, double& v,
+                                        double* Ju, double* Jv, double* ku, double* kv) {
+  constexpr int ND = model_nd(MODEL);
+  const double fx = k[0], fy = k[1], cx = k[2], cy = k[3];
+  const double* d = k + 5;
+  if constexpr (MODEL == MODEL_FISHEYE) {
+    const double iz = 1.0 / X[2];
+    const double a = X[0] * iz, b = X[1] * iz;
+    const double r2 = a * a + b * b;
+    const double r = sqrt(r2);
+    const double th = atan(r);
+    const double t2 = th * th, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+    const double thd = th * (1.0 + d[0] * t2 + d[1] * t4 + d[2] * t6 + d[3] * t8);
+    const bool big = r > 1e-8;
+    const double inv_r = big ? 1.0 / r : 1.0;
+    const double cd = big ? thd * inv_r : 1.0;
+    const double xd = a * cd, yd = b * cd;
+    u = fx * xd + cx;
+    v = fy * yd + cy;
+    if constexpr (JAC) {
+      const double dthd = 1.0 + 3.0 * d[0] * t2 + 5.0 * d[1] * t4 + 7.0 * d[2] * t6 + 9.0 * d[3] * t8;
+      const double dcd_r = big ? (dthd / (1.0 + r2) - cd) * inv_r * inv_r : 0.0;   // (d cd/dr)/r
+      const double xa = cd + a * a * dcd_r, xb = a * b * dcd_r, yb = cd + b * b * dcd_r;
+      Ju[0] = fx * xa * iz; Ju[1] = fx * xb * iz; Ju[2] = -fx * (xa * a + xb * b) * iz;
+      Jv[0] = fy * xb * iz; Jv[1] = fy * yb * iz; Jv[2] = -fy * (xb * a + yb * b) * iz;
+      ku[0] = xd; ku[2] = 1.0;
+      kv[1] = yd; kv[3] = 1.0;
+      const double air = big ? a * inv_r : 0.0, bir = big ? b * inv_r : 0.0;
+      const double t3 = th * t2;
+      ku[4] = fx * air * t3; ku[5] = fx * air * t3 * t2; ku[6] = fx * air * t3 * t4; ku[7] = fx * air * t3 * t6;
+      kv[4] = fy * bir * t3; kv[5] = fy * bir * t3 * t2; kv[6] = fy * bir * t3 * t4; kv[7] = fy * bir * t3 * t6;
+    }
+  } else {
+    const double Z = X[2];
+    const double iz = (Z != 0.0) ? 1.0 / Z : 1.0;      // cv2.projectPoints: z ? 1/z : 1
+    const double x = X[0] * iz, y = X[1] * iz;
+    const double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    const double k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+    const double cdist = 1.0 + k1 * r2 + k2 * r4 + k3 * r6;
+    double icd2 = 1.0;
+    if constexpr (ND >= 8) icd2 = 1.0 / (1.0 + d[5] * r2 + d[6] * r4 + d[7] * r6);
+    const double a1 = 2.0 * x * y, a2 = r2 + 2.0 * x * x, a3 = r2 + 2.0 * y * y;
+    const double rad = cdist * icd2;
+    double xd = x * rad + p1 * a1 + p2 * a2;
+    double yd = y * rad + p1 * a3 + p2 * a1;
+    if constexpr (ND >= 12) {
+      xd += d[8] * r2 + d[9] * r4;
+      yd += d[10] * r2 + d[11] * r4;
+    }
+    u = fx * xd + cx;
+    v = fy * yd + cy;
+    if constexpr (JAC) {
+      const double dcd = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
+      double drad = dcd;
+      if constexpr (ND >= 8) drad = dcd * icd2 - cdist * icd2 * icd2 * (d[5] + 2.0 * d[6] * r2 + 3.0 * d[7] * r4);
+      double tpx = 0.0, tpy = 0.0;
+      if constexpr (ND >= 12) { tpx = d[8] + 2.0 * d[9] * r2; tpy = d[10] + 2.0 * d[11] * r2; }
+      const double cross = a1 * drad + 2.0 * p1 * x + 2.0 * p2 * y;
+      const double xx = rad + 2.0 * x * x * drad + 2.0 * p1 * y + 6.0 * p2 * x + 2.0 * x * tpx;
+      const double xy = cross + 2.0 * y * tpx;
+      const double yx = cross + 2.0 * x * tpy;
+      const double yy = rad + 2.0 * y * y * drad + 6.0 * p1 * y + 2.0 * p2 * x + 2.0 * y * tpy;
+      Ju[0] = fx * xx * iz; Ju[1] = fx * xy * iz; Ju[2] = -fx * (xx * x + xy * y) * iz;
+      Jv[0] = fy * yx * iz; Jv[1] = fy * yy * iz; Jv[2] = -fy * (yx * x + yy * y) * iz;
+      ku[0] = xd; ku[2] = 1.0;
+      kv[1] = yd; kv[3] = 1.0;
+      const double fxx = fx * x * icd2, fyy = fy * y * icd2;
+      ku[4] = fxx * r2; ku[5] = fxx * r4; ku[6] = fx * a1; ku[7] = fx * a2; ku[8] = fxx * r6;
+      kv[4] = fyy * r2; kv[5] = fyy * r4; kv[6] = fy * a3; kv[7] = fy * a1; kv[8] = fyy * r6;
+      if constexpr (ND >= 8) {
+        const double gx = -fxx * rad, gy = -fyy * rad;     // -f x cdist icd2^2
+        ku[9] = gx * r2; ku[10] = gx * r4; ku[11] = gx * r6;
+        kv[9] = gy * r2; kv[10] = gy * r4; kv[11] = gy * r6;
+      }
+      if constexpr (ND >= 12) {
+        ku[12] = fx * r2; ku[13] = fx * r4; ku[14] = 0.0; ku[15] = 0.0;
+        kv[12] = 0.0; kv[13] = 0.0; kv[14] = fy * r2; kv[15] = fy * r4;
+      }
+    }
+  }
+}
+
+// scipy robust losses on z = (f/f_scale)^2 (least_squares.py:183-219); returns rho0, rho1, rho2
+__device__ __forceinline__ void loss_rho(int loss, double z, double& r0, double& r1, double& r2) {
+  switch (loss) {
+    case 1: { const double t = 1.0 + z; const double s = sqrt(t); r0 = 2.0 * (s - 1.0); r1 = 1.0 / s; r2 = -0.5 / (t * s); break; }
+    case 2: if (z <= 1.0) { r0 = z; r1 = 1.0; r2 = 0.0; } else { const double s = sqrt(z); r0 = 2.0 * s - 1.0; r1 = 1.0 / s; r2 = -0.5 / (z * s); } break;
+    case 3: r0 = log1p(z); r1 = 1.0 / (1.0 + z); r2 = -1.0 / ((1.0 + z) * (1.0 + z)); break;
+    case 4: { const double t = 1.0 + z * z; r0 = atan(z); r1 = 1.0 / t; r2 = -2.0 * z / (t * t); break; }
+    default: r0 = z; r1 = 1.0; r2 = 0.0;
+  }
+}
+
+}  // namespace mcba

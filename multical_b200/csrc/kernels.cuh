@@ -1,0 +1,509 @@
+// kernels.cuh — sm_100a kernels of the bundle-adjustment hot path.
+//
+// Data layout in HBM (built once by mcba_upload, solver.cu): corners are stored FRAME-MAJOR, sorted by
+// (frame, camera, board, point), so that every "view" (frame,camera,board) is one contiguous run and all
+// views of one frame are contiguous (frames are also the multi-GPU sharding unit):
+//   obs   double2[N]   observed (u,v)                       16 B / corner   (point_table.points, calibration.py:206)
+//   pid   uint16[N]    point index inside the board          2 B / corner
+//   orig  uint32[N]    canonical packed index (np.argwhere(inliers) row) -- only read by the API hooks
+//   view_start int[V+1], view_cam/frame/board int[V]       16 B / view
+// Algorithmic bytes of one linearisation pass = 18 B / corner (+16 B / view).
+//
+// Kernel map (what each replaces in the reference is cited at the kernel):
+//   k_prepare          rtvec -> R,t,JL tables                     pose_set.py:55-57, rtvec.py:24-27
+//   k_views<MODE>      residual / cost / per-view moments          calibration.py:204-206 + scipy FD Jacobian
+//   k_expand_frames    per-frame Hessian blocks H_ff, W_f, g_f     (J^T J restricted to one motion pose; pose_set.py:59-60)
+//   k_expand_shared    shared blocks H_ss, g_s                     (camera pose / board pose / intrinsics columns)
+//   k_scale, k_quad, k_schur_*, k_chol_solve, k_backsub, k_step    scipy _lsq/trf.py trf_no_bounds (LSMR replaced by an
+//                                                                   exact damped solve through the Schur complement)
+#pragma once
+#include <stdint.h>
+#include "geometry.cuh"
+
+namespace mcba {
+
+// ------------------------------------------------------------------------------------------------
+struct DeviceProblem {
+  int C, F, B, P, model, nd, kint, D, T;   // T = D(D+1)/2 + D + 1 moment entries per view
+  int64_t N;
+  int V;
+  const double2* obs;
+  const uint16_t* pid;
+  const uint32_t* orig;
+  const int* view_start;
+  const int* view_cam;
+  const int* view_frame;
+  const int* view_board;
+  const int* frame_view_start;   // [F+1]
+  const int* cam_view_start;     // [C+1]
+  const int* cam_view_list;      // [V] view ids grouped by camera
+  const double* board_pts;       // [B][P][3]
+  // parameter state (full, including fixed blocks)
+  double* cam_rt;    // [C][6]
+  double* board_rt;  // [B][6]
+  double* frame_rt;  // [F][6]
+  double* intr;      // [C][kint]
+  // derived tables
+  PoseT* cam_T;
+  PoseT* frame_T;
+  PoseT* board_T;
+  // solver variable layout: x = [shared (n_s) | frames (6F if motion free)]
+  int n, n_s, n_f;
+  int off_cp, off_bp, off_in;    // offsets inside shared, -1 when the block is fixed
+  int motion_on, fix_aspect;
+};
+
+__host__ __device__ constexpr int tri_index(int D, int i, int j) { return i * D - (i * (i - 1)) / 2 + (j - i); }
+__device__ __forceinline__ double msym(const double* M, int D, int i, int j) {
+  return i <= j ? M[tri_index(D, i, j)] : M[tri_index(D, j, i)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_prepare: one thread per pose.  rtvec -> (R, t, JL).   pose_set.py:55-57 / transform/rtvec.py:24-27
+__global__ void k_prepare(DeviceProblem p, const double* cam_rt, const double* board_rt, const double* frame_rt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* src; PoseT* dst;
+  if (i < p.C) { src = cam_rt + 6 * i; dst = p.cam_T + i; }
+  else if (i < p.C + p.B) { src = board_rt + 6 * (i - p.C); dst = p.board_T + (i - p.C); }
+  else if (i < p.C + p.B + p.F) { src = frame_rt + 6 * (i - p.C - p.B); dst = p.frame_T + (i - p.C - p.B); }
+  else return;
+  PoseT t;
+  rodrigues(src, t.R, t.JL);
+  t.t[0] = src[3]; t.t[1] = src[4]; t.t[2] = src[5];
+  t.pad[0] = t.pad[1] = t.pad[2] = 0;
+  *dst = t;
+}
+
+// compose T_cfb = T_c T_f T_b for one view (every lane of the warp computes the same small product)
+struct ViewPose { double R[9]; double t[3]; };
+__device__ __forceinline__ void compose_view(const PoseT& c, const PoseT& f, const PoseT& b, ViewPose& o) {
+  double Rcf[9], tcf[3];
+  mat3_mul(c.R, f.R, Rcf);
+  mat3_vec(c.R, f.t, tcf);
+  tcf[0] += c.t[0]; tcf[1] += c.t[1]; tcf[2] += c.t[2];
+  mat3_mul(Rcf, b.R, o.R);
+  mat3_vec(Rcf, b.t, o.t);
+  o.t[0] += tcf[0]; o.t[1] += tcf[1]; o.t[2] += tcf[2];
+}
+
+struct ViewKernelArgs {
+  int loss;
+  double f_scale;
+  double* moments;     // MODE_MOMENTS: [V][T]
+  double* view_cost;   // MODE_COST   : [V]
+  double* resid;       // MODE_RESID  : [2N] canonical order
+  double* err;         // MODE_ERROR  : [N]  canonical order
+};
+enum { MODE_COST = 0, MODE_MOMENTS = 1, MODE_RESID = 2, MODE_ERROR = 3 };
+
+constexpr int VIEW_WARPS = 4;          // warps per CTA for k_views
+constexpr double SCIPY_EPS = 2.220446049250313e-16;
+
+// k_views: one warp per view, lanes stride over the view's corners (one thread per corner per step).
+//   MODE_COST    -> 0.5*sum rho(f)                         (trial-point evaluation, trf.py cost_new)
+//   MODE_RESID   -> residual vector in canonical order     (calibration.py:204-206)
+//   MODE_ERROR   -> per-corner ||proj - obs||              (tables.py:244-249)
+//   MODE_MOMENTS -> per-view sum of G^T G, G^T r, cost with G = d r / d[camera-frame twist | intrinsics]
+//                   (replaces scipy's 2-point FD Jacobian; entries [PART*CH, (PART+1)*CH) of the T moments)
+template <int MODEL, int MODE, int PART, int NPARTS>
+__global__ void __launch_bounds__(VIEW_WARPS * 32)
+k_views(DeviceProblem p, ViewKernelArgs a) {
+  constexpr int ND = model_nd(MODEL);
+  constexpr int D = 10 + ND;
+  constexpr int E = D * (D + 1) / 2;
+  constexpr int T = E + D + 1;
+  constexpr int CH = (T + NPARTS - 1) / NPARTS;
+  constexpr int LO = PART * CH;
+  constexpr int HI = (LO + CH < T) ? LO + CH : T;
+  constexpr int NACC = (MODE == MODE_MOMENTS) ? (HI - LO) : 1;
+  constexpr int KINT = 5 + ND;
+
+  __shared__ double red[(MODE == MODE_MOMENTS) ? VIEW_WARPS * 32 * 33 : 1];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * VIEW_WARPS + warp;
+  const int nw = gridDim.x * VIEW_WARPS;
+
+  for (int v = gw; v < p.V; v += nw) {
+    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
+    const int beg = p.view_start[v], end = p.view_start[v + 1];
+    ViewPose vp;
+    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
+    double k[KINT];
+#pragma unroll
+    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
+    const double* bp = p.board_pts + (size_t)b * p.P * 3;
+
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+
+    for (int idx = beg + lane; idx < end; idx += 32) {
+      const double2 ob = p.obs[idx];
+      const int pi = p.pid[idx];
+      const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
+      double Xc[3];
+      mat3_vec(vp.R, X, Xc);
+      Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+      double u, w_;
+      double Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
+      project<MODEL, MODE == MODE_MOMENTS>(Xc, k, u, w_, Ju, Jv, ku, kv);
+      double ru = u - ob.x, rv = w_ - ob.y;           // projected - observed (calibration.py:206)
+
+      if constexpr (MODE == MODE_RESID) {
+        const uint32_t o = p.orig[idx];
+        a.resid[2 * (size_t)o] = ru;
+        a.resid[2 * (size_t)o + 1] = rv;
+      } else if constexpr (MODE == MODE_ERROR) {
+        a.err[p.orig[idx]] = sqrt(ru * ru + rv * rv);
+      } else {
+        // robust loss per scalar residual (least_squares.py construct_loss_function, common.py:720-731)
+        double cost, wu = 1.0, wv = 1.0;
+        if (a.loss == 0) {
+          cost = 0.5 * (ru * ru + rv * rv);
+        } else {
+          const double is = 1.0 / a.f_scale, fs2 = a.f_scale * a.f_scale;
+          double zu = ru * is, zv = rv * is;
+          zu *= zu; zv *= zv;
+          double r0u, r1u, r2u, r0v, r1v, r2v;
+          loss_rho(a.loss, zu, r0u, r1u, r2u);
+          loss_rho(a.loss, zv, r0v, r1v, r2v);
+          cost = 0.5 * fs2 * (r0u + r0v);
+          if constexpr (MODE == MODE_MOMENTS) {
+            // rho[2] /= f_scale^2 ; J_scale = rho1 + 2 rho2 f^2 = rho1 + 2 rho2' z
+            double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
+            ju = ju < SCIPY_EPS ? SCIPY_EPS : ju;
+            jv = jv < SCIPY_EPS ? SCIPY_EPS : jv;
+            wu = sqrt(ju); wv = sqrt(jv);
+            ru *= r1u / wu; rv *= r1v / wv;
+          }
+        }
+        if constexpr (MODE == MODE_COST) {
+          acc[0] += cost;
+        } else {
+          // local Jacobian rows: [omega(3) v(3) fx fy cx cy dist(ND)]
+          double gu[D], gv[D];
+          gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
+          gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
+#pragma unroll
+          for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
+          gu[6] = ku[0] * wu; gu[7] = 0.0; gu[8] = wu; gu[9] = 0.0;
+          gv[6] = 0.0; gv[7] = kv[1] * wv; gv[8] = 0.0; gv[9] = wv;
+#pragma unroll
+          for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
+          // structural zeros: fx(6),cx(8) only in the u row; fy(7),cy(9) only in the v row
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+#pragma unroll
+            for (int j = i; j < D; j++) {
+              const int e = tri_index(D, i, j);
+              if (e >= LO && e < HI) {
+                const bool iu = !(i == 7 || i == 9), iv = !(i == 6 || i == 8);
+                const bool ju_ = !(j == 7 || j == 9), jv_ = !(j == 6 || j == 8);
+                double s = acc[e - LO];
+                if (iu && ju_) s = fma(gu[i], gu[j], s);
+                if (iv && jv_) s = fma(gv[i], gv[j], s);
+                acc[e - LO] = s;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            const int e = E + i;
+            if (e >= LO && e < HI) {
+              double s = acc[e - LO];
+              if (!(i == 7 || i == 9)) s = fma(gu[i], ru, s);
+              if (!(i == 6 || i == 8)) s = fma(gv[i], rv, s);
+              acc[e - LO] = s;
+            }
+          }
+          if (T - 1 >= LO && T - 1 < HI) acc[T - 1 - LO] += cost;
+        }
+      }
+    }
+
+    if constexpr (MODE == MODE_COST) {
+      double s = acc[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) a.view_cost[v] = s;
+    } else if constexpr (MODE == MODE_MOMENTS) {
+      // transposed warp reduction through shared memory, 32 accumulators per round:
+      // lane l writes its value of accumulator q to [q*33 + l]; then lane q sums row q.
+      double* sm = red + warp * 32 * 33;
+      double* out = a.moments + (size_t)v * T + LO;
+#pragma unroll
+      for (int r0 = 0; r0 < NACC; r0 += 32) {
+#pragma unroll
+        for (int q = 0; q < 32; q++)
+          if (r0 + q < NACC) sm[q * 33 + lane] = acc[r0 + q];
+        __syncwarp();
+        if (r0 + lane < NACC) {
+          double s = 0.0;
+#pragma unroll 8
+          for (int j = 0; j < 32; j++) s += sm[lane * 33 + j];
+          out[r0 + lane] = s;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block maps shared by the two expand kernels.
+struct SolverBuffers {
+  double* moments;   // [V][T]
+  double* Hss;       // [n_s][n_s] full symmetric (local contribution of this rank)
+  double* g;         // [n] gradient J^T f  (shared part local until all-reduced)
+  double* Hff;       // [F][36]
+  double* W;         // [F][n_s][6]   H[shared, frame f]
+  double* cost_part; // per-CTA partial costs of k_expand_shared
+};
+
+__device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int local /*0..3+nd*/) {
+  // local [fx fy cx cy dist...] -> index in [fx fy cx cy skew dist...]; fix_aspect folds fy onto fx (camera.py:159-160)
+  if (local == 1 && p.fix_aspect) return 0;
+  return local < 4 ? local : local + 1;
+}
+
+// k_expand_frames: one CTA per frame.  Turns the per-view moments of the frame's views into
+//   H_ff (6x6), g_f (6) and the coupling W_f (n_s x 6) with every shared block the frame touches.
+constexpr int EXP_THREADS = 128;
+__global__ void __launch_bounds__(EXP_THREADS)
+k_expand_frames(DeviceProblem p, SolverBuffers s) {
+  extern __shared__ double sh[];
+  const int D = p.D, T = p.T, n_s = p.n_s;
+  double* Wf = sh;                     // n_s*6
+  double* Ms = Wf + (size_t)n_s * 6;   // T
+  double* Tm = Ms + T;                 // D*6
+  double* Ac = Tm + D * 6;             // 36
+  double* Af = Ac + 36;
+  double* Ab = Af + 36;
+  double* Hf = Ab + 36;                // 36
+  double* gf = Hf + 36;                // 6
+  const int f = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < n_s * 6; i += EXP_THREADS) Wf[i] = 0.0;
+  if (tid < 36) Hf[tid] = 0.0;
+  if (tid < 6) gf[tid] = 0.0;
+  __syncthreads();
+  const int E = D * (D + 1) / 2;
+  const int v0 = p.frame_view_start[f], v1 = p.frame_view_start[f + 1];
+  for (int v = v0; v < v1; v++) {
+    const int c = p.view_cam[v], b = p.view_board[v];
+    for (int i = tid; i < T; i += EXP_THREADS) Ms[i] = s.moments[(size_t)v * T + i];
+    if (tid < 3) {
+      const PoseT& pc = p.cam_T[c]; const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
+      double Rcf[9], tcf[3];
+      mat3_mul(pc.R, pf.R, Rcf);
+      mat3_vec(pc.R, pf.t, tcf);
+      tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
+      if (tid == 0) {
+        const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        twist_map(I3, pc.JL, pc.t, Ac);
+      } else if (tid == 1) {
+        twist_map(pc.R, pf.JL, tcf, Af);
+      } else {
+        double tb[3];
+        mat3_vec(Rcf, pb.t, tb);
+        tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
+        twist_map(Rcf, pb.JL, tb, Ab);
+      }
+    }
+    __syncthreads();
+    // Tm = M[:, xi] * Af   (D x 6)
+    for (int o = tid; o < D * 6; o += EXP_THREADS) {
+      const int i = o / 6, j = o % 6;
+      double acc = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Af[kk * 6 + j];
+      Tm[o] = acc;
+    }
+    __syncthreads();
+    // outputs: Hff 36 | gf 6 | W[cp] 36 | W[bp] 36 | W[intr] (4+nd)*6
+    const int nin = 4 + p.nd;
+    const int total = 36 + 6 + 36 + 36 + nin * 6;
+    for (int o = tid; o < total; o += EXP_THREADS) {
+      if (o < 36) {
+        const int i = o / 6, j = o % 6; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Tm[kk * 6 + j];
+        Hf[o] += acc;
+      } else if (o < 42) {
+        const int i = o - 36; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Ms[E + kk];
+        gf[i] += acc;
+      } else if (o < 78) {
+        if (p.off_cp >= 0) {
+          const int i = (o - 42) / 6, j = (o - 42) % 6; double acc = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * Tm[kk * 6 + j];
+          Wf[(p.off_cp + 6 * c + i) * 6 + j] += acc;
+        }
+      } else if (o < 114) {
+        if (p.off_bp >= 0) {
+          const int i = (o - 78) / 6, j = (o - 78) % 6; double acc = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Tm[kk * 6 + j];
+          Wf[(p.off_bp + 6 * b + i) * 6 + j] += acc;
+        }
+      } else if (p.off_in >= 0) {
+        const int i = (o - 114) / 6, j = (o - 114) % 6;
+        if (!(p.fix_aspect && i == 1)) {
+          double val = Tm[(6 + i) * 6 + j];
+          if (p.fix_aspect && i == 0) val += Tm[(6 + 1) * 6 + j];
+          Wf[(p.off_in + p.kint * c + intr_param_index(p, i)) * 6 + j] += val;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n_s * 6; i += EXP_THREADS) s.W[(size_t)f * n_s * 6 + i] = Wf[i];
+  if (tid < 36) s.Hff[(size_t)f * 36 + tid] = Hf[tid];
+  if (tid < 6) s.g[n_s + 6 * f + tid] = gf[tid];
+}
+
+// k_expand_shared: one CTA per (camera, chunk of that camera's views).  Accumulates the camera's own
+// (pose+intrinsics) block as a plain sum of view moments (its twist map is view independent) and the
+// camera-board / board-board blocks per view, then adds them into H_ss / g_s with fp64 atomics.
+__global__ void __launch_bounds__(EXP_THREADS)
+k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
+  extern __shared__ double sh[];
+  const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
+  const int E = D * (D + 1) / 2;
+  double* Msum = sh;                 // T
+  double* Ms = Msum + T;             // T
+  double* Um = Ms + T;               // D*6 (per view)
+  double* Ub = Um + D * 6;           // B * D*6
+  double* Hbb = Ub + (size_t)B * D * 6;  // B*36
+  double* gb = Hbb + B * 36;         // B*6
+  double* Ab = gb + B * 6;           // 36
+  double* Ac = Ab + 36;              // 36
+  const int c = blockIdx.x / chunks, chunk = blockIdx.x % chunks, tid = threadIdx.x;
+  const int nsh = 2 * T + D * 6 + B * D * 6 + B * 36 + B * 6;
+  for (int i = tid; i < nsh; i += EXP_THREADS) sh[i] = 0.0;
+  __syncthreads();
+  const int l0 = p.cam_view_start[c], l1 = p.cam_view_start[c + 1];
+  const int per = (l1 - l0 + chunks - 1) / chunks;
+  const int a0 = l0 + chunk * per, a1 = min(l1, a0 + per);
+  const PoseT& pc = p.cam_T[c];
+  for (int li = a0; li < a1; li++) {
+    const int v = p.cam_view_list[li];
+    const int f = p.view_frame[v], b = p.view_board[v];
+    for (int i = tid; i < T; i += EXP_THREADS) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; Msum[i] += m; }
+    if (tid == 0 && p.off_bp >= 0) {
+      const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
+      double Rcf[9], tcf[3], tb[3];
+      mat3_mul(pc.R, pf.R, Rcf);
+      mat3_vec(pc.R, pf.t, tcf);
+      tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
+      mat3_vec(Rcf, pb.t, tb);
+      tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
+      twist_map(Rcf, pb.JL, tb, Ab);
+    }
+    __syncthreads();
+    if (p.off_bp >= 0) {
+      for (int o = tid; o < D * 6; o += EXP_THREADS) {
+        const int i = o / 6, j = o % 6; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Ab[kk * 6 + j];
+        Um[o] = acc;
+        Ub[(size_t)b * D * 6 + o] += acc;
+      }
+      __syncthreads();
+      if (tid < 36) {
+        const int i = tid / 6, j = tid % 6; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Um[kk * 6 + j];
+        Hbb[b * 36 + tid] += acc;
+      } else if (tid < 42) {
+        const int i = tid - 36; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Ms[E + kk];
+        gb[b * 6 + i] += acc;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- flush
+  if (tid == 0) {
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    twist_map(I3, pc.JL, pc.t, Ac);
+    s.cost_part[blockIdx.x] = Msum[T - 1];
+  }
+  __syncthreads();
+  // Um = Msum[:, xi] * Ac   (D x 6)
+  for (int o = tid; o < D * 6; o += EXP_THREADS) {
+    const int i = o / 6, j = o % 6; double acc = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 6; kk++) acc += msym(Msum, D, i, kk) * Ac[kk * 6 + j];
+    Um[o] = acc;
+  }
+  __syncthreads();
+  const int nin = 4 + p.nd;
+  const int cp = p.off_cp >= 0 ? p.off_cp + 6 * c : -1;
+  const int in0 = p.off_in >= 0 ? p.off_in + p.kint * c : -1;
+  auto addH = [&](int i, int j, double val) {
+    atomicAdd(&s.Hss[(size_t)i * n_s + j], val);
+    if (i != j) atomicAdd(&s.Hss[(size_t)j * n_s + i], val);
+  };
+  // camera pose x camera pose (upper triangle) and gradient
+  if (cp >= 0) {
+    for (int o = tid; o < 36; o += EXP_THREADS) {
+      const int i = o / 6, j = o % 6;
+      if (j < i) continue;
+      double acc = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * Um[kk * 6 + j];
+      addH(cp + i, cp + j, acc);
+    }
+    if (tid < 6) {
+      double acc = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + tid] * Msum[E + kk];
+      atomicAdd(&s.g[cp + tid], acc);
+    }
+  }
+  if (in0 >= 0) {
+    // intrinsics x camera pose: Um rows 6..D ; intrinsics x intrinsics: Msum ; gradient
+    for (int o = tid; o < nin * 6; o += EXP_THREADS) {
+      if (cp < 0) break;
+      const int i = o / 6, j = o % 6;
+      atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + cp + j], Um[(6 + i) * 6 + j]);
+      atomicAdd(&s.Hss[(size_t)(cp + j) * n_s + in0 + intr_param_index(p, i)], Um[(6 + i) * 6 + j]);
+    }
+    for (int o = tid; o < nin * nin; o += EXP_THREADS) {
+      const int i = o / nin, j = o % nin;
+      atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + in0 + intr_param_index(p, j)], msym(Msum, D, 6 + i, 6 + j));
+    }
+    for (int i = tid; i < nin; i += EXP_THREADS) atomicAdd(&s.g[in0 + intr_param_index(p, i)], Msum[E + 6 + i]);
+  }
+  if (p.off_bp >= 0) {
+    for (int b = 0; b < B; b++) {
+      const int bp = p.off_bp + 6 * b;
+      const double* U = Ub + (size_t)b * D * 6;
+      if (cp >= 0)
+        for (int o = tid; o < 36; o += EXP_THREADS) {   // camera pose x board pose = Ac^T U_xi
+          const int i = o / 6, j = o % 6; double acc = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * U[kk * 6 + j];
+          if (acc != 0.0) { atomicAdd(&s.Hss[(size_t)(cp + i) * n_s + bp + j], acc); atomicAdd(&s.Hss[(size_t)(bp + j) * n_s + cp + i], acc); }
+        }
+      if (in0 >= 0)
+        for (int o = tid; o < nin * 6; o += EXP_THREADS) {  // intrinsics x board pose = U_k
+          const int i = o / 6, j = o % 6; const double val = U[(6 + i) * 6 + j];
+          if (val != 0.0) { atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + bp + j], val);
+                            atomicAdd(&s.Hss[(size_t)(bp + j) * n_s + in0 + intr_param_index(p, i)], val); }
+        }
+      for (int o = tid; o < 36; o += EXP_THREADS) {
+        const double val = Hbb[b * 36 + o];
+        if (val != 0.0) atomicAdd(&s.Hss[(size_t)(bp + o / 6) * n_s + bp + o % 6], val);
+      }
+      if (tid < 6 && gb[b * 6 + tid] != 0.0) atomicAdd(&s.g[bp + tid], gb[b * 6 + tid]);
+    }
+  }
+}
+
+}  // namespace mcba

@@ -1,0 +1,744 @@
+// solver.cu — host side of libmcba.so: context, problem packing/upload, the trust-region driver and the
+// extern "C" entry points declared in include/mcba.h.  No CPU fallback: everything numeric runs in the
+// kernels of kernels.cuh / solver_kernels.cuh.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcba.h"
+#include "solver_kernels.cuh"
+
+using namespace mcba;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------- NCCL through dlopen (torch's copy if loaded)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl is missing symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    n = count ? count : 1;
+    return cudaMalloc(&p, n * sizeof(T));
+  }
+};
+
+}  // namespace
+
+struct mcba_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  int launches = 0;
+  int num_sms = 148;
+
+  bool uploaded = false;
+  DeviceProblem P{};
+  // problem arrays
+  DevBuf<double2> obs; DevBuf<uint16_t> pid; DevBuf<uint32_t> orig;
+  DevBuf<int> view_start, view_cam, view_frame, view_board, frame_view_start, cam_view_start, cam_view_list;
+  DevBuf<double> board_pts, cam_rt, board_rt, frame_rt, intr;
+  DevBuf<PoseT> cam_T, frame_T, board_T;
+  // trial parameter state
+  DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2;
+  // solver buffers
+  DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
+  DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part;
+  DevBuf<SolverState> state;
+  int shared_chunks = 1;
+  std::vector<int> perm;   // internal index -> canonical param_vec index
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return MCBA_ERR_CUDA;                                                                        \
+    }                                                                                              \
+  } while (0)
+#define CKL()                                                                                      \
+  do {                                                                                             \
+    ctx->launches++;                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                           \
+    if (e_ != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e_); return MCBA_ERR_CUDA; } \
+  } while (0)
+#define REQUIRE(cond, code, msg)                                                                   \
+  do { if (!(cond)) { ctx->err = msg; return code; } } while (0)
+
+namespace {
+
+int allreduce(mcba_ctx* ctx, double* buf, size_t count, int op) {
+  if (ctx->world == 1) return MCBA_OK;
+  int r = g_nccl.AllReduce(buf, buf, count, NCCL_FLOAT64, op, ctx->comm, ctx->stream);
+  if (r != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return MCBA_ERR_NCCL; }
+  return MCBA_OK;
+}
+#define AR(buf, count, op) do { int r_ = allreduce(ctx, buf, count, op); if (r_) return r_; } while (0)
+
+int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : 2; }
+
+// parameters of block-structured vector x (internal order) <-> full parameter state
+__global__ void k_scatter_params(DeviceProblem p, const double* x, double* cam_rt, double* board_rt, double* frame_rt, double* intr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const double v = x[i];
+  if (i >= p.n_s) { frame_rt[i - p.n_s] = v; return; }
+  if (p.off_cp >= 0 && i >= p.off_cp && i < p.off_cp + 6 * p.C) { cam_rt[i - p.off_cp] = v; return; }
+  if (p.off_bp >= 0 && i >= p.off_bp && i < p.off_bp + 6 * p.B) { board_rt[i - p.off_bp] = v; return; }
+  if (p.off_in >= 0 && i >= p.off_in) { intr[i - p.off_in] = v; }
+}
+__global__ void k_gather_params(DeviceProblem p, double* x, const double* cam_rt, const double* board_rt, const double* frame_rt, const double* intr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  double v = 0.0;
+  if (i >= p.n_s) v = frame_rt[i - p.n_s];
+  else if (p.off_cp >= 0 && i >= p.off_cp && i < p.off_cp + 6 * p.C) v = cam_rt[i - p.off_cp];
+  else if (p.off_bp >= 0 && i >= p.off_bp && i < p.off_bp + 6 * p.B) v = board_rt[i - p.off_bp];
+  else if (p.off_in >= 0 && i >= p.off_in) v = intr[i - p.off_in];
+  x[i] = v;
+}
+// copies the fixed blocks so that a trial state is complete; with fix_aspect fy follows fx (camera.py:159-160)
+__global__ void k_fix_aspect(DeviceProblem p, double* intr) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < p.C && p.fix_aspect) intr[c * p.kint + 1] = intr[c * p.kint];
+}
+
+template <int MODE>
+int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a) {
+  const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
+  const int th = VIEW_WARPS * 32;
+  cudaStream_t s = ctx->stream;
+#define LV(MODEL, PART, NP) k_views<MODEL, MODE, PART, NP><<<blocks, th, 0, s>>>(P, a); CKL();
+  if constexpr (MODE != MODE_MOMENTS) {
+    switch (P.model) {
+      case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 1) break;
+      case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 1) break;
+      case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM, 0, 1) break;
+      default: LV(MODEL_FISHEYE, 0, 1) break;
+    }
+  } else {
+    switch (P.model) {
+      case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 2) LV(MODEL_STANDARD, 1, 2) break;
+      case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 3) LV(MODEL_RATIONAL, 1, 3) LV(MODEL_RATIONAL, 2, 3) break;
+      case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM, 0, 4) LV(MODEL_THIN_PRISM, 1, 4) LV(MODEL_THIN_PRISM, 2, 4) LV(MODEL_THIN_PRISM, 3, 4) break;
+      default: LV(MODEL_FISHEYE, 0, 2) LV(MODEL_FISHEYE, 1, 2) break;
+    }
+  }
+#undef LV
+  return MCBA_OK;
+}
+
+// DeviceProblem view whose parameter pointers are the trial state
+DeviceProblem with_state(const mcba_ctx* ctx, bool trial) {
+  DeviceProblem P = ctx->P;
+  if (trial) { P.cam_rt = ctx->cam_rt2.p; P.board_rt = ctx->board_rt2.p; P.frame_rt = ctx->frame_rt2.p; P.intr = ctx->intr2.p; }
+  return P;
+}
+
+int prepare(mcba_ctx* ctx, const DeviceProblem& P) {
+  const int np = P.C + P.B + P.F;
+  k_prepare<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P, P.cam_rt, P.board_rt, P.frame_rt);
+  CKL();
+  return MCBA_OK;
+}
+
+// push vector x (internal order) into the (trial or current) parameter state and rebuild the pose tables
+int set_state_from_x(mcba_ctx* ctx, const double* x, bool trial) {
+  DeviceProblem P = with_state(ctx, trial);
+  if (P.n > 0) {
+    k_scatter_params<<<(P.n + 255) / 256, 256, 0, ctx->stream>>>(P, x, P.cam_rt, P.board_rt, P.frame_rt, P.intr);
+    CKL();
+    if (P.fix_aspect && P.off_in >= 0) { k_fix_aspect<<<(P.C + 127) / 128, 128, 0, ctx->stream>>>(P, P.intr); CKL(); }
+  }
+  return prepare(ctx, P);
+}
+
+size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)P.n_s * 6 + P.T + P.D * 6 + 36 * 4 + 6); }
+size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)2 * P.T + P.D * 6 + (size_t)P.B * P.D * 6 + P.B * 36 + P.B * 6 + 72); }
+
+// linearise at the CURRENT parameter state: moments -> H_ss, g, H_ff, W, cost (red[RED_COST]), diag_s
+int linearize(mcba_ctx* ctx, int loss, double f_scale) {
+  DeviceProblem P = with_state(ctx, false);
+  SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p};
+  cudaStream_t s = ctx->stream;
+  ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p;
+  int r = launch_views<MODE_MOMENTS>(ctx, P, a); if (r) return r;
+  CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
+  CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
+  if (P.motion_on && P.F > 0) {
+    k_expand_frames<<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb); CKL();
+  }
+  const int nb = P.C * ctx->shared_chunks;
+  k_expand_shared<<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
+  k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL();
+  if (P.n_s > 0) { k_diag<<<(P.n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, P.n_s, ctx->diag_s.p); CKL(); }
+  // cross-rank: shared gradient, shared diagonal, cost
+  if (ctx->world > 1) {
+    if (P.n_s > 0) { AR(ctx->g.p, P.n_s, NCCL_SUM); AR(ctx->diag_s.p, P.n_s, NCCL_SUM); }
+    AR(ctx->red.p + RED_COST, 1, NCCL_SUM);
+  }
+  return MCBA_OK;
+}
+
+// cost at the TRIAL state -> red[RED_COSTNEW]
+int trial_cost(mcba_ctx* ctx, int loss, double f_scale, bool trial, int slot) {
+  DeviceProblem P = with_state(ctx, trial);
+  ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.view_cost = ctx->view_cost.p;
+  int r = launch_views<MODE_COST>(ctx, P, a); if (r) return r;
+  k_sum_partials<<<1, 1024, 0, ctx->stream>>>(ctx->view_cost.p, P.V, 1, 1, ctx->red.p + slot); CKL();
+  return MCBA_OK;
+}
+
+int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two) {
+  const DeviceProblem& P = ctx->P;
+  const int nframe = P.motion_on ? P.F : 0;
+  const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
+  const int nb = nframe + nsh;
+  if (nb == 0) return MCBA_OK;
+  k_quad<<<nb, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p); CKL();
+  // RED_AGG, RED_AGN, RED_ANN are consecutive
+  k_sum_partials<<<1, 256, 0, ctx->stream>>>(ctx->quad_part.p, nb, 3, two ? 3 : 1, ctx->red.p + RED_AGG); CKL();
+  if (ctx->world > 1) AR(ctx->red.p + RED_AGG, two ? 3 : 1, NCCL_SUM);
+  return MCBA_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int mcba_version(void) { return 100; }
+
+const char* mcba_last_error(const mcba_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mcba_create(int device, mcba_ctx** out) {
+  if (!out) return MCBA_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) { g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e); return MCBA_ERR_CUDA; }
+  if (device < 0 || device >= count) { g_create_error = "device ordinal out of range"; return MCBA_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MCBA_ERR_CUDA; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MCBA_ERR_CUDA; }
+  if (prop.major != 10) { g_create_error = "libmcba is built for sm_100a only (found sm_" + std::to_string(prop.major * 10 + prop.minor) + ")"; return MCBA_ERR_CUDA; }
+  mcba_ctx* ctx = new mcba_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
+  cudaFuncSetAttribute(k_expand_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  *out = ctx;
+  return MCBA_OK;
+}
+
+void mcba_destroy(mcba_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  delete ctx;
+}
+
+int mcba_set_stream(mcba_ctx* ctx, void* stream) {
+  if (!ctx) return MCBA_ERR_ARG;
+  ctx->stream = (cudaStream_t)stream;
+  return MCBA_OK;
+}
+
+int mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]) {
+  if (!ctx || !out_id) return MCBA_ERR_ARG;
+  if (!g_nccl.load(ctx->err)) return MCBA_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) { ctx->err = "ncclGetUniqueId failed"; return MCBA_ERR_NCCL; }
+  memcpy(out_id, id.internal, 128);
+  return MCBA_OK;
+}
+
+int mcba_comm_init(mcba_ctx* ctx, const char id_[128], int rank, int world) {
+  if (!ctx || !id_) return MCBA_ERR_ARG;
+  REQUIRE(world >= 1 && rank >= 0 && rank < world, MCBA_ERR_ARG, "bad rank/world");
+  ctx->rank = rank; ctx->world = world;
+  if (world == 1) return MCBA_OK;
+  if (!g_nccl.load(ctx->err)) return MCBA_ERR_NCCL;
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId id; memcpy(id.internal, id_, 128);
+  int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+  if (r != 0) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return MCBA_ERR_NCCL; }
+  return MCBA_OK;
+}
+
+int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam, const int32_t* frame,
+                const int32_t* board, const int32_t* point, const double* obs, const double* board_points) {
+  if (!ctx || !desc) return MCBA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
+  const int64_t N = desc->N;
+  REQUIRE(C > 0 && F >= 0 && B > 0 && Pn > 0 && N >= 0, MCBA_ERR_ARG, "bad problem dimensions");
+  REQUIRE(Pn <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
+  REQUIRE(N < (int64_t)1 << 31, MCBA_ERR_UNSUPPORTED, "more than 2^31 corners per rank");
+  REQUIRE(desc->model >= 0 && desc->model <= 3, MCBA_ERR_ARG, "unknown camera model");
+  REQUIRE(N == 0 || (cam && frame && board && point && obs), MCBA_ERR_ARG, "null corner arrays");
+  REQUIRE(board_points != nullptr, MCBA_ERR_ARG, "null board points");
+
+  // ---- pack: stable counting sort of the canonical (c,f,b,p)-ordered corners by frame => (f,c,b,p) order
+  std::vector<int64_t> fcount((size_t)F + 1, 0);
+  for (int64_t k = 0; k < N; k++) {
+    const int c = cam[k], f = frame[k], b = board[k], p = point[k];
+    if (c < 0 || c >= C || f < 0 || f >= F || b < 0 || b >= B || p < 0 || p >= Pn) { ctx->err = "corner index out of range"; return MCBA_ERR_ARG; }
+    fcount[(size_t)f + 1]++;
+  }
+  for (int f = 0; f < F; f++) fcount[(size_t)f + 1] += fcount[f];
+  std::vector<uint32_t> order((size_t)N);
+  {
+    std::vector<int64_t> cursor(fcount.begin(), fcount.end() - 1);
+    for (int64_t k = 0; k < N; k++) order[(size_t)cursor[frame[k]]++] = (uint32_t)k;
+  }
+  std::vector<double2> h_obs((size_t)N);
+  std::vector<uint16_t> h_pid((size_t)N);
+  std::vector<int> vstart, vcam, vframe, vboard, fvs((size_t)F + 1, 0);
+  int prev_c = -1, prev_f = -1, prev_b = -1;
+  for (int64_t i = 0; i < N; i++) {
+    const uint32_t k = order[(size_t)i];
+    h_obs[(size_t)i] = make_double2(obs[2 * (size_t)k], obs[2 * (size_t)k + 1]);
+    h_pid[(size_t)i] = (uint16_t)point[k];
+    const int c = cam[k], f = frame[k], b = board[k];
+    if (c != prev_c || f != prev_f || b != prev_b) {
+      vstart.push_back((int)i); vcam.push_back(c); vframe.push_back(f); vboard.push_back(b);
+      prev_c = c; prev_f = f; prev_b = b;
+    }
+  }
+  const int V = (int)vcam.size();
+  vstart.push_back((int)N);
+  {
+    std::vector<int> cnt((size_t)F + 1, 0);
+    for (int v = 0; v < V; v++) cnt[(size_t)vframe[v] + 1]++;
+    for (int f = 0; f < F; f++) cnt[(size_t)f + 1] += cnt[f];
+    fvs = cnt;
+  }
+  std::vector<int> cvs((size_t)C + 1, 0), cvl((size_t)V);
+  {
+    for (int v = 0; v < V; v++) cvs[(size_t)vcam[v] + 1]++;
+    for (int c = 0; c < C; c++) cvs[(size_t)c + 1] += cvs[c];
+    std::vector<int> cur(cvs.begin(), cvs.end() - 1);
+    for (int v = 0; v < V; v++) cvl[(size_t)cur[vcam[v]]++] = v;
+  }
+
+  DeviceProblem& P = ctx->P;
+  P = DeviceProblem{};
+  P.C = C; P.F = F; P.B = B; P.P = Pn; P.model = desc->model; P.nd = model_nd(desc->model);
+  P.kint = 5 + P.nd; P.D = model_D(desc->model); P.T = P.D * (P.D + 1) / 2 + P.D + 1;
+  P.N = N; P.V = V;
+  const int opt = desc->optimize;
+  P.motion_on = (opt & MCBA_OPT_MOTION) ? 1 : 0;
+  P.fix_aspect = (opt & MCBA_OPT_FIX_ASPECT) ? 1 : 0;
+  int off = 0;
+  P.off_cp = (opt & MCBA_OPT_CAMERA_POSES) ? off : -1; if (P.off_cp >= 0) off += 6 * C;
+  P.off_bp = (opt & MCBA_OPT_BOARD_POSES) ? off : -1; if (P.off_bp >= 0) off += 6 * B;
+  P.off_in = (opt & MCBA_OPT_CAMERAS) ? off : -1; if (P.off_in >= 0) off += P.kint * C;
+  P.n_s = off; P.n_f = P.motion_on ? 6 * F : 0; P.n = P.n_s + P.n_f;
+  // internal -> canonical permutation: canonical = [cp | bp | motion | cameras]
+  ctx->perm.assign((size_t)P.n, 0);
+  {
+    int canon = 0;
+    if (P.off_cp >= 0) { for (int i = 0; i < 6 * C; i++) ctx->perm[(size_t)P.off_cp + i] = canon + i; canon += 6 * C; }
+    if (P.off_bp >= 0) { for (int i = 0; i < 6 * B; i++) ctx->perm[(size_t)P.off_bp + i] = canon + i; canon += 6 * B; }
+    if (P.motion_on) { for (int i = 0; i < 6 * F; i++) ctx->perm[(size_t)P.n_s + i] = canon + i; canon += 6 * F; }
+    if (P.off_in >= 0) { for (int i = 0; i < P.kint * C; i++) ctx->perm[(size_t)P.off_in + i] = canon + i; canon += P.kint * C; }
+  }
+
+#define UP(buf, vec) do { CK(ctx->buf.alloc((vec).size())); if (!(vec).empty()) CK(cudaMemcpyAsync(ctx->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, ctx->stream)); } while (0)
+  UP(obs, h_obs); UP(pid, h_pid); UP(orig, order);
+  UP(view_start, vstart); UP(view_cam, vcam); UP(view_frame, vframe); UP(view_board, vboard);
+  UP(frame_view_start, fvs); UP(cam_view_start, cvs); UP(cam_view_list, cvl);
+#undef UP
+  CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
+  CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr.alloc((size_t)C * P.kint));
+  CK(ctx->cam_rt2.alloc((size_t)C * 6)); CK(ctx->board_rt2.alloc((size_t)B * 6)); CK(ctx->frame_rt2.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr2.alloc((size_t)C * P.kint));
+  CK(ctx->cam_T.alloc(C)); CK(ctx->frame_T.alloc(std::max(F, 1))); CK(ctx->board_T.alloc(B));
+  // solver buffers
+  ctx->shared_chunks = std::max(1, std::min(32, (ctx->num_sms * 2) / std::max(C, 1)));
+  if (V / std::max(C, 1) < 64) ctx->shared_chunks = 1;
+  CK(ctx->moments.alloc((size_t)std::max(V, 1) * P.T));
+  CK(ctx->Hss.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1)));
+  CK(ctx->g.alloc((size_t)std::max(P.n, 1)));
+  CK(ctx->Hff.alloc((size_t)std::max(F, 1) * 36));
+  CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
+  CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
+  CK(ctx->Lf.alloc((size_t)std::max(F, 1) * 36)); CK(ctx->zf.alloc((size_t)std::max(F, 1) * 6));
+  CK(ctx->cost_part.alloc((size_t)C * ctx->shared_chunks)); CK(ctx->view_cost.alloc((size_t)std::max(V, 1)));
+  CK(ctx->diag_s.alloc((size_t)std::max(P.n_s, 1)));
+  const size_t nn = (size_t)std::max(P.n, 1);
+  CK(ctx->x.alloc(nn)); CK(ctx->x_new.alloc(nn)); CK(ctx->sinv.alloc(nn)); CK(ctx->d.alloc(nn)); CK(ctx->gh.alloc(nn)); CK(ctx->gn.alloc(nn));
+  CK(ctx->S.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1))); CK(ctx->rhs.alloc((size_t)std::max(P.n_s, 1)));
+  CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
+  CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
+  CK(ctx->state.alloc(1));
+  CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
+  CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
+  CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
+  CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
+
+  P.obs = ctx->obs.p; P.pid = ctx->pid.p; P.orig = ctx->orig.p;
+  P.view_start = ctx->view_start.p; P.view_cam = ctx->view_cam.p; P.view_frame = ctx->view_frame.p; P.view_board = ctx->view_board.p;
+  P.frame_view_start = ctx->frame_view_start.p; P.cam_view_start = ctx->cam_view_start.p; P.cam_view_list = ctx->cam_view_list.p;
+  P.board_pts = ctx->board_pts.p;
+  P.cam_rt = ctx->cam_rt.p; P.board_rt = ctx->board_rt.p; P.frame_rt = ctx->frame_rt.p; P.intr = ctx->intr.p;
+  P.cam_T = ctx->cam_T.p; P.frame_T = ctx->frame_T.p; P.board_T = ctx->board_T.p;
+  REQUIRE(expand_frames_smem(P) <= 200 * 1024 && expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
+  CK(cudaStreamSynchronize(ctx->stream));    // host staging vectors go out of scope
+  ctx->uploaded = true;
+  return MCBA_OK;
+}
+
+int mcba_set_params(mcba_ctx* ctx, const double* cam_rt, const double* board_rt, const double* frame_rt, const double* intrinsics) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  REQUIRE(cam_rt && board_rt && intrinsics && (frame_rt || ctx->P.F == 0), MCBA_ERR_ARG, "null parameter array");
+  const DeviceProblem& P = ctx->P;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->cam_rt.p, cam_rt, sizeof(double) * P.C * 6, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->board_rt.p, board_rt, sizeof(double) * P.B * 6, cudaMemcpyHostToDevice, ctx->stream));
+  if (P.F) CK(cudaMemcpyAsync(ctx->frame_rt.p, frame_rt, sizeof(double) * P.F * 6, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->intr.p, intrinsics, sizeof(double) * P.C * P.kint, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_get_params(mcba_ctx* ctx, double* cam_rt, double* board_rt, double* frame_rt, double* intrinsics) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  CK(cudaSetDevice(ctx->device));
+  if (cam_rt) CK(cudaMemcpyAsync(cam_rt, ctx->cam_rt.p, sizeof(double) * P.C * 6, cudaMemcpyDeviceToHost, ctx->stream));
+  if (board_rt) CK(cudaMemcpyAsync(board_rt, ctx->board_rt.p, sizeof(double) * P.B * 6, cudaMemcpyDeviceToHost, ctx->stream));
+  if (frame_rt && P.F) CK(cudaMemcpyAsync(frame_rt, ctx->frame_rt.p, sizeof(double) * P.F * 6, cudaMemcpyDeviceToHost, ctx->stream));
+  if (intrinsics) CK(cudaMemcpyAsync(intrinsics, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_num_params(mcba_ctx* ctx, int64_t* n) {
+  if (!ctx || !n) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  *n = ctx->P.n;
+  return MCBA_OK;
+}
+
+static int read_x_canonical(mcba_ctx* ctx, double* x) {
+  const DeviceProblem& P = ctx->P;
+  if (P.n == 0) return MCBA_OK;
+  k_gather_params<<<(P.n + 255) / 256, 256, 0, ctx->stream>>>(P, ctx->x.p, P.cam_rt, P.board_rt, P.frame_rt, P.intr); CKL();
+  std::vector<double> h((size_t)P.n);
+  CK(cudaMemcpyAsync(h.data(), ctx->x.p, sizeof(double) * P.n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < P.n; i++) x[ctx->perm[(size_t)i]] = h[(size_t)i];
+  return MCBA_OK;
+}
+static int write_x_canonical(mcba_ctx* ctx, const double* x, double* dev_x) {
+  const DeviceProblem& P = ctx->P;
+  if (P.n == 0) return MCBA_OK;
+  std::vector<double> h((size_t)P.n);
+  for (int i = 0; i < P.n; i++) h[(size_t)i] = x[ctx->perm[(size_t)i]];
+  CK(cudaMemcpyAsync(dev_x, h.data(), sizeof(double) * P.n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_get_param_vec(mcba_ctx* ctx, double* x) {
+  if (!ctx || !x) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  CK(cudaSetDevice(ctx->device));
+  return read_x_canonical(ctx, x);
+}
+
+int mcba_set_param_vec(mcba_ctx* ctx, const double* x) {
+  if (!ctx || !x) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  CK(cudaSetDevice(ctx->device));
+  int r = write_x_canonical(ctx, x, ctx->x.p); if (r) return r;
+  r = set_state_from_x(ctx, ctx->x.p, false); if (r) return r;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_residuals(mcba_ctx* ctx, const double* x, double* r_out, double* cost) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  CK(cudaSetDevice(ctx->device));
+  const DeviceProblem& P0 = ctx->P;
+  bool trial = false;
+  if (x) {
+    // evaluate at x without disturbing the stored parameters: trial state = current state overwritten by x
+    CK(cudaMemcpyAsync(ctx->cam_rt2.p, ctx->cam_rt.p, sizeof(double) * P0.C * 6, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->board_rt2.p, ctx->board_rt.p, sizeof(double) * P0.B * 6, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (P0.F) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P0.F * 6, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P0.C * P0.kint, cudaMemcpyDeviceToDevice, ctx->stream));
+    int r = write_x_canonical(ctx, x, ctx->x_new.p); if (r) return r;
+    r = set_state_from_x(ctx, ctx->x_new.p, true); if (r) return r;
+    trial = true;
+  } else {
+    int r = prepare(ctx, with_state(ctx, false)); if (r) return r;
+  }
+  DeviceProblem P = with_state(ctx, trial);
+  if (r_out && P.N > 0) {
+    DevBuf<double> dr; CK(dr.alloc((size_t)2 * P.N));
+    ViewKernelArgs a{}; a.resid = dr.p;
+    int r = launch_views<MODE_RESID>(ctx, P, a); if (r) return r;
+    CK(cudaMemcpyAsync(r_out, dr.p, sizeof(double) * 2 * P.N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (cost) {
+    int r = trial_cost(ctx, 0, 1.0, trial, RED_COSTNEW); if (r) return r;
+    CK(cudaMemcpyAsync(cost, ctx->red.p + RED_COSTNEW, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return MCBA_OK;
+}
+
+int mcba_reprojection_error(mcba_ctx* ctx, double* err) {
+  if (!ctx || !err) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  CK(cudaSetDevice(ctx->device));
+  DeviceProblem P = with_state(ctx, false);
+  if (P.N == 0) return MCBA_OK;
+  int r = prepare(ctx, P); if (r) return r;
+  DevBuf<double> de; CK(de.alloc((size_t)P.N));
+  ViewKernelArgs a{}; a.err = de.p;
+  r = launch_views<MODE_ERROR>(ctx, P, a); if (r) return r;
+  CK(cudaMemcpyAsync(err, de.p, sizeof(double) * P.N, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_linearize(mcba_ctx* ctx, const double* x, double* JtJ, double* Jtr, double* cost) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  CK(cudaSetDevice(ctx->device));
+  const DeviceProblem& P = ctx->P;
+  if (x) { int r = mcba_set_param_vec(ctx, x); if (r) return r; }
+  else { int r = prepare(ctx, with_state(ctx, false)); if (r) return r; }
+  int r = linearize(ctx, 0, 1.0); if (r) return r;
+  const int n = P.n, n_s = P.n_s, F = P.motion_on ? P.F : 0;
+  std::vector<double> hHss((size_t)n_s * n_s), hg((size_t)n), hHff((size_t)F * 36), hW((size_t)F * n_s * 6);
+  if (n_s) CK(cudaMemcpyAsync(hHss.data(), ctx->Hss.p, sizeof(double) * hHss.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  if (n) CK(cudaMemcpyAsync(hg.data(), ctx->g.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (F) CK(cudaMemcpyAsync(hHff.data(), ctx->Hff.p, sizeof(double) * hHff.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  if (F && n_s) CK(cudaMemcpyAsync(hW.data(), ctx->W.p, sizeof(double) * hW.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  double hcost = 0;
+  CK(cudaMemcpyAsync(&hcost, ctx->red.p + RED_COST, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const std::vector<int>& pm = ctx->perm;
+  if (JtJ) {
+    std::fill(JtJ, JtJ + (size_t)n * n, 0.0);
+    for (int i = 0; i < n_s; i++) for (int j = 0; j < n_s; j++) JtJ[(size_t)pm[i] * n + pm[j]] = hHss[(size_t)i * n_s + j];
+    for (int f = 0; f < F; f++) {
+      for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) JtJ[(size_t)pm[n_s + 6 * f + i] * n + pm[n_s + 6 * f + j]] = hHff[(size_t)f * 36 + i * 6 + j];
+      for (int s = 0; s < n_s; s++) for (int j = 0; j < 6; j++) {
+        const double w = hW[((size_t)f * n_s + s) * 6 + j];
+        JtJ[(size_t)pm[s] * n + pm[n_s + 6 * f + j]] = w;
+        JtJ[(size_t)pm[n_s + 6 * f + j] * n + pm[s]] = w;
+      }
+    }
+  }
+  if (Jtr) for (int i = 0; i < n; i++) Jtr[pm[i]] = hg[(size_t)i];
+  if (cost) *cost = hcost;
+  return MCBA_OK;
+}
+
+int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* result, mcba_log_row* log, int32_t log_capacity) {
+  if (!ctx || !opts || !result) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  REQUIRE(opts->loss >= 0 && opts->loss <= 4, MCBA_ERR_ARG, "unknown loss");
+  REQUIRE(opts->max_nfev > 0, MCBA_ERR_ARG, "max_nfev must be positive");
+  REQUIRE(opts->f_scale > 0, MCBA_ERR_ARG, "f_scale must be positive");
+  CK(cudaSetDevice(ctx->device));
+  const DeviceProblem& P = ctx->P;
+  cudaStream_t s = ctx->stream;
+  const int n = P.n, n_s = P.n_s, F = P.motion_on ? P.F : 0;
+  memset(result, 0, sizeof(*result));
+  ctx->launches = 0;
+  cudaEvent_t ev0, ev1;
+  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  CK(cudaEventRecord(ev0, s));
+
+  SolverState h{};
+  h.ftol = opts->ftol; h.xtol = opts->xtol; h.gtol = opts->gtol; h.reg_floor = 1e-12; h.max_nfev = opts->max_nfev;
+  h.nfev = 1; h.njev = 1; h.iteration = 0; h.status = -99; h.first_scale = 1;
+  CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  int r;
+  // x0 from the current state
+  if (n) { k_gather_params<<<(n + 255) / 256, 256, 0, s>>>(P, ctx->x.p, P.cam_rt, P.board_rt, P.frame_rt, P.intr); CKL(); }
+  r = prepare(ctx, with_state(ctx, false)); if (r) return r;
+  r = linearize(ctx, opts->loss, opts->f_scale); if (r) return r;
+
+  double last_reduction = NAN, last_step = NAN;
+  int nlog = 0;
+  const bool chol_smem = ((size_t)n_s * n_s + n_s) * sizeof(double) <= 220 * 1024;
+  int first = 1;
+  while (true) {
+    if (n) { k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p); CKL(); }
+    first = 0;
+    if (ctx->world > 1) {
+      AR(ctx->red.p + RED_GH2_F, 1, NCCL_SUM); AR(ctx->red.p + RED_XS2_F, 1, NCCL_SUM); AR(ctx->red.p + RED_GMAX_F, 1, NCCL_MAX);
+    }
+    k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+    CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; cudaEventDestroy(ev0); cudaEventDestroy(ev1); return MCBA_ERR_NONFINITE; }
+    if (h.iteration == 0) result->initial_cost = h.cost;
+    if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.nfev, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
+    if (h.done || n == 0) break;
+
+    r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0); if (r) return r;
+    k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+    // Schur complement of the frame blocks
+    if (n_s > 0) {
+      const size_t nn2 = (size_t)n_s * n_s;
+      k_schur_init<<<(unsigned)((nn2 + 255) / 256), 256, 0, s>>>(n_s, ctx->Hss.p, ctx->d.p, ctx->S.p, ctx->rhs.p); CKL();
+    }
+    if (F > 0) {
+      k_schur_frames<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p); CKL();
+      if (n_s > 0) {
+        const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
+        int chunks = std::max(1, std::min((F + SYRK_FR - 1) / SYRK_FR, (ctx->num_sms * 4) / std::max(1, tiles * (tiles + 1) / 2)));
+        const int cf = ((F + chunks - 1) / chunks + SYRK_FR - 1) / SYRK_FR * SYRK_FR;
+        chunks = (F + cf - 1) / cf;
+        k_schur_syrk<<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p); CKL();
+        k_schur_rhs<<<dim3((n_s + 127) / 128, chunks), 128, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->zf.p, ctx->rhs.p); CKL();
+      }
+    }
+    if (n_s > 0) {
+      if (ctx->world > 1) { AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); }
+      const size_t sm = chol_smem ? ((size_t)n_s * n_s + n_s) * sizeof(double) : (size_t)n_s * sizeof(double);
+      k_chol_solve<<<1, CHOL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p, chol_smem ? 1 : 0); CKL();
+    }
+    if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
+    k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
+    if (ctx->world > 1) { AR(ctx->red.p + RED_DOTGN_F, 1, NCCL_SUM); AR(ctx->red.p + RED_GN2_F, 1, NCCL_SUM); }
+    r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1); if (r) return r;
+    k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+
+    // inner loop: shrink the radius until the cost decreases (trf.py)
+    bool accepted = false;
+    while (true) {
+      k_tr_step<<<1, 1, 0, s>>>(ctx->state.p); CKL();
+      k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
+      // trial state = current state with the free blocks replaced by x_new
+      CK(cudaMemcpyAsync(ctx->cam_rt2.p, ctx->cam_rt.p, sizeof(double) * P.C * 6, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(ctx->board_rt2.p, ctx->board_rt.p, sizeof(double) * P.B * 6, cudaMemcpyDeviceToDevice, s));
+      if (P.F) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P.F * 6, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToDevice, s));
+      r = set_state_from_x(ctx, ctx->x_new.p, true); if (r) return r;
+      r = trial_cost(ctx, opts->loss, opts->f_scale, true, RED_COSTNEW); if (r) return r;
+      if (ctx->world > 1) { AR(ctx->red.p + RED_COSTNEW, 1, NCCL_SUM); AR(ctx->red.p + RED_STEP2_F, 1, NCCL_SUM); AR(ctx->red.p + RED_XN2_F, 1, NCCL_SUM); }
+      k_accept<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+      CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      accepted = h.accepted != 0;
+      if (h.status != -99) break;
+      if (accepted || h.nfev >= h.max_nfev) break;
+    }
+    if (accepted) {
+      // x = x_new ; cost = cost_new ; J = jac(x)   (trf.py)
+      std::swap(ctx->x.p, ctx->x_new.p);
+      std::swap(ctx->cam_rt.p, ctx->cam_rt2.p); std::swap(ctx->board_rt.p, ctx->board_rt2.p);
+      std::swap(ctx->frame_rt.p, ctx->frame_rt2.p); std::swap(ctx->intr.p, ctx->intr2.p);
+      ctx->P.cam_rt = ctx->cam_rt.p; ctx->P.board_rt = ctx->board_rt.p; ctx->P.frame_rt = ctx->frame_rt.p; ctx->P.intr = ctx->intr.p;
+      h.cost = h.cost_new;
+      h.njev += 1;
+      last_reduction = h.actual_reduction; last_step = h.step_norm;
+      // pose tables already hold the trial (= new) state
+      r = linearize(ctx, opts->loss, opts->f_scale); if (r) return r;
+    } else {
+      last_reduction = 0.0; last_step = 0.0;
+    }
+    h.iteration += 1;
+    h.accepted = 0;
+    CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  }
+
+  CK(cudaEventRecord(ev1, s));
+  CK(cudaEventSynchronize(ev1));
+  float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  result->cost = h.cost; result->optimality = h.g_norm; result->nfev = h.nfev; result->njev = h.njev;
+  result->status = h.status == -99 ? 0 : h.status; result->n_log = nlog; result->device_ms = ms;
+  result->kernel_launches = ctx->launches; result->chol_retries = h.chol_fail;
+  return MCBA_OK;
+}
+
+int mcba_bench_info(mcba_ctx* ctx, int which, int64_t* corners, int64_t* bytes, int32_t* launches) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  const int np = nparts_for(P.model);
+  int64_t per_corner = 18, per_view = 16, l = 1;
+  if (which == MCBA_BENCH_LINEARIZE) { l = np; }
+  else if (which == MCBA_BENCH_RESIDUAL) { per_corner = 18 + 4 + 16; }
+  if (corners) *corners = P.N;
+  if (bytes) *bytes = per_corner * P.N + per_view * P.V;      // per LAUNCH (each PART re-reads the corners)
+  if (launches) *launches = (int32_t)l;
+  return MCBA_OK;
+}
+
+int mcba_bench_launch(mcba_ctx* ctx, int which, int repeats) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  CK(cudaSetDevice(ctx->device));
+  DeviceProblem P = with_state(ctx, false);
+  int r = prepare(ctx, P); if (r) return r;
+  for (int i = 0; i < repeats; i++) {
+    ViewKernelArgs a{}; a.loss = 0; a.f_scale = 1.0;
+    if (which == MCBA_BENCH_LINEARIZE) { a.moments = ctx->moments.p; r = launch_views<MODE_MOMENTS>(ctx, P, a); }
+    else if (which == MCBA_BENCH_COST) { a.view_cost = ctx->view_cost.p; r = launch_views<MODE_COST>(ctx, P, a); }
+    else { ctx->err = "unsupported bench kernel"; return MCBA_ERR_ARG; }
+    if (r) return r;
+  }
+  return MCBA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,562 @@
+// solver_kernels.cuh — on-device trust-region machinery.
+//
+// Follows scipy.optimize._lsq.trf.trf_no_bounds (the solver behind calibration.py:209-210) step by step:
+// jac scaling (common.py compute_jac_scale), regularised Gauss-Newton direction, 2-D subspace trust-region
+// step, ratio test / radius update (update_tr_radius), termination tests (check_termination).
+// The one deliberate change: scipy's LSMR inner iteration is replaced by an EXACT solve of
+//     (A + reg I) gn = g_h ,   A = D H D  (H = J^T J block-arrow: shared | per-frame 6x6)
+// through the Schur complement of the per-frame blocks (S = A_ss + reg I - sum_f Y_f Y_f^T).
+#pragma once
+#include "kernels.cuh"
+
+namespace mcba {
+
+struct SolverState {
+  double ftol, xtol, gtol, reg_floor;
+  int max_nfev;
+  int nfev, njev, iteration, status, accepted, first_scale, chol_fail, done;
+  double cost, cost_new, Delta, reg;
+  double g_norm, gh_norm;
+  double alpha, beta;            // step_h = alpha*gh + beta*gn
+  double B11, B12, B22, gS1, gS2, n1, n2, mu;
+  double step_h_norm, predicted, step_norm, x_norm, actual_reduction, ratio;
+  double last_step_norm, last_reduction;
+};
+
+// slots of the cross-rank reduction scratch `red` (doubles). Entries marked F hold only the contribution of
+// this rank's frames and are summed (or maxed) over ranks; S entries are computed from replicated data.
+enum {
+  RED_GH2_S = 0, RED_GH2_F, RED_GMAX_S, RED_GMAX_F, RED_XS2_S, RED_XS2_F,      // k_scale
+  RED_AGG,                                                                         // gh^T A gh   (local sum)
+  RED_AGN, RED_ANN, RED_DOTGN_S, RED_DOTGN_F, RED_GN2_S, RED_GN2_F,              // after back-substitution
+  RED_COSTNEW, RED_STEP2_S, RED_STEP2_F, RED_XN2_S, RED_XN2_F,                    // trial step
+  RED_COST,                                                                        // cost at linearisation
+  RED_COUNT
+};
+
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < nw ? sm[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;   // valid in thread 0
+}
+__device__ __forceinline__ double block_max(double v, double* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < nw ? sm[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  }
+  return r;
+}
+
+// deterministic sum of per-CTA partials: out[j] = sum_i part[i*stride + j]
+__global__ void k_sum_partials(const double* part, int count, int stride, int nout, double* out) {
+  __shared__ double sm[32];
+  for (int j = 0; j < nout; j++) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += part[(size_t)i * stride + j];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) out[j] = s;
+    __syncthreads();
+  }
+}
+
+// extract diag(H_ss) so that it can be all-reduced as a vector
+__global__ void k_diag(const double* Hss, int n_s, double* diag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_s) diag[i] = Hss[(size_t)i * n_s + i];
+}
+
+// common.py compute_jac_scale: scale_inv = ||J[:,i]|| = sqrt(H_ii); zero -> 1 on the first call, running max after;
+// also g_h = d*g, ||g||_inf, ||g_h||^2 and ||x*scale_inv||^2 (initial Delta, trf.py).  Single CTA.
+__global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hff, const double* g, const double* x,
+                        double* sinv, double* d, double* gh, int first, double* red) {
+  __shared__ double sm[32];
+  double gh2s = 0, gh2f = 0, gms = 0, gmf = 0, xs2s = 0, xs2f = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double hd;
+    if (i < n_s) hd = diag_s[i];
+    else { const int f = (i - n_s) / 6, j = (i - n_s) % 6; hd = Hff[(size_t)f * 36 + j * 7]; }
+    double nrm = sqrt(fmax(hd, 0.0));
+    double si;
+    if (first) si = (nrm == 0.0) ? 1.0 : nrm; else si = fmax(nrm, sinv[i]);
+    sinv[i] = si;
+    const double di = 1.0 / si;
+    d[i] = di;
+    const double gi = g[i], ghi = di * gi, xs = x[i] * si;
+    gh[i] = ghi;
+    if (i < n_s) { gh2s += ghi * ghi; gms = fmax(gms, fabs(gi)); xs2s += xs * xs; }
+    else { gh2f += ghi * ghi; gmf = fmax(gmf, fabs(gi)); xs2f += xs * xs; }
+  }
+  double r;
+  r = block_sum(gh2s, sm); if (threadIdx.x == 0) red[RED_GH2_S] = r;
+  r = block_sum(gh2f, sm); if (threadIdx.x == 0) red[RED_GH2_F] = r;
+  r = block_max(gms, sm);  if (threadIdx.x == 0) red[RED_GMAX_S] = r;
+  r = block_max(gmf, sm);  if (threadIdx.x == 0) red[RED_GMAX_F] = r;
+  r = block_sum(xs2s, sm); if (threadIdx.x == 0) red[RED_XS2_S] = r;
+  r = block_sum(xs2f, sm); if (threadIdx.x == 0) red[RED_XS2_F] = r;
+}
+
+// quadratic forms u^T A v, A = D H D, for (u,u) [, (u,v), (v,v)].  Grid = F frame CTAs + shared CTAs.
+// partial[cta][3].  u, v are scaled-space vectors (gh, gn).
+constexpr int QUAD_THREADS = 128;
+__global__ void __launch_bounds__(QUAD_THREADS)
+k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, const double* W, const double* d,
+       const double* u, const double* v, int two, double* partial) {
+  __shared__ double sm[32];
+  __shared__ double tt[12];
+  const int tid = threadIdx.x;
+  const int nframe = motion_on ? F : 0;
+  double uu = 0, uv = 0, vv = 0;
+  if ((int)blockIdx.x < nframe) {
+    const int f = blockIdx.x;
+    const double* Wf = W + (size_t)f * n_s * 6;
+    double tu[6] = {0, 0, 0, 0, 0, 0}, tv[6] = {0, 0, 0, 0, 0, 0};
+    for (int s = tid; s < n_s; s += QUAD_THREADS) {
+      const double us = d[s] * u[s], vs = two ? d[s] * v[s] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; j++) { const double w = Wf[s * 6 + j]; tu[j] += w * us; tv[j] += w * vs; }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      double r = block_sum(tu[j], sm); if (tid == 0) tt[j] = r;
+      if (two) { r = block_sum(tv[j], sm); if (tid == 0) tt[6 + j] = r; }
+    }
+    if (tid == 0) {
+      double uf[6], vf[6];
+      for (int j = 0; j < 6; j++) { const int i = n_s + 6 * f + j; uf[j] = d[i] * u[i]; vf[j] = two ? d[i] * v[i] : 0.0; }
+      const double* H = Hff + (size_t)f * 36;
+      for (int i = 0; i < 6; i++) {
+        double hu = 0, hv = 0;
+        for (int j = 0; j < 6; j++) { hu += H[i * 6 + j] * uf[j]; hv += H[i * 6 + j] * vf[j]; }
+        uu += uf[i] * (hu + 2.0 * tt[i]);
+        if (two) { uv += uf[i] * hv + uf[i] * tt[6 + i] + vf[i] * tt[i]; vv += vf[i] * (hv + 2.0 * tt[6 + i]); }
+      }
+      partial[(size_t)blockIdx.x * 3 + 0] = uu; partial[(size_t)blockIdx.x * 3 + 1] = uv; partial[(size_t)blockIdx.x * 3 + 2] = vv;
+    }
+  } else {
+    const int i = (blockIdx.x - nframe) * QUAD_THREADS + tid;
+    if (i < n_s) {
+      double hu = 0, hv = 0;
+      for (int j = 0; j < n_s; j++) {
+        const double h = Hss[(size_t)j * n_s + i];
+        hu += h * d[j] * u[j];
+        if (two) hv += h * d[j] * v[j];
+      }
+      const double ui = d[i] * u[i], vi = two ? d[i] * v[i] : 0.0;
+      uu = ui * hu; uv = ui * hv; vv = vi * hv;
+    }
+    double r;
+    r = block_sum(uu, sm); if (tid == 0) partial[(size_t)blockIdx.x * 3 + 0] = r;
+    r = block_sum(uv, sm); if (tid == 0) partial[(size_t)blockIdx.x * 3 + 1] = r;
+    r = block_sum(vv, sm); if (tid == 0) partial[(size_t)blockIdx.x * 3 + 2] = r;
+  }
+}
+
+// trf.py: reg_term = -ag_value / Delta^2 with ag_value = min over [0, Delta/||g_h||] of a t^2 + b t,
+// a = g_h^T A g_h, b = -||g_h||^2 (build_quadratic_1d / minimize_quadratic_1d).  Also finalises ||g||_inf,
+// the initial Delta and the gtol / max_nfev exits at the top of the outer loop.
+__global__ void k_begin_iteration(SolverState* st, double* red) {
+  const double gh2 = red[RED_GH2_S] + red[RED_GH2_F];
+  st->gh_norm = sqrt(gh2);
+  st->g_norm = fmax(red[RED_GMAX_S], red[RED_GMAX_F]);
+  if (st->first_scale) {
+    st->cost = red[RED_COST];
+    double D0 = sqrt(red[RED_XS2_S] + red[RED_XS2_F]);
+    st->Delta = (D0 == 0.0) ? 1.0 : D0;
+    st->first_scale = 0;
+  }
+  if (st->g_norm < st->gtol) st->status = 1;
+  st->done = (st->status != -99) || (st->nfev >= st->max_nfev);
+}
+
+__global__ void k_reg(SolverState* st, const double* red) {
+  const double a = red[RED_AGG];
+  const double gh2 = st->gh_norm * st->gh_norm;
+  const double b = -gh2;
+  const double ub = st->Delta / st->gh_norm;
+  // minimize a t^2 + b t on [0, ub]
+  double best_t = 0.0, best = 0.0;
+  { const double yv = a * ub * ub + b * ub; if (yv < best) { best = yv; best_t = ub; } }
+  if (a != 0.0) { const double ext = -0.5 * b / a; if (ext > 0.0 && ext < ub) { const double yv = a * ext * ext + b * ext; if (yv < best) { best = yv; best_t = ext; } } }
+  (void)best_t;
+  double reg = -best / (st->Delta * st->Delta);
+  if (!(reg > st->reg_floor)) reg = st->reg_floor;
+  st->reg = reg;
+}
+
+// per frame: L L^T = D_f H_ff D_f + reg I ; Y_f = (D_s W_f D_f) L^-T (n_s x 6) ; z_f = L^-1 (D_f g_f)
+constexpr int SCHUR_THREADS = 128;
+__global__ void __launch_bounds__(SCHUR_THREADS)
+k_schur_frames(int n_s, const double* Hff, const double* W, const double* d, const double* gh,
+               const SolverState* st, double* Y, double* Lf, double* zf) {
+  __shared__ double L[36];
+  __shared__ double df[6];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    const double reg = st->reg;
+    const double* H = Hff + (size_t)f * 36;
+    double A[36];
+    for (int j = 0; j < 6; j++) df[j] = d[n_s + 6 * f + j];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i * 6 + j] = df[i] * df[j] * H[i * 6 + j] + (i == j ? reg : 0.0);
+    for (int j = 0; j < 6; j++) {
+      double s = A[j * 6 + j];
+      for (int k = 0; k < j; k++) s -= L[j * 6 + k] * L[j * 6 + k];
+      const double piv = sqrt(fmax(s, 1e-300));
+      L[j * 6 + j] = piv;
+      for (int i = j + 1; i < 6; i++) {
+        double t = A[i * 6 + j];
+        for (int k = 0; k < j; k++) t -= L[i * 6 + k] * L[j * 6 + k];
+        L[i * 6 + j] = t / piv;
+      }
+      for (int i = 0; i < j; i++) L[i * 6 + j] = 0.0;
+    }
+    double z[6];
+    for (int i = 0; i < 6; i++) {
+      double t = gh[n_s + 6 * f + i];
+      for (int k = 0; k < i; k++) t -= L[i * 6 + k] * z[k];
+      z[i] = t / L[i * 6 + i];
+      zf[(size_t)f * 6 + i] = z[i];
+    }
+    for (int i = 0; i < 36; i++) Lf[(size_t)f * 36 + i] = L[i];
+  }
+  __syncthreads();
+  const double* Wf = W + (size_t)f * n_s * 6;
+  double* Yf = Y + (size_t)f * n_s * 6;
+  for (int s = tid; s < n_s; s += SCHUR_THREADS) {
+    const double ds = d[s];
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      double t = ds * Wf[s * 6 + i] * df[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) t -= L[i * 6 + k] * y[k];
+      y[i] = t / L[i * 6 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) Yf[s * 6 + i] = y[i];
+  }
+}
+
+// S_local = D_s H_ss D_s ; rhs_local = 0      (the reg*I and D_s g_s terms are added after the all-reduce)
+__global__ void k_schur_init(int n_s, const double* Hss, const double* d, double* S, double* rhs) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)n_s * n_s) { const int i = idx / n_s, j = idx % n_s; S[idx] = d[i] * d[j] * Hss[idx]; }
+  if (idx < (size_t)n_s) rhs[idx] = 0.0;
+}
+
+// S -= sum_f Y_f Y_f^T over this CTA's frame chunk; 32x32 output tile per CTA, 2x2 micro-tile per thread.
+constexpr int SYRK_TILE = 32, SYRK_FR = 8;
+__global__ void __launch_bounds__(256)
+k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S) {
+  __shared__ double Yi[SYRK_FR][SYRK_TILE][6];
+  __shared__ double Yj[SYRK_FR][SYRK_TILE][6];
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj < ti) return;
+  const int f0 = blockIdx.z * chunk_frames, f1 = min(F, f0 + chunk_frames);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int fb = f0; fb < f1; fb += SYRK_FR) {
+    const int nf = min(SYRK_FR, f1 - fb);
+    for (int o = threadIdx.x; o < SYRK_FR * SYRK_TILE * 6; o += 256) {
+      const int ff = o / (SYRK_TILE * 6), rem = o % (SYRK_TILE * 6), r = rem / 6, k = rem % 6;
+      const int gi = ti * SYRK_TILE + r, gj = tj * SYRK_TILE + r;
+      (&Yi[0][0][0])[o] = (ff < nf && gi < n_s) ? Y[((size_t)(fb + ff) * n_s + gi) * 6 + k] : 0.0;
+      (&Yj[0][0][0])[o] = (ff < nf && gj < n_s) ? Y[((size_t)(fb + ff) * n_s + gj) * 6 + k] : 0.0;
+    }
+    __syncthreads();
+    for (int ff = 0; ff < nf; ff++) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const double a0 = Yi[ff][ty][k], a1 = Yi[ff][ty + 16][k], b0 = Yj[ff][tx][k], b1 = Yj[ff][tx + 16][k];
+        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = ti * SYRK_TILE + ty + 16 * a, j = tj * SYRK_TILE + tx + 16 * b;
+      if (i < n_s && j < n_s && (ti != tj || j >= i)) {
+        atomicAdd(&S[(size_t)i * n_s + j], -acc[a][b]);
+        if (i != j) atomicAdd(&S[(size_t)j * n_s + i], -acc[a][b]);
+      }
+    }
+}
+
+// rhs -= sum_f Y_f z_f   (thread per shared row, frame chunks over blockIdx.y)
+__global__ void k_schur_rhs(int n_s, int F, int chunk_frames, const double* Y, const double* zf, double* rhs) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_s) return;
+  const int f0 = blockIdx.y * chunk_frames, f1 = min(F, f0 + chunk_frames);
+  double acc = 0.0;
+  for (int f = f0; f < f1; f++) {
+    const double* y = Y + ((size_t)f * n_s + s) * 6;
+    const double* z = zf + (size_t)f * 6;
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc += y[k] * z[k];
+  }
+  atomicAdd(&rhs[s], -acc);
+}
+
+// Dense SPD solve of the reduced (shared-parameter) system, one CTA:
+//   (S + reg I) p_s = rhs + D_s g_s      -> gn[0..n_s)
+// In-place right-looking Cholesky; the matrix lives in shared memory when it fits (n_s <= CHOL_SMEM_N),
+// otherwise in global memory (L2 resident).
+constexpr int CHOL_THREADS = 1024;
+__global__ void __launch_bounds__(CHOL_THREADS)
+k_chol_solve(int n, double* Sg, const double* rhs, const double* gh, SolverState* st, double* out, int use_smem) {
+  extern __shared__ double shm[];
+  double* col = shm;                       // n
+  double* A = use_smem ? shm + n : Sg;     // n*n
+  const int tid = threadIdx.x;
+  const double reg = st->reg;
+  if (use_smem) {
+    for (size_t i = tid; i < (size_t)n * n; i += CHOL_THREADS) A[i] = Sg[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += CHOL_THREADS) A[(size_t)i * n + i] += reg;
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    const double akk = A[(size_t)k * n + k];
+    const double piv = sqrt(fmax(akk, 1e-300));
+    if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
+    const double ip = 1.0 / piv;
+    __syncthreads();
+    for (int i = k + tid; i < n; i += CHOL_THREADS) {
+      const double l = (i == k) ? piv : A[(size_t)i * n + k] * ip;
+      A[(size_t)i * n + k] = l;
+      col[i] = l;
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: A[i][j] -= l_i l_j  for k < j <= i
+    const int m = n - k - 1;
+    const long total = (long)m * (m + 1) / 2;
+    for (long o = tid; o < total; o += CHOL_THREADS) {
+      // row r (0..m-1) has r+1 entries
+      int r = (int)((sqrt(8.0 * (double)o + 1.0) - 1.0) * 0.5);
+      while ((long)r * (r + 1) / 2 > o) r--;
+      while ((long)(r + 1) * (r + 2) / 2 <= o) r++;
+      const int cidx = (int)(o - (long)r * (r + 1) / 2);
+      const int i = k + 1 + r, j = k + 1 + cidx;
+      A[(size_t)i * n + j] -= col[i] * col[j];
+    }
+    __syncthreads();
+  }
+  // forward: L y = b ; backward: L^T x = y   (b = rhs + gh_s); column-oriented, one CTA
+  for (int i = tid; i < n; i += CHOL_THREADS) col[i] = rhs[i] + gh[i];
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    if (tid == 0) col[k] = col[k] / A[(size_t)k * n + k];
+    __syncthreads();
+    const double yk = col[k];
+    for (int i = k + 1 + tid; i < n; i += CHOL_THREADS) col[i] -= A[(size_t)i * n + k] * yk;
+    __syncthreads();
+  }
+  for (int k = n - 1; k >= 0; k--) {
+    if (tid == 0) col[k] = col[k] / A[(size_t)k * n + k];
+    __syncthreads();
+    const double xk = col[k];
+    for (int i = tid; i < k; i += CHOL_THREADS) col[i] -= A[(size_t)k * n + i] * xk;
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += CHOL_THREADS) out[i] = col[i];
+}
+
+// back-substitution of the eliminated frame blocks: gn_f = L^-T (z_f - Y_f^T gn_s)
+__global__ void __launch_bounds__(SCHUR_THREADS)
+k_backsub(int n_s, const double* Y, const double* Lf, const double* zf, double* gn) {
+  __shared__ double sm[32];
+  __shared__ double t[6];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const double* Yf = Y + (size_t)f * n_s * 6;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int s = tid; s < n_s; s += SCHUR_THREADS) {
+    const double ps = gn[s];
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc[k] += Yf[s * 6 + k] * ps;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const double r = block_sum(acc[k], sm); if (tid == 0) t[k] = r; }
+  if (tid == 0) {
+    const double* L = Lf + (size_t)f * 36;
+    double y[6];
+    for (int i = 0; i < 6; i++) y[i] = zf[(size_t)f * 6 + i] - t[i];
+    for (int i = 5; i >= 0; i--) {
+      double v = y[i];
+      for (int k = i + 1; k < 6; k++) v -= L[k * 6 + i] * y[k];
+      y[i] = v / L[i * 6 + i];
+    }
+    for (int i = 0; i < 6; i++) gn[n_s + 6 * f + i] = y[i];
+  }
+}
+
+// gh.gn and ||gn||^2, split shared / frame.  Single CTA.
+__global__ void k_dots(int n, int n_s, const double* gh, const double* gn, double* red) {
+  __shared__ double sm[32];
+  double ds = 0, df = 0, ns = 0, nf = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double a = gh[i], b = gn[i];
+    if (i < n_s) { ds += a * b; ns += b * b; } else { df += a * b; nf += b * b; }
+  }
+  double r;
+  r = block_sum(ds, sm); if (threadIdx.x == 0) red[RED_DOTGN_S] = r;
+  r = block_sum(df, sm); if (threadIdx.x == 0) red[RED_DOTGN_F] = r;
+  r = block_sum(ns, sm); if (threadIdx.x == 0) red[RED_GN2_S] = r;
+  r = block_sum(nf, sm); if (threadIdx.x == 0) red[RED_GN2_F] = r;
+}
+
+// trf.py: S = qr([g_h, gn_h]); B_S = (J_h S)^T (J_h S); g_S = S^T g_h   -- expressed through Gram-Schmidt
+// coefficients so that no basis vectors are materialised: q1 = gh/n1, q2 = (gn - mu q1)/n2.
+__global__ void k_subspace(SolverState* st, const double* red) {
+  const double n1 = st->gh_norm;
+  const double dot = red[RED_DOTGN_S] + red[RED_DOTGN_F];
+  const double gn2 = red[RED_GN2_S] + red[RED_GN2_F];
+  const double mu = dot / n1;
+  double n2sq = gn2 - mu * mu;
+  const double agg = red[RED_AGG], agn = red[RED_AGN], ann = red[RED_ANN];
+  st->n1 = n1; st->mu = mu;
+  st->B11 = agg / (n1 * n1);
+  st->gS1 = n1; st->gS2 = 0.0;
+  if (!(n2sq > 1e-28 * gn2) || !(n2sq > 0.0)) {     // gn parallel to gh: 1-D subspace
+    st->n2 = 0.0; st->B12 = 0.0; st->B22 = 1.0;
+  } else {
+    const double n2 = sqrt(n2sq), c = mu / n1;
+    st->n2 = n2;
+    st->B12 = (agn - c * agg) / (n1 * n2);
+    st->B22 = (ann - 2.0 * c * agn + c * c * agg) / (n2 * n2);
+  }
+}
+
+// common.py solve_trust_region_2d: minimise 0.5 p^T B p + g^T p, ||p|| <= Delta  (B 2x2 symmetric).
+// Interior Newton point if B is positive definite and inside; otherwise the global boundary minimiser via
+// the secular equation in the eigenbasis of B (equivalent to scipy's argmin over the quartic's real roots).
+__device__ inline void solve_tr_2d(double b11, double b12, double b22, double g1, double g2, double Delta, double& p1, double& p2) {
+  const double det = b11 * b22 - b12 * b12;
+  if (b11 > 0.0 && det > 0.0) {
+    const double q1 = -(b22 * g1 - b12 * g2) / det, q2 = -(b11 * g2 - b12 * g1) / det;
+    if (q1 * q1 + q2 * q2 <= Delta * Delta) { p1 = q1; p2 = q2; return; }
+  }
+  // eigen-decomposition
+  const double tr = b11 + b22, df = b11 - b22;
+  const double rad = sqrt(df * df + 4.0 * b12 * b12);
+  const double l1 = 0.5 * (tr - rad), l2 = 0.5 * (tr + rad);       // l1 <= l2
+  double v1x, v1y;
+  if (fabs(b12) > 1e-300 * fmax(fabs(tr), 1.0)) { v1x = l1 - b22; v1y = b12; const double nn = hypot(v1x, v1y); if (nn > 0) { v1x /= nn; v1y /= nn; } else { v1x = 1; v1y = 0; } }
+  else if (b11 <= b22) { v1x = 1; v1y = 0; } else { v1x = 0; v1y = 1; }
+  const double v2x = -v1y, v2y = v1x;
+  const double h1 = v1x * g1 + v1y * g2, h2 = v2x * g1 + v2y * g2;
+  // find sigma >= max(0,-l1) with h1^2/(l1+s)^2 + h2^2/(l2+s)^2 = Delta^2
+  const double gnorm = hypot(h1, h2);
+  double lo = fmax(0.0, -l1);
+  double hi = fmax(lo, gnorm / Delta - l1) + 1e-300;
+  auto pn2 = [&](double s) { const double a = h1 / (l1 + s), b = h2 / (l2 + s); return a * a + b * b; };
+  double c1, c2;
+  // hard case: h1 ~ 0 and the l2-component alone stays inside at s = -l1
+  const bool hard = (fabs(h1) <= 1e-14 * gnorm) && (l2 + lo > 0.0) && (h2 * h2 / ((l2 + lo) * (l2 + lo)) <= Delta * Delta);
+  if (hard || gnorm == 0.0) {
+    c2 = (l2 + lo > 0.0) ? -h2 / (l2 + lo) : 0.0;
+    const double rem = Delta * Delta - c2 * c2;
+    c1 = sqrt(fmax(rem, 0.0));
+  } else {
+    while (pn2(hi) > Delta * Delta) hi = 2.0 * hi + 1e-12;
+    double s = hi;
+    for (int it = 0; it < 200; it++) {
+      s = 0.5 * (lo + hi);
+      if (pn2(s) > Delta * Delta) lo = s; else hi = s;
+      if (hi - lo <= 1e-16 * fmax(hi, 1e-300)) break;
+    }
+    s = 0.5 * (lo + hi);
+    c1 = -h1 / (l1 + s); c2 = -h2 / (l2 + s);
+    const double nn = hypot(c1, c2);
+    if (nn > 0.0) { c1 *= Delta / nn; c2 *= Delta / nn; }
+  }
+  p1 = c1 * v1x + c2 * v2x;
+  p2 = c1 * v1y + c2 * v2y;
+}
+
+__global__ void k_tr_step(SolverState* st) {
+  double p1, p2;
+  solve_tr_2d(st->B11, st->B12, st->B22, st->gS1, st->gS2, st->Delta, p1, p2);
+  if (st->n2 == 0.0) p2 = 0.0;
+  st->step_h_norm = sqrt(p1 * p1 + p2 * p2);
+  st->predicted = -(0.5 * (st->B11 * p1 * p1 + 2.0 * st->B12 * p1 * p2 + st->B22 * p2 * p2) + st->gS1 * p1 + st->gS2 * p2);
+  // step_h = p1 q1 + p2 q2 = alpha gh + beta gn
+  if (st->n2 == 0.0) { st->alpha = p1 / st->n1; st->beta = 0.0; }
+  else { st->beta = p2 / st->n2; st->alpha = p1 / st->n1 - st->beta * st->mu / st->n1; }
+}
+
+// x_new = x + d*(alpha gh + beta gn); norms of step and x (split shared / frame). Single CTA.
+__global__ void k_step(int n, int n_s, const SolverState* st, const double* x, const double* d, const double* gh,
+                       const double* gn, double* x_new, double* red) {
+  __shared__ double sm[32];
+  const double al = st->alpha, be = st->beta;
+  double s2s = 0, s2f = 0, x2s = 0, x2f = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double stp = d[i] * (al * gh[i] + be * gn[i]);
+    const double xi = x[i];
+    x_new[i] = xi + stp;
+    if (i < n_s) { s2s += stp * stp; x2s += xi * xi; } else { s2f += stp * stp; x2f += xi * xi; }
+  }
+  double r;
+  r = block_sum(s2s, sm); if (threadIdx.x == 0) red[RED_STEP2_S] = r;
+  r = block_sum(s2f, sm); if (threadIdx.x == 0) red[RED_STEP2_F] = r;
+  r = block_sum(x2s, sm); if (threadIdx.x == 0) red[RED_XN2_S] = r;
+  r = block_sum(x2f, sm); if (threadIdx.x == 0) red[RED_XN2_F] = r;
+}
+
+// trf.py inner loop after fun(x_new): actual reduction, update_tr_radius, check_termination.
+__global__ void k_accept(SolverState* st, const double* red) {
+  st->nfev += 1;
+  const double cost_new = red[RED_COSTNEW];
+  st->cost_new = cost_new;
+  const double shn = st->step_h_norm;
+  if (!isfinite(cost_new)) {            // trf.py: non-finite f_new -> shrink and retry
+    st->Delta = 0.25 * shn;
+    st->actual_reduction = -1.0;
+    st->accepted = 0;
+    return;
+  }
+  const double actual = st->cost - cost_new;
+  const double pred = st->predicted;
+  double ratio;
+  if (pred > 0.0) ratio = actual / pred; else if (pred == 0.0 && actual == 0.0) ratio = 1.0; else ratio = 0.0;
+  double Dn = st->Delta;
+  if (ratio < 0.25) Dn = 0.25 * shn;
+  else if (ratio > 0.75 && shn > 0.95 * st->Delta) Dn = 2.0 * st->Delta;
+  const double step_norm = sqrt(red[RED_STEP2_S] + red[RED_STEP2_F]);
+  const double x_norm = sqrt(red[RED_XN2_S] + red[RED_XN2_F]);
+  st->step_norm = step_norm; st->x_norm = x_norm; st->actual_reduction = actual; st->ratio = ratio;
+  const bool ft = (actual < st->ftol * st->cost) && (ratio > 0.25);
+  const bool xt = step_norm < st->xtol * (st->xtol + x_norm);
+  int status = -99;
+  if (ft && xt) status = 4; else if (ft) status = 2; else if (xt) status = 3;
+  st->status = status;
+  if (status == -99) st->Delta = Dn;
+  st->accepted = actual > 0.0;
+}
+
+__global__ void k_axpby_copy(int n, const double* src, double* dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+}  // namespace mcba

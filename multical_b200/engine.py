@@ -1,0 +1,173 @@
+"""Python face of libmcba.so: one `Engine` = one C-ABI context on one GPU.
+
+The engine replaces exactly one call of the reference,
+`scipy.optimize.least_squares(evaluate, ...)` (multical/optimization/calibration.py:209-210),
+together with the `evaluate` closure (204-206) and the reprojection-error pass (tables.py:244-249).
+Everything numeric happens in CUDA kernels behind include/mcba.h; numpy is only used to lay
+out the packed input arrays."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+from ._native import NativeError
+
+
+def pack_corners(inliers, points):
+  """Dense [C,F,B,P] mask + [C,F,B,P,2] observations -> packed corner arrays in the reference's
+  boolean-mask order (np.argwhere(inliers) row-major == `(...)[self.inliers]`, calibration.py:206)."""
+  idx = np.argwhere(inliers).astype(np.int32)                     # [N,4] rows (c,f,b,p)
+  obs = np.ascontiguousarray(points[inliers], dtype=np.float64)   # [N,2]
+  return idx, obs
+
+
+class SolveInfo(dict):
+  __getattr__ = dict.__getitem__
+
+
+class Engine:
+  def __init__(self, device=0, stream=None):
+    self.lib = nat.load()
+    h = C.c_void_p()
+    rc = self.lib.mcba_create(int(device), C.byref(h))
+    if rc != 0:
+      raise NativeError(f"mcba_create failed ({rc}): {self.lib.mcba_last_error(None).decode()}")
+    self.h = h
+    self.device = device
+    self.desc = None
+    if stream is not None:
+      self._ck(self.lib.mcba_set_stream(self.h, C.c_void_p(int(stream))))
+
+  def close(self):
+    if getattr(self, "h", None):
+      self.lib.mcba_destroy(self.h)
+      self.h = None
+
+  def __del__(self):
+    try: self.close()
+    except Exception: pass
+
+  def _ck(self, rc):
+    if rc == 0: return
+    msg = self.lib.mcba_last_error(self.h).decode()
+    if rc == 1: raise AssertionError(msg)            # reference uses `assert` for bad inputs (calibration.py:59-61)
+    if rc == 5: raise ValueError(msg)                # scipy: "Residuals are not finite in the initial point."
+    if rc == 6: raise NotImplementedError(msg)
+    raise NativeError(f"libmcba error {rc}: {msg}")
+
+  # ---- multi-GPU --------------------------------------------------------------------------------
+  def comm_unique_id(self):
+    buf = C.create_string_buffer(128)
+    self._ck(self.lib.mcba_comm_unique_id(self.h, buf))
+    return buf.raw
+
+  def comm_init(self, uid, rank, world):
+    self._ck(self.lib.mcba_comm_init(self.h, uid, int(rank), int(world)))
+    self.rank, self.world = rank, world
+
+  # ---- problem ----------------------------------------------------------------------------------
+  def upload(self, model, optimize_bits, dims, idx, obs, board_points):
+    Cn, F, B, P = (int(v) for v in dims)
+    idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 4)
+    cols = [np.ascontiguousarray(idx[:, j]) for j in range(4)]
+    obs = nat.f64(obs).reshape(-1, 2)
+    bp = nat.f64(board_points).reshape(B, P, 3)
+    d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], int(optimize_bits), idx.shape[0])
+    self._ck(self.lib.mcba_upload(self.h, C.byref(d), nat.iptr(cols[0]), nat.iptr(cols[1]), nat.iptr(cols[2]),
+                                  nat.iptr(cols[3]), nat.dptr(obs), nat.dptr(bp)))
+    self.desc = d
+    self.model = model
+    self.kint = 5 + nat.DIST_SIZES[model]
+    self.N = idx.shape[0]
+
+  def set_params(self, cam_rt, board_rt, frame_rt, intrinsics):
+    d = self.desc
+    cam_rt, board_rt, intrinsics = nat.f64(cam_rt), nat.f64(board_rt), nat.f64(intrinsics)
+    frame_rt = nat.f64(frame_rt) if d.F else np.zeros((1, 6))
+    assert cam_rt.size == 6 * d.C and board_rt.size == 6 * d.B and intrinsics.size == self.kint * d.C
+    assert d.F == 0 or frame_rt.size == 6 * d.F
+    self._ck(self.lib.mcba_set_params(self.h, nat.dptr(cam_rt), nat.dptr(board_rt), nat.dptr(frame_rt), nat.dptr(intrinsics)))
+
+  def get_params(self):
+    d = self.desc
+    out = (np.zeros((d.C, 6)), np.zeros((d.B, 6)), np.zeros((max(d.F, 1), 6)), np.zeros((d.C, self.kint)))
+    self._ck(self.lib.mcba_get_params(self.h, *[nat.dptr(a) for a in out]))
+    return out[0], out[1], out[2][:d.F], out[3]
+
+  @property
+  def num_params(self):
+    n = C.c_int64()
+    self._ck(self.lib.mcba_num_params(self.h, C.byref(n)))
+    return n.value
+
+  @property
+  def param_vec(self):
+    x = np.zeros(max(self.num_params, 1))
+    self._ck(self.lib.mcba_get_param_vec(self.h, nat.dptr(x)))
+    return x[:self.num_params]
+
+  def set_param_vec(self, x):
+    x = nat.f64(x)
+    assert x.size == self.num_params, f"inconsistent parameter sizes, got {x.size}, expected {self.num_params}"
+    if x.size: self._ck(self.lib.mcba_set_param_vec(self.h, nat.dptr(x)))
+
+  # ---- parity hooks -----------------------------------------------------------------------------
+  def residuals(self, x=None, with_cost=False):
+    r = np.zeros(max(2 * self.N, 1))
+    cost = C.c_double()
+    if x is not None:
+      x = nat.f64(x)
+      assert x.size == self.num_params
+    self._ck(self.lib.mcba_residuals(self.h, nat.dptr(x) if x is not None and x.size else None, nat.dptr(r),
+                                     C.cast(C.byref(cost), C.POINTER(C.c_double)) if with_cost else None))
+    r = r[:2 * self.N]
+    return (r, cost.value) if with_cost else r
+
+  def linearize(self, x=None):
+    n = self.num_params
+    JtJ, Jtr = np.zeros((max(n, 1), max(n, 1))), np.zeros(max(n, 1))
+    cost = C.c_double()
+    if x is not None: x = nat.f64(x)
+    self._ck(self.lib.mcba_linearize(self.h, nat.dptr(x) if x is not None and x.size else None, nat.dptr(JtJ), nat.dptr(Jtr),
+                                     C.cast(C.byref(cost), C.POINTER(C.c_double))))
+    return JtJ[:n, :n], Jtr[:n], cost.value
+
+  def reprojection_error(self):
+    e = np.zeros(max(self.N, 1))
+    self._ck(self.lib.mcba_reprojection_error(self.h, nat.dptr(e)))
+    return e[:self.N]
+
+  # ---- the solve --------------------------------------------------------------------------------
+  def solve(self, ftol=1e-8, xtol=1e-8, gtol=1e-8, f_scale=1.0, max_nfev=100, loss="linear"):
+    if loss not in nat.LOSS_IDS:
+      raise ValueError(f"`loss` must be one of {list(nat.LOSS_IDS)} or a callable.")
+    opts = nat.SolveOpts(ftol, xtol, gtol, f_scale, int(max_nfev), nat.LOSS_IDS[loss])
+    res = nat.SolveResult()
+    cap = int(max_nfev) + 2
+    log = (nat.LogRow * cap)()
+    self._ck(self.lib.mcba_solve(self.h, C.byref(opts), C.byref(res), log, cap))
+    rows = [(r.iteration, r.nfev, r.cost, r.cost_reduction, r.step_norm, r.optimality) for r in log[:res.n_log]]
+    return SolveInfo(cost=res.cost, initial_cost=res.initial_cost, optimality=res.optimality, nfev=res.nfev,
+                     njev=res.njev, status=res.status, message=nat.STATUS_MESSAGES.get(res.status, ""),
+                     device_ms=res.device_ms, kernel_launches=res.kernel_launches, log=rows,
+                     chol_retries=res.chol_retries)
+
+  # ---- measurement hooks ------------------------------------------------------------------------
+  def bench_launch(self, which, repeats=1):
+    self._ck(self.lib.mcba_bench_launch(self.h, int(which), int(repeats)))
+
+  def bench_info(self, which):
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int32()
+    self._ck(self.lib.mcba_bench_info(self.h, int(which), C.byref(a), C.byref(b), C.byref(c)))
+    return dict(corners=a.value, bytes_per_launch=b.value, launches_per_call=c.value)
+
+
+def format_log(rows):
+  """scipy's verbose=2 iteration table (scipy/optimize/_lsq/common.py print_header_nonlinear /
+  print_iteration_nonlinear), which the reference forwards to its logger (calibration.py:208)."""
+  lines = ["{:^15}{:^15}{:^15}{:^15}{:^15}{:^15}".format("Iteration", "Total nfev", "Cost", "Cost reduction", "Step norm", "Optimality")]
+  for it, nfev, cost, red, step, opt in rows:
+    red_s = " " * 15 if red is None or np.isnan(red) else f"{red:^15.2e}"
+    step_s = " " * 15 if step is None or np.isnan(step) else f"{step:^15.2e}"
+    lines.append(f"{it:^15}{nfev:^15}{cost:^15.4e}{red_s}{step_s}{opt:^15.2e}")
+  return lines
