@@ -1,0 +1,73 @@
+"""Generate golden vectors from the UNMODIFIED reference (imported through tests/refshim).
+
+Run in the build container only (`/root/reference` must exist):
+    python tests/golden/make_golden.py
+For each small synthetic scene it stores the inputs (plain arrays) and what the reference computes:
+  x0            Calibration.param_vec                          (parameters.py:44-46)
+  r0, r1        evaluate(x0), evaluate(x1)                     (calibration.py:204-206)
+  sp_indptr/sp_indices   Calibration.sparsity_matrix (CSR)     (calibration.py:173-196)
+  err_valid     Calibration.reprojection_error                 (calibration.py:134-136)
+  ba_x, ba_cost, ba_nfev, ba_rms   bundle_adjust() result      (calibration.py:199-212)
+The bundle_adjust trajectory of the reference is numerically chaotic (LSMR inner solves on a gauge-
+singular Jacobian: a 1e-13 px perturbation of the residuals changes the final cost in the 5th digit,
+see DESIGN.md), so ba_* are compared with a tolerance that reflects that, not bit-wise.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "refshim"))
+
+from multical_b200 import synthetic  # noqa: E402
+import loader  # noqa: E402
+
+CASES = {
+  "standard_2x6": dict(C=2, F=6, vis=0.5, seed=11, model="standard"),
+  "fisheye_3x5": dict(C=3, F=5, vis=0.5, seed=12, model="fisheye"),
+  "rational_2x5": dict(C=2, F=5, vis=0.5, seed=13, model="rational"),
+  "cube3_3x6": dict(C=3, F=6, vis=0.6, seed=14, model="standard", boards=("cube", 10, 10, 0.04, 3), rig="dome"),
+  "poses_only_2x6": dict(C=2, F=6, vis=0.5, seed=15, model="standard"),
+  "invalid_poses_3x6": dict(C=3, F=6, vis=0.5, seed=16, model="standard"),
+}
+
+
+def main():
+  ref = loader.load()
+  for name, kw in CASES.items():
+    scene = synthetic.make_scene(**kw)
+    if name.startswith("invalid"):
+      scene["frame_valid"][2] = False
+      scene["cam_valid"][1] = False
+    calib = loader.build_calibration(ref, scene)
+    if not name.startswith("poses_only"):
+      calib = calib.enable(cameras=True)
+    x0 = calib.param_vec
+    inl = calib.inliers
+    def evaluate(x):
+      c = calib.with_param_vec(x)
+      return (c.reprojected.points - c.point_table.points)[inl].ravel()
+    rng = np.random.default_rng(100)
+    x1 = x0 + rng.normal(0, 1e-3, x0.size)
+    S = calib.sparsity_matrix.tocsr(); S.sort_indices()
+    out = calib.bundle_adjust()
+    data = dict(
+      model=scene["model"], points=scene["points"], valid=scene["valid"],
+      cam_valid=scene["cam_valid"], frame_valid=scene["frame_valid"], board_valid=scene["board_valid"],
+      board_points=np.stack(scene["board_points"]), K=scene["init"]["K"], dist=scene["init"]["dist"],
+      cam_poses=scene["init"]["cam_poses"], frame_poses=scene["init"]["frame_poses"], board_poses=scene["init"]["board_poses"],
+      image_size=np.array(scene["image_size"]), cameras_enabled=not name.startswith("poses_only"),
+      x0=x0, x1=x1, r0=evaluate(x0), r1=evaluate(x1), sp_indptr=S.indptr, sp_indices=S.indices, sp_shape=np.array(S.shape),
+      err_valid=calib.reprojection_error, ba_x=out.param_vec,
+      ba_cost=0.5 * float(np.sum(evaluate(out.param_vec) ** 2)),
+      ba_rms=float(np.sqrt(np.mean(out.reprojection_error ** 2))))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **data)
+    print(name, "N", int(inl.sum()), "n", x0.size, "cost", data["ba_cost"], "rms", data["ba_rms"], os.path.getsize(path) // 1024, "KB")
+
+
+if __name__ == "__main__":
+  main()

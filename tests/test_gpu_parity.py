@@ -1,0 +1,201 @@
+"""GPU (-m gpu): the CUDA path through the C-ABI against the oracle and the golden vectors.
+
+Tolerances (all fp64 on the device):
+  indexing / parameter layout ........ bit exact
+  residuals at identical x ........... <= 1e-9 px       (observed ~5e-13)
+  J^T J, J^T r vs oracle 3-point FD .. <= 1e-6 relative (FD noise ~1e-8)
+  converged cost vs dense exact-TR oracle (scipy tr_solver='exact', tight tolerances) <= 1e-8 relative
+  gauge-normalised converged parameters vs the same oracle: intrinsics rel 1e-6, poses 1e-6
+  final cost at the reference's default tolerance: never worse than the reference's own result (+1e-6 rel)
+"""
+import numpy as np
+import pytest
+from scipy import optimize
+from scipy.optimize._numdiff import approx_derivative, group_columns
+
+from conftest import GOLDEN_CASES, load_golden, optimize_of
+from multical_b200 import synthetic
+from multical_b200.calibration import from_scene, select_threshold
+from oracle.ba_oracle import Problem, matrix_to_rtvec
+
+pytestmark = pytest.mark.gpu
+
+
+def make(name):
+  scene, z = load_golden(name)
+  calib = from_scene(scene)
+  if bool(z["cameras_enabled"]): calib = calib.enable(cameras=True)
+  return scene, z, calib, Problem.from_scene(scene, optimize=optimize_of(z))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_residuals_match_reference_golden_and_oracle(name):
+  scene, z, calib, prob = make(name)
+  eng = calib._upload(calib.inliers)
+  assert eng.N == z["r0"].size // 2
+  assert np.array_equal(eng.param_vec, z["x0"])                       # layout: bit exact
+  r0 = eng.residuals()
+  assert np.abs(r0 - z["r0"]).max() < 1e-9                            # vs the running reference
+  r1, cost = eng.residuals(z["x1"], with_cost=True)
+  assert np.abs(r1 - z["r1"]).max() < 1e-9
+  assert np.abs(r1 - prob.residuals(z["x1"])).max() < 1e-9           # vs the oracle
+  assert abs(cost - 0.5 * z["r1"] @ z["r1"]) <= 1e-12 * cost
+  assert np.array_equal(eng.param_vec, z["x0"])                       # evaluating at x1 must not move the state
+  err = eng.reprojection_error()
+  assert np.abs(err - np.linalg.norm(z["r0"].reshape(-1, 2), axis=1)).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_reprojection_error_over_valid(name):
+  scene, z, calib, prob = make(name)
+  assert np.abs(calib.reprojection_error - z["err_valid"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_normal_equations_match_finite_differences(name):
+  scene, z, calib, prob = make(name)
+  eng = calib._upload(calib.inliers)
+  x1 = z["x1"]
+  S = prob.sparsity_matrix()
+  J = approx_derivative(prob.residuals, x1, method="3-point", sparsity=(S, group_columns(S))).toarray()
+  r = prob.residuals(x1)
+  H, g = J.T @ J, J.T @ r
+  JtJ, Jtr, cost = eng.linearize(x1)
+  nrm = np.sqrt(np.outer(np.diag(H), np.diag(H)))
+  live = nrm > 0
+  assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  assert np.abs(JtJ[~live]).max(initial=0.0) == 0.0                   # dead columns (skew, invalid poses) stay exactly zero
+  assert np.abs(Jtr - g).max() < 1e-6 * np.abs(g).max()
+  assert abs(cost - 0.5 * r @ r) < 1e-12 * cost
+  assert np.allclose(JtJ, JtJ.T, rtol=0, atol=0)
+
+
+def gauge_normalised(cam_poses, frame_poses, board_poses):
+  """camera 0 and board 0 as the two free gauges (calibration.py:99-112 `with_master`)."""
+  G = cam_poses[0]; Hb = board_poses[0]
+  cams = cam_poses @ np.linalg.inv(G)
+  frames = G @ frame_poses @ Hb
+  boards = np.linalg.inv(Hb) @ board_poses
+  return matrix_to_rtvec(cams), matrix_to_rtvec(frames), matrix_to_rtvec(boards)
+
+
+@pytest.mark.parametrize("name", ["standard_2x6", "fisheye_3x5", "cube3_3x6", "poses_only_2x6", "invalid_poses_3x6"])
+def test_converged_solution_matches_dense_exact_oracle(name):
+  scene, z, calib, prob = make(name)
+  # tight-tolerance oracle: scipy dense exact trust region on the oracle residual with a 3-point Jacobian
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14,
+                               max_nfev=300, method="trf", tr_solver="exact")
+  out = calib.bundle_adjust(tolerance=1e-13, xtol=1e-13, gtol=1e-13, max_iterations=200)
+  res = out.last_solve
+  assert abs(res.cost - ref.cost) <= 1e-8 * ref.cost, (res.cost, ref.cost)
+  # at default tolerance the GPU solve must not be worse than what the reference reached
+  quick = calib.bundle_adjust()
+  assert quick.last_solve.cost <= float(z["ba_cost"]) * (1 + 1e-6)
+  assert quick.last_solve.status in (1, 2, 3, 4)
+  # gauge-normalised parameters
+  o = prob.with_param_vec(ref.x)
+  a = gauge_normalised(out.camera_poses.poses, out.motion.poses, out.board_poses.poses)
+  b = gauge_normalised(o.cam_poses, o.frame_poses, o.board_poses)
+  ok_c, ok_f, ok_b = scene["cam_valid"], scene["frame_valid"], scene["board_valid"]
+  if ok_c[0] and ok_b[0]:
+    assert np.abs(a[0][ok_c] - b[0][ok_c]).max() < 1e-6
+    assert np.abs(a[1][ok_f] - b[1][ok_f]).max() < 1e-6
+    assert np.abs(a[2][ok_b] - b[2][ok_b]).max() < 1e-6
+  if bool(z["cameras_enabled"]):
+    Kg = np.stack([c.intrinsic for c in out.cameras]); dg = np.stack([np.ravel(c.dist) for c in out.cameras])
+    assert np.abs(Kg - o.K)[ok_c].max() < 1e-6 * 1000.0
+    assert np.abs(dg - o.dist.reshape(dg.shape))[ok_c].max() < 1e-5
+  # invalid poses must come back untouched (empty Jacobian columns, parameters.py:145-147)
+  assert np.allclose(out.camera_poses.poses[~ok_c], calib.camera_poses.poses[~ok_c], atol=1e-12)
+  assert np.allclose(out.motion.poses[~ok_f], calib.motion.poses[~ok_f], atol=1e-12)
+
+
+@pytest.mark.parametrize("loss", ["soft_l1", "huber", "cauchy", "arctan"])
+def test_robust_losses_follow_scipy(loss):
+  scene = synthetic.make_scene(C=2, F=6, vis=0.5, seed=31, outlier_fraction=0.03)
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  out = calib.bundle_adjust(loss=loss, f_scale=2.0, tolerance=1e-10, max_iterations=200)
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-12, xtol=1e-12, gtol=1e-12,
+                               max_nfev=400, method="trf", tr_solver="exact", loss=loss, f_scale=2.0)
+  assert abs(out.last_solve.cost - ref.cost) <= 1e-6 * ref.cost, (out.last_solve.cost, ref.cost)
+
+
+def test_outlier_loop_matches_reference_semantics():
+  scene = synthetic.make_scene(C=3, F=8, vis=0.5, seed=41, outlier_fraction=0.02)
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  err, mask = prob.reprojection_error()
+  thr = select_threshold(quantile=0.75, factor=5.0)(err[mask])
+  rejected = calib.reject_outliers(select_threshold(quantile=0.75, factor=5.0)(calib.reprojection_error))
+  assert np.array_equal(rejected.inliers, (err < thr) & mask)          # same inlier set as the reference rule
+  final = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=5.0))
+  rms = np.sqrt(np.mean(final.reprojection_inliers ** 2))
+  assert 0.35 < rms < 0.5                                              # 0.3 px noise -> 0.3*sqrt(2) expected
+
+
+def test_fixed_blocks_and_fix_aspect():
+  scene = synthetic.make_scene(C=2, F=6, vis=0.5, seed=51)
+  calib = from_scene(scene).enable(cameras=True, board_poses=False, camera_poses=False)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True, board_poses=False, camera_poses=False))
+  eng = calib._upload(calib.inliers)
+  assert np.array_equal(eng.param_vec, prob.param_vec)
+  x1 = prob.param_vec + np.random.default_rng(3).normal(0, 1e-3, prob.param_vec.size)
+  assert np.abs(eng.residuals(x1) - prob.residuals(x1)).max() < 1e-9
+  out = calib.bundle_adjust(tolerance=1e-12, max_iterations=100)
+  assert np.allclose(out.camera_poses.poses, calib.camera_poses.poses) and np.allclose(out.board_poses.poses, calib.board_poses.poses)
+  assert out.last_solve.cost < 0.51 * 2 * 0.09 * eng.N * 1.2          # ~ N * sigma^2
+  # fix_aspect: one focal parameter drives fx and fy (camera.py:147-148,159-160)
+  for c in calib.cameras.param_objects: c.fix_aspect = True
+  calib2 = from_scene(scene).enable(cameras=True)
+  for c in calib2.cameras.param_objects: c.fix_aspect = True
+  prob2 = Problem.from_scene(scene, optimize=dict(cameras=True), fix_aspect=True)
+  eng2 = calib2._upload(calib2.inliers)
+  x0 = prob2.param_vec
+  assert np.array_equal(eng2.param_vec, x0)
+  x1 = x0 + np.random.default_rng(4).normal(0, 1e-3, x0.size)
+  assert np.abs(eng2.residuals(x1) - prob2.residuals(x1)).max() < 1e-9
+  S = prob2.sparsity_matrix()
+  J = approx_derivative(prob2.residuals, x1, method="3-point", sparsity=(S, group_columns(S))).toarray()
+  JtJ, Jtr, _ = eng2.linearize(x1)
+  H = J.T @ J
+  nrm = np.sqrt(np.outer(np.diag(H), np.diag(H))); live = nrm > 0
+  assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  out2 = calib2.bundle_adjust(tolerance=1e-10)
+  for c in out2.cameras: assert c.intrinsic[0, 0] == c.intrinsic[1, 1]
+
+
+def test_bad_inputs_raise_like_the_reference():
+  scene = synthetic.make_scene(C=2, F=4, vis=0.5, seed=61)
+  calib = from_scene(scene).enable(cameras=True)
+  eng = calib._upload(calib.inliers)
+  with pytest.raises(AssertionError):
+    eng.set_param_vec(np.zeros(3))                                    # parameters.py:93-95
+  with pytest.raises(ValueError):
+    eng.solve(loss="bogus")
+  bad = from_scene(scene).enable(cameras=True)
+  bad.cameras.param_objects[0].intrinsic[0, 0] = np.nan
+  with pytest.raises(ValueError):                                      # scipy: residuals not finite at x0
+    bad.bundle_adjust()
+
+
+def test_large_scene_properties():
+  """BASELINE cfg2 size: size-independent properties (no oracle run): cost decreases monotonically, RMS lands
+  at sigma*sqrt(2), re-solving from the solution is a fixed point, gradient is ~0 at the optimum."""
+  scene = synthetic.make_workload("cfg2")
+  calib = from_scene(scene).enable(cameras=True)
+  out = calib.bundle_adjust()
+  costs = [row[2] for row in out.last_solve.log]
+  assert all(b <= a for a, b in zip(costs, costs[1:]))
+  rms = np.sqrt(np.mean(out.reprojection_error ** 2))
+  assert abs(rms - 0.3 * np.sqrt(2)) < 5e-3
+  again = out.bundle_adjust()
+  assert again.last_solve.nfev <= 3 and abs(again.last_solve.cost - out.last_solve.cost) <= 1e-6 * out.last_solve.cost
+  eng = out._upload(out.inliers)
+  JtJ, Jtr, cost = eng.linearize()
+  d = np.sqrt(np.diag(JtJ)); d[d == 0] = 1
+  assert np.abs(Jtr / d).max() < 1e-3 * np.sqrt(2 * cost)

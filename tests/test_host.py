@@ -1,0 +1,113 @@
+"""CPU: host-side logic (parameter plumbing, packing order, C-ABI surface) -- no compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, ROOT, load_golden, optimize_of
+from multical_b200 import _native, parameters, rtvec, synthetic
+from multical_b200.calibration import Calibration, default_optimize, error_stats, from_scene, select_threshold
+from multical_b200.engine import format_log, pack_corners
+from oracle.ba_oracle import Problem
+
+
+def test_cabi_library_exports_every_declared_symbol(build_lib):
+  header = open(os.path.join(ROOT, "include", "mcba.h")).read()
+  declared = sorted(set(re.findall(r"\b(mcba_[a-z_]+)\s*\(", header)))
+  assert len(declared) >= 15
+  lib = _native.load()
+  for sym in declared:
+    assert hasattr(lib, sym), f"libmcba.so does not export {sym}"
+  assert sorted(_native.EXPORTS) == declared
+  assert lib.mcba_version() >= 100
+
+
+def test_engine_fails_loudly_without_gpu(build_lib):
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("a GPU is present")
+  from multical_b200.engine import Engine
+  with pytest.raises(_native.NativeError):
+    Engine(0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_param_vec_layout_matches_reference(name):
+  """Calibration.param_vec must equal the reference's vector bit for bit (parameters.py:104-106,
+  calibration.py:146-161, camera.py:150-155, pose_set.py:51-53)."""
+  scene, z = load_golden(name)
+  calib = from_scene(scene)
+  if bool(z["cameras_enabled"]): calib = calib.enable(cameras=True)
+  assert np.array_equal(calib.param_vec, z["x0"])
+  # round trip through with_param_vec
+  # (the reference drops a perturbed skew back to 0 unless has_skew: camera.py:139-141,163-171)
+  again = calib.with_param_vec(z["x1"])
+  expect = Problem.from_scene(scene, optimize=optimize_of(z)).with_param_vec(z["x1"]).param_vec
+  assert np.allclose(again.param_vec, expect, rtol=0, atol=1e-12)
+  S = calib.sparsity_matrix.tocsr(); S.sort_indices()
+  assert np.array_equal(S.indptr, z["sp_indptr"]) and np.array_equal(S.indices, z["sp_indices"])
+
+
+def test_pack_corners_order_is_boolean_mask_order():
+  scene = synthetic.make_scene(C=2, F=3, vis=0.4, seed=2)
+  idx, obs = pack_corners(scene["valid"], scene["points"])
+  assert np.array_equal(idx, np.argwhere(scene["valid"]))
+  assert np.array_equal(obs, scene["points"][scene["valid"]])
+  lin = np.ravel_multi_index(idx.T, scene["valid"].shape)
+  assert np.all(np.diff(lin) > 0)           # row-major, strictly increasing
+
+
+def test_parameters_split_join_roundtrip():
+  tree = dict(a=np.arange(6.0).reshape(2, 3), b=[np.arange(4.0), np.arange(2.0)])
+  v = parameters.join(tree)
+  assert v.tolist() == [0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 0, 1]
+  back = parameters.split(v * 2, tree)
+  assert back["a"].shape == (2, 3) and back["b"][1].tolist() == [0, 2]
+  with pytest.raises(AssertionError):
+    parameters.split(v[:-1], tree)
+
+
+def test_rtvec_roundtrip():
+  rng = np.random.default_rng(0)
+  rt = rng.normal(0, 0.7, (20, 6))
+  assert np.allclose(rtvec.from_matrix(rtvec.to_matrix(rt)), rt, atol=1e-12)
+
+
+def test_calibration_api_surface():
+  scene = synthetic.make_scene(C=2, F=3, vis=0.4, seed=2)
+  calib = from_scene(scene)
+  assert dict(calib.size) == dict(cameras=2, rig_poses=3, boards=1, points=315)
+  assert calib.optimize == default_optimize and calib.param_vec.size == 6 * (2 + 1 + 3)
+  with pytest.raises(AssertionError):
+    calib.enable(bogus=True)
+  c2 = calib.enable(cameras=True)
+  assert c2.param_vec.size == 6 * 6 + 2 * 10 and calib.optimize["cameras"] is False
+  import pickle
+  c3 = pickle.loads(pickle.dumps(c2))
+  assert np.array_equal(c3.param_vec, c2.param_vec)
+  assert sorted(c2.__getstate__()) == sorted(["cameras", "boards", "point_table", "camera_poses", "board_poses", "motion", "inlier_mask", "optimize"])
+  # with_master keeps the product T_cam T_frame unchanged
+  m = c2.with_master(1)
+  a = c2.camera_poses.poses[:, None] @ c2.motion.poses[None]
+  b = m.camera_poses.poses[:, None] @ m.motion.poses[None]
+  assert np.allclose(a, b, atol=1e-12) and np.allclose(m.camera_poses.poses[1], np.eye(4), atol=1e-12)
+  assert np.isclose(select_threshold(0.5, 2.0)(np.arange(5.0)), 4.0)
+  st = error_stats(np.array([3.0, 4.0]))
+  assert np.isclose(st.rms, np.sqrt(12.5)) and st.n == 2
+  assert error_stats(np.zeros(0)).n == 1         # empty-array guard of the reference (calibration.py:304-306)
+
+
+def test_valid_mask_matches_oracle():
+  scene, z = load_golden("invalid_poses_3x6")
+  calib = from_scene(scene)
+  prob = Problem.from_scene(scene)
+  assert np.array_equal(calib.valid, prob.valid)
+  assert calib.valid.sum() == z["r0"].size // 2
+
+
+def test_log_table_format():
+  lines = format_log([(0, 1, 2.8654e6, float("nan"), float("nan"), 9.18e7), (1, 2, 784.08, 2.86e6, 11.9, 3.22e5)])
+  assert lines[0].split() == ["Iteration", "Total", "nfev", "Cost", "Cost", "reduction", "Step", "norm", "Optimality"]
+  assert lines[1].split() == ["0", "1", "2.8654e+06", "9.18e+07"]
+  assert lines[2].split() == ["1", "2", "7.8408e+02", "2.86e+06", "1.19e+01", "3.22e+05"]
