@@ -1,0 +1,73 @@
+"""Frame sharding across GPUs (one process per GPU).
+
+Every residual depends on exactly one frame pose plus the shared parameters (motion/static_frames.py:16-25),
+so frames are the natural shard: each rank holds a contiguous frame range, its corners and its frame poses, and a
+replica of the shared blocks.  The only data-path exchange is the all-reduce of the reduced (shared-parameter)
+normal equations inside libmcba (NCCL over NVLink); this module is the host plumbing around it."""
+import numpy as np
+
+
+def frame_range(F, rank, world):
+  """Contiguous, balanced [start, stop) of frames owned by `rank`."""
+  base, rem = divmod(F, world)
+  start = rank * base + min(rank, rem)
+  return start, start + base + (1 if rank < rem else 0)
+
+
+def frame_owner(F, world):
+  owner = np.zeros(F, np.int32)
+  for r in range(world):
+    a, b = frame_range(F, r, world)
+    owner[a:b] = r
+  return owner
+
+
+def init_comm(engine, rank, world, group=None):
+  """Create the engine's NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it."""
+  import torch.distributed as dist
+  uid = [engine.comm_unique_id() if rank == 0 else None]
+  dist.broadcast_object_list(uid, src=0, group=group)
+  engine.comm_init(uid[0], rank, world)
+
+
+def shard_calibration(calib, rank, world):
+  """Local view of a Calibration: this rank's frames only (point table, inlier mask, motion poses)."""
+  F = calib.size.rig_poses
+  a, b = frame_range(F, rank, world)
+  pt = calib.point_table
+  make = getattr(type(pt), "create")
+  local_pt = make(points=np.asarray(pt.points)[:, a:b], valid=np.asarray(pt.valid)[:, a:b])
+  mt = calib.motion.pose_table
+  local_motion = calib.motion.copy(pose_table=type(mt).create(poses=np.asarray(mt.poses)[a:b], valid=np.asarray(mt.valid)[a:b]),
+                                   names=None)
+  mask = None if calib.inlier_mask is None else calib.inlier_mask[:, a:b]
+  return calib.copy(point_table=local_pt, motion=local_motion, inlier_mask=mask), (a, b)
+
+
+def gather_frames(local_frame_poses, F, rank, world, group=None):
+  """All-gather the per-rank frame poses back into the full [F,4,4] table (host side, after the solve)."""
+  import torch.distributed as dist
+  parts = [None] * world
+  dist.all_gather_object(parts, np.asarray(local_frame_poses), group=group)
+  out = np.concatenate(parts, axis=0)
+  assert out.shape[0] == F
+  return out
+
+
+def bundle_adjust(calib, group=None, **kwargs):
+  """Multi-GPU `Calibration.bundle_adjust`: call on every rank with the same full Calibration; returns the same
+  full, updated Calibration on every rank."""
+  import torch.distributed as dist
+  from .calibration import get_engine
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  local, (a, b) = shard_calibration(calib, rank, world)
+  eng = get_engine()
+  if getattr(eng, "world", 1) != world:
+    init_comm(eng, rank, world, group)
+  out_local = local.bundle_adjust(**kwargs)
+  poses = gather_frames(out_local.motion.poses, calib.size.rig_poses, rank, world, group)
+  mt = calib.motion.pose_table
+  motion = calib.motion.copy(pose_table=type(mt).create(poses=poses, valid=np.asarray(mt.valid)))
+  out = calib.copy(cameras=out_local.cameras, camera_poses=out_local.camera_poses, board_poses=out_local.board_poses, motion=motion)
+  out.__dict__["last_solve"] = out_local.last_solve
+  return out
