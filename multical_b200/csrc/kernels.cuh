@@ -98,6 +98,7 @@ enum { MODE_COST = 0, MODE_MOMENTS = 1, MODE_RESID = 2, MODE_ERROR = 3 };
 
 constexpr int VIEW_WARPS = 4;          // warps per CTA for k_views
 constexpr double SCIPY_EPS = 2.220446049250313e-16;
+constexpr double TRIGGS_FLOOR = 0.1;
 
 // k_views: one warp per view, lanes stride over the view's corners (one thread per corner per step).
 //   MODE_COST    -> 0.5*sum rho(f)                         (trial-point evaluation, trf.py cost_new)
@@ -172,9 +173,13 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
           cost = 0.5 * fs2 * (r0u + r0v);
           if constexpr (MODE == MODE_MOMENTS) {
             // rho[2] /= f_scale^2 ; J_scale = rho1 + 2 rho2 f^2 = rho1 + 2 rho2' z
+            // scipy floors the Triggs-corrected row scale at machine epsilon (common.py:727), which removes all
+            // curvature of residuals beyond the loss's inflection point and stalls an exact inner solve when most
+            // rows are there (poor initial guess).  We floor it at TRIGGS_FLOOR*rho' instead (a damped IRLS
+            // weight): the gradient J'^T f' = rho' J^T f, hence the minimiser, is the same for any positive floor.
             double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
-            ju = ju < SCIPY_EPS ? SCIPY_EPS : ju;
-            jv = jv < SCIPY_EPS ? SCIPY_EPS : jv;
+            ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
+            jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
             wu = sqrt(ju); wv = sqrt(jv);
             ru *= r1u / wu; rv *= r1v / wv;
           }

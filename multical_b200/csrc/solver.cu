@@ -270,7 +270,7 @@ int mcba_create(int device, mcba_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   cudaFuncSetAttribute(k_expand_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   *out = ctx;
   return MCBA_OK;
 }
@@ -617,7 +617,6 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
 
   double last_reduction = NAN, last_step = NAN;
   int nlog = 0;
-  const bool chol_smem = ((size_t)n_s * n_s + n_s) * sizeof(double) <= 220 * 1024;
   int first = 1;
   while (true) {
     if (n) { k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p); CKL(); }
@@ -653,8 +652,22 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     }
     if (n_s > 0) {
       if (ctx->world > 1) { AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); }
-      const size_t sm = chol_smem ? ((size_t)n_s * n_s + n_s) * sizeof(double) : (size_t)n_s * sizeof(double);
-      k_chol_solve<<<1, CHOL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p, chol_smem ? 1 : 0); CKL();
+      if (n_s <= CHOL_SMALL_MAX) {
+        const size_t sm = ((size_t)n_s * (n_s + 1) + n_s) * sizeof(double);
+        k_chol_small<<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); CKL();
+      } else {
+        k_chol_addreg<<<(n_s + 127) / 128, 128, 0, s>>>(n_s, ctx->S.p, ctx->state.p); CKL();
+        for (int kb = 0; kb < n_s; kb += CHOL_NB) {
+          k_chol_diag<<<1, 256, 0, s>>>(n_s, kb, ctx->S.p, ctx->state.p); CKL();
+          const int rem = n_s - kb - CHOL_NB;
+          if (rem > 0) {
+            k_chol_trsm<<<(rem + 127) / 128, 128, 0, s>>>(n_s, kb, ctx->S.p); CKL();
+            const int t = (rem + 31) / 32;
+            k_chol_syrk<<<dim3(t, t), 256, 0, s>>>(n_s, kb, ctx->S.p); CKL();
+          }
+        }
+        k_chol_substitute<<<1, 1024, (size_t)n_s * sizeof(double), s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->gn.p); CKL();
+      }
     }
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();

@@ -317,68 +317,162 @@ __global__ void k_schur_rhs(int n_s, int F, int chunk_frames, const double* Y, c
   atomicAdd(&rhs[s], -acc);
 }
 
-// Dense SPD solve of the reduced (shared-parameter) system, one CTA:
-//   (S + reg I) p_s = rhs + D_s g_s      -> gn[0..n_s)
-// In-place right-looking Cholesky; the matrix lives in shared memory when it fits (n_s <= CHOL_SMEM_N),
-// otherwise in global memory (L2 resident).
-constexpr int CHOL_THREADS = 1024;
-__global__ void __launch_bounds__(CHOL_THREADS)
-k_chol_solve(int n, double* Sg, const double* rhs, const double* gh, SolverState* st, double* out, int use_smem) {
+// Dense SPD solve of the reduced (shared-parameter) system   (S + reg I) p_s = rhs + D_s g_s  -> gn[0..n_s)
+//  * n_s <= CHOL_SMALL_MAX : one CTA, matrix resident in shared memory (k_chol_small)
+//  * larger                : right-looking blocked Cholesky, NB=32 panels: k_chol_diag (1 CTA) -> k_chol_trsm
+//                            (row chunks) -> k_chol_syrk (tiles), then k_chol_substitute (1 CTA)
+constexpr int CHOL_SMALL_MAX = 160;
+constexpr int CHOL_SMALL_THREADS = 256;
+__global__ void __launch_bounds__(CHOL_SMALL_THREADS)
+k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, SolverState* st, double* out) {
   extern __shared__ double shm[];
-  double* col = shm;                       // n
-  double* A = use_smem ? shm + n : Sg;     // n*n
-  const int tid = threadIdx.x;
+  double* A = shm;                 // n x (n+1) padded rows
+  double* b = shm + (size_t)n * (n + 1);
+  const int ld = n + 1;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const double reg = st->reg;
-  if (use_smem) {
-    for (size_t i = tid; i < (size_t)n * n; i += CHOL_THREADS) A[i] = Sg[i];
-    __syncthreads();
-  }
-  for (int i = tid; i < n; i += CHOL_THREADS) A[(size_t)i * n + i] += reg;
+  for (int o = tid; o < n * n; o += CHOL_SMALL_THREADS) { const int i = o / n, j = o % n; A[i * ld + j] = Sg[o] + (i == j ? reg : 0.0); }
+  for (int i = tid; i < n; i += CHOL_SMALL_THREADS) b[i] = rhs[i] + gh[i];
   __syncthreads();
   for (int k = 0; k < n; k++) {
-    const double akk = A[(size_t)k * n + k];
-    const double piv = sqrt(fmax(akk, 1e-300));
+    const double akk = A[k * ld + k];
     if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
-    const double ip = 1.0 / piv;
+    const double ip = rsqrt(fmax(akk, 1e-300));
     __syncthreads();
-    for (int i = k + tid; i < n; i += CHOL_THREADS) {
-      const double l = (i == k) ? piv : A[(size_t)i * n + k] * ip;
-      A[(size_t)i * n + k] = l;
-      col[i] = l;
-    }
+    for (int i = k + tid; i < n; i += CHOL_SMALL_THREADS) A[i * ld + k] *= ip;      // A[k][k] -> sqrt(akk)
     __syncthreads();
-    // trailing update of the lower triangle: A[i][j] -= l_i l_j  for k < j <= i
-    const int m = n - k - 1;
-    const long total = (long)m * (m + 1) / 2;
-    for (long o = tid; o < total; o += CHOL_THREADS) {
-      // row r (0..m-1) has r+1 entries
-      int r = (int)((sqrt(8.0 * (double)o + 1.0) - 1.0) * 0.5);
-      while ((long)r * (r + 1) / 2 > o) r--;
-      while ((long)(r + 1) * (r + 2) / 2 <= o) r++;
-      const int cidx = (int)(o - (long)r * (r + 1) / 2);
-      const int i = k + 1 + r, j = k + 1 + cidx;
-      A[(size_t)i * n + j] -= col[i] * col[j];
+    for (int i = k + 1 + ty; i < n; i += 16) {
+      const double li = A[i * ld + k];
+      for (int j = k + 1 + tx; j <= i; j += 16) A[i * ld + j] -= li * A[j * ld + k];
     }
     __syncthreads();
   }
-  // forward: L y = b ; backward: L^T x = y   (b = rhs + gh_s); column-oriented, one CTA
-  for (int i = tid; i < n; i += CHOL_THREADS) col[i] = rhs[i] + gh[i];
+  // forward then backward substitution (warp 0; lanes own rows)
+  if (tid < 32) {
+    for (int k = 0; k < n; k++) {
+      const double yk = b[k] / A[k * ld + k];
+      __syncwarp();
+      if (tid == 0) b[k] = yk;
+      for (int i = k + 1 + tid; i < n; i += 32) b[i] -= A[i * ld + k] * yk;
+      __syncwarp();
+    }
+    for (int k = n - 1; k >= 0; k--) {
+      const double xk = b[k] / A[k * ld + k];
+      __syncwarp();
+      if (tid == 0) b[k] = xk;
+      for (int i = tid; i < k; i += 32) b[i] -= A[k * ld + i] * xk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += CHOL_SMALL_THREADS) out[i] = b[i];
+}
+
+constexpr int CHOL_NB = 32;
+// add reg to the diagonal (once, before the blocked factorisation)
+__global__ void k_chol_addreg(int n, double* S, const SolverState* st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) S[(size_t)i * n + i] += st->reg;
+}
+// factor the NB x NB diagonal block at kb (lower), in place
+__global__ void __launch_bounds__(256)
+k_chol_diag(int n, int kb, double* S, SolverState* st) {
+  __shared__ double A[CHOL_NB][CHOL_NB + 1];
+  const int nb = min(CHOL_NB, n - kb);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int o = tid; o < nb * nb; o += 256) A[o / nb][o % nb] = S[(size_t)(kb + o / nb) * n + kb + o % nb];
+  __syncthreads();
+  for (int k = 0; k < nb; k++) {
+    const double akk = A[k][k];
+    if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
+    const double piv = sqrt(fmax(akk, 1e-300));
+    __syncthreads();
+    for (int i = k + tid; i < nb; i += 256) A[i][k] = (i == k) ? piv : A[i][k] / piv;
+    __syncthreads();
+    for (int i = k + 1 + ty; i < nb; i += 16) {
+      const double li = A[i][k];
+      for (int j = k + 1 + tx; j <= i; j += 16) A[i][j] -= li * A[j][k];
+    }
+    __syncthreads();
+  }
+  for (int o = tid; o < nb * nb; o += 256) { const int i = o / nb, j = o % nb; if (j <= i) S[(size_t)(kb + i) * n + kb + j] = A[i][j]; }
+}
+// panel: rows below the diagonal block:  L[i, kb:kb+nb] = A[i, kb:kb+nb] L_kk^-T   (one thread per row)
+__global__ void __launch_bounds__(128)
+k_chol_trsm(int n, int kb, double* S) {
+  __shared__ double L[CHOL_NB][CHOL_NB + 1];
+  const int nb = min(CHOL_NB, n - kb);
+  for (int o = threadIdx.x; o < nb * nb; o += 128) L[o / nb][o % nb] = S[(size_t)(kb + o / nb) * n + kb + o % nb];
+  __syncthreads();
+  const int i = kb + nb + blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  double x[CHOL_NB];
+  double* row = S + (size_t)i * n + kb;
+#pragma unroll
+  for (int j = 0; j < CHOL_NB; j++) {
+    if (j < nb) {
+      double t = row[j];
+#pragma unroll
+      for (int k = 0; k < CHOL_NB; k++) if (k < j) t -= L[j][k] * x[k];
+      x[j] = t / L[j][j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CHOL_NB; j++) if (j < nb) row[j] = x[j];
+}
+// trailing update (lower triangle): A[i][j] -= sum_k L[i][kb+k] L[j][kb+k], 32x32 tiles, 2x2 per thread
+__global__ void __launch_bounds__(256)
+k_chol_syrk(int n, int kb, double* S) {
+  __shared__ double Li[CHOL_NB][CHOL_NB + 1];
+  __shared__ double Lj[CHOL_NB][CHOL_NB + 1];
+  const int nb = min(CHOL_NB, n - kb);
+  const int base = kb + nb;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  const int i0 = base + ti * 32, j0 = base + tj * 32;
+  if (i0 >= n) return;
+  for (int o = threadIdx.x; o < 32 * nb; o += 256) {
+    const int r = o / nb, k = o % nb;
+    Li[r][k] = (i0 + r < n) ? S[(size_t)(i0 + r) * n + kb + k] : 0.0;
+    Lj[r][k] = (j0 + r < n) ? S[(size_t)(j0 + r) * n + kb + k] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int k = 0; k < nb; k++) {
+    const double a0 = Li[ty][k], a1 = Li[ty + 16][k], b0 = Lj[tx][k], b1 = Lj[tx + 16][k];
+    acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+  }
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+      if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[a][b];
+    }
+}
+// substitution with the factor in global memory (lower): one CTA
+__global__ void __launch_bounds__(1024)
+k_chol_substitute(int n, const double* L, const double* rhs, const double* gh, double* out) {
+  extern __shared__ double col[];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += 1024) col[i] = rhs[i] + gh[i];
   __syncthreads();
   for (int k = 0; k < n; k++) {
-    if (tid == 0) col[k] = col[k] / A[(size_t)k * n + k];
+    const double yk = col[k] / L[(size_t)k * n + k];
     __syncthreads();
-    const double yk = col[k];
-    for (int i = k + 1 + tid; i < n; i += CHOL_THREADS) col[i] -= A[(size_t)i * n + k] * yk;
+    if (tid == 0) col[k] = yk;
+    for (int i = k + 1 + tid; i < n; i += 1024) col[i] -= L[(size_t)i * n + k] * yk;
     __syncthreads();
   }
   for (int k = n - 1; k >= 0; k--) {
-    if (tid == 0) col[k] = col[k] / A[(size_t)k * n + k];
+    const double xk = col[k] / L[(size_t)k * n + k];
     __syncthreads();
-    const double xk = col[k];
-    for (int i = tid; i < k; i += CHOL_THREADS) col[i] -= A[(size_t)k * n + i] * xk;
+    if (tid == 0) col[k] = xk;
+    for (int i = tid; i < k; i += 1024) col[i] -= L[(size_t)k * n + i] * xk;
     __syncthreads();
   }
-  for (int i = tid; i < n; i += CHOL_THREADS) out[i] = col[i];
+  for (int i = tid; i < n; i += 1024) out[i] = col[i];
 }
 
 // back-substitution of the eliminated frame blocks: gn_f = L^-T (z_f - Y_f^T gn_s)

@@ -105,6 +105,10 @@ def test_converged_solution_matches_dense_exact_oracle(name):
     assert np.abs(a[2][ok_b] - b[2][ok_b]).max() < 1e-6
   if bool(z["cameras_enabled"]):
     Kg = np.stack([c.intrinsic for c in out.cameras]); dg = np.stack([np.ravel(c.dist) for c in out.cameras])
+    # K[0,1] (skew) is a dead parameter (cv2 ignores it): it must come back exactly as it went in; scipy's dense
+    # SVD step lets it drift by numerical noise, so it is excluded from the comparison with that oracle
+    assert all(c.intrinsic[0, 1] == 0.0 for c in out.cameras)
+    Kg[:, 0, 1] = o.K[:, 0, 1]
     assert np.abs(Kg - o.K)[ok_c].max() < 1e-6 * 1000.0
     assert np.abs(dg - o.dist.reshape(dg.shape))[ok_c].max() < 1e-5
   # invalid poses must come back untouched (empty Jacobian columns, parameters.py:145-147)
@@ -122,7 +126,10 @@ def test_robust_losses_follow_scipy(loss):
   jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
   ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-12, xtol=1e-12, gtol=1e-12,
                                max_nfev=400, method="trf", tr_solver="exact", loss=loss, f_scale=2.0)
-  assert abs(out.last_solve.cost - ref.cost) <= 1e-6 * ref.cost, (out.last_solve.cost, ref.cost)
+  # never worse than scipy's dense exact trust region; equal where that converges (it does not for arctan in 400 nfev)
+  assert out.last_solve.cost <= ref.cost * (1 + 1e-6), (out.last_solve.cost, ref.cost)
+  if ref.status > 0:
+    assert abs(out.last_solve.cost - ref.cost) <= 1e-6 * ref.cost, (out.last_solve.cost, ref.cost)
 
 
 def test_outlier_loop_matches_reference_semantics():
@@ -148,7 +155,11 @@ def test_fixed_blocks_and_fix_aspect():
   assert np.abs(eng.residuals(x1) - prob.residuals(x1)).max() < 1e-9
   out = calib.bundle_adjust(tolerance=1e-12, max_iterations=100)
   assert np.allclose(out.camera_poses.poses, calib.camera_poses.poses) and np.allclose(out.board_poses.poses, calib.board_poses.poses)
-  assert out.last_solve.cost < 0.51 * 2 * 0.09 * eng.N * 1.2          # ~ N * sigma^2
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14,
+                               max_nfev=300, method="trf", tr_solver="exact")
+  assert abs(out.last_solve.cost - ref.cost) <= 1e-8 * ref.cost, (out.last_solve.cost, ref.cost)
   # fix_aspect: one focal parameter drives fx and fy (camera.py:147-148,159-160)
   for c in calib.cameras.param_objects: c.fix_aspect = True
   calib2 = from_scene(scene).enable(cameras=True)
