@@ -1,0 +1,41 @@
+"""torchrun target: frame-sharded solve on WORLD_SIZE GPUs must reproduce the single-GPU solve."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from multical_b200 import distributed as mdist, synthetic
+from multical_b200.calibration import from_scene, get_engine
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ["MCBA_DEVICE"] = str(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+for name, kw in [("cfg1", {}), ("cfg1", dict(model="fisheye", C=3, F=11)), ("cfg2", {}),
+                 ("cfg1", dict(boards=("cube", 10, 10, 0.04, 3), rig="dome", C=5, F=33))]:
+  scene = synthetic.make_workload(name, **kw)
+  calib = from_scene(scene).enable(cameras=True)
+  # single-GPU reference solve: detach the engine from the communicator (world=1), every rank solves redundantly
+  eng = get_engine()
+  eng.comm_init(bytes(128), 0, 1)
+  single = calib.bundle_adjust()
+  ref = [dict(cost=single.last_solve.cost, nfev=single.last_solve.nfev, x=single.param_vec)]
+  t = time.time()
+  out = mdist.bundle_adjust(calib)
+  dt = time.time() - t
+  res = out.last_solve
+  if rank == 0:
+    if ref[0] is not None:
+      rel = abs(res.cost - ref[0]["cost"]) / ref[0]["cost"]
+      dx = np.abs(out.param_vec - ref[0]["x"]).max()
+      print(f"{name} {kw}: single cost {ref[0]['cost']:.9f} nfev {ref[0]['nfev']} | {world} GPUs cost {res.cost:.9f} nfev {res.nfev} "
+            f"rel {rel:.2e} max|dx| {dx:.2e} dev_ms {res.device_ms:.3f} wall {dt:.3f}", flush=True)
+      assert rel < 1e-9 and res.nfev == ref[0]["nfev"] and dx < 1e-6, (rel, dx)
+    else:
+      print(f"{name} {kw}: {world} GPUs cost {res.cost:.9f} nfev {res.nfev} dev_ms {res.device_ms:.3f} wall {dt:.3f}", flush=True)
+      r = calib  # sanity: cost decreased and RMS plausible
+      rms = np.sqrt(2 * res.cost / int(calib.inliers.sum()))
+      assert 0.3 < rms < 0.5, rms
+dist.barrier()
+if rank == 0: print("MULTI_GPU_OK")
+dist.destroy_process_group()

@@ -1,0 +1,94 @@
+"""Frame sharding: host logic on CPU with world_size-2 gloo; the NCCL path itself on >=2 GPUs (-m gpu)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from multical_b200 import distributed as mdist
+from multical_b200 import synthetic
+from multical_b200.calibration import from_scene
+
+
+def test_frame_ranges_partition_all_frames():
+  for F in (1, 7, 200, 1001):
+    for world in (1, 2, 3, 8):
+      ranges = [mdist.frame_range(F, r, world) for r in range(world)]
+      assert ranges[0][0] == 0 and ranges[-1][1] == F
+      assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+      sizes = [b - a for a, b in ranges]
+      assert max(sizes) - min(sizes) <= 1
+      owner = mdist.frame_owner(F, world)
+      assert all((owner[a:b] == r).all() for r, (a, b) in enumerate(ranges))
+
+
+def test_shards_cover_every_corner_exactly_once():
+  scene = synthetic.make_scene(C=3, F=7, vis=0.5, seed=5)
+  calib = from_scene(scene).enable(cameras=True)
+  total, frames = 0, []
+  for r in range(3):
+    local, (a, b) = mdist.shard_calibration(calib, r, 3)
+    assert local.size.rig_poses == b - a and local.size.cameras == 3
+    assert np.array_equal(local.point_table.points, scene["points"][:, a:b])
+    assert np.array_equal(local.motion.poses, calib.motion.poses[a:b])
+    # shared blocks are replicated, frame block is local
+    assert local.param_vec.size == calib.param_vec.size - 6 * (7 - (b - a))
+    total += int(local.inliers.sum()); frames += list(range(a, b))
+  assert total == int(calib.inliers.sum()) and frames == list(range(7))
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["MCBA_ROOT"])
+from multical_b200 import distributed as mdist, synthetic
+from multical_b200.calibration import from_scene
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+scene = synthetic.make_scene(C=2, F=5, vis=0.5, seed=9)
+calib = from_scene(scene)
+local, (a, b) = mdist.shard_calibration(calib, rank, world)
+# each rank perturbs its own frames; the gather must reassemble them in frame order on every rank
+mine = np.asarray(local.motion.poses).copy(); mine[:, 0, 3] += 100.0 * (rank + 1)
+full = mdist.gather_frames(mine, 5, rank, world)
+expect = np.asarray(calib.motion.poses).copy()
+for r in range(world):
+  lo, hi = mdist.frame_range(5, r, world); expect[lo:hi, 0, 3] += 100.0 * (r + 1)
+assert np.array_equal(full, expect)
+# the unique-id broadcast used for the NCCL communicator (object broadcast from rank 0)
+uid = [bytes(range(128)) if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+assert uid[0] == bytes(range(128))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def _free_port():
+  s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def test_gather_and_broadcast_with_gloo_world2(tmp_path):
+  script = tmp_path / "worker.py"; script.write_text(_GLOO_WORKER)
+  env = dict(os.environ, MCBA_ROOT=ROOT)
+  cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", str(_free_port()), str(script)]
+  out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0, out.stdout + out.stderr
+  assert out.stdout.count("ok") == 2
+
+
+@pytest.mark.gpu
+def test_two_gpu_solve_matches_single_gpu():
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+         "--master-port", str(_free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+  assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+  assert "MULTI_GPU_OK" in out.stdout
