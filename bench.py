@@ -139,6 +139,10 @@ def run_ours(args):
   F_total = scene["F"]
   my_frames = mdist.frame_range(F_total, rank, world)
   local_scene = subsample_frames(scene, np.arange(*my_frames)) if world > 1 else scene
+  # the step's inputs live in pinned host memory (the e2e timed region copies them to the device every step)
+  for key in ("points", "valid"):
+    pinned = torch.from_numpy(np.ascontiguousarray(local_scene[key])).pin_memory()
+    local_scene[key] = pinned.numpy()
   calib = from_scene(local_scene).enable(cameras=True)
   eng = get_engine(local)
   stream = torch.cuda.current_stream()
@@ -201,7 +205,8 @@ def run_ours(args):
   e2e_value = n_total * evals_e / t_e2e
   sampler.stop_flag = True; sampler.join(timeout=2)
   n_params = eng.num_params
-  h2d = n_local * (4 * 4 + 16) + int(np.prod(calib.board_points.points.shape)) * 8 + sum(a.size for a in state0) * 8
+  # dense upload: mask (1 B/entry) + observations (16 B/entry) of the [C,F,B,P] table, board points, parameter state
+  h2d = int(calib.inliers.size) * (1 + 16) + int(np.prod(calib.board_points.points.shape)) * 8 + sum(a.size for a in state0) * 8
   d2h = n_params * 8 + 64
 
   if rank != 0:

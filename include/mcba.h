@@ -89,6 +89,13 @@ int  mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc,
                  const int32_t* cam, const int32_t* frame, const int32_t* board, const int32_t* point,
                  const double* obs, const double* board_points);
 
+/* Dense variant (the reference's own wire format): mask uint8[C][F][B][P] = calib.inliers (calibration.py:78-81),
+ * points f64[C][F][B][P][2] = point_table.points (tables.make_point_table, tables.py:68-81).  Packing into the
+ * frame-major corner arrays happens on the device; *n_corners receives the number of selected corners.  The packed
+ * order seen through mcba_residuals is still np.argwhere(mask) order.                                              */
+int  mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* mask, const double* points,
+                       const double* board_points, int64_t* n_corners);
+
 /* full parameter state (also the values of disabled/fixed blocks):
  * cam_rt f64[C][6], board_rt f64[B][6], frame_rt f64[F][6] (PoseSet.params, pose_set.py:51-53),
  * intrinsics f64[C][5+nd] (Camera.params, camera.py:144-155)                                      */

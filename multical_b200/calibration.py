@@ -138,10 +138,7 @@ class Calibration(Parameters):
   def _upload(self, mask, points=None, device=None):
     eng = get_engine(device)
     pts = np.asarray(self.point_table.points) if points is None else points
-    idx, obs = pack_corners(mask, pts)
-    s = self.size
-    eng.upload(self.engine_model, self._optimize_bits(), (s.cameras, s.rig_poses, s.boards, s.points),
-               idx, obs, self.board_points.points)
+    eng.upload_dense(self.engine_model, self._optimize_bits(), mask, pts, self.board_points.points)
     eng.set_params(*self._state_arrays())
     return eng
 

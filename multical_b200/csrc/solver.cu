@@ -12,6 +12,7 @@
 
 #include "../../include/mcba.h"
 #include "solver_kernels.cuh"
+#include "pack_kernels.cuh"
 
 using namespace mcba;
 
@@ -29,6 +30,8 @@ struct NcclApi {
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   bool load(std::string& err) {
     if (lib) return true;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -39,6 +42,8 @@ struct NcclApi {
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+    GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
     if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl is missing symbols"; return false; }
     return true;
   }
@@ -77,6 +82,7 @@ struct mcba_ctx {
   DevBuf<double2> obs; DevBuf<uint16_t> pid; DevBuf<uint32_t> orig;
   DevBuf<int> view_start, view_cam, view_frame, view_board, frame_view_start, cam_view_start, cam_view_list;
   DevBuf<double> board_pts, cam_rt, board_rt, frame_rt, intr;
+  DevBuf<uint8_t> dense_mask; DevBuf<double2> dense_pts; DevBuf<int> scan;
   DevBuf<PoseT> cam_T, frame_T, board_T;
   // trial parameter state
   DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2;
@@ -114,6 +120,8 @@ int allreduce(mcba_ctx* ctx, double* buf, size_t count, int op) {
   return MCBA_OK;
 }
 #define AR(buf, count, op) do { int r_ = allreduce(ctx, buf, count, op); if (r_) return r_; } while (0)
+#define AR_GROUP_BEGIN() do { if (ctx->world > 1 && g_nccl.GroupStart) g_nccl.GroupStart(); } while (0)
+#define AR_GROUP_END() do { if (ctx->world > 1 && g_nccl.GroupEnd) g_nccl.GroupEnd(); } while (0)
 
 int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : 2; }
 
@@ -214,8 +222,10 @@ int linearize(mcba_ctx* ctx, int loss, double f_scale) {
   if (P.n_s > 0) { k_diag<<<(P.n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, P.n_s, ctx->diag_s.p); CKL(); }
   // cross-rank: shared gradient, shared diagonal, cost
   if (ctx->world > 1) {
+    AR_GROUP_BEGIN();
     if (P.n_s > 0) { AR(ctx->g.p, P.n_s, NCCL_SUM); AR(ctx->diag_s.p, P.n_s, NCCL_SUM); }
     AR(ctx->red.p + RED_COST, 1, NCCL_SUM);
+    AR_GROUP_END();
   }
   return MCBA_OK;
 }
@@ -238,7 +248,76 @@ int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two) {
   k_quad<<<nb, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p); CKL();
   // RED_AGG, RED_AGN, RED_ANN are consecutive
   k_sum_partials<<<1, 256, 0, ctx->stream>>>(ctx->quad_part.p, nb, 3, two ? 3 : 1, ctx->red.p + RED_AGG); CKL();
-  if (ctx->world > 1) AR(ctx->red.p + RED_AGG, two ? 3 : 1, NCCL_SUM);
+  return MCBA_OK;     // the caller all-reduces red[RED_AGG ...]
+}
+
+
+// dimensions, variable layout, permutation and every solver buffer that depends on (C,F,B,P,N,V)
+int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V) {
+  const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
+  DeviceProblem& P = ctx->P;
+  P = DeviceProblem{};
+  P.C = C; P.F = F; P.B = B; P.P = Pn; P.model = desc->model; P.nd = model_nd(desc->model);
+  P.kint = 5 + P.nd; P.D = model_D(desc->model); P.T = P.D * (P.D + 1) / 2 + P.D + 1;
+  P.N = N; P.V = V;
+  const int opt = desc->optimize;
+  P.motion_on = (opt & MCBA_OPT_MOTION) ? 1 : 0;
+  P.fix_aspect = (opt & MCBA_OPT_FIX_ASPECT) ? 1 : 0;
+  int off = 0;
+  P.off_cp = (opt & MCBA_OPT_CAMERA_POSES) ? off : -1; if (P.off_cp >= 0) off += 6 * C;
+  P.off_bp = (opt & MCBA_OPT_BOARD_POSES) ? off : -1; if (P.off_bp >= 0) off += 6 * B;
+  P.off_in = (opt & MCBA_OPT_CAMERAS) ? off : -1; if (P.off_in >= 0) off += P.kint * C;
+  P.n_s = off; P.n_f = P.motion_on ? 6 * F : 0; P.n = P.n_s + P.n_f;
+  // internal -> canonical permutation: canonical = [cp | bp | motion | cameras]
+  ctx->perm.assign((size_t)P.n, 0);
+  {
+    int canon = 0;
+    if (P.off_cp >= 0) { for (int i = 0; i < 6 * C; i++) ctx->perm[(size_t)P.off_cp + i] = canon + i; canon += 6 * C; }
+    if (P.off_bp >= 0) { for (int i = 0; i < 6 * B; i++) ctx->perm[(size_t)P.off_bp + i] = canon + i; canon += 6 * B; }
+    if (P.motion_on) { for (int i = 0; i < 6 * F; i++) ctx->perm[(size_t)P.n_s + i] = canon + i; canon += 6 * F; }
+    if (P.off_in >= 0) { for (int i = 0; i < P.kint * C; i++) ctx->perm[(size_t)P.off_in + i] = canon + i; canon += P.kint * C; }
+  }
+
+  CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr.alloc((size_t)C * P.kint));
+  CK(ctx->cam_rt2.alloc((size_t)C * 6)); CK(ctx->board_rt2.alloc((size_t)B * 6)); CK(ctx->frame_rt2.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr2.alloc((size_t)C * P.kint));
+  CK(ctx->cam_T.alloc(C)); CK(ctx->frame_T.alloc(std::max(F, 1))); CK(ctx->board_T.alloc(B));
+  // solver buffers
+  ctx->shared_chunks = std::max(1, std::min(32, (ctx->num_sms * 2) / std::max(C, 1)));
+  if (V / std::max(C, 1) < 64) ctx->shared_chunks = 1;
+  CK(ctx->moments.alloc((size_t)std::max(V, 1) * P.T));
+  CK(ctx->Hss.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1)));
+  CK(ctx->g.alloc((size_t)std::max(P.n, 1)));
+  CK(ctx->Hff.alloc((size_t)std::max(F, 1) * 36));
+  CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
+  CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
+  CK(ctx->Lf.alloc((size_t)std::max(F, 1) * 36)); CK(ctx->zf.alloc((size_t)std::max(F, 1) * 6));
+  CK(ctx->cost_part.alloc((size_t)C * ctx->shared_chunks)); CK(ctx->view_cost.alloc((size_t)std::max(V, 1)));
+  CK(ctx->diag_s.alloc((size_t)std::max(P.n_s, 1)));
+  const size_t nn = (size_t)std::max(P.n, 1);
+  CK(ctx->x.alloc(nn)); CK(ctx->x_new.alloc(nn)); CK(ctx->sinv.alloc(nn)); CK(ctx->d.alloc(nn)); CK(ctx->gh.alloc(nn)); CK(ctx->gn.alloc(nn));
+  CK(ctx->S.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1))); CK(ctx->rhs.alloc((size_t)std::max(P.n_s, 1)));
+  CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
+  CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
+  CK(ctx->state.alloc(1));
+  CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
+  CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
+  CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
+  CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
+
+  P.obs = ctx->obs.p; P.pid = ctx->pid.p; P.orig = ctx->orig.p;
+  P.view_start = ctx->view_start.p; P.view_cam = ctx->view_cam.p; P.view_frame = ctx->view_frame.p; P.view_board = ctx->view_board.p;
+  P.frame_view_start = ctx->frame_view_start.p; P.cam_view_start = ctx->cam_view_start.p; P.cam_view_list = ctx->cam_view_list.p;
+  P.board_pts = ctx->board_pts.p;
+  P.cam_rt = ctx->cam_rt.p; P.board_rt = ctx->board_rt.p; P.frame_rt = ctx->frame_rt.p; P.intr = ctx->intr.p;
+  P.cam_T = ctx->cam_T.p; P.frame_T = ctx->frame_T.p; P.board_T = ctx->board_T.p;
+  REQUIRE(expand_frames_smem(P) <= 200 * 1024 && expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
+  return MCBA_OK;
+}
+int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
+  REQUIRE(desc->C > 0 && desc->F >= 0 && desc->B > 0 && desc->P > 0, MCBA_ERR_ARG, "bad problem dimensions");
+  REQUIRE(desc->P <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
+  REQUIRE(desc->model >= 0 && desc->model <= 3, MCBA_ERR_ARG, "unknown camera model");
+  REQUIRE((int64_t)desc->C * desc->F * desc->B * desc->P < ((int64_t)1 << 31), MCBA_ERR_UNSUPPORTED, "more than 2^31 table entries per rank");
   return MCBA_OK;
 }
 
@@ -316,10 +395,8 @@ int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam
   CK(cudaSetDevice(ctx->device));
   const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
   const int64_t N = desc->N;
-  REQUIRE(C > 0 && F >= 0 && B > 0 && Pn > 0 && N >= 0, MCBA_ERR_ARG, "bad problem dimensions");
-  REQUIRE(Pn <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
-  REQUIRE(N < (int64_t)1 << 31, MCBA_ERR_UNSUPPORTED, "more than 2^31 corners per rank");
-  REQUIRE(desc->model >= 0 && desc->model <= 3, MCBA_ERR_ARG, "unknown camera model");
+  { int r = check_desc(ctx, desc); if (r) return r; }
+  REQUIRE(N >= 0 && N < ((int64_t)1 << 31), MCBA_ERR_UNSUPPORTED, "corner count out of range");
   REQUIRE(N == 0 || (cam && frame && board && point && obs), MCBA_ERR_ARG, "null corner arrays");
   REQUIRE(board_points != nullptr, MCBA_ERR_ARG, "null board points");
 
@@ -366,29 +443,6 @@ int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam
     for (int v = 0; v < V; v++) cvl[(size_t)cur[vcam[v]]++] = v;
   }
 
-  DeviceProblem& P = ctx->P;
-  P = DeviceProblem{};
-  P.C = C; P.F = F; P.B = B; P.P = Pn; P.model = desc->model; P.nd = model_nd(desc->model);
-  P.kint = 5 + P.nd; P.D = model_D(desc->model); P.T = P.D * (P.D + 1) / 2 + P.D + 1;
-  P.N = N; P.V = V;
-  const int opt = desc->optimize;
-  P.motion_on = (opt & MCBA_OPT_MOTION) ? 1 : 0;
-  P.fix_aspect = (opt & MCBA_OPT_FIX_ASPECT) ? 1 : 0;
-  int off = 0;
-  P.off_cp = (opt & MCBA_OPT_CAMERA_POSES) ? off : -1; if (P.off_cp >= 0) off += 6 * C;
-  P.off_bp = (opt & MCBA_OPT_BOARD_POSES) ? off : -1; if (P.off_bp >= 0) off += 6 * B;
-  P.off_in = (opt & MCBA_OPT_CAMERAS) ? off : -1; if (P.off_in >= 0) off += P.kint * C;
-  P.n_s = off; P.n_f = P.motion_on ? 6 * F : 0; P.n = P.n_s + P.n_f;
-  // internal -> canonical permutation: canonical = [cp | bp | motion | cameras]
-  ctx->perm.assign((size_t)P.n, 0);
-  {
-    int canon = 0;
-    if (P.off_cp >= 0) { for (int i = 0; i < 6 * C; i++) ctx->perm[(size_t)P.off_cp + i] = canon + i; canon += 6 * C; }
-    if (P.off_bp >= 0) { for (int i = 0; i < 6 * B; i++) ctx->perm[(size_t)P.off_bp + i] = canon + i; canon += 6 * B; }
-    if (P.motion_on) { for (int i = 0; i < 6 * F; i++) ctx->perm[(size_t)P.n_s + i] = canon + i; canon += 6 * F; }
-    if (P.off_in >= 0) { for (int i = 0; i < P.kint * C; i++) ctx->perm[(size_t)P.off_in + i] = canon + i; canon += P.kint * C; }
-  }
-
 #define UP(buf, vec) do { CK(ctx->buf.alloc((vec).size())); if (!(vec).empty()) CK(cudaMemcpyAsync(ctx->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, ctx->stream)); } while (0)
   UP(obs, h_obs); UP(pid, h_pid); UP(orig, order);
   UP(view_start, vstart); UP(view_cam, vcam); UP(view_frame, vframe); UP(view_board, vboard);
@@ -396,40 +450,59 @@ int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam
 #undef UP
   CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
   CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, ctx->stream));
-  CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr.alloc((size_t)C * P.kint));
-  CK(ctx->cam_rt2.alloc((size_t)C * 6)); CK(ctx->board_rt2.alloc((size_t)B * 6)); CK(ctx->frame_rt2.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr2.alloc((size_t)C * P.kint));
-  CK(ctx->cam_T.alloc(C)); CK(ctx->frame_T.alloc(std::max(F, 1))); CK(ctx->board_T.alloc(B));
-  // solver buffers
-  ctx->shared_chunks = std::max(1, std::min(32, (ctx->num_sms * 2) / std::max(C, 1)));
-  if (V / std::max(C, 1) < 64) ctx->shared_chunks = 1;
-  CK(ctx->moments.alloc((size_t)std::max(V, 1) * P.T));
-  CK(ctx->Hss.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1)));
-  CK(ctx->g.alloc((size_t)std::max(P.n, 1)));
-  CK(ctx->Hff.alloc((size_t)std::max(F, 1) * 36));
-  CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
-  CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
-  CK(ctx->Lf.alloc((size_t)std::max(F, 1) * 36)); CK(ctx->zf.alloc((size_t)std::max(F, 1) * 6));
-  CK(ctx->cost_part.alloc((size_t)C * ctx->shared_chunks)); CK(ctx->view_cost.alloc((size_t)std::max(V, 1)));
-  CK(ctx->diag_s.alloc((size_t)std::max(P.n_s, 1)));
-  const size_t nn = (size_t)std::max(P.n, 1);
-  CK(ctx->x.alloc(nn)); CK(ctx->x_new.alloc(nn)); CK(ctx->sinv.alloc(nn)); CK(ctx->d.alloc(nn)); CK(ctx->gh.alloc(nn)); CK(ctx->gn.alloc(nn));
-  CK(ctx->S.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1))); CK(ctx->rhs.alloc((size_t)std::max(P.n_s, 1)));
-  CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
-  CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
-  CK(ctx->state.alloc(1));
-  CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
-  CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
-  CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
-  CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
-
-  P.obs = ctx->obs.p; P.pid = ctx->pid.p; P.orig = ctx->orig.p;
-  P.view_start = ctx->view_start.p; P.view_cam = ctx->view_cam.p; P.view_frame = ctx->view_frame.p; P.view_board = ctx->view_board.p;
-  P.frame_view_start = ctx->frame_view_start.p; P.cam_view_start = ctx->cam_view_start.p; P.cam_view_list = ctx->cam_view_list.p;
-  P.board_pts = ctx->board_pts.p;
-  P.cam_rt = ctx->cam_rt.p; P.board_rt = ctx->board_rt.p; P.frame_rt = ctx->frame_rt.p; P.intr = ctx->intr.p;
-  P.cam_T = ctx->cam_T.p; P.frame_T = ctx->frame_T.p; P.board_T = ctx->board_T.p;
-  REQUIRE(expand_frames_smem(P) <= 200 * 1024 && expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
+  { int r = setup_problem(ctx, desc, N, V); if (r) return r; }
   CK(cudaStreamSynchronize(ctx->stream));    // host staging vectors go out of scope
+  ctx->uploaded = true;
+  return MCBA_OK;
+}
+
+// Dense variant: the [C,F,B,P] inlier mask and [C,F,B,P,2] observations go to the device as they are and the
+// packing (frame-major order, view records, canonical index map) happens there (pack_kernels.cuh).
+int mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* mask, const double* points,
+                      const double* board_points, int64_t* n_corners) {
+  if (!ctx || !desc) return MCBA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  { int r = check_desc(ctx, desc); if (r) return r; }
+  REQUIRE(mask && points && board_points, MCBA_ERR_ARG, "null dense table");
+  const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
+  const int nv = C * F * B;
+  const size_t dense = (size_t)nv * Pn;
+  cudaStream_t s = ctx->stream;
+  CK(ctx->dense_mask.alloc(std::max<size_t>(dense, 1))); CK(ctx->dense_pts.alloc(std::max<size_t>(dense, 1)));
+  CK(ctx->scan.alloc((size_t)4 * (nv + 1)));
+  if (dense) {
+    CK(cudaMemcpyAsync(ctx->dense_mask.p, mask, dense, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, s));
+  }
+  CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
+  CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
+  int* cnt_can = ctx->scan.p; int* cnt_fm = cnt_can + (nv + 1); int* flag_can = cnt_fm + (nv + 1); int* flag_fm = flag_can + (nv + 1);
+  int totals[2] = {0, 0};
+  if (nv > 0) {
+    k_pack_count<<<(nv * 32 + 255) / 256, 256, 0, s>>>(ctx->dense_mask.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
+    k_scan_exclusive<<<1, 1024, 0, s>>>(cnt_can, nv); CKL();
+    k_scan_exclusive<<<1, 1024, 0, s>>>(cnt_fm, nv); CKL();
+    k_scan_exclusive<<<1, 1024, 0, s>>>(flag_can, nv); CKL();
+    k_scan_exclusive<<<1, 1024, 0, s>>>(flag_fm, nv); CKL();
+    CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  const int64_t N = totals[0]; const int V = totals[1];
+  CK(ctx->obs.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->pid.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->orig.alloc((size_t)std::max<int64_t>(N, 1)));
+  CK(ctx->view_start.alloc((size_t)V + 1)); CK(ctx->view_cam.alloc((size_t)std::max(V, 1))); CK(ctx->view_frame.alloc((size_t)std::max(V, 1))); CK(ctx->view_board.alloc((size_t)std::max(V, 1)));
+  CK(ctx->frame_view_start.alloc((size_t)F + 1)); CK(ctx->cam_view_start.alloc((size_t)C + 1)); CK(ctx->cam_view_list.alloc((size_t)std::max(V, 1)));
+  if (nv > 0) {
+    PackOut o{ctx->obs.p, ctx->pid.p, ctx->orig.p, ctx->view_start.p, ctx->view_cam.p, ctx->view_frame.p, ctx->view_board.p,
+              ctx->frame_view_start.p, ctx->cam_view_start.p, ctx->cam_view_list.p};
+    k_pack_scatter<<<(nv * 32 + 255) / 256, 256, 0, s>>>(ctx->dense_mask.p, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL();
+  } else {
+    CK(cudaMemsetAsync(ctx->view_start.p, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctx->frame_view_start.p, 0, sizeof(int) * (F + 1), s));
+    CK(cudaMemsetAsync(ctx->cam_view_start.p, 0, sizeof(int) * (C + 1), s));
+  }
+  { int r = setup_problem(ctx, desc, N, V); if (r) return r; }
+  CK(cudaStreamSynchronize(s));
+  if (n_corners) *n_corners = N;
   ctx->uploaded = true;
   return MCBA_OK;
 }
@@ -622,7 +695,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (n) { k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p); CKL(); }
     first = 0;
     if (ctx->world > 1) {
-      AR(ctx->red.p + RED_GH2_F, 1, NCCL_SUM); AR(ctx->red.p + RED_XS2_F, 1, NCCL_SUM); AR(ctx->red.p + RED_GMAX_F, 1, NCCL_MAX);
+      AR_GROUP_BEGIN(); AR(ctx->red.p + RED_GH2_F, 2, NCCL_SUM); AR(ctx->red.p + RED_GMAX_F, 1, NCCL_MAX); AR_GROUP_END();
     }
     k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
     CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -633,6 +706,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (h.done || n == 0) break;
 
     r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0); if (r) return r;
+    if (ctx->world > 1) AR(ctx->red.p + RED_AGG, 1, NCCL_SUM);
     k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
     // Schur complement of the frame blocks
     if (n_s > 0) {
@@ -651,7 +725,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       }
     }
     if (n_s > 0) {
-      if (ctx->world > 1) { AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); }
+      if (ctx->world > 1) { AR_GROUP_BEGIN(); AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); AR_GROUP_END(); }
       if (n_s <= CHOL_SMALL_MAX) {
         const size_t sm = ((size_t)n_s * (n_s + 1) + n_s) * sizeof(double);
         k_chol_small<<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); CKL();
@@ -671,8 +745,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     }
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
-    if (ctx->world > 1) { AR(ctx->red.p + RED_DOTGN_F, 1, NCCL_SUM); AR(ctx->red.p + RED_GN2_F, 1, NCCL_SUM); }
     r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1); if (r) return r;
+    if (ctx->world > 1) AR(ctx->red.p + RED_AGG, 5, NCCL_SUM);        // AGG AGN ANN DOTGN_F GN2_F
     k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
 
     // inner loop: shrink the radius until the cost decreases (trf.py)
@@ -687,7 +761,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToDevice, s));
       r = set_state_from_x(ctx, ctx->x_new.p, true); if (r) return r;
       r = trial_cost(ctx, opts->loss, opts->f_scale, true, RED_COSTNEW); if (r) return r;
-      if (ctx->world > 1) { AR(ctx->red.p + RED_COSTNEW, 1, NCCL_SUM); AR(ctx->red.p + RED_STEP2_F, 1, NCCL_SUM); AR(ctx->red.p + RED_XN2_F, 1, NCCL_SUM); }
+      if (ctx->world > 1) AR(ctx->red.p + RED_COSTNEW, 3, NCCL_SUM);   // COSTNEW STEP2_F XN2_F
       k_accept<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));

@@ -26,11 +26,12 @@ struct SolverState {
 // slots of the cross-rank reduction scratch `red` (doubles). Entries marked F hold only the contribution of
 // this rank's frames and are summed (or maxed) over ranks; S entries are computed from replicated data.
 enum {
-  RED_GH2_S = 0, RED_GH2_F, RED_GMAX_S, RED_GMAX_F, RED_XS2_S, RED_XS2_F,      // k_scale
-  RED_AGG,                                                                         // gh^T A gh   (local sum)
-  RED_AGN, RED_ANN, RED_DOTGN_S, RED_DOTGN_F, RED_GN2_S, RED_GN2_F,              // after back-substitution
-  RED_COSTNEW, RED_STEP2_S, RED_STEP2_F, RED_XN2_S, RED_XN2_F,                    // trial step
-  RED_COST,                                                                        // cost at linearisation
+  RED_GH2_F = 0, RED_XS2_F,                                     // k_scale, frame parts        (1 all-reduce, sum)
+  RED_GMAX_F,                                                    // k_scale                     (all-reduce, max)
+  RED_AGG, RED_AGN, RED_ANN, RED_DOTGN_F, RED_GN2_F,           // quadratic forms + dots      (1 all-reduce, sum)
+  RED_COSTNEW, RED_STEP2_F, RED_XN2_F,                          // trial step                  (1 all-reduce, sum)
+  RED_COST,                                                      // cost at the linearisation   (grouped with g_s, diag_s)
+  RED_GH2_S, RED_XS2_S, RED_GMAX_S, RED_DOTGN_S, RED_GN2_S, RED_STEP2_S, RED_XN2_S,   // replicated (shared) parts: never reduced
   RED_COUNT
 };
 

@@ -80,6 +80,25 @@ class Engine:
     self.kint = 5 + nat.DIST_SIZES[model]
     self.N = idx.shape[0]
 
+  def upload_dense(self, model, optimize_bits, mask, points, board_points):
+    """Dense [C,F,B,P] mask + [C,F,B,P,2] observations as the reference holds them (point_table, inliers);
+    the packing into frame-major corner arrays happens on the device (csrc/pack_kernels.cuh)."""
+    mask = np.ascontiguousarray(mask)
+    Cn, F, B, P = mask.shape
+    m8 = mask.view(np.uint8) if mask.dtype == np.bool_ else np.ascontiguousarray(mask, dtype=np.uint8)
+    pts = nat.f64(points)
+    assert pts.shape == (Cn, F, B, P, 2), f"points {pts.shape} do not match mask {mask.shape}"
+    bp = nat.f64(board_points).reshape(B, P, 3)
+    d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], int(optimize_bits), 0)
+    n = C.c_int64()
+    self._ck(self.lib.mcba_upload_dense(self.h, C.byref(d), m8.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts),
+                                        nat.dptr(bp), C.byref(n)))
+    d.N = n.value
+    self.desc = d
+    self.model = model
+    self.kint = 5 + nat.DIST_SIZES[model]
+    self.N = n.value
+
   def set_params(self, cam_rt, board_rt, frame_rt, intrinsics):
     d = self.desc
     cam_rt, board_rt, intrinsics = nat.f64(cam_rt), nat.f64(board_rt), nat.f64(intrinsics)

@@ -210,3 +210,45 @@ def test_large_scene_properties():
   JtJ, Jtr, cost = eng.linearize()
   d = np.sqrt(np.diag(JtJ)); d[d == 0] = 1
   assert np.abs(Jtr / d).max() < 1e-3 * np.sqrt(2 * cost)
+
+
+@pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6", "invalid_poses_3x6"])
+def test_device_packing_equals_host_packing(name):
+  """mcba_upload_dense (mask + dense table, packed on the GPU) and mcba_upload (np.argwhere rows packed on the host)
+  must give the same corner order, residuals and normal equations."""
+  from multical_b200.calibration import get_engine
+  from multical_b200.engine import pack_corners
+  scene, z, calib, prob = make(name)
+  eng = calib._upload(calib.inliers)                 # dense path
+  r_dense = eng.residuals(z["x1"]).copy()
+  H_dense, g_dense, _ = eng.linearize(z["x1"])
+  idx, obs = pack_corners(calib.inliers, np.asarray(calib.point_table.points))
+  s = calib.size
+  eng.upload(calib.engine_model, calib._optimize_bits(), (s.cameras, s.rig_poses, s.boards, s.points), idx, obs, calib.board_points.points)
+  eng.set_params(*calib._state_arrays())
+  assert eng.N == idx.shape[0]
+  assert np.array_equal(eng.residuals(z["x1"]), r_dense)
+  H, g, _ = eng.linearize(z["x1"])
+  assert np.allclose(H, H_dense, rtol=1e-12, atol=0) and np.allclose(g, g_dense, rtol=1e-10, atol=1e-9)
+
+
+def test_empty_and_ragged_inputs():
+  scene = synthetic.make_scene(C=2, F=4, vis=0.5, seed=71)
+  # a camera that sees nothing, a frame that nobody sees, single-corner views
+  scene["valid"][1] = False
+  scene["valid"][:, 2] = False
+  scene["valid"][0, 0, 0, 1:] = False
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  eng = calib._upload(calib.inliers)
+  assert eng.N == int(scene["valid"].sum())
+  assert np.abs(eng.residuals() - prob.residuals()).max() < 1e-9
+  out = calib.bundle_adjust(max_iterations=30)
+  assert np.isfinite(out.last_solve.cost)
+  assert np.allclose(out.motion.poses[2], calib.motion.poses[2]) and np.allclose(out.camera_poses.poses[1], calib.camera_poses.poses[1])
+  # nothing selected at all
+  empty = from_scene(scene).copy(inlier_mask=np.zeros_like(scene["valid"]))
+  eng = empty._upload(empty.inliers)
+  assert eng.N == 0 and eng.residuals().size == 0
+  res = eng.solve(max_nfev=5)
+  assert res.cost == 0.0 and res.status == 1        # gradient is exactly zero -> gtol
