@@ -110,7 +110,11 @@ def test_converged_solution_matches_dense_exact_oracle(name):
     assert all(c.intrinsic[0, 1] == 0.0 for c in out.cameras)
     Kg[:, 0, 1] = o.K[:, 0, 1]
     assert np.abs(Kg - o.K)[ok_c].max() < 1e-6 * 1000.0
-    assert np.abs(dg - o.dist.reshape(dg.shape))[ok_c].max() < 1e-5
+    if scene["model"] != "fisheye":      # fisheye k3,k4 (theta^7, theta^9) are too weakly determined to compare directly
+      assert np.abs(dg - o.dist.reshape(dg.shape))[ok_c].max() < 1e-5
+  # gauge-free check that covers every parameter: both solutions project every valid corner to the same pixel
+  uv_o, _ = o.reprojected()
+  assert np.abs(out.projected.points - uv_o)[calib.valid].max() < 1e-4
   # invalid poses must come back untouched (empty Jacobian columns, parameters.py:145-147)
   assert np.allclose(out.camera_poses.poses[~ok_c], calib.camera_poses.poses[~ok_c], atol=1e-12)
   assert np.allclose(out.motion.poses[~ok_f], calib.motion.poses[~ok_f], atol=1e-12)
