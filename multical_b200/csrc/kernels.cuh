@@ -257,6 +257,142 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_views_mma: the per-view moment accumulation as what it is -- a small fp64 SYRK.  Per 32-corner chunk the warp
+// stages Gt = [G | r] (64 residual rows x NC columns, NC = D+1 padded to a multiple of 8) in shared memory and
+// accumulates M += Gt^T Gt on the fp64 tensor path (mma.sync m8n8k4 "DMMA"; tcgen05 has no fp64 kind).  The 8x8 C
+// fragments ARE the per-view accumulators (2 doubles per lane and tile), so one pass produces all D(D+1)/2 + D
+// moments: no register-limited PART split, no cross-lane reduction.  Same outputs as k_views<MODE_MOMENTS>.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int MMA_KPAD = 68;     // 64 residual rows + 4: (column stride mod 16 doubles) == 4 -> conflict-free fragment loads
+__host__ __device__ constexpr int mma_nc(int model) { return ((model_D(model) + 1 + 7) / 8) * 8; }
+
+template <int MODEL>
+__global__ void __launch_bounds__(VIEW_WARPS * 32)
+k_views_mma(DeviceProblem p, ViewKernelArgs a) {
+  constexpr int ND = model_nd(MODEL);
+  constexpr int D = 10 + ND;
+  constexpr int E = D * (D + 1) / 2;
+  constexpr int T = E + D + 1;
+  constexpr int NC = mma_nc(MODEL);
+  constexpr int NT = NC / 8;
+  constexpr int NPAIR = NT * (NT + 1) / 2;
+  constexpr int KINT = 5 + ND;
+  extern __shared__ double stage_all[];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * VIEW_WARPS + warp;
+  const int nw = gridDim.x * VIEW_WARPS;
+  double* stage = stage_all + (size_t)warp * NC * MMA_KPAD;      // [NC][MMA_KPAD], element (row k, col j) at j*KPAD + k
+  const int grp = lane >> 2, tig = lane & 3;
+
+  for (int v = gw; v < p.V; v += nw) {
+    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
+    const int beg = p.view_start[v], end = p.view_start[v + 1];
+    ViewPose vp;
+    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
+    double k[KINT];
+#pragma unroll
+    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
+    const double* bp = p.board_pts + (size_t)b * p.P * 3;
+
+    double acc[NPAIR][2];
+#pragma unroll
+    for (int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    double cost_acc = 0.0;
+
+    for (int base = beg; base < end; base += 32) {
+      const int idx = base + lane;
+      double gu[NC], gv[NC];
+#pragma unroll
+      for (int i = 0; i < NC; i++) { gu[i] = 0.0; gv[i] = 0.0; }
+      if (idx < end) {
+        const double2 ob = p.obs[idx];
+        const int pi = p.pid[idx];
+        const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
+        double Xc[3];
+        mat3_vec(vp.R, X, Xc);
+        Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+        double u, w_;
+        double Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
+        project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
+        double ru = u - ob.x, rv = w_ - ob.y;
+        double wu = 1.0, wv = 1.0;
+        if (a.loss == 0) {
+          cost_acc += 0.5 * (ru * ru + rv * rv);
+        } else {
+          const double is = 1.0 / a.f_scale, fs2 = a.f_scale * a.f_scale;
+          double zu = ru * is, zv = rv * is;
+          zu *= zu; zv *= zv;
+          double r0u, r1u, r2u, r0v, r1v, r2v;
+          loss_rho(a.loss, zu, r0u, r1u, r2u);
+          loss_rho(a.loss, zv, r0v, r1v, r2v);
+          cost_acc += 0.5 * fs2 * (r0u + r0v);
+          double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
+          ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
+          jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
+          wu = sqrt(ju); wv = sqrt(jv);
+          ru *= r1u / wu; rv *= r1v / wv;
+        }
+        gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
+        gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
+        gu[6] = ku[0] * wu; gu[8] = wu;
+        gv[7] = kv[1] * wv; gv[9] = wv;
+#pragma unroll
+        for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
+        gu[D] = ru; gv[D] = rv;                      // residual column: Gt^T Gt then carries G^T r as well
+      }
+      // stage: rows 2*lane (u) and 2*lane+1 (v); one 16-byte store per column, consecutive lanes -> consecutive addresses
+#pragma unroll
+      for (int j = 0; j < NC; j++)
+        *reinterpret_cast<double2*>(stage + j * MMA_KPAD + 2 * lane) = make_double2(gu[j], gv[j]);
+      __syncwarp();
+      // 16 k-steps of 4 residual rows; fragment of column tile I = Gt[k0 + tig][8 I + grp] serves as A (row tile) and B (col tile)
+#pragma unroll 4
+      for (int ks = 0; ks < 16; ks++) {
+        double fr[NT];
+#pragma unroll
+        for (int I = 0; I < NT; I++) fr[I] = stage[(8 * I + grp) * MMA_KPAD + 4 * ks + tig];
+        int t = 0;
+#pragma unroll
+        for (int I = 0; I < NT; I++)
+#pragma unroll
+          for (int J = I; J < NT; J++) { dmma884(acc[t][0], acc[t][1], fr[I], fr[J]); t++; }
+      }
+      __syncwarp();
+    }
+
+    // ---- write the view's moments in the layout the expand kernels read
+    double* out = a.moments + (size_t)v * T;
+    {
+      int t = 0;
+#pragma unroll
+      for (int I = 0; I < NT; I++)
+#pragma unroll
+        for (int J = I; J < NT; J++) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int i = 8 * I + grp, j = 8 * J + 2 * tig + h;
+            const double val = acc[t][h];
+            if (i < D && j < D && i <= j) out[tri_index(D, i, j)] = val;
+            else if (i < D && j == D) out[E + i] = val;
+          }
+          t++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
+    if (lane == 0) out[T - 1] = cost_acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Block maps shared by the two expand kernels.
 struct SolverBuffers {
   double* moments;   // [V][T]

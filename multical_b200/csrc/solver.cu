@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -75,6 +76,7 @@ struct mcba_ctx {
   ncclComm_t comm = nullptr;
   int launches = 0;
   int num_sms = 148;
+  bool use_mma = true;    // per-view moments on the fp64 tensor path (MCBA_MOMENTS=fma selects the DFMA kernels)
 
   bool uploaded = false;
   DeviceProblem P{};
@@ -176,6 +178,22 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
   return MCBA_OK;
 }
 
+int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a) {
+  if (!ctx->use_mma) return launch_views<MODE_MOMENTS>(ctx, P, a);
+  const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 16));
+  const int th = VIEW_WARPS * 32;
+  const size_t sm = (size_t)VIEW_WARPS * mma_nc(P.model) * MMA_KPAD * sizeof(double);
+  cudaStream_t s = ctx->stream;
+  switch (P.model) {
+    case MODEL_STANDARD: k_views_mma<MODEL_STANDARD><<<blocks, th, sm, s>>>(P, a); break;
+    case MODEL_RATIONAL: k_views_mma<MODEL_RATIONAL><<<blocks, th, sm, s>>>(P, a); break;
+    case MODEL_THIN_PRISM: k_views_mma<MODEL_THIN_PRISM><<<blocks, th, sm, s>>>(P, a); break;
+    default: k_views_mma<MODEL_FISHEYE><<<blocks, th, sm, s>>>(P, a); break;
+  }
+  CKL();
+  return MCBA_OK;
+}
+
 // DeviceProblem view whose parameter pointers are the trial state
 DeviceProblem with_state(const mcba_ctx* ctx, bool trial) {
   DeviceProblem P = ctx->P;
@@ -210,7 +228,7 @@ int linearize(mcba_ctx* ctx, int loss, double f_scale) {
   SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p};
   cudaStream_t s = ctx->stream;
   ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p;
-  int r = launch_views<MODE_MOMENTS>(ctx, P, a); if (r) return r;
+  int r = launch_moments(ctx, P, a); if (r) return r;
   CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
   CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
   if (P.motion_on && P.F > 0) {
@@ -243,9 +261,10 @@ int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two) {
   const DeviceProblem& P = ctx->P;
   const int nframe = P.motion_on ? P.F : 0;
   const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
-  const int nb = nframe + nsh;
+  const int fb = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
+  const int nb = nframe + nsh;          // number of partial records
   if (nb == 0) return MCBA_OK;
-  k_quad<<<nb, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p); CKL();
+  k_quad<<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p); CKL();
   // RED_AGG, RED_AGN, RED_ANN are consecutive
   k_sum_partials<<<1, 256, 0, ctx->stream>>>(ctx->quad_part.p, nb, 3, two ? 3 : 1, ctx->red.p + RED_AGG); CKL();
   return MCBA_OK;     // the caller all-reduces red[RED_AGG ...]
@@ -347,6 +366,11 @@ int mcba_create(int device, mcba_ctx** out) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
+  { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
+  cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_THIN_PRISM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_expand_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -727,7 +751,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (n_s > 0) {
       if (ctx->world > 1) { AR_GROUP_BEGIN(); AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); AR_GROUP_END(); }
       if (n_s <= CHOL_SMALL_MAX) {
-        const size_t sm = ((size_t)n_s * (n_s + 1) + n_s) * sizeof(double);
+        const size_t sm = ((size_t)n_s * (n_s | 1) + n_s) * sizeof(double);
         k_chol_small<<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); CKL();
       } else {
         k_chol_addreg<<<(n_s + 127) / 128, 128, 0, s>>>(n_s, ctx->S.p, ctx->state.p); CKL();
@@ -804,7 +828,7 @@ int mcba_bench_info(mcba_ctx* ctx, int which, int64_t* corners, int64_t* bytes, 
   const DeviceProblem& P = ctx->P;
   const int np = nparts_for(P.model);
   int64_t per_corner = 18, per_view = 16, l = 1;
-  if (which == MCBA_BENCH_LINEARIZE) { l = np; }
+  if (which == MCBA_BENCH_LINEARIZE) { l = ctx->use_mma ? 1 : np; }
   else if (which == MCBA_BENCH_RESIDUAL) { per_corner = 18 + 4 + 16; }
   if (corners) *corners = P.N;
   if (bytes) *bytes = per_corner * P.N + per_view * P.V;      // per LAUNCH (each PART re-reads the corners)
@@ -820,7 +844,7 @@ int mcba_bench_launch(mcba_ctx* ctx, int which, int repeats) {
   int r = prepare(ctx, P); if (r) return r;
   for (int i = 0; i < repeats; i++) {
     ViewKernelArgs a{}; a.loss = 0; a.f_scale = 1.0;
-    if (which == MCBA_BENCH_LINEARIZE) { a.moments = ctx->moments.p; r = launch_views<MODE_MOMENTS>(ctx, P, a); }
+    if (which == MCBA_BENCH_LINEARIZE) { a.moments = ctx->moments.p; r = launch_moments(ctx, P, a); }
     else if (which == MCBA_BENCH_COST) { a.view_cost = ctx->view_cost.p; r = launch_views<MODE_COST>(ctx, P, a); }
     else { ctx->err = "unsupported bench kernel"; return MCBA_ERR_ARG; }
     if (r) return r;

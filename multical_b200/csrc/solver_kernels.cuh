@@ -117,42 +117,52 @@ __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hff,
 // quadratic forms u^T A v, A = D H D, for (u,u) [, (u,v), (v,v)].  Grid = F frame CTAs + shared CTAs.
 // partial[cta][3].  u, v are scaled-space vectors (gh, gn).
 constexpr int QUAD_THREADS = 128;
+constexpr int QUAD_WARPS = QUAD_THREADS / 32;
+// blocks [0, frame_blocks): one WARP per frame (W_f^T u_s by lane-strided sums + shuffles, then the 6x6 part);
+// remaining blocks: one thread per shared row (column walk of the symmetric H_ss is coalesced).
+// partial[frame or F + shared block][3]
 __global__ void __launch_bounds__(QUAD_THREADS)
 k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, const double* W, const double* d,
        const double* u, const double* v, int two, double* partial) {
   __shared__ double sm[32];
-  __shared__ double tt[12];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nframe = motion_on ? F : 0;
-  double uu = 0, uv = 0, vv = 0;
-  if ((int)blockIdx.x < nframe) {
-    const int f = blockIdx.x;
+  const int frame_blocks = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
+  if ((int)blockIdx.x < frame_blocks) {
+    const int f = blockIdx.x * QUAD_WARPS + warp;
+    if (f >= nframe) return;
     const double* Wf = W + (size_t)f * n_s * 6;
     double tu[6] = {0, 0, 0, 0, 0, 0}, tv[6] = {0, 0, 0, 0, 0, 0};
-    for (int s = tid; s < n_s; s += QUAD_THREADS) {
+    for (int s = lane; s < n_s; s += 32) {
       const double us = d[s] * u[s], vs = two ? d[s] * v[s] : 0.0;
 #pragma unroll
       for (int j = 0; j < 6; j++) { const double w = Wf[s * 6 + j]; tu[j] += w * us; tv[j] += w * vs; }
     }
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-      double r = block_sum(tu[j], sm); if (tid == 0) tt[j] = r;
-      if (two) { r = block_sum(tv[j], sm); if (tid == 0) tt[6 + j] = r; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { tu[j] += __shfl_xor_sync(0xffffffffu, tu[j], o); tv[j] += __shfl_xor_sync(0xffffffffu, tv[j], o); }
     }
-    if (tid == 0) {
-      double uf[6], vf[6];
+    if (lane == 0) {
+      double uf[6], vf[6], uu = 0, uv = 0, vv = 0;
+#pragma unroll
       for (int j = 0; j < 6; j++) { const int i = n_s + 6 * f + j; uf[j] = d[i] * u[i]; vf[j] = two ? d[i] * v[i] : 0.0; }
       const double* H = Hff + (size_t)f * 36;
+#pragma unroll
       for (int i = 0; i < 6; i++) {
         double hu = 0, hv = 0;
+#pragma unroll
         for (int j = 0; j < 6; j++) { hu += H[i * 6 + j] * uf[j]; hv += H[i * 6 + j] * vf[j]; }
-        uu += uf[i] * (hu + 2.0 * tt[i]);
-        if (two) { uv += uf[i] * hv + uf[i] * tt[6 + i] + vf[i] * tt[i]; vv += vf[i] * (hv + 2.0 * tt[6 + i]); }
+        uu += uf[i] * (hu + 2.0 * tu[i]);
+        uv += uf[i] * hv + uf[i] * tv[i] + vf[i] * tu[i];
+        vv += vf[i] * (hv + 2.0 * tv[i]);
       }
-      partial[(size_t)blockIdx.x * 3 + 0] = uu; partial[(size_t)blockIdx.x * 3 + 1] = uv; partial[(size_t)blockIdx.x * 3 + 2] = vv;
+      partial[(size_t)f * 3 + 0] = uu; partial[(size_t)f * 3 + 1] = uv; partial[(size_t)f * 3 + 2] = vv;
     }
   } else {
-    const int i = (blockIdx.x - nframe) * QUAD_THREADS + tid;
+    const int sb = blockIdx.x - frame_blocks;
+    const int i = sb * QUAD_THREADS + tid;
+    double uu = 0, uv = 0, vv = 0;
     if (i < n_s) {
       double hu = 0, hv = 0;
       for (int j = 0; j < n_s; j++) {
@@ -164,9 +174,9 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
       uu = ui * hu; uv = ui * hv; vv = vi * hv;
     }
     double r;
-    r = block_sum(uu, sm); if (tid == 0) partial[(size_t)blockIdx.x * 3 + 0] = r;
-    r = block_sum(uv, sm); if (tid == 0) partial[(size_t)blockIdx.x * 3 + 1] = r;
-    r = block_sum(vv, sm); if (tid == 0) partial[(size_t)blockIdx.x * 3 + 2] = r;
+    r = block_sum(uu, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 0] = r;
+    r = block_sum(uv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 1] = r;
+    r = block_sum(vv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 2] = r;
   }
 }
 
@@ -324,48 +334,106 @@ __global__ void k_schur_rhs(int n_s, int F, int chunk_frames, const double* Y, c
 //                            (row chunks) -> k_chol_syrk (tiles), then k_chol_substitute (1 CTA)
 constexpr int CHOL_SMALL_MAX = 160;
 constexpr int CHOL_SMALL_THREADS = 256;
+constexpr int CHOL_PB = 8;          // panel width of the in-shared-memory factorisation
+// One CTA, matrix resident in shared memory.  Right-looking with 8-wide panels: warp 0 factors the 8x8 diagonal block,
+// every thread solves one row of the panel in registers, the trailing update is 8 FMAs per entry with the thread's
+// own panel row cached in registers -> 3 barriers per 8 columns instead of 3 per column.  Substitution is blocked the
+// same way (8x8 triangle by one thread, parallel update of the remaining right-hand side).
 __global__ void __launch_bounds__(CHOL_SMALL_THREADS)
 k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, SolverState* st, double* out) {
   extern __shared__ double shm[];
-  double* A = shm;                 // n x (n+1) padded rows
-  double* b = shm + (size_t)n * (n + 1);
-  const int ld = n + 1;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ld = n | 1;            // odd leading dimension: conflict-free column walks
+  double* A = shm;                 // n x ld
+  double* b = shm + (size_t)n * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double reg = st->reg;
   for (int o = tid; o < n * n; o += CHOL_SMALL_THREADS) { const int i = o / n, j = o % n; A[i * ld + j] = Sg[o] + (i == j ? reg : 0.0); }
   for (int i = tid; i < n; i += CHOL_SMALL_THREADS) b[i] = rhs[i] + gh[i];
   __syncthreads();
-  for (int k = 0; k < n; k++) {
-    const double akk = A[k * ld + k];
-    if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
-    const double ip = rsqrt(fmax(akk, 1e-300));
+  for (int kb = 0; kb < n; kb += CHOL_PB) {
+    const int nb = min(CHOL_PB, n - kb);
+    if (warp == 0) {               // diagonal block: lane = row inside the block
+      for (int k = 0; k < nb; k++) {
+        const double akk = A[(kb + k) * ld + kb + k];
+        if (lane == 0 && !(akk > 0.0)) st->chol_fail += 1;
+        const double rs = rsqrt(fmax(akk, 1e-300));
+        double l = 0.0;
+        if (lane >= k && lane < nb) { l = A[(kb + lane) * ld + kb + k] * rs; A[(kb + lane) * ld + kb + k] = l; }
+        __syncwarp();
+        if (lane > k && lane < nb)
+          for (int j = k + 1; j <= lane; j++) A[(kb + lane) * ld + kb + j] -= l * A[(kb + j) * ld + kb + k];
+        __syncwarp();
+      }
+    }
     __syncthreads();
-    for (int i = k + tid; i < n; i += CHOL_SMALL_THREADS) A[i * ld + k] *= ip;      // A[k][k] -> sqrt(akk)
+    // panel rows below the block: x = A[i, kb:kb+nb] L_kk^-T
+    for (int i = kb + nb + tid; i < n; i += CHOL_SMALL_THREADS) {
+      double x[CHOL_PB];
+#pragma unroll
+      for (int j = 0; j < CHOL_PB; j++) {
+        if (j < nb) {
+          double t = A[i * ld + kb + j];
+#pragma unroll
+          for (int k = 0; k < CHOL_PB; k++) if (k < j) t -= A[(kb + j) * ld + kb + k] * x[k];
+          x[j] = t / A[(kb + j) * ld + kb + j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CHOL_PB; j++) if (j < nb) A[i * ld + kb + j] = x[j];
+    }
     __syncthreads();
-    for (int i = k + 1 + ty; i < n; i += 16) {
-      const double li = A[i * ld + k];
-      for (int j = k + 1 + tx; j <= i; j += 16) A[i * ld + j] -= li * A[j * ld + k];
+    // trailing update of the lower triangle; thread (ty,tx) covers rows ty+16a, columns tx+16b
+    const int base = kb + nb;
+    const int tx = tid & 15, ty = tid >> 4;
+    for (int i = base + ty; i < n; i += 16) {
+      double li[CHOL_PB];
+#pragma unroll
+      for (int k = 0; k < CHOL_PB; k++) li[k] = k < nb ? A[i * ld + kb + k] : 0.0;
+      for (int j = base + tx; j <= i; j += 16) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < CHOL_PB; k++) if (k < nb) acc += li[k] * A[j * ld + kb + k];
+        A[i * ld + j] -= acc;
+      }
     }
     __syncthreads();
   }
-  // forward then backward substitution (warp 0; lanes own rows)
-  if (tid < 32) {
-    for (int k = 0; k < n; k++) {
-      const double yk = b[k] / A[k * ld + k];
-      __syncwarp();
-      if (tid == 0) b[k] = yk;
-      for (int i = k + 1 + tid; i < n; i += 32) b[i] -= A[i * ld + k] * yk;
-      __syncwarp();
+  // forward substitution L y = b, blocked
+  for (int kb = 0; kb < n; kb += CHOL_PB) {
+    const int nb = min(CHOL_PB, n - kb);
+    if (tid == 0)
+      for (int j = 0; j < nb; j++) {
+        double t = b[kb + j];
+        for (int k = 0; k < j; k++) t -= A[(kb + j) * ld + kb + k] * b[kb + k];
+        b[kb + j] = t / A[(kb + j) * ld + kb + j];
+      }
+    __syncthreads();
+    for (int i = kb + nb + tid; i < n; i += CHOL_SMALL_THREADS) {
+      double t = b[i];
+#pragma unroll
+      for (int k = 0; k < CHOL_PB; k++) if (k < nb) t -= A[i * ld + kb + k] * b[kb + k];
+      b[i] = t;
     }
-    for (int k = n - 1; k >= 0; k--) {
-      const double xk = b[k] / A[k * ld + k];
-      __syncwarp();
-      if (tid == 0) b[k] = xk;
-      for (int i = tid; i < k; i += 32) b[i] -= A[k * ld + i] * xk;
-      __syncwarp();
-    }
+    __syncthreads();
   }
-  __syncthreads();
+  // backward substitution L^T x = y, blocked from the last panel
+  for (int kb = ((n - 1) / CHOL_PB) * CHOL_PB; kb >= 0; kb -= CHOL_PB) {
+    const int nb = min(CHOL_PB, n - kb);
+    if (tid == 0)
+      for (int j = nb - 1; j >= 0; j--) {
+        double t = b[kb + j];
+        for (int k = j + 1; k < nb; k++) t -= A[(kb + k) * ld + kb + j] * b[kb + k];
+        b[kb + j] = t / A[(kb + j) * ld + kb + j];
+      }
+    __syncthreads();
+    for (int i = tid; i < kb; i += CHOL_SMALL_THREADS) {
+      double t = b[i];
+#pragma unroll
+      for (int k = 0; k < CHOL_PB; k++) if (k < nb) t -= A[(kb + k) * ld + i] * b[kb + k];
+      b[i] = t;
+    }
+    __syncthreads();
+  }
   for (int i = tid; i < n; i += CHOL_SMALL_THREADS) out[i] = b[i];
 }
 
