@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcba.so")
+LIB_PATH = os.environ.get("MCBA_LIB", os.path.join(_HERE, "libmcba.so"))     # MCBA_LIB: developer A/B builds only
 
 MODEL_IDS = {"standard": 0, "rational": 1, "thin_prism": 2, "fisheye": 3}
 DIST_SIZES = {"standard": 5, "rational": 8, "thin_prism": 12, "fisheye": 4}

@@ -267,11 +267,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+#ifndef MMA_MIN_CTAS
+#define MMA_MIN_CTAS 4
+#endif
 constexpr int MMA_KPAD = 68;     // 64 residual rows + 4: (column stride mod 16 doubles) == 4 -> conflict-free fragment loads
 __host__ __device__ constexpr int mma_nc(int model) { return ((model_D(model) + 1 + 7) / 8) * 8; }
 
 template <int MODEL>
-__global__ void __launch_bounds__(VIEW_WARPS * 32)
+__global__ void __launch_bounds__(VIEW_WARPS * 32, MMA_MIN_CTAS)
 k_views_mma(DeviceProblem p, ViewKernelArgs a) {
   constexpr int ND = model_nd(MODEL);
   constexpr int D = 10 + ND;
@@ -354,8 +357,9 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
         *reinterpret_cast<double2*>(stage + j * MMA_KPAD + 2 * lane) = make_double2(gu[j], gv[j]);
       __syncwarp();
       // 16 k-steps of 4 residual rows; fragment of column tile I = Gt[k0 + tig][8 I + grp] serves as A (row tile) and B (col tile)
+      const int ksteps = (2 * min(32, end - base) + 3) >> 2;       // ragged last chunk: skip all-zero row groups
 #pragma unroll 4
-      for (int ks = 0; ks < 16; ks++) {
+      for (int ks = 0; ks < ksteps; ks++) {
         double fr[NT];
 #pragma unroll
         for (int I = 0; I < NT; I++) fr[I] = stage[(8 * I + grp) * MMA_KPAD + 4 * ks + tig];
@@ -409,174 +413,251 @@ __device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int loca
   return local < 4 ? local : local + 1;
 }
 
-// k_expand_frames: one CTA per frame.  Turns the per-view moments of the frame's views into
-//   H_ff (6x6), g_f (6) and the coupling W_f (n_s x 6) with every shared block the frame touches.
+// Both expand kernels work warp-per-view: a warp pulls one view's moment record (T doubles) into its private shared
+// memory slice, builds the 6x6 twist maps it needs, and does the small products with lane-owned outputs -- only
+// __syncwarp inside the view loop; warps of a CTA run different views concurrently and meet once at the end.
 constexpr int EXP_THREADS = 128;
+constexpr int EXP_WARPS = EXP_THREADS / 32;
+
+__device__ __forceinline__ void view_chain(const PoseT& pc, const PoseT& pf, double* Rcf, double* tcf) {
+  mat3_mul(pc.R, pf.R, Rcf);
+  mat3_vec(pc.R, pf.t, tcf);
+  tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
+}
+
+// per-warp shared slice of k_expand_frames: Ms[T] | Tm[D*6] | Ac[36] | Af[36] | Ab[36] | Wb[B*36]
+__host__ __device__ inline int expf_warp_doubles(int T, int D, int B) { return T + D * 6 + 108 + B * 36; }
+
+// k_expand_frames: one CTA per frame -> H_ff (6x6), g_f (6) and W_f (n_s x 6).  Warp w owns the cameras c == w (mod
+// EXP_WARPS): the camera-pose and intrinsics rows of W_f are written by exactly one warp (registers, flushed when the
+// camera changes); board-pose rows, H_ff and g_f are per-warp partials summed at the end.
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand_frames(DeviceProblem p, SolverBuffers s) {
   extern __shared__ double sh[];
-  const int D = p.D, T = p.T, n_s = p.n_s;
-  double* Wf = sh;                     // n_s*6
-  double* Ms = Wf + (size_t)n_s * 6;   // T
-  double* Tm = Ms + T;                 // D*6
-  double* Ac = Tm + D * 6;             // 36
+  const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
+  const int E = D * (D + 1) / 2;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wd = expf_warp_doubles(T, D, B);
+  double* Ms = sh + (size_t)warp * wd;
+  double* Tm = Ms + T;
+  double* Ac = Tm + D * 6;
   double* Af = Ac + 36;
   double* Ab = Af + 36;
-  double* Hf = Ab + 36;                // 36
-  double* gf = Hf + 36;                // 6
-  const int f = blockIdx.x, tid = threadIdx.x;
+  double* Wb = Ab + 36;                              // [B][36] partial board rows of this warp
+  double* red = sh + (size_t)EXP_WARPS * wd;        // [EXP_WARPS][42]  H_ff | g_f partials
+  double* Wf = s.W + (size_t)f * n_s * 6;
   for (int i = tid; i < n_s * 6; i += EXP_THREADS) Wf[i] = 0.0;
-  if (tid < 36) Hf[tid] = 0.0;
-  if (tid < 6) gf[tid] = 0.0;
-  __syncthreads();
-  const int E = D * (D + 1) / 2;
+  for (int i = lane; i < B * 36; i += 32) Wb[i] = 0.0;
+  __syncthreads();                                   // W_f zeroed before any warp adds its camera rows
+
+  const int nin = 4 + p.nd;
+  const int ncam_out = 36 + nin * 6;                 // camera pose (6x6) + intrinsics (nin x 6) rows of W_f
+  constexpr int MAXOUT = 5;                          // ceil((36 + 16*6)/32)
+  double hacc0 = 0.0, hacc1 = 0.0;                   // lane-owned H_ff (36) | g_f (6) outputs: o = lane, lane+32
+  double wacc[MAXOUT];
+#pragma unroll
+  for (int i = 0; i < MAXOUT; i++) wacc[i] = 0.0;
+  int cur_cam = -1;
+
+  auto flush_camera = [&](int c) {
+    if (c < 0) return;
+#pragma unroll
+    for (int q = 0; q < MAXOUT; q++) {
+      const int o = lane + 32 * q;
+      if (o < ncam_out) {
+        const double val = wacc[q];
+        if (o < 36) { if (p.off_cp >= 0) Wf[(p.off_cp + 6 * c + o / 6) * 6 + o % 6] = val; }
+        else if (p.off_in >= 0) {
+          const int i = (o - 36) / 6, j = (o - 36) % 6;
+          if (!(p.fix_aspect && i == 1)) Wf[(p.off_in + p.kint * c + intr_param_index(p, i)) * 6 + j] = val;
+        }
+      }
+      wacc[q] = 0.0;
+    }
+  };
+
   const int v0 = p.frame_view_start[f], v1 = p.frame_view_start[f + 1];
   for (int v = v0; v < v1; v++) {
-    const int c = p.view_cam[v], b = p.view_board[v];
-    for (int i = tid; i < T; i += EXP_THREADS) Ms[i] = s.moments[(size_t)v * T + i];
-    if (tid < 3) {
+    const int c = p.view_cam[v];
+    if (c % EXP_WARPS != warp) continue;
+    const int b = p.view_board[v];
+    if (c != cur_cam) { flush_camera(cur_cam); cur_cam = c; }
+    for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
+    if (lane < 3) {
       const PoseT& pc = p.cam_T[c]; const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
       double Rcf[9], tcf[3];
-      mat3_mul(pc.R, pf.R, Rcf);
-      mat3_vec(pc.R, pf.t, tcf);
-      tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
-      if (tid == 0) {
-        const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-        twist_map(I3, pc.JL, pc.t, Ac);
-      } else if (tid == 1) {
-        twist_map(pc.R, pf.JL, tcf, Af);
-      } else {
-        double tb[3];
-        mat3_vec(Rcf, pb.t, tb);
-        tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
-        twist_map(Rcf, pb.JL, tb, Ab);
-      }
+      view_chain(pc, pf, Rcf, tcf);
+      if (lane == 0) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
+      else if (lane == 1) twist_map(pc.R, pf.JL, tcf, Af);
+      else { double tb[3]; mat3_vec(Rcf, pb.t, tb); tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2]; twist_map(Rcf, pb.JL, tb, Ab); }
     }
-    __syncthreads();
-    // Tm = M[:, xi] * Af   (D x 6)
-    for (int o = tid; o < D * 6; o += EXP_THREADS) {
-      const int i = o / 6, j = o % 6;
-      double acc = 0.0;
+    __syncwarp();
+    for (int o = lane; o < D * 6; o += 32) {          // Tm = M[:, xi] Af
+      const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
       for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Af[kk * 6 + j];
       Tm[o] = acc;
     }
-    __syncthreads();
-    // outputs: Hff 36 | gf 6 | W[cp] 36 | W[bp] 36 | W[intr] (4+nd)*6
-    const int nin = 4 + p.nd;
-    const int total = 36 + 6 + 36 + 36 + nin * 6;
-    for (int o = tid; o < total; o += EXP_THREADS) {
-      if (o < 36) {
-        const int i = o / 6, j = o % 6; double acc = 0.0;
+    __syncwarp();
+    // H_ff += Af^T Tm_xi (36) ; g_f += Af^T g_xi (6)
+    {
+      const int o = lane;
+      { const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Tm[kk * 6 + j];
-        Hf[o] += acc;
-      } else if (o < 42) {
-        const int i = o - 36; double acc = 0.0;
+        hacc0 += acc; }
+      const int o2 = lane + 32;
+      if (o2 < 36) { const int i = o2 / 6, j = o2 % 6; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Tm[kk * 6 + j];
+        hacc1 += acc; }
+      else if (o2 < 42) { const int i = o2 - 36; double acc = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Ms[E + kk];
-        gf[i] += acc;
-      } else if (o < 78) {
-        if (p.off_cp >= 0) {
-          const int i = (o - 42) / 6, j = (o - 42) % 6; double acc = 0.0;
+        hacc1 += acc; }
+    }
+    // camera rows: Ac^T Tm_xi (36) | Tm_k (nin x 6, fix_aspect folds fy onto fx)
 #pragma unroll
-          for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * Tm[kk * 6 + j];
-          Wf[(p.off_cp + 6 * c + i) * 6 + j] += acc;
-        }
-      } else if (o < 114) {
-        if (p.off_bp >= 0) {
-          const int i = (o - 78) / 6, j = (o - 78) % 6; double acc = 0.0;
+    for (int q = 0; q < MAXOUT; q++) {
+      const int o = lane + 32 * q;
+      if (o < 36) { const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Tm[kk * 6 + j];
-          Wf[(p.off_bp + 6 * b + i) * 6 + j] += acc;
-        }
-      } else if (p.off_in >= 0) {
-        const int i = (o - 114) / 6, j = (o - 114) % 6;
-        if (!(p.fix_aspect && i == 1)) {
-          double val = Tm[(6 + i) * 6 + j];
-          if (p.fix_aspect && i == 0) val += Tm[(6 + 1) * 6 + j];
-          Wf[(p.off_in + p.kint * c + intr_param_index(p, i)) * 6 + j] += val;
-        }
+        for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * Tm[kk * 6 + j];
+        wacc[q] += acc; }
+      else if (o < ncam_out) {
+        const int i = (o - 36) / 6, j = (o - 36) % 6;
+        double val = Tm[(6 + i) * 6 + j];
+        if (p.fix_aspect && i == 0) val += Tm[(6 + 1) * 6 + j];
+        wacc[q] += val;
       }
     }
-    __syncthreads();
+    // board rows (shared between cameras): per-warp partial
+    if (p.off_bp >= 0) {
+      for (int o = lane; o < 36; o += 32) { const int i = o / 6, j = o % 6; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Tm[kk * 6 + j];
+        Wb[b * 36 + o] += acc; }
+    }
+    __syncwarp();
   }
-  for (int i = tid; i < n_s * 6; i += EXP_THREADS) s.W[(size_t)f * n_s * 6 + i] = Wf[i];
-  if (tid < 36) s.Hff[(size_t)f * 36 + tid] = Hf[tid];
-  if (tid < 6) s.g[n_s + 6 * f + tid] = gf[tid];
+  flush_camera(cur_cam);
+  // ---- meet: sum the per-warp partials
+  red[warp * 42 + lane] = hacc0;
+  if (lane + 32 < 42) red[warp * 42 + lane + 32] = hacc1;
+  __syncthreads();
+  if (tid < 42) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < EXP_WARPS; w++) acc += red[w * 42 + tid];
+    if (tid < 36) s.Hff[(size_t)f * 36 + tid] = acc; else s.g[n_s + 6 * f + tid - 36] = acc;
+  }
+  if (p.off_bp >= 0)
+    for (int o = tid; o < B * 36; o += EXP_THREADS) {
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 0; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + T + D * 6 + 108 + o];
+      const int b = o / 36, i = (o % 36) / 6, j = o % 6;
+      Wf[(p.off_bp + 6 * b + i) * 6 + j] = acc;
+    }
 }
 
-// k_expand_shared: one CTA per (camera, chunk of that camera's views).  Accumulates the camera's own
-// (pose+intrinsics) block as a plain sum of view moments (its twist map is view independent) and the
-// camera-board / board-board blocks per view, then adds them into H_ss / g_s with fp64 atomics.
+// per-warp shared slice of k_expand_shared: Ms[T] | Um[D*6] | Ab[36] | Ub[B*D*6] | Hbb[B*36] | gb[B*6]
+__host__ __device__ inline int exps_warp_doubles(int T, int D, int B) { return T + D * 6 + 36 + B * (D * 6 + 42); }
+
+// k_expand_shared: one CTA per (camera, chunk of that camera's views).  The camera's own (pose+intrinsics) block is a
+// plain sum of moment records (its twist map does not depend on the view) kept lane-distributed in registers; the
+// camera-board and board-board blocks need the per-view board twist map.  Per-warp partials are summed once at the
+// end and added into H_ss / g_s with fp64 atomics.
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
   extern __shared__ double sh[];
   const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
   const int E = D * (D + 1) / 2;
-  double* Msum = sh;                 // T
-  double* Ms = Msum + T;             // T
-  double* Um = Ms + T;               // D*6 (per view)
-  double* Ub = Um + D * 6;           // B * D*6
-  double* Hbb = Ub + (size_t)B * D * 6;  // B*36
-  double* gb = Hbb + B * 36;         // B*6
-  double* Ab = gb + B * 6;           // 36
-  double* Ac = Ab + 36;              // 36
-  const int c = blockIdx.x / chunks, chunk = blockIdx.x % chunks, tid = threadIdx.x;
-  const int nsh = 2 * T + D * 6 + B * D * 6 + B * 36 + B * 6;
-  for (int i = tid; i < nsh; i += EXP_THREADS) sh[i] = 0.0;
-  __syncthreads();
+  const int c = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wd = exps_warp_doubles(T, D, B);
+  double* Ms = sh + (size_t)warp * wd;
+  double* Um = Ms + T;
+  double* Ab = Um + D * 6;
+  double* Ub = Ab + 36;
+  double* Hbb = Ub + (size_t)B * D * 6;
+  double* gb = Hbb + B * 36;
+  double* Msum = sh + (size_t)EXP_WARPS * wd;          // [T] block total
+  double* Ac = Msum + T;                                // 36
+  for (int i = lane; i < B * (D * 6 + 42); i += 32) Ub[i] = 0.0;
+  constexpr int MAXT = 9;                                // ceil(276/32)
+  double macc[MAXT];
+#pragma unroll
+  for (int q = 0; q < MAXT; q++) macc[q] = 0.0;
+  __syncwarp();
+
   const int l0 = p.cam_view_start[c], l1 = p.cam_view_start[c + 1];
   const int per = (l1 - l0 + chunks - 1) / chunks;
   const int a0 = l0 + chunk * per, a1 = min(l1, a0 + per);
   const PoseT& pc = p.cam_T[c];
-  for (int li = a0; li < a1; li++) {
+  for (int li = a0 + warp; li < a1; li += EXP_WARPS) {
     const int v = p.cam_view_list[li];
     const int f = p.view_frame[v], b = p.view_board[v];
-    for (int i = tid; i < T; i += EXP_THREADS) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; Msum[i] += m; }
-    if (tid == 0 && p.off_bp >= 0) {
-      const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
-      double Rcf[9], tcf[3], tb[3];
-      mat3_mul(pc.R, pf.R, Rcf);
-      mat3_vec(pc.R, pf.t, tcf);
-      tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
-      mat3_vec(Rcf, pb.t, tb);
-      tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
-      twist_map(Rcf, pb.JL, tb, Ab);
+#pragma unroll
+    for (int q = 0; q < MAXT; q++) {
+      const int i = lane + 32 * q;
+      if (i < T) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; macc[q] += m; }
     }
-    __syncthreads();
     if (p.off_bp >= 0) {
-      for (int o = tid; o < D * 6; o += EXP_THREADS) {
+      if (lane == 0) {
+        const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
+        double Rcf[9], tcf[3], tb[3];
+        view_chain(pc, pf, Rcf, tcf);
+        mat3_vec(Rcf, pb.t, tb);
+        tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
+        twist_map(Rcf, pb.JL, tb, Ab);
+      }
+      __syncwarp();
+      for (int o = lane; o < D * 6; o += 32) {
         const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Ab[kk * 6 + j];
         Um[o] = acc;
         Ub[(size_t)b * D * 6 + o] += acc;
       }
-      __syncthreads();
-      if (tid < 36) {
-        const int i = tid / 6, j = tid % 6; double acc = 0.0;
+      __syncwarp();
+      for (int o = lane; o < 42; o += 32) {
+        if (o < 36) { const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Um[kk * 6 + j];
-        Hbb[b * 36 + tid] += acc;
-      } else if (tid < 42) {
-        const int i = tid - 36; double acc = 0.0;
+          for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Um[kk * 6 + j];
+          Hbb[b * 36 + o] += acc; }
+        else { const int i = o - 36; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Ms[E + kk];
-        gb[b * 6 + i] += acc;
+          for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Ms[E + kk];
+          gb[b * 6 + i] += acc; }
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
-  // ---- flush
-  if (tid == 0) {
-    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    twist_map(I3, pc.JL, pc.t, Ac);
-    s.cost_part[blockIdx.x] = Msum[T - 1];
-  }
+  // ---- meet: block totals (warp 0's slice becomes the sum)
+#pragma unroll
+  for (int q = 0; q < MAXT; q++) { const int i = lane + 32 * q; if (i < T) Ms[i] = macc[q]; }
   __syncthreads();
-  // Um = Msum[:, xi] * Ac   (D x 6)
-  for (int o = tid; o < D * 6; o += EXP_THREADS) {
+  for (int i = tid; i < T; i += EXP_THREADS) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + i];
+    Msum[i] = acc;
+  }
+  const int nb_part = B * (D * 6 + 42);
+  const int part_off = T + D * 6 + 36;
+  for (int i = tid; i < nb_part; i += EXP_THREADS) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 1; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + part_off + i];
+    sh[part_off + i] += acc;                             // warp 0's Ub | Hbb | gb now hold the block totals
+  }
+  if (tid == 0) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
+  __syncthreads();
+  Um = sh + T;                                           // warp 0's Um, reused by the whole block
+  Ub = sh + part_off; Hbb = Ub + (size_t)B * D * 6; gb = Hbb + B * 36;
+  if (tid == 0) s.cost_part[blockIdx.x] = Msum[T - 1];
+  for (int o = tid; o < D * 6; o += EXP_THREADS) {       // Um = Msum[:, xi] Ac
     const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
     for (int kk = 0; kk < 6; kk++) acc += msym(Msum, D, i, kk) * Ac[kk * 6 + j];
@@ -590,7 +671,6 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
     atomicAdd(&s.Hss[(size_t)i * n_s + j], val);
     if (i != j) atomicAdd(&s.Hss[(size_t)j * n_s + i], val);
   };
-  // camera pose x camera pose (upper triangle) and gradient
   if (cp >= 0) {
     for (int o = tid; o < 36; o += EXP_THREADS) {
       const int i = o / 6, j = o % 6;
@@ -608,13 +688,11 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
     }
   }
   if (in0 >= 0) {
-    // intrinsics x camera pose: Um rows 6..D ; intrinsics x intrinsics: Msum ; gradient
-    for (int o = tid; o < nin * 6; o += EXP_THREADS) {
-      if (cp < 0) break;
-      const int i = o / 6, j = o % 6;
-      atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + cp + j], Um[(6 + i) * 6 + j]);
-      atomicAdd(&s.Hss[(size_t)(cp + j) * n_s + in0 + intr_param_index(p, i)], Um[(6 + i) * 6 + j]);
-    }
+    if (cp >= 0)
+      for (int o = tid; o < nin * 6; o += EXP_THREADS) {
+        const int i = o / 6, j = o % 6;
+        addH(in0 + intr_param_index(p, i), cp + j, Um[(6 + i) * 6 + j]);
+      }
     for (int o = tid; o < nin * nin; o += EXP_THREADS) {
       const int i = o / nin, j = o % nin;
       atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + in0 + intr_param_index(p, j)], msym(Msum, D, 6 + i, 6 + j));
@@ -626,17 +704,16 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
       const int bp = p.off_bp + 6 * b;
       const double* U = Ub + (size_t)b * D * 6;
       if (cp >= 0)
-        for (int o = tid; o < 36; o += EXP_THREADS) {   // camera pose x board pose = Ac^T U_xi
+        for (int o = tid; o < 36; o += EXP_THREADS) {     // camera pose x board pose = Ac^T U_xi
           const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
           for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * U[kk * 6 + j];
-          if (acc != 0.0) { atomicAdd(&s.Hss[(size_t)(cp + i) * n_s + bp + j], acc); atomicAdd(&s.Hss[(size_t)(bp + j) * n_s + cp + i], acc); }
+          if (acc != 0.0) addH(cp + i, bp + j, acc);
         }
       if (in0 >= 0)
-        for (int o = tid; o < nin * 6; o += EXP_THREADS) {  // intrinsics x board pose = U_k
+        for (int o = tid; o < nin * 6; o += EXP_THREADS) { // intrinsics x board pose = U_k
           const int i = o / 6, j = o % 6; const double val = U[(6 + i) * 6 + j];
-          if (val != 0.0) { atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + bp + j], val);
-                            atomicAdd(&s.Hss[(size_t)(bp + j) * n_s + in0 + intr_param_index(p, i)], val); }
+          if (val != 0.0) addH(in0 + intr_param_index(p, i), bp + j, val);
         }
       for (int o = tid; o < 36; o += EXP_THREADS) {
         const double val = Hbb[b * 36 + o];

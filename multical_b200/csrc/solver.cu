@@ -219,8 +219,8 @@ int set_state_from_x(mcba_ctx* ctx, const double* x, bool trial) {
   return prepare(ctx, P);
 }
 
-size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)P.n_s * 6 + P.T + P.D * 6 + 36 * 4 + 6); }
-size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)2 * P.T + P.D * 6 + (size_t)P.B * P.D * 6 + P.B * 36 + P.B * 6 + 72); }
+size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * expf_warp_doubles(P.T, P.D, P.B) + EXP_WARPS * 42); }
+size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exps_warp_doubles(P.T, P.D, P.B) + P.T + 36); }
 
 // linearise at the CURRENT parameter state: moments -> H_ss, g, H_ff, W, cost (red[RED_COST]), diag_s
 int linearize(mcba_ctx* ctx, int loss, double f_scale) {
@@ -373,7 +373,14 @@ int mcba_create(int device, mcba_ctx** out) {
   cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_expand_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(k_chol_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_chol_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   *out = ctx;
   return MCBA_OK;
 }
@@ -751,8 +758,12 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (n_s > 0) {
       if (ctx->world > 1) { AR_GROUP_BEGIN(); AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); AR_GROUP_END(); }
       if (n_s <= CHOL_SMALL_MAX) {
-        const size_t sm = ((size_t)n_s * (n_s | 1) + n_s) * sizeof(double);
-        k_chol_small<<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); CKL();
+        const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
+        const int R = (n_s + 15) / 16;
+#define CS(RR) case RR: k_chol_small<RR><<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); break;
+        switch (R) { CS(1) CS(2) CS(3) CS(4) CS(5) CS(6) CS(7) CS(8) }
+#undef CS
+        CKL();
       } else {
         k_chol_addreg<<<(n_s + 127) / 128, 128, 0, s>>>(n_s, ctx->S.p, ctx->state.p); CKL();
         for (int kb = 0; kb < n_s; kb += CHOL_NB) {

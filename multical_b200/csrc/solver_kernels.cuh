@@ -332,109 +332,110 @@ __global__ void k_schur_rhs(int n_s, int F, int chunk_frames, const double* Y, c
 //  * n_s <= CHOL_SMALL_MAX : one CTA, matrix resident in shared memory (k_chol_small)
 //  * larger                : right-looking blocked Cholesky, NB=32 panels: k_chol_diag (1 CTA) -> k_chol_trsm
 //                            (row chunks) -> k_chol_syrk (tiles), then k_chol_substitute (1 CTA)
-constexpr int CHOL_SMALL_MAX = 160;
+constexpr int CHOL_SMALL_MAX = 128;
 constexpr int CHOL_SMALL_THREADS = 256;
-constexpr int CHOL_PB = 8;          // panel width of the in-shared-memory factorisation
-// One CTA, matrix resident in shared memory.  Right-looking with 8-wide panels: warp 0 factors the 8x8 diagonal block,
-// every thread solves one row of the panel in registers, the trailing update is 8 FMAs per entry with the thread's
-// own panel row cached in registers -> 3 barriers per 8 columns instead of 3 per column.  Substitution is blocked the
-// same way (8x8 triangle by one thread, parallel update of the remaining right-hand side).
+// One CTA of 16x16 threads; the matrix lives in REGISTERS, cyclically distributed: thread (ty,tx) owns A[ty+16p][tx+16q],
+// p,q < R (R = ceil(n/16) <= 8).  Per column: the pivot and the scaled column go through shared memory (2 barriers), the
+// rank-1 update is R*R predicated FMAs on registers.  The factor is then written to shared memory and warp 0 does both
+// substitutions with the right-hand side in registers and one shuffle broadcast per column.
+template <int R>
 __global__ void __launch_bounds__(CHOL_SMALL_THREADS)
 k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, SolverState* st, double* out) {
   extern __shared__ double shm[];
-  const int ld = n | 1;            // odd leading dimension: conflict-free column walks
-  double* A = shm;                 // n x ld
-  double* b = shm + (size_t)n * ld;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ld = n | 1;
+  double* Lm = shm;                       // n x ld   (written after the factorisation)
+  double* colbuf = Lm + (size_t)n * ld;   // n
+  double* invd = colbuf + n;              // n        1 / L_kk
+  double* piv = invd + n;                 // 1 (+1 pad)
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const double reg = st->reg;
-  for (int o = tid; o < n * n; o += CHOL_SMALL_THREADS) { const int i = o / n, j = o % n; A[i * ld + j] = Sg[o] + (i == j ? reg : 0.0); }
-  for (int i = tid; i < n; i += CHOL_SMALL_THREADS) b[i] = rhs[i] + gh[i];
+  double a[R][R];
+#pragma unroll
+  for (int p = 0; p < R; p++)
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      a[p][q] = (i < n && j < n) ? Sg[(size_t)i * n + j] + (i == j ? reg : 0.0) : 0.0;
+    }
+  if (tid == 0) piv[0] = a[0][0];
   __syncthreads();
-  for (int kb = 0; kb < n; kb += CHOL_PB) {
-    const int nb = min(CHOL_PB, n - kb);
-    if (warp == 0) {               // diagonal block: lane = row inside the block
-      for (int k = 0; k < nb; k++) {
-        const double akk = A[(kb + k) * ld + kb + k];
-        if (lane == 0 && !(akk > 0.0)) st->chol_fail += 1;
-        const double rs = rsqrt(fmax(akk, 1e-300));
-        double l = 0.0;
-        if (lane >= k && lane < nb) { l = A[(kb + lane) * ld + kb + k] * rs; A[(kb + lane) * ld + kb + k] = l; }
-        __syncwarp();
-        if (lane > k && lane < nb)
-          for (int j = k + 1; j <= lane; j++) A[(kb + lane) * ld + kb + j] -= l * A[(kb + j) * ld + kb + k];
-        __syncwarp();
+  for (int k = 0; k < n; k++) {
+    const int kq = k >> 4, kt = k & 15;
+    const double akk = piv[0];
+    if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
+    const double rs = rsqrt(fmax(akk, 1e-300));
+    if (tx == kt) {
+#pragma unroll
+      for (int p = 0; p < R; p++) {
+        const int i = ty + 16 * p;
+#pragma unroll
+        for (int q = 0; q < R; q++)
+          if (q == kq && i >= k && i < n) { const double l = a[p][q] * rs; a[p][q] = l; colbuf[i] = l; }
       }
+      if (ty == kt) invd[k] = rs;
     }
     __syncthreads();
-    // panel rows below the block: x = A[i, kb:kb+nb] L_kk^-T
-    for (int i = kb + nb + tid; i < n; i += CHOL_SMALL_THREADS) {
-      double x[CHOL_PB];
+    double ci[R], cj[R];
 #pragma unroll
-      for (int j = 0; j < CHOL_PB; j++) {
-        if (j < nb) {
-          double t = A[i * ld + kb + j];
+    for (int p = 0; p < R; p++) { const int i = ty + 16 * p; ci[p] = (i > k && i < n) ? colbuf[i] : 0.0; }
 #pragma unroll
-          for (int k = 0; k < CHOL_PB; k++) if (k < j) t -= A[(kb + j) * ld + kb + k] * x[k];
-          x[j] = t / A[(kb + j) * ld + kb + j];
-        }
-      }
+    for (int q = 0; q < R; q++) { const int j = tx + 16 * q; cj[q] = (j > k && j < n) ? colbuf[j] : 0.0; }
 #pragma unroll
-      for (int j = 0; j < CHOL_PB; j++) if (j < nb) A[i * ld + kb + j] = x[j];
-    }
-    __syncthreads();
-    // trailing update of the lower triangle; thread (ty,tx) covers rows ty+16a, columns tx+16b
-    const int base = kb + nb;
-    const int tx = tid & 15, ty = tid >> 4;
-    for (int i = base + ty; i < n; i += 16) {
-      double li[CHOL_PB];
+    for (int p = 0; p < R; p++)
 #pragma unroll
-      for (int k = 0; k < CHOL_PB; k++) li[k] = k < nb ? A[i * ld + kb + k] : 0.0;
-      for (int j = base + tx; j <= i; j += 16) {
-        double acc = 0.0;
+      for (int q = 0; q < R; q++) a[p][q] -= ci[p] * cj[q];       // (also touches the unused upper triangle: harmless)
+    // publish the next pivot
+    {
+      const int k1 = k + 1, q1 = k1 >> 4, t1 = k1 & 15;
+      if (k1 < n && ty == t1 && tx == t1) {
 #pragma unroll
-        for (int k = 0; k < CHOL_PB; k++) if (k < nb) acc += li[k] * A[j * ld + kb + k];
-        A[i * ld + j] -= acc;
+        for (int p = 0; p < R; p++) if (p == q1) piv[0] = a[p][p];
       }
     }
     __syncthreads();
   }
-  // forward substitution L y = b, blocked
-  for (int kb = 0; kb < n; kb += CHOL_PB) {
-    const int nb = min(CHOL_PB, n - kb);
-    if (tid == 0)
-      for (int j = 0; j < nb; j++) {
-        double t = b[kb + j];
-        for (int k = 0; k < j; k++) t -= A[(kb + j) * ld + kb + k] * b[kb + k];
-        b[kb + j] = t / A[(kb + j) * ld + kb + j];
-      }
-    __syncthreads();
-    for (int i = kb + nb + tid; i < n; i += CHOL_SMALL_THREADS) {
-      double t = b[i];
+  // factor -> shared memory (lower triangle incl. diagonal)
 #pragma unroll
-      for (int k = 0; k < CHOL_PB; k++) if (k < nb) t -= A[i * ld + kb + k] * b[kb + k];
-      b[i] = t;
-    }
-    __syncthreads();
-  }
-  // backward substitution L^T x = y, blocked from the last panel
-  for (int kb = ((n - 1) / CHOL_PB) * CHOL_PB; kb >= 0; kb -= CHOL_PB) {
-    const int nb = min(CHOL_PB, n - kb);
-    if (tid == 0)
-      for (int j = nb - 1; j >= 0; j--) {
-        double t = b[kb + j];
-        for (int k = j + 1; k < nb; k++) t -= A[(kb + k) * ld + kb + j] * b[kb + k];
-        b[kb + j] = t / A[(kb + j) * ld + kb + j];
-      }
-    __syncthreads();
-    for (int i = tid; i < kb; i += CHOL_SMALL_THREADS) {
-      double t = b[i];
+  for (int p = 0; p < R; p++)
 #pragma unroll
-      for (int k = 0; k < CHOL_PB; k++) if (k < nb) t -= A[(kb + k) * ld + i] * b[kb + k];
-      b[i] = t;
+    for (int q = 0; q < R; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      if (i < n && j <= i) Lm[i * ld + j] = a[p][q];
     }
-    __syncthreads();
+  __syncthreads();
+  if (tid < 32) {
+    constexpr int RS = (R * 16 + 31) / 32;       // rows per lane
+    const int lane = tid;
+    double bs[RS];
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; bs[s2] = i < n ? rhs[i] + gh[i] : 0.0; }
+    // forward: L y = b
+#pragma unroll
+    for (int s1 = 0; s1 < RS; s1++) {
+      for (int kk = 0; kk < 32; kk++) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) break;
+        const double yk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = yk;
+#pragma unroll
+        for (int s2 = s1; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i > k && i < n) bs[s2] -= Lm[i * ld + k] * yk; }
+      }
+    }
+    // backward: L^T x = y
+#pragma unroll
+    for (int s1 = RS - 1; s1 >= 0; s1--) {
+      for (int kk = 31; kk >= 0; kk--) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) continue;
+        const double xk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = xk;
+#pragma unroll
+        for (int s2 = 0; s2 <= s1; s2++) { const int i = lane + 32 * s2; if (i < k) bs[s2] -= Lm[k * ld + i] * xk; }
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i < n) out[i] = bs[s2]; }
   }
-  for (int i = tid; i < n; i += CHOL_SMALL_THREADS) out[i] = b[i];
 }
 
 constexpr int CHOL_NB = 32;
