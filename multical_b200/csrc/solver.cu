@@ -90,7 +90,7 @@ struct mcba_ctx {
   DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2;
   // solver buffers
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
-  DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part;
+  DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
   DevBuf<SolverState> state;
   int shared_chunks = 1;
   std::vector<int> perm;   // internal index -> canonical param_vec index
@@ -315,6 +315,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   const size_t nn = (size_t)std::max(P.n, 1);
   CK(ctx->x.alloc(nn)); CK(ctx->x_new.alloc(nn)); CK(ctx->sinv.alloc(nn)); CK(ctx->d.alloc(nn)); CK(ctx->gh.alloc(nn)); CK(ctx->gn.alloc(nn));
   CK(ctx->S.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1))); CK(ctx->rhs.alloc((size_t)std::max(P.n_s, 1)));
+  CK(ctx->Linv.alloc((size_t)((std::max(P.n_s, 1) + CHOL_NB - 1) / CHOL_NB) * CHOL_NB * CHOL_NB));
   CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
   CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
   CK(ctx->state.alloc(1));
@@ -767,15 +768,16 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       } else {
         k_chol_addreg<<<(n_s + 127) / 128, 128, 0, s>>>(n_s, ctx->S.p, ctx->state.p); CKL();
         for (int kb = 0; kb < n_s; kb += CHOL_NB) {
-          k_chol_diag<<<1, 256, 0, s>>>(n_s, kb, ctx->S.p, ctx->state.p); CKL();
+          k_chol_diag<<<1, 256, 0, s>>>(n_s, kb, ctx->S.p, ctx->Linv.p, ctx->state.p); CKL();
           const int rem = n_s - kb - CHOL_NB;
           if (rem > 0) {
-            k_chol_trsm<<<(rem + 127) / 128, 128, 0, s>>>(n_s, kb, ctx->S.p); CKL();
             const int t = (rem + 31) / 32;
+            k_chol_trsm<<<t, 256, 0, s>>>(n_s, kb, ctx->S.p, ctx->Linv.p); CKL();
             k_chol_syrk<<<dim3(t, t), 256, 0, s>>>(n_s, kb, ctx->S.p); CKL();
           }
         }
-        k_chol_substitute<<<1, 1024, (size_t)n_s * sizeof(double), s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->gn.p); CKL();
+        const int nblk = (n_s + CHOL_NB - 1) / CHOL_NB;
+        k_chol_substitute<<<1, 512, (size_t)nblk * CHOL_NB * sizeof(double), s>>>(n_s, ctx->S.p, ctx->Linv.p, ctx->rhs.p, ctx->gh.p, ctx->gn.p); CKL();
       }
     }
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }

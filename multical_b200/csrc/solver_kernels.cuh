@@ -347,7 +347,9 @@ k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, Solve
   double* colbuf = Lm + (size_t)n * ld;   // n
   double* invd = colbuf + n;              // n        1 / L_kk
   double* piv = invd + n;                 // 1 (+1 pad)
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // column index is the SLOW thread index: all owners of a matrix column sit in one half-warp, so only that warp
+  // executes the pivot / column-scaling code
+  const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
   const double reg = st->reg;
   double a[R][R];
 #pragma unroll
@@ -355,24 +357,21 @@ k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, Solve
 #pragma unroll
     for (int q = 0; q < R; q++) {
       const int i = ty + 16 * p, j = tx + 16 * q;
-      a[p][q] = (i < n && j < n) ? Sg[(size_t)i * n + j] + (i == j ? reg : 0.0) : 0.0;
+      a[p][q] = (i < n && j < n) ? Sg[(size_t)j * n + i] + (i == j ? reg : 0.0) : 0.0;     // S is symmetric: coalesced read
     }
   if (tid == 0) piv[0] = a[0][0];
   __syncthreads();
   for (int k = 0; k < n; k++) {
     const int kq = k >> 4, kt = k & 15;
-    const double akk = piv[0];
-    if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
-    const double rs = rsqrt(fmax(akk, 1e-300));
     if (tx == kt) {
-#pragma unroll
-      for (int p = 0; p < R; p++) {
-        const int i = ty + 16 * p;
-#pragma unroll
-        for (int q = 0; q < R; q++)
-          if (q == kq && i >= k && i < n) { const double l = a[p][q] * rs; a[p][q] = l; colbuf[i] = l; }
-      }
+      const double akk = piv[0];
+      if (ty == kt && !(akk > 0.0)) st->chol_fail += 1;
+      const double rs = rsqrt(fmax(akk, 1e-300));
       if (ty == kt) invd[k] = rs;
+#define MCBA_SCALE_Q(Q) case Q: if constexpr (Q < R) { _Pragma("unroll") for (int p = 0; p < R; p++) { const int i = ty + 16 * p; \
+        if (i >= k && i < n) { const double l = a[p][Q < R ? Q : 0] * rs; a[p][Q < R ? Q : 0] = l; colbuf[i] = l; } } } break;
+      switch (kq) { MCBA_SCALE_Q(0) MCBA_SCALE_Q(1) MCBA_SCALE_Q(2) MCBA_SCALE_Q(3) MCBA_SCALE_Q(4) MCBA_SCALE_Q(5) MCBA_SCALE_Q(6) MCBA_SCALE_Q(7) }
+#undef MCBA_SCALE_Q
     }
     __syncthreads();
     double ci[R], cj[R];
@@ -444,51 +443,112 @@ __global__ void k_chol_addreg(int n, double* S, const SolverState* st) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) S[(size_t)i * n + i] += st->reg;
 }
-// factor the NB x NB diagonal block at kb (lower), in place
+// Factor the 32x32 diagonal block at kb in registers (16x16 threads, 2x2 entries each, same scheme as k_chol_small),
+// write L_kk back (lower) and its inverse to Linv[kb/32] (row-major 32x32, identity-padded for a short last block):
+// the panel solve and both substitutions then become plain matrix products.
 __global__ void __launch_bounds__(256)
-k_chol_diag(int n, int kb, double* S, SolverState* st) {
-  __shared__ double A[CHOL_NB][CHOL_NB + 1];
+k_chol_diag(int n, int kb, double* S, double* Linv_all, SolverState* st) {
+  __shared__ double Lm[CHOL_NB][CHOL_NB + 1];
+  __shared__ double colbuf[CHOL_NB], invd[CHOL_NB], piv[2];
   const int nb = min(CHOL_NB, n - kb);
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int o = tid; o < nb * nb; o += 256) A[o / nb][o % nb] = S[(size_t)(kb + o / nb) * n + kb + o % nb];
+  const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+  double a[2][2];
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      a[p][q] = (i < nb && j < nb) ? (j <= i ? S[(size_t)(kb + i) * n + kb + j] : S[(size_t)(kb + j) * n + kb + i]) : (i == j ? 1.0 : 0.0);
+    }
+  if (tid == 0) piv[0] = a[0][0];
   __syncthreads();
-  for (int k = 0; k < nb; k++) {
-    const double akk = A[k][k];
-    if (tid == 0 && !(akk > 0.0)) st->chol_fail += 1;
-    const double piv = sqrt(fmax(akk, 1e-300));
+  for (int k = 0; k < CHOL_NB; k++) {
+    const int kq = k >> 4, kt = k & 15;
+    if (tx == kt) {
+      const double akk = piv[0];
+      if (ty == kt && k < nb && !(akk > 0.0)) st->chol_fail += 1;
+      const double rs = rsqrt(fmax(akk, 1e-300));
+      if (ty == kt) invd[k] = rs;
+#pragma unroll
+      for (int p = 0; p < 2; p++) {
+        const int i = ty + 16 * p;
+        if (i >= k) {
+          if (kq == 0) { const double l = a[p][0] * rs; a[p][0] = l; colbuf[i] = l; }
+          else { const double l = a[p][1] * rs; a[p][1] = l; colbuf[i] = l; }
+        }
+      }
+    }
     __syncthreads();
-    for (int i = k + tid; i < nb; i += 256) A[i][k] = (i == k) ? piv : A[i][k] / piv;
-    __syncthreads();
-    for (int i = k + 1 + ty; i < nb; i += 16) {
-      const double li = A[i][k];
-      for (int j = k + 1 + tx; j <= i; j += 16) A[i][j] -= li * A[j][k];
+    double ci[2], cj[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) { const int i = ty + 16 * p; ci[p] = i > k ? colbuf[i] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < 2; q++) { const int j = tx + 16 * q; cj[q] = j > k ? colbuf[j] : 0.0; }
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) a[p][q] -= ci[p] * cj[q];
+    {
+      const int k1 = k + 1, q1 = k1 >> 4, t1 = k1 & 15;
+      if (k1 < CHOL_NB && ty == t1 && tx == t1) piv[0] = q1 == 0 ? a[0][0] : a[1][1];
     }
     __syncthreads();
   }
-  for (int o = tid; o < nb * nb; o += 256) { const int i = o / nb, j = o % nb; if (j <= i) S[(size_t)(kb + i) * n + kb + j] = A[i][j]; }
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      Lm[i][j] = j <= i ? a[p][q] : 0.0;
+      if (i < nb && j <= i) S[(size_t)(kb + i) * n + kb + j] = a[p][q];
+    }
+  __syncthreads();
+  // inverse: thread j < 32 solves L z = e_j
+  if (tid < CHOL_NB) {
+    const int j = tid;
+    double z[CHOL_NB];
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; i++) {
+      double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k2 = 0; k2 < CHOL_NB; k2++) if (k2 < i) t -= Lm[i][k2] * z[k2];
+      z[i] = (i >= j) ? t * invd[i] : 0.0;
+    }
+    double* Li = Linv_all + (size_t)(kb / CHOL_NB) * CHOL_NB * CHOL_NB;
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; i++) Li[i * CHOL_NB + j] = z[i];
+  }
 }
-// panel: rows below the diagonal block:  L[i, kb:kb+nb] = A[i, kb:kb+nb] L_kk^-T   (one thread per row)
-__global__ void __launch_bounds__(128)
-k_chol_trsm(int n, int kb, double* S) {
-  __shared__ double L[CHOL_NB][CHOL_NB + 1];
+// panel below the diagonal block: X = A[:, kb:kb+32] L_kk^-T as a product with the block inverse; 32 rows per CTA.
+// Also mirrors the panel into the upper triangle (S[kb+j][i] = X[i][j]) so that L^T is readable row-wise.
+__global__ void __launch_bounds__(256)
+k_chol_trsm(int n, int kb, double* S, const double* Linv_all) {
+  __shared__ double Li[CHOL_NB][CHOL_NB + 1];
+  __shared__ double At[CHOL_NB][CHOL_NB + 1];
   const int nb = min(CHOL_NB, n - kb);
-  for (int o = threadIdx.x; o < nb * nb; o += 128) L[o / nb][o % nb] = S[(size_t)(kb + o / nb) * n + kb + o % nb];
+  const double* Lg = Linv_all + (size_t)(kb / CHOL_NB) * CHOL_NB * CHOL_NB;
+  const int i0 = kb + nb + blockIdx.x * CHOL_NB;
+  for (int o = threadIdx.x; o < CHOL_NB * CHOL_NB; o += 256) {
+    const int r = o / CHOL_NB, c = o % CHOL_NB;
+    Li[r][c] = Lg[o];
+    At[r][c] = (i0 + r < n && c < nb) ? S[(size_t)(i0 + r) * n + kb + c] : 0.0;
+  }
   __syncthreads();
-  const int i = kb + nb + blockIdx.x * 128 + threadIdx.x;
-  if (i >= n) return;
-  double x[CHOL_NB];
-  double* row = S + (size_t)i * n + kb;
+  const int r = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  double x[4] = {0, 0, 0, 0};
+#pragma unroll 8
+  for (int k = 0; k < CHOL_NB; k++) {
+    const double av = At[r][k];
 #pragma unroll
-  for (int j = 0; j < CHOL_NB; j++) {
-    if (j < nb) {
-      double t = row[j];
+    for (int q = 0; q < 4; q++) x[q] += av * Li[cg * 4 + q][k];       // X[i][j] = sum_k A[i][k] Linv[j][k]
+  }
+  if (i0 + r < n) {
 #pragma unroll
-      for (int k = 0; k < CHOL_NB; k++) if (k < j) t -= L[j][k] * x[k];
-      x[j] = t / L[j][j];
+    for (int q = 0; q < 4; q++) {
+      const int j = cg * 4 + q;
+      if (j < nb) { S[(size_t)(i0 + r) * n + kb + j] = x[q]; S[(size_t)(kb + j) * n + i0 + r] = x[q]; }
     }
   }
-#pragma unroll
-  for (int j = 0; j < CHOL_NB; j++) if (j < nb) row[j] = x[j];
 }
 // trailing update (lower triangle): A[i][j] -= sum_k L[i][kb+k] L[j][kb+k], 32x32 tiles, 2x2 per thread
 __global__ void __launch_bounds__(256)
@@ -521,28 +581,57 @@ k_chol_syrk(int n, int kb, double* S) {
       if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[a][b];
     }
 }
-// substitution with the factor in global memory (lower): one CTA
-__global__ void __launch_bounds__(1024)
-k_chol_substitute(int n, const double* L, const double* rhs, const double* gh, double* out) {
-  extern __shared__ double col[];
+// Both substitutions with the factor in global memory (lower = L, strict upper = L^T mirror) and the inverted diagonal
+// blocks: per 32-block a 32x32 product by warp 0, then every thread updates one remaining row with 32 FMAs.
+__global__ void __launch_bounds__(512)
+k_chol_substitute(int n, const double* L, const double* Linv_all, const double* rhs, const double* gh, double* out) {
+  extern __shared__ double bsh[];                    // n (+32 pad)
+  __shared__ double yb[CHOL_NB];
   const int tid = threadIdx.x;
-  for (int i = tid; i < n; i += 1024) col[i] = rhs[i] + gh[i];
+  const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
+  for (int i = tid; i < nblk * CHOL_NB; i += 512) bsh[i] = i < n ? rhs[i] + gh[i] : 0.0;
   __syncthreads();
-  for (int k = 0; k < n; k++) {
-    const double yk = col[k] / L[(size_t)k * n + k];
+  for (int blk = 0; blk < nblk; blk++) {              // forward: L y = b
+    const int kb = blk * CHOL_NB;
+    const double* Li = Linv_all + (size_t)blk * CHOL_NB * CHOL_NB;
+    if (tid < CHOL_NB) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_NB; k++) acc += Li[tid * CHOL_NB + k] * bsh[kb + k];
+      yb[tid] = acc;
+    }
     __syncthreads();
-    if (tid == 0) col[k] = yk;
-    for (int i = k + 1 + tid; i < n; i += 1024) col[i] -= L[(size_t)i * n + k] * yk;
+    if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
+    for (int i = kb + CHOL_NB + tid; i < n; i += 512) {
+      const double* row = L + (size_t)i * n + kb;
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_NB; k++) acc += row[k] * yb[k];
+      bsh[i] -= acc;
+    }
     __syncthreads();
   }
-  for (int k = n - 1; k >= 0; k--) {
-    const double xk = col[k] / L[(size_t)k * n + k];
+  for (int blk = nblk - 1; blk >= 0; blk--) {         // backward: L^T x = y
+    const int kb = blk * CHOL_NB;
+    const double* Li = Linv_all + (size_t)blk * CHOL_NB * CHOL_NB;
+    if (tid < CHOL_NB) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_NB; k++) acc += Li[k * CHOL_NB + tid] * bsh[kb + k];      // (L_kk^-1)^T
+      yb[tid] = acc;
+    }
     __syncthreads();
-    if (tid == 0) col[k] = xk;
-    for (int i = tid; i < k; i += 1024) col[i] -= L[(size_t)k * n + i] * xk;
+    if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
+    const int nbv = min(CHOL_NB, n - kb);
+    for (int i = tid; i < kb; i += 512) {
+      const double* row = L + (size_t)i * n + kb;      // mirrored panel: row[k] = L[kb+k][i]
+      double acc = 0.0;
+      for (int k = 0; k < nbv; k++) acc += row[k] * yb[k];
+      bsh[i] -= acc;
+    }
     __syncthreads();
   }
-  for (int i = tid; i < n; i += 1024) out[i] = col[i];
+  for (int i = tid; i < n; i += 512) out[i] = bsh[i];
 }
 
 // back-substitution of the eliminated frame blocks: gn_f = L^-T (z_f - Y_f^T gn_s)
