@@ -74,6 +74,36 @@ __global__ void k_prepare(DeviceProblem p, const double* cam_rt, const double* b
   *dst = t;
 }
 
+// k_make_trial: trial parameter state = current state with the free blocks replaced by x (internal order), and the
+// pose tables of that state, in one launch.  One thread per pose, then one per camera (intrinsics).
+__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int np = p.C + p.B + p.F;
+  if (i < np) {
+    const double* cur; const double* src = nullptr; double* dst; PoseT* tab;
+    if (i < p.C) { cur = p.cam_rt + 6 * i; dst = cam_o + 6 * i; tab = p.cam_T + i; if (p.off_cp >= 0) src = x + p.off_cp + 6 * i; }
+    else if (i < p.C + p.B) { const int b = i - p.C; cur = p.board_rt + 6 * b; dst = board_o + 6 * b; tab = p.board_T + b; if (p.off_bp >= 0) src = x + p.off_bp + 6 * b; }
+    else { const int f = i - p.C - p.B; cur = p.frame_rt + 6 * f; dst = frame_o + 6 * f; tab = p.frame_T + f; if (p.motion_on) src = x + p.n_s + 6 * f; }
+    if (!src) src = cur;
+    double v[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { v[j] = src[j]; dst[j] = v[j]; }
+    PoseT t;
+    rodrigues(v, t.R, t.JL);
+    t.t[0] = v[3]; t.t[1] = v[4]; t.t[2] = v[5];
+    t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    *tab = t;
+  } else if (i < np + p.C) {
+    const int c = i - np;
+    const double* src = p.off_in >= 0 ? x + p.off_in + p.kint * c : p.intr + p.kint * c;
+    for (int j = 0; j < p.kint; j++) {
+      double v = src[j];
+      if (j == 1 && p.fix_aspect && p.off_in >= 0) v = src[0];      // fy follows fx (camera.py:159-160)
+      intr_o[p.kint * c + j] = v;
+    }
+  }
+}
+
 // compose T_cfb = T_c T_f T_b for one view (every lane of the warp computes the same small product)
 struct ViewPose { double R[9]; double t[3]; };
 __device__ __forceinline__ void compose_view(const PoseT& c, const PoseT& f, const PoseT& b, ViewPose& o) {

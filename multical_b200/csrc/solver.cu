@@ -222,13 +222,18 @@ int set_state_from_x(mcba_ctx* ctx, const double* x, bool trial) {
 size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * expf_warp_doubles(P.T, P.D, P.B) + EXP_WARPS * 42); }
 size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exps_warp_doubles(P.T, P.D, P.B) + P.T + 36); }
 
-// linearise at the CURRENT parameter state: moments -> H_ss, g, H_ff, W, cost (red[RED_COST]), diag_s
-int linearize(mcba_ctx* ctx, int loss, double f_scale) {
+// per-view moment records of the (trial or current) state; the pose tables must already describe that state
+int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial) {
+  DeviceProblem P = with_state(ctx, trial);
+  ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p;
+  return launch_moments(ctx, P, a);
+}
+
+// moment records -> H_ss, g, H_ff, W and the per-CTA cost partials (pose tables = the state the moments were taken at)
+int expand(mcba_ctx* ctx) {
   DeviceProblem P = with_state(ctx, false);
   SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p};
   cudaStream_t s = ctx->stream;
-  ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p;
-  int r = launch_moments(ctx, P, a); if (r) return r;
   CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
   CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
   if (P.motion_on && P.F > 0) {
@@ -236,9 +241,16 @@ int linearize(mcba_ctx* ctx, int loss, double f_scale) {
   }
   const int nb = P.C * ctx->shared_chunks;
   k_expand_shared<<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
+  return MCBA_OK;
+}
+
+// cost sum, diag(H_ss) and their all-reduces as separate steps (multi-GPU path and the mcba_linearize hook)
+int finish_linearization(mcba_ctx* ctx) {
+  const DeviceProblem& P = ctx->P;
+  cudaStream_t s = ctx->stream;
+  const int nb = P.C * ctx->shared_chunks;
   k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL();
   if (P.n_s > 0) { k_diag<<<(P.n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, P.n_s, ctx->diag_s.p); CKL(); }
-  // cross-rank: shared gradient, shared diagonal, cost
   if (ctx->world > 1) {
     AR_GROUP_BEGIN();
     if (P.n_s > 0) { AR(ctx->g.p, P.n_s, NCCL_SUM); AR(ctx->diag_s.p, P.n_s, NCCL_SUM); }
@@ -246,6 +258,12 @@ int linearize(mcba_ctx* ctx, int loss, double f_scale) {
     AR_GROUP_END();
   }
   return MCBA_OK;
+}
+
+int linearize(mcba_ctx* ctx, int loss, double f_scale) {
+  int r = moments_at(ctx, loss, f_scale, false); if (r) return r;
+  r = expand(ctx); if (r) return r;
+  return finish_linearization(ctx);
 }
 
 // cost at the TRIAL state -> red[RED_COSTNEW]
@@ -718,27 +736,39 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   // x0 from the current state
   if (n) { k_gather_params<<<(n + 255) / 256, 256, 0, s>>>(P, ctx->x.p, P.cam_rt, P.board_rt, P.frame_rt, P.intr); CKL(); }
   r = prepare(ctx, with_state(ctx, false)); if (r) return r;
-  r = linearize(ctx, opts->loss, opts->f_scale); if (r) return r;
+  r = moments_at(ctx, opts->loss, opts->f_scale, false); if (r) return r;
+  r = expand(ctx); if (r) return r;
 
+  // One host synchronisation per trial step: everything from the Jacobian scaling to the acceptance test of the next
+  // trial point is queued behind the previous step; k_begin_iteration's `done` flag turns the tail into no-ops.
+  const bool single = ctx->world == 1;
+  const int ncp = P.C * ctx->shared_chunks;
   double last_reduction = NAN, last_step = NAN;
   int nlog = 0;
   int first = 1;
-  while (true) {
-    if (n) { k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p); CKL(); }
-    first = 0;
-    if (ctx->world > 1) {
-      AR_GROUP_BEGIN(); AR(ctx->red.p + RED_GH2_F, 2, NCCL_SUM); AR(ctx->red.p + RED_GMAX_F, 1, NCCL_MAX); AR_GROUP_END();
-    }
-    k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
-    CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  bool finished = false;
+  if (n == 0) {      // nothing to optimise: report the cost and leave
+    r = finish_linearization(ctx); if (r) return r;
+    CK(cudaMemcpyAsync(&h.cost, ctx->red.p + RED_COST, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; cudaEventDestroy(ev0); cudaEventDestroy(ev1); return MCBA_ERR_NONFINITE; }
-    if (h.iteration == 0) result->initial_cost = h.cost;
-    if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.nfev, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
-    if (h.done || n == 0) break;
+    result->initial_cost = h.cost; h.status = 1; finished = true;
+    if (log && log_capacity > 0) { log[0] = mcba_log_row{0, 1, h.cost, NAN, NAN, 0.0}; nlog = 1; }
+  }
+  while (!finished) {
+    if (single) {
+      k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
+                                 1, ctx->cost_part.p, ncp, ctx->state.p); CKL();
+    } else {
+      r = finish_linearization(ctx); if (r) return r;
+      k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
+                                 0, nullptr, 0, ctx->state.p); CKL();
+      AR_GROUP_BEGIN(); AR(ctx->red.p + RED_GH2_F, 2, NCCL_SUM); AR(ctx->red.p + RED_GMAX_F, 1, NCCL_MAX); AR_GROUP_END();
+      k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+    }
+    first = 0;
 
     r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0); if (r) return r;
-    if (ctx->world > 1) AR(ctx->red.p + RED_AGG, 1, NCCL_SUM);
+    if (!single) AR(ctx->red.p + RED_AGG, 1, NCCL_SUM);
     k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
     // Schur complement of the frame blocks
     if (n_s > 0) {
@@ -757,7 +787,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       }
     }
     if (n_s > 0) {
-      if (ctx->world > 1) { AR_GROUP_BEGIN(); AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); AR_GROUP_END(); }
+      if (!single) { AR_GROUP_BEGIN(); AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); AR_GROUP_END(); }
       if (n_s <= CHOL_SMALL_MAX) {
         const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
         const int R = (n_s + 15) / 16;
@@ -783,31 +813,42 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
     r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1); if (r) return r;
-    if (ctx->world > 1) AR(ctx->red.p + RED_AGG, 5, NCCL_SUM);        // AGG AGN ANN DOTGN_F GN2_F
+    if (!single) AR(ctx->red.p + RED_AGG, 5, NCCL_SUM);        // AGG AGN ANN DOTGN_F GN2_F
     k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
 
-    // inner loop: shrink the radius until the cost decreases (trf.py)
-    bool accepted = false;
+    // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
+    // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.
+    bool accepted = false, top_logged = false;
     while (true) {
-      k_tr_step<<<1, 1, 0, s>>>(ctx->state.p); CKL();
       k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
-      // trial state = current state with the free blocks replaced by x_new
-      CK(cudaMemcpyAsync(ctx->cam_rt2.p, ctx->cam_rt.p, sizeof(double) * P.C * 6, cudaMemcpyDeviceToDevice, s));
-      CK(cudaMemcpyAsync(ctx->board_rt2.p, ctx->board_rt.p, sizeof(double) * P.B * 6, cudaMemcpyDeviceToDevice, s));
-      if (P.F) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P.F * 6, cudaMemcpyDeviceToDevice, s));
-      CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToDevice, s));
-      r = set_state_from_x(ctx, ctx->x_new.p, true); if (r) return r;
-      r = trial_cost(ctx, opts->loss, opts->f_scale, true, RED_COSTNEW); if (r) return r;
-      if (ctx->world > 1) AR(ctx->red.p + RED_COSTNEW, 3, NCCL_SUM);   // COSTNEW STEP2_F XN2_F
-      k_accept<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+      {
+        const int nt = P.C + P.B + P.F + P.C;
+        k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p); CKL();
+      }
+      r = moments_at(ctx, opts->loss, opts->f_scale, true); if (r) return r;
+      if (single) {
+        k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p, P.V, P.T); CKL();
+      } else {
+        k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p, P.V, P.T, ctx->red.p); CKL();
+        AR(ctx->red.p + RED_COSTNEW, 3, NCCL_SUM);   // COSTNEW STEP2_F XN2_F
+        k_accept<<<1, 32, 0, s>>>(ctx->state.p, ctx->red.p, nullptr, 0, 0); CKL();
+      }
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
+      if (!top_logged) {      // the row scipy prints at the top of this outer iteration
+        if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; cudaEventDestroy(ev0); cudaEventDestroy(ev1); return MCBA_ERR_NONFINITE; }
+        if (h.iteration == 0) result->initial_cost = h.cost;
+        if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.done ? h.nfev : h.nfev - 1, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
+        top_logged = true;
+      }
+      if (h.done) { finished = true; break; }
       accepted = h.accepted != 0;
       if (h.status != -99) break;
       if (accepted || h.nfev >= h.max_nfev) break;
     }
+    if (finished) break;
     if (accepted) {
-      // x = x_new ; cost = cost_new ; J = jac(x)   (trf.py)
+      // x = x_new ; cost = cost_new ; J = jac(x)   (trf.py): the trial state, its pose tables and its moments become current
       std::swap(ctx->x.p, ctx->x_new.p);
       std::swap(ctx->cam_rt.p, ctx->cam_rt2.p); std::swap(ctx->board_rt.p, ctx->board_rt2.p);
       std::swap(ctx->frame_rt.p, ctx->frame_rt2.p); std::swap(ctx->intr.p, ctx->intr2.p);
@@ -815,14 +856,21 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       h.cost = h.cost_new;
       h.njev += 1;
       last_reduction = h.actual_reduction; last_step = h.step_norm;
-      // pose tables already hold the trial (= new) state
-      r = linearize(ctx, opts->loss, opts->f_scale); if (r) return r;
+      r = expand(ctx); if (r) return r;
     } else {
       last_reduction = 0.0; last_step = 0.0;
+      if (h.status == -99 && h.nfev >= h.max_nfev) {
+        // out of evaluations on a rejected step: the pose tables describe the rejected point, restore them
+        r = prepare(ctx, with_state(ctx, false)); if (r) return r;
+      }
     }
     h.iteration += 1;
     h.accepted = 0;
     CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  }
+  if (!finished || n > 0) {
+    // leave the context consistent: pose tables of the final (current) state
+    r = prepare(ctx, with_state(ctx, false)); if (r) return r;
   }
 
   CK(cudaEventRecord(ev1, s));

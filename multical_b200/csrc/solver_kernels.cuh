@@ -84,15 +84,35 @@ __global__ void k_diag(const double* Hss, int n_s, double* diag) {
   if (i < n_s) diag[i] = Hss[(size_t)i * n_s + i];
 }
 
+// trf.py top of the outer loop: ||g||_inf, gtol / max_nfev exits, first-iteration cost and Delta.
+__device__ inline void begin_iteration(SolverState* st, const double* red) {
+  const double gh2 = red[RED_GH2_S] + red[RED_GH2_F];
+  st->gh_norm = sqrt(gh2);
+  st->g_norm = fmax(red[RED_GMAX_S], red[RED_GMAX_F]);
+  if (st->first_scale) {
+    st->cost = red[RED_COST];
+    double D0 = sqrt(red[RED_XS2_S] + red[RED_XS2_F]);
+    st->Delta = (D0 == 0.0) ? 1.0 : D0;
+    st->first_scale = 0;
+  }
+  if (st->g_norm < st->gtol) st->status = 1;
+  st->done = (st->status != -99) || (st->nfev >= st->max_nfev);
+}
+__global__ void k_begin_iteration(SolverState* st, double* red) { begin_iteration(st, red); }
+
 // common.py compute_jac_scale: scale_inv = ||J[:,i]|| = sqrt(H_ii); zero -> 1 on the first call, running max after;
 // also g_h = d*g, ||g||_inf, ||g_h||^2 and ||x*scale_inv||^2 (initial Delta, trf.py).  Single CTA.
-__global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hff, const double* g, const double* x,
-                        double* sinv, double* d, double* gh, int first, double* red) {
+// Single-GPU fast path (fused != 0): reads diag(H_ss) in place, sums the per-CTA cost partials of k_expand_shared and
+// runs the begin-of-iteration logic itself; with several ranks those three need all-reduces in between.
+__global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss, const double* Hff, const double* g, const double* x,
+                        double* sinv, double* d, double* gh, int first, double* red,
+                        int fused, const double* cost_part, int n_cost_part, SolverState* st) {
   __shared__ double sm[32];
+  if (fused && st->done) return;
   double gh2s = 0, gh2f = 0, gms = 0, gmf = 0, xs2s = 0, xs2f = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double hd;
-    if (i < n_s) hd = diag_s[i];
+    if (i < n_s) hd = fused ? Hss[(size_t)i * n_s + i] : diag_s[i];
     else { const int f = (i - n_s) / 6, j = (i - n_s) % 6; hd = Hff[(size_t)f * 36 + j * 7]; }
     double nrm = sqrt(fmax(hd, 0.0));
     double si;
@@ -112,6 +132,12 @@ __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hff,
   r = block_max(gmf, sm);  if (threadIdx.x == 0) red[RED_GMAX_F] = r;
   r = block_sum(xs2s, sm); if (threadIdx.x == 0) red[RED_XS2_S] = r;
   r = block_sum(xs2f, sm); if (threadIdx.x == 0) red[RED_XS2_F] = r;
+  if (fused) {
+    double c = 0.0;
+    for (int i = threadIdx.x; i < n_cost_part; i += blockDim.x) c += cost_part[i];
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) { red[RED_COST] = c; begin_iteration(st, red); }
+  }
 }
 
 // quadratic forms u^T A v, A = D H D, for (u,u) [, (u,v), (v,v)].  Grid = F frame CTAs + shared CTAs.
@@ -181,22 +207,7 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
 }
 
 // trf.py: reg_term = -ag_value / Delta^2 with ag_value = min over [0, Delta/||g_h||] of a t^2 + b t,
-// a = g_h^T A g_h, b = -||g_h||^2 (build_quadratic_1d / minimize_quadratic_1d).  Also finalises ||g||_inf,
-// the initial Delta and the gtol / max_nfev exits at the top of the outer loop.
-__global__ void k_begin_iteration(SolverState* st, double* red) {
-  const double gh2 = red[RED_GH2_S] + red[RED_GH2_F];
-  st->gh_norm = sqrt(gh2);
-  st->g_norm = fmax(red[RED_GMAX_S], red[RED_GMAX_F]);
-  if (st->first_scale) {
-    st->cost = red[RED_COST];
-    double D0 = sqrt(red[RED_XS2_S] + red[RED_XS2_F]);
-    st->Delta = (D0 == 0.0) ? 1.0 : D0;
-    st->first_scale = 0;
-  }
-  if (st->g_norm < st->gtol) st->status = 1;
-  st->done = (st->status != -99) || (st->nfev >= st->max_nfev);
-}
-
+// a = g_h^T A g_h, b = -||g_h||^2 (build_quadratic_1d / minimize_quadratic_1d).
 __global__ void k_reg(SolverState* st, const double* red) {
   const double a = red[RED_AGG];
   const double gh2 = st->gh_norm * st->gh_norm;
@@ -746,7 +757,7 @@ __device__ inline void solve_tr_2d(double b11, double b12, double b22, double g1
   p2 = c1 * v1y + c2 * v2y;
 }
 
-__global__ void k_tr_step(SolverState* st) {
+__device__ inline void tr_step_compute(SolverState* st) {
   double p1, p2;
   solve_tr_2d(st->B11, st->B12, st->B22, st->gS1, st->gS2, st->Delta, p1, p2);
   if (st->n2 == 0.0) p2 = 0.0;
@@ -758,9 +769,12 @@ __global__ void k_tr_step(SolverState* st) {
 }
 
 // x_new = x + d*(alpha gh + beta gn); norms of step and x (split shared / frame). Single CTA.
-__global__ void k_step(int n, int n_s, const SolverState* st, const double* x, const double* d, const double* gh,
+__global__ void k_step(int n, int n_s, SolverState* st, const double* x, const double* d, const double* gh,
                        const double* gn, double* x_new, double* red) {
   __shared__ double sm[32];
+  if (st->done) return;
+  if (threadIdx.x == 0) tr_step_compute(st);      // 2-D trust-region subproblem for the current Delta
+  __syncthreads();
   const double al = st->alpha, be = st->beta;
   double s2s = 0, s2f = 0, x2s = 0, x2f = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -777,7 +791,26 @@ __global__ void k_step(int n, int n_s, const SolverState* st, const double* x, c
 }
 
 // trf.py inner loop after fun(x_new): actual reduction, update_tr_radius, check_termination.
-__global__ void k_accept(SolverState* st, const double* red) {
+// sum of the per-view cost entries of the moment records (moments[v][T-1]) -> red[RED_COSTNEW]
+__global__ void k_cost_from_moments(const double* moments, int V, int T, double* red) {
+  __shared__ double sm[32];
+  double c = 0.0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T + T - 1];
+  c = block_sum(c, sm);
+  if (threadIdx.x == 0) red[RED_COSTNEW] = c;
+}
+
+// single-GPU: the cost sum is done by the same CTA (moments != nullptr); multi-GPU: k_cost_from_moments, all-reduce, then this
+__global__ void k_accept(SolverState* st, double* red, const double* moments, int V, int T) {
+  __shared__ double sm[32];
+  if (st->done) return;
+  if (moments) {
+    double c = 0.0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T + T - 1];
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) red[RED_COSTNEW] = c;
+  }
+  if (threadIdx.x != 0) return;
   st->nfev += 1;
   const double cost_new = red[RED_COSTNEW];
   st->cost_new = cost_new;
