@@ -92,6 +92,7 @@ struct mcba_ctx {
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
   DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
   DevBuf<SolverState> state;
+  DevBuf<unsigned> counter;
   int shared_chunks = 1;
   std::vector<int> perm;   // internal index -> canonical param_vec index
 };
@@ -275,19 +276,18 @@ int trial_cost(mcba_ctx* ctx, int loss, double f_scale, bool trial, int slot) {
   return MCBA_OK;
 }
 
-int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two) {
+// quadratic forms of the scaled Hessian; single-GPU: the last CTA also sums the partials and runs the scalar step that
+// consumes them (finalize 2 = reg, 3 = subspace); multi-GPU: sum only, the caller all-reduces and launches k_reg / k_subspace
+int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int finalize) {
   const DeviceProblem& P = ctx->P;
   const int nframe = P.motion_on ? P.F : 0;
   const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
   const int fb = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
-  const int nb = nframe + nsh;          // number of partial records
-  if (nb == 0) return MCBA_OK;
-  k_quad<<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p); CKL();
-  // RED_AGG, RED_AGN, RED_ANN are consecutive
-  k_sum_partials<<<1, 256, 0, ctx->stream>>>(ctx->quad_part.p, nb, 3, two ? 3 : 1, ctx->red.p + RED_AGG); CKL();
-  return MCBA_OK;     // the caller all-reduces red[RED_AGG ...]
+  if (fb + nsh == 0) return MCBA_OK;
+  k_quad<<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
+                                                      finalize, ctx->counter.p, ctx->red.p, ctx->state.p); CKL();
+  return MCBA_OK;
 }
-
 
 // dimensions, variable layout, permutation and every solver buffer that depends on (C,F,B,P,N,V)
 int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V) {
@@ -337,6 +337,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
   CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
   CK(ctx->state.alloc(1));
+  CK(ctx->counter.alloc(4)); CK(cudaMemsetAsync(ctx->counter.p, 0, 4 * sizeof(unsigned), ctx->stream));
   CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
   CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
   CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
@@ -766,24 +767,34 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
     }
     first = 0;
+    if (h.status != -99 || h.nfev >= h.max_nfev) {
+      // the host already knows this is the last pass of the outer loop (termination test fired or out of evaluations):
+      // only the gradient norm of the final point is still needed for the last table row
+      CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; cudaEventDestroy(ev0); cudaEventDestroy(ev1); return MCBA_ERR_NONFINITE; }
+      if (h.iteration == 0) result->initial_cost = h.cost;
+      if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.nfev, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
+      finished = true;
+      break;
+    }
 
-    r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0); if (r) return r;
-    if (!single) AR(ctx->red.p + RED_AGG, 1, NCCL_SUM);
-    k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+    r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, single ? 2 : 1); if (r) return r;
+    if (!single) { AR(ctx->red.p + RED_AGG, 1, NCCL_SUM); k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }
     // Schur complement of the frame blocks
-    if (n_s > 0) {
+    if (n_s > 0 && F == 0) {
       const size_t nn2 = (size_t)n_s * n_s;
       k_schur_init<<<(unsigned)((nn2 + 255) / 256), 256, 0, s>>>(n_s, ctx->Hss.p, ctx->d.p, ctx->S.p, ctx->rhs.p); CKL();
     }
     if (F > 0) {
-      k_schur_frames<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p); CKL();
+      k_schur_frames<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p,
+                                                   ctx->Hss.p, ctx->S.p, ctx->rhs.p); CKL();
       if (n_s > 0) {
         const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
         int chunks = std::max(1, std::min((F + SYRK_FR - 1) / SYRK_FR, (ctx->num_sms * 4) / std::max(1, tiles * (tiles + 1) / 2)));
         const int cf = ((F + chunks - 1) / chunks + SYRK_FR - 1) / SYRK_FR * SYRK_FR;
         chunks = (F + cf - 1) / cf;
-        k_schur_syrk<<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p); CKL();
-        k_schur_rhs<<<dim3((n_s + 127) / 128, chunks), 128, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->zf.p, ctx->rhs.p); CKL();
+        k_schur_syrk<<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p, ctx->zf.p, ctx->rhs.p); CKL();
       }
     }
     if (n_s > 0) {
@@ -812,9 +823,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     }
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
-    r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1); if (r) return r;
-    if (!single) AR(ctx->red.p + RED_AGG, 5, NCCL_SUM);        // AGG AGN ANN DOTGN_F GN2_F
-    k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+    r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1); if (r) return r;
+    if (!single) { AR(ctx->red.p + RED_AGG, 5, NCCL_SUM); k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }   // AGG AGN ANN DOTGN_F GN2_F
 
     // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
     // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.

@@ -142,6 +142,9 @@ __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss,
 
 // quadratic forms u^T A v, A = D H D, for (u,u) [, (u,v), (v,v)].  Grid = F frame CTAs + shared CTAs.
 // partial[cta][3].  u, v are scaled-space vectors (gh, gn).
+__device__ inline void reg_compute(SolverState* st, const double* red);
+__device__ inline void subspace_compute(SolverState* st, const double* red);
+
 constexpr int QUAD_THREADS = 128;
 constexpr int QUAD_WARPS = QUAD_THREADS / 32;
 // blocks [0, frame_blocks): one WARP per frame (W_f^T u_s by lane-strided sums + shuffles, then the 6x6 part);
@@ -149,41 +152,44 @@ constexpr int QUAD_WARPS = QUAD_THREADS / 32;
 // partial[frame or F + shared block][3]
 __global__ void __launch_bounds__(QUAD_THREADS)
 k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, const double* W, const double* d,
-       const double* u, const double* v, int two, double* partial) {
+       const double* u, const double* v, int two, double* partial,
+       int finalize /*0 none, 1 sum, 2 sum+reg, 3 sum+subspace*/, unsigned* counter, double* red, SolverState* st) {
   __shared__ double sm[32];
+  __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nframe = motion_on ? F : 0;
   const int frame_blocks = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
   if ((int)blockIdx.x < frame_blocks) {
     const int f = blockIdx.x * QUAD_WARPS + warp;
-    if (f >= nframe) return;
-    const double* Wf = W + (size_t)f * n_s * 6;
-    double tu[6] = {0, 0, 0, 0, 0, 0}, tv[6] = {0, 0, 0, 0, 0, 0};
-    for (int s = lane; s < n_s; s += 32) {
-      const double us = d[s] * u[s], vs = two ? d[s] * v[s] : 0.0;
+    if (f < nframe) {
+      const double* Wf = W + (size_t)f * n_s * 6;
+      double tu[6] = {0, 0, 0, 0, 0, 0}, tv[6] = {0, 0, 0, 0, 0, 0};
+      for (int s = lane; s < n_s; s += 32) {
+        const double us = d[s] * u[s], vs = two ? d[s] * v[s] : 0.0;
 #pragma unroll
-      for (int j = 0; j < 6; j++) { const double w = Wf[s * 6 + j]; tu[j] += w * us; tv[j] += w * vs; }
-    }
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { tu[j] += __shfl_xor_sync(0xffffffffu, tu[j], o); tv[j] += __shfl_xor_sync(0xffffffffu, tv[j], o); }
-    }
-    if (lane == 0) {
-      double uf[6], vf[6], uu = 0, uv = 0, vv = 0;
-#pragma unroll
-      for (int j = 0; j < 6; j++) { const int i = n_s + 6 * f + j; uf[j] = d[i] * u[i]; vf[j] = two ? d[i] * v[i] : 0.0; }
-      const double* H = Hff + (size_t)f * 36;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        double hu = 0, hv = 0;
-#pragma unroll
-        for (int j = 0; j < 6; j++) { hu += H[i * 6 + j] * uf[j]; hv += H[i * 6 + j] * vf[j]; }
-        uu += uf[i] * (hu + 2.0 * tu[i]);
-        uv += uf[i] * hv + uf[i] * tv[i] + vf[i] * tu[i];
-        vv += vf[i] * (hv + 2.0 * tv[i]);
+        for (int j = 0; j < 6; j++) { const double w = Wf[s * 6 + j]; tu[j] += w * us; tv[j] += w * vs; }
       }
-      partial[(size_t)f * 3 + 0] = uu; partial[(size_t)f * 3 + 1] = uv; partial[(size_t)f * 3 + 2] = vv;
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { tu[j] += __shfl_xor_sync(0xffffffffu, tu[j], o); tv[j] += __shfl_xor_sync(0xffffffffu, tv[j], o); }
+      }
+      if (lane == 0) {
+        double uf[6], vf[6], uu = 0, uv = 0, vv = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) { const int i = n_s + 6 * f + j; uf[j] = d[i] * u[i]; vf[j] = two ? d[i] * v[i] : 0.0; }
+        const double* H = Hff + (size_t)f * 36;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          double hu = 0, hv = 0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) { hu += H[i * 6 + j] * uf[j]; hv += H[i * 6 + j] * vf[j]; }
+          uu += uf[i] * (hu + 2.0 * tu[i]);
+          uv += uf[i] * hv + uf[i] * tv[i] + vf[i] * tu[i];
+          vv += vf[i] * (hv + 2.0 * tv[i]);
+        }
+        partial[(size_t)f * 3 + 0] = uu; partial[(size_t)f * 3 + 1] = uv; partial[(size_t)f * 3 + 2] = vv;
+      }
     }
   } else {
     const int sb = blockIdx.x - frame_blocks;
@@ -204,11 +210,32 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
     r = block_sum(uv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 1] = r;
     r = block_sum(vv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 2] = r;
   }
+  if (!finalize) return;
+  // last-block reduction: deterministic (index-ordered) sum of all partial records, then the scalar step that needs it
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) { const unsigned t = atomicAdd(counter, 1u); is_last = (t == gridDim.x - 1); }
+  __syncthreads();
+  if (!is_last) return;
+  const int nparts = nframe + (int)gridDim.x - frame_blocks;
+  const int nout = two ? 3 : 1;
+  for (int j = 0; j < nout; j++) {
+    double acc = 0.0;
+    for (int i = tid; i < nparts; i += QUAD_THREADS) acc += __ldcg(&partial[(size_t)i * 3 + j]);
+    acc = block_sum(acc, sm);
+    if (tid == 0) red[RED_AGG + j] = acc;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *counter = 0;
+    if (finalize == 2) reg_compute(st, red);
+    else if (finalize == 3) subspace_compute(st, red);
+  }
 }
 
 // trf.py: reg_term = -ag_value / Delta^2 with ag_value = min over [0, Delta/||g_h||] of a t^2 + b t,
 // a = g_h^T A g_h, b = -||g_h||^2 (build_quadratic_1d / minimize_quadratic_1d).
-__global__ void k_reg(SolverState* st, const double* red) {
+__device__ inline void reg_compute(SolverState* st, const double* red) {
   const double a = red[RED_AGG];
   const double gh2 = st->gh_norm * st->gh_norm;
   const double b = -gh2;
@@ -223,14 +250,22 @@ __global__ void k_reg(SolverState* st, const double* red) {
   st->reg = reg;
 }
 
+__global__ void k_reg(SolverState* st, const double* red) { reg_compute(st, red); }
+
 // per frame: L L^T = D_f H_ff D_f + reg I ; Y_f = (D_s W_f D_f) L^-T (n_s x 6) ; z_f = L^-1 (D_f g_f)
 constexpr int SCHUR_THREADS = 128;
 __global__ void __launch_bounds__(SCHUR_THREADS)
 k_schur_frames(int n_s, const double* Hff, const double* W, const double* d, const double* gh,
-               const SolverState* st, double* Y, double* Lf, double* zf) {
+               const SolverState* st, double* Y, double* Lf, double* zf, const double* Hss, double* S, double* rhs) {
   __shared__ double L[36];
   __shared__ double df[6];
   const int f = blockIdx.x, tid = threadIdx.x;
+  // S_local = D_s H_ss D_s, rhs_local = 0 (grid-stride; the SYRK kernel that follows subtracts sum_f Y_f Y_f^T)
+  for (size_t idx = (size_t)blockIdx.x * SCHUR_THREADS + tid; idx < (size_t)n_s * n_s; idx += (size_t)gridDim.x * SCHUR_THREADS) {
+    const int i = idx / n_s, j = idx % n_s;
+    S[idx] = d[i] * d[j] * Hss[idx];
+    if (idx < (size_t)n_s) rhs[idx] = 0.0;
+  }
   if (tid == 0) {
     const double reg = st->reg;
     const double* H = Hff + (size_t)f * 36;
@@ -286,7 +321,7 @@ __global__ void k_schur_init(int n_s, const double* Hss, const double* d, double
 // S -= sum_f Y_f Y_f^T over this CTA's frame chunk; 32x32 output tile per CTA, 2x2 micro-tile per thread.
 constexpr int SYRK_TILE = 32, SYRK_FR = 8;
 __global__ void __launch_bounds__(256)
-k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S) {
+k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S, const double* zf, double* rhs) {
   __shared__ double Yi[SYRK_FR][SYRK_TILE][6];
   __shared__ double Yj[SYRK_FR][SYRK_TILE][6];
   const int ti = blockIdx.y, tj = blockIdx.x;
@@ -294,6 +329,7 @@ k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S) {
   const int f0 = blockIdx.z * chunk_frames, f1 = min(F, f0 + chunk_frames);
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   double acc[2][2] = {{0, 0}, {0, 0}};
+  double racc = 0.0;                     // diagonal tiles also accumulate rhs -= Y_f z_f for their 32 rows
   for (int fb = f0; fb < f1; fb += SYRK_FR) {
     const int nf = min(SYRK_FR, f1 - fb);
     for (int o = threadIdx.x; o < SYRK_FR * SYRK_TILE * 6; o += 256) {
@@ -310,7 +346,18 @@ k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S) {
         acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
       }
     }
+    if (ti == tj && threadIdx.x < SYRK_TILE) {
+      for (int ff = 0; ff < nf; ff++) {
+        const double* z = zf + (size_t)(fb + ff) * 6;
+#pragma unroll
+        for (int k = 0; k < 6; k++) racc += Yi[ff][threadIdx.x][k] * z[k];
+      }
+    }
     __syncthreads();
+  }
+  if (ti == tj && threadIdx.x < SYRK_TILE) {
+    const int i = ti * SYRK_TILE + threadIdx.x;
+    if (i < n_s) atomicAdd(&rhs[i], -racc);
   }
 #pragma unroll
   for (int a = 0; a < 2; a++)
@@ -690,7 +737,7 @@ __global__ void k_dots(int n, int n_s, const double* gh, const double* gn, doubl
 
 // trf.py: S = qr([g_h, gn_h]); B_S = (J_h S)^T (J_h S); g_S = S^T g_h   -- expressed through Gram-Schmidt
 // coefficients so that no basis vectors are materialised: q1 = gh/n1, q2 = (gn - mu q1)/n2.
-__global__ void k_subspace(SolverState* st, const double* red) {
+__device__ inline void subspace_compute(SolverState* st, const double* red) {
   const double n1 = st->gh_norm;
   const double dot = red[RED_DOTGN_S] + red[RED_DOTGN_F];
   const double gn2 = red[RED_GN2_S] + red[RED_GN2_F];
@@ -709,6 +756,8 @@ __global__ void k_subspace(SolverState* st, const double* red) {
     st->B22 = (ann - 2.0 * c * agn + c * c * agg) / (n2 * n2);
   }
 }
+
+__global__ void k_subspace(SolverState* st, const double* red) { subspace_compute(st, red); }
 
 // common.py solve_trust_region_2d: minimise 0.5 p^T B p + g^T p, ||p|| <= Delta  (B 2x2 symmetric).
 // Interior Newton point if B is positive definite and inside; otherwise the global boundary minimiser via
