@@ -81,6 +81,11 @@ int  mcba_version(void);
 int  mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]);      /* rank 0, then broadcast by the host   */
 int  mcba_comm_init(mcba_ctx* ctx, const char id[128], int rank, int world);
 
+/* Optional: exchange steps over NVLink peer memory instead of NCCL (payloads up to cap_doubles per step; larger ones keep
+ * using NCCL).  Every rank exports one IPC handle (64 bytes), the host all-gathers them, every rank imports all of them. */
+int  mcba_peer_export(mcba_ctx* ctx, int64_t cap_doubles, char out_handle[64]);
+int  mcba_peer_import(mcba_ctx* ctx, const char* handles /* world x 64 bytes in rank order */);
+
 /* -- problem upload: replaces what `evaluate` closes over (calibration.py:204-206) --------------
  * cam/frame/board/point: int32[N] rows of np.argwhere(inliers) (frame ids local to this rank);
  * obs: f64[N][2] = point_table.points[inliers] (calibration.py:206);

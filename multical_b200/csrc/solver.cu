@@ -14,6 +14,7 @@
 #include "../../include/mcba.h"
 #include "solver_kernels.cuh"
 #include "pack_kernels.cuh"
+#include "peer_allreduce.cuh"
 
 using namespace mcba;
 
@@ -94,6 +95,10 @@ struct mcba_ctx {
   DevBuf<SolverState> state;
   DevBuf<unsigned> counter;
   int shared_chunks = 1;
+  // peer-memory all-reduce (peer_allreduce.cuh)
+  double* peer_own = nullptr; int peer_cap = 0; bool peer_ready = false; unsigned peer_seq = 0;
+  double* peer_base[PEER_MAX_WORLD] = {nullptr};
+  std::vector<void*> peer_opened;
   std::vector<int> perm;   // internal index -> canonical param_vec index
 };
 
@@ -116,15 +121,35 @@ struct mcba_ctx {
 
 namespace {
 
-int allreduce(mcba_ctx* ctx, double* buf, size_t count, int op) {
-  if (ctx->world == 1) return MCBA_OK;
-  int r = g_nccl.AllReduce(buf, buf, count, NCCL_FLOAT64, op, ctx->comm, ctx->stream);
-  if (r != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return MCBA_ERR_NCCL; }
+// One exchange step = up to PEER_MAX_SEG (buffer, count, op) segments reduced across ranks.  Over NVLink peer memory when
+// the communicator has peer buffers and the payload fits a slot (one kernel, ~one-way latency); NCCL otherwise.
+struct Exchange {
+  PeerSeg seg[PEER_MAX_SEG]; int n = 0;
+  void add(double* buf, size_t count, int op) { if (count) { seg[n].buf = buf; seg[n].count = (int)count; seg[n].op = op; n++; } }
+};
+int run_exchange(mcba_ctx* ctx, const Exchange& ex) {
+  if (ctx->world == 1 || ex.n == 0) return MCBA_OK;
+  size_t total = 0;
+  for (int i = 0; i < ex.n; i++) total += ex.seg[i].count;
+  if (ctx->peer_ready && total <= (size_t)ctx->peer_cap) {
+    PeerArgs a{};
+    for (int i = 0; i < ex.n; i++) a.seg[i] = ex.seg[i];
+    a.nseg = ex.n; a.rank = ctx->rank; a.world = ctx->world; a.cap = ctx->peer_cap; a.seq = ++ctx->peer_seq;
+    for (int r = 0; r < ctx->world; r++) a.base[r] = ctx->peer_base[r];
+    a.counter = ctx->counter.p + 1;
+    const int blocks = (int)std::min<size_t>(32, (total + 255) / 256);
+    k_peer_allreduce<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(a); CKL();
+    return MCBA_OK;
+  }
+  if (g_nccl.GroupStart) g_nccl.GroupStart();
+  int rc = 0;
+  for (int i = 0; i < ex.n && rc == 0; i++)
+    rc = g_nccl.AllReduce(ex.seg[i].buf, ex.seg[i].buf, ex.seg[i].count, NCCL_FLOAT64, ex.seg[i].op == 0 ? NCCL_SUM : NCCL_MAX, ctx->comm, ctx->stream);
+  if (g_nccl.GroupEnd) g_nccl.GroupEnd();
+  if (rc != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return MCBA_ERR_NCCL; }
   return MCBA_OK;
 }
-#define AR(buf, count, op) do { int r_ = allreduce(ctx, buf, count, op); if (r_) return r_; } while (0)
-#define AR_GROUP_BEGIN() do { if (ctx->world > 1 && g_nccl.GroupStart) g_nccl.GroupStart(); } while (0)
-#define AR_GROUP_END() do { if (ctx->world > 1 && g_nccl.GroupEnd) g_nccl.GroupEnd(); } while (0)
+#define EXCHANGE(...) do { if (ctx->world > 1) { Exchange ex_; __VA_ARGS__; int r_ = run_exchange(ctx, ex_); if (r_) return r_; } } while (0)
 
 int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : 2; }
 
@@ -252,12 +277,7 @@ int finish_linearization(mcba_ctx* ctx) {
   const int nb = P.C * ctx->shared_chunks;
   k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL();
   if (P.n_s > 0) { k_diag<<<(P.n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, P.n_s, ctx->diag_s.p); CKL(); }
-  if (ctx->world > 1) {
-    AR_GROUP_BEGIN();
-    if (P.n_s > 0) { AR(ctx->g.p, P.n_s, NCCL_SUM); AR(ctx->diag_s.p, P.n_s, NCCL_SUM); }
-    AR(ctx->red.p + RED_COST, 1, NCCL_SUM);
-    AR_GROUP_END();
-  }
+  EXCHANGE(ex_.add(ctx->g.p, P.n_s, 0); ex_.add(ctx->diag_s.p, P.n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0));
   return MCBA_OK;
 }
 
@@ -408,6 +428,8 @@ int mcba_create(int device, mcba_ctx** out) {
 void mcba_destroy(mcba_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
+  if (ctx->peer_own) cudaFree(ctx->peer_own);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   delete ctx;
 }
@@ -430,13 +452,47 @@ int mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]) {
 int mcba_comm_init(mcba_ctx* ctx, const char id_[128], int rank, int world) {
   if (!ctx || !id_) return MCBA_ERR_ARG;
   REQUIRE(world >= 1 && rank >= 0 && rank < world, MCBA_ERR_ARG, "bad rank/world");
-  ctx->rank = rank; ctx->world = world;
+  ctx->rank = rank; ctx->world = world; ctx->peer_ready = false;
   if (world == 1) return MCBA_OK;
   if (!g_nccl.load(ctx->err)) return MCBA_ERR_NCCL;
   CK(cudaSetDevice(ctx->device));
   ncclUniqueId id; memcpy(id.internal, id_, 128);
   int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
   if (r != 0) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return MCBA_ERR_NCCL; }
+  return MCBA_OK;
+}
+
+int mcba_peer_export(mcba_ctx* ctx, int64_t cap_doubles, char out_handle[64]) {
+  if (!ctx || !out_handle) return MCBA_ERR_ARG;
+  REQUIRE(ctx->world > 1 && ctx->world <= PEER_MAX_WORLD, MCBA_ERR_STATE, "peer buffers need an initialised communicator with 2..16 ranks");
+  REQUIRE(cap_doubles > 0 && cap_doubles < ((int64_t)1 << 28), MCBA_ERR_ARG, "bad peer slot capacity");
+  REQUIRE(sizeof(cudaIpcMemHandle_t) == 64, MCBA_ERR_UNSUPPORTED, "unexpected cudaIpcMemHandle_t size");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->peer_own) { cudaFree(ctx->peer_own); ctx->peer_own = nullptr; }
+  ctx->peer_ready = false; ctx->peer_cap = (int)cap_doubles;
+  const size_t bytes = peer_buffer_doubles(ctx->world, ctx->peer_cap) * sizeof(double);
+  CK(cudaMalloc(&ctx->peer_own, bytes));
+  CK(cudaMemset(ctx->peer_own, 0, bytes));
+  CK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->peer_own));
+  memcpy(out_handle, &h, 64);
+  return MCBA_OK;
+}
+
+int mcba_peer_import(mcba_ctx* ctx, const char* handles /* world x 64 bytes, rank order */) {
+  if (!ctx || !handles) return MCBA_ERR_ARG;
+  REQUIRE(ctx->peer_own != nullptr, MCBA_ERR_STATE, "mcba_peer_export has not been called");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->world; r++) {
+    if (r == ctx->rank) { ctx->peer_base[r] = ctx->peer_own; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_base[r] = (double*)p; ctx->peer_opened.push_back(p);
+  }
+  ctx->peer_seq = 0;
+  ctx->peer_ready = true;
   return MCBA_OK;
 }
 
@@ -763,7 +819,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       r = finish_linearization(ctx); if (r) return r;
       k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
                                  0, nullptr, 0, ctx->state.p); CKL();
-      AR_GROUP_BEGIN(); AR(ctx->red.p + RED_GH2_F, 2, NCCL_SUM); AR(ctx->red.p + RED_GMAX_F, 1, NCCL_MAX); AR_GROUP_END();
+      EXCHANGE(ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1));
       k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
     }
     first = 0;
@@ -780,7 +836,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     }
 
     r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, single ? 2 : 1); if (r) return r;
-    if (!single) { AR(ctx->red.p + RED_AGG, 1, NCCL_SUM); k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }
+    if (!single) { EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 1, 0)); k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }
     // Schur complement of the frame blocks
     if (n_s > 0 && F == 0) {
       const size_t nn2 = (size_t)n_s * n_s;
@@ -798,7 +854,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       }
     }
     if (n_s > 0) {
-      if (!single) { AR_GROUP_BEGIN(); AR(ctx->S.p, (size_t)n_s * n_s, NCCL_SUM); AR(ctx->rhs.p, n_s, NCCL_SUM); AR_GROUP_END(); }
+      EXCHANGE(ex_.add(ctx->S.p, (size_t)n_s * n_s, 0); ex_.add(ctx->rhs.p, n_s, 0));
       if (n_s <= CHOL_SMALL_MAX) {
         const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
         const int R = (n_s + 15) / 16;
@@ -824,7 +880,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
     r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1); if (r) return r;
-    if (!single) { AR(ctx->red.p + RED_AGG, 5, NCCL_SUM); k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }   // AGG AGN ANN DOTGN_F GN2_F
+    if (!single) { EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0)); k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }   // AGG AGN ANN DOTGN_F GN2_F
 
     // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
     // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.
@@ -840,7 +896,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p, P.V, P.T); CKL();
       } else {
         k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p, P.V, P.T, ctx->red.p); CKL();
-        AR(ctx->red.p + RED_COSTNEW, 3, NCCL_SUM);   // COSTNEW STEP2_F XN2_F
+        EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0));   // COSTNEW STEP2_F XN2_F
         k_accept<<<1, 32, 0, s>>>(ctx->state.p, ctx->red.p, nullptr, 0, 0); CKL();
       }
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));

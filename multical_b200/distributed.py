@@ -22,12 +22,20 @@ def frame_owner(F, world):
   return owner
 
 
-def init_comm(engine, rank, world, group=None):
-  """Create the engine's NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it."""
+def init_comm(engine, rank, world, group=None, peer_cap=None):
+  """Create the engine's communicator: rank 0 makes the NCCL unique id, torch.distributed broadcasts it; then every rank
+  exports an NVLink exchange buffer (IPC handle) and imports everyone else's, so that the latency-bound exchanges of an
+  LM iteration run as one-shot peer-memory all-reduces (csrc/peer_allreduce.cuh).  MCBA_PEER=0 keeps everything on NCCL."""
+  import os
   import torch.distributed as dist
   uid = [engine.comm_unique_id() if rank == 0 else None]
   dist.broadcast_object_list(uid, src=0, group=group)
   engine.comm_init(uid[0], rank, world)
+  if world > 1 and os.environ.get("MCBA_PEER", "1") != "0":
+    cap = int(os.environ.get("MCBA_PEER_CAP", peer_cap or (1 << 16)))
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.peer_export(cap), group=group)
+    engine.peer_import(handles)
 
 
 def shard_calibration(calib, rank, world):

@@ -65,6 +65,17 @@ class Engine:
     self._ck(self.lib.mcba_comm_init(self.h, uid, int(rank), int(world)))
     self.rank, self.world = rank, world
 
+  def peer_export(self, cap_doubles):
+    """Allocate this rank's NVLink exchange buffer and return its 64-byte IPC handle (include/mcba.h)."""
+    buf = C.create_string_buffer(64)
+    self._ck(self.lib.mcba_peer_export(self.h, int(cap_doubles), buf))
+    return buf.raw
+
+  def peer_import(self, handles):
+    """handles: list of the 64-byte IPC handles of all ranks, in rank order."""
+    blob = b"".join(handles)
+    self._ck(self.lib.mcba_peer_import(self.h, blob))
+
   # ---- problem ----------------------------------------------------------------------------------
   def upload(self, model, optimize_bits, dims, idx, obs, board_points):
     Cn, F, B, P = (int(v) for v in dims)
