@@ -11,6 +11,7 @@
 // Two parities suffice: a rank cannot finish #seq+1 before every peer has posted #seq+1, i.e. finished reading #seq.
 #pragma once
 #include <stdint.h>
+#include "solver_kernels.cuh"
 
 namespace mcba {
 
@@ -25,6 +26,9 @@ struct PeerArgs {
   unsigned seq;
   double* base[PEER_MAX_WORLD];          // peer-mapped base pointer of every rank's buffer (base[rank] = own)
   unsigned* counter;
+  int epilogue;                          // EPI_* scalar step run by thread 0 after the reduction (single-CTA exchanges only)
+  SolverState* st;
+  double* red;
 };
 
 __host__ __device__ inline size_t peer_flag_off(int world, int parity, int src) { return (size_t)(parity * world + src) * PEER_FLAG_STRIDE; }
@@ -85,6 +89,10 @@ k_peer_allreduce(PeerArgs a) {
       acc = a.seg[s].op == 0 ? acc + v : fmax(acc, v);
     }
     a.seg[s].buf[off] = acc;
+  }
+  if (a.epilogue) {                      // launched with one CTA: all reduced values are in place after this barrier
+    __syncthreads();
+    if (tid == 0) run_epilogue(a.epilogue, a.st, a.red);
   }
 }
 

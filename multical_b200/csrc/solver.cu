@@ -124,19 +124,20 @@ namespace {
 // One exchange step = up to PEER_MAX_SEG (buffer, count, op) segments reduced across ranks.  Over NVLink peer memory when
 // the communicator has peer buffers and the payload fits a slot (one kernel, ~one-way latency); NCCL otherwise.
 struct Exchange {
-  PeerSeg seg[PEER_MAX_SEG]; int n = 0;
+  PeerSeg seg[PEER_MAX_SEG]; int n = 0; int epilogue = 0;
   void add(double* buf, size_t count, int op) { if (count) { seg[n].buf = buf; seg[n].count = (int)count; seg[n].op = op; n++; } }
 };
 int run_exchange(mcba_ctx* ctx, const Exchange& ex) {
-  if (ctx->world == 1 || ex.n == 0) return MCBA_OK;
+  if (ctx->world == 1) return MCBA_OK;
   size_t total = 0;
   for (int i = 0; i < ex.n; i++) total += ex.seg[i].count;
-  if (ctx->peer_ready && total <= (size_t)ctx->peer_cap) {
+  if (ctx->peer_ready && total > 0 && total <= (size_t)ctx->peer_cap && (!ex.epilogue || total <= 256)) {
     PeerArgs a{};
     for (int i = 0; i < ex.n; i++) a.seg[i] = ex.seg[i];
     a.nseg = ex.n; a.rank = ctx->rank; a.world = ctx->world; a.cap = ctx->peer_cap; a.seq = ++ctx->peer_seq;
     for (int r = 0; r < ctx->world; r++) a.base[r] = ctx->peer_base[r];
     a.counter = ctx->counter.p + 1;
+    a.epilogue = ex.epilogue; a.st = ctx->state.p; a.red = ctx->red.p;
     const int blocks = (int)std::min<size_t>(32, (total + 255) / 256);
     k_peer_allreduce<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(a); CKL();
     return MCBA_OK;
@@ -147,6 +148,7 @@ int run_exchange(mcba_ctx* ctx, const Exchange& ex) {
     rc = g_nccl.AllReduce(ex.seg[i].buf, ex.seg[i].buf, ex.seg[i].count, NCCL_FLOAT64, ex.seg[i].op == 0 ? NCCL_SUM : NCCL_MAX, ctx->comm, ctx->stream);
   if (g_nccl.GroupEnd) g_nccl.GroupEnd();
   if (rc != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return MCBA_ERR_NCCL; }
+  if (ex.epilogue) { k_epilogue<<<1, 1, 0, ctx->stream>>>(ex.epilogue, ctx->state.p, ctx->red.p); CKL(); }
   return MCBA_OK;
 }
 #define EXCHANGE(...) do { if (ctx->world > 1) { Exchange ex_; __VA_ARGS__; int r_ = run_exchange(ctx, ex_); if (r_) return r_; } } while (0)
@@ -819,8 +821,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       r = finish_linearization(ctx); if (r) return r;
       k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
                                  0, nullptr, 0, ctx->state.p); CKL();
-      EXCHANGE(ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1));
-      k_begin_iteration<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL();
+      EXCHANGE(ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1); ex_.epilogue = EPI_BEGIN);
     }
     first = 0;
     if (h.status != -99 || h.nfev >= h.max_nfev) {
@@ -836,7 +837,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     }
 
     r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, single ? 2 : 1); if (r) return r;
-    if (!single) { EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 1, 0)); k_reg<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }
+    EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 1, 0); ex_.epilogue = EPI_REG);
     // Schur complement of the frame blocks
     if (n_s > 0 && F == 0) {
       const size_t nn2 = (size_t)n_s * n_s;
@@ -880,7 +881,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
     r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1); if (r) return r;
-    if (!single) { EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0)); k_subspace<<<1, 1, 0, s>>>(ctx->state.p, ctx->red.p); CKL(); }   // AGG AGN ANN DOTGN_F GN2_F
+    EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE);   // AGG AGN ANN DOTGN_F GN2_F
 
     // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
     // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.
@@ -896,8 +897,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p, P.V, P.T); CKL();
       } else {
         k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p, P.V, P.T, ctx->red.p); CKL();
-        EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0));   // COSTNEW STEP2_F XN2_F
-        k_accept<<<1, 32, 0, s>>>(ctx->state.p, ctx->red.p, nullptr, 0, 0); CKL();
+        EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0); ex_.epilogue = EPI_ACCEPT);   // COSTNEW STEP2_F XN2_F
       }
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));

@@ -849,17 +849,8 @@ __global__ void k_cost_from_moments(const double* moments, int V, int T, double*
   if (threadIdx.x == 0) red[RED_COSTNEW] = c;
 }
 
-// single-GPU: the cost sum is done by the same CTA (moments != nullptr); multi-GPU: k_cost_from_moments, all-reduce, then this
-__global__ void k_accept(SolverState* st, double* red, const double* moments, int V, int T) {
-  __shared__ double sm[32];
-  if (st->done) return;
-  if (moments) {
-    double c = 0.0;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T + T - 1];
-    c = block_sum(c, sm);
-    if (threadIdx.x == 0) red[RED_COSTNEW] = c;
-  }
-  if (threadIdx.x != 0) return;
+// trf.py inner loop after fun(x_new): actual reduction, update_tr_radius, check_termination (one thread)
+__device__ inline void accept_compute(SolverState* st, const double* red) {
   st->nfev += 1;
   const double cost_new = red[RED_COSTNEW];
   st->cost_new = cost_new;
@@ -888,6 +879,34 @@ __global__ void k_accept(SolverState* st, double* red, const double* moments, in
   if (status == -99) st->Delta = Dn;
   st->accepted = actual > 0.0;
 }
+
+// single-GPU: the cost sum is done by the same CTA (moments != nullptr); multi-GPU: the sum, the exchange and the test are
+// separate (k_cost_from_moments, then the exchange kernel runs accept_compute as its epilogue)
+__global__ void k_accept(SolverState* st, double* red, const double* moments, int V, int T) {
+  __shared__ double sm[32];
+  if (st->done) return;
+  if (moments) {
+    double c = 0.0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T + T - 1];
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) red[RED_COSTNEW] = c;
+  }
+  if (threadIdx.x != 0) return;
+  accept_compute(st, red);
+}
+
+// scalar step that follows an exchange (run inside the exchange kernel when it goes over peer memory, as a 1-thread kernel after NCCL)
+enum { EPI_NONE = 0, EPI_BEGIN = 1, EPI_REG = 2, EPI_SUBSPACE = 3, EPI_ACCEPT = 4 };
+__device__ inline void run_epilogue(int epi, SolverState* st, double* red) {
+  switch (epi) {
+    case EPI_BEGIN: begin_iteration(st, red); break;
+    case EPI_REG: reg_compute(st, red); break;
+    case EPI_SUBSPACE: subspace_compute(st, red); break;
+    case EPI_ACCEPT: if (!st->done) accept_compute(st, red); break;
+    default: break;
+  }
+}
+__global__ void k_epilogue(int epi, SolverState* st, double* red) { run_epilogue(epi, st, red); }
 
 __global__ void k_axpby_copy(int n, const double* src, double* dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
