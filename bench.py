@@ -116,7 +116,7 @@ def run_reference(args):
                                 sample=f"{args.workload}: first {nf} of {scene['F']} frames ({n} corners), scipy TRF+LSMR with 2-point FD Jacobian, "
                                        f"host has {os.cpu_count()} cores, numpy/scipy path is single threaded"),
               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-  print(json.dumps(line))
+  emit(line)
 
 
 def run_ours(args):
@@ -250,11 +250,25 @@ def run_ours(args):
               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1e3 * t_e2e / args.steps,
                        lm_iters_per_sec=njev / t_e2e),
               gpu_launches=launches, clocks=sampler.summary(), roofline=roofline, cpu_baseline=cpu_baseline)
-  print(json.dumps(line))
+  emit(line)
   if world > 1: dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+  """The one JSON line goes to the real stdout; everything else this process (or NCCL) prints was sent to stderr."""
+  out = os.fdopen(os.dup(_REAL_STDOUT), "w") if _REAL_STDOUT is not None else sys.stdout
+  out.write(json.dumps(line) + "\n"); out.flush()
+
+
 def main():
+  global _REAL_STDOUT
+  # libraries (NCCL's version banner, torchrun warnings) may write to fd 1: keep stdout clean for the single JSON line
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=10)

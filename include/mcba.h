@@ -15,7 +15,8 @@
  * np.argwhere(calib.inliers) = (camera, frame, board, point) in row-major order of the dense
  * [C,F,B,P] table (calibration.py:206 boolean-mask order); residual vector element 2k is u, 2k+1 is v.
  * Parameter vector layout = reference order (calibration.py:146-153, parameters.py:104-106):
- *   [camera_poses 6C][board_poses 6B][motion 6F][cameras (5+nd)C]   (enabled blocks only)
+ *   [camera_poses 6C][board_poses 6B][motion 6F][cameras (5+nd)C][boards 3*B*P]   (enabled blocks only; the boards
+ *   block is the padded stack of tables.stack_boards -- the host strips the padding of boards with fewer points)
  *   pose = [rx ry rz tx ty tz] (transform/rtvec.py:16-27), camera = [fx fy cx cy skew dist...]
  *   (camera.py:144-155).
  */
@@ -40,6 +41,7 @@ enum { MCBA_LOSS_LINEAR = 0, MCBA_LOSS_SOFT_L1 = 1, MCBA_LOSS_HUBER = 2, MCBA_LO
 
 /* which parameter blocks are free: Calibration.optimize (calibration.py:28-35,155-161) */
 enum { MCBA_OPT_CAMERA_POSES = 1, MCBA_OPT_BOARD_POSES = 2, MCBA_OPT_MOTION = 4, MCBA_OPT_CAMERAS = 8,
+       MCBA_OPT_BOARDS = 16 /* board points as parameters (board/charuco.py:112-117); block layout = padded [B][P][3] */,
        MCBA_OPT_FIX_ASPECT = 256 /* camera.py:147-148,159-160 */ };
 
 typedef struct {

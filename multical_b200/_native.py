@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MCBA_LIB", os.path.join(_HERE, "libmcba.so"))     # M
 MODEL_IDS = {"standard": 0, "rational": 1, "thin_prism": 2, "fisheye": 3}
 DIST_SIZES = {"standard": 5, "rational": 8, "thin_prism": 12, "fisheye": 4}
 LOSS_IDS = {"linear": 0, "soft_l1": 1, "huber": 2, "cauchy": 3, "arctan": 4}
-OPT_BITS = {"camera_poses": 1, "board_poses": 2, "motion": 4, "cameras": 8}
+OPT_BITS = {"camera_poses": 1, "board_poses": 2, "motion": 4, "cameras": 8, "boards": 16}
 OPT_FIX_ASPECT = 256
 STATUS_MESSAGES = {
   -1: "Improper input parameters status returned from `leastsq`",

@@ -121,19 +121,42 @@ class Calibration(Parameters):
     return models.pop()
 
   def _optimize_bits(self):
-    if self.optimize["boards"] is True:
-      raise NotImplementedError("boards=True (board points as parameters) is not implemented on the GPU path yet")
     bits = sum(bit for k, bit in OPT_BITS.items() if self.optimize[k] is True)
     fix = {bool(getattr(c, "fix_aspect", False)) for c in self.cameras}
     assert len(fix) == 1, "fix_aspect must agree across cameras"
     return bits | (OPT_FIX_ASPECT if fix.pop() else 0)
 
   def _state_arrays(self):
-    cam_rt = rtvec.from_matrix(np.asarray(self.camera_poses.poses))
-    board_rt = rtvec.from_matrix(np.asarray(self.board_poses.poses))
-    frame_rt = rtvec.from_matrix(np.asarray(self.motion.poses))
+    # one rotation-vector conversion for all pose sets (the scipy call dominates the host time of a small solve)
+    sets = [np.asarray(self.camera_poses.poses), np.asarray(self.board_poses.poses), np.asarray(self.motion.poses)]
+    rt = rtvec.from_matrix(np.concatenate(sets, axis=0))
+    n0, n1 = sets[0].shape[0], sets[0].shape[0] + sets[1].shape[0]
     intr = np.stack([np.asarray(c.param_vec, np.float64) for c in self.cameras])
-    return cam_rt, board_rt, frame_rt, intr
+    return rt[:n0], rt[n0:n1], rt[n1:], intr
+
+  # The C-ABI keeps the `boards` block as the padded [B][P][3] stack (tables.stack_boards); the reference's vector holds
+  # only each board's own points (board/charuco.py:112-117).  These two helpers translate between the two layouts.
+  def _board_block_slices(self):
+    P = self.size.points
+    keep = np.concatenate([np.arange(3 * P) < 3 * b.num_points for b in self.boards])
+    return keep
+
+  def _to_engine_vec(self, x):
+    if self.optimize["boards"] is not True: return np.asarray(x, np.float64)
+    keep = self._board_block_slices()
+    head = x.size - int(keep.sum())
+    out = np.zeros(head + keep.size)
+    out[:head] = x[:head]
+    tail = np.asarray(self.board_points.points, np.float64).ravel().copy()
+    tail[keep] = x[head:]
+    out[head:] = tail
+    return out
+
+  def _from_engine_vec(self, xe):
+    if self.optimize["boards"] is not True: return xe
+    keep = self._board_block_slices()
+    head = xe.size - keep.size
+    return np.concatenate([xe[:head], xe[head:][keep]])
 
   def _upload(self, mask, points=None, device=None):
     eng = get_engine(device)
@@ -228,7 +251,7 @@ class Calibration(Parameters):
     info(res.message)
     info(f"Function evaluations {res.nfev}, initial cost {res.initial_cost:.4e}, final cost {res.cost:.4e}, "
          f"first-order optimality {res.optimality:.2e}.")
-    out = self.with_param_vec(eng.param_vec)
+    out = self.with_param_vec(self._from_engine_vec(eng.param_vec))
     out.__dict__["last_solve"] = res
     return out
 

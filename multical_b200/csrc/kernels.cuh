@@ -37,7 +37,7 @@ struct DeviceProblem {
   const int* frame_view_start;   // [F+1]
   const int* cam_view_start;     // [C+1]
   const int* cam_view_list;      // [V] view ids grouped by camera
-  const double* board_pts;       // [B][P][3]
+  double* board_pts;             // [B][P][3]  (parameters when off_pt >= 0: boards=True, board/charuco.py:112-117)
   // parameter state (full, including fixed blocks)
   double* cam_rt;    // [C][6]
   double* board_rt;  // [B][6]
@@ -49,7 +49,7 @@ struct DeviceProblem {
   PoseT* board_T;
   // solver variable layout: x = [shared (n_s) | frames (6F if motion free)]
   int n, n_s, n_f;
-  int off_cp, off_bp, off_in;    // offsets inside shared, -1 when the block is fixed
+  int off_cp, off_bp, off_in, off_pt;   // offsets inside shared, -1 when the block is fixed (off_pt: 3 per padded board point)
   int motion_on, fix_aspect;
 };
 
@@ -76,7 +76,7 @@ __global__ void k_prepare(DeviceProblem p, const double* cam_rt, const double* b
 
 // k_make_trial: trial parameter state = current state with the free blocks replaced by x (internal order), and the
 // pose tables of that state, in one launch.  One thread per pose, then one per camera (intrinsics).
-__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o) {
+__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int np = p.C + p.B + p.F;
   if (i < np) {
@@ -101,6 +101,10 @@ __global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, do
       if (j == 1 && p.fix_aspect && p.off_in >= 0) v = src[0];      // fy follows fx (camera.py:159-160)
       intr_o[p.kint * c + j] = v;
     }
+  } else if (i < np + p.C + p.B * p.P) {
+    const int q = i - np - p.C;                                       // padded board point index b*P + p
+    const double* src = p.off_pt >= 0 ? x + p.off_pt + 3 * q : p.board_pts + 3 * q;
+    bpts_o[3 * q] = src[0]; bpts_o[3 * q + 1] = src[1]; bpts_o[3 * q + 2] = src[2];
   }
 }
 
@@ -441,6 +445,125 @@ __device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int loca
   // local [fx fy cx cy dist...] -> index in [fx fy cx cy skew dist...]; fix_aspect folds fy onto fx (camera.py:159-160)
   if (local == 1 && p.fix_aspect) return 0;
   return local < 4 ? local : local + 1;
+}
+
+__device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int local);
+
+// k_point_blocks (boards=True only): board points as shared parameters (3 per padded point).  One warp per view, one
+// thread per corner: d r / d X_board = J_proj R_cfb; the point's own 3x3 block, its gradient and its couplings with the
+// camera pose / intrinsics / board pose (H_ss) and the frame pose (W_f) are added with fp64 atomics on top of what the
+// expand kernels wrote.  Replaces the axis-3 column block of the reference's sparsity pattern (calibration.py:188-190).
+template <int MODEL>
+__global__ void __launch_bounds__(VIEW_WARPS * 32)
+k_point_blocks(DeviceProblem p, ViewKernelArgs a, double* Hss, double* W, double* g) {
+  constexpr int ND = model_nd(MODEL);
+  constexpr int KINT = 5 + ND;
+  constexpr int NIN = 4 + ND;
+  __shared__ double maps[VIEW_WARPS][108];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * VIEW_WARPS + warp, nw = gridDim.x * VIEW_WARPS;
+  const int n_s = p.n_s;
+  double* Ac = maps[warp]; double* Af = Ac + 36; double* Ab = Af + 36;
+  for (int v = gw; v < p.V; v += nw) {
+    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
+    const int beg = p.view_start[v], end = p.view_start[v + 1];
+    const PoseT& pc = p.cam_T[c]; const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
+    ViewPose vp;
+    compose_view(pc, pf, pb, vp);
+    __syncwarp();
+    if (lane < 3) {
+      double Rcf[9], tcf[3];
+      mat3_mul(pc.R, pf.R, Rcf);
+      mat3_vec(pc.R, pf.t, tcf);
+      tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
+      if (lane == 0) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
+      else if (lane == 1) twist_map(pc.R, pf.JL, tcf, Af);
+      else twist_map(Rcf, pb.JL, vp.t, Ab);
+    }
+    __syncwarp();
+    double k[KINT];
+#pragma unroll
+    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
+    const double* bp = p.board_pts + (size_t)b * p.P * 3;
+    const int cp = p.off_cp >= 0 ? p.off_cp + 6 * c : -1;
+    const int bpo = p.off_bp >= 0 ? p.off_bp + 6 * b : -1;
+    const int in0 = p.off_in >= 0 ? p.off_in + p.kint * c : -1;
+    for (int idx = beg + lane; idx < end; idx += 32) {
+      const double2 ob = p.obs[idx];
+      const int pi = p.pid[idx];
+      const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
+      double Xc[3];
+      mat3_vec(vp.R, X, Xc);
+      Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+      double u, w_, Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
+      project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
+      double ru = u - ob.x, rv = w_ - ob.y, wu = 1.0, wv = 1.0;
+      if (a.loss != 0) {
+        const double is = 1.0 / a.f_scale;
+        double zu = ru * is, zv = rv * is;
+        zu *= zu; zv *= zv;
+        double r0u, r1u, r2u, r0v, r1v, r2v;
+        loss_rho(a.loss, zu, r0u, r1u, r2u);
+        loss_rho(a.loss, zv, r0v, r1v, r2v);
+        double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
+        ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
+        jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
+        wu = sqrt(ju); wv = sqrt(jv);
+        ru *= r1u / wu; rv *= r1v / wv;
+      }
+      // local rows: twist (6) then [fx fy cx cy dist] (NIN)
+      double gu[6 + NIN], gv[6 + NIN];
+      gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
+      gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
+#pragma unroll
+      for (int i = 0; i < NIN; i++) { gu[6 + i] = 0.0; gv[6 + i] = 0.0; }
+      gu[6] = ku[0] * wu; gu[8] = wu; gv[7] = kv[1] * wv; gv[9] = wv;
+#pragma unroll
+      for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
+      // point rows: d r / d X_board = J_proj R_cfb
+      double xu[3], xv[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        xu[j] = (Ju[0] * vp.R[j] + Ju[1] * vp.R[3 + j] + Ju[2] * vp.R[6 + j]) * wu;
+        xv[j] = (Jv[0] * vp.R[j] + Jv[1] * vp.R[3 + j] + Jv[2] * vp.R[6 + j]) * wv;
+      }
+      const int pt = p.off_pt + 3 * (b * p.P + pi);
+      auto addS = [&](int i, int j, double val) {
+        atomicAdd(&Hss[(size_t)i * n_s + j], val);
+        atomicAdd(&Hss[(size_t)j * n_s + i], val);
+      };
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        atomicAdd(&g[pt + r], xu[r] * ru + xv[r] * rv);
+#pragma unroll
+        for (int q = r; q < 3; q++) {
+          const double val = xu[r] * xu[q] + xv[r] * xv[q];
+          if (q == r) atomicAdd(&Hss[(size_t)(pt + r) * n_s + pt + r], val); else addS(pt + r, pt + q, val);
+        }
+        double Q[6];
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) Q[kk] = xu[r] * gu[kk] + xv[r] * gv[kk];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          double vc = 0.0, vf = 0.0, vb = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 6; kk++) { vc += Q[kk] * Ac[kk * 6 + j]; vf += Q[kk] * Af[kk * 6 + j]; vb += Q[kk] * Ab[kk * 6 + j]; }
+          if (cp >= 0) addS(pt + r, cp + j, vc);
+          if (bpo >= 0) addS(pt + r, bpo + j, vb);
+          if (p.motion_on) atomicAdd(&W[((size_t)f * n_s + pt + r) * 6 + j], vf);
+        }
+        if (in0 >= 0) {
+#pragma unroll
+          for (int i = 0; i < NIN; i++) {
+            const double val = xu[r] * gu[6 + i] + xv[r] * gv[6 + i];
+            if (val != 0.0) addS(pt + r, in0 + intr_param_index(p, i), val);
+          }
+        }
+      }
+    }
+  }
 }
 
 // Both expand kernels work warp-per-view: a warp pulls one view's moment record (T doubles) into its private shared

@@ -88,13 +88,14 @@ struct mcba_ctx {
   DevBuf<uint8_t> dense_mask; DevBuf<double2> dense_pts; DevBuf<int> scan;
   DevBuf<PoseT> cam_T, frame_T, board_T;
   // trial parameter state
-  DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2;
+  DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2, board_pts2;
   // solver buffers
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
   DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
   DevBuf<SolverState> state;
   DevBuf<unsigned> counter;
   int shared_chunks = 1;
+  int cur_loss = 0; double cur_f_scale = 1.0;     // loss of the linearisation in flight (k_point_blocks re-derives the row weights)
   // peer-memory all-reduce (peer_allreduce.cuh)
   double* peer_own = nullptr; int peer_cap = 0; bool peer_ready = false; unsigned peer_seq = 0;
   double* peer_base[PEER_MAX_WORLD] = {nullptr};
@@ -163,7 +164,8 @@ __global__ void k_scatter_params(DeviceProblem p, const double* x, double* cam_r
   if (i >= p.n_s) { frame_rt[i - p.n_s] = v; return; }
   if (p.off_cp >= 0 && i >= p.off_cp && i < p.off_cp + 6 * p.C) { cam_rt[i - p.off_cp] = v; return; }
   if (p.off_bp >= 0 && i >= p.off_bp && i < p.off_bp + 6 * p.B) { board_rt[i - p.off_bp] = v; return; }
-  if (p.off_in >= 0 && i >= p.off_in) { intr[i - p.off_in] = v; }
+  if (p.off_in >= 0 && i >= p.off_in && i < p.off_in + p.kint * p.C) { intr[i - p.off_in] = v; return; }
+  if (p.off_pt >= 0 && i >= p.off_pt) { p.board_pts[i - p.off_pt] = v; }
 }
 __global__ void k_gather_params(DeviceProblem p, double* x, const double* cam_rt, const double* board_rt, const double* frame_rt, const double* intr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,7 +174,8 @@ __global__ void k_gather_params(DeviceProblem p, double* x, const double* cam_rt
   if (i >= p.n_s) v = frame_rt[i - p.n_s];
   else if (p.off_cp >= 0 && i >= p.off_cp && i < p.off_cp + 6 * p.C) v = cam_rt[i - p.off_cp];
   else if (p.off_bp >= 0 && i >= p.off_bp && i < p.off_bp + 6 * p.B) v = board_rt[i - p.off_bp];
-  else if (p.off_in >= 0 && i >= p.off_in) v = intr[i - p.off_in];
+  else if (p.off_in >= 0 && i >= p.off_in && i < p.off_in + p.kint * p.C) v = intr[i - p.off_in];
+  else if (p.off_pt >= 0 && i >= p.off_pt) v = p.board_pts[i - p.off_pt];
   x[i] = v;
 }
 // copies the fixed blocks so that a trial state is complete; with fix_aspect fy follows fx (camera.py:159-160)
@@ -225,7 +228,7 @@ int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& 
 // DeviceProblem view whose parameter pointers are the trial state
 DeviceProblem with_state(const mcba_ctx* ctx, bool trial) {
   DeviceProblem P = ctx->P;
-  if (trial) { P.cam_rt = ctx->cam_rt2.p; P.board_rt = ctx->board_rt2.p; P.frame_rt = ctx->frame_rt2.p; P.intr = ctx->intr2.p; }
+  if (trial) { P.cam_rt = ctx->cam_rt2.p; P.board_rt = ctx->board_rt2.p; P.frame_rt = ctx->frame_rt2.p; P.intr = ctx->intr2.p; P.board_pts = ctx->board_pts2.p; }
   return P;
 }
 
@@ -252,6 +255,7 @@ size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((si
 
 // per-view moment records of the (trial or current) state; the pose tables must already describe that state
 int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial) {
+  ctx->cur_loss = loss; ctx->cur_f_scale = f_scale;
   DeviceProblem P = with_state(ctx, trial);
   ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p;
   return launch_moments(ctx, P, a);
@@ -269,6 +273,17 @@ int expand(mcba_ctx* ctx) {
   }
   const int nb = P.C * ctx->shared_chunks;
   k_expand_shared<<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
+  if (P.off_pt >= 0 && P.V > 0) {         // boards=True: board-point blocks on top (atomics)
+    ViewKernelArgs a{}; a.loss = ctx->cur_loss; a.f_scale = ctx->cur_f_scale;
+    const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
+    switch (P.model) {
+      case MODEL_STANDARD: k_point_blocks<MODEL_STANDARD><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
+      case MODEL_RATIONAL: k_point_blocks<MODEL_RATIONAL><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
+      case MODEL_THIN_PRISM: k_point_blocks<MODEL_THIN_PRISM><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
+      default: k_point_blocks<MODEL_FISHEYE><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
+    }
+    CKL();
+  }
   return MCBA_OK;
 }
 
@@ -326,6 +341,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   P.off_cp = (opt & MCBA_OPT_CAMERA_POSES) ? off : -1; if (P.off_cp >= 0) off += 6 * C;
   P.off_bp = (opt & MCBA_OPT_BOARD_POSES) ? off : -1; if (P.off_bp >= 0) off += 6 * B;
   P.off_in = (opt & MCBA_OPT_CAMERAS) ? off : -1; if (P.off_in >= 0) off += P.kint * C;
+  P.off_pt = (opt & MCBA_OPT_BOARDS) ? off : -1; if (P.off_pt >= 0) off += 3 * B * Pn;
   P.n_s = off; P.n_f = P.motion_on ? 6 * F : 0; P.n = P.n_s + P.n_f;
   // internal -> canonical permutation: canonical = [cp | bp | motion | cameras]
   ctx->perm.assign((size_t)P.n, 0);
@@ -335,6 +351,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     if (P.off_bp >= 0) { for (int i = 0; i < 6 * B; i++) ctx->perm[(size_t)P.off_bp + i] = canon + i; canon += 6 * B; }
     if (P.motion_on) { for (int i = 0; i < 6 * F; i++) ctx->perm[(size_t)P.n_s + i] = canon + i; canon += 6 * F; }
     if (P.off_in >= 0) { for (int i = 0; i < P.kint * C; i++) ctx->perm[(size_t)P.off_in + i] = canon + i; canon += P.kint * C; }
+    if (P.off_pt >= 0) { for (int i = 0; i < 3 * B * Pn; i++) ctx->perm[(size_t)P.off_pt + i] = canon + i; canon += 3 * B * Pn; }
   }
 
   CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr.alloc((size_t)C * P.kint));
@@ -699,6 +716,7 @@ int mcba_residuals(mcba_ctx* ctx, const double* x, double* r_out, double* cost) 
     CK(cudaMemcpyAsync(ctx->board_rt2.p, ctx->board_rt.p, sizeof(double) * P0.B * 6, cudaMemcpyDeviceToDevice, ctx->stream));
     if (P0.F) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P0.F * 6, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P0.C * P0.kint, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->board_pts2.p, ctx->board_pts.p, sizeof(double) * P0.B * P0.P * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     int r = write_x_canonical(ctx, x, ctx->x_new.p); if (r) return r;
     r = set_state_from_x(ctx, ctx->x_new.p, true); if (r) return r;
     trial = true;
@@ -889,8 +907,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     while (true) {
       k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
       {
-        const int nt = P.C + P.B + P.F + P.C;
-        k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p); CKL();
+        const int nt = P.C + P.B + P.F + P.C + P.B * P.P;
+        k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p); CKL();
       }
       r = moments_at(ctx, opts->loss, opts->f_scale, true); if (r) return r;
       if (single) {
@@ -917,7 +935,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       // x = x_new ; cost = cost_new ; J = jac(x)   (trf.py): the trial state, its pose tables and its moments become current
       std::swap(ctx->x.p, ctx->x_new.p);
       std::swap(ctx->cam_rt.p, ctx->cam_rt2.p); std::swap(ctx->board_rt.p, ctx->board_rt2.p);
-      std::swap(ctx->frame_rt.p, ctx->frame_rt2.p); std::swap(ctx->intr.p, ctx->intr2.p);
+      std::swap(ctx->frame_rt.p, ctx->frame_rt2.p); std::swap(ctx->intr.p, ctx->intr2.p); std::swap(ctx->board_pts.p, ctx->board_pts2.p);
+      ctx->P.board_pts = ctx->board_pts.p;
       ctx->P.cam_rt = ctx->cam_rt.p; ctx->P.board_rt = ctx->board_rt.p; ctx->P.frame_rt = ctx->frame_rt.p; ctx->P.intr = ctx->intr.p;
       h.cost = h.cost_new;
       h.njev += 1;

@@ -256,3 +256,39 @@ def test_empty_and_ragged_inputs():
   assert eng.N == 0 and eng.residuals().size == 0
   res = eng.solve(max_nfev=5)
   assert res.cost == 0.0 and res.status == 1        # gradient is exactly zero -> gtol
+
+
+def test_board_points_as_parameters():
+  """boards=True (adjust_board): 3 parameters per board point, axis-3 columns of the reference's Jacobian
+  (calibration.py:188-190, board/charuco.py:112-117)."""
+  scene = synthetic.make_scene(C=3, F=8, vis=0.6, seed=81, boards=("cube", 6, 5, 0.05, 2), rig="dome")
+  opt = dict(cameras=True, boards=True)
+  calib = from_scene(scene).enable(**opt)
+  prob = Problem.from_scene(scene, optimize=opt)
+  x0 = prob.param_vec
+  assert np.array_equal(calib.param_vec, x0)
+  eng = calib._upload(calib.inliers)
+  assert np.array_equal(calib._from_engine_vec(eng.param_vec), x0)
+  x1 = x0 + np.random.default_rng(8).normal(0, 1e-3, x0.size)
+  r1 = eng.residuals(calib._to_engine_vec(x1))
+  assert np.abs(r1 - prob.residuals(x1)).max() < 1e-9
+  S = prob.sparsity_matrix()
+  J = approx_derivative(prob.residuals, x1, method="3-point", sparsity=(S, group_columns(S))).toarray()
+  H, g = J.T @ J, J.T @ prob.residuals(x1)
+  JtJ, Jtr, cost = eng.linearize(calib._to_engine_vec(x1))
+  keep = calib._board_block_slices()
+  head = JtJ.shape[0] - keep.size
+  sel = np.concatenate([np.ones(head, bool), keep])
+  JtJ, Jtr = JtJ[np.ix_(sel, sel)], Jtr[sel]
+  nrm = np.sqrt(np.outer(np.diag(H), np.diag(H))); live = nrm > 0
+  assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  assert np.abs(Jtr - g).max() < 1e-6 * np.abs(g).max()
+  # the solve: never worse than the reference algorithm, and board points actually move
+  out = calib.bundle_adjust(tolerance=1e-8, max_iterations=60)
+  _, ref = prob.bundle_adjust(tolerance=1e-8, max_iterations=60)
+  assert out.last_solve.cost <= ref.cost * (1 + 1e-6), (out.last_solve.cost, ref.cost)
+  moved = max(np.abs(np.asarray(b1.adjusted_points) - np.asarray(b0.adjusted_points)).max() for b0, b1 in zip(calib.boards, out.boards))
+  assert 0 < moved < 0.05
+  # without boards=True the same scene must reach a higher (or equal) cost
+  base = from_scene(scene).enable(cameras=True).bundle_adjust(tolerance=1e-8, max_iterations=60)
+  assert out.last_solve.cost <= base.last_solve.cost * (1 + 1e-9)
