@@ -357,6 +357,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr.alloc((size_t)C * P.kint));
   CK(ctx->cam_rt2.alloc((size_t)C * 6)); CK(ctx->board_rt2.alloc((size_t)B * 6)); CK(ctx->frame_rt2.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr2.alloc((size_t)C * P.kint));
   CK(ctx->cam_T.alloc(C)); CK(ctx->frame_T.alloc(std::max(F, 1))); CK(ctx->board_T.alloc(B));
+  CK(ctx->board_pts2.alloc((size_t)B * Pn * 3));
   // solver buffers
   ctx->shared_chunks = std::max(1, std::min(32, (ctx->num_sms * 2) / std::max(C, 1)));
   if (V / std::max(C, 1) < 64) ctx->shared_chunks = 1;
