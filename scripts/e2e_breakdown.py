@@ -1,0 +1,40 @@
+"""Where does the end-to-end time of Calibration.bundle_adjust() go? (developer diagnostics, GPU box)"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from multical_b200 import synthetic
+from multical_b200.calibration import from_scene, get_engine
+from multical_b200.engine import format_log
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+scene = synthetic.make_workload(wl)
+for key in ("points", "valid"):
+  scene[key] = torch.from_numpy(np.ascontiguousarray(scene[key])).pin_memory().numpy()
+eng = get_engine()
+def T(label, f, n=20):
+  f(); torch.cuda.synchronize()
+  t = time.perf_counter()
+  for _ in range(n): out = f()
+  torch.cuda.synchronize()
+  print(f"{label:40s} {(time.perf_counter() - t) / n * 1e3:8.3f} ms", flush=True)
+  return out
+calib = from_scene(scene).enable(cameras=True)
+T("from_scene + enable", lambda: from_scene(scene).enable(cameras=True))
+T("inliers (valid mask)", lambda: from_scene(scene).inliers)
+T("board_points", lambda: from_scene(scene).board_points)
+T("_optimize_bits + engine_model", lambda: (from_scene(scene).enable(cameras=True)._optimize_bits(), from_scene(scene).engine_model))
+m, pts, bp = calib.inliers, np.asarray(calib.point_table.points), calib.board_points.points
+T("upload_dense", lambda: eng.upload_dense(calib.engine_model, calib._optimize_bits(), m, pts, bp))
+T("_state_arrays", lambda: from_scene(scene).enable(cameras=True)._state_arrays())
+st = calib._state_arrays()
+T("set_params", lambda: eng.set_params(*st))
+def solve():
+  eng.set_params(*st); return eng.solve(ftol=1e-4, max_nfev=100)
+res = T("set_params + solve", solve)
+print("   device_ms", res.device_ms, "launches", res.kernel_launches)
+T("format_log + info", lambda: [l for l in format_log(res.log)])
+T("eng.param_vec", lambda: eng.param_vec)
+x = eng.param_vec
+T("with_param_vec", lambda: calib.with_param_vec(x))
+T("full bundle_adjust (fresh object)", lambda: from_scene(scene).enable(cameras=True).bundle_adjust())
