@@ -32,9 +32,10 @@ typedef struct mcba_ctx mcba_ctx;
 enum { MCBA_OK = 0, MCBA_ERR_ARG = 1, MCBA_ERR_CUDA = 2, MCBA_ERR_STATE = 3, MCBA_ERR_NCCL = 4,
        MCBA_ERR_NONFINITE = 5, MCBA_ERR_UNSUPPORTED = 6 };
 
-/* camera models: camera.py:43-48 (cv2.projectPoints, 5/8/12 coefficients) and
+/* camera models: camera.py:43-48 (cv2.projectPoints, 5/8/12/14 coefficients) and
  * camera_fisheye.py:113-117 (cv2.fisheye.projectPoints, 4 coefficients) */
-enum { MCBA_MODEL_STANDARD = 0, MCBA_MODEL_RATIONAL = 1, MCBA_MODEL_THIN_PRISM = 2, MCBA_MODEL_FISHEYE = 3 };
+enum { MCBA_MODEL_STANDARD = 0, MCBA_MODEL_RATIONAL = 1, MCBA_MODEL_THIN_PRISM = 2, MCBA_MODEL_FISHEYE = 3,
+       MCBA_MODEL_TILTED = 4 /* 14 coefficients: thin prism + sensor tilt (tauX, tauY) */ };
 
 /* loss names of scipy.optimize.least_squares (config/arguments.py:59) */
 enum { MCBA_LOSS_LINEAR = 0, MCBA_LOSS_SOFT_L1 = 1, MCBA_LOSS_HUBER = 2, MCBA_LOSS_CAUCHY = 3, MCBA_LOSS_ARCTAN = 4 };

@@ -8,8 +8,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MCBA_LIB", os.path.join(_HERE, "libmcba.so"))     # MCBA_LIB: developer A/B builds only
 
-MODEL_IDS = {"standard": 0, "rational": 1, "thin_prism": 2, "fisheye": 3}
-DIST_SIZES = {"standard": 5, "rational": 8, "thin_prism": 12, "fisheye": 4}
+MODEL_IDS = {"standard": 0, "rational": 1, "thin_prism": 2, "fisheye": 3, "tilted": 4}
+DIST_SIZES = {"standard": 5, "rational": 8, "thin_prism": 12, "fisheye": 4, "tilted": 14}
 LOSS_IDS = {"linear": 0, "soft_l1": 1, "huber": 2, "cauchy": 3, "arctan": 4}
 OPT_BITS = {"camera_poses": 1, "board_poses": 2, "motion": 4, "cameras": 8, "boards": 16}
 OPT_FIX_ASPECT = 256

@@ -78,7 +78,6 @@ def engine_model_of(camera):
   """Which CUDA camera model a (reference or mirror) camera object needs."""
   if type(camera).__name__ == "CameraFisheye": return "fisheye"
   model = getattr(camera, "model", "standard")
-  if model == "tilted": raise NotImplementedError("tilted (14-coefficient) sensor model is not implemented on the GPU path")
   nd = np.size(camera.dist)
   expect = DIST_SIZE[model]
   assert nd == expect, f"camera model {model} expects {expect} distortion coefficients, got {nd}"

@@ -11,10 +11,10 @@
 
 namespace mcba {
 
-enum { MODEL_STANDARD = 0, MODEL_RATIONAL = 1, MODEL_THIN_PRISM = 2, MODEL_FISHEYE = 3 };
+enum { MODEL_STANDARD = 0, MODEL_RATIONAL = 1, MODEL_THIN_PRISM = 2, MODEL_FISHEYE = 3, MODEL_TILTED = 4 };
 
 __host__ __device__ constexpr int model_nd(int model) {
-  return model == MODEL_STANDARD ? 5 : model == MODEL_RATIONAL ? 8 : model == MODEL_THIN_PRISM ? 12 : 4;
+  return model == MODEL_STANDARD ? 5 : model == MODEL_RATIONAL ? 8 : model == MODEL_THIN_PRISM ? 12 : model == MODEL_TILTED ? 14 : 4;
 }
 // local Jacobian layout of one residual row: [omega(3) v(3) fx fy cx cy dist(nd)]  (skew has no effect:
 // cv2 ignores K[0,1]) -> D = 10 + nd
@@ -90,6 +90,34 @@ __device__ __forceinline__ void twist_map(const double* Rl, const double* JL, co
   }
 }
 
+// Tilted-sensor matrix of the 14-coefficient model and its derivatives wrt (tauX, tauY): restatement of OpenCV's
+// cv::detail::computeTiltProjectionMatrix (the reference reaches it through cv2.projectPoints, camera.py:43-48,124-128).
+//   matTilt = P_z(R_y R_x) R_y R_x ,  P_z(R) = [[R22, 0, -R02], [0, R22, -R12], [0, 0, 1]]
+__device__ inline void tilt_matrices(double tx, double ty, double* M, double* dMx, double* dMy) {
+  double sx, cx, sy, cy;
+  sincos(tx, &sx, &cx);
+  sincos(ty, &sy, &cy);
+  const double Rx[9] = {1, 0, 0, 0, cx, sx, 0, -sx, cx};
+  const double Ry[9] = {cy, 0, -sy, 0, 1, 0, sy, 0, cy};
+  const double dRx[9] = {0, 0, 0, 0, -sx, cx, 0, -cx, -sx};
+  const double dRy[9] = {-sy, 0, -cy, 0, 0, 0, cy, 0, -sy};
+  double R[9], dRa[9], dRb[9];
+  mat3_mul(Ry, Rx, R);
+  mat3_mul(Ry, dRx, dRa);        // d(RyRx)/dtauX
+  mat3_mul(dRy, Rx, dRb);        // d(RyRx)/dtauY
+  const double Pz[9] = {R[8], 0, -R[2], 0, R[8], -R[5], 0, 0, 1};
+  const double dPa[9] = {dRa[8], 0, -dRa[2], 0, dRa[8], -dRa[5], 0, 0, 0};
+  const double dPb[9] = {dRb[8], 0, -dRb[2], 0, dRb[8], -dRb[5], 0, 0, 0};
+  double t1[9], t2[9];
+  mat3_mul(Pz, R, M);
+  mat3_mul(Pz, dRa, t1); mat3_mul(dPa, R, t2);
+#pragma unroll
+  for (int i = 0; i < 9; i++) dMx[i] = t1[i] + t2[i];
+  mat3_mul(Pz, dRb, t1); mat3_mul(dPb, R, t2);
+#pragma unroll
+  for (int i = 0; i < 9; i++) dMy[i] = t1[i] + t2[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Camera models.  k points at [fx fy cx cy skew dist...] (camera.py:144-155).  Outputs u,v; when JAC:
 //   Ju,Jv = d(u,v)/dX_cam (3 each);  ku,kv = d(u,v)/d[fx fy cx cy dist...] (4+nd each; fy,cy of ku and
@@ -144,8 +172,13 @@ __device__ __forceinline__ void project(const double* X, const double* __restric
       xd += d[8] * r2 + d[9] * r4;
       yd += d[10] * r2 + d[11] * r4;
     }
-    u = fx * xd + cx;
-    v = fy * yd + cy;
+    if constexpr (ND < 14) {
+      u = fx * xd + cx;
+      v = fy * yd + cy;
+    }
+    // derivatives of the distorted normalised point (xd, yd) wrt (x, y) and wrt the distortion coefficients
+    double xx = 0, xy = 0, yx = 0, yy = 0;
+    double dxk[ND], dyk[ND];
     if constexpr (JAC) {
       const double dcd = k1 + 2.0 * k2 * r2 + 3.0 * k3 * r4;
       double drad = dcd;
@@ -153,25 +186,59 @@ __device__ __forceinline__ void project(const double* X, const double* __restric
       double tpx = 0.0, tpy = 0.0;
       if constexpr (ND >= 12) { tpx = d[8] + 2.0 * d[9] * r2; tpy = d[10] + 2.0 * d[11] * r2; }
       const double cross = a1 * drad + 2.0 * p1 * x + 2.0 * p2 * y;
-      const double xx = rad + 2.0 * x * x * drad + 2.0 * p1 * y + 6.0 * p2 * x + 2.0 * x * tpx;
-      const double xy = cross + 2.0 * y * tpx;
-      const double yx = cross + 2.0 * x * tpy;
-      const double yy = rad + 2.0 * y * y * drad + 6.0 * p1 * y + 2.0 * p2 * x + 2.0 * y * tpy;
-      Ju[0] = fx * xx * iz; Ju[1] = fx * xy * iz; Ju[2] = -fx * (xx * x + xy * y) * iz;
-      Jv[0] = fy * yx * iz; Jv[1] = fy * yy * iz; Jv[2] = -fy * (yx * x + yy * y) * iz;
-      ku[0] = xd; ku[2] = 1.0;
-      kv[1] = yd; kv[3] = 1.0;
-      const double fxx = fx * x * icd2, fyy = fy * y * icd2;
-      ku[4] = fxx * r2; ku[5] = fxx * r4; ku[6] = fx * a1; ku[7] = fx * a2; ku[8] = fxx * r6;
-      kv[4] = fyy * r2; kv[5] = fyy * r4; kv[6] = fy * a3; kv[7] = fy * a1; kv[8] = fyy * r6;
+      xx = rad + 2.0 * x * x * drad + 2.0 * p1 * y + 6.0 * p2 * x + 2.0 * x * tpx;
+      xy = cross + 2.0 * y * tpx;
+      yx = cross + 2.0 * x * tpy;
+      yy = rad + 2.0 * y * y * drad + 6.0 * p1 * y + 2.0 * p2 * x + 2.0 * y * tpy;
+      const double xi = x * icd2, yi = y * icd2;
+      dxk[0] = xi * r2; dxk[1] = xi * r4; dxk[2] = a1; dxk[3] = a2; dxk[4] = xi * r6;
+      dyk[0] = yi * r2; dyk[1] = yi * r4; dyk[2] = a3; dyk[3] = a1; dyk[4] = yi * r6;
       if constexpr (ND >= 8) {
-        const double gx = -fxx * rad, gy = -fyy * rad;     // -f x cdist icd2^2
-        ku[9] = gx * r2; ku[10] = gx * r4; ku[11] = gx * r6;
-        kv[9] = gy * r2; kv[10] = gy * r4; kv[11] = gy * r6;
+        const double gx = -xi * rad, gy = -yi * rad;     // -x cdist icd2^2
+        dxk[5] = gx * r2; dxk[6] = gx * r4; dxk[7] = gx * r6;
+        dyk[5] = gy * r2; dyk[6] = gy * r4; dyk[7] = gy * r6;
       }
       if constexpr (ND >= 12) {
-        ku[12] = fx * r2; ku[13] = fx * r4; ku[14] = 0.0; ku[15] = 0.0;
-        kv[12] = 0.0; kv[13] = 0.0; kv[14] = fy * r2; kv[15] = fy * r4;
+        dxk[8] = r2; dxk[9] = r4; dxk[10] = 0.0; dxk[11] = 0.0;
+        dyk[8] = 0.0; dyk[9] = 0.0; dyk[10] = r2; dyk[11] = r4;
+      }
+    }
+    if constexpr (ND < 14) {
+      if constexpr (JAC) {
+        Ju[0] = fx * xx * iz; Ju[1] = fx * xy * iz; Ju[2] = -fx * (xx * x + xy * y) * iz;
+        Jv[0] = fy * yx * iz; Jv[1] = fy * yy * iz; Jv[2] = -fy * (yx * x + yy * y) * iz;
+        ku[0] = xd; ku[2] = 1.0;
+        kv[1] = yd; kv[3] = 1.0;
+#pragma unroll
+        for (int i = 0; i < ND; i++) { ku[4 + i] = fx * dxk[i]; kv[4 + i] = fy * dyk[i]; }
+      }
+    } else {
+      // tilted sensor: (xt, yt) = perspective division of matTilt (xd, yd, 1)
+      double M[9], dMx[9], dMy[9];
+      tilt_matrices(d[12], d[13], M, dMx, dMy);
+      const double v0 = M[0] * xd + M[1] * yd + M[2], v1 = M[3] * xd + M[4] * yd + M[5], v2 = M[6] * xd + M[7] * yd + M[8];
+      const double ip = (v2 != 0.0) ? 1.0 / v2 : 1.0;
+      const double xt = v0 * ip, yt = v1 * ip;
+      u = fx * xt + cx;
+      v = fy * yt + cy;
+      if constexpr (JAC) {
+        const double T00 = (M[0] - M[6] * xt) * ip, T01 = (M[1] - M[7] * xt) * ip;
+        const double T10 = (M[3] - M[6] * yt) * ip, T11 = (M[4] - M[7] * yt) * ip;
+        const double ux = T00 * xx + T01 * yx, uy = T00 * xy + T01 * yy;      // d xt / d(x, y)
+        const double vx = T10 * xx + T11 * yx, vy = T10 * xy + T11 * yy;      // d yt / d(x, y)
+        Ju[0] = fx * ux * iz; Ju[1] = fx * uy * iz; Ju[2] = -fx * (ux * x + uy * y) * iz;
+        Jv[0] = fy * vx * iz; Jv[1] = fy * vy * iz; Jv[2] = -fy * (vx * x + vy * y) * iz;
+        ku[0] = xt; ku[2] = 1.0;
+        kv[1] = yt; kv[3] = 1.0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+          ku[4 + i] = fx * (T00 * dxk[i] + T01 * dyk[i]);
+          kv[4 + i] = fy * (T10 * dxk[i] + T11 * dyk[i]);
+        }
+        const double ax0 = dMx[0] * xd + dMx[1] * yd + dMx[2], ax1 = dMx[3] * xd + dMx[4] * yd + dMx[5], ax2 = dMx[6] * xd + dMx[7] * yd + dMx[8];
+        const double ay0 = dMy[0] * xd + dMy[1] * yd + dMy[2], ay1 = dMy[3] * xd + dMy[4] * yd + dMy[5], ay2 = dMy[6] * xd + dMy[7] * yd + dMy[8];
+        ku[16] = fx * (ax0 - xt * ax2) * ip; kv[16] = fy * (ax1 - yt * ax2) * ip;
+        ku[17] = fx * (ay0 - xt * ay2) * ip; kv[17] = fy * (ay1 - yt * ay2) * ip;
       }
     }
   }

@@ -307,8 +307,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 constexpr int MMA_KPAD = 68;     // 64 residual rows + 4: (column stride mod 16 doubles) == 4 -> conflict-free fragment loads
 __host__ __device__ constexpr int mma_nc(int model) { return ((model_D(model) + 1 + 7) / 8) * 8; }
 
-template <int MODEL>
-__global__ void __launch_bounds__(VIEW_WARPS * 32, MMA_MIN_CTAS)
+// WPV = warps per view: 1 (one warp owns a view; many views) or VIEW_WARPS (the CTA's warps split one view's chunks and meet in
+// shared memory once: few, long views -- e.g. 4 cameras x 200 frames -- would otherwise leave most of the machine idle).
+template <int MODEL, int WPV>
+__global__ void __launch_bounds__(VIEW_WARPS * 32, (MODEL == MODEL_TILTED ? 2 : MMA_MIN_CTAS))
 k_views_mma(DeviceProblem p, ViewKernelArgs a) {
   constexpr int ND = model_nd(MODEL);
   constexpr int D = 10 + ND;
@@ -322,10 +324,12 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * VIEW_WARPS + warp;
-  const int nw = gridDim.x * VIEW_WARPS;
+  const int gw = (WPV == 1) ? blockIdx.x * VIEW_WARPS + warp : blockIdx.x;
+  const int nw = (WPV == 1) ? gridDim.x * VIEW_WARPS : gridDim.x;
   double* stage = stage_all + (size_t)warp * NC * MMA_KPAD;      // [NC][MMA_KPAD], element (row k, col j) at j*KPAD + k
+  double* xred = stage_all + (size_t)VIEW_WARPS * NC * MMA_KPAD; // WPV > 1: [warp][2*NPAIR + 1][32]
   const int grp = lane >> 2, tig = lane & 3;
+  const int sub = (WPV == 1) ? 0 : warp;
 
   for (int v = gw; v < p.V; v += nw) {
     const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
@@ -342,7 +346,7 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
     for (int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
     double cost_acc = 0.0;
 
-    for (int base = beg; base < end; base += 32) {
+    for (int base = beg + 32 * sub; base < end; base += 32 * WPV) {
       const int idx = base + lane;
       double gu[NC], gv[NC];
 #pragma unroll
@@ -406,6 +410,24 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
       __syncwarp();
     }
 
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
+    if constexpr (WPV > 1) {       // meet: warp 0 adds the other warps' fragments (same lane -> same matrix element)
+      __syncthreads();
+      if (warp > 0) {
+#pragma unroll
+        for (int t = 0; t < NPAIR; t++) { xred[((warp * (2 * NPAIR + 1)) + 2 * t) * 32 + lane] = acc[t][0]; xred[((warp * (2 * NPAIR + 1)) + 2 * t + 1) * 32 + lane] = acc[t][1]; }
+        if (lane == 0) xred[(warp * (2 * NPAIR + 1) + 2 * NPAIR) * 32] = cost_acc;
+      }
+      __syncthreads();
+      if (warp > 0) continue;
+#pragma unroll
+      for (int w = 1; w < WPV; w++) {
+#pragma unroll
+        for (int t = 0; t < NPAIR; t++) { acc[t][0] += xred[((w * (2 * NPAIR + 1)) + 2 * t) * 32 + lane]; acc[t][1] += xred[((w * (2 * NPAIR + 1)) + 2 * t + 1) * 32 + lane]; }
+        cost_acc += xred[(w * (2 * NPAIR + 1) + 2 * NPAIR) * 32];
+      }
+    }
     // ---- write the view's moments in the layout the expand kernels read
     double* out = a.moments + (size_t)v * T;
     {
@@ -424,8 +446,6 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
           t++;
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
     if (lane == 0) out[T - 1] = cost_acc;
   }
 }
@@ -738,7 +758,7 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
   double* Msum = sh + (size_t)EXP_WARPS * wd;          // [T] block total
   double* Ac = Msum + T;                                // 36
   for (int i = lane; i < B * (D * 6 + 42); i += 32) Ub[i] = 0.0;
-  constexpr int MAXT = 9;                                // ceil(276/32)
+  constexpr int MAXT = 11;                               // ceil(325/32): tilted model, D = 24
   double macc[MAXT];
 #pragma unroll
   for (int q = 0; q < MAXT; q++) macc[q] = 0.0;

@@ -154,7 +154,7 @@ int run_exchange(mcba_ctx* ctx, const Exchange& ex) {
 }
 #define EXCHANGE(...) do { if (ctx->world > 1) { Exchange ex_; __VA_ARGS__; int r_ = run_exchange(ctx, ex_); if (r_) return r_; } } while (0)
 
-int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : 2; }
+int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : model == MODEL_TILTED ? 5 : 2; }
 
 // parameters of block-structured vector x (internal order) <-> full parameter state
 __global__ void k_scatter_params(DeviceProblem p, const double* x, double* cam_rt, double* board_rt, double* frame_rt, double* intr) {
@@ -195,6 +195,7 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
       case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 1) break;
       case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 1) break;
       case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM, 0, 1) break;
+      case MODEL_TILTED: LV(MODEL_TILTED, 0, 1) break;
       default: LV(MODEL_FISHEYE, 0, 1) break;
     }
   } else {
@@ -202,6 +203,7 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
       case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 2) LV(MODEL_STANDARD, 1, 2) break;
       case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 3) LV(MODEL_RATIONAL, 1, 3) LV(MODEL_RATIONAL, 2, 3) break;
       case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM, 0, 4) LV(MODEL_THIN_PRISM, 1, 4) LV(MODEL_THIN_PRISM, 2, 4) LV(MODEL_THIN_PRISM, 3, 4) break;
+      case MODEL_TILTED: ctx->err = "the tilted model is only available on the DMMA path (unset MCBA_MOMENTS=fma)"; return MCBA_ERR_UNSUPPORTED;
       default: LV(MODEL_FISHEYE, 0, 2) LV(MODEL_FISHEYE, 1, 2) break;
     }
   }
@@ -211,16 +213,22 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
 
 int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a) {
   if (!ctx->use_mma) return launch_views<MODE_MOMENTS>(ctx, P, a);
-  const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 16));
   const int th = VIEW_WARPS * 32;
-  const size_t sm = (size_t)VIEW_WARPS * mma_nc(P.model) * MMA_KPAD * sizeof(double);
+  const int nc = mma_nc(P.model), npair = (nc / 8) * (nc / 8 + 1) / 2;
+  const size_t sm = ((size_t)VIEW_WARPS * nc * MMA_KPAD + (size_t)VIEW_WARPS * (2 * npair + 1) * 32) * sizeof(double);
   cudaStream_t s = ctx->stream;
+  // few long views (cfg2: 800 views of ~200 corners): let the 4 warps of a CTA share one view
+  const bool split = P.V < ctx->num_sms * 16;
+  const int blocks = split ? std::max(1, P.V) : std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 16));
+#define LM(MODEL) if (split) k_views_mma<MODEL, VIEW_WARPS><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1><<<blocks, th, sm, s>>>(P, a);
   switch (P.model) {
-    case MODEL_STANDARD: k_views_mma<MODEL_STANDARD><<<blocks, th, sm, s>>>(P, a); break;
-    case MODEL_RATIONAL: k_views_mma<MODEL_RATIONAL><<<blocks, th, sm, s>>>(P, a); break;
-    case MODEL_THIN_PRISM: k_views_mma<MODEL_THIN_PRISM><<<blocks, th, sm, s>>>(P, a); break;
-    default: k_views_mma<MODEL_FISHEYE><<<blocks, th, sm, s>>>(P, a); break;
+    case MODEL_STANDARD: LM(MODEL_STANDARD) break;
+    case MODEL_RATIONAL: LM(MODEL_RATIONAL) break;
+    case MODEL_THIN_PRISM: LM(MODEL_THIN_PRISM) break;
+    case MODEL_TILTED: LM(MODEL_TILTED) break;
+    default: LM(MODEL_FISHEYE) break;
   }
+#undef LM
   CKL();
   return MCBA_OK;
 }
@@ -280,6 +288,7 @@ int expand(mcba_ctx* ctx) {
       case MODEL_STANDARD: k_point_blocks<MODEL_STANDARD><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
       case MODEL_RATIONAL: k_point_blocks<MODEL_RATIONAL><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
       case MODEL_THIN_PRISM: k_point_blocks<MODEL_THIN_PRISM><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
+      case MODEL_TILTED: k_point_blocks<MODEL_TILTED><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
       default: k_point_blocks<MODEL_FISHEYE><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
     }
     CKL();
@@ -395,7 +404,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
 int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
   REQUIRE(desc->C > 0 && desc->F >= 0 && desc->B > 0 && desc->P > 0, MCBA_ERR_ARG, "bad problem dimensions");
   REQUIRE(desc->P <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
-  REQUIRE(desc->model >= 0 && desc->model <= 3, MCBA_ERR_ARG, "unknown camera model");
+  REQUIRE(desc->model >= 0 && desc->model <= 4, MCBA_ERR_ARG, "unknown camera model");
   REQUIRE((int64_t)desc->C * desc->F * desc->B * desc->P < ((int64_t)1 << 31), MCBA_ERR_UNSUPPORTED, "more than 2^31 table entries per rank");
   return MCBA_OK;
 }
@@ -427,10 +436,16 @@ int mcba_create(int device, mcba_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
-  cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_THIN_PRISM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_THIN_PRISM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_THIN_PRISM, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_TILTED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_views_mma<MODEL_TILTED, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_expand_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_chol_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

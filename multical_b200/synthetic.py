@@ -76,6 +76,12 @@ def distort_project(model, X, K, dist):
     rad = (1 + r2 * (k1 + r2 * (k2 + r2 * k3))) / (1 + r2 * (k4 + r2 * (k5 + r2 * k6)))
     xd = x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + r2 * (s1 + r2 * s2)
     yd = y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + r2 * (s3 + r2 * s4)
+    if d[12] != 0 or d[13] != 0:      # tilted sensor (14 coefficients)
+      cx_, sx_, cy_, sy_ = np.cos(d[12]), np.sin(d[12]), np.cos(d[13]), np.sin(d[13])
+      Rxy = np.array([[cy_, 0, -sy_], [0, 1, 0], [sy_, 0, cy_]]) @ np.array([[1, 0, 0], [0, cx_, sx_], [0, -sx_, cx_]])
+      M = np.array([[Rxy[2, 2], 0, -Rxy[0, 2]], [0, Rxy[2, 2], -Rxy[1, 2]], [0, 0, 1]]) @ Rxy
+      vt = np.stack([xd, yd, np.ones_like(xd)], axis=-1) @ M.T
+      xd, yd = vt[..., 0] / vt[..., 2], vt[..., 1] / vt[..., 2]
   return np.stack([fx * xd + cx, fy * yd + cy], axis=-1)
 
 
@@ -83,6 +89,7 @@ DIST_GT = {
   "standard": np.array([-0.1, 0.05, 1e-3, -1e-3, 0.01]),
   "rational": np.array([-0.1, 0.05, 1e-3, -1e-3, 0.01, 0.02, -0.01, 0.005]),
   "thin_prism": np.array([-0.1, 0.05, 1e-3, -1e-3, 0.01, 0.02, -0.01, 0.005, 1e-3, -5e-4, 5e-4, 1e-3]),
+  "tilted": np.array([-0.1, 0.05, 1e-3, -1e-3, 0.01, 0.02, -0.01, 0.005, 1e-3, -5e-4, 5e-4, 1e-3, 0.02, -0.015]),
   "fisheye": np.array([0.02, -0.01, 3e-3, -1e-3]),
 }
 

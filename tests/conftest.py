@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["standard_2x6", "fisheye_3x5", "rational_2x5", "cube3_3x6", "poses_only_2x6", "invalid_poses_3x6"]
+GOLDEN_CASES = ["standard_2x6", "fisheye_3x5", "rational_2x5", "cube3_3x6", "poses_only_2x6", "invalid_poses_3x6",
+                "thin_prism_2x5", "tilted_2x5"]
 
 
 def pytest_configure(config):

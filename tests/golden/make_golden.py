@@ -32,12 +32,16 @@ CASES = {
   "cube3_3x6": dict(C=3, F=6, vis=0.6, seed=14, model="standard", boards=("cube", 10, 10, 0.04, 3), rig="dome"),
   "poses_only_2x6": dict(C=2, F=6, vis=0.5, seed=15, model="standard"),
   "invalid_poses_3x6": dict(C=3, F=6, vis=0.5, seed=16, model="standard"),
+  "thin_prism_2x5": dict(C=2, F=5, vis=0.5, seed=17, model="thin_prism"),
+  "tilted_2x5": dict(C=2, F=5, vis=0.5, seed=18, model="tilted"),
 }
 
 
 def main():
   ref = loader.load()
+  only = sys.argv[1:]          # optional: regenerate just the named cases (existing fixtures stay byte-identical)
   for name, kw in CASES.items():
+    if only and name not in only: continue
     scene = synthetic.make_scene(**kw)
     if name.startswith("invalid"):
       scene["frame_valid"][2] = False

@@ -198,10 +198,11 @@ def test_bad_inputs_raise_like_the_reference():
     bad.bundle_adjust()
 
 
-def test_large_scene_properties():
-  """BASELINE cfg2 size: size-independent properties (no oracle run): cost decreases monotonically, RMS lands
-  at sigma*sqrt(2), re-solving from the solution is a fixed point, gradient is ~0 at the optimum."""
-  scene = synthetic.make_workload("cfg2")
+@pytest.mark.parametrize("workload", ["cfg2", "cfg3"])
+def test_large_scene_properties(workload):
+  """BASELINE cfg2 / cfg3 (fisheye, 1M corners) sizes: size-independent properties (no oracle run): cost decreases
+  monotonically, RMS lands at sigma*sqrt(2), re-solving from the solution is a fixed point, gradient ~0 at the optimum."""
+  scene = synthetic.make_workload(workload)
   calib = from_scene(scene).enable(cameras=True)
   out = calib.bundle_adjust()
   costs = [row[2] for row in out.last_solve.log]
