@@ -446,7 +446,7 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
           t++;
         }
     }
-    if (lane == 0) out[T - 1] = cost_acc;
+    if (lane == 0) { out[T - 1] = cost_acc; if (a.view_cost) a.view_cost[v] = cost_acc; }     // compact copy for the acceptance test
   }
 }
 

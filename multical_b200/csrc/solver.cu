@@ -265,7 +265,7 @@ size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((si
 int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial) {
   ctx->cur_loss = loss; ctx->cur_f_scale = f_scale;
   DeviceProblem P = with_state(ctx, trial);
-  ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p;
+  ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p; a.view_cost = ctx->view_cost.p;
   return launch_moments(ctx, P, a);
 }
 
@@ -928,9 +928,14 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       }
       r = moments_at(ctx, opts->loss, opts->f_scale, true); if (r) return r;
       if (single) {
-        k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p, P.V, P.T); CKL();
+        // per-view costs: compact array written by the DMMA kernel, or the last entry of each moment record (DFMA kernels)
+        if (ctx->use_mma) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->view_cost.p, P.V, 1);
+        else k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p + (P.T - 1), P.V, P.T);
+        CKL();
       } else {
-        k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p, P.V, P.T, ctx->red.p); CKL();
+        if (ctx->use_mma) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->view_cost.p, P.V, 1, ctx->red.p);
+        else k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p + (P.T - 1), P.V, P.T, ctx->red.p);
+        CKL();
         EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0); ex_.epilogue = EPI_ACCEPT);   // COSTNEW STEP2_F XN2_F
       }
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));

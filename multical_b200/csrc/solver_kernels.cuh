@@ -844,7 +844,7 @@ __global__ void k_step(int n, int n_s, SolverState* st, const double* x, const d
 __global__ void k_cost_from_moments(const double* moments, int V, int T, double* red) {
   __shared__ double sm[32];
   double c = 0.0;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T + T - 1];
+  for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T];       // T == 1: compact per-view costs
   c = block_sum(c, sm);
   if (threadIdx.x == 0) red[RED_COSTNEW] = c;
 }
@@ -887,7 +887,7 @@ __global__ void k_accept(SolverState* st, double* red, const double* moments, in
   if (st->done) return;
   if (moments) {
     double c = 0.0;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T + T - 1];
+    for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T];     // T == 1: compact per-view costs
     c = block_sum(c, sm);
     if (threadIdx.x == 0) red[RED_COSTNEW] = c;
   }
