@@ -243,7 +243,7 @@ def run_ours(args):
               ms_per_step=t_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
               data="synthetic",
               config=dict(workload=args.workload, cameras=scene["C"], frames=F_total, boards=scene["B"], corners=n_total,
-                          params=n_params if world == 1 else None, frames_per_gpu=base["F"], model=scene["model"],
+                          params=n_params if world == 1 else None, frames_per_gpu=base["F"], camera_model=scene["model"],
                           solver="TRF semantics (ftol=1e-4, x_scale=jac, max_nfev=100), exact Schur inner solve",
                           l2="flushed between timed iterations (256 MiB write)", seed=args.seed),
               lm_iters_per_sec=njev / (t_dev * 1e-3), nfev_plus_njev_per_step=evals / args.steps,

@@ -270,51 +270,56 @@ class Calibration(Parameters):
     d = self.__getstate__(); d.update(k)
     return Calibration(**d)
 
-  # ---- outliers (calibration.py:234-268) --------------------------------------------------------
+  # ---- outliers (same rules and log lines as calibration.py:234-268, 290-310) -------------------------
   def reject_outliers_quantile(self, quantile=0.95, factor=1.0):
-    threshold = np.quantile(self.reprojection_error, quantile)
-    return self.reject_outliers(threshold=threshold * factor)
+    """Inliers = valid corners whose pixel error is below factor x the given error quantile."""
+    return self.reject_outliers(threshold=factor * np.quantile(self.reprojection_error, quantile))
 
   def reject_outliers(self, threshold):
+    """New Calibration whose inlier mask keeps the valid corners with error < threshold (pixels)."""
     valid = self.valid
-    inliers = np.zeros_like(valid)
-    inliers[valid] = self._valid_errors < threshold
-    num_outliers = valid.sum() - inliers.sum()
-    inlier_percent = 100.0 * inliers.sum() / valid.sum()
-    info(f"Rejecting {num_outliers} outliers with error > {threshold:.2f} pixels, "
-         f"keeping {inliers.sum()} / {valid.sum()} inliers, ({inlier_percent:.2f}%)")
-    return self.copy(inlier_mask=inliers)
+    keep = np.zeros(valid.shape, dtype=bool)
+    keep[valid] = self._valid_errors < threshold          # errors come back in boolean-mask order
+    n_valid, n_keep = int(valid.sum()), int(keep.sum())
+    info(f"Rejecting {n_valid - n_keep} outliers with error > {threshold:.2f} pixels, "
+         f"keeping {n_keep} / {n_valid} inliers, ({100.0 * n_keep / n_valid:.2f}%)")
+    return self.copy(inlier_mask=keep)
 
   def adjust_outliers(self, num_adjustments=3, select_scale=None, select_outliers=None, **kwargs):
+    """Alternate outlier rejection and bundle adjustment `num_adjustments` times (workspace.py:228-247 drives this).
+    select_outliers / select_scale map the current error vector to a pixel threshold / to the loss f_scale."""
     info(f"Beginning adjustments ({num_adjustments}) enabled: {self.optimize}, options: {kwargs}")
-    for i in range(num_adjustments):
-      self.report(f"Adjust_outliers {i}:")
-      f_scale = (None if select_scale is None else select_scale(self.reprojection_error)) or 1.0
+    calib = self
+    for round_index in range(num_adjustments):
+      calib.report(f"Adjust_outliers {round_index}:")
+      errors = calib.reprojection_error
+      f_scale = 1.0
       if select_scale is not None:
+        f_scale = select_scale(errors) or 1.0
         info(f"Auto scaling for outliers influence at {f_scale:.2f} pixels")
       if select_outliers is not None:
-        self = self.reject_outliers(select_outliers(self.reprojection_error))
-      self = self.bundle_adjust(f_scale=f_scale, **kwargs)
-    self.report("Adjust_outliers end:")
-    return self
+        calib = calib.reject_outliers(select_outliers(errors))
+      calib = calib.bundle_adjust(f_scale=f_scale, **kwargs)
+    calib.report("Adjust_outliers end:")
+    return calib
 
   def report(self, stage=""):
-    overall = error_stats(self.reprojection_error)
-    inliers = error_stats(self.reprojection_inliers)
-    if self.inlier_mask is not None:
-      info(f"{stage} reprojection RMS={inliers.rms:.3f} ({overall.rms:.3f}), "
-           f"n={inliers.n} ({overall.n}), quantiles={overall.quantiles}")
+    everything, kept = error_stats(self.reprojection_error), error_stats(self.reprojection_inliers)
+    if self.inlier_mask is None:
+      info(f"{stage} reprojection RMS={everything.rms:.3f}, n={everything.n}, quantiles={everything.quantiles}")
     else:
-      info(f"{stage} reprojection RMS={overall.rms:.3f}, n={overall.n}, quantiles={overall.quantiles}")
+      info(f"{stage} reprojection RMS={kept.rms:.3f} ({everything.rms:.3f}), "
+           f"n={kept.n} ({everything.n}), quantiles={everything.quantiles}")
 
 
 def error_stats(errors):
-  """calibration.py:303-310"""
-  errors = np.asarray(errors)
-  if len(errors) == 0: errors = np.zeros((1, 1), np.float32)
-  mse = np.square(errors).mean()
-  quantiles = np.array([np.quantile(errors, n) for n in [0, 0.25, 0.5, 0.75, 1]])
-  return struct(mse=mse, rms=np.sqrt(mse), quantiles=quantiles, n=errors.size)
+  """mse / rms / five-number summary of a pixel-error vector; an empty vector counts as a single zero
+  (the reference's guard, calibration.py:303-310)."""
+  e = np.asarray(errors, dtype=np.float64).ravel()
+  if e.size == 0:
+    e = np.zeros(1)
+  mse = float(np.mean(e * e))
+  return struct(mse=mse, rms=float(np.sqrt(mse)), quantiles=np.quantile(e, [0.0, 0.25, 0.5, 0.75, 1.0]), n=e.size)
 
 
 def from_scene(scene, guess=True, **kwargs):
