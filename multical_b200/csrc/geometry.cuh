@@ -5,6 +5,8 @@
 //   pinhole      cv2.projectPoints(rvec=0,tvec=0,K,dist)    camera.py:124-128   (5/8/12 coefficients, camera.py:43-48)
 //   fisheye      cv2.fisheye.projectPoints(...)             camera_fisheye.py:113-117
 // plus the analytic derivatives that scipy obtains by 2-point finite differences (calibration.py:209-210).
+// The math here is __host__ __device__ so that tests/host_math can run the very same source on the CPU against cv2 / scipy
+// (analytic Jacobians vs the Jacobian cv2.projectPoints returns); the product only ever calls it from kernels.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -28,21 +30,21 @@ struct PoseT {
   double pad[3];
 };
 
-__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+__host__ __device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
 #pragma unroll
   for (int i = 0; i < 3; i++)
 #pragma unroll
     for (int j = 0; j < 3; j++)
       C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
-__device__ __forceinline__ void mat3_vec(const double* A, const double* x, double* y) {
+__host__ __device__ __forceinline__ void mat3_vec(const double* A, const double* x, double* y) {
 #pragma unroll
   for (int i = 0; i < 3; i++) y[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
 }
 
 // rotvec -> R (transform/rtvec.py:24-27, scipy Rotation.from_rotvec) and left Jacobian JL with
 //   R(r + dr) ~= exp([JL dr]x) R(r)
-__device__ inline void rodrigues(const double* r, double* R, double* JL) {
+__host__ __device__ inline void rodrigues(const double* r, double* R, double* JL) {
   const double x = r[0], y = r[1], z = r[2];
   const double th2 = x * x + y * y + z * z;
   double A, B, Cc;            // sin(th)/th, (1-cos th)/th^2, (th - sin th)/th^3
@@ -74,7 +76,7 @@ __device__ inline void rodrigues(const double* r, double* R, double* JL) {
 // x_cam.  With Rl, tl = rotation / translation of everything LEFT of the perturbed pose in the chain
 // (identity for the camera pose) and tcur = translation of the chain up to and including this pose:
 //   omega = Rl JL dr ,   v = [tcur]x Rl JL dr + Rl dt
-__device__ __forceinline__ void twist_map(const double* Rl, const double* JL, const double* tcur, double* A /*6x6 row-major*/) {
+__host__ __device__ __forceinline__ void twist_map(const double* Rl, const double* JL, const double* tcur, double* A /*6x6 row-major*/) {
   double RJ[9];
   mat3_mul(Rl, JL, RJ);
   const double tx = tcur[0], ty = tcur[1], tz = tcur[2];
@@ -93,7 +95,7 @@ __device__ __forceinline__ void twist_map(const double* Rl, const double* JL, co
 // Tilted-sensor matrix of the 14-coefficient model and its derivatives wrt (tauX, tauY): restatement of OpenCV's
 // cv::detail::computeTiltProjectionMatrix (the reference reaches it through cv2.projectPoints, camera.py:43-48,124-128).
 //   matTilt = P_z(R_y R_x) R_y R_x ,  P_z(R) = [[R22, 0, -R02], [0, R22, -R12], [0, 0, 1]]
-__device__ inline void tilt_matrices(double tx, double ty, double* M, double* dMx, double* dMy) {
+__host__ __device__ inline void tilt_matrices(double tx, double ty, double* M, double* dMx, double* dMy) {
   double sx, cx, sy, cy;
   sincos(tx, &sx, &cx);
   sincos(ty, &sy, &cy);
@@ -123,7 +125,7 @@ __device__ inline void tilt_matrices(double tx, double ty, double* M, double* dM
 //   Ju,Jv = d(u,v)/dX_cam (3 each);  ku,kv = d(u,v)/d[fx fy cx cy dist...] (4+nd each; fy,cy of ku and
 //   fx,cx of kv are structurally zero and not written)
 template <int MODEL, bool JAC>
-__device__ __forceinline__ void project(const double* X, const double* __restrict__ k, double& u, double& v,
+__host__ __device__ __forceinline__ void project(const double* X, const double* __restrict__ k, double& u, double& v,
                                         double* Ju, double* Jv, double* ku, double* kv) {
   constexpr int ND = model_nd(MODEL);
   const double fx = k[0], fy = k[1], cx = k[2], cy = k[3];
@@ -245,7 +247,7 @@ __device__ __forceinline__ void project(const double* X, const double* __restric
 }
 
 // scipy robust losses on z = (f/f_scale)^2 (least_squares.py:183-219); returns rho0, rho1, rho2
-__device__ __forceinline__ void loss_rho(int loss, double z, double& r0, double& r1, double& r2) {
+__host__ __device__ __forceinline__ void loss_rho(int loss, double z, double& r0, double& r1, double& r2) {
   switch (loss) {
     case 1: { const double t = 1.0 + z; const double s = sqrt(t); r0 = 2.0 * (s - 1.0); r1 = 1.0 / s; r2 = -0.5 / (t * s); break; }
     case 2: if (z <= 1.0) { r0 = z; r1 = 1.0; r2 = 0.0; } else { const double s = sqrt(z); r0 = 2.0 * s - 1.0; r1 = 1.0 / s; r2 = -0.5 / (z * s); } break;

@@ -762,7 +762,7 @@ __global__ void k_subspace(SolverState* st, const double* red) { subspace_comput
 // common.py solve_trust_region_2d: minimise 0.5 p^T B p + g^T p, ||p|| <= Delta  (B 2x2 symmetric).
 // Interior Newton point if B is positive definite and inside; otherwise the global boundary minimiser via
 // the secular equation in the eigenbasis of B (equivalent to scipy's argmin over the quartic's real roots).
-__device__ inline void solve_tr_2d(double b11, double b12, double b22, double g1, double g2, double Delta, double& p1, double& p2) {
+__host__ __device__ inline void solve_tr_2d(double b11, double b12, double b22, double g1, double g2, double Delta, double& p1, double& p2) {
   const double det = b11 * b22 - b12 * b12;
   if (b11 > 0.0 && det > 0.0) {
     const double q1 = -(b22 * g1 - b12 * g2) / det, q2 = -(b11 * g2 - b12 * g1) / det;

@@ -293,3 +293,29 @@ def test_board_points_as_parameters():
   # without boards=True the same scene must reach a higher (or equal) cost
   base = from_scene(scene).enable(cameras=True).bundle_adjust(tolerance=1e-8, max_iterations=60)
   assert out.last_solve.cost <= base.last_solve.cost * (1 + 1e-9)
+
+
+@pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6"])
+def test_iteration_table_matches_the_trf_model(name):
+  """The device solver claims scipy's trf_no_bounds semantics with an exact inner solve.  oracle/trf_exact_model.py is
+  that statement in numpy (scipy's own helper functions); the per-iteration table (nfev, cost, cost reduction, step norm)
+  must agree until the two Jacobians (analytic vs finite differences) differ by more than their noise."""
+  from oracle.trf_exact_model import trf_exact
+  scene, z, calib, prob = make(name)
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  _, cost, nfev, njev, status, rows = trf_exact(prob.residuals, jac, prob.param_vec, ftol=1e-4)
+  out = calib.bundle_adjust(tolerance=1e-4)
+  log = out.last_solve.log
+  compared = 0
+  for (it, nf, c, red, sn, gn), (it2, nf2, c2, red2, sn2, gn2) in zip(log, rows):
+    if red2 is not None and not red2 > 1e-6 * c2:
+      break            # from here on the step is inside the finite-difference noise of the model's Jacobian
+    assert (it, nf) == (it2, nf2)
+    assert abs(c - c2) <= 1e-7 * c2
+    assert abs(gn - gn2) <= 1e-4 * gn2
+    if red2 is not None:
+      assert abs(red - red2) <= 1e-5 * red2 and abs(sn - sn2) <= 1e-4 * sn2
+    compared += 1
+  assert compared >= 3
+  assert out.last_solve.cost <= cost * (1 + 1e-7)
