@@ -211,6 +211,22 @@ class Calibration(Parameters):
     updated = {k: self.param_objects[k].with_param_vec(v) for k, v in params.items()}
     return self.copy(**updated)
 
+  def with_param_vec(self, param_vec):
+    """parameters.py:48-50 semantics (split the vector over the enabled blocks in order) without first flattening the
+    current parameters just to learn the block sizes -- that costs three rotation-vector conversions per call."""
+    param_vec = np.asarray(param_vec)
+    sizes = {}
+    for k, obj in self.param_objects.items():
+      if self.optimize[k] is True:
+        n = getattr(obj, "num_params", None)
+        sizes[k] = int(n) if n is not None else int(obj.param_vec.size)
+    total = sum(sizes.values())
+    assert param_vec.size == total, f"inconsistent parameter sizes, got {param_vec.size}, expected {total}"
+    chunks, pos = {}, 0
+    for k, n in sizes.items():
+      chunks[k] = param_vec[pos:pos + n]; pos += n
+    return self.with_params(chunks)
+
   @cached_property
   def sparsity_matrix(self):
     """Jacobian sparsity as the reference builds it for scipy (calibration.py:173-196).  The GPU solver

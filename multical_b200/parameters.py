@@ -61,5 +61,7 @@ class ParamList(Parameters):
 
   @cached_property
   def params(self): return [p.param_vec for p in self.param_objects]
+  @property
+  def num_params(self): return sum(p.param_vec.size for p in self.param_objects)
   def with_params(self, params):
     return ParamList([o.with_param_vec(p) for o, p in zip(self.param_objects, params)], self.names)

@@ -77,6 +77,16 @@ class PoseSet(Parameters):
     rt = np.asarray(params, dtype=np.float64).reshape(self.size, rtvec.size)
     return self.copy(pose_table=self.pose_table._update(poses=rtvec.to_matrix(rt)))
 
+  @property
+  def num_params(self):
+    return rtvec.size * self.size
+
+  def with_param_vec(self, param_vec):
+    # the generic path would convert every pose to an rtvec just to learn the shape (6 per pose) of the vector to split
+    param_vec = np.asarray(param_vec)
+    assert param_vec.size == self.num_params, f"inconsistent parameter sizes, got {param_vec.size}, expected {self.num_params}"
+    return self.with_params(param_vec)
+
   # -- copy / pickle -------------------------------------------------------------------------------
   def __getstate__(self):
     return {k: getattr(self, k) for k in self._state_keys}
