@@ -110,6 +110,10 @@ int  mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8
 int  mcba_set_params(mcba_ctx* ctx, const double* cam_rt, const double* board_rt,
                      const double* frame_rt, const double* intrinsics);
 int  mcba_get_params(mcba_ctx* ctx, double* cam_rt, double* board_rt, double* frame_rt, double* intrinsics);
+/* the same state as 4x4 pose matrices, f64[C+B+F][4][4] in the order cameras, boards, frames (PoseSet.poses,
+ * pose_set.py:40-42): matrix <-> rtvec (transform/rtvec.py:24-32) is done on the device */
+int  mcba_set_state_matrices(mcba_ctx* ctx, const double* pose_matrices, const double* intrinsics);
+int  mcba_get_state_matrices(mcba_ctx* ctx, double* pose_matrices, double* intrinsics);
 int  mcba_num_params(mcba_ctx* ctx, int64_t* n);      /* length of param_vec for the enabled blocks    */
 int  mcba_get_param_vec(mcba_ctx* ctx, double* x);    /* Parameters.param_vec (parameters.py:44-46)    */
 int  mcba_set_param_vec(mcba_ctx* ctx, const double* x);   /* with_param_vec (parameters.py:48-50)     */

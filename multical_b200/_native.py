@@ -22,7 +22,7 @@ STATUS_MESSAGES = {
   4: "Both `ftol` and `xtol` termination conditions are satisfied.",
 }
 EXPORTS = ["mcba_create", "mcba_destroy", "mcba_last_error", "mcba_set_stream", "mcba_version",
-           "mcba_comm_unique_id", "mcba_comm_init", "mcba_peer_export", "mcba_peer_import", "mcba_upload", "mcba_upload_dense", "mcba_set_params", "mcba_get_params",
+           "mcba_comm_unique_id", "mcba_comm_init", "mcba_peer_export", "mcba_peer_import", "mcba_upload", "mcba_upload_dense", "mcba_set_params", "mcba_get_params", "mcba_set_state_matrices", "mcba_get_state_matrices",
            "mcba_num_params", "mcba_get_param_vec", "mcba_set_param_vec", "mcba_residuals",
            "mcba_linearize", "mcba_reprojection_error", "mcba_solve", "mcba_bench_launch", "mcba_bench_info"]
 
@@ -77,6 +77,8 @@ def load():
   lib.mcba_upload_dense.argtypes = [P, C.POINTER(ProblemDesc), C.POINTER(C.c_uint8), D, D, C.POINTER(C.c_int64)]
   lib.mcba_set_params.argtypes = [P, D, D, D, D]
   lib.mcba_get_params.argtypes = [P, D, D, D, D]
+  lib.mcba_set_state_matrices.argtypes = [P, D, D]
+  lib.mcba_get_state_matrices.argtypes = [P, D, D]
   lib.mcba_num_params.argtypes = [P, C.POINTER(C.c_int64)]
   lib.mcba_get_param_vec.argtypes = [P, D]
   lib.mcba_set_param_vec.argtypes = [P, D]

@@ -162,8 +162,26 @@ class Calibration(Parameters):
     eng = get_engine(device)
     pts = np.asarray(self.point_table.points) if points is None else points
     eng.upload_dense(self.engine_model, self._optimize_bits(), mask, pts, self.board_points.points)
-    eng.set_params(*self._state_arrays())
+    # poses go over as 4x4 matrices: the matrix -> rotation-vector conversion (transform/rtvec.py:29-32) runs on the device
+    mats = np.concatenate([np.asarray(self.camera_poses.poses, np.float64), np.asarray(self.board_poses.poses, np.float64),
+                           np.asarray(self.motion.poses, np.float64)], axis=0)
+    eng.set_state_matrices(mats, np.stack([np.asarray(c.param_vec, np.float64) for c in self.cameras]))
     return eng
+
+  def _with_engine_state(self, eng):
+    """New Calibration holding the engine's solved state -- what `self.with_param_vec(res.x)` returns in the reference
+    (calibration.py:212), built from the pose matrices the device hands back (rtvec -> matrix, rtvec.py:24-27, done there)."""
+    if self.optimize["boards"] is True or not hasattr(self.motion, "pose_table"):
+      return self.with_param_vec(self._from_engine_vec(eng.param_vec))
+    cam_T, board_T, frame_T, intr = eng.get_state_matrices()
+    def moved(pose_set, poses):
+      return pose_set.copy(pose_table=pose_set.pose_table._update(poses=poses))
+    changes = {}
+    if self.optimize["camera_poses"] is True: changes["camera_poses"] = moved(self.camera_poses, cam_T)
+    if self.optimize["board_poses"] is True: changes["board_poses"] = moved(self.board_poses, board_T)
+    if self.optimize["motion"] is True: changes["motion"] = moved(self.motion, frame_T)
+    if self.optimize["cameras"] is True: changes["cameras"] = self.cameras.with_param_vec(intr.ravel())
+    return self.copy(**changes)
 
   # ---- projection / errors (calibration.py:115-141, tables.py:239-249) ---------------------------
   def _project(self, mask):
@@ -267,7 +285,7 @@ class Calibration(Parameters):
     info(res.message)
     info(f"Function evaluations {res.nfev}, initial cost {res.initial_cost:.4e}, final cost {res.cost:.4e}, "
          f"first-order optimality {res.optimality:.2e}.")
-    out = self.with_param_vec(self._from_engine_vec(eng.param_vec))
+    out = self._with_engine_state(eng)
     out.__dict__["last_solve"] = res
     return out
 

@@ -72,6 +72,33 @@ __host__ __device__ inline void rodrigues(const double* r, double* R, double* JL
   }
 }
 
+// 4x4 (row-major, last row ignored) -> rtvec [rx ry rz tx ty tz] with the rotation vector in canonical form (angle in [0, pi]):
+// the reference's transform/rtvec.py:29-32 (scipy Rotation.from_matrix(...).as_rotvec()), restated with the same steps --
+// largest-pivot quaternion extraction, w >= 0, angle = 2 atan2(|xyz|, w), series below 1e-3 rad.
+__host__ __device__ inline void matrix_to_rtvec(const double* T, double* rt) {
+  const double m00 = T[0], m01 = T[1], m02 = T[2], m10 = T[4], m11 = T[5], m12 = T[6], m20 = T[8], m21 = T[9], m22 = T[10];
+  const double tr = m00 + m11 + m22;
+  double q[4];
+  int choice = 3; double best = tr;
+  if (m00 > best) { best = m00; choice = 0; }
+  if (m11 > best) { best = m11; choice = 1; }
+  if (m22 > best) { best = m22; choice = 2; }
+  if (choice == 0)      { q[0] = 1.0 - tr + 2.0 * m00; q[1] = m10 + m01; q[2] = m20 + m02; q[3] = m21 - m12; }
+  else if (choice == 1) { q[1] = 1.0 - tr + 2.0 * m11; q[2] = m21 + m12; q[0] = m01 + m10; q[3] = m02 - m20; }
+  else if (choice == 2) { q[2] = 1.0 - tr + 2.0 * m22; q[0] = m02 + m20; q[1] = m12 + m21; q[3] = m10 - m01; }
+  else                  { q[0] = m21 - m12; q[1] = m02 - m20; q[2] = m10 - m01; q[3] = 1.0 + tr; }
+  const double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  double s = (q[3] < 0.0 ? -1.0 : 1.0) / nq;
+  const double x = q[0] * s, y = q[1] * s, z = q[2] * s, w = q[3] * s;
+  const double nv = sqrt(x * x + y * y + z * z);
+  const double angle = 2.0 * atan2(nv, w);
+  double scale;
+  if (angle <= 1e-3) { const double a2 = angle * angle; scale = 2.0 + a2 / 12.0 + 7.0 * a2 * a2 / 2880.0; }
+  else scale = angle / sin(0.5 * angle);
+  rt[0] = scale * x; rt[1] = scale * y; rt[2] = scale * z;
+  rt[3] = T[3]; rt[4] = T[7]; rt[5] = T[11];
+}
+
 // 6x6 map from a pose-parameter increment (dr, dt) to the camera-frame twist (omega, v) it induces on
 // x_cam.  With Rl, tl = rotation / translation of everything LEFT of the perturbed pose in the chain
 // (identity for the camera pose) and tcur = translation of the chain up to and including this pose:

@@ -74,6 +74,28 @@ __global__ void k_prepare(DeviceProblem p, const double* cam_rt, const double* b
   *dst = t;
 }
 
+// pose matrices <-> rtvec parameter state, one thread per pose (the host never converts rotations itself)
+__global__ void k_matrices_to_state(int C, int B, int F, const double* mats /*[C+B+F][16]*/, double* cam_rt, double* board_rt, double* frame_rt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C + B + F) return;
+  double* dst = i < C ? cam_rt + 6 * i : i < C + B ? board_rt + 6 * (i - C) : frame_rt + 6 * (i - C - B);
+  double rt[6];
+  matrix_to_rtvec(mats + (size_t)16 * i, rt);
+#pragma unroll
+  for (int j = 0; j < 6; j++) dst[j] = rt[j];
+}
+__global__ void k_state_to_matrices(int C, int B, int F, const double* cam_rt, const double* board_rt, const double* frame_rt, double* mats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C + B + F) return;
+  const double* src = i < C ? cam_rt + 6 * i : i < C + B ? board_rt + 6 * (i - C) : frame_rt + 6 * (i - C - B);
+  double R[9], JL[9];
+  rodrigues(src, R, JL);
+  double* M = mats + (size_t)16 * i;
+#pragma unroll
+  for (int r = 0; r < 3; r++) { M[4 * r] = R[3 * r]; M[4 * r + 1] = R[3 * r + 1]; M[4 * r + 2] = R[3 * r + 2]; M[4 * r + 3] = src[3 + r]; }
+  M[12] = 0.0; M[13] = 0.0; M[14] = 0.0; M[15] = 1.0;
+}
+
 // k_make_trial: trial parameter state = current state with the free blocks replaced by x (internal order), and the
 // pose tables of that state, in one launch.  One thread per pose, then one per camera (intrinsics).
 __global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o) {

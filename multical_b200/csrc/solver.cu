@@ -88,7 +88,7 @@ struct mcba_ctx {
   DevBuf<uint8_t> dense_mask; DevBuf<double2> dense_pts; DevBuf<int> scan;
   DevBuf<PoseT> cam_T, frame_T, board_T;
   // trial parameter state
-  DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2, board_pts2;
+  DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2, board_pts2, pose_mats;
   // solver buffers
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
   DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
@@ -659,6 +659,39 @@ int mcba_set_params(mcba_ctx* ctx, const double* cam_rt, const double* board_rt,
   CK(cudaMemcpyAsync(ctx->board_rt.p, board_rt, sizeof(double) * P.B * 6, cudaMemcpyHostToDevice, ctx->stream));
   if (P.F) CK(cudaMemcpyAsync(ctx->frame_rt.p, frame_rt, sizeof(double) * P.F * 6, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->intr.p, intrinsics, sizeof(double) * P.C * P.kint, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+// Same state as 4x4 pose matrices (PoseSet.poses): the rotation-vector conversions of transform/rtvec.py run on the device.
+// mats: f64[C+B+F][4][4] in the order cameras, boards, frames.
+int mcba_set_state_matrices(mcba_ctx* ctx, const double* mats, const double* intrinsics) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  REQUIRE(mats && intrinsics, MCBA_ERR_ARG, "null parameter array");
+  const DeviceProblem& P = ctx->P;
+  CK(cudaSetDevice(ctx->device));
+  const int np = P.C + P.B + P.F;
+  CK(ctx->pose_mats.alloc((size_t)np * 16));
+  CK(cudaMemcpyAsync(ctx->pose_mats.p, mats, sizeof(double) * 16 * np, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->intr.p, intrinsics, sizeof(double) * P.C * P.kint, cudaMemcpyHostToDevice, ctx->stream));
+  k_matrices_to_state<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P.C, P.B, P.F, ctx->pose_mats.p, P.cam_rt, P.board_rt, P.frame_rt); CKL();
+  CK(cudaStreamSynchronize(ctx->stream));     // the host arrays are borrowed only for the call
+  return MCBA_OK;
+}
+
+int mcba_get_state_matrices(mcba_ctx* ctx, double* mats, double* intrinsics) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  CK(cudaSetDevice(ctx->device));
+  const int np = P.C + P.B + P.F;
+  if (mats) {
+    CK(ctx->pose_mats.alloc((size_t)np * 16));
+    k_state_to_matrices<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P.C, P.B, P.F, P.cam_rt, P.board_rt, P.frame_rt, ctx->pose_mats.p); CKL();
+    CK(cudaMemcpyAsync(mats, ctx->pose_mats.p, sizeof(double) * 16 * np, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (intrinsics) CK(cudaMemcpyAsync(intrinsics, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MCBA_OK;
 }

@@ -118,6 +118,19 @@ class Engine:
     assert d.F == 0 or frame_rt.size == 6 * d.F
     self._ck(self.lib.mcba_set_params(self.h, nat.dptr(cam_rt), nat.dptr(board_rt), nat.dptr(frame_rt), nat.dptr(intrinsics)))
 
+  def set_state_matrices(self, pose_matrices, intrinsics):
+    """Parameter state from 4x4 pose matrices f64[C+B+F,4,4] (cameras, boards, frames): the device converts to rtvecs."""
+    d = self.desc
+    mats, intrinsics = nat.f64(pose_matrices), nat.f64(intrinsics)
+    assert mats.shape == (d.C + d.B + d.F, 4, 4) and intrinsics.size == self.kint * d.C
+    self._ck(self.lib.mcba_set_state_matrices(self.h, nat.dptr(mats), nat.dptr(intrinsics)))
+
+  def get_state_matrices(self):
+    d = self.desc
+    mats, intr = np.zeros((d.C + d.B + d.F, 4, 4)), np.zeros((d.C, self.kint))
+    self._ck(self.lib.mcba_get_state_matrices(self.h, nat.dptr(mats), nat.dptr(intr)))
+    return mats[:d.C], mats[d.C:d.C + d.B], mats[d.C + d.B:], intr
+
   def get_params(self):
     d = self.desc
     out = (np.zeros((d.C, 6)), np.zeros((d.B, 6)), np.zeros((max(d.F, 1), 6)), np.zeros((d.C, self.kint)))

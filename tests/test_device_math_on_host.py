@@ -33,6 +33,7 @@ def hm():
   lib.hm_project.argtypes = [C.c_int, C.c_int, D, D, D, D, D]
   lib.hm_rodrigues.argtypes = [D, D, D]
   lib.hm_twist_map.argtypes = [D, D, D, D]
+  lib.hm_matrix_to_rtvec.argtypes = [D, D]
   lib.hm_tr2d.argtypes = [C.c_double] * 6 + [D]
   lib.hm_loss.argtypes = [C.c_int, C.c_double, D]
   return lib
@@ -101,6 +102,23 @@ def test_rodrigues_and_left_jacobian(hm):
       lhs = Rotation.from_rotvec(r + d).as_matrix()
       rhs = Rotation.from_rotvec(JL @ d).as_matrix() @ R
       assert np.abs(lhs - rhs).max() < 1e-11
+
+
+def test_matrix_to_rtvec_matches_scipy(hm):
+  """Device-side restatement of transform/rtvec.py:29-32 (Rotation.from_matrix(...).as_rotvec()), incl. angles near 0 and pi."""
+  rng = np.random.default_rng(5)
+  rvs = list(rng.normal(0, 1.2, (200, 3))) + [np.zeros(3), np.array([1e-9, 0, 0]), np.array([2e-4, -1e-4, 3e-4]),
+                                                 np.array([np.pi - 1e-7, 0, 0]), np.array([0, np.pi, 0]), np.array([2.2, -2.2, 0.1])]
+  for r in rvs:
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec(r).as_matrix(); T[:3, 3] = rng.normal(0, 1, 3)
+    rt = np.zeros(6)
+    hm.hm_matrix_to_rtvec(dp(np.ascontiguousarray(T)), dp(rt))
+    ref = Rotation.from_matrix(T[:3, :3]).as_rotvec()
+    if np.linalg.norm(ref) > np.pi - 1e-6:          # at pi the axis sign is arbitrary: compare the rotations
+      assert np.abs(Rotation.from_rotvec(rt[:3]).as_matrix() - T[:3, :3]).max() < 1e-9
+    else:
+      assert np.abs(rt[:3] - ref).max() < 1e-14
+    assert np.array_equal(rt[3:], T[:3, 3])
 
 
 def test_twist_map_is_the_derivative_of_the_pose_chain(hm):
