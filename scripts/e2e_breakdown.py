@@ -26,12 +26,14 @@ T("board_points", lambda: from_scene(scene).board_points)
 T("_optimize_bits + engine_model", lambda: (from_scene(scene).enable(cameras=True)._optimize_bits(), from_scene(scene).engine_model))
 m, pts, bp = calib.inliers, np.asarray(calib.point_table.points), calib.board_points.points
 T("upload_dense", lambda: eng.upload_dense(calib.engine_model, calib._optimize_bits(), m, pts, bp))
-T("_state_arrays", lambda: from_scene(scene).enable(cameras=True)._state_arrays())
-st = calib._state_arrays()
-T("set_params", lambda: eng.set_params(*st))
+mats = np.concatenate([calib.camera_poses.poses, calib.board_poses.poses, calib.motion.poses])
+intr = np.stack([c.param_vec for c in calib.cameras])
+T("set_state_matrices", lambda: eng.set_state_matrices(mats, intr))
 def solve():
-  eng.set_params(*st); return eng.solve(ftol=1e-4, max_nfev=100)
-res = T("set_params + solve", solve)
+  eng.set_state_matrices(mats, intr); return eng.solve(ftol=1e-4, max_nfev=100)
+res = T("set_state_matrices + solve", solve)
+T("get_state_matrices", lambda: eng.get_state_matrices())
+T("_with_engine_state", lambda: calib._with_engine_state(eng))
 print("   device_ms", res.device_ms, "launches", res.kernel_launches)
 T("format_log + info", lambda: [l for l in format_log(res.log)])
 T("eng.param_vec", lambda: eng.param_vec)
