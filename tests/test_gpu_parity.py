@@ -318,7 +318,8 @@ def test_iteration_table_matches_the_trf_model(name):
     if gn2 > 1e-4 * rows[0][5]:                       # later gradients are dominated by the finite-difference noise
       assert abs(gn - gn2) <= 1e-3 * gn2
     if red2 is not None:
-      assert abs(red - red2) <= 1e-5 * red2 and abs(sn - sn2) <= 1e-4 * sn2
+      # both costs agree to 1e-7 relative, so their difference can only agree to ~1e-7 * cost in absolute terms
+      assert abs(red - red2) <= 1e-5 * red2 + 2e-7 * c2 and abs(sn - sn2) <= 1e-3 * sn2
     compared += 1
   assert compared >= 3
   assert out.last_solve.cost <= cost * (1 + 1e-7)
