@@ -24,8 +24,9 @@ __global__ void k_pack_count(const uint8_t* mask, int C, int F, int B, int P, in
   }
 }
 
-// in-place exclusive scan of int32 data[n] by one CTA; data[n] receives the total
-__global__ void k_scan_exclusive(int* data, int n) {
+// in-place exclusive scan of int32 arrays of n (+1 slot for the total) elements, one CTA per array (arrays `stride` apart)
+__global__ void k_scan_exclusive(int* data_all, int n, int stride) {
+  int* data = data_all + (size_t)blockIdx.x * stride;
   __shared__ int warp_sums[32];
   __shared__ int carry;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nt = blockDim.x;

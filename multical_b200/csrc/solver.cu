@@ -622,10 +622,7 @@ int mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_
   int totals[2] = {0, 0};
   if (nv > 0) {
     k_pack_count<<<(nv * 32 + 255) / 256, 256, 0, s>>>(ctx->dense_mask.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
-    k_scan_exclusive<<<1, 1024, 0, s>>>(cnt_can, nv); CKL();
-    k_scan_exclusive<<<1, 1024, 0, s>>>(cnt_fm, nv); CKL();
-    k_scan_exclusive<<<1, 1024, 0, s>>>(flag_can, nv); CKL();
-    k_scan_exclusive<<<1, 1024, 0, s>>>(flag_fm, nv); CKL();
+    k_scan_exclusive<<<4, 1024, 0, s>>>(cnt_can, nv, nv + 1); CKL();      // cnt_can | cnt_fm | flag_can | flag_fm
     CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -924,8 +921,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (n_s > 0) {
       EXCHANGE(ex_.add(ctx->S.p, (size_t)n_s * n_s, 0); ex_.add(ctx->rhs.p, n_s, 0));
       if (n_s <= CHOL_SMALL_MAX) {
-        const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
         const int R = (n_s + 15) / 16;
+        const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * 16 * (size_t)R + (size_t)n_s + 2) * sizeof(double);
 #define CS(RR) case RR: k_chol_small<RR><<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); break;
         switch (R) { CS(1) CS(2) CS(3) CS(4) CS(5) CS(6) CS(7) CS(8) }
 #undef CS
