@@ -921,8 +921,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (n_s > 0) {
       EXCHANGE(ex_.add(ctx->S.p, (size_t)n_s * n_s, 0); ex_.add(ctx->rhs.p, n_s, 0));
       if (n_s <= CHOL_SMALL_MAX) {
+        const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
         const int R = (n_s + 15) / 16;
-        const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * 16 * (size_t)R + (size_t)n_s + 2) * sizeof(double);
 #define CS(RR) case RR: k_chol_small<RR><<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); break;
         switch (R) { CS(1) CS(2) CS(3) CS(4) CS(5) CS(6) CS(7) CS(8) }
 #undef CS

@@ -393,50 +393,21 @@ __global__ void k_schur_rhs(int n_s, int F, int chunk_frames, const double* Y, c
 constexpr int CHOL_SMALL_MAX = 128;
 constexpr int CHOL_SMALL_THREADS = 256;
 // One CTA of 16x16 threads; the matrix lives in REGISTERS, cyclically distributed: thread (ty,tx) owns A[ty+16p][tx+16q],
-// p,q < R (R = ceil(n/16) <= 8).  The scaled pivot column travels through a double-buffered shared array and there is ONE
-// barrier per column: the half-warp that owns column k+1 updates that column first, factors it (pivot broadcast by a
-// half-warp shuffle, rsqrt, scale) and publishes it while the other warps are still applying column k (look-ahead).
-// The factor is then written to shared memory and warp 0 does both substitutions with the right-hand side in registers
-// and one shuffle broadcast per column.
-template <int R>
-__device__ __forceinline__ void chol_owner_step(double (&a)[R][R], int k, int n, int ty, unsigned half_mask, int half_base,
-                                                double* colbuf, double* invd, SolverState* st) {
-  const int kq = k >> 4, kt = k & 15;
-  double col[R];
-#define MCBA_GETQ(Q) case Q: if constexpr (Q < R) { _Pragma("unroll") for (int p = 0; p < R; p++) col[p] = a[p][Q < R ? Q : 0]; } break;
-  switch (kq) { MCBA_GETQ(0) MCBA_GETQ(1) MCBA_GETQ(2) MCBA_GETQ(3) MCBA_GETQ(4) MCBA_GETQ(5) MCBA_GETQ(6) MCBA_GETQ(7) }
-#undef MCBA_GETQ
-  double mine = 0.0;
-#pragma unroll
-  for (int p = 0; p < R; p++) if (p == kq) mine = col[p];
-  const double akk = __shfl_sync(half_mask, mine, half_base + kt);       // A[k][k] lives in lane ty == k % 16 of this half-warp
-  if (ty == kt && !(akk > 0.0)) st->chol_fail += 1;
-  const double rs = rsqrt(fmax(akk, 1e-300));
-  if (ty == kt) invd[k] = rs;
-#pragma unroll
-  for (int p = 0; p < R; p++) {
-    const int i = ty + 16 * p;
-    const double l = col[p] * rs;
-    if (i >= k) col[p] = l;
-    colbuf[i] = (i > k && i < n) ? l : 0.0;          // rows <= k (finished) and >= n (padding) read as zero: no predicates in the update
-  }
-#define MCBA_SETQ(Q) case Q: if constexpr (Q < R) { _Pragma("unroll") for (int p = 0; p < R; p++) a[p][Q < R ? Q : 0] = col[p]; } break;
-  switch (kq) { MCBA_SETQ(0) MCBA_SETQ(1) MCBA_SETQ(2) MCBA_SETQ(3) MCBA_SETQ(4) MCBA_SETQ(5) MCBA_SETQ(6) MCBA_SETQ(7) }
-#undef MCBA_SETQ
-}
-
+// p,q < R (R = ceil(n/16) <= 8).  Per column: the pivot and the scaled column go through shared memory (2 barriers), the
+// rank-1 update is R*R predicated FMAs on registers.  The factor is then written to shared memory and warp 0 does both
+// substitutions with the right-hand side in registers and one shuffle broadcast per column.
 template <int R>
 __global__ void __launch_bounds__(CHOL_SMALL_THREADS)
 k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, SolverState* st, double* out) {
   extern __shared__ double shm[];
   const int ld = n | 1;
   double* Lm = shm;                       // n x ld   (written after the factorisation)
-  double* colbuf = Lm + (size_t)n * ld;   // 2 x 16R  (double buffered pivot column)
-  double* invd = colbuf + 2 * 16 * R;     // n        1 / L_kk
-  // column index is the SLOW thread index: all owners of a matrix column sit in one half-warp
+  double* colbuf = Lm + (size_t)n * ld;   // n
+  double* invd = colbuf + n;              // n        1 / L_kk
+  double* piv = invd + n;                 // 1 (+1 pad)
+  // column index is the SLOW thread index: all owners of a matrix column sit in one half-warp, so only that warp
+  // executes the pivot / column-scaling code
   const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
-  const unsigned half_mask = (tx & 1) ? 0xffff0000u : 0x0000ffffu;
-  const int half_base = (tx & 1) * 16;
   const double reg = st->reg;
   double a[R][R];
 #pragma unroll
@@ -446,37 +417,37 @@ k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, Solve
       const int i = ty + 16 * p, j = tx + 16 * q;
       a[p][q] = (i < n && j < n) ? Sg[(size_t)j * n + i] + (i == j ? reg : 0.0) : 0.0;     // S is symmetric: coalesced read
     }
-  if (tx == 0) chol_owner_step<R>(a, 0, n, ty, half_mask, half_base, colbuf, invd, st);
+  if (tid == 0) piv[0] = a[0][0];
   __syncthreads();
   for (int k = 0; k < n; k++) {
-    const double* cb = colbuf + (k & 1) * 16 * R;
+    const int kq = k >> 4, kt = k & 15;
+    if (tx == kt) {
+      const double akk = piv[0];
+      if (ty == kt && !(akk > 0.0)) st->chol_fail += 1;
+      const double rs = rsqrt(fmax(akk, 1e-300));
+      if (ty == kt) invd[k] = rs;
+#define MCBA_SCALE_Q(Q) case Q: if constexpr (Q < R) { _Pragma("unroll") for (int p = 0; p < R; p++) { const int i = ty + 16 * p; \
+        if (i >= k && i < n) { const double l = a[p][Q < R ? Q : 0] * rs; a[p][Q < R ? Q : 0] = l; colbuf[i] = l; } } } break;
+      switch (kq) { MCBA_SCALE_Q(0) MCBA_SCALE_Q(1) MCBA_SCALE_Q(2) MCBA_SCALE_Q(3) MCBA_SCALE_Q(4) MCBA_SCALE_Q(5) MCBA_SCALE_Q(6) MCBA_SCALE_Q(7) }
+#undef MCBA_SCALE_Q
+    }
+    __syncthreads();
     double ci[R], cj[R];
 #pragma unroll
-    for (int p = 0; p < R; p++) ci[p] = cb[ty + 16 * p];
+    for (int p = 0; p < R; p++) { const int i = ty + 16 * p; ci[p] = (i > k && i < n) ? colbuf[i] : 0.0; }
 #pragma unroll
-    for (int q = 0; q < R; q++) cj[q] = cb[tx + 16 * q];
-    const int k1 = k + 1;
-    if (k1 < n && tx == (k1 & 15)) {
-      // look-ahead: bring my column k+1 up to date, factor and publish it, then finish applying column k
-      const int q1 = k1 >> 4;
+    for (int q = 0; q < R; q++) { const int j = tx + 16 * q; cj[q] = (j > k && j < n) ? colbuf[j] : 0.0; }
 #pragma unroll
-      for (int q = 0; q < R; q++)
-        if (q == q1) {
+    for (int p = 0; p < R; p++)
 #pragma unroll
-          for (int p = 0; p < R; p++) a[p][q] -= ci[p] * cj[q];
-        }
-      chol_owner_step<R>(a, k1, n, ty, half_mask, half_base, colbuf + (k1 & 1) * 16 * R, invd, st);
+      for (int q = 0; q < R; q++) a[p][q] -= ci[p] * cj[q];       // (also touches the unused upper triangle: harmless)
+    // publish the next pivot
+    {
+      const int k1 = k + 1, q1 = k1 >> 4, t1 = k1 & 15;
+      if (k1 < n && ty == t1 && tx == t1) {
 #pragma unroll
-      for (int q = 0; q < R; q++)
-        if (q != q1) {
-#pragma unroll
-          for (int p = 0; p < R; p++) a[p][q] -= ci[p] * cj[q];
-        }
-    } else {
-#pragma unroll
-      for (int p = 0; p < R; p++)
-#pragma unroll
-        for (int q = 0; q < R; q++) a[p][q] -= ci[p] * cj[q];       // (also touches the unused upper triangle: harmless)
+        for (int p = 0; p < R; p++) if (p == q1) piv[0] = a[p][p];
+      }
     }
     __syncthreads();
   }
