@@ -54,14 +54,32 @@ def cpu_reference_step(scene):
 
 
 class ClockSampler(threading.Thread):
+  """SM clock and throttle reasons sampled DURING the timed regions: NVML (1 ms period) when importable, else nvidia-smi."""
+  REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
   def __init__(self, index=0):
     super().__init__(daemon=True)
-    self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+    self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.source = index, [], set(), False, None, None
 
-  def run(self):
+  def _run_nvml(self):
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+    self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+    get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+    self.source = "nvml"
+    while not self.stop_flag:
+      self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+      mask = int(get_reasons(h))
+      for bit, name in self.REASONS.items():
+        if mask & bit: self.reasons.add(name)
+      time.sleep(0.001)
+
+  def _run_smi(self):
     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    self.source = "nvidia-smi"
     while not self.stop_flag:
       try:
         out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
@@ -71,11 +89,17 @@ class ClockSampler(threading.Thread):
           if "Active" in v and "Not" not in v: self.reasons.add(n)
       except Exception:
         pass
-      time.sleep(0.1)
+      time.sleep(0.05)
+
+  def run(self):
+    try:
+      self._run_nvml()
+    except Exception:
+      if not self.stop_flag: self._run_smi()
 
   def summary(self):
     return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
-                reasons=sorted(self.reasons), samples=len(self.samples))
+                reasons=sorted(self.reasons), samples=len(self.samples), source=self.source)
 
 
 def measured_peak():
