@@ -323,3 +323,34 @@ def test_iteration_table_matches_the_trf_model(name):
     compared += 1
   assert compared >= 3
   assert out.last_solve.cost <= cost * (1 + 1e-7)
+
+
+@pytest.mark.parametrize("opt", [dict(cameras=True, motion=False), dict(camera_poses=False, board_poses=False, motion=True),
+                                 dict(cameras=False, camera_poses=False, board_poses=False, motion=False)])
+def test_degenerate_block_selections(opt):
+  """No frame block to eliminate (motion fixed), no shared block at all (only the rig poses free), nothing free."""
+  scene = synthetic.make_scene(C=2, F=6, vis=0.5, seed=91)
+  calib = from_scene(scene).enable(**opt)
+  prob = Problem.from_scene(scene, optimize=opt)
+  x0 = prob.param_vec
+  eng = calib._upload(calib.inliers)
+  assert eng.num_params == x0.size
+  if x0.size:
+    x1 = x0 + np.random.default_rng(9).normal(0, 1e-3, x0.size)
+    assert np.abs(eng.residuals(x1) - prob.residuals(x1)).max() < 1e-9
+    S = prob.sparsity_matrix()
+    J = approx_derivative(prob.residuals, x1, method="3-point", sparsity=(S, group_columns(S))).toarray()
+    JtJ, Jtr, _ = eng.linearize(x1)
+    H = J.T @ J
+    nrm = np.sqrt(np.outer(np.diag(H), np.diag(H))); live = nrm > 0
+    assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  out = calib.bundle_adjust(tolerance=1e-10, max_iterations=60)
+  r0 = prob.residuals()
+  assert out.last_solve.cost <= 0.5 * r0 @ r0 * (1 + 1e-12)
+  if x0.size:
+    jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, group_columns(S))).toarray()
+    ref = optimize.least_squares(prob.residuals, x0, jac=jac, x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14,
+                                 max_nfev=300, method="trf", tr_solver="exact")
+    assert abs(out.last_solve.cost - ref.cost) <= 1e-7 * ref.cost, (out.last_solve.cost, ref.cost)
+  else:
+    assert out.last_solve.nfev == 1 and np.allclose(out.motion.poses, calib.motion.poses)
