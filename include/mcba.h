@@ -132,7 +132,8 @@ int  mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* r
                 mcba_log_row* log, int32_t log_capacity);
 
 /* -- measurement hooks (bench.py): launch one kernel family on the context stream -------------- */
-enum { MCBA_BENCH_LINEARIZE = 0, MCBA_BENCH_RESIDUAL = 1, MCBA_BENCH_COST = 2 };
+enum { MCBA_BENCH_LINEARIZE = 0, MCBA_BENCH_RESIDUAL = 1, MCBA_BENCH_COST = 2,
+       MCBA_BENCH_NO_PREPARE = 256 /* or-ed in: reuse the pose tables of the previous call (times the kernel alone) */ };
 int  mcba_bench_launch(mcba_ctx* ctx, int which, int repeats);
 int  mcba_bench_info(mcba_ctx* ctx, int which, int64_t* corners, int64_t* bytes_per_launch, int32_t* launches_per_call);
 

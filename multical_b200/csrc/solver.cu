@@ -1038,7 +1038,9 @@ int mcba_bench_launch(mcba_ctx* ctx, int which, int repeats) {
   REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
   CK(cudaSetDevice(ctx->device));
   DeviceProblem P = with_state(ctx, false);
-  int r = prepare(ctx, P); if (r) return r;
+  int r;
+  if (!(which & MCBA_BENCH_NO_PREPARE)) { r = prepare(ctx, P); if (r) return r; }
+  which &= ~MCBA_BENCH_NO_PREPARE;
   for (int i = 0; i < repeats; i++) {
     ViewKernelArgs a{}; a.loss = 0; a.f_scale = 1.0;
     if (which == MCBA_BENCH_LINEARIZE) { a.moments = ctx->moments.p; r = launch_moments(ctx, P, a); }
