@@ -131,6 +131,47 @@ int  mcba_reprojection_error(mcba_ctx* ctx, double* err);
 int  mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* result,
                 mcba_log_row* log, int32_t log_capacity);
 
+/* -- resident point table: the outlier loop without host round trips --------------------------------
+ * Calibration.adjust_outliers (calibration.py:250-266) alternates  report -> select threshold (np.quantile of the
+ * per-corner error over `valid`, calibration.py:37-40) -> reject_outliers (calibration.py:240-252, errors from
+ * tables.reprojection_error, tables.py:244-249) -> bundle_adjust.  With the table resident, the dense
+ * [C,F,B,P] observations cross PCIe once; each round moves a few order statistics and one mask count.
+ *
+ * mcba_table_upload: valid uint8[C][F][B][P] = point_table.valid & pose validity (calibration.py:73-76),
+ *   points f64[C][F][B][P][2]; the inlier mask starts equal to `valid`; the packed set is `valid`.
+ * mcba_table_from_detections: the same table built on the device from the per-image detection lists the
+ *   reference keeps before tables.make_point_table (tables.py:68-81; fill_sparse 15-21): list w = (c*F+f)*B+b
+ *   holds det_ids[det_start[w]..det_start[w+1]) (point ids on board b) and det_xy (pixel corners).  Ids outside
+ *   [0,P) fail with MCBA_ERR_ARG; a repeated id within one list keeps an unspecified one of its corners.
+ * Both reset the parameter state to zero like mcba_upload; set it afterwards.                                    */
+typedef struct mcba_table_stats {
+  int64_t n_valid, n_inliers;          /* corners in `valid` / in the current inlier mask                        */
+  double  sumsq_valid, sumsq_inliers;  /* sum of squared pixel errors over each set (mse = sumsq / n)            */
+} mcba_table_stats;
+enum { MCBA_TABLE_VALID = 0, MCBA_TABLE_INLIERS = 1 };
+
+int  mcba_table_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const double* points,
+                       const double* board_points, int64_t* n_valid);
+int  mcba_table_from_detections(mcba_ctx* ctx, const mcba_problem_desc* desc, const int64_t* det_start,
+                                const int32_t* det_ids, const double* det_xy, const double* board_points,
+                                int64_t* n_valid);
+/* read the resident table back (either pointer may be NULL): valid uint8[C][F][B][P], points f64[C][F][B][P][2] */
+int  mcba_table_download(mcba_ctx* ctx, uint8_t* valid, double* points);
+/* inlier mask uint8[C][F][B][P]; set: NULL restores inliers = valid, otherwise the mask is and-ed with `valid` */
+int  mcba_table_set_inliers(mcba_ctx* ctx, const uint8_t* mask);
+int  mcba_table_get_inliers(mcba_ctx* ctx, uint8_t* mask);
+/* pack `valid` or the inlier mask as the problem the solver / residual entry points work on; the parameter state
+ * is kept.  *n_corners (may be NULL) receives the packed count. */
+int  mcba_table_select(mcba_ctx* ctx, int which, int64_t* n_corners);
+/* per-corner error over `valid` at the current parameters, kept on the device sorted (all valid, and the inlier
+ * subset) for mcba_table_error_ranks / mcba_table_reject; selects MCBA_TABLE_VALID as a side effect. */
+int  mcba_table_errors(mcba_ctx* ctx, mcba_table_stats* stats);
+/* out[i] = ranks[i]-th smallest error (0-based) of the chosen set -- the order statistics np.quantile interpolates */
+int  mcba_table_error_ranks(mcba_ctx* ctx, int which, const int64_t* ranks, int32_t n, double* out);
+/* inliers = valid & (error < threshold) (calibration.py:243-244) with the errors of the last mcba_table_errors;
+ * MCBA_ERR_STATE if parameters or selection changed since.  Follow with mcba_table_select(MCBA_TABLE_INLIERS). */
+int  mcba_table_reject(mcba_ctx* ctx, double threshold, int64_t* n_valid, int64_t* n_keep);
+
 /* -- measurement hooks (bench.py): launch one kernel family on the context stream -------------- */
 enum { MCBA_BENCH_LINEARIZE = 0, MCBA_BENCH_RESIDUAL = 1, MCBA_BENCH_COST = 2,
        MCBA_BENCH_NO_PREPARE = 256 /* or-ed in: reuse the pose tables of the previous call (times the kernel alone) */ };

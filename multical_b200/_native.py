@@ -24,7 +24,10 @@ STATUS_MESSAGES = {
 EXPORTS = ["mcba_create", "mcba_destroy", "mcba_last_error", "mcba_set_stream", "mcba_version",
            "mcba_comm_unique_id", "mcba_comm_init", "mcba_peer_export", "mcba_peer_import", "mcba_upload", "mcba_upload_dense", "mcba_set_params", "mcba_get_params", "mcba_set_state_matrices", "mcba_get_state_matrices",
            "mcba_num_params", "mcba_get_param_vec", "mcba_set_param_vec", "mcba_residuals",
-           "mcba_linearize", "mcba_reprojection_error", "mcba_solve", "mcba_bench_launch", "mcba_bench_info"]
+           "mcba_linearize", "mcba_reprojection_error", "mcba_solve", "mcba_bench_launch", "mcba_bench_info",
+           "mcba_table_upload", "mcba_table_from_detections", "mcba_table_download", "mcba_table_set_inliers",
+           "mcba_table_get_inliers", "mcba_table_select", "mcba_table_errors", "mcba_table_error_ranks", "mcba_table_reject"]
+TABLE_VALID, TABLE_INLIERS = 0, 1
 
 
 class ProblemDesc(C.Structure):
@@ -46,6 +49,10 @@ class SolveResult(C.Structure):
   _fields_ = [("cost", C.c_double), ("initial_cost", C.c_double), ("optimality", C.c_double),
               ("nfev", C.c_int32), ("njev", C.c_int32), ("status", C.c_int32), ("n_log", C.c_int32),
               ("device_ms", C.c_double), ("kernel_launches", C.c_int32), ("chol_retries", C.c_int32)]
+
+
+class TableStats(C.Structure):
+  _fields_ = [("n_valid", C.c_int64), ("n_inliers", C.c_int64), ("sumsq_valid", C.c_double), ("sumsq_inliers", C.c_double)]
 
 
 class NativeError(RuntimeError):
@@ -88,6 +95,16 @@ def load():
   lib.mcba_solve.argtypes = [P, C.POINTER(SolveOpts), C.POINTER(SolveResult), C.POINTER(LogRow), C.c_int32]
   lib.mcba_bench_launch.argtypes = [P, C.c_int, C.c_int]
   lib.mcba_bench_info.argtypes = [P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+  U8, I64 = C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
+  lib.mcba_table_upload.argtypes = [P, C.POINTER(ProblemDesc), U8, D, D, I64]
+  lib.mcba_table_from_detections.argtypes = [P, C.POINTER(ProblemDesc), I64, I32, D, D, I64]
+  lib.mcba_table_download.argtypes = [P, U8, D]
+  lib.mcba_table_set_inliers.argtypes = [P, U8]
+  lib.mcba_table_get_inliers.argtypes = [P, U8]
+  lib.mcba_table_select.argtypes = [P, C.c_int, I64]
+  lib.mcba_table_errors.argtypes = [P, C.POINTER(TableStats)]
+  lib.mcba_table_error_ranks.argtypes = [P, C.c_int, I64, C.c_int32, D]
+  lib.mcba_table_reject.argtypes = [P, C.c_double, I64, I64]
   _lib = lib
   return lib
 

@@ -19,17 +19,11 @@ from .board import stack_boards
 from .camera import engine_model_of
 from .engine import Engine, format_log, pack_corners
 from .log import info
+from .outliers import QuantileThreshold, select_threshold      # noqa: F401  (select_threshold: calibration.py:37-40)
 from .parameters import Parameters
 from .structs import Table, struct
 
 default_optimize = struct(cameras=False, boards=False, camera_poses=True, board_poses=True, motion=True)
-
-
-def select_threshold(quantile=0.75, factor=5.0):
-  """calibration.py:37-40"""
-  def f(reprojection_error):
-    return np.quantile(reprojection_error, quantile) * factor
-  return f
 
 
 _engines = {}
@@ -162,11 +156,14 @@ class Calibration(Parameters):
     eng = get_engine(device)
     pts = np.asarray(self.point_table.points) if points is None else points
     eng.upload_dense(self.engine_model, self._optimize_bits(), mask, pts, self.board_points.points)
+    self._push_state(eng)
+    return eng
+
+  def _push_state(self, eng):
     # poses go over as 4x4 matrices: the matrix -> rotation-vector conversion (transform/rtvec.py:29-32) runs on the device
     mats = np.concatenate([np.asarray(self.camera_poses.poses, np.float64), np.asarray(self.board_poses.poses, np.float64),
                            np.asarray(self.motion.poses, np.float64)], axis=0)
     eng.set_state_matrices(mats, np.stack([np.asarray(c.param_vec, np.float64) for c in self.cameras]))
-    return eng
 
   def _with_engine_state(self, eng):
     """New Calibration holding the engine's solved state -- what `self.with_param_vec(res.x)` returns in the reference
@@ -280,14 +277,19 @@ class Calibration(Parameters):
     """Non-linear least squares on point reprojection error (calibration.py:199-212), solved on the GPU
     with scipy-TRF semantics: ftol=tolerance, max_nfev=max_iterations, x_scale='jac', robust `loss`."""
     eng = self._upload(self.inliers)
+    res = self._solve_logged(eng, tolerance, f_scale, max_iterations, loss, xtol, gtol)
+    out = self._with_engine_state(eng)
+    out.__dict__["last_solve"] = res
+    return out
+
+  @staticmethod
+  def _solve_logged(eng, tolerance=1e-4, f_scale=1.0, max_iterations=100, loss="linear", xtol=1e-8, gtol=1e-8):
     res = eng.solve(ftol=tolerance, xtol=xtol, gtol=gtol, f_scale=f_scale, max_nfev=max_iterations, loss=loss)
     for line in format_log(res.log): info(line)
     info(res.message)
     info(f"Function evaluations {res.nfev}, initial cost {res.initial_cost:.4e}, final cost {res.cost:.4e}, "
          f"first-order optimality {res.optimality:.2e}.")
-    out = self._with_engine_state(eng)
-    out.__dict__["last_solve"] = res
-    return out
+    return res
 
   def enable(self, **flags):
     for k in flags.keys():
@@ -323,6 +325,9 @@ class Calibration(Parameters):
     """Alternate outlier rejection and bundle adjustment `num_adjustments` times (workspace.py:228-247 drives this).
     select_outliers / select_scale map the current error vector to a pixel threshold / to the loss f_scale."""
     info(f"Beginning adjustments ({num_adjustments}) enabled: {self.optimize}, options: {kwargs}")
+    on_device = all(s is None or isinstance(s, QuantileThreshold) for s in (select_scale, select_outliers))
+    if on_device and self.valid.any() and not os.environ.get("MCBA_HOST_OUTLIERS"):
+      return self._adjust_outliers_resident(num_adjustments, select_scale, select_outliers, **kwargs)
     calib = self
     for round_index in range(num_adjustments):
       calib.report(f"Adjust_outliers {round_index}:")
@@ -337,13 +342,66 @@ class Calibration(Parameters):
     calib.report("Adjust_outliers end:")
     return calib
 
+  def _adjust_outliers_resident(self, num_adjustments, select_scale, select_outliers, **kwargs):
+    """The same loop with the point table resident on the GPU (include/mcba.h "resident point table"): the dense table is
+    uploaded once; each round the host sees the five-number summaries for the log, the order statistics around the selected
+    quantiles and the inlier count.  The error vector, the masks and the repacking stay on the device."""
+    eng = get_engine()
+    eng.table_upload(self.engine_model, self._optimize_bits(), self.valid, np.asarray(self.point_table.points),
+                     self.board_points.points)
+    self._push_state(eng)
+    masked = self.inlier_mask is not None
+    if masked: eng.table_set_inliers(np.asarray(self.inlier_mask))
+    five = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+
+    def summary(which, n, sumsq):
+      if n == 0:                                   # the reference's guard: an empty vector counts as a single zero
+        return struct(mse=0.0, rms=0.0, quantiles=np.zeros(5), n=1)
+      return struct(mse=sumsq / n, rms=float(np.sqrt(sumsq / n)), quantiles=eng.table_quantile(which, n, five), n=n)
+
+    def report(stage):
+      st = eng.table_errors()
+      _report_line(stage, summary("valid", st.n_valid, st.sumsq_valid),
+                   summary("inliers", st.n_inliers, st.sumsq_inliers) if masked else None)
+      return st
+
+    res = None
+    for round_index in range(num_adjustments):
+      st = report(f"Adjust_outliers {round_index}:")
+      f_scale = 1.0
+      if select_scale is not None:
+        f_scale = eng.table_quantile("valid", st.n_valid, select_scale.quantile) * select_scale.factor or 1.0
+        info(f"Auto scaling for outliers influence at {f_scale:.2f} pixels")
+      if select_outliers is not None:
+        threshold = eng.table_quantile("valid", st.n_valid, select_outliers.quantile) * select_outliers.factor
+        n_valid, n_keep = eng.table_reject(threshold)
+        masked = True
+        info(f"Rejecting {n_valid - n_keep} outliers with error > {threshold:.2f} pixels, "
+             f"keeping {n_keep} / {n_valid} inliers, ({100.0 * n_keep / n_valid:.2f}%)")
+      eng.table_select("inliers")
+      res = self._solve_logged(eng, f_scale=f_scale, **_solve_args(**kwargs))
+    report("Adjust_outliers end:")
+    out = self._with_engine_state(eng)
+    if masked: out = out.copy(inlier_mask=eng.table_get_inliers())
+    out.__dict__["last_solve"] = res
+    return out
+
   def report(self, stage=""):
-    everything, kept = error_stats(self.reprojection_error), error_stats(self.reprojection_inliers)
-    if self.inlier_mask is None:
-      info(f"{stage} reprojection RMS={everything.rms:.3f}, n={everything.n}, quantiles={everything.quantiles}")
-    else:
-      info(f"{stage} reprojection RMS={kept.rms:.3f} ({everything.rms:.3f}), "
-           f"n={kept.n} ({everything.n}), quantiles={everything.quantiles}")
+    _report_line(stage, error_stats(self.reprojection_error),
+                 None if self.inlier_mask is None else error_stats(self.reprojection_inliers))
+
+
+def _solve_args(tolerance=1e-4, max_iterations=100, loss="linear", xtol=1e-8, gtol=1e-8):
+  """bundle_adjust's keyword arguments (f_scale is chosen by the outlier loop), checked the way a call would check them."""
+  return dict(tolerance=tolerance, max_iterations=max_iterations, loss=loss, xtol=xtol, gtol=gtol)
+
+
+def _report_line(stage, everything, kept):
+  if kept is None:
+    info(f"{stage} reprojection RMS={everything.rms:.3f}, n={everything.n}, quantiles={everything.quantiles}")
+  else:
+    info(f"{stage} reprojection RMS={kept.rms:.3f} ({everything.rms:.3f}), "
+         f"n={kept.n} ({everything.n}), quantiles={everything.quantiles}")
 
 
 def error_stats(errors):

@@ -2,6 +2,7 @@
 // extern "C" entry points declared in include/mcba.h.  No CPU fallback: everything numeric runs in the
 // kernels of kernels.cuh / solver_kernels.cuh.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
@@ -14,6 +15,7 @@
 #include "../../include/mcba.h"
 #include "solver_kernels.cuh"
 #include "pack_kernels.cuh"
+#include "table_kernels.cuh"
 #include "peer_allreduce.cuh"
 
 using namespace mcba;
@@ -101,6 +103,14 @@ struct mcba_ctx {
   double* peer_base[PEER_MAX_WORLD] = {nullptr};
   std::vector<void*> peer_opened;
   std::vector<int> perm;   // internal index -> canonical param_vec index
+  // resident point table (mcba_table_*): `valid` and inlier masks, sorted per-corner errors
+  bool table = false; int table_selected = -1; bool errors_current = false;
+  mcba_problem_desc table_desc{};
+  int64_t n_valid = 0, n_inliers = 0;
+  DevBuf<uint8_t> valid_mask, inlier_mask;
+  DevBuf<double> err_valid, err_sorted, err_inl, err_inl_sorted, table_part, table_out;
+  DevBuf<int64_t> table_ranks;
+  DevBuf<unsigned char> sort_tmp;
 };
 
 #define CK(call)                                                                                   \
@@ -336,7 +346,7 @@ int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int fin
 }
 
 // dimensions, variable layout, permutation and every solver buffer that depends on (C,F,B,P,N,V)
-int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V) {
+int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V, bool keep_state = false) {
   const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
   DeviceProblem& P = ctx->P;
   P = DeviceProblem{};
@@ -387,10 +397,12 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
   CK(ctx->state.alloc(1));
   CK(ctx->counter.alloc(4)); CK(cudaMemsetAsync(ctx->counter.p, 0, 4 * sizeof(unsigned), ctx->stream));
-  CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
-  CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
-  CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
-  CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
+  if (!keep_state) {     // a re-selection of the resident table (mcba_table_select) keeps the parameter state
+    CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
+    CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
+    CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
+    CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
+  }
 
   P.obs = ctx->obs.p; P.pid = ctx->pid.p; P.orig = ctx->orig.p;
   P.view_start = ctx->view_start.p; P.view_cam = ctx->view_cam.p; P.view_frame = ctx->view_frame.p; P.view_board = ctx->view_board.p;
@@ -406,6 +418,40 @@ int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
   REQUIRE(desc->P <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
   REQUIRE(desc->model >= 0 && desc->model <= 4, MCBA_ERR_ARG, "unknown camera model");
   REQUIRE((int64_t)desc->C * desc->F * desc->B * desc->P < ((int64_t)1 << 31), MCBA_ERR_UNSUPPORTED, "more than 2^31 table entries per rank");
+  return MCBA_OK;
+}
+
+// pack the resident dense table (ctx->dense_pts) under a device mask into the frame-major corner arrays the kernels read
+int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_mask, bool keep_state, int64_t* n_corners) {
+  const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
+  const int nv = C * F * B;
+  cudaStream_t s = ctx->stream;
+  CK(ctx->scan.alloc((size_t)4 * (nv + 1)));
+  int* cnt_can = ctx->scan.p; int* cnt_fm = cnt_can + (nv + 1); int* flag_can = cnt_fm + (nv + 1); int* flag_fm = flag_can + (nv + 1);
+  int totals[2] = {0, 0};
+  if (nv > 0) {
+    k_pack_count<<<(nv * 32 + 255) / 256, 256, 0, s>>>(d_mask, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
+    k_scan_exclusive<<<4, 1024, 0, s>>>(cnt_can, nv, nv + 1); CKL();      // cnt_can | cnt_fm | flag_can | flag_fm
+    CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  const int64_t N = totals[0]; const int V = totals[1];
+  CK(ctx->obs.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->pid.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->orig.alloc((size_t)std::max<int64_t>(N, 1)));
+  CK(ctx->view_start.alloc((size_t)V + 1)); CK(ctx->view_cam.alloc((size_t)std::max(V, 1))); CK(ctx->view_frame.alloc((size_t)std::max(V, 1))); CK(ctx->view_board.alloc((size_t)std::max(V, 1)));
+  CK(ctx->frame_view_start.alloc((size_t)F + 1)); CK(ctx->cam_view_start.alloc((size_t)C + 1)); CK(ctx->cam_view_list.alloc((size_t)std::max(V, 1)));
+  if (nv > 0) {
+    PackOut o{ctx->obs.p, ctx->pid.p, ctx->orig.p, ctx->view_start.p, ctx->view_cam.p, ctx->view_frame.p, ctx->view_board.p,
+              ctx->frame_view_start.p, ctx->cam_view_start.p, ctx->cam_view_list.p};
+    k_pack_scatter<<<(nv * 32 + 255) / 256, 256, 0, s>>>(d_mask, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL();
+  } else {
+    CK(cudaMemsetAsync(ctx->view_start.p, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctx->frame_view_start.p, 0, sizeof(int) * (F + 1), s));
+    CK(cudaMemsetAsync(ctx->cam_view_start.p, 0, sizeof(int) * (C + 1), s));
+  }
+  { int r = setup_problem(ctx, desc, N, V, keep_state); if (r) return r; }
+  CK(cudaStreamSynchronize(s));
+  if (n_corners) *n_corners = N;
+  ctx->uploaded = true;
   return MCBA_OK;
 }
 
@@ -541,6 +587,7 @@ int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam
   REQUIRE(N >= 0 && N < ((int64_t)1 << 31), MCBA_ERR_UNSUPPORTED, "corner count out of range");
   REQUIRE(N == 0 || (cam && frame && board && point && obs), MCBA_ERR_ARG, "null corner arrays");
   REQUIRE(board_points != nullptr, MCBA_ERR_ARG, "null board points");
+  ctx->table = false; ctx->table_selected = -1; ctx->errors_current = false;
 
   // ---- pack: stable counting sort of the canonical (c,f,b,p)-ordered corners by frame => (f,c,b,p) order
   std::vector<int64_t> fcount((size_t)F + 1, 0);
@@ -618,31 +665,234 @@ int mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_
   }
   CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
   CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
-  int* cnt_can = ctx->scan.p; int* cnt_fm = cnt_can + (nv + 1); int* flag_can = cnt_fm + (nv + 1); int* flag_fm = flag_can + (nv + 1);
-  int totals[2] = {0, 0};
-  if (nv > 0) {
-    k_pack_count<<<(nv * 32 + 255) / 256, 256, 0, s>>>(ctx->dense_mask.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
-    k_scan_exclusive<<<4, 1024, 0, s>>>(cnt_can, nv, nv + 1); CKL();      // cnt_can | cnt_fm | flag_can | flag_fm
-    CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ctx->table = false; ctx->table_selected = -1; ctx->errors_current = false;
+  return pack_dense(ctx, desc, ctx->dense_mask.p, false, n_corners);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Resident point table (include/mcba.h "resident point table"): Calibration.adjust_outliers without host round trips.
+
+namespace {
+
+int table_begin(mcba_ctx* ctx, const mcba_problem_desc* desc, const double* board_points, size_t* dense_out) {
+  CK(cudaSetDevice(ctx->device));
+  { int r = check_desc(ctx, desc); if (r) return r; }
+  REQUIRE(board_points != nullptr, MCBA_ERR_ARG, "null board points");
+  const size_t dense = (size_t)desc->C * desc->F * desc->B * desc->P;
+  CK(ctx->valid_mask.alloc(std::max<size_t>(dense, 1))); CK(ctx->inlier_mask.alloc(std::max<size_t>(dense, 1)));
+  CK(ctx->dense_pts.alloc(std::max<size_t>(dense, 1)));
+  CK(ctx->board_pts.alloc((size_t)desc->B * desc->P * 3));
+  CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)desc->B * desc->P * 3, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->table = false; ctx->table_selected = -1; ctx->errors_current = false;
+  *dense_out = dense;
+  return MCBA_OK;
+}
+
+// inliers = valid, pack `valid`, remember the description
+int table_finish(mcba_ctx* ctx, const mcba_problem_desc* desc, size_t dense, int64_t* n_valid) {
+  if (dense) CK(cudaMemcpyAsync(ctx->inlier_mask.p, ctx->valid_mask.p, dense, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->table_desc = *desc;
+  int64_t n = 0;
+  { int r = pack_dense(ctx, desc, ctx->valid_mask.p, false, &n); if (r) return r; }
+  ctx->table = true; ctx->table_selected = MCBA_TABLE_VALID;
+  ctx->n_valid = n; ctx->n_inliers = n;
+  if (n_valid) *n_valid = n;
+  return MCBA_OK;
+}
+
+size_t table_dense(const mcba_ctx* ctx) {
+  const mcba_problem_desc& d = ctx->table_desc;
+  return (size_t)d.C * d.F * d.B * d.P;
+}
+
+int sort_errors(mcba_ctx* ctx, const double* in, double* out, int64_t n) {
+  size_t bytes = 0;
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, n, 0, 64, ctx->stream));
+  CK(ctx->sort_tmp.alloc(bytes));
+  bytes = ctx->sort_tmp.n;
+  CK(cub::DeviceRadixSort::SortKeys(ctx->sort_tmp.p, bytes, in, out, n, 0, 64, ctx->stream));
+  ctx->launches += 4;
+  return MCBA_OK;
+}
+
+}  // namespace
+
+int mcba_table_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const double* points,
+                      const double* board_points, int64_t* n_valid) {
+  if (!ctx || !desc) return MCBA_ERR_ARG;
+  REQUIRE(valid && points, MCBA_ERR_ARG, "null dense table");
+  size_t dense = 0;
+  { int r = table_begin(ctx, desc, board_points, &dense); if (r) return r; }
+  if (dense) {
+    CK(cudaMemcpyAsync(ctx->valid_mask.p, valid, dense, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return table_finish(ctx, desc, dense, n_valid);
+}
+
+int mcba_table_from_detections(mcba_ctx* ctx, const mcba_problem_desc* desc, const int64_t* det_start, const int32_t* det_ids,
+                               const double* det_xy, const double* board_points, int64_t* n_valid) {
+  if (!ctx || !desc) return MCBA_ERR_ARG;
+  REQUIRE(det_start != nullptr, MCBA_ERR_ARG, "null detection offsets");
+  size_t dense = 0;
+  { int r = table_begin(ctx, desc, board_points, &dense); if (r) return r; }
+  const int nv = desc->C * desc->F * desc->B;
+  const int64_t total = det_start[nv];
+  REQUIRE(det_start[0] == 0 && total >= 0 && total < ((int64_t)1 << 31), MCBA_ERR_ARG, "bad detection offsets");
+  REQUIRE(total == 0 || (det_ids && det_xy), MCBA_ERR_ARG, "null detection arrays");
+  cudaStream_t s = ctx->stream;
+  DevBuf<int64_t> d_start; DevBuf<int32_t> d_ids; DevBuf<double2> d_xy; DevBuf<int> d_bad;
+  CK(d_start.alloc((size_t)nv + 1)); CK(d_ids.alloc((size_t)std::max<int64_t>(total, 1))); CK(d_xy.alloc((size_t)std::max<int64_t>(total, 1))); CK(d_bad.alloc(1));
+  CK(cudaMemcpyAsync(d_start.p, det_start, sizeof(int64_t) * ((size_t)nv + 1), cudaMemcpyHostToDevice, s));
+  if (total) {
+    CK(cudaMemcpyAsync(d_ids.p, det_ids, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_xy.p, det_xy, sizeof(double2) * (size_t)total, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), s));
+  if (dense) {
+    CK(cudaMemsetAsync(ctx->valid_mask.p, 0, dense, s));
+    CK(cudaMemsetAsync(ctx->dense_pts.p, 0, dense * sizeof(double2), s));    // fill_sparse leaves zeros where nothing was detected
+  }
+  int bad = 0;
+  k_table_check_offsets<<<(nv + 1 + 255) / 256, 256, 0, s>>>(d_start.p, nv, total, d_bad.p); CKL();
+  CK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  REQUIRE(!bad, MCBA_ERR_ARG, "detection offsets are not a monotone CSR over C*F*B lists");
+  if (nv > 0 && total > 0) {
+    k_table_fill<<<(nv * 32 + 255) / 256, 256, 0, s>>>(d_start.p, d_ids.p, d_xy.p, nv, desc->P, ctx->valid_mask.p, ctx->dense_pts.p, d_bad.p); CKL();
+    CK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    REQUIRE(!bad, MCBA_ERR_ARG, "detection id outside [0, P)");
+  }
+  return table_finish(ctx, desc, dense, n_valid);
+}
+
+int mcba_table_download(mcba_ctx* ctx, uint8_t* valid, double* points) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table, MCBA_ERR_STATE, "no resident table (mcba_table_upload / mcba_table_from_detections)");
+  CK(cudaSetDevice(ctx->device));
+  const size_t dense = table_dense(ctx);
+  if (valid && dense) CK(cudaMemcpyAsync(valid, ctx->valid_mask.p, dense, cudaMemcpyDeviceToHost, ctx->stream));
+  if (points && dense) CK(cudaMemcpyAsync(points, ctx->dense_pts.p, dense * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_table_set_inliers(mcba_ctx* ctx, const uint8_t* mask) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table, MCBA_ERR_STATE, "no resident table (mcba_table_upload / mcba_table_from_detections)");
+  CK(cudaSetDevice(ctx->device));
+  const size_t dense = table_dense(ctx);
+  if (dense) {
+    if (mask) {
+      CK(cudaMemcpyAsync(ctx->inlier_mask.p, mask, dense, cudaMemcpyHostToDevice, ctx->stream));
+      k_mask_and<<<(unsigned)((dense + 255) / 256), 256, 0, ctx->stream>>>(ctx->inlier_mask.p, ctx->valid_mask.p, dense, ctx->inlier_mask.p); CKL();
+    } else {
+      CK(cudaMemcpyAsync(ctx->inlier_mask.p, ctx->valid_mask.p, dense, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));      // the host mask is borrowed only for the call
+  ctx->errors_current = false;
+  if (ctx->table_selected == MCBA_TABLE_INLIERS) ctx->table_selected = -1;     // the packed set no longer matches the mask
+  return MCBA_OK;
+}
+
+int mcba_table_get_inliers(mcba_ctx* ctx, uint8_t* mask) {
+  if (!ctx || !mask) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table, MCBA_ERR_STATE, "no resident table (mcba_table_upload / mcba_table_from_detections)");
+  CK(cudaSetDevice(ctx->device));
+  const size_t dense = table_dense(ctx);
+  if (dense) CK(cudaMemcpyAsync(mask, ctx->inlier_mask.p, dense, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_table_select(mcba_ctx* ctx, int which, int64_t* n_corners) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table, MCBA_ERR_STATE, "no resident table (mcba_table_upload / mcba_table_from_detections)");
+  REQUIRE(which == MCBA_TABLE_VALID || which == MCBA_TABLE_INLIERS, MCBA_ERR_ARG, "unknown table selection");
+  CK(cudaSetDevice(ctx->device));
+  int64_t n = ctx->P.N;
+  if (ctx->table_selected != which) {
+    ctx->errors_current = false;
+    const uint8_t* m = which == MCBA_TABLE_VALID ? ctx->valid_mask.p : ctx->inlier_mask.p;
+    int r = pack_dense(ctx, &ctx->table_desc, m, true, &n); if (r) return r;
+    ctx->table_selected = which;
+    if (which == MCBA_TABLE_INLIERS) ctx->n_inliers = n;
+  }
+  if (n_corners) *n_corners = n;
+  return MCBA_OK;
+}
+
+int mcba_table_errors(mcba_ctx* ctx, mcba_table_stats* stats) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table, MCBA_ERR_STATE, "no resident table (mcba_table_upload / mcba_table_from_detections)");
+  { int r = mcba_table_select(ctx, MCBA_TABLE_VALID, nullptr); if (r) return r; }
+  const DeviceProblem P = with_state(ctx, false);
+  cudaStream_t s = ctx->stream;
+  const int64_t N = P.N;
+  double sums[3] = {0.0, 0.0, 0.0};
+  if (N > 0) {
+    CK(ctx->err_valid.alloc((size_t)N)); CK(ctx->err_sorted.alloc((size_t)N));
+    CK(ctx->err_inl.alloc((size_t)N)); CK(ctx->err_inl_sorted.alloc((size_t)N));
+    CK(ctx->table_part.alloc((size_t)3 * P.V + 3));
+    { int r = prepare(ctx, P); if (r) return r; }
+    ViewKernelArgs a{}; a.err = ctx->err_valid.p;
+    { int r = launch_views<MODE_ERROR>(ctx, P, a); if (r) return r; }
+    const int blocks = std::max(1, std::min((P.V + TABLE_WARPS - 1) / TABLE_WARPS, ctx->num_sms * 8));
+    k_table_stats<<<blocks, TABLE_WARPS * 32, 0, s>>>(P, ctx->err_valid.p, ctx->inlier_mask.p, ctx->err_inl.p, ctx->table_part.p); CKL();
+    double* d_sums = ctx->table_part.p + (size_t)3 * P.V;
+    k_sum_partials<<<1, 1024, 0, s>>>(ctx->table_part.p, P.V, 3, 3, d_sums); CKL();
+    CK(cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, s));
+    { int r = sort_errors(ctx, ctx->err_valid.p, ctx->err_sorted.p, N); if (r) return r; }
+    { int r = sort_errors(ctx, ctx->err_inl.p, ctx->err_inl_sorted.p, N); if (r) return r; }
     CK(cudaStreamSynchronize(s));
   }
-  const int64_t N = totals[0]; const int V = totals[1];
-  CK(ctx->obs.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->pid.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->orig.alloc((size_t)std::max<int64_t>(N, 1)));
-  CK(ctx->view_start.alloc((size_t)V + 1)); CK(ctx->view_cam.alloc((size_t)std::max(V, 1))); CK(ctx->view_frame.alloc((size_t)std::max(V, 1))); CK(ctx->view_board.alloc((size_t)std::max(V, 1)));
-  CK(ctx->frame_view_start.alloc((size_t)F + 1)); CK(ctx->cam_view_start.alloc((size_t)C + 1)); CK(ctx->cam_view_list.alloc((size_t)std::max(V, 1)));
-  if (nv > 0) {
-    PackOut o{ctx->obs.p, ctx->pid.p, ctx->orig.p, ctx->view_start.p, ctx->view_cam.p, ctx->view_frame.p, ctx->view_board.p,
-              ctx->frame_view_start.p, ctx->cam_view_start.p, ctx->cam_view_list.p};
-    k_pack_scatter<<<(nv * 32 + 255) / 256, 256, 0, s>>>(ctx->dense_mask.p, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL();
-  } else {
-    CK(cudaMemsetAsync(ctx->view_start.p, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctx->frame_view_start.p, 0, sizeof(int) * (F + 1), s));
-    CK(cudaMemsetAsync(ctx->cam_view_start.p, 0, sizeof(int) * (C + 1), s));
+  ctx->n_valid = N; ctx->n_inliers = (int64_t)llround(sums[2]);
+  ctx->errors_current = true;
+  if (stats) { stats->n_valid = N; stats->n_inliers = ctx->n_inliers; stats->sumsq_valid = sums[0]; stats->sumsq_inliers = sums[1]; }
+  return MCBA_OK;
+}
+
+int mcba_table_error_ranks(mcba_ctx* ctx, int which, const int64_t* ranks, int32_t n, double* out) {
+  if (!ctx || (n > 0 && (!ranks || !out))) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table && ctx->errors_current, MCBA_ERR_STATE, "mcba_table_errors has not run since the parameters or the selection changed");
+  REQUIRE(which == MCBA_TABLE_VALID || which == MCBA_TABLE_INLIERS, MCBA_ERR_ARG, "unknown table selection");
+  if (n <= 0) return MCBA_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t count = which == MCBA_TABLE_VALID ? ctx->n_valid : ctx->n_inliers;
+  for (int i = 0; i < n; i++) REQUIRE(ranks[i] >= 0 && ranks[i] < count, MCBA_ERR_ARG, "error rank out of range");
+  CK(ctx->table_ranks.alloc((size_t)n)); CK(ctx->table_out.alloc((size_t)n));
+  CK(cudaMemcpyAsync(ctx->table_ranks.p, ranks, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_gather_ranks<<<(n + 127) / 128, 128, 0, ctx->stream>>>(which == MCBA_TABLE_VALID ? ctx->err_sorted.p : ctx->err_inl_sorted.p,
+                                                         ctx->table_ranks.p, n, ctx->table_out.p); CKL();
+  CK(cudaMemcpyAsync(out, ctx->table_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_table_reject(mcba_ctx* ctx, double threshold, int64_t* n_valid, int64_t* n_keep) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table && ctx->errors_current && ctx->table_selected == MCBA_TABLE_VALID, MCBA_ERR_STATE,
+          "mcba_table_errors has not run since the parameters or the selection changed");
+  CK(cudaSetDevice(ctx->device));
+  const DeviceProblem& P = ctx->P;
+  cudaStream_t s = ctx->stream;
+  const size_t dense = table_dense(ctx);
+  double kept = 0.0;
+  if (dense) CK(cudaMemsetAsync(ctx->inlier_mask.p, 0, dense, s));
+  if (P.N > 0) {
+    const int blocks = std::max(1, std::min((P.V + TABLE_WARPS - 1) / TABLE_WARPS, ctx->num_sms * 8));
+    k_table_reject<<<blocks, TABLE_WARPS * 32, 0, s>>>(P, ctx->err_valid.p, threshold, ctx->inlier_mask.p, ctx->table_part.p); CKL();
+    double* d_sum = ctx->table_part.p + (size_t)3 * P.V;
+    k_sum_partials<<<1, 1024, 0, s>>>(ctx->table_part.p, P.V, 1, 1, d_sum); CKL();
+    CK(cudaMemcpyAsync(&kept, d_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
   }
-  { int r = setup_problem(ctx, desc, N, V); if (r) return r; }
   CK(cudaStreamSynchronize(s));
-  if (n_corners) *n_corners = N;
-  ctx->uploaded = true;
+  ctx->n_inliers = (int64_t)llround(kept);
+  ctx->errors_current = false;           // the sorted inlier errors describe the previous mask
+  if (n_valid) *n_valid = P.N;
+  if (n_keep) *n_keep = ctx->n_inliers;
   return MCBA_OK;
 }
 
@@ -652,6 +902,7 @@ int mcba_set_params(mcba_ctx* ctx, const double* cam_rt, const double* board_rt,
   REQUIRE(cam_rt && board_rt && intrinsics && (frame_rt || ctx->P.F == 0), MCBA_ERR_ARG, "null parameter array");
   const DeviceProblem& P = ctx->P;
   CK(cudaSetDevice(ctx->device));
+  ctx->errors_current = false;
   CK(cudaMemcpyAsync(ctx->cam_rt.p, cam_rt, sizeof(double) * P.C * 6, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->board_rt.p, board_rt, sizeof(double) * P.B * 6, cudaMemcpyHostToDevice, ctx->stream));
   if (P.F) CK(cudaMemcpyAsync(ctx->frame_rt.p, frame_rt, sizeof(double) * P.F * 6, cudaMemcpyHostToDevice, ctx->stream));
@@ -669,6 +920,7 @@ int mcba_set_state_matrices(mcba_ctx* ctx, const double* mats, const double* int
   const DeviceProblem& P = ctx->P;
   CK(cudaSetDevice(ctx->device));
   const int np = P.C + P.B + P.F;
+  ctx->errors_current = false;
   CK(ctx->pose_mats.alloc((size_t)np * 16));
   CK(cudaMemcpyAsync(ctx->pose_mats.p, mats, sizeof(double) * 16 * np, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->intr.p, intrinsics, sizeof(double) * P.C * P.kint, cudaMemcpyHostToDevice, ctx->stream));
@@ -744,6 +996,7 @@ int mcba_set_param_vec(mcba_ctx* ctx, const double* x) {
   if (!ctx || !x) return MCBA_ERR_ARG;
   REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
   CK(cudaSetDevice(ctx->device));
+  ctx->errors_current = false;
   int r = write_x_canonical(ctx, x, ctx->x.p); if (r) return r;
   r = set_state_from_x(ctx, ctx->x.p, false); if (r) return r;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -847,6 +1100,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   const int n = P.n, n_s = P.n_s, F = P.motion_on ? P.F : 0;
   memset(result, 0, sizeof(*result));
   ctx->launches = 0;
+  ctx->errors_current = false;
   cudaEvent_t ev0, ev1;
   CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
   CK(cudaEventRecord(ev0, s));

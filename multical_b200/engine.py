@@ -110,6 +110,100 @@ class Engine:
     self.kint = 5 + nat.DIST_SIZES[model]
     self.N = n.value
 
+  # ---- resident point table (include/mcba.h "resident point table") ------------------------------
+  def _table_ready(self, d, model, n):
+    d.N = n
+    self.desc, self.model, self.kint, self.N = d, model, 5 + nat.DIST_SIZES[model], n
+
+  def table_upload(self, model, optimize_bits, valid, points, board_points):
+    """Keep the whole [C,F,B,P] table on the device: `valid` mask + observations.  Inliers start equal to `valid`,
+    which is also the packed selection; returns the number of valid corners."""
+    valid = np.ascontiguousarray(valid)
+    Cn, F, B, P = valid.shape
+    v8 = valid.view(np.uint8) if valid.dtype == np.bool_ else np.ascontiguousarray(valid, dtype=np.uint8)
+    pts = nat.f64(points)
+    assert pts.shape == (Cn, F, B, P, 2), f"points {pts.shape} do not match mask {valid.shape}"
+    bp = nat.f64(board_points).reshape(B, P, 3)
+    d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], int(optimize_bits), 0)
+    n = C.c_int64()
+    self._ck(self.lib.mcba_table_upload(self.h, C.byref(d), v8.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts),
+                                        nat.dptr(bp), C.byref(n)))
+    self._table_ready(d, model, n.value)
+    return n.value
+
+  def table_from_detections(self, model, optimize_bits, dims, det_start, det_ids, det_xy, board_points):
+    """Build the table on the device from detection lists: list w = (c*F+f)*B+b holds point ids
+    det_ids[det_start[w]:det_start[w+1]] and their pixel corners det_xy (what tables.make_point_table consumes)."""
+    Cn, F, B, P = (int(v) for v in dims)
+    det_start = np.ascontiguousarray(det_start, dtype=np.int64)
+    assert det_start.shape == (Cn * F * B + 1,), f"expected {Cn * F * B + 1} list offsets, got {det_start.shape}"
+    det_ids = np.ascontiguousarray(det_ids, dtype=np.int32).reshape(-1)
+    det_xy = nat.f64(det_xy).reshape(-1, 2)
+    assert det_ids.size == det_xy.shape[0] == int(det_start[-1]), "detection arrays do not match the offsets"
+    bp = nat.f64(board_points).reshape(B, P, 3)
+    d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], int(optimize_bits), 0)
+    n = C.c_int64()
+    self._ck(self.lib.mcba_table_from_detections(self.h, C.byref(d), det_start.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 nat.iptr(det_ids), nat.dptr(det_xy), nat.dptr(bp), C.byref(n)))
+    self._table_ready(d, model, n.value)
+    return n.value
+
+  def _dense_shape(self):
+    d = self.desc
+    return (d.C, d.F, d.B, d.P)
+
+  def table_download(self, points=True):
+    valid = np.zeros(self._dense_shape(), dtype=np.uint8)
+    pts = np.zeros((*self._dense_shape(), 2)) if points else None
+    self._ck(self.lib.mcba_table_download(self.h, valid.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts)))
+    return valid.astype(bool), pts
+
+  def table_set_inliers(self, mask=None):
+    if mask is None:
+      self._ck(self.lib.mcba_table_set_inliers(self.h, None)); return
+    mask = np.ascontiguousarray(mask)
+    assert mask.shape == self._dense_shape(), f"mask {mask.shape} does not match the table {self._dense_shape()}"
+    m8 = mask.view(np.uint8) if mask.dtype == np.bool_ else np.ascontiguousarray(mask, dtype=np.uint8)
+    self._ck(self.lib.mcba_table_set_inliers(self.h, m8.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+  def table_get_inliers(self):
+    mask = np.zeros(self._dense_shape(), dtype=np.uint8)
+    self._ck(self.lib.mcba_table_get_inliers(self.h, mask.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return mask.astype(bool)
+
+  def table_select(self, which):
+    """which: 'valid' or 'inliers' -- the corner set the solver and the residual entry points then work on."""
+    n = C.c_int64()
+    self._ck(self.lib.mcba_table_select(self.h, {"valid": nat.TABLE_VALID, "inliers": nat.TABLE_INLIERS}[which], C.byref(n)))
+    self.N = self.desc.N = n.value
+    return n.value
+
+  def table_errors(self):
+    """Per-corner pixel error over `valid` at the current parameters; stays on the device, sorted.  Returns the counts and
+    sums of squares of the valid and the inlier set (tables.py:244-249, calibration.py:303-310)."""
+    st = nat.TableStats()
+    self._ck(self.lib.mcba_table_errors(self.h, C.byref(st)))
+    self.N = self.desc.N = st.n_valid
+    return SolveInfo(n_valid=st.n_valid, n_inliers=st.n_inliers, sumsq_valid=st.sumsq_valid, sumsq_inliers=st.sumsq_inliers)
+
+  def table_error_ranks(self, which, ranks):
+    ranks = np.ascontiguousarray(ranks, dtype=np.int64).reshape(-1)
+    out = np.zeros(max(ranks.size, 1))
+    self._ck(self.lib.mcba_table_error_ranks(self.h, {"valid": nat.TABLE_VALID, "inliers": nat.TABLE_INLIERS}[which],
+                                             ranks.ctypes.data_as(C.POINTER(C.c_int64)), ranks.size, nat.dptr(out)))
+    return out[:ranks.size]
+
+  def table_quantile(self, which, n, q):
+    """np.quantile(errors of the chosen set, q), computed from order statistics fetched from the device."""
+    from .outliers import quantile_from_sorted
+    return quantile_from_sorted(lambda r: self.table_error_ranks(which, r), n, q)
+
+  def table_reject(self, threshold):
+    """inliers = valid & (error < threshold) with the errors of the last table_errors(); returns (n_valid, n_keep)."""
+    nv, nk = C.c_int64(), C.c_int64()
+    self._ck(self.lib.mcba_table_reject(self.h, float(threshold), C.byref(nv), C.byref(nk)))
+    return nv.value, nk.value
+
   def set_params(self, cam_rt, board_rt, frame_rt, intrinsics):
     d = self.desc
     cam_rt, board_rt, intrinsics = nat.f64(cam_rt), nat.f64(board_rt), nat.f64(intrinsics)

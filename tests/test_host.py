@@ -111,3 +111,64 @@ def test_log_table_format():
   assert lines[0].split() == ["Iteration", "Total", "nfev", "Cost", "Cost", "reduction", "Step", "norm", "Optimality"]
   assert lines[1].split() == ["0", "1", "2.8654e+06", "9.18e+07"]
   assert lines[2].split() == ["1", "2", "7.8408e+02", "2.86e+06", "1.19e+01", "3.22e+05"]
+
+
+def _run_outlier_loop(monkeypatch, scene, host, **kwargs):
+  """adjust_outliers over the numpy stand-in engine (tests/fake_engine.py); returns (result, log lines, engine calls)."""
+  import logging
+  from fake_engine import FakeEngine
+  from multical_b200 import calibration
+  eng = FakeEngine()
+  monkeypatch.setattr(calibration, "get_engine", lambda device=None: eng)
+  if host: monkeypatch.setenv("MCBA_HOST_OUTLIERS", "1")
+  else: monkeypatch.delenv("MCBA_HOST_OUTLIERS", raising=False)
+  lines = []
+  handler = logging.Handler(); handler.emit = lambda rec: lines.append(rec.getMessage())
+  logger = logging.getLogger("calibration"); old = logger.level
+  logger.addHandler(handler); logger.setLevel(logging.INFO)
+  try:
+    out = from_scene(scene).enable(cameras=True).adjust_outliers(**kwargs)
+  finally:
+    logger.removeHandler(handler); logger.setLevel(old)
+  return out, lines, eng.calls
+
+
+@pytest.mark.parametrize("with_scale", [False, True])
+def test_resident_outlier_loop_is_the_host_loop(monkeypatch, with_scale):
+  """The device-resident loop must make the decisions of the host loop (calibration.py:250-266): same thresholds, same
+  masks, same log lines -- checked over a numpy engine so that only the control flow is under test here."""
+  scene = synthetic.make_scene(C=2, F=5, vis=0.6, seed=43, outlier_fraction=0.03)
+  kw = dict(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=5.0), tolerance=1e-6, max_iterations=30)
+  if with_scale: kw.update(select_scale=select_threshold(quantile=0.5, factor=4.0), loss="soft_l1")
+  host, host_log, host_calls = _run_outlier_loop(monkeypatch, scene, host=True, **kw)
+  res, res_log, res_calls = _run_outlier_loop(monkeypatch, scene, host=False, **kw)
+  assert res_calls.count("table_upload") == 1 and "upload_dense" not in res_calls       # the table crosses once
+  assert host_calls.count("upload_dense") >= 5
+  assert [c for c in res_calls if c.startswith("solve")] == [c for c in host_calls if c.startswith("solve")]
+  assert res_log == host_log
+  assert any(l.startswith("Rejecting") for l in res_log) and sum(l.startswith("Adjust_outliers") for l in res_log) == 3
+  assert np.array_equal(res.inlier_mask, host.inlier_mask) and res.inlier_mask.sum() < res.valid.sum()
+  assert np.allclose(res.camera_poses.poses, host.camera_poses.poses, atol=1e-12)
+  assert np.allclose(res.cameras.param_vec, host.cameras.param_vec, atol=1e-12)
+
+
+def test_resident_loop_falls_back_for_opaque_selectors(monkeypatch):
+  """A plain callable cannot be evaluated on the device: the loop must then take the host path, not guess."""
+  scene = synthetic.make_scene(C=2, F=4, vis=0.6, seed=44, outlier_fraction=0.03)
+  rule = lambda errors: np.quantile(errors, 0.75) * 5.0
+  _, _, calls = _run_outlier_loop(monkeypatch, scene, host=False, num_adjustments=1, select_outliers=rule, max_iterations=10)
+  assert "table_upload" not in calls and "upload_dense" in calls
+
+
+def test_quantile_from_order_statistics_is_numpy_quantile():
+  from multical_b200.outliers import quantile_from_sorted
+  rng = np.random.default_rng(5)
+  for trial in range(300):
+    n = int(rng.integers(1, 40)) if trial % 2 else int(rng.integers(1, 50000))
+    a = np.abs(rng.standard_normal(n)) * rng.uniform(0.1, 10)
+    srt = np.sort(a)
+    q = np.append(rng.uniform(0, 1, 4), rng.choice([0.0, 0.25, 0.5, 0.75, 0.95, 1.0]))
+    assert np.array_equal(quantile_from_sorted(lambda r: srt[r], n, q), np.quantile(a, q))
+    assert quantile_from_sorted(lambda r: srt[r], n, 0.75) == np.quantile(a, 0.75)
+  thr = select_threshold(0.75, 5.0)
+  assert thr(srt) == np.quantile(srt, 0.75) * 5.0 and (thr.quantile, thr.factor) == (0.75, 5.0)
