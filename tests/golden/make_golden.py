@@ -37,9 +37,40 @@ CASES = {
 }
 
 
+def outlier_case(ref, name="outliers_3x6"):
+  """The steps either side of bundle_adjust, from the running reference, at a state where rejection means something (true
+  parameters, 0.3 px noise, 2 % gross outliers):
+    thr_q75x5       select_threshold(0.75, 5.0)(calib.reprojection_error)              (calibration.py:37-40)
+    inliers_thr     calib.reject_outliers(thr_q75x5).inliers                           (calibration.py:240-252)
+    inliers_q95     calib.reject_outliers_quantile(0.95).inliers                       (calibration.py:234-238)
+    adj_inliers, adj_rms   calib.adjust_outliers(2, select_outliers=select_threshold(0.75, 5.0)) -> inlier mask and the
+                    RMS error of its inliers                                           (calibration.py:254-268)"""
+  scene = synthetic.make_scene(C=3, F=6, vis=0.5, seed=19, model="standard", outlier_fraction=0.02)
+  calib = loader.build_calibration(ref, scene, guess=False).enable(cameras=True)
+  err = calib.reprojection_error
+  thr = ref.select_threshold(quantile=0.75, factor=5.0)(err)
+  adjusted = calib.adjust_outliers(num_adjustments=2, select_outliers=ref.select_threshold(quantile=0.75, factor=5.0))
+  gt = scene["gt"]
+  data = dict(
+    model=scene["model"], points=scene["points"], valid=scene["valid"],
+    cam_valid=scene["cam_valid"], frame_valid=scene["frame_valid"], board_valid=scene["board_valid"],
+    board_points=np.stack(scene["board_points"]), K=gt["K"], dist=gt["dist"],
+    cam_poses=gt["cam_poses"], frame_poses=gt["frame_poses"], board_poses=gt["board_poses"],
+    image_size=np.array(scene["image_size"]), cameras_enabled=True,
+    x0=calib.param_vec, err_valid=err, thr_q75x5=float(thr),
+    inliers_thr=calib.reject_outliers(thr).inliers, inliers_q95=calib.reject_outliers_quantile(0.95).inliers,
+    adj_inliers=adjusted.inliers, adj_rms=float(np.sqrt(np.mean(adjusted.reprojection_inliers ** 2))))
+  path = os.path.join(HERE, name + ".npz")
+  np.savez_compressed(path, **data)
+  print(name, "valid", int(calib.valid.sum()), "thr", thr, "kept", int(data["inliers_thr"].sum()), "q95 kept",
+        int(data["inliers_q95"].sum()), "adjusted kept", int(data["adj_inliers"].sum()), "rms", data["adj_rms"],
+        os.path.getsize(path) // 1024, "KB")
+
+
 def main():
   ref = loader.load()
   only = sys.argv[1:]          # optional: regenerate just the named cases (existing fixtures stay byte-identical)
+  if not only or "outliers_3x6" in only: outlier_case(ref)
   for name, kw in CASES.items():
     if only and name not in only: continue
     scene = synthetic.make_scene(**kw)

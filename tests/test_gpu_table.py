@@ -7,6 +7,7 @@ so costs agree to 1e-6 relative and per-corner errors to 1e-2 px (poses themselv
 import numpy as np
 import pytest
 
+from conftest import load_golden
 from multical_b200 import _native, synthetic
 from multical_b200.calibration import from_scene, get_engine, select_threshold
 from oracle.ba_oracle import Problem
@@ -148,3 +149,30 @@ def test_table_state_machine_refuses_stale_errors():
   eng.table_errors()
   assert eng.table_reject(0.0) == (n, 0)
   assert eng.table_select("inliers") == 0 and eng.residuals().size == 0
+
+
+def test_outlier_steps_match_reference_golden():
+  """The steps either side of bundle_adjust against what the running reference produced at the same state
+  (tests/golden/outliers_3x6.npz, generated by tests/golden/make_golden.py outlier_case)."""
+  scene, z = load_golden("outliers_3x6")
+  calib = from_scene(scene).enable(cameras=True)
+  thr_ref = float(z["thr_q75x5"])
+  # the reference-named host API (errors from k_views<MODE_ERROR>)
+  assert np.abs(calib.reprojection_error - z["err_valid"]).max() < 1e-9
+  assert abs(select_threshold(quantile=0.75, factor=5.0)(calib.reprojection_error) - thr_ref) < 1e-9
+  assert np.array_equal(calib.reject_outliers(thr_ref).inliers, z["inliers_thr"])
+  assert np.array_equal(calib.reject_outliers_quantile(0.95).inliers, z["inliers_q95"])
+  # the same decisions on the resident table
+  eng, n = resident_engine(calib)
+  st = eng.table_errors()
+  assert st.n_valid == z["err_valid"].size
+  assert abs(eng.table_quantile("valid", n, 0.75) * 5.0 - thr_ref) < 1e-9
+  assert eng.table_reject(thr_ref) == (n, int(z["inliers_thr"].sum()))
+  assert np.array_equal(eng.table_get_inliers(), z["inliers_thr"])
+  eng.table_errors()
+  assert eng.table_reject(eng.table_quantile("valid", n, 0.95)) == (n, int(z["inliers_q95"].sum()))
+  assert np.array_equal(eng.table_get_inliers(), z["inliers_q95"])
+  # and the whole loop: same inlier set as the reference's adjust_outliers, same inlier RMS
+  out = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=5.0))
+  assert np.array_equal(out.inlier_mask, z["adj_inliers"])
+  assert abs(np.sqrt(np.mean(out.reprojection_inliers ** 2)) - float(z["adj_rms"])) < 2e-3

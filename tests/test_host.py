@@ -172,3 +172,24 @@ def test_quantile_from_order_statistics_is_numpy_quantile():
     assert quantile_from_sorted(lambda r: srt[r], n, 0.75) == np.quantile(a, 0.75)
   thr = select_threshold(0.75, 5.0)
   assert thr(srt) == np.quantile(srt, 0.75) * 5.0 and (thr.quantile, thr.factor) == (0.75, 5.0)
+
+
+def test_outlier_steps_follow_reference_golden_over_numpy_engine(monkeypatch):
+  """Host plumbing of reject_outliers / reject_outliers_quantile / adjust_outliers (mask order, thresholds, resident loop)
+  against what the running reference produced (tests/golden/outliers_3x6.npz); errors come from the numpy engine."""
+  from fake_engine import FakeEngine
+  from multical_b200 import calibration
+  scene, z = load_golden("outliers_3x6")
+  eng = FakeEngine()
+  monkeypatch.setattr(calibration, "get_engine", lambda device=None: eng)
+  monkeypatch.delenv("MCBA_HOST_OUTLIERS", raising=False)
+  calib = from_scene(scene).enable(cameras=True)
+  assert np.abs(calib.reprojection_error - z["err_valid"]).max() < 1e-9
+  thr = select_threshold(quantile=0.75, factor=5.0)(calib.reprojection_error)
+  assert abs(thr - float(z["thr_q75x5"])) < 1e-9
+  assert np.array_equal(calib.reject_outliers(float(z["thr_q75x5"])).inliers, z["inliers_thr"])
+  assert np.array_equal(calib.reject_outliers_quantile(0.95).inliers, z["inliers_q95"])
+  out = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=5.0))
+  assert "table_upload" in eng.calls
+  assert np.array_equal(out.inlier_mask, z["adj_inliers"])
+  assert abs(np.sqrt(np.mean(out.reprojection_inliers ** 2)) - float(z["adj_rms"])) < 2e-3

@@ -28,6 +28,21 @@ def test_oracle_matches_golden_vectors(name):
   assert np.abs(err[mask] - z["err_valid"]).max() < 1e-9
 
 
+def test_oracle_outlier_steps_match_reference_golden():
+  """reprojection_error / select_threshold / reject_outliers / reject_outliers_quantile of the running reference
+  (tests/golden/make_golden.py outlier_case; calibration.py:37-40, 234-252)."""
+  scene, z = load_golden("outliers_3x6")
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  assert np.array_equal(prob.param_vec, z["x0"])
+  err, mask = prob.reprojection_error()
+  assert np.abs(err[mask] - z["err_valid"]).max() < 1e-9
+  thr = np.quantile(err[mask], 0.75) * 5.0
+  assert abs(thr - float(z["thr_q75x5"])) < 1e-9
+  assert np.array_equal((err < float(z["thr_q75x5"])) & mask, z["inliers_thr"])
+  assert np.array_equal((err < np.quantile(err[mask], 0.95)) & mask, z["inliers_q95"])
+  assert z["inliers_thr"].sum() < mask.sum() and np.array_equal(z["adj_inliers"] & mask, z["adj_inliers"])
+
+
 @pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6"])
 def test_oracle_bundle_adjust_close_to_reference_run(name):
   """The reference's TRF+LSMR trajectory is chaotic at the 1e-5 level in final cost, so the
