@@ -108,7 +108,25 @@ class Problem:
 
   def __init__(self, model, K, dist, cam_poses, frame_poses, board_poses, board_points,
                points, valid, cam_valid=None, frame_valid=None, board_valid=None,
-               inlier_mask=None, optimize=None, fix_aspect=False, has_skew=False):
+               inlier_mask=None, optimize=None, fix_aspect=False, has_skew=False,
+               motion="static", frame_poses_end=None, image_size=None,
+               base_wrt_gripper=None, world_wrt_base=None, gripper_wrt_camera=None):
+    """motion: "static"  -- one rig pose per frame (motion/static_frames.py:29-42; every BASELINE configuration);
+               "rolling" -- RollingFrames: a start pose (frame_poses) and an end pose (frame_poses_end) per frame, blended per
+                            corner by its observed image row (motion/rolling_frames.py:15-41,66-150); needs image_size (W, H);
+               "hand_eye" -- HandEye: frame pose f = gripper_wrt_camera @ base_wrt_gripper[f] @ world_wrt_base with the two
+                            outer transforms as the 12 motion parameters (motion/hand_eye.py:14-90); frame_poses is ignored."""
+    assert motion in ("static", "rolling", "hand_eye")
+    self.motion = motion
+    self.image_size = None if image_size is None else tuple(int(v) for v in image_size)
+    self.frame_poses_end = None if frame_poses_end is None else np.array(frame_poses_end, np.float64)
+    self.base_wrt_gripper = None if base_wrt_gripper is None else np.array(base_wrt_gripper, np.float64)
+    self.world_wrt_base = None if world_wrt_base is None else np.array(world_wrt_base, np.float64)
+    self.gripper_wrt_camera = None if gripper_wrt_camera is None else np.array(gripper_wrt_camera, np.float64)
+    if motion == "hand_eye":        # motion/hand_eye.py:43-46
+      frame_poses = self.gripper_wrt_camera[None] @ self.base_wrt_gripper @ self.world_wrt_base[None]
+    if motion == "rolling":
+      assert self.image_size is not None and self.frame_poses_end is not None
     self.model = model
     self.K = np.array(K, np.float64); self.dist = np.array(dist, np.float64)
     self.cam_poses = np.array(cam_poses, np.float64)
@@ -138,7 +156,9 @@ class Problem:
              board_points=self.board_points, points=self.points, valid=self.point_valid,
              cam_valid=self.cam_valid, frame_valid=self.frame_valid, board_valid=self.board_valid,
              inlier_mask=self.inlier_mask, optimize=self.optimize, fix_aspect=self.fix_aspect,
-             has_skew=self.has_skew)
+             has_skew=self.has_skew, motion=self.motion, frame_poses_end=self.frame_poses_end,
+             image_size=self.image_size, base_wrt_gripper=self.base_wrt_gripper,
+             world_wrt_base=self.world_wrt_base, gripper_wrt_camera=self.gripper_wrt_camera)
     d.update(k)
     return Problem(**d)
 
@@ -173,9 +193,16 @@ class Problem:
     """Ordered (name, flat vector) of every parameter block; order = calibration.py:146-153."""
     return [("camera_poses", matrix_to_rtvec(self.cam_poses).ravel()),
             ("board_poses", matrix_to_rtvec(self.board_poses).ravel()),
-            ("motion", matrix_to_rtvec(self.frame_poses).ravel()),
+            ("motion", self.motion_params()),
             ("cameras", self.camera_params().ravel()),
             ("boards", np.concatenate([p.ravel() for p in self.board_points]))]
+
+  def motion_params(self):
+    if self.motion == "rolling":        # rolling_frames.py:135-140: [start rtvecs | end rtvecs]
+      return np.concatenate([matrix_to_rtvec(self.frame_poses).ravel(), matrix_to_rtvec(self.frame_poses_end).ravel()])
+    if self.motion == "hand_eye":       # hand_eye.py:76-81: struct(world_wrt_base, gripper_wrt_camera)
+      return np.concatenate([matrix_to_rtvec(self.world_wrt_base).ravel(), matrix_to_rtvec(self.gripper_wrt_camera).ravel()])
+    return matrix_to_rtvec(self.frame_poses).ravel()   # pose_set.py:51-53
 
   @property
   def param_vec(self):
@@ -191,7 +218,12 @@ class Problem:
       p = x[i:i + v.size]; i += v.size
       if k == "camera_poses": upd["cam_poses"] = rtvec_to_matrix(p)            # pose_set.py:55-57
       elif k == "board_poses": upd["board_poses"] = rtvec_to_matrix(p)
-      elif k == "motion": upd["frame_poses"] = rtvec_to_matrix(p)
+      elif k == "motion":
+        if self.motion == "rolling":      # rolling_frames.py:142-144
+          upd["frame_poses"] = rtvec_to_matrix(p[:p.size // 2]); upd["frame_poses_end"] = rtvec_to_matrix(p[p.size // 2:])
+        elif self.motion == "hand_eye":   # hand_eye.py:83-87
+          upd["world_wrt_base"] = rtvec_to_matrix(p[:POSE])[0]; upd["gripper_wrt_camera"] = rtvec_to_matrix(p[POSE:])[0]
+        else: upd["frame_poses"] = rtvec_to_matrix(p)
       elif k == "cameras":                                                       # camera.py:157-171
         cp = p.reshape(self.C, -1)
         K = np.tile(np.eye(3), (self.C, 1, 1))
@@ -212,6 +244,13 @@ class Problem:
     Xw = np.einsum("bij,bpj->bpi", Tb[:, :3, :3], X) + Tb[:, None, :3, 3]           # world_points
     Tcf = self.cam_poses[:, None] @ self.frame_poses[None, :]                        # expand_views
     Xc = np.einsum("cfij,bpj->cfbpi", Tcf[..., :3, :3], Xw) + Tcf[:, :, None, None, :3, 3]
+    if self.motion == "rolling":
+      # rolling_frames.py:15-41,115-123 with estimates = the measured point table (calibration.py:124-130): the corner is
+      # transformed by the start and by the end pose and the two camera-frame points are blended by its observed row / height
+      Tce = self.cam_poses[:, None] @ self.frame_poses_end[None, :]
+      Xe = np.einsum("cfij,bpj->cfbpi", Tce[..., :3, :3], Xw) + Tce[:, :, None, None, :3, 3]
+      t = (self.points[..., 1] / float(self.image_size[1]))[..., None]
+      Xc = Xc * (1 - t) + Xe * t
     proj = project_fisheye if self.model == "fisheye" else project_pinhole
     with np.errstate(all="ignore"):
       uv = np.stack([proj(Xc[c], self.K[c], self.dist[c]) for c in range(self.C)])  # project_cameras
@@ -254,7 +293,15 @@ class Problem:
       col0 += nblocks * nper
     if self.optimize["camera_poses"] is True: add(0, idx[:, 0], POSE, self.cam_valid)
     if self.optimize["board_poses"] is True: add(2, idx[:, 2], POSE, self.board_valid)
-    if self.optimize["motion"] is True: add(1, idx[:, 1], POSE, self.frame_valid)
+    if self.optimize["motion"] is True:
+      if self.motion == "hand_eye":       # hand_eye.py:89-90: every residual depends on the 12 shared parameters
+        for j in range(2 * POSE):
+          for comp in range(2):
+            cols.append(np.full(N, col0 + j)); rws.append(rows2[:, comp])
+        col0 += 2 * POSE
+      else:
+        add(1, idx[:, 1], POSE, self.frame_valid)
+        if self.motion == "rolling": add(1, idx[:, 1], POSE, self.frame_valid)     # rolling_frames.py:146-150: start + end
     if self.optimize["cameras"] is True:
       add(0, idx[:, 0], self.camera_params().shape[1], np.ones(C, bool))
     if self.optimize["boards"] is True:

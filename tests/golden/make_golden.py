@@ -67,10 +67,71 @@ def outlier_case(ref, name="outliers_3x6"):
         os.path.getsize(path) // 1024, "KB")
 
 
+def small_motion(rng, n, rot=0.01, trans=0.01):
+  from scipy.spatial.transform import Rotation
+  T = np.tile(np.eye(4), (n, 1, 1))
+  T[:, :3, :3] = Rotation.from_rotvec(rng.normal(0, rot, (n, 3))).as_matrix()
+  T[:, :3, 3] = rng.normal(0, trans, (n, 3))
+  return T
+
+
+def motion_cases(ref, only):
+  """The two motion models the BASELINE configurations do not use, pinned the same way as the static
+  cases: parameter layout, evaluate() at two points, Jacobian sparsity, per-corner error, one bundle_adjust of the reference.
+    rolling_2x6   RollingFrames: start pose = the scene's frame pose, end pose = start moved by ~1 cm / 0.6 deg; the blend
+                  weight of a corner is its observed row / image height           (motion/rolling_frames.py:15-41,66-150)
+    handeye_2x6   HandEye: frame pose = gripper_wrt_camera @ base_wrt_gripper[f] @ world_wrt_base; arm poses constructed so that
+                  the scene's frame poses are reproduced exactly, then the two optimised transforms are perturbed; blocks enabled
+                  as HandEyeCalibration.initialise leaves them (optimization/hand_eye.py:37)   (motion/hand_eye.py:14-90)"""
+  rng = np.random.default_rng(200)
+  for name in ("rolling_2x6", "handeye_2x6"):
+    if only and name not in only: continue
+    scene = synthetic.make_scene(C=2, F=6, vis=0.5, seed=20 if name.startswith("rolling") else 21, model="standard")
+    # hand-eye fixes cameras and camera poses (optimization/hand_eye.py:37), so that case starts from their true values
+    src = scene["init"] if name.startswith("rolling") else scene["gt"]
+    extra = {}
+    if name.startswith("rolling"):
+      end = small_motion(rng, scene["F"]) @ src["frame_poses"]
+      calib = loader.build_calibration(ref, scene, motion=("rolling", end)).enable(cameras=True)
+      extra = dict(motion="rolling", frame_poses_end=end)
+      enabled = dict(cameras=True)
+    else:
+      g2c = small_motion(rng, 1, 0.3, 0.1)[0]; w2b = small_motion(rng, 1, 0.5, 0.5)[0]
+      arm = np.linalg.inv(g2c)[None] @ src["frame_poses"] @ np.linalg.inv(w2b)[None]        # base_wrt_gripper per frame
+      g2c0 = small_motion(rng, 1, 0.005, 0.005)[0] @ g2c; w2b0 = w2b @ small_motion(rng, 1, 0.005, 0.005)[0]
+      calib = loader.build_calibration(ref, scene, guess=False, motion=("hand_eye", arm, w2b0, g2c0)).enable(camera_poses=False, cameras=False)
+      extra = dict(motion="hand_eye", base_wrt_gripper=arm, world_wrt_base=w2b0, gripper_wrt_camera=g2c0)
+      enabled = dict(camera_poses=False, cameras=False)
+    x0 = calib.param_vec
+    inl = calib.inliers
+    def evaluate(x):
+      c = calib.with_param_vec(x)
+      return (c.reprojected.points - c.point_table.points)[inl].ravel()
+    x1 = x0 + np.random.default_rng(101).normal(0, 1e-3, x0.size)
+    S = calib.sparsity_matrix.tocsr(); S.sort_indices()
+    out = calib.bundle_adjust()
+    data = dict(
+      model=scene["model"], points=scene["points"], valid=scene["valid"],
+      cam_valid=scene["cam_valid"], frame_valid=scene["frame_valid"], board_valid=scene["board_valid"],
+      board_points=np.stack(scene["board_points"]), K=src["K"], dist=src["dist"],
+      cam_poses=src["cam_poses"], frame_poses=src["frame_poses"], board_poses=src["board_poses"],
+      image_size=np.array(scene["image_size"]),
+      enabled_keys=np.array(list(enabled.keys())), enabled_values=np.array(list(enabled.values())),
+      x0=x0, x1=x1, r0=evaluate(x0), r1=evaluate(x1), sp_indptr=S.indptr, sp_indices=S.indices, sp_shape=np.array(S.shape),
+      err_valid=calib.reprojection_error, ba_x=out.param_vec,
+      ba_cost=0.5 * float(np.sum(evaluate(out.param_vec) ** 2)),
+      ba_rms=float(np.sqrt(np.mean(out.reprojection_error ** 2))), **extra)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **data)
+    print(name, "N", int(inl.sum()), "n", x0.size, "cost0", 0.5 * float(np.sum(data["r0"] ** 2)), "cost", data["ba_cost"],
+          "rms", data["ba_rms"], os.path.getsize(path) // 1024, "KB")
+
+
 def main():
   ref = loader.load()
   only = sys.argv[1:]          # optional: regenerate just the named cases (existing fixtures stay byte-identical)
   if not only or "outliers_3x6" in only: outlier_case(ref)
+  if not only or any(n in only for n in ("rolling_2x6", "handeye_2x6")): motion_cases(ref, only)
   for name, kw in CASES.items():
     if only and name not in only: continue
     scene = synthetic.make_scene(**kw)

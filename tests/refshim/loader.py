@@ -67,8 +67,10 @@ def load():
     tables=tables, Table=Table, struct=struct)
 
 
-def build_calibration(ref, scene, guess=True):
-  """Reference Calibration from a multical_b200.synthetic scene dict (plain numpy)."""
+def build_calibration(ref, scene, guess=True, motion=None):
+  """Reference Calibration from a multical_b200.synthetic scene dict (plain numpy).
+  motion: None -> StaticFrames over the scene's frame poses; ("rolling", end_poses) -> RollingFrames with the scene's frame poses
+  as start poses; ("hand_eye", base_wrt_gripper, world_wrt_base, gripper_wrt_camera) -> HandEye."""
   import numpy as np
   s = scene
   src = s["init"] if guess else s["gt"]
@@ -87,5 +89,18 @@ def build_calibration(ref, scene, guess=True):
     ref.ParamList(cams, cam_names), ref.ParamList(boards, board_names), pt,
     ref.PoseSet(pose_table(src["cam_poses"], s["cam_valid"]), cam_names),
     ref.PoseSet(pose_table(src["board_poses"], s["board_valid"]), board_names),
-    ref.StaticFrames(pose_table(src["frame_poses"], s["frame_valid"]), None))
+    _motion_model(ref, motion, src, s, pose_table))
   return calib
+
+
+def _motion_model(ref, motion, src, s, pose_table):
+  if motion is None:
+    return ref.StaticFrames(pose_table(src["frame_poses"], s["frame_valid"]), None)
+  names = [str(i) for i in range(s["F"])]
+  if motion[0] == "rolling":
+    from multical.motion.rolling_frames import RollingFrames
+    return RollingFrames(src["frame_poses"].copy(), motion[1].copy(), s["frame_valid"].copy(), names)
+  if motion[0] == "hand_eye":
+    from multical.motion.hand_eye import HandEye
+    return HandEye(pose_table(motion[1], s["frame_valid"]), motion[2].copy(), motion[3].copy(), names)
+  raise ValueError(motion)
