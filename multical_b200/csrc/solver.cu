@@ -73,7 +73,8 @@ struct DevBuf {
 
 struct mcba_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // the stream every entry point works on
+  cudaStream_t own_stream = nullptr;   // created by mcba_create; `stream` differs after mcba_set_stream
   std::string err;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -430,7 +431,7 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
   int* cnt_can = ctx->scan.p; int* cnt_fm = cnt_can + (nv + 1); int* flag_can = cnt_fm + (nv + 1); int* flag_fm = flag_can + (nv + 1);
   int totals[2] = {0, 0};
   if (nv > 0) {
-    k_pack_count<<<(nv * 32 + 255) / 256, 256, 0, s>>>(d_mask, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
+    k_pack_count<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_mask, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
     k_scan_exclusive<<<4, 1024, 0, s>>>(cnt_can, nv, nv + 1); CKL();      // cnt_can | cnt_fm | flag_can | flag_fm
     CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -443,7 +444,7 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
   if (nv > 0) {
     PackOut o{ctx->obs.p, ctx->pid.p, ctx->orig.p, ctx->view_start.p, ctx->view_cam.p, ctx->view_frame.p, ctx->view_board.p,
               ctx->frame_view_start.p, ctx->cam_view_start.p, ctx->cam_view_list.p};
-    k_pack_scatter<<<(nv * 32 + 255) / 256, 256, 0, s>>>(d_mask, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL();
+    k_pack_scatter<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_mask, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL();
   } else {
     CK(cudaMemsetAsync(ctx->view_start.p, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctx->frame_view_start.p, 0, sizeof(int) * (F + 1), s));
     CK(cudaMemsetAsync(ctx->cam_view_start.p, 0, sizeof(int) * (C + 1), s));
@@ -480,7 +481,8 @@ int mcba_create(int device, mcba_ctx** out) {
   mcba_ctx* ctx = new mcba_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
+  ctx->stream = ctx->own_stream;
   { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
   cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -509,15 +511,20 @@ int mcba_create(int device, mcba_ctx** out) {
 void mcba_destroy(mcba_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
   if (ctx->peer_own) cudaFree(ctx->peer_own);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-  delete ctx;
+  cudaStream_t own = ctx->own_stream;
+  delete ctx;                            // device buffers are freed by their destructors
+  if (own) cudaStreamDestroy(own);
 }
 
 int mcba_set_stream(mcba_ctx* ctx, void* stream) {
   if (!ctx) return MCBA_ERR_ARG;
-  ctx->stream = (cudaStream_t)stream;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));          // nothing of ours may still be in flight on the stream we leave
+  ctx->stream = (cudaStream_t)stream;              // NULL is the legacy default stream (what torch reports as stream 0)
   return MCBA_OK;
 }
 
@@ -759,7 +766,7 @@ int mcba_table_from_detections(mcba_ctx* ctx, const mcba_problem_desc* desc, con
   CK(cudaStreamSynchronize(s));
   REQUIRE(!bad, MCBA_ERR_ARG, "detection offsets are not a monotone CSR over C*F*B lists");
   if (nv > 0 && total > 0) {
-    k_table_fill<<<(nv * 32 + 255) / 256, 256, 0, s>>>(d_start.p, d_ids.p, d_xy.p, nv, desc->P, ctx->valid_mask.p, ctx->dense_pts.p, d_bad.p); CKL();
+    k_table_fill<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_start.p, d_ids.p, d_xy.p, nv, desc->P, ctx->valid_mask.p, ctx->dense_pts.p, d_bad.p); CKL();
     CK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     REQUIRE(!bad, MCBA_ERR_ARG, "detection id outside [0, P)");
@@ -1101,8 +1108,12 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   memset(result, 0, sizeof(*result));
   ctx->launches = 0;
   ctx->errors_current = false;
-  cudaEvent_t ev0, ev1;
-  CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+  struct EventPair {       // destroyed on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+  cudaEvent_t ev0 = ev.a, ev1 = ev.b;
   CK(cudaEventRecord(ev0, s));
 
   SolverState h{};
@@ -1147,7 +1158,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       // only the gradient norm of the final point is still needed for the last table row
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; cudaEventDestroy(ev0); cudaEventDestroy(ev1); return MCBA_ERR_NONFINITE; }
+      if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; return MCBA_ERR_NONFINITE; }
       if (h.iteration == 0) result->initial_cost = h.cost;
       if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.nfev, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
       finished = true;
@@ -1225,7 +1236,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       if (!top_logged) {      // the row scipy prints at the top of this outer iteration
-        if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; cudaEventDestroy(ev0); cudaEventDestroy(ev1); return MCBA_ERR_NONFINITE; }
+        if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; return MCBA_ERR_NONFINITE; }
         if (h.iteration == 0) result->initial_cost = h.cost;
         if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.done ? h.nfev : h.nfev - 1, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
         top_logged = true;
@@ -1266,7 +1277,6 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   CK(cudaEventRecord(ev1, s));
   CK(cudaEventSynchronize(ev1));
   float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   result->cost = h.cost; result->optimality = h.g_norm; result->nfev = h.nfev; result->njev = h.njev;
   result->status = h.status == -99 ? 0 : h.status; result->n_log = nlog; result->device_ms = ms;
   result->kernel_launches = ctx->launches; result->chol_retries = h.chol_fail;
