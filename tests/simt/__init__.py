@@ -1,0 +1,128 @@
+"""TEST INFRASTRUCTURE ONLY -- host build of the CUDA sources for the SIMT interpreter (tests/simt/shim/simt.h).
+
+`build()` translates multical_b200/csrc/*.cu[h] textually (kernel launches -> simt::launch, `__shared__` -> per-block storage,
+the three inline-PTX statements -> their C++ meaning), compiles the result with g++ against the stand-in cuda_runtime.h and
+returns the path of tests/simt/build/libmcba_simt.so, which exports the same C-ABI as multical_b200/libmcba.so.  The product
+never loads this library (multical_b200/_native.py only knows libmcba.so); tests/test_simt_kernels.py points the ctypes binding
+at it so that the CPU suite (-m "not gpu") runs the real kernels and the real host driver at small sizes.
+"""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "multical_b200", "csrc")
+OUT = os.path.join(HERE, "build")
+LIB = os.path.join(OUT, "libmcba_simt.so")
+
+
+def _match_back(s, i, open_c, close_c):
+  """index of the `open_c` matching the `close_c` at s[i]."""
+  depth = 0
+  while i >= 0:
+    if s[i] == close_c: depth += 1
+    elif s[i] == open_c:
+      depth -= 1
+      if depth == 0: return i
+    i -= 1
+  raise ValueError("unbalanced")
+
+
+def _match_fwd(s, i, open_c, close_c):
+  depth = 0
+  while i < len(s):
+    if s[i] == open_c: depth += 1
+    elif s[i] == close_c:
+      depth -= 1
+      if depth == 0: return i
+    i += 1
+  raise ValueError("unbalanced")
+
+
+def _split_top(s):
+  parts, depth, cur = [], 0, ""
+  for ch in s:
+    if ch in "([{": depth += 1
+    elif ch in ")]}": depth -= 1
+    if ch == "," and depth == 0: parts.append(cur.strip()); cur = ""
+    else: cur += ch
+  parts.append(cur.strip())
+  return parts
+
+
+def rewrite_launches(src):
+  out, pos = "", 0
+  while True:
+    i = src.find("<<<", pos)
+    if i < 0: return out + src[pos:]
+    # kernel expression: identifier, optionally followed by a balanced <...> template argument list
+    j = i - 1
+    while src[j].isspace(): j -= 1
+    if src[j] == ">": j = _match_back(src, j, "<", ">") - 1
+    while j >= 0 and (src[j].isalnum() or src[j] in "_:"): j -= 1
+    kernel = src[j + 1:i].strip()
+    k = src.find(">>>", i)
+    cfg = _split_top(src[i + 3:k])
+    a0 = src.find("(", k)
+    assert src[k + 3:a0].strip() == "", f"unexpected text after launch configuration of {kernel}"
+    a1 = _match_fwd(src, a0, "(", ")")
+    args = src[a0 + 1:a1]
+    grid, block = cfg[0], cfg[1]
+    smem = cfg[2] if len(cfg) > 2 else "0"
+    name = kernel.replace('"', "")
+    out += src[pos:j + 1] + f'simt::launch("{name}", dim3({grid}), dim3({block}), (size_t)({smem}), [&]() {{ {kernel}({args}); }})'
+    pos = a1 + 1
+
+
+ASM = re.compile(r"asm\s+volatile\s*\((.*?)\)\s*;", re.S)
+
+
+def rewrite_asm(m):
+  body = m.group(1)
+  if "mma.sync.aligned.m8n8k4" in body: return "simt::dmma884(c0, c1, a, b);"
+  if "ld.volatile.global.u64" in body: return "v = *(volatile const unsigned long long*)p;"
+  if "st.volatile.global.u64" in body: return "*(volatile unsigned long long*)p = v;"
+  raise ValueError("inline PTX without a host meaning: " + body[:80])
+
+
+def translate(src):
+  src = rewrite_launches(src)
+  src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)simt::dyn_smem();", src)
+  src = re.sub(r"\b__shared__\b", "static", src)
+  src = ASM.sub(rewrite_asm, src)
+  src = src.replace('#include "../../include/mcba.h"', f'#include "{os.path.join(ROOT, "include", "mcba.h")}"')
+  return src
+
+
+def sources():
+  return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+
+
+def stale():
+  if not os.path.exists(LIB): return True
+  t = os.path.getmtime(LIB)
+  deps = [os.path.join(CSRC, f) for f in sources()] + [os.path.join(ROOT, "include", "mcba.h"), os.path.abspath(__file__)]
+  shim = os.path.join(HERE, "shim")
+  for d, _, fs in os.walk(shim): deps += [os.path.join(d, f) for f in fs]
+  return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False):
+  if not (force or stale()): return LIB
+  os.makedirs(OUT, exist_ok=True)
+  main = None
+  for f in sources():
+    with open(os.path.join(CSRC, f)) as fh: text = translate(fh.read())
+    dst = os.path.join(OUT, f[:-3] + ".cpp" if f.endswith(".cu") else f)
+    with open(dst, "w") as fh: fh.write(text)
+    if f.endswith(".cu"): main = dst
+  cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fno-strict-aliasing", "-w", "-Wno-unknown-pragmas",
+         "-I", os.path.join(HERE, "shim"), "-o", LIB, main, "-ldl"]
+  subprocess.run(cmd, check=True, cwd=OUT)
+  return LIB
+
+
+if __name__ == "__main__":
+  import sys
+  print(build(force="--force" in sys.argv))

@@ -1,0 +1,75 @@
+"""CPU (-m "not gpu"): the REAL CUDA kernels and the REAL host driver of multical_b200/csrc, executed by the SIMT interpreter of
+tests/simt (every CUDA thread a fiber, blocks one after the other) behind the same C-ABI, against the same oracle / golden
+assertions as the GPU suite.  The test functions are the ones of tests/test_gpu_parity.py and tests/test_gpu_table.py -- imported,
+not copied -- with the ctypes binding pointed at tests/simt/build/libmcba_simt.so for the duration of each test.
+
+What this proves without a GPU: indexing, math, shared-memory layouts, warp-collective usage (full-mask discipline, barrier
+placement -- a divergent barrier aborts the interpreter) and the host-side plumbing of every kernel launched by these tests.
+What it cannot prove: anything about concurrency (blocks and fibers run deterministically) or speed; that is the GPU suite's job.
+The library is test infrastructure: the product (multical_b200/_native.py) never loads it.
+"""
+
+import pytest
+
+import test_gpu_parity as gp
+import test_gpu_table as gt
+from multical_b200 import _native, calibration
+
+
+@pytest.fixture(scope="session")
+def simt_library():
+  import simt                     # tests/simt/__init__.py (tests/ is on sys.path: pytest rootdir/conftest import mode)
+  return simt.build()
+
+
+@pytest.fixture(autouse=True)
+def on_the_interpreter(simt_library, monkeypatch):
+  """Point the ctypes binding at the interpreter build for one test; engines are per-library, so the cache is swapped as well."""
+  monkeypatch.setattr(_native, "LIB_PATH", simt_library)
+  monkeypatch.setattr(_native, "_lib", None)
+  monkeypatch.setattr(calibration, "_engines", {})
+  monkeypatch.delenv("SIMT_SMS", raising=False)
+  yield
+  for eng in calibration._engines.values(): eng.close()
+
+
+# ---- tests/test_gpu_parity.py on the interpreter (the two large-scene property tests stay GPU-only: minutes of fiber switching)
+test_residuals_match_reference_golden_and_oracle = gp.test_residuals_match_reference_golden_and_oracle
+test_reprojection_error_over_valid = gp.test_reprojection_error_over_valid
+test_normal_equations_match_finite_differences = gp.test_normal_equations_match_finite_differences
+test_converged_solution_matches_dense_exact_oracle = gp.test_converged_solution_matches_dense_exact_oracle
+test_robust_losses_follow_scipy = gp.test_robust_losses_follow_scipy
+test_outlier_loop_matches_reference_semantics = gp.test_outlier_loop_matches_reference_semantics
+test_fixed_blocks_and_fix_aspect = gp.test_fixed_blocks_and_fix_aspect
+test_bad_inputs_raise_like_the_reference = gp.test_bad_inputs_raise_like_the_reference
+test_device_packing_equals_host_packing = gp.test_device_packing_equals_host_packing
+test_empty_and_ragged_inputs = gp.test_empty_and_ragged_inputs
+test_board_points_as_parameters = gp.test_board_points_as_parameters
+test_iteration_table_matches_the_trf_model = gp.test_iteration_table_matches_the_trf_model
+test_degenerate_block_selections = gp.test_degenerate_block_selections
+
+# ---- tests/test_gpu_table.py on the interpreter
+test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors = gt.test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors
+test_resident_adjust_outliers_equals_host_loop = gt.test_resident_adjust_outliers_equals_host_loop
+test_table_from_detections_is_make_point_table = gt.test_table_from_detections_is_make_point_table
+test_table_state_machine_refuses_stale_errors = gt.test_table_state_machine_refuses_stale_errors
+test_outlier_steps_match_reference_golden = gt.test_outlier_steps_match_reference_golden
+
+
+@pytest.mark.parametrize("sms", ["1", "148"])
+def test_one_warp_per_view_and_split_view_moment_kernels_agree(sms, monkeypatch):
+  """k_views_mma<MODEL, 1> (V >= 16 x SMs) and k_views_mma<MODEL, VIEW_WARPS> (few long views) must give the same normal
+  equations; the interpreter's reported SM count selects the variant (csrc/solver.cu launch_moments)."""
+  import numpy as np
+  monkeypatch.setenv("SIMT_SMS", sms)
+  scene, z, calib, prob = gp.make("cube3_3x6")
+  eng = calib._upload(calib.inliers)
+  JtJ, Jtr, cost = eng.linearize(z["x1"])
+  monkeypatch.setenv("MCBA_MOMENTS", "fma")           # the DFMA kernels as the independent second opinion
+  monkeypatch.setattr(calibration, "_engines", {})
+  eng2 = calib._upload(calib.inliers)
+  JtJ2, Jtr2, cost2 = eng2.linearize(z["x1"])
+  eng2.close()
+  assert np.abs(JtJ - JtJ2).max() <= 1e-11 * np.abs(JtJ).max()
+  assert np.abs(Jtr - Jtr2).max() <= 1e-11 * np.abs(Jtr).max()
+  assert abs(cost - cost2) <= 1e-13 * cost
