@@ -15,7 +15,7 @@
  * np.argwhere(calib.inliers) = (camera, frame, board, point) in row-major order of the dense
  * [C,F,B,P] table (calibration.py:206 boolean-mask order); residual vector element 2k is u, 2k+1 is v.
  * Parameter vector layout = reference order (calibration.py:146-153, parameters.py:104-106):
- *   [camera_poses 6C][board_poses 6B][motion 6F][cameras (5+nd)C][boards 3*B*P]   (enabled blocks only; the boards
+ *   [camera_poses 6C][board_poses 6B][motion 6F | 12F rolling | 12 hand-eye][cameras (5+nd)C][boards 3*B*P]   (enabled blocks only; the boards
  *   block is the padded stack of tables.stack_boards -- the host strips the padding of boards with fewer points)
  *   pose = [rx ry rz tx ty tz] (transform/rtvec.py:16-27), camera = [fx fy cx cy skew dist...]
  *   (camera.py:144-155).
@@ -44,6 +44,16 @@ enum { MCBA_LOSS_LINEAR = 0, MCBA_LOSS_SOFT_L1 = 1, MCBA_LOSS_HUBER = 2, MCBA_LO
 enum { MCBA_OPT_CAMERA_POSES = 1, MCBA_OPT_BOARD_POSES = 2, MCBA_OPT_MOTION = 4, MCBA_OPT_CAMERAS = 8,
        MCBA_OPT_BOARDS = 16 /* board points as parameters (board/charuco.py:112-117); block layout = padded [B][P][3] */,
        MCBA_OPT_FIX_ASPECT = 256 /* camera.py:147-148,159-160 */ };
+/* motion model = the `motion` argument of Calibration (calibration.py:44-46), or-ed into mcba_problem_desc.optimize:
+ *   (none)                StaticFrames: one rig pose per frame (motion/static_frames.py:29-42)
+ *   MCBA_MOTION_ROLLING   RollingFrames: a start and an end pose per frame; a corner is transformed by both and the two
+ *                         camera-frame points are blended by its observed row / image height (motion/rolling_frames.py:15-41,
+ *                         66-150).  motion block of the parameter vector = [start F x 6 | end F x 6] (135-140).
+ *   MCBA_MOTION_HAND_EYE  HandEye: frame pose f = gripper_wrt_camera @ base_wrt_gripper[f] @ world_wrt_base with the arm
+ *                         poses fixed (motion/hand_eye.py:14-90).  motion block = [world_wrt_base 6 | gripper_wrt_camera 6]
+ *                         (76-81), shared by every residual (89-90).
+ * MCBA_OPT_BOARDS is only implemented for static frames (MCBA_ERR_UNSUPPORTED otherwise). */
+enum { MCBA_MOTION_ROLLING = 1 << 16, MCBA_MOTION_HAND_EYE = 1 << 17 };
 
 typedef struct {
   int32_t C, F, B, P;       /* Calibration.size (calibration.py:64-67); F = frames held by THIS rank   */
@@ -114,6 +124,16 @@ int  mcba_get_params(mcba_ctx* ctx, double* cam_rt, double* board_rt, double* fr
  * pose_set.py:40-42): matrix <-> rtvec (transform/rtvec.py:24-32) is done on the device */
 int  mcba_set_state_matrices(mcba_ctx* ctx, const double* pose_matrices, const double* intrinsics);
 int  mcba_get_state_matrices(mcba_ctx* ctx, double* pose_matrices, double* intrinsics);
+/* motion-model state (after the upload, next to mcba_set_params / mcba_set_state_matrices):
+ * rolling: the frames of the calls above are the START poses (mcba_set_params: frame_rt is f64[F][12], start | end of a
+ *   frame adjacent); end poses f64[F][4][4] and image heights f64[C] (rolling_times, rolling_frames.py:15-19) come here.
+ * hand-eye: the frames of the calls above are ignored on input (mcba_get_state_matrices returns the derived frame poses);
+ *   base_wrt_gripper f64[F][4][4] (constants), world_wrt_base and gripper_wrt_camera f64[4][4] (the parameters). */
+int  mcba_set_rolling(mcba_ctx* ctx, const double* end_pose_matrices, const double* image_heights);
+int  mcba_get_rolling(mcba_ctx* ctx, double* end_pose_matrices);
+int  mcba_set_hand_eye(mcba_ctx* ctx, const double* base_wrt_gripper, const double* world_wrt_base,
+                       const double* gripper_wrt_camera);
+int  mcba_get_hand_eye(mcba_ctx* ctx, double* world_wrt_base, double* gripper_wrt_camera);
 int  mcba_num_params(mcba_ctx* ctx, int64_t* n);      /* length of param_vec for the enabled blocks    */
 int  mcba_get_param_vec(mcba_ctx* ctx, double* x);    /* Parameters.param_vec (parameters.py:44-46)    */
 int  mcba_set_param_vec(mcba_ctx* ctx, const double* x);   /* with_param_vec (parameters.py:48-50)     */

@@ -13,6 +13,7 @@ DIST_SIZES = {"standard": 5, "rational": 8, "thin_prism": 12, "fisheye": 4, "til
 LOSS_IDS = {"linear": 0, "soft_l1": 1, "huber": 2, "cauchy": 3, "arctan": 4}
 OPT_BITS = {"camera_poses": 1, "board_poses": 2, "motion": 4, "cameras": 8, "boards": 16}
 OPT_FIX_ASPECT = 256
+MOTION_ROLLING, MOTION_HAND_EYE = 1 << 16, 1 << 17        # include/mcba.h MCBA_MOTION_*: or-ed into ProblemDesc.optimize
 STATUS_MESSAGES = {
   -1: "Improper input parameters status returned from `leastsq`",
   0: "The maximum number of function evaluations is exceeded.",
@@ -23,6 +24,7 @@ STATUS_MESSAGES = {
 }
 EXPORTS = ["mcba_create", "mcba_destroy", "mcba_last_error", "mcba_set_stream", "mcba_version",
            "mcba_comm_unique_id", "mcba_comm_init", "mcba_peer_export", "mcba_peer_import", "mcba_upload", "mcba_upload_dense", "mcba_set_params", "mcba_get_params", "mcba_set_state_matrices", "mcba_get_state_matrices",
+           "mcba_set_rolling", "mcba_get_rolling", "mcba_set_hand_eye", "mcba_get_hand_eye",
            "mcba_num_params", "mcba_get_param_vec", "mcba_set_param_vec", "mcba_residuals",
            "mcba_linearize", "mcba_reprojection_error", "mcba_solve", "mcba_bench_launch", "mcba_bench_info",
            "mcba_table_upload", "mcba_table_from_detections", "mcba_table_download", "mcba_table_set_inliers",
@@ -86,6 +88,10 @@ def load():
   lib.mcba_get_params.argtypes = [P, D, D, D, D]
   lib.mcba_set_state_matrices.argtypes = [P, D, D]
   lib.mcba_get_state_matrices.argtypes = [P, D, D]
+  lib.mcba_set_rolling.argtypes = [P, D, D]
+  lib.mcba_get_rolling.argtypes = [P, D]
+  lib.mcba_set_hand_eye.argtypes = [P, D, D, D]
+  lib.mcba_get_hand_eye.argtypes = [P, D, D]
   lib.mcba_num_params.argtypes = [P, C.POINTER(C.c_int64)]
   lib.mcba_get_param_vec.argtypes = [P, D]
   lib.mcba_set_param_vec.argtypes = [P, D]

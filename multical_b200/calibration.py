@@ -19,6 +19,7 @@ from .board import stack_boards
 from .camera import engine_model_of
 from .engine import Engine, format_log, pack_corners
 from .log import info
+from .motion import MOTION_HAND_EYE, MOTION_ROLLING, motion_kind
 from .outliers import QuantileThreshold, select_threshold      # noqa: F401  (select_threshold: calibration.py:37-40)
 from .parameters import Parameters
 from .structs import Table, struct
@@ -118,7 +119,7 @@ class Calibration(Parameters):
     bits = sum(bit for k, bit in OPT_BITS.items() if self.optimize[k] is True)
     fix = {bool(getattr(c, "fix_aspect", False)) for c in self.cameras}
     assert len(fix) == 1, "fix_aspect must agree across cameras"
-    return bits | (OPT_FIX_ASPECT if fix.pop() else 0)
+    return bits | (OPT_FIX_ASPECT if fix.pop() else 0) | motion_kind(self.motion)
 
   def _state_arrays(self):
     # one rotation-vector conversion for all pose sets (the scipy call dominates the host time of a small solve)
@@ -161,9 +162,15 @@ class Calibration(Parameters):
 
   def _push_state(self, eng):
     # poses go over as 4x4 matrices: the matrix -> rotation-vector conversion (transform/rtvec.py:29-32) runs on the device
+    kind = motion_kind(self.motion)
+    frames = self.motion.pose_start if kind == MOTION_ROLLING else self.motion.poses
     mats = np.concatenate([np.asarray(self.camera_poses.poses, np.float64), np.asarray(self.board_poses.poses, np.float64),
-                           np.asarray(self.motion.poses, np.float64)], axis=0)
+                           np.asarray(frames, np.float64)], axis=0)
     eng.set_state_matrices(mats, np.stack([np.asarray(c.param_vec, np.float64) for c in self.cameras]))
+    if kind == MOTION_ROLLING:      # `motion.poses` above were the start poses
+      eng.set_rolling(self.motion.pose_end, [c.image_size[1] for c in self.cameras])
+    elif kind == MOTION_HAND_EYE:   # the frames above are derived poses, ignored by the engine
+      eng.set_hand_eye(self.motion.base_wrt_gripper.poses, self.motion.world_wrt_base, self.motion.gripper_wrt_camera)
 
   def _with_engine_state(self, eng):
     """New Calibration holding the engine's solved state -- what `self.with_param_vec(res.x)` returns in the reference
@@ -176,27 +183,51 @@ class Calibration(Parameters):
     changes = {}
     if self.optimize["camera_poses"] is True: changes["camera_poses"] = moved(self.camera_poses, cam_T)
     if self.optimize["board_poses"] is True: changes["board_poses"] = moved(self.board_poses, board_T)
-    if self.optimize["motion"] is True: changes["motion"] = moved(self.motion, frame_T)
+    if self.optimize["motion"] is True:
+      kind = motion_kind(self.motion)
+      if kind == MOTION_ROLLING: changes["motion"] = self.motion.copy(pose_start=frame_T, pose_end=eng.get_rolling())
+      elif kind == MOTION_HAND_EYE:
+        world_wrt_base, gripper_wrt_camera = eng.get_hand_eye()
+        changes["motion"] = self.motion.copy(world_wrt_base=world_wrt_base, gripper_wrt_camera=gripper_wrt_camera)
+      else: changes["motion"] = moved(self.motion, frame_T)
     if self.optimize["cameras"] is True: changes["cameras"] = self.cameras.with_param_vec(intr.ravel())
     return self.copy(**changes)
 
   # ---- projection / errors (calibration.py:115-141, tables.py:239-249) ---------------------------
-  def _project(self, mask):
-    """Dense [C,F,B,P,2] projections of the points selected by `mask` (zeros elsewhere)."""
+  def _project(self, mask, estimates=None):
+    """Dense [C,F,B,P,2] projections of the points selected by `mask` (zeros elsewhere).  `estimates` [C,F,B,P,2]: image
+    points whose rows give the rolling-shutter blend weights (rolling_frames.py:115-123); irrelevant for other motion models."""
     out = np.zeros((*mask.shape, 2))
     if mask.any():
-      eng = self._upload(mask, points=np.zeros((*mask.shape, 2)))
-      out[mask] = eng.residuals().reshape(-1, 2)        # projected - 0
+      obs = np.zeros((*mask.shape, 2)) if estimates is None else np.ascontiguousarray(estimates, dtype=np.float64)
+      eng = self._upload(mask, points=obs)
+      out[mask] = eng.residuals().reshape(-1, 2) + obs[mask]      # residual = projected - "observed"
     return out
 
   @cached_property
+  def _projectable(self):
+    return self.pose_valid[..., None] & self.board_points.valid[None, None]
+
+  @cached_property
   def projected(self):
-    ok = self.pose_valid[..., None] & self.board_points.valid[None, None]
-    return _mk_table(self.point_table, points=self._project(ok), valid=ok)
+    """calibration.py:115-121: projection without measurements.  Rolling frames start from mid-exposure (row = height / 2) and
+    re-project `max_iterations` times with the rows of the previous projection (rolling_frames.py:115-133)."""
+    ok = self._projectable
+    if motion_kind(self.motion) != MOTION_ROLLING:
+      return _mk_table(self.point_table, points=self._project(ok), valid=ok)
+    heights = np.array([c.image_size[1] for c in self.cameras], dtype=np.float64)
+    est = np.zeros((*ok.shape, 2)); est[..., 1] = 0.5 * heights[:, None, None, None]
+    points = self._project(ok, est)
+    for _ in range(getattr(self.motion, "max_iterations", 4)):
+      points = self._project(ok, points)
+    return _mk_table(self.point_table, points=points, valid=ok)
 
   @cached_property
   def reprojected(self):
-    return self.projected          # static frames: the measured points do not change the projection
+    """calibration.py:124-130: projection given the measured points; they only matter to rolling frames (their rows)."""
+    if motion_kind(self.motion) != MOTION_ROLLING: return self.projected
+    ok = self._projectable
+    return _mk_table(self.point_table, points=self._project(ok, np.asarray(self.point_table.points)), valid=ok)
 
   @cached_property
   def _valid_errors(self):
@@ -261,7 +292,13 @@ class Calibration(Parameters):
       col0 += enabled.size * nper
     if self.optimize["camera_poses"] is True: add(idx[:, 0], 6, np.asarray(self.camera_poses.valid))
     if self.optimize["board_poses"] is True: add(idx[:, 2], 6, np.asarray(self.board_poses.valid))
-    if self.optimize["motion"] is True: add(idx[:, 1], 6, np.asarray(self.motion.valid))
+    if self.optimize["motion"] is True:
+      kind = motion_kind(self.motion)
+      if kind == MOTION_HAND_EYE:       # hand_eye.py:89-90: all 12 parameters touch every row
+        add(np.zeros(N, dtype=np.int64), 12, np.ones(1, bool))
+      else:
+        add(idx[:, 1], 6, np.asarray(self.motion.valid))
+        if kind == MOTION_ROLLING: add(idx[:, 1], 6, np.asarray(self.motion.valid))   # rolling_frames.py:146-150: start + end
     if self.optimize["cameras"] is True:
       add(idx[:, 0], self.cameras.param_vec.size // self.size.cameras, np.ones(self.size.cameras, bool))
     if self.optimize["boards"] is True:

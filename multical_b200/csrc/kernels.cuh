@@ -47,11 +47,24 @@ struct DeviceProblem {
   PoseT* cam_T;
   PoseT* frame_T;
   PoseT* board_T;
-  // solver variable layout: x = [shared (n_s) | frames (6F if motion free)]
+  // solver variable layout: x = [shared (n_s) | frames (fb*F if motion free)]
   int n, n_s, n_f;
   int off_cp, off_bp, off_in, off_pt;   // offsets inside shared, -1 when the block is fixed (off_pt: 3 per padded board point)
-  int motion_on, fix_aspect;
+  int motion_on, fix_aspect;            // motion_on: per-frame blocks are free (static / rolling frames)
+  // motion model (the `motion` argument of Calibration, calibration.py:44-46)
+  int motion;        // MOTION_STATIC: one rig pose per frame (motion/static_frames.py:29-42)
+                     // MOTION_ROLLING: start + end pose per frame, blended per corner by its observed row (motion/rolling_frames.py:15-41,66-150)
+                     // MOTION_HAND_EYE: frame pose = gripper_wrt_camera base_wrt_gripper[f] world_wrt_base (motion/hand_eye.py:14-90)
+  int npf;           // pose-table entries per frame: frame_T[f*npf + j], frame_rt + 6*(f*npf + j)   (2 for rolling, else 1)
+  int fb;            // parameters of one eliminated frame block: 6 (static), 12 (rolling: start | end), 0 (hand-eye: none)
+  int koff;          // local Jacobian layout of a residual row: [camera-frame twists (koff = 6 or 12) | fx fy cx cy dist]; D = koff + 4 + nd
+  const double* img_h;   // [C] image heights (rolling_times, rolling_frames.py:15-19)
+  double* he_rt;     // [12] world_wrt_base | gripper_wrt_camera as rtvecs (HandEye.params, hand_eye.py:76-81)
+  PoseT* he_T;       // [2]
+  const PoseT* arm_T;    // [F] base_wrt_gripper (R, t only)
+  int off_he;        // offset of the 12 hand-eye parameters inside shared, -1 when fixed or not a hand-eye problem
 };
+enum { MOTION_STATIC = 0, MOTION_ROLLING = 1, MOTION_HAND_EYE = 2 };
 
 __host__ __device__ constexpr int tri_index(int D, int i, int j) { return i * D - (i * (i - 1)) / 2 + (j - i); }
 __device__ __forceinline__ double msym(const double* M, int D, int i, int j) {
@@ -59,61 +72,111 @@ __device__ __forceinline__ double msym(const double* M, int D, int i, int j) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// (R, t) of A B
+__host__ __device__ __forceinline__ void se3_mul(const double* Ra, const double* ta, const double* Rb, const double* tb, double* R, double* t) {
+  mat3_mul(Ra, Rb, R);
+  mat3_vec(Ra, tb, t);
+  t[0] += ta[0]; t[1] += ta[1]; t[2] += ta[2];
+}
+__device__ __forceinline__ void pose_from_rt(const double* rt, PoseT& t) {
+  rodrigues(rt, t.R, t.JL);
+  t.t[0] = rt[3]; t.t[1] = rt[4]; t.t[2] = rt[5];
+  t.pad[0] = t.pad[1] = t.pad[2] = 0;
+}
+// hand-eye frame pose T_f = G A_f W (motion/hand_eye.py:43-46) from the rtvecs he = [W | G]; JL is not used for derived poses
+__device__ __forceinline__ void hand_eye_frame(const double* he, const PoseT& arm, PoseT& out) {
+  PoseT W, G;
+  pose_from_rt(he, W);
+  pose_from_rt(he + 6, G);
+  double Rga[9], tga[3];
+  se3_mul(G.R, G.t, arm.R, arm.t, Rga, tga);
+  se3_mul(Rga, tga, W.R, W.t, out.R, out.t);
+#pragma unroll
+  for (int i = 0; i < 9; i++) out.JL[i] = 0.0;
+  out.pad[0] = out.pad[1] = out.pad[2] = 0;
+}
+
 // k_prepare: one thread per pose.  rtvec -> (R, t, JL).   pose_set.py:55-57 / transform/rtvec.py:24-27
 __global__ void k_prepare(DeviceProblem p, const double* cam_rt, const double* board_rt, const double* frame_rt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nfp = p.F * p.npf;
   const double* src; PoseT* dst;
   if (i < p.C) { src = cam_rt + 6 * i; dst = p.cam_T + i; }
   else if (i < p.C + p.B) { src = board_rt + 6 * (i - p.C); dst = p.board_T + (i - p.C); }
-  else if (i < p.C + p.B + p.F) { src = frame_rt + 6 * (i - p.C - p.B); dst = p.frame_T + (i - p.C - p.B); }
+  else if (i < p.C + p.B + nfp) {
+    const int q = i - p.C - p.B;
+    if (p.motion == MOTION_HAND_EYE) { PoseT t; hand_eye_frame(p.he_rt, p.arm_T[q], t); p.frame_T[q] = t; return; }
+    src = frame_rt + 6 * q; dst = p.frame_T + q;
+  }
+  else if (p.motion == MOTION_HAND_EYE && i < p.C + p.B + nfp + 2) { const int j = i - p.C - p.B - nfp; src = p.he_rt + 6 * j; dst = p.he_T + j; }
   else return;
   PoseT t;
-  rodrigues(src, t.R, t.JL);
-  t.t[0] = src[3]; t.t[1] = src[4]; t.t[2] = src[5];
-  t.pad[0] = t.pad[1] = t.pad[2] = 0;
+  pose_from_rt(src, t);
   *dst = t;
 }
 
 // pose matrices <-> rtvec parameter state, one thread per pose (the host never converts rotations itself)
-__global__ void k_matrices_to_state(int C, int B, int F, const double* mats /*[C+B+F][16]*/, double* cam_rt, double* board_rt, double* frame_rt) {
+// frame f goes to frame_rt + fstride*f (fstride = 6; 12 for rolling frames, whose start | end poses are adjacent; 0 = frames are
+// derived, hand-eye, and not stored)
+__global__ void k_matrices_to_state(int C, int B, int F, const double* mats /*[C+B+F][16]*/, double* cam_rt, double* board_rt, double* frame_rt, int fstride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C + B + F) return;
-  double* dst = i < C ? cam_rt + 6 * i : i < C + B ? board_rt + 6 * (i - C) : frame_rt + 6 * (i - C - B);
+  if (i >= C + B && fstride == 0) return;
+  double* dst = i < C ? cam_rt + 6 * i : i < C + B ? board_rt + 6 * (i - C) : frame_rt + fstride * (i - C - B);
   double rt[6];
   matrix_to_rtvec(mats + (size_t)16 * i, rt);
 #pragma unroll
   for (int j = 0; j < 6; j++) dst[j] = rt[j];
 }
-__global__ void k_state_to_matrices(int C, int B, int F, const double* cam_rt, const double* board_rt, const double* frame_rt, double* mats) {
+// frame_T != nullptr: frame matrices come from the pose table (hand-eye: derived poses; the table must be current)
+__global__ void k_state_to_matrices(int C, int B, int F, const double* cam_rt, const double* board_rt, const double* frame_rt, double* mats, int fstride,
+                                    const PoseT* frame_T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C + B + F) return;
-  const double* src = i < C ? cam_rt + 6 * i : i < C + B ? board_rt + 6 * (i - C) : frame_rt + 6 * (i - C - B);
+  double* M = mats + (size_t)16 * i;
+  if (i >= C + B && frame_T) {
+    const PoseT& t = frame_T[i - C - B];
+#pragma unroll
+    for (int r = 0; r < 3; r++) { M[4 * r] = t.R[3 * r]; M[4 * r + 1] = t.R[3 * r + 1]; M[4 * r + 2] = t.R[3 * r + 2]; M[4 * r + 3] = t.t[r]; }
+    M[12] = 0.0; M[13] = 0.0; M[14] = 0.0; M[15] = 1.0;
+    return;
+  }
+  const double* src = i < C ? cam_rt + 6 * i : i < C + B ? board_rt + 6 * (i - C) : frame_rt + fstride * (i - C - B);
   double R[9], JL[9];
   rodrigues(src, R, JL);
-  double* M = mats + (size_t)16 * i;
 #pragma unroll
   for (int r = 0; r < 3; r++) { M[4 * r] = R[3 * r]; M[4 * r + 1] = R[3 * r + 1]; M[4 * r + 2] = R[3 * r + 2]; M[4 * r + 3] = src[3 + r]; }
   M[12] = 0.0; M[13] = 0.0; M[14] = 0.0; M[15] = 1.0;
 }
 
 // k_make_trial: trial parameter state = current state with the free blocks replaced by x (internal order), and the
-// pose tables of that state, in one launch.  One thread per pose, then one per camera (intrinsics).
-__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o) {
+// pose tables of that state, in one launch.  One thread per pose, then one per camera (intrinsics), per board point, and one
+// for the hand-eye pair (which must be complete before the derived frame poses: those threads recompute it themselves).
+__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o, double* he_o) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int np = p.C + p.B + p.F;
+  const int nfp = p.F * p.npf;
+  const int np = p.C + p.B + nfp;
   if (i < np) {
     const double* cur; const double* src = nullptr; double* dst; PoseT* tab;
     if (i < p.C) { cur = p.cam_rt + 6 * i; dst = cam_o + 6 * i; tab = p.cam_T + i; if (p.off_cp >= 0) src = x + p.off_cp + 6 * i; }
     else if (i < p.C + p.B) { const int b = i - p.C; cur = p.board_rt + 6 * b; dst = board_o + 6 * b; tab = p.board_T + b; if (p.off_bp >= 0) src = x + p.off_bp + 6 * b; }
-    else { const int f = i - p.C - p.B; cur = p.frame_rt + 6 * f; dst = frame_o + 6 * f; tab = p.frame_T + f; if (p.motion_on) src = x + p.n_s + 6 * f; }
+    else {
+      const int q = i - p.C - p.B;
+      if (p.motion == MOTION_HAND_EYE) {
+        double he[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) he[j] = p.off_he >= 0 ? x[p.off_he + j] : p.he_rt[j];
+        PoseT t; hand_eye_frame(he, p.arm_T[q], t); p.frame_T[q] = t;
+        return;
+      }
+      cur = p.frame_rt + 6 * q; dst = frame_o + 6 * q; tab = p.frame_T + q; if (p.motion_on) src = x + p.n_s + 6 * q;
+    }
     if (!src) src = cur;
     double v[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) { v[j] = src[j]; dst[j] = v[j]; }
     PoseT t;
-    rodrigues(v, t.R, t.JL);
-    t.t[0] = v[3]; t.t[1] = v[4]; t.t[2] = v[5];
-    t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    pose_from_rt(v, t);
     *tab = t;
   } else if (i < np + p.C) {
     const int c = i - np;
@@ -127,6 +190,15 @@ __global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, do
     const int q = i - np - p.C;                                       // padded board point index b*P + p
     const double* src = p.off_pt >= 0 ? x + p.off_pt + 3 * q : p.board_pts + 3 * q;
     bpts_o[3 * q] = src[0]; bpts_o[3 * q + 1] = src[1]; bpts_o[3 * q + 2] = src[2];
+  } else if (i < np + p.C + p.B * p.P + 2 && p.motion == MOTION_HAND_EYE) {
+    const int j = i - np - p.C - p.B * p.P;
+    const double* src = p.off_he >= 0 ? x + p.off_he + 6 * j : p.he_rt + 6 * j;
+    double v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { v[k] = src[k]; he_o[6 * j + k] = v[k]; }
+    PoseT t;
+    pose_from_rt(v, t);
+    p.he_T[j] = t;
   }
 }
 
@@ -140,6 +212,31 @@ __device__ __forceinline__ void compose_view(const PoseT& c, const PoseT& f, con
   mat3_mul(Rcf, b.R, o.R);
   mat3_vec(Rcf, b.t, o.t);
   o.t[0] += tcf[0]; o.t[1] += tcf[1]; o.t[2] += tcf[2];
+}
+
+// the view's chain(s): static / hand-eye frames have one pose table entry per frame, rolling frames two (start, end)
+template <bool ROLL>
+__device__ __forceinline__ void compose_views(const DeviceProblem& p, int c, int f, int b, ViewPose& vp, ViewPose& vpe) {
+  if constexpr (ROLL) {
+    compose_view(p.cam_T[c], p.frame_T[2 * f], p.board_T[b], vp);
+    compose_view(p.cam_T[c], p.frame_T[2 * f + 1], p.board_T[b], vpe);
+  } else {
+    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
+  }
+}
+// camera-frame point of a corner.  Rolling shutter (rolling_frames.py:21-41 transformed_linear + interpolate.py:6-8 lerp): the
+// board point is transformed by the start and by the end chain and the two are blended by tau = observed row / image height.
+template <bool ROLL>
+__device__ __forceinline__ void corner_point(const ViewPose& vp, const ViewPose& vpe, const double* X, double tau,
+                                             double* Xc, double* Xs, double* Xe) {
+  mat3_vec(vp.R, X, Xc);
+  Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+  if constexpr (ROLL) {
+    mat3_vec(vpe.R, X, Xe);
+    Xe[0] += vpe.t[0]; Xe[1] += vpe.t[1]; Xe[2] += vpe.t[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { Xs[i] = Xc[i]; Xc[i] = Xs[i] * (1.0 - tau) + Xe[i] * tau; }
+  }
 }
 
 struct ViewKernelArgs {
@@ -162,9 +259,10 @@ constexpr double TRIGGS_FLOOR = 0.1;
 //   MODE_ERROR   -> per-corner ||proj - obs||              (tables.py:244-249)
 //   MODE_MOMENTS -> per-view sum of G^T G, G^T r, cost with G = d r / d[camera-frame twist | intrinsics]
 //                   (replaces scipy's 2-point FD Jacobian; entries [PART*CH, (PART+1)*CH) of the T moments)
-template <int MODEL, int MODE, int PART, int NPARTS>
+template <int MODEL, int MODE, int PART, int NPARTS, bool ROLL = false>
 __global__ void __launch_bounds__(VIEW_WARPS * 32)
 k_views(DeviceProblem p, ViewKernelArgs a) {
+  static_assert(!(ROLL && MODE == MODE_MOMENTS), "rolling frames are linearised by k_views_mma only");
   constexpr int ND = model_nd(MODEL);
   constexpr int D = 10 + ND;
   constexpr int E = D * (D + 1) / 2;
@@ -185,8 +283,9 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
   for (int v = gw; v < p.V; v += nw) {
     const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
     const int beg = p.view_start[v], end = p.view_start[v + 1];
-    ViewPose vp;
-    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
+    ViewPose vp, vpe;
+    compose_views<ROLL>(p, c, f, b, vp, vpe);
+    const double inv_h = ROLL ? 1.0 / p.img_h[c] : 0.0;
     double k[KINT];
 #pragma unroll
     for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
@@ -200,9 +299,8 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
       const double2 ob = p.obs[idx];
       const int pi = p.pid[idx];
       const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
-      double Xc[3];
-      mat3_vec(vp.R, X, Xc);
-      Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+      double Xc[3], Xs[3], Xe[3];
+      corner_point<ROLL>(vp, vpe, X, ob.y * inv_h, Xc, Xs, Xe);
       double u, w_;
       double Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
       project<MODEL, MODE == MODE_MOMENTS>(Xc, k, u, w_, Ju, Jv, ku, kv);
@@ -327,18 +425,21 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #define MMA_MIN_CTAS 4
 #endif
 constexpr int MMA_KPAD = 68;     // 64 residual rows + 4: (column stride mod 16 doubles) == 4 -> conflict-free fragment loads
-__host__ __device__ constexpr int mma_nc(int model) { return ((model_D(model) + 1 + 7) / 8) * 8; }
+__host__ __device__ constexpr int mma_nc(int model, bool roll = false) { return ((model_D(model) + (roll ? 6 : 0) + 1 + 7) / 8) * 8; }
 
 // WPV = warps per view: 1 (one warp owns a view; many views) or VIEW_WARPS (the CTA's warps split one view's chunks and meet in
 // shared memory once: few, long views -- e.g. 4 cameras x 200 frames -- would otherwise leave most of the machine idle).
-template <int MODEL, int WPV>
-__global__ void __launch_bounds__(VIEW_WARPS * 32, (MODEL == MODEL_TILTED ? 2 : MMA_MIN_CTAS))
+// ROLL (RollingFrames): the local row has two twist blocks, [xi_start (6) | xi_end (6) | fx fy cx cy dist], weighted by
+// (1 - tau) and tau -- d x_cam = (1-tau) (omega_s x X_s + v_s) + tau (omega_e x X_e + v_e).
+template <int MODEL, int WPV, bool ROLL = false>
+__global__ void __launch_bounds__(VIEW_WARPS * 32, ((MODEL == MODEL_TILTED || ROLL) ? 2 : MMA_MIN_CTAS))
 k_views_mma(DeviceProblem p, ViewKernelArgs a) {
   constexpr int ND = model_nd(MODEL);
-  constexpr int D = 10 + ND;
+  constexpr int KO = ROLL ? 12 : 6;              // offset of the intrinsics in the local row
+  constexpr int D = KO + 4 + ND;
   constexpr int E = D * (D + 1) / 2;
   constexpr int T = E + D + 1;
-  constexpr int NC = mma_nc(MODEL);
+  constexpr int NC = mma_nc(MODEL, ROLL);
   constexpr int NT = NC / 8;
   constexpr int NPAIR = NT * (NT + 1) / 2;
   constexpr int KINT = 5 + ND;
@@ -356,8 +457,9 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
   for (int v = gw; v < p.V; v += nw) {
     const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
     const int beg = p.view_start[v], end = p.view_start[v + 1];
-    ViewPose vp;
-    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
+    ViewPose vp, vpe;
+    compose_views<ROLL>(p, c, f, b, vp, vpe);
+    const double inv_h = ROLL ? 1.0 / p.img_h[c] : 0.0;
     double k[KINT];
 #pragma unroll
     for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
@@ -377,9 +479,9 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
         const double2 ob = p.obs[idx];
         const int pi = p.pid[idx];
         const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
-        double Xc[3];
-        mat3_vec(vp.R, X, Xc);
-        Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+        const double tau = ob.y * inv_h;
+        double Xc[3], Xs[3], Xe[3];
+        corner_point<ROLL>(vp, vpe, X, tau, Xc, Xs, Xe);
         double u, w_;
         double Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
         project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
@@ -401,14 +503,24 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
           wu = sqrt(ju); wv = sqrt(jv);
           ru *= r1u / wu; rv *= r1v / wv;
         }
-        gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
-        gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
+        if constexpr (!ROLL) {
+          gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
+          gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
 #pragma unroll
-        for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
-        gu[6] = ku[0] * wu; gu[8] = wu;
-        gv[7] = kv[1] * wv; gv[9] = wv;
+          for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
+        } else {
+          const double su = (1.0 - tau) * wu, sv = (1.0 - tau) * wv, eu = tau * wu, ev = tau * wv;
+          gu[0] = (Xs[1] * Ju[2] - Xs[2] * Ju[1]) * su; gu[1] = (Xs[2] * Ju[0] - Xs[0] * Ju[2]) * su; gu[2] = (Xs[0] * Ju[1] - Xs[1] * Ju[0]) * su;
+          gv[0] = (Xs[1] * Jv[2] - Xs[2] * Jv[1]) * sv; gv[1] = (Xs[2] * Jv[0] - Xs[0] * Jv[2]) * sv; gv[2] = (Xs[0] * Jv[1] - Xs[1] * Jv[0]) * sv;
+          gu[6] = (Xe[1] * Ju[2] - Xe[2] * Ju[1]) * eu; gu[7] = (Xe[2] * Ju[0] - Xe[0] * Ju[2]) * eu; gu[8] = (Xe[0] * Ju[1] - Xe[1] * Ju[0]) * eu;
+          gv[6] = (Xe[1] * Jv[2] - Xe[2] * Jv[1]) * ev; gv[7] = (Xe[2] * Jv[0] - Xe[0] * Jv[2]) * ev; gv[8] = (Xe[0] * Jv[1] - Xe[1] * Jv[0]) * ev;
 #pragma unroll
-        for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
+          for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * su; gv[3 + i] = Jv[i] * sv; gu[9 + i] = Ju[i] * eu; gv[9 + i] = Jv[i] * ev; }
+        }
+        gu[KO] = ku[0] * wu; gu[KO + 2] = wu;
+        gv[KO + 1] = kv[1] * wv; gv[KO + 3] = wv;
+#pragma unroll
+        for (int i = 0; i < ND; i++) { gu[KO + 4 + i] = ku[4 + i] * wu; gv[KO + 4 + i] = kv[4 + i] * wv; }
         gu[D] = ru; gv[D] = rv;                      // residual column: Gt^T Gt then carries G^T r as well
       }
       // stage: rows 2*lane (u) and 2*lane+1 (v); one 16-byte store per column, consecutive lanes -> consecutive addresses
@@ -620,36 +732,64 @@ __device__ __forceinline__ void view_chain(const PoseT& pc, const PoseT& pf, dou
   tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
 }
 
-// per-warp shared slice of k_expand_frames: Ms[T] | Tm[D*6] | Ac[36] | Af[36] | Ab[36] | Wb[B*36]
-__host__ __device__ inline int expf_warp_doubles(int T, int D, int B) { return T + D * 6 + 108 + B * 36; }
+// NP = twist blocks of the local row / pose-table entries per frame: 1 (static, hand-eye), 2 (rolling: start, end).  A parameter
+// block reaches the local twists through NP 6x6 maps (camera pose: the same map for every block; board pose: one map per chain;
+// frame pose j: its own map into block j only), so every product below is the static one summed over the NP blocks.
+// per-warp shared slice of k_expand_frames: Ms[T] | Tm[D*FB] | Ac[36] | Af[NP*36] | Ab[NP*36] | Wb[B*6*FB]
+__host__ __device__ inline int expf_warp_doubles(int T, int D, int B, int NP) { return T + D * 6 * NP + 36 + 72 * NP + B * 36 * NP; }
 
-// k_expand_frames: one CTA per frame -> H_ff (6x6), g_f (6) and W_f (n_s x 6).  Warp w owns the cameras c == w (mod
-// EXP_WARPS): the camera-pose and intrinsics rows of W_f are written by exactly one warp (registers, flushed when the
-// camera changes); board-pose rows, H_ff and g_f are per-warp partials summed at the end.
+// the view's twist maps: Ac (camera pose), Af[j] (frame pose j), Ab[j] (board pose through chain j); lanes 0 .. 2 NP of the warp
+template <int NP>
+__device__ __forceinline__ void view_twist_maps(const DeviceProblem& p, int c, int f, int b, int lane, double* Ac, double* Af, double* Ab) {
+  if (lane > 2 * NP) return;
+  const PoseT& pc = p.cam_T[c];
+  if (lane == 0) { if (Ac) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); } return; }
+  const int j = (lane - 1) % NP;
+  const PoseT& pf = p.frame_T[f * NP + j];
+  double Rcf[9], tcf[3];
+  view_chain(pc, pf, Rcf, tcf);
+  if (lane <= NP) { if (Af) twist_map(pc.R, pf.JL, tcf, Af + 36 * j); return; }
+  if (!Ab) return;
+  const PoseT& pb = p.board_T[b];
+  double tb[3];
+  mat3_vec(Rcf, pb.t, tb);
+  tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
+  twist_map(Rcf, pb.JL, tb, Ab + 36 * j);
+}
+
+// k_expand_frames: one CTA per frame -> H_ff (FB x FB), g_f (FB) and W_f (n_s x FB), FB = 6 NP.  Warp w owns the cameras
+// c == w (mod EXP_WARPS): the camera-pose and intrinsics rows of W_f are written by exactly one warp (registers, flushed when
+// the camera changes); board-pose rows, H_ff and g_f are per-warp partials summed at the end.
+template <int NP>
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand_frames(DeviceProblem p, SolverBuffers s) {
+  constexpr int FB = 6 * NP, KO = 6 * NP;
+  constexpr int NHF = FB * FB + FB;                  // H_ff | g_f outputs
   extern __shared__ double sh[];
   const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
   const int E = D * (D + 1) / 2;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wd = expf_warp_doubles(T, D, B);
+  const int wd = expf_warp_doubles(T, D, B, NP);
   double* Ms = sh + (size_t)warp * wd;
-  double* Tm = Ms + T;
-  double* Ac = Tm + D * 6;
+  double* Tm = Ms + T;                               // [D][FB]: column block j = M[:, xi_j] Af_j
+  double* Ac = Tm + D * FB;
   double* Af = Ac + 36;
-  double* Ab = Af + 36;
-  double* Wb = Ab + 36;                              // [B][36] partial board rows of this warp
-  double* red = sh + (size_t)EXP_WARPS * wd;        // [EXP_WARPS][42]  H_ff | g_f partials
-  double* Wf = s.W + (size_t)f * n_s * 6;
-  for (int i = tid; i < n_s * 6; i += EXP_THREADS) Wf[i] = 0.0;
-  for (int i = lane; i < B * 36; i += 32) Wb[i] = 0.0;
+  double* Ab = Af + 36 * NP;
+  double* Wb = Ab + 36 * NP;                         // [B][6][FB] partial board rows of this warp
+  double* red = sh + (size_t)EXP_WARPS * wd;        // [EXP_WARPS][NHF]  H_ff | g_f partials
+  double* Wf = s.W + (size_t)f * n_s * FB;
+  for (int i = tid; i < n_s * FB; i += EXP_THREADS) Wf[i] = 0.0;
+  for (int i = lane; i < B * 6 * FB; i += 32) Wb[i] = 0.0;
   __syncthreads();                                   // W_f zeroed before any warp adds its camera rows
 
   const int nin = 4 + p.nd;
-  const int ncam_out = 36 + nin * 6;                 // camera pose (6x6) + intrinsics (nin x 6) rows of W_f
-  constexpr int MAXOUT = 5;                          // ceil((36 + 16*6)/32)
-  double hacc0 = 0.0, hacc1 = 0.0;                   // lane-owned H_ff (36) | g_f (6) outputs: o = lane, lane+32
+  const int ncam_out = (6 + nin) * FB;               // camera pose (6 x FB) + intrinsics (nin x FB) rows of W_f
+  constexpr int MAXOUT = ((6 + 16) * FB + 31) / 32;
+  constexpr int NH = (NHF + 31) / 32;
+  double hacc[NH];                                   // lane-owned H_ff | g_f outputs: o = lane + 32 q
   double wacc[MAXOUT];
+#pragma unroll
+  for (int i = 0; i < NH; i++) hacc[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < MAXOUT; i++) wacc[i] = 0.0;
   int cur_cam = -1;
@@ -661,10 +801,10 @@ k_expand_frames(DeviceProblem p, SolverBuffers s) {
       const int o = lane + 32 * q;
       if (o < ncam_out) {
         const double val = wacc[q];
-        if (o < 36) { if (p.off_cp >= 0) Wf[(p.off_cp + 6 * c + o / 6) * 6 + o % 6] = val; }
+        if (o < 6 * FB) { if (p.off_cp >= 0) Wf[(p.off_cp + 6 * c + o / FB) * FB + o % FB] = val; }
         else if (p.off_in >= 0) {
-          const int i = (o - 36) / 6, j = (o - 36) % 6;
-          if (!(p.fix_aspect && i == 1)) Wf[(p.off_in + p.kint * c + intr_param_index(p, i)) * 6 + j] = val;
+          const int i = (o - 6 * FB) / FB, j = (o - 6 * FB) % FB;
+          if (!(p.fix_aspect && i == 1)) Wf[(p.off_in + p.kint * c + intr_param_index(p, i)) * FB + j] = val;
         }
       }
       wacc[q] = 0.0;
@@ -678,109 +818,106 @@ k_expand_frames(DeviceProblem p, SolverBuffers s) {
     const int b = p.view_board[v];
     if (c != cur_cam) { flush_camera(cur_cam); cur_cam = c; }
     for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
-    if (lane < 3) {
-      const PoseT& pc = p.cam_T[c]; const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
-      double Rcf[9], tcf[3];
-      view_chain(pc, pf, Rcf, tcf);
-      if (lane == 0) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
-      else if (lane == 1) twist_map(pc.R, pf.JL, tcf, Af);
-      else { double tb[3]; mat3_vec(Rcf, pb.t, tb); tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2]; twist_map(Rcf, pb.JL, tb, Ab); }
-    }
+    view_twist_maps<NP>(p, c, f, b, lane, Ac, Af, Ab);
     __syncwarp();
-    for (int o = lane; o < D * 6; o += 32) {          // Tm = M[:, xi] Af
-      const int i = o / 6, j = o % 6; double acc = 0.0;
+    for (int o = lane; o < D * FB; o += 32) {         // Tm[:, 6j+k] = M[:, xi_j] Af_j
+      const int i = o / FB, col = o % FB, j = col / 6, k = col % 6; double acc = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Af[kk * 6 + j];
+      for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, 6 * j + kk) * Af[36 * j + kk * 6 + k];
       Tm[o] = acc;
     }
     __syncwarp();
-    // H_ff += Af^T Tm_xi (36) ; g_f += Af^T g_xi (6)
-    {
-      const int o = lane;
-      { const int i = o / 6, j = o % 6; double acc = 0.0;
+    // H_ff[6a+i, col] += Af_a^T Tm[xi_a rows, col] ; g_f[6a+i] += Af_a^T g_xi_a
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Tm[kk * 6 + j];
-        hacc0 += acc; }
-      const int o2 = lane + 32;
-      if (o2 < 36) { const int i = o2 / 6, j = o2 % 6; double acc = 0.0;
+    for (int q = 0; q < NH; q++) {
+      const int o = lane + 32 * q;
+      if (o < FB * FB) {
+        const int r = o / FB, col = o % FB, a = r / 6, i = r % 6; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Tm[kk * 6 + j];
-        hacc1 += acc; }
-      else if (o2 < 42) { const int i = o2 - 36; double acc = 0.0;
+        for (int kk = 0; kk < 6; kk++) acc += Af[36 * a + kk * 6 + i] * Tm[(6 * a + kk) * FB + col];
+        hacc[q] += acc;
+      } else if (o < NHF) {
+        const int r = o - FB * FB, a = r / 6, i = r % 6; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Af[kk * 6 + i] * Ms[E + kk];
-        hacc1 += acc; }
+        for (int kk = 0; kk < 6; kk++) acc += Af[36 * a + kk * 6 + i] * Ms[E + 6 * a + kk];
+        hacc[q] += acc;
+      }
     }
-    // camera rows: Ac^T Tm_xi (36) | Tm_k (nin x 6, fix_aspect folds fy onto fx)
+    // camera rows: sum_a Ac^T Tm[xi_a rows] (6 x FB) | Tm_k (nin x FB, fix_aspect folds fy onto fx)
 #pragma unroll
     for (int q = 0; q < MAXOUT; q++) {
       const int o = lane + 32 * q;
-      if (o < 36) { const int i = o / 6, j = o % 6; double acc = 0.0;
+      if (o < 6 * FB) {
+        const int i = o / FB, col = o % FB; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * Tm[kk * 6 + j];
-        wacc[q] += acc; }
-      else if (o < ncam_out) {
-        const int i = (o - 36) / 6, j = (o - 36) % 6;
-        double val = Tm[(6 + i) * 6 + j];
-        if (p.fix_aspect && i == 0) val += Tm[(6 + 1) * 6 + j];
+        for (int kk = 0; kk < KO; kk++) acc += Ac[(kk % 6) * 6 + i] * Tm[kk * FB + col];
+        wacc[q] += acc;
+      } else if (o < ncam_out) {
+        const int i = (o - 6 * FB) / FB, col = (o - 6 * FB) % FB;
+        double val = Tm[(KO + i) * FB + col];
+        if (p.fix_aspect && i == 0) val += Tm[(KO + 1) * FB + col];
         wacc[q] += val;
       }
     }
     // board rows (shared between cameras): per-warp partial
     if (p.off_bp >= 0) {
-      for (int o = lane; o < 36; o += 32) { const int i = o / 6, j = o % 6; double acc = 0.0;
+      for (int o = lane; o < 6 * FB; o += 32) {
+        const int i = o / FB, col = o % FB; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Tm[kk * 6 + j];
-        Wb[b * 36 + o] += acc; }
+        for (int kk = 0; kk < KO; kk++) acc += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Tm[kk * FB + col];
+        Wb[b * 6 * FB + o] += acc;
+      }
     }
     __syncwarp();
   }
   flush_camera(cur_cam);
   // ---- meet: sum the per-warp partials
-  red[warp * 42 + lane] = hacc0;
-  if (lane + 32 < 42) red[warp * 42 + lane + 32] = hacc1;
+#pragma unroll
+  for (int q = 0; q < NH; q++) { const int o = lane + 32 * q; if (o < NHF) red[warp * NHF + o] = hacc[q]; }
   __syncthreads();
-  if (tid < 42) {
+  for (int o = tid; o < NHF; o += EXP_THREADS) {
     double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < EXP_WARPS; w++) acc += red[w * 42 + tid];
-    if (tid < 36) s.Hff[(size_t)f * 36 + tid] = acc; else s.g[n_s + 6 * f + tid - 36] = acc;
+    for (int w = 0; w < EXP_WARPS; w++) acc += red[w * NHF + o];
+    if (o < FB * FB) s.Hff[(size_t)f * FB * FB + o] = acc; else s.g[n_s + FB * f + o - FB * FB] = acc;
   }
   if (p.off_bp >= 0)
-    for (int o = tid; o < B * 36; o += EXP_THREADS) {
+    for (int o = tid; o < B * 6 * FB; o += EXP_THREADS) {
       double acc = 0.0;
 #pragma unroll
-      for (int w = 0; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + T + D * 6 + 108 + o];
-      const int b = o / 36, i = (o % 36) / 6, j = o % 6;
-      Wf[(p.off_bp + 6 * b + i) * 6 + j] = acc;
+      for (int w = 0; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + T + D * FB + 36 + 72 * NP + o];
+      const int b = o / (6 * FB), i = (o % (6 * FB)) / FB, j = o % FB;
+      Wf[(p.off_bp + 6 * b + i) * FB + j] = acc;
     }
 }
 
-// per-warp shared slice of k_expand_shared: Ms[T] | Um[D*6] | Ab[36] | Ub[B*D*6] | Hbb[B*36] | gb[B*6]
-__host__ __device__ inline int exps_warp_doubles(int T, int D, int B) { return T + D * 6 + 36 + B * (D * 6 + 42); }
+// per-warp shared slice of k_expand_shared: Ms[T] | Um[D*6] | Ab[NP*36] | Ub[B*D*6] | Hbb[B*36] | gb[B*6]
+__host__ __device__ inline int exps_warp_doubles(int T, int D, int B, int NP) { return T + D * 6 + 36 * NP + B * (D * 6 + 42); }
 
 // k_expand_shared: one CTA per (camera, chunk of that camera's views).  The camera's own (pose+intrinsics) block is a
 // plain sum of moment records (its twist map does not depend on the view) kept lane-distributed in registers; the
-// camera-board and board-board blocks need the per-view board twist map.  Per-warp partials are summed once at the
+// camera-board and board-board blocks need the per-view board twist map(s).  Per-warp partials are summed once at the
 // end and added into H_ss / g_s with fp64 atomics.
+template <int NP>
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
+  constexpr int KO = 6 * NP;
   extern __shared__ double sh[];
   const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
   const int E = D * (D + 1) / 2;
   const int c = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wd = exps_warp_doubles(T, D, B);
+  const int wd = exps_warp_doubles(T, D, B, NP);
   double* Ms = sh + (size_t)warp * wd;
   double* Um = Ms + T;
   double* Ab = Um + D * 6;
-  double* Ub = Ab + 36;
+  double* Ub = Ab + 36 * NP;
   double* Hbb = Ub + (size_t)B * D * 6;
   double* gb = Hbb + B * 36;
   double* Msum = sh + (size_t)EXP_WARPS * wd;          // [T] block total
   double* Ac = Msum + T;                                // 36
   for (int i = lane; i < B * (D * 6 + 42); i += 32) Ub[i] = 0.0;
-  constexpr int MAXT = 11;                               // ceil(325/32): tilted model, D = 24
+  constexpr int MAXT = NP == 1 ? 11 : 16;                // ceil(T/32): tilted model, D = 24 (T = 325) / rolling tilted, D = 30 (T = 496)
   double macc[MAXT];
 #pragma unroll
   for (int q = 0; q < MAXT; q++) macc[q] = 0.0;
@@ -799,19 +936,12 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
       if (i < T) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; macc[q] += m; }
     }
     if (p.off_bp >= 0) {
-      if (lane == 0) {
-        const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
-        double Rcf[9], tcf[3], tb[3];
-        view_chain(pc, pf, Rcf, tcf);
-        mat3_vec(Rcf, pb.t, tb);
-        tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
-        twist_map(Rcf, pb.JL, tb, Ab);
-      }
+      view_twist_maps<NP>(p, c, f, b, lane, nullptr, nullptr, Ab);
       __syncwarp();
-      for (int o = lane; o < D * 6; o += 32) {
+      for (int o = lane; o < D * 6; o += 32) {           // Um = sum_a M[:, xi_a] Ab_a
         const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Ab[kk * 6 + j];
+        for (int kk = 0; kk < KO; kk++) acc += msym(Ms, D, i, kk) * Ab[36 * (kk / 6) + (kk % 6) * 6 + j];
         Um[o] = acc;
         Ub[(size_t)b * D * 6 + o] += acc;
       }
@@ -819,11 +949,11 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
       for (int o = lane; o < 42; o += 32) {
         if (o < 36) { const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Um[kk * 6 + j];
+          for (int kk = 0; kk < KO; kk++) acc += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Um[kk * 6 + j];
           Hbb[b * 36 + o] += acc; }
         else { const int i = o - 36; double acc = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Ms[E + kk];
+          for (int kk = 0; kk < KO; kk++) acc += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Ms[E + kk];
           gb[b * 6 + i] += acc; }
       }
     }
@@ -840,7 +970,7 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
     Msum[i] = acc;
   }
   const int nb_part = B * (D * 6 + 42);
-  const int part_off = T + D * 6 + 36;
+  const int part_off = T + D * 6 + 36 * NP;
   for (int i = tid; i < nb_part; i += EXP_THREADS) {
     double acc = 0.0;
 #pragma unroll
@@ -852,10 +982,10 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
   Um = sh + T;                                           // warp 0's Um, reused by the whole block
   Ub = sh + part_off; Hbb = Ub + (size_t)B * D * 6; gb = Hbb + B * 36;
   if (tid == 0) s.cost_part[blockIdx.x] = Msum[T - 1];
-  for (int o = tid; o < D * 6; o += EXP_THREADS) {       // Um = Msum[:, xi] Ac
+  for (int o = tid; o < D * 6; o += EXP_THREADS) {       // Um = sum_a Msum[:, xi_a] Ac  (the camera's map is the same for every chain)
     const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
-    for (int kk = 0; kk < 6; kk++) acc += msym(Msum, D, i, kk) * Ac[kk * 6 + j];
+    for (int kk = 0; kk < KO; kk++) acc += msym(Msum, D, i, kk) * Ac[(kk % 6) * 6 + j];
     Um[o] = acc;
   }
   __syncthreads();
@@ -872,13 +1002,13 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
       if (j < i) continue;
       double acc = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * Um[kk * 6 + j];
+      for (int kk = 0; kk < KO; kk++) acc += Ac[(kk % 6) * 6 + i] * Um[kk * 6 + j];
       addH(cp + i, cp + j, acc);
     }
     if (tid < 6) {
       double acc = 0.0;
 #pragma unroll
-      for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + tid] * Msum[E + kk];
+      for (int kk = 0; kk < KO; kk++) acc += Ac[(kk % 6) * 6 + tid] * Msum[E + kk];
       atomicAdd(&s.g[cp + tid], acc);
     }
   }
@@ -886,28 +1016,28 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
     if (cp >= 0)
       for (int o = tid; o < nin * 6; o += EXP_THREADS) {
         const int i = o / 6, j = o % 6;
-        addH(in0 + intr_param_index(p, i), cp + j, Um[(6 + i) * 6 + j]);
+        addH(in0 + intr_param_index(p, i), cp + j, Um[(KO + i) * 6 + j]);
       }
     for (int o = tid; o < nin * nin; o += EXP_THREADS) {
       const int i = o / nin, j = o % nin;
-      atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + in0 + intr_param_index(p, j)], msym(Msum, D, 6 + i, 6 + j));
+      atomicAdd(&s.Hss[(size_t)(in0 + intr_param_index(p, i)) * n_s + in0 + intr_param_index(p, j)], msym(Msum, D, KO + i, KO + j));
     }
-    for (int i = tid; i < nin; i += EXP_THREADS) atomicAdd(&s.g[in0 + intr_param_index(p, i)], Msum[E + 6 + i]);
+    for (int i = tid; i < nin; i += EXP_THREADS) atomicAdd(&s.g[in0 + intr_param_index(p, i)], Msum[E + KO + i]);
   }
   if (p.off_bp >= 0) {
     for (int b = 0; b < B; b++) {
       const int bp = p.off_bp + 6 * b;
       const double* U = Ub + (size_t)b * D * 6;
       if (cp >= 0)
-        for (int o = tid; o < 36; o += EXP_THREADS) {     // camera pose x board pose = Ac^T U_xi
+        for (int o = tid; o < 36; o += EXP_THREADS) {     // camera pose x board pose = sum_a Ac^T U_xi_a
           const int i = o / 6, j = o % 6; double acc = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * U[kk * 6 + j];
+          for (int kk = 0; kk < KO; kk++) acc += Ac[(kk % 6) * 6 + i] * U[kk * 6 + j];
           if (acc != 0.0) addH(cp + i, bp + j, acc);
         }
       if (in0 >= 0)
         for (int o = tid; o < nin * 6; o += EXP_THREADS) { // intrinsics x board pose = U_k
-          const int i = o / 6, j = o % 6; const double val = U[(6 + i) * 6 + j];
+          const int i = o / 6, j = o % 6; const double val = U[(KO + i) * 6 + j];
           if (val != 0.0) addH(in0 + intr_param_index(p, i), bp + j, val);
         }
       for (int o = tid; o < 36; o += EXP_THREADS) {
@@ -917,6 +1047,144 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
       if (tid < 6 && gb[b * 6 + tid] != 0.0) atomicAdd(&s.g[bp + tid], gb[b * 6 + tid]);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hand-eye motion (motion/hand_eye.py:14-90): the frame pose is G A_f W with the arm pose A_f fixed, so the "motion" block is
+// 12 SHARED parameters he = [W = world_wrt_base (6) | G = gripper_wrt_camera (6)] that every residual depends on
+// (hand_eye.py:89-90) and there are no per-frame blocks to eliminate.  The per-view moments are the static ones (the chain
+// T_c T_f T_b only changed how T_f is obtained); this kernel adds the he rows and columns of H_ss / g_s on top of
+// k_expand_shared<1>.  Twist maps of one view (camera c, frame f):
+//   W: left part T_c G A_f, chain translation up to and including W = t(T_c T_f)      -> twist_map(R_c R_G R_Af, JL_W, t_cf)
+//   G: left part T_c,       chain translation up to and including G = R_c t_G + t_c   -> twist_map(R_c, JL_G, t_cG)
+// per-warp shared slice: Ms[T] | Eh[6*12] | Ab[36] | Uh[D*12] | UhS[D*12] | Hhh[144] | gh[12] | Hbh[B*72]
+__host__ __device__ inline int exph_warp_doubles(int T, int D, int B) { return T + 72 + 36 + 2 * D * 12 + 156 + B * 72; }
+
+__global__ void __launch_bounds__(EXP_THREADS)
+k_expand_hand_eye(DeviceProblem p, SolverBuffers s, int chunks) {
+  extern __shared__ double sh[];
+  const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
+  const int E = D * (D + 1) / 2;
+  const int c = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wd = exph_warp_doubles(T, D, B);
+  double* Ms = sh + (size_t)warp * wd;
+  double* Eh = Ms + T;                 // [6][12]
+  double* Ab = Eh + 72;
+  double* Uh = Ab + 36;                // [D][12]  M[:, xi] Eh of the current view
+  double* UhS = Uh + D * 12;           // [D][12]  summed over this warp's views
+  double* Hhh = UhS + D * 12;          // [12][12]
+  double* gh = Hhh + 144;              // [12]
+  double* Hbh = gh + 12;               // [B][6][12]
+  const int npart = D * 12 + 156 + B * 72;
+  for (int i = lane; i < npart; i += 32) UhS[i] = 0.0;
+  __syncwarp();
+
+  const int l0 = p.cam_view_start[c], l1 = p.cam_view_start[c + 1];
+  const int per = (l1 - l0 + chunks - 1) / chunks;
+  const int a0 = l0 + chunk * per, a1 = min(l1, a0 + per);
+  const PoseT& pc = p.cam_T[c];
+  const PoseT& pW = p.he_T[0];
+  const PoseT& pG = p.he_T[1];
+  for (int li = a0 + warp; li < a1; li += EXP_WARPS) {
+    const int v = p.cam_view_list[li];
+    const int f = p.view_frame[v], b = p.view_board[v];
+    for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
+    if (lane < 3) {
+      const PoseT& pf = p.frame_T[f];
+      double Rcf[9], tcf[3], A[36];
+      view_chain(pc, pf, Rcf, tcf);
+      if (lane == 0) {           // W
+        const PoseT& pa = p.arm_T[f];
+        double Rcg[9], Rl[9];
+        mat3_mul(pc.R, pG.R, Rcg);
+        mat3_mul(Rcg, pa.R, Rl);
+        twist_map(Rl, pW.JL, tcf, A);
+        for (int kk = 0; kk < 6; kk++) for (int j = 0; j < 6; j++) Eh[kk * 12 + j] = A[kk * 6 + j];
+      } else if (lane == 1) {    // G
+        double tcg[3];
+        mat3_vec(pc.R, pG.t, tcg);
+        tcg[0] += pc.t[0]; tcg[1] += pc.t[1]; tcg[2] += pc.t[2];
+        twist_map(pc.R, pG.JL, tcg, A);
+        for (int kk = 0; kk < 6; kk++) for (int j = 0; j < 6; j++) Eh[kk * 12 + 6 + j] = A[kk * 6 + j];
+      } else if (p.off_bp >= 0) {
+        const PoseT& pb = p.board_T[b];
+        double tb[3];
+        mat3_vec(Rcf, pb.t, tb);
+        tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
+        twist_map(Rcf, pb.JL, tb, Ab);
+      }
+    }
+    __syncwarp();
+    for (int o = lane; o < D * 12; o += 32) {            // Uh = M[:, xi] Eh
+      const int i = o / 12, j = o % 12; double acc = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, kk) * Eh[kk * 12 + j];
+      Uh[o] = acc;
+      UhS[o] += acc;
+    }
+    __syncwarp();
+    for (int o = lane; o < 156; o += 32) {               // Hhh += Eh^T Uh_xi ; gh += Eh^T g_xi
+      double acc = 0.0;
+      if (o < 144) { const int i = o / 12, j = o % 12;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Eh[kk * 12 + i] * Uh[kk * 12 + j];
+      } else { const int i = o - 144;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Eh[kk * 12 + i] * Ms[E + kk];
+      }
+      Hhh[o] += acc;                                     // gh follows Hhh in the slice
+    }
+    if (p.off_bp >= 0)
+      for (int o = lane; o < 72; o += 32) {              // board pose x he = Ab^T Uh_xi
+        const int i = o / 12, j = o % 12; double acc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 6; kk++) acc += Ab[kk * 6 + i] * Uh[kk * 12 + j];
+        Hbh[b * 72 + o] += acc;
+      }
+    __syncwarp();
+  }
+  // ---- meet: warp 0's partials become the block totals
+  __syncthreads();
+  const int part_off = T + 72 + 36 + D * 12;
+  for (int i = tid; i < npart; i += EXP_THREADS) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 1; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + part_off + i];
+    sh[part_off + i] += acc;
+  }
+  double* Ac = sh + T;                                    // warp 0's Eh slot is free now
+  if (tid == 0) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
+  __syncthreads();
+  UhS = sh + part_off; Hhh = UhS + D * 12; gh = Hhh + 144; Hbh = gh + 12;
+  const int he = p.off_he;
+  const int nin = 4 + p.nd;
+  const int cp = p.off_cp >= 0 ? p.off_cp + 6 * c : -1;
+  const int in0 = p.off_in >= 0 ? p.off_in + p.kint * c : -1;
+  auto addS = [&](int i, int j, double val) {             // off-diagonal block: both triangles
+    atomicAdd(&s.Hss[(size_t)i * n_s + j], val);
+    atomicAdd(&s.Hss[(size_t)j * n_s + i], val);
+  };
+  for (int o = tid; o < 144; o += EXP_THREADS) atomicAdd(&s.Hss[(size_t)(he + o / 12) * n_s + he + o % 12], Hhh[o]);
+  if (tid < 12) atomicAdd(&s.g[he + tid], gh[tid]);
+  if (cp >= 0)
+    for (int o = tid; o < 72; o += EXP_THREADS) {         // camera pose x he = Ac^T UhS_xi
+      const int i = o / 12, j = o % 12; double acc = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 6; kk++) acc += Ac[kk * 6 + i] * UhS[kk * 12 + j];
+      addS(cp + i, he + j, acc);
+    }
+  if (in0 >= 0)
+    for (int o = tid; o < nin * 12; o += EXP_THREADS) {   // intrinsics x he = UhS_k
+      const int i = o / 12, j = o % 12;
+      addS(in0 + intr_param_index(p, i), he + j, UhS[(6 + i) * 12 + j]);
+    }
+  if (p.off_bp >= 0)
+    for (int o = tid; o < B * 72; o += EXP_THREADS) {
+      const int b = o / 72, i = (o % 72) / 12, j = o % 12;
+      const double val = Hbh[o];
+      if (val != 0.0) addS(p.off_bp + 6 * b + i, he + j, val);
+    }
 }
 
 }  // namespace mcba

@@ -92,6 +92,8 @@ struct mcba_ctx {
   DevBuf<PoseT> cam_T, frame_T, board_T;
   // trial parameter state
   DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2, board_pts2, pose_mats;
+  // motion models: image heights (rolling), hand-eye pair (current / trial) with its pose table and the fixed arm poses
+  DevBuf<double> img_h, he_rt, he_rt2; DevBuf<PoseT> he_T, arm_T;
   // solver buffers
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
   DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
@@ -176,7 +178,8 @@ __global__ void k_scatter_params(DeviceProblem p, const double* x, double* cam_r
   if (p.off_cp >= 0 && i >= p.off_cp && i < p.off_cp + 6 * p.C) { cam_rt[i - p.off_cp] = v; return; }
   if (p.off_bp >= 0 && i >= p.off_bp && i < p.off_bp + 6 * p.B) { board_rt[i - p.off_bp] = v; return; }
   if (p.off_in >= 0 && i >= p.off_in && i < p.off_in + p.kint * p.C) { intr[i - p.off_in] = v; return; }
-  if (p.off_pt >= 0 && i >= p.off_pt) { p.board_pts[i - p.off_pt] = v; }
+  if (p.off_pt >= 0 && i >= p.off_pt && i < p.off_pt + 3 * p.B * p.P) { p.board_pts[i - p.off_pt] = v; return; }
+  if (p.off_he >= 0 && i >= p.off_he && i < p.off_he + 12) p.he_rt[i - p.off_he] = v;
 }
 __global__ void k_gather_params(DeviceProblem p, double* x, const double* cam_rt, const double* board_rt, const double* frame_rt, const double* intr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,7 +189,8 @@ __global__ void k_gather_params(DeviceProblem p, double* x, const double* cam_rt
   else if (p.off_cp >= 0 && i >= p.off_cp && i < p.off_cp + 6 * p.C) v = cam_rt[i - p.off_cp];
   else if (p.off_bp >= 0 && i >= p.off_bp && i < p.off_bp + 6 * p.B) v = board_rt[i - p.off_bp];
   else if (p.off_in >= 0 && i >= p.off_in && i < p.off_in + p.kint * p.C) v = intr[i - p.off_in];
-  else if (p.off_pt >= 0 && i >= p.off_pt) v = p.board_pts[i - p.off_pt];
+  else if (p.off_pt >= 0 && i >= p.off_pt && i < p.off_pt + 3 * p.B * p.P) v = p.board_pts[i - p.off_pt];
+  else if (p.off_he >= 0 && i >= p.off_he && i < p.off_he + 12) v = p.he_rt[i - p.off_he];
   x[i] = v;
 }
 // copies the fixed blocks so that a trial state is complete; with fix_aspect fy follows fx (camera.py:159-160)
@@ -201,7 +205,18 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
   const int th = VIEW_WARPS * 32;
   cudaStream_t s = ctx->stream;
 #define LV(MODEL, PART, NP) k_views<MODEL, MODE, PART, NP><<<blocks, th, 0, s>>>(P, a); CKL();
+#define LR(MODEL) k_views<MODEL, MODE, 0, 1, true><<<blocks, th, 0, s>>>(P, a); CKL();
   if constexpr (MODE != MODE_MOMENTS) {
+    if (P.motion == MOTION_ROLLING) {
+      switch (P.model) {
+        case MODEL_STANDARD: LR(MODEL_STANDARD) break;
+        case MODEL_RATIONAL: LR(MODEL_RATIONAL) break;
+        case MODEL_THIN_PRISM: LR(MODEL_THIN_PRISM) break;
+        case MODEL_TILTED: LR(MODEL_TILTED) break;
+        default: LR(MODEL_FISHEYE) break;
+      }
+      return MCBA_OK;
+    }
     switch (P.model) {
       case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 1) break;
       case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 1) break;
@@ -210,6 +225,7 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
       default: LV(MODEL_FISHEYE, 0, 1) break;
     }
   } else {
+    if (P.motion == MOTION_ROLLING) { ctx->err = "rolling frames are only linearised on the DMMA path (unset MCBA_MOMENTS=fma)"; return MCBA_ERR_UNSUPPORTED; }
     switch (P.model) {
       case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 2) LV(MODEL_STANDARD, 1, 2) break;
       case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 3) LV(MODEL_RATIONAL, 1, 3) LV(MODEL_RATIONAL, 2, 3) break;
@@ -219,19 +235,22 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
     }
   }
 #undef LV
+#undef LR
   return MCBA_OK;
 }
 
 int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a) {
   if (!ctx->use_mma) return launch_views<MODE_MOMENTS>(ctx, P, a);
   const int th = VIEW_WARPS * 32;
-  const int nc = mma_nc(P.model), npair = (nc / 8) * (nc / 8 + 1) / 2;
+  const bool roll = P.motion == MOTION_ROLLING;
+  const int nc = mma_nc(P.model, roll), npair = (nc / 8) * (nc / 8 + 1) / 2;
   const size_t sm = ((size_t)VIEW_WARPS * nc * MMA_KPAD + (size_t)VIEW_WARPS * (2 * npair + 1) * 32) * sizeof(double);
   cudaStream_t s = ctx->stream;
   // few long views (cfg2: 800 views of ~200 corners): let the 4 warps of a CTA share one view
   const bool split = P.V < ctx->num_sms * 16;
   const int blocks = split ? std::max(1, P.V) : std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 16));
-#define LM(MODEL) if (split) k_views_mma<MODEL, VIEW_WARPS><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1><<<blocks, th, sm, s>>>(P, a);
+#define LM(MODEL) if (roll) { if (split) k_views_mma<MODEL, VIEW_WARPS, true><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1, true><<<blocks, th, sm, s>>>(P, a); } \
+                  else { if (split) k_views_mma<MODEL, VIEW_WARPS><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1><<<blocks, th, sm, s>>>(P, a); }
   switch (P.model) {
     case MODEL_STANDARD: LM(MODEL_STANDARD) break;
     case MODEL_RATIONAL: LM(MODEL_RATIONAL) break;
@@ -247,12 +266,12 @@ int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& 
 // DeviceProblem view whose parameter pointers are the trial state
 DeviceProblem with_state(const mcba_ctx* ctx, bool trial) {
   DeviceProblem P = ctx->P;
-  if (trial) { P.cam_rt = ctx->cam_rt2.p; P.board_rt = ctx->board_rt2.p; P.frame_rt = ctx->frame_rt2.p; P.intr = ctx->intr2.p; P.board_pts = ctx->board_pts2.p; }
+  if (trial) { P.cam_rt = ctx->cam_rt2.p; P.board_rt = ctx->board_rt2.p; P.frame_rt = ctx->frame_rt2.p; P.intr = ctx->intr2.p; P.board_pts = ctx->board_pts2.p; P.he_rt = ctx->he_rt2.p; }
   return P;
 }
 
 int prepare(mcba_ctx* ctx, const DeviceProblem& P) {
-  const int np = P.C + P.B + P.F;
+  const int np = P.C + P.B + P.F * P.npf + (P.motion == MOTION_HAND_EYE ? 2 : 0);
   k_prepare<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P, P.cam_rt, P.board_rt, P.frame_rt);
   CKL();
   return MCBA_OK;
@@ -269,8 +288,9 @@ int set_state_from_x(mcba_ctx* ctx, const double* x, bool trial) {
   return prepare(ctx, P);
 }
 
-size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * expf_warp_doubles(P.T, P.D, P.B) + EXP_WARPS * 42); }
-size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exps_warp_doubles(P.T, P.D, P.B) + P.T + 36); }
+size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * expf_warp_doubles(P.T, P.D, P.B, P.npf) + EXP_WARPS * (P.fb * P.fb + P.fb)); }
+size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exps_warp_doubles(P.T, P.D, P.B, P.npf) + P.T + 36); }
+size_t expand_hand_eye_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exph_warp_doubles(P.T, P.D, P.B)); }
 
 // per-view moment records of the (trial or current) state; the pose tables must already describe that state
 int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial) {
@@ -287,11 +307,19 @@ int expand(mcba_ctx* ctx) {
   cudaStream_t s = ctx->stream;
   CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
   CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
+  const bool roll = P.motion == MOTION_ROLLING;
   if (P.motion_on && P.F > 0) {
-    k_expand_frames<<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb); CKL();
+    if (roll) k_expand_frames<2><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+    else k_expand_frames<1><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+    CKL();
   }
   const int nb = P.C * ctx->shared_chunks;
-  k_expand_shared<<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
+  if (roll) k_expand_shared<2><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks);
+  else k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks);
+  CKL();
+  if (P.off_he >= 0 && P.V > 0) {         // hand-eye: the 12 shared motion parameters and their couplings on top (atomics)
+    k_expand_hand_eye<<<nb, EXP_THREADS, expand_hand_eye_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
+  }
   if (P.off_pt >= 0 && P.V > 0) {         // boards=True: board-point blocks on top (atomics)
     ViewKernelArgs a{}; a.loss = ctx->cur_loss; a.f_scale = ctx->cur_f_scale;
     const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
@@ -341,8 +369,11 @@ int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int fin
   const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
   const int fb = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
   if (fb + nsh == 0) return MCBA_OK;
-  k_quad<<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
-                                                      finalize, ctx->counter.p, ctx->red.p, ctx->state.p); CKL();
+  if (P.fb == 12) k_quad<12><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
+                                                                          finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
+  else k_quad<6><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
+                                                             finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
+  CKL();
   return MCBA_OK;
 }
 
@@ -352,31 +383,46 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   DeviceProblem& P = ctx->P;
   P = DeviceProblem{};
   P.C = C; P.F = F; P.B = B; P.P = Pn; P.model = desc->model; P.nd = model_nd(desc->model);
-  P.kint = 5 + P.nd; P.D = model_D(desc->model); P.T = P.D * (P.D + 1) / 2 + P.D + 1;
-  P.N = N; P.V = V;
   const int opt = desc->optimize;
-  P.motion_on = (opt & MCBA_OPT_MOTION) ? 1 : 0;
+  P.motion = (opt & MCBA_MOTION_ROLLING) ? MOTION_ROLLING : (opt & MCBA_MOTION_HAND_EYE) ? MOTION_HAND_EYE : MOTION_STATIC;
+  P.npf = P.motion == MOTION_ROLLING ? 2 : 1;
+  P.fb = P.motion == MOTION_ROLLING ? 12 : P.motion == MOTION_HAND_EYE ? 0 : 6;
+  P.koff = 6 * P.npf;
+  P.kint = 5 + P.nd; P.D = P.koff + 4 + P.nd; P.T = P.D * (P.D + 1) / 2 + P.D + 1;
+  P.N = N; P.V = V;
+  P.motion_on = ((opt & MCBA_OPT_MOTION) && P.fb > 0) ? 1 : 0;
   P.fix_aspect = (opt & MCBA_OPT_FIX_ASPECT) ? 1 : 0;
   int off = 0;
   P.off_cp = (opt & MCBA_OPT_CAMERA_POSES) ? off : -1; if (P.off_cp >= 0) off += 6 * C;
   P.off_bp = (opt & MCBA_OPT_BOARD_POSES) ? off : -1; if (P.off_bp >= 0) off += 6 * B;
   P.off_in = (opt & MCBA_OPT_CAMERAS) ? off : -1; if (P.off_in >= 0) off += P.kint * C;
   P.off_pt = (opt & MCBA_OPT_BOARDS) ? off : -1; if (P.off_pt >= 0) off += 3 * B * Pn;
-  P.n_s = off; P.n_f = P.motion_on ? 6 * F : 0; P.n = P.n_s + P.n_f;
+  P.off_he = (P.motion == MOTION_HAND_EYE && (opt & MCBA_OPT_MOTION)) ? off : -1; if (P.off_he >= 0) off += 12;
+  P.n_s = off; P.n_f = P.motion_on ? P.fb * F : 0; P.n = P.n_s + P.n_f;
+  REQUIRE(P.off_pt < 0 || P.motion == MOTION_STATIC, MCBA_ERR_UNSUPPORTED, "boards=True is only implemented for static frames");
   // internal -> canonical permutation: canonical = [cp | bp | motion | cameras]
   ctx->perm.assign((size_t)P.n, 0);
   {
     int canon = 0;
     if (P.off_cp >= 0) { for (int i = 0; i < 6 * C; i++) ctx->perm[(size_t)P.off_cp + i] = canon + i; canon += 6 * C; }
     if (P.off_bp >= 0) { for (int i = 0; i < 6 * B; i++) ctx->perm[(size_t)P.off_bp + i] = canon + i; canon += 6 * B; }
-    if (P.motion_on) { for (int i = 0; i < 6 * F; i++) ctx->perm[(size_t)P.n_s + i] = canon + i; canon += 6 * F; }
+    // motion block of the reference vector: static [F][6]; rolling [start F x 6 | end F x 6] (rolling_frames.py:135-140) while the
+    // solver keeps a frame's start | end adjacent; hand-eye [world_wrt_base 6 | gripper_wrt_camera 6] (hand_eye.py:76-81)
+    if (P.motion_on) {
+      for (int f = 0; f < F; f++) for (int j = 0; j < P.npf; j++) for (int k = 0; k < 6; k++)
+        ctx->perm[(size_t)P.n_s + (size_t)f * P.fb + 6 * j + k] = canon + j * 6 * F + 6 * f + k;
+      canon += P.fb * F;
+    }
+    if (P.off_he >= 0) { for (int i = 0; i < 12; i++) ctx->perm[(size_t)P.off_he + i] = canon + i; canon += 12; }
     if (P.off_in >= 0) { for (int i = 0; i < P.kint * C; i++) ctx->perm[(size_t)P.off_in + i] = canon + i; canon += P.kint * C; }
     if (P.off_pt >= 0) { for (int i = 0; i < 3 * B * Pn; i++) ctx->perm[(size_t)P.off_pt + i] = canon + i; canon += 3 * B * Pn; }
   }
 
-  CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr.alloc((size_t)C * P.kint));
-  CK(ctx->cam_rt2.alloc((size_t)C * 6)); CK(ctx->board_rt2.alloc((size_t)B * 6)); CK(ctx->frame_rt2.alloc((size_t)std::max(F, 1) * 6)); CK(ctx->intr2.alloc((size_t)C * P.kint));
-  CK(ctx->cam_T.alloc(C)); CK(ctx->frame_T.alloc(std::max(F, 1))); CK(ctx->board_T.alloc(B));
+  const size_t fbs = (size_t)std::max(P.fb, 6);      // doubles per frame in frame_rt and in the per-frame solver blocks
+  CK(ctx->cam_rt.alloc((size_t)C * 6)); CK(ctx->board_rt.alloc((size_t)B * 6)); CK(ctx->frame_rt.alloc((size_t)std::max(F, 1) * fbs)); CK(ctx->intr.alloc((size_t)C * P.kint));
+  CK(ctx->cam_rt2.alloc((size_t)C * 6)); CK(ctx->board_rt2.alloc((size_t)B * 6)); CK(ctx->frame_rt2.alloc((size_t)std::max(F, 1) * fbs)); CK(ctx->intr2.alloc((size_t)C * P.kint));
+  CK(ctx->cam_T.alloc(C)); CK(ctx->frame_T.alloc((size_t)std::max(F, 1) * P.npf)); CK(ctx->board_T.alloc(B));
+  CK(ctx->img_h.alloc(C)); CK(ctx->he_rt.alloc(12)); CK(ctx->he_rt2.alloc(12)); CK(ctx->he_T.alloc(2)); CK(ctx->arm_T.alloc(std::max(F, 1)));
   CK(ctx->board_pts2.alloc((size_t)B * Pn * 3));
   // solver buffers
   ctx->shared_chunks = std::max(1, std::min(32, (ctx->num_sms * 2) / std::max(C, 1)));
@@ -384,10 +430,10 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->moments.alloc((size_t)std::max(V, 1) * P.T));
   CK(ctx->Hss.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1)));
   CK(ctx->g.alloc((size_t)std::max(P.n, 1)));
-  CK(ctx->Hff.alloc((size_t)std::max(F, 1) * 36));
-  CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
-  CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * 6));
-  CK(ctx->Lf.alloc((size_t)std::max(F, 1) * 36)); CK(ctx->zf.alloc((size_t)std::max(F, 1) * 6));
+  CK(ctx->Hff.alloc((size_t)std::max(F, 1) * fbs * fbs));
+  CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * fbs));
+  CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * fbs));
+  CK(ctx->Lf.alloc((size_t)std::max(F, 1) * fbs * fbs)); CK(ctx->zf.alloc((size_t)std::max(F, 1) * fbs));
   CK(ctx->cost_part.alloc((size_t)C * ctx->shared_chunks)); CK(ctx->view_cost.alloc((size_t)std::max(V, 1)));
   CK(ctx->diag_s.alloc((size_t)std::max(P.n_s, 1)));
   const size_t nn = (size_t)std::max(P.n, 1);
@@ -401,8 +447,18 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   if (!keep_state) {     // a re-selection of the resident table (mcba_table_select) keeps the parameter state
     CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
     CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
-    CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * 6, ctx->stream));
+    CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * fbs, ctx->stream));
     CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
+    // motion-model state: identity arm / hand-eye poses, unit image heights until mcba_set_rolling / mcba_set_hand_eye
+    CK(cudaMemsetAsync(ctx->he_rt.p, 0, sizeof(double) * 12, ctx->stream));
+    {
+      std::vector<double> ones((size_t)C, 1.0);
+      CK(cudaMemcpyAsync(ctx->img_h.p, ones.data(), sizeof(double) * C, cudaMemcpyHostToDevice, ctx->stream));
+      PoseT id{}; id.R[0] = id.R[4] = id.R[8] = 1.0;
+      std::vector<PoseT> arms((size_t)std::max(F, 1), id);
+      CK(cudaMemcpyAsync(ctx->arm_T.p, arms.data(), sizeof(PoseT) * arms.size(), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
   }
 
   P.obs = ctx->obs.p; P.pid = ctx->pid.p; P.orig = ctx->orig.p;
@@ -411,6 +467,8 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   P.board_pts = ctx->board_pts.p;
   P.cam_rt = ctx->cam_rt.p; P.board_rt = ctx->board_rt.p; P.frame_rt = ctx->frame_rt.p; P.intr = ctx->intr.p;
   P.cam_T = ctx->cam_T.p; P.frame_T = ctx->frame_T.p; P.board_T = ctx->board_T.p;
+  P.img_h = ctx->img_h.p; P.he_rt = ctx->he_rt.p; P.he_T = ctx->he_T.p; P.arm_T = ctx->arm_T.p;
+  REQUIRE(expand_hand_eye_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the hand-eye expand kernel");
   REQUIRE(expand_frames_smem(P) <= 200 * 1024 && expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
   return MCBA_OK;
 }
@@ -418,6 +476,7 @@ int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
   REQUIRE(desc->C > 0 && desc->F >= 0 && desc->B > 0 && desc->P > 0, MCBA_ERR_ARG, "bad problem dimensions");
   REQUIRE(desc->P <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
   REQUIRE(desc->model >= 0 && desc->model <= 4, MCBA_ERR_ARG, "unknown camera model");
+  REQUIRE(!((desc->optimize & MCBA_MOTION_ROLLING) && (desc->optimize & MCBA_MOTION_HAND_EYE)), MCBA_ERR_ARG, "more than one motion model");
   REQUIRE((int64_t)desc->C * desc->F * desc->B * desc->P < ((int64_t)1 << 31), MCBA_ERR_UNSUPPORTED, "more than 2^31 table entries per rank");
   return MCBA_OK;
 }
@@ -484,18 +543,18 @@ int mcba_create(int device, mcba_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
   { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
-  cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_THIN_PRISM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_STANDARD, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_RATIONAL, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_THIN_PRISM, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_FISHEYE, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_TILTED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_views_mma<MODEL_TILTED, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_expand_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+#define MMA_ATTR(MODEL) \
+  cudaFuncSetAttribute(k_views_mma<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+  cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+  cudaFuncSetAttribute(k_views_mma<MODEL, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+  cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  MMA_ATTR(MODEL_STANDARD) MMA_ATTR(MODEL_RATIONAL) MMA_ATTR(MODEL_THIN_PRISM) MMA_ATTR(MODEL_FISHEYE) MMA_ATTR(MODEL_TILTED)
+#undef MMA_ATTR
+  cudaFuncSetAttribute(k_expand_frames<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_frames<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_shared<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_shared<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_hand_eye, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_chol_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_chol_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(k_chol_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -906,13 +965,13 @@ int mcba_table_reject(mcba_ctx* ctx, double threshold, int64_t* n_valid, int64_t
 int mcba_set_params(mcba_ctx* ctx, const double* cam_rt, const double* board_rt, const double* frame_rt, const double* intrinsics) {
   if (!ctx) return MCBA_ERR_ARG;
   REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
-  REQUIRE(cam_rt && board_rt && intrinsics && (frame_rt || ctx->P.F == 0), MCBA_ERR_ARG, "null parameter array");
+  REQUIRE(cam_rt && board_rt && intrinsics && (frame_rt || ctx->P.F == 0 || ctx->P.fb == 0), MCBA_ERR_ARG, "null parameter array");
   const DeviceProblem& P = ctx->P;
   CK(cudaSetDevice(ctx->device));
   ctx->errors_current = false;
   CK(cudaMemcpyAsync(ctx->cam_rt.p, cam_rt, sizeof(double) * P.C * 6, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->board_rt.p, board_rt, sizeof(double) * P.B * 6, cudaMemcpyHostToDevice, ctx->stream));
-  if (P.F) CK(cudaMemcpyAsync(ctx->frame_rt.p, frame_rt, sizeof(double) * P.F * 6, cudaMemcpyHostToDevice, ctx->stream));
+  if (P.F && P.fb) CK(cudaMemcpyAsync(ctx->frame_rt.p, frame_rt, sizeof(double) * P.F * P.fb, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->intr.p, intrinsics, sizeof(double) * P.C * P.kint, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MCBA_OK;
@@ -931,7 +990,7 @@ int mcba_set_state_matrices(mcba_ctx* ctx, const double* mats, const double* int
   CK(ctx->pose_mats.alloc((size_t)np * 16));
   CK(cudaMemcpyAsync(ctx->pose_mats.p, mats, sizeof(double) * 16 * np, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->intr.p, intrinsics, sizeof(double) * P.C * P.kint, cudaMemcpyHostToDevice, ctx->stream));
-  k_matrices_to_state<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P.C, P.B, P.F, ctx->pose_mats.p, P.cam_rt, P.board_rt, P.frame_rt); CKL();
+  k_matrices_to_state<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P.C, P.B, P.F, ctx->pose_mats.p, P.cam_rt, P.board_rt, P.frame_rt, P.fb); CKL();
   CK(cudaStreamSynchronize(ctx->stream));     // the host arrays are borrowed only for the call
   return MCBA_OK;
 }
@@ -944,10 +1003,89 @@ int mcba_get_state_matrices(mcba_ctx* ctx, double* mats, double* intrinsics) {
   const int np = P.C + P.B + P.F;
   if (mats) {
     CK(ctx->pose_mats.alloc((size_t)np * 16));
-    k_state_to_matrices<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P.C, P.B, P.F, P.cam_rt, P.board_rt, P.frame_rt, ctx->pose_mats.p); CKL();
+    const PoseT* derived = nullptr;
+    if (P.motion == MOTION_HAND_EYE) { int r = prepare(ctx, with_state(ctx, false)); if (r) return r; derived = P.frame_T; }
+    k_state_to_matrices<<<(np + 127) / 128, 128, 0, ctx->stream>>>(P.C, P.B, P.F, P.cam_rt, P.board_rt, P.frame_rt, ctx->pose_mats.p, P.fb, derived); CKL();
     CK(cudaMemcpyAsync(mats, ctx->pose_mats.p, sizeof(double) * 16 * np, cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (intrinsics) CK(cudaMemcpyAsync(intrinsics, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+// RollingFrames (motion/rolling_frames.py:66-150): the frames of mcba_set_state_matrices are the start poses; the end poses
+// f64[F][4][4] and the image heights f64[C] that turn an observed row into the blend weight (rolling_times, 15-19) come here.
+int mcba_set_rolling(mcba_ctx* ctx, const double* end_pose_matrices, const double* image_heights) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  REQUIRE(P.motion == MOTION_ROLLING, MCBA_ERR_STATE, "the problem was not uploaded with MCBA_MOTION_ROLLING");
+  REQUIRE((end_pose_matrices || P.F == 0) && image_heights, MCBA_ERR_ARG, "null parameter array");
+  for (int c = 0; c < P.C; c++) REQUIRE(image_heights[c] > 0, MCBA_ERR_ARG, "image heights must be positive");
+  CK(cudaSetDevice(ctx->device));
+  ctx->errors_current = false;
+  CK(cudaMemcpyAsync(ctx->img_h.p, image_heights, sizeof(double) * P.C, cudaMemcpyHostToDevice, ctx->stream));
+  if (P.F) {
+    CK(ctx->pose_mats.alloc((size_t)P.F * 16));
+    CK(cudaMemcpyAsync(ctx->pose_mats.p, end_pose_matrices, sizeof(double) * 16 * P.F, cudaMemcpyHostToDevice, ctx->stream));
+    // "cameras = 0, boards = 0, frames = F" view of the same kernel, writing the second half of every frame block
+    k_matrices_to_state<<<(P.F + 127) / 128, 128, 0, ctx->stream>>>(0, 0, P.F, ctx->pose_mats.p, nullptr, nullptr, P.frame_rt + 6, 12); CKL();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_get_rolling(mcba_ctx* ctx, double* end_pose_matrices) {
+  if (!ctx || !end_pose_matrices) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  REQUIRE(P.motion == MOTION_ROLLING, MCBA_ERR_STATE, "the problem was not uploaded with MCBA_MOTION_ROLLING");
+  CK(cudaSetDevice(ctx->device));
+  if (P.F) {
+    CK(ctx->pose_mats.alloc((size_t)P.F * 16));
+    k_state_to_matrices<<<(P.F + 127) / 128, 128, 0, ctx->stream>>>(0, 0, P.F, nullptr, nullptr, P.frame_rt + 6, ctx->pose_mats.p, 12, nullptr); CKL();
+    CK(cudaMemcpyAsync(end_pose_matrices, ctx->pose_mats.p, sizeof(double) * 16 * P.F, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+// HandEye (motion/hand_eye.py:14-90): frame pose f = gripper_wrt_camera base_wrt_gripper[f] world_wrt_base; the arm poses are
+// constants, the two outer transforms are the 12 motion parameters.  The frames of mcba_set_state_matrices are ignored.
+int mcba_set_hand_eye(mcba_ctx* ctx, const double* base_wrt_gripper, const double* world_wrt_base, const double* gripper_wrt_camera) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  REQUIRE(P.motion == MOTION_HAND_EYE, MCBA_ERR_STATE, "the problem was not uploaded with MCBA_MOTION_HAND_EYE");
+  REQUIRE((base_wrt_gripper || P.F == 0) && world_wrt_base && gripper_wrt_camera, MCBA_ERR_ARG, "null parameter array");
+  CK(cudaSetDevice(ctx->device));
+  ctx->errors_current = false;
+  std::vector<PoseT> arms((size_t)std::max(P.F, 1));
+  for (int f = 0; f < P.F; f++) {
+    const double* M = base_wrt_gripper + (size_t)16 * f;
+    PoseT t{};
+    for (int r = 0; r < 3; r++) { t.R[3 * r] = M[4 * r]; t.R[3 * r + 1] = M[4 * r + 1]; t.R[3 * r + 2] = M[4 * r + 2]; t.t[r] = M[4 * r + 3]; }
+    arms[(size_t)f] = t;
+  }
+  CK(cudaMemcpyAsync(ctx->arm_T.p, arms.data(), sizeof(PoseT) * arms.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->pose_mats.alloc(32));
+  CK(cudaMemcpyAsync(ctx->pose_mats.p, world_wrt_base, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pose_mats.p + 16, gripper_wrt_camera, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  k_matrices_to_state<<<1, 128, 0, ctx->stream>>>(0, 0, 2, ctx->pose_mats.p, nullptr, nullptr, P.he_rt, 6); CKL();
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
+int mcba_get_hand_eye(mcba_ctx* ctx, double* world_wrt_base, double* gripper_wrt_camera) {
+  if (!ctx) return MCBA_ERR_ARG;
+  REQUIRE(ctx->uploaded, MCBA_ERR_STATE, "mcba_upload has not been called");
+  const DeviceProblem& P = ctx->P;
+  REQUIRE(P.motion == MOTION_HAND_EYE, MCBA_ERR_STATE, "the problem was not uploaded with MCBA_MOTION_HAND_EYE");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->pose_mats.alloc(32));
+  k_state_to_matrices<<<1, 128, 0, ctx->stream>>>(0, 0, 2, nullptr, nullptr, P.he_rt, ctx->pose_mats.p, 6, nullptr); CKL();
+  if (world_wrt_base) CK(cudaMemcpyAsync(world_wrt_base, ctx->pose_mats.p, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gripper_wrt_camera) CK(cudaMemcpyAsync(gripper_wrt_camera, ctx->pose_mats.p + 16, sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MCBA_OK;
 }
@@ -959,7 +1097,7 @@ int mcba_get_params(mcba_ctx* ctx, double* cam_rt, double* board_rt, double* fra
   CK(cudaSetDevice(ctx->device));
   if (cam_rt) CK(cudaMemcpyAsync(cam_rt, ctx->cam_rt.p, sizeof(double) * P.C * 6, cudaMemcpyDeviceToHost, ctx->stream));
   if (board_rt) CK(cudaMemcpyAsync(board_rt, ctx->board_rt.p, sizeof(double) * P.B * 6, cudaMemcpyDeviceToHost, ctx->stream));
-  if (frame_rt && P.F) CK(cudaMemcpyAsync(frame_rt, ctx->frame_rt.p, sizeof(double) * P.F * 6, cudaMemcpyDeviceToHost, ctx->stream));
+  if (frame_rt && P.F && P.fb) CK(cudaMemcpyAsync(frame_rt, ctx->frame_rt.p, sizeof(double) * P.F * P.fb, cudaMemcpyDeviceToHost, ctx->stream));
   if (intrinsics) CK(cudaMemcpyAsync(intrinsics, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return MCBA_OK;
@@ -1020,7 +1158,8 @@ int mcba_residuals(mcba_ctx* ctx, const double* x, double* r_out, double* cost) 
     // evaluate at x without disturbing the stored parameters: trial state = current state overwritten by x
     CK(cudaMemcpyAsync(ctx->cam_rt2.p, ctx->cam_rt.p, sizeof(double) * P0.C * 6, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->board_rt2.p, ctx->board_rt.p, sizeof(double) * P0.B * 6, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (P0.F) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P0.F * 6, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (P0.F && P0.fb) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P0.F * P0.fb, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->he_rt2.p, ctx->he_rt.p, sizeof(double) * 12, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P0.C * P0.kint, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->board_pts2.p, ctx->board_pts.p, sizeof(double) * P0.B * P0.P * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     int r = write_x_canonical(ctx, x, ctx->x_new.p); if (r) return r;
@@ -1069,7 +1208,8 @@ int mcba_linearize(mcba_ctx* ctx, const double* x, double* JtJ, double* Jtr, dou
   else { int r = prepare(ctx, with_state(ctx, false)); if (r) return r; }
   int r = linearize(ctx, 0, 1.0); if (r) return r;
   const int n = P.n, n_s = P.n_s, F = P.motion_on ? P.F : 0;
-  std::vector<double> hHss((size_t)n_s * n_s), hg((size_t)n), hHff((size_t)F * 36), hW((size_t)F * n_s * 6);
+  const int fb = P.fb;
+  std::vector<double> hHss((size_t)n_s * n_s), hg((size_t)n), hHff((size_t)F * fb * fb), hW((size_t)F * n_s * fb);
   if (n_s) CK(cudaMemcpyAsync(hHss.data(), ctx->Hss.p, sizeof(double) * hHss.size(), cudaMemcpyDeviceToHost, ctx->stream));
   if (n) CK(cudaMemcpyAsync(hg.data(), ctx->g.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   if (F) CK(cudaMemcpyAsync(hHff.data(), ctx->Hff.p, sizeof(double) * hHff.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1082,11 +1222,11 @@ int mcba_linearize(mcba_ctx* ctx, const double* x, double* JtJ, double* Jtr, dou
     std::fill(JtJ, JtJ + (size_t)n * n, 0.0);
     for (int i = 0; i < n_s; i++) for (int j = 0; j < n_s; j++) JtJ[(size_t)pm[i] * n + pm[j]] = hHss[(size_t)i * n_s + j];
     for (int f = 0; f < F; f++) {
-      for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) JtJ[(size_t)pm[n_s + 6 * f + i] * n + pm[n_s + 6 * f + j]] = hHff[(size_t)f * 36 + i * 6 + j];
-      for (int s = 0; s < n_s; s++) for (int j = 0; j < 6; j++) {
-        const double w = hW[((size_t)f * n_s + s) * 6 + j];
-        JtJ[(size_t)pm[s] * n + pm[n_s + 6 * f + j]] = w;
-        JtJ[(size_t)pm[n_s + 6 * f + j] * n + pm[s]] = w;
+      for (int i = 0; i < fb; i++) for (int j = 0; j < fb; j++) JtJ[(size_t)pm[n_s + fb * f + i] * n + pm[n_s + fb * f + j]] = hHff[((size_t)f * fb + i) * fb + j];
+      for (int s = 0; s < n_s; s++) for (int j = 0; j < fb; j++) {
+        const double w = hW[((size_t)f * n_s + s) * fb + j];
+        JtJ[(size_t)pm[s] * n + pm[n_s + fb * f + j]] = w;
+        JtJ[(size_t)pm[n_s + fb * f + j] * n + pm[s]] = w;
       }
     }
   }
@@ -1145,11 +1285,11 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   while (!finished) {
     if (single) {
       k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
-                                 1, ctx->cost_part.p, ncp, ctx->state.p); CKL();
+                                 1, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1)); CKL();
     } else {
       r = finish_linearization(ctx); if (r) return r;
       k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
-                                 0, nullptr, 0, ctx->state.p); CKL();
+                                 0, nullptr, 0, ctx->state.p, std::max(P.fb, 1)); CKL();
       EXCHANGE(ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1); ex_.epilogue = EPI_BEGIN);
     }
     first = 0;
@@ -1173,14 +1313,20 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       k_schur_init<<<(unsigned)((nn2 + 255) / 256), 256, 0, s>>>(n_s, ctx->Hss.p, ctx->d.p, ctx->S.p, ctx->rhs.p); CKL();
     }
     if (F > 0) {
-      k_schur_frames<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p,
-                                                   ctx->Hss.p, ctx->S.p, ctx->rhs.p); CKL();
+      if (P.fb == 12) k_schur_frames<12><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p,
+                                                                      ctx->Hss.p, ctx->S.p, ctx->rhs.p);
+      else k_schur_frames<6><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p,
+                                                         ctx->Hss.p, ctx->S.p, ctx->rhs.p);
+      CKL();
       if (n_s > 0) {
+        const int SYRK_FR = syrk_fr(P.fb);
         const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
         int chunks = std::max(1, std::min((F + SYRK_FR - 1) / SYRK_FR, (ctx->num_sms * 4) / std::max(1, tiles * (tiles + 1) / 2)));
         const int cf = ((F + chunks - 1) / chunks + SYRK_FR - 1) / SYRK_FR * SYRK_FR;
         chunks = (F + cf - 1) / cf;
-        k_schur_syrk<<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p, ctx->zf.p, ctx->rhs.p); CKL();
+        if (P.fb == 12) k_schur_syrk<12><<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p, ctx->zf.p, ctx->rhs.p);
+        else k_schur_syrk<6><<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p, ctx->zf.p, ctx->rhs.p);
+        CKL();
       }
     }
     if (n_s > 0) {
@@ -1207,7 +1353,11 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         k_chol_substitute<<<1, 512, (size_t)nblk * CHOL_NB * sizeof(double), s>>>(n_s, ctx->S.p, ctx->Linv.p, ctx->rhs.p, ctx->gh.p, ctx->gn.p); CKL();
       }
     }
-    if (F > 0) { k_backsub<<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p); CKL(); }
+    if (F > 0) {
+      if (P.fb == 12) k_backsub<12><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p);
+      else k_backsub<6><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p);
+      CKL();
+    }
     k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
     r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1); if (r) return r;
     EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE);   // AGG AGN ANN DOTGN_F GN2_F
@@ -1218,8 +1368,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     while (true) {
       k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
       {
-        const int nt = P.C + P.B + P.F + P.C + P.B * P.P;
-        k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p); CKL();
+        const int nt = P.C + P.B + P.F * P.npf + P.C + P.B * P.P + 2;
+        k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p, ctx->he_rt2.p); CKL();
       }
       r = moments_at(ctx, opts->loss, opts->f_scale, true); if (r) return r;
       if (single) {
@@ -1252,6 +1402,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       std::swap(ctx->x.p, ctx->x_new.p);
       std::swap(ctx->cam_rt.p, ctx->cam_rt2.p); std::swap(ctx->board_rt.p, ctx->board_rt2.p);
       std::swap(ctx->frame_rt.p, ctx->frame_rt2.p); std::swap(ctx->intr.p, ctx->intr2.p); std::swap(ctx->board_pts.p, ctx->board_pts2.p);
+      std::swap(ctx->he_rt.p, ctx->he_rt2.p); ctx->P.he_rt = ctx->he_rt.p;
       ctx->P.board_pts = ctx->board_pts.p;
       ctx->P.cam_rt = ctx->cam_rt.p; ctx->P.board_rt = ctx->board_rt.p; ctx->P.frame_rt = ctx->frame_rt.p; ctx->P.intr = ctx->intr.p;
       h.cost = h.cost_new;

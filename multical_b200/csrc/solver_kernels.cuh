@@ -106,14 +106,14 @@ __global__ void k_begin_iteration(SolverState* st, double* red) { begin_iteratio
 // runs the begin-of-iteration logic itself; with several ranks those three need all-reduces in between.
 __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss, const double* Hff, const double* g, const double* x,
                         double* sinv, double* d, double* gh, int first, double* red,
-                        int fused, const double* cost_part, int n_cost_part, SolverState* st) {
+                        int fused, const double* cost_part, int n_cost_part, SolverState* st, int fb) {
   __shared__ double sm[32];
   if (fused && st->done) return;
   double gh2s = 0, gh2f = 0, gms = 0, gmf = 0, xs2s = 0, xs2f = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double hd;
     if (i < n_s) hd = fused ? Hss[(size_t)i * n_s + i] : diag_s[i];
-    else { const int f = (i - n_s) / 6, j = (i - n_s) % 6; hd = Hff[(size_t)f * 36 + j * 7]; }
+    else { const int f = (i - n_s) / fb, j = (i - n_s) % fb; hd = Hff[(size_t)f * fb * fb + j * (fb + 1)]; }
     double nrm = sqrt(fmax(hd, 0.0));
     double si;
     if (first) si = (nrm == 0.0) ? 1.0 : nrm; else si = fmax(nrm, sinv[i]);
@@ -149,7 +149,8 @@ constexpr int QUAD_THREADS = 128;
 constexpr int QUAD_WARPS = QUAD_THREADS / 32;
 // blocks [0, frame_blocks): one WARP per frame (W_f^T u_s by lane-strided sums + shuffles, then the 6x6 part);
 // remaining blocks: one thread per shared row (column walk of the symmetric H_ss is coalesced).
-// partial[frame or F + shared block][3]
+// partial[frame or F + shared block][3].  FB = parameters per frame block (6; 12 for RollingFrames' start+end pose)
+template <int FB>
 __global__ void __launch_bounds__(QUAD_THREADS)
 k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, const double* W, const double* d,
        const double* u, const double* v, int two, double* partial,
@@ -162,28 +163,30 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
   if ((int)blockIdx.x < frame_blocks) {
     const int f = blockIdx.x * QUAD_WARPS + warp;
     if (f < nframe) {
-      const double* Wf = W + (size_t)f * n_s * 6;
-      double tu[6] = {0, 0, 0, 0, 0, 0}, tv[6] = {0, 0, 0, 0, 0, 0};
+      const double* Wf = W + (size_t)f * n_s * FB;
+      double tu[FB], tv[FB];
+#pragma unroll
+      for (int j = 0; j < FB; j++) { tu[j] = 0.0; tv[j] = 0.0; }
       for (int s = lane; s < n_s; s += 32) {
         const double us = d[s] * u[s], vs = two ? d[s] * v[s] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 6; j++) { const double w = Wf[s * 6 + j]; tu[j] += w * us; tv[j] += w * vs; }
+        for (int j = 0; j < FB; j++) { const double w = Wf[s * FB + j]; tu[j] += w * us; tv[j] += w * vs; }
       }
 #pragma unroll
-      for (int j = 0; j < 6; j++) {
+      for (int j = 0; j < FB; j++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { tu[j] += __shfl_xor_sync(0xffffffffu, tu[j], o); tv[j] += __shfl_xor_sync(0xffffffffu, tv[j], o); }
       }
       if (lane == 0) {
-        double uf[6], vf[6], uu = 0, uv = 0, vv = 0;
+        double uf[FB], vf[FB], uu = 0, uv = 0, vv = 0;
 #pragma unroll
-        for (int j = 0; j < 6; j++) { const int i = n_s + 6 * f + j; uf[j] = d[i] * u[i]; vf[j] = two ? d[i] * v[i] : 0.0; }
-        const double* H = Hff + (size_t)f * 36;
+        for (int j = 0; j < FB; j++) { const int i = n_s + FB * f + j; uf[j] = d[i] * u[i]; vf[j] = two ? d[i] * v[i] : 0.0; }
+        const double* H = Hff + (size_t)f * FB * FB;
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < FB; i++) {
           double hu = 0, hv = 0;
 #pragma unroll
-          for (int j = 0; j < 6; j++) { hu += H[i * 6 + j] * uf[j]; hv += H[i * 6 + j] * vf[j]; }
+          for (int j = 0; j < FB; j++) { hu += H[i * FB + j] * uf[j]; hv += H[i * FB + j] * vf[j]; }
           uu += uf[i] * (hu + 2.0 * tu[i]);
           uv += uf[i] * hv + uf[i] * tv[i] + vf[i] * tu[i];
           vv += vf[i] * (hv + 2.0 * tv[i]);
@@ -254,11 +257,12 @@ __global__ void k_reg(SolverState* st, const double* red) { reg_compute(st, red)
 
 // per frame: L L^T = D_f H_ff D_f + reg I ; Y_f = (D_s W_f D_f) L^-T (n_s x 6) ; z_f = L^-1 (D_f g_f)
 constexpr int SCHUR_THREADS = 128;
+template <int FB>
 __global__ void __launch_bounds__(SCHUR_THREADS)
 k_schur_frames(int n_s, const double* Hff, const double* W, const double* d, const double* gh,
                const SolverState* st, double* Y, double* Lf, double* zf, const double* Hss, double* S, double* rhs) {
-  __shared__ double L[36];
-  __shared__ double df[6];
+  __shared__ double L[FB * FB];
+  __shared__ double df[FB];
   const int f = blockIdx.x, tid = threadIdx.x;
   // S_local = D_s H_ss D_s, rhs_local = 0 (grid-stride; the SYRK kernel that follows subtracts sum_f Y_f Y_f^T)
   for (size_t idx = (size_t)blockIdx.x * SCHUR_THREADS + tid; idx < (size_t)n_s * n_s; idx += (size_t)gridDim.x * SCHUR_THREADS) {
@@ -268,46 +272,46 @@ k_schur_frames(int n_s, const double* Hff, const double* W, const double* d, con
   }
   if (tid == 0) {
     const double reg = st->reg;
-    const double* H = Hff + (size_t)f * 36;
-    double A[36];
-    for (int j = 0; j < 6; j++) df[j] = d[n_s + 6 * f + j];
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) A[i * 6 + j] = df[i] * df[j] * H[i * 6 + j] + (i == j ? reg : 0.0);
-    for (int j = 0; j < 6; j++) {
-      double s = A[j * 6 + j];
-      for (int k = 0; k < j; k++) s -= L[j * 6 + k] * L[j * 6 + k];
+    const double* H = Hff + (size_t)f * FB * FB;
+    double A[FB * FB];
+    for (int j = 0; j < FB; j++) df[j] = d[n_s + FB * f + j];
+    for (int i = 0; i < FB; i++) for (int j = 0; j < FB; j++) A[i * FB + j] = df[i] * df[j] * H[i * FB + j] + (i == j ? reg : 0.0);
+    for (int j = 0; j < FB; j++) {
+      double s = A[j * FB + j];
+      for (int k = 0; k < j; k++) s -= L[j * FB + k] * L[j * FB + k];
       const double piv = sqrt(fmax(s, 1e-300));
-      L[j * 6 + j] = piv;
-      for (int i = j + 1; i < 6; i++) {
-        double t = A[i * 6 + j];
-        for (int k = 0; k < j; k++) t -= L[i * 6 + k] * L[j * 6 + k];
-        L[i * 6 + j] = t / piv;
+      L[j * FB + j] = piv;
+      for (int i = j + 1; i < FB; i++) {
+        double t = A[i * FB + j];
+        for (int k = 0; k < j; k++) t -= L[i * FB + k] * L[j * FB + k];
+        L[i * FB + j] = t / piv;
       }
-      for (int i = 0; i < j; i++) L[i * 6 + j] = 0.0;
+      for (int i = 0; i < j; i++) L[i * FB + j] = 0.0;
     }
-    double z[6];
-    for (int i = 0; i < 6; i++) {
-      double t = gh[n_s + 6 * f + i];
-      for (int k = 0; k < i; k++) t -= L[i * 6 + k] * z[k];
-      z[i] = t / L[i * 6 + i];
-      zf[(size_t)f * 6 + i] = z[i];
+    double z[FB];
+    for (int i = 0; i < FB; i++) {
+      double t = gh[n_s + FB * f + i];
+      for (int k = 0; k < i; k++) t -= L[i * FB + k] * z[k];
+      z[i] = t / L[i * FB + i];
+      zf[(size_t)f * FB + i] = z[i];
     }
-    for (int i = 0; i < 36; i++) Lf[(size_t)f * 36 + i] = L[i];
+    for (int i = 0; i < FB * FB; i++) Lf[(size_t)f * FB * FB + i] = L[i];
   }
   __syncthreads();
-  const double* Wf = W + (size_t)f * n_s * 6;
-  double* Yf = Y + (size_t)f * n_s * 6;
+  const double* Wf = W + (size_t)f * n_s * FB;
+  double* Yf = Y + (size_t)f * n_s * FB;
   for (int s = tid; s < n_s; s += SCHUR_THREADS) {
     const double ds = d[s];
-    double y[6];
+    double y[FB];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      double t = ds * Wf[s * 6 + i] * df[i];
+    for (int i = 0; i < FB; i++) {
+      double t = ds * Wf[s * FB + i] * df[i];
 #pragma unroll
-      for (int k = 0; k < i; k++) t -= L[i * 6 + k] * y[k];
-      y[i] = t / L[i * 6 + i];
+      for (int k = 0; k < i; k++) t -= L[i * FB + k] * y[k];
+      y[i] = t / L[i * FB + i];
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) Yf[s * 6 + i] = y[i];
+    for (int i = 0; i < FB; i++) Yf[s * FB + i] = y[i];
   }
 }
 
@@ -319,11 +323,14 @@ __global__ void k_schur_init(int n_s, const double* Hss, const double* d, double
 }
 
 // S -= sum_f Y_f Y_f^T over this CTA's frame chunk; 32x32 output tile per CTA, 2x2 micro-tile per thread.
-constexpr int SYRK_TILE = 32, SYRK_FR = 8;
+constexpr int SYRK_TILE = 32;
+__host__ __device__ constexpr int syrk_fr(int fb) { return 48 / fb; }       // frames staged per step: 2 x 12 KB of shared memory
+template <int FB>
 __global__ void __launch_bounds__(256)
 k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S, const double* zf, double* rhs) {
-  __shared__ double Yi[SYRK_FR][SYRK_TILE][6];
-  __shared__ double Yj[SYRK_FR][SYRK_TILE][6];
+  constexpr int SYRK_FR = syrk_fr(FB);
+  __shared__ double Yi[SYRK_FR][SYRK_TILE][FB];
+  __shared__ double Yj[SYRK_FR][SYRK_TILE][FB];
   const int ti = blockIdx.y, tj = blockIdx.x;
   if (tj < ti) return;
   const int f0 = blockIdx.z * chunk_frames, f1 = min(F, f0 + chunk_frames);
@@ -332,25 +339,25 @@ k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S, const
   double racc = 0.0;                     // diagonal tiles also accumulate rhs -= Y_f z_f for their 32 rows
   for (int fb = f0; fb < f1; fb += SYRK_FR) {
     const int nf = min(SYRK_FR, f1 - fb);
-    for (int o = threadIdx.x; o < SYRK_FR * SYRK_TILE * 6; o += 256) {
-      const int ff = o / (SYRK_TILE * 6), rem = o % (SYRK_TILE * 6), r = rem / 6, k = rem % 6;
+    for (int o = threadIdx.x; o < SYRK_FR * SYRK_TILE * FB; o += 256) {
+      const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
       const int gi = ti * SYRK_TILE + r, gj = tj * SYRK_TILE + r;
-      (&Yi[0][0][0])[o] = (ff < nf && gi < n_s) ? Y[((size_t)(fb + ff) * n_s + gi) * 6 + k] : 0.0;
-      (&Yj[0][0][0])[o] = (ff < nf && gj < n_s) ? Y[((size_t)(fb + ff) * n_s + gj) * 6 + k] : 0.0;
+      (&Yi[0][0][0])[o] = (ff < nf && gi < n_s) ? Y[((size_t)(fb + ff) * n_s + gi) * FB + k] : 0.0;
+      (&Yj[0][0][0])[o] = (ff < nf && gj < n_s) ? Y[((size_t)(fb + ff) * n_s + gj) * FB + k] : 0.0;
     }
     __syncthreads();
     for (int ff = 0; ff < nf; ff++) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) {
+      for (int k = 0; k < FB; k++) {
         const double a0 = Yi[ff][ty][k], a1 = Yi[ff][ty + 16][k], b0 = Yj[ff][tx][k], b1 = Yj[ff][tx + 16][k];
         acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
       }
     }
     if (ti == tj && threadIdx.x < SYRK_TILE) {
       for (int ff = 0; ff < nf; ff++) {
-        const double* z = zf + (size_t)(fb + ff) * 6;
+        const double* z = zf + (size_t)(fb + ff) * FB;
 #pragma unroll
-        for (int k = 0; k < 6; k++) racc += Yi[ff][threadIdx.x][k] * z[k];
+        for (int k = 0; k < FB; k++) racc += Yi[ff][threadIdx.x][k] * z[k];
       }
     }
     __syncthreads();
@@ -369,21 +376,6 @@ k_schur_syrk(int n_s, int F, int chunk_frames, const double* Y, double* S, const
         if (i != j) atomicAdd(&S[(size_t)j * n_s + i], -acc[a][b]);
       }
     }
-}
-
-// rhs -= sum_f Y_f z_f   (thread per shared row, frame chunks over blockIdx.y)
-__global__ void k_schur_rhs(int n_s, int F, int chunk_frames, const double* Y, const double* zf, double* rhs) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_s) return;
-  const int f0 = blockIdx.y * chunk_frames, f1 = min(F, f0 + chunk_frames);
-  double acc = 0.0;
-  for (int f = f0; f < f1; f++) {
-    const double* y = Y + ((size_t)f * n_s + s) * 6;
-    const double* z = zf + (size_t)f * 6;
-#pragma unroll
-    for (int k = 0; k < 6; k++) acc += y[k] * z[k];
-  }
-  atomicAdd(&rhs[s], -acc);
 }
 
 // Dense SPD solve of the reduced (shared-parameter) system   (S + reg I) p_s = rhs + D_s g_s  -> gn[0..n_s)
@@ -693,30 +685,33 @@ k_chol_substitute(int n, const double* L, const double* Linv_all, const double* 
 }
 
 // back-substitution of the eliminated frame blocks: gn_f = L^-T (z_f - Y_f^T gn_s)
+template <int FB>
 __global__ void __launch_bounds__(SCHUR_THREADS)
 k_backsub(int n_s, const double* Y, const double* Lf, const double* zf, double* gn) {
   __shared__ double sm[32];
-  __shared__ double t[6];
+  __shared__ double t[FB];
   const int f = blockIdx.x, tid = threadIdx.x;
-  const double* Yf = Y + (size_t)f * n_s * 6;
-  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const double* Yf = Y + (size_t)f * n_s * FB;
+  double acc[FB];
+#pragma unroll
+  for (int k = 0; k < FB; k++) acc[k] = 0.0;
   for (int s = tid; s < n_s; s += SCHUR_THREADS) {
     const double ps = gn[s];
 #pragma unroll
-    for (int k = 0; k < 6; k++) acc[k] += Yf[s * 6 + k] * ps;
+    for (int k = 0; k < FB; k++) acc[k] += Yf[s * FB + k] * ps;
   }
 #pragma unroll
-  for (int k = 0; k < 6; k++) { const double r = block_sum(acc[k], sm); if (tid == 0) t[k] = r; }
+  for (int k = 0; k < FB; k++) { const double r = block_sum(acc[k], sm); if (tid == 0) t[k] = r; }
   if (tid == 0) {
-    const double* L = Lf + (size_t)f * 36;
-    double y[6];
-    for (int i = 0; i < 6; i++) y[i] = zf[(size_t)f * 6 + i] - t[i];
-    for (int i = 5; i >= 0; i--) {
+    const double* L = Lf + (size_t)f * FB * FB;
+    double y[FB];
+    for (int i = 0; i < FB; i++) y[i] = zf[(size_t)f * FB + i] - t[i];
+    for (int i = FB - 1; i >= 0; i--) {
       double v = y[i];
-      for (int k = i + 1; k < 6; k++) v -= L[k * 6 + i] * y[k];
-      y[i] = v / L[i * 6 + i];
+      for (int k = i + 1; k < FB; k++) v -= L[k * FB + i] * y[k];
+      y[i] = v / L[i * FB + i];
     }
-    for (int i = 0; i < 6; i++) gn[n_s + 6 * f + i] = y[i];
+    for (int i = 0; i < FB; i++) gn[n_s + FB * f + i] = y[i];
   }
 }
 

@@ -225,6 +225,31 @@ class Engine:
     self._ck(self.lib.mcba_get_state_matrices(self.h, nat.dptr(mats), nat.dptr(intr)))
     return mats[:d.C], mats[d.C:d.C + d.B], mats[d.C + d.B:], intr
 
+  # ---- motion-model state (include/mcba.h mcba_set_rolling / mcba_set_hand_eye) ----------------------
+  def set_rolling(self, end_pose_matrices, image_heights):
+    """RollingFrames: end poses f64[F,4,4] (the frames of set_state_matrices are the start poses) and the image height of
+    every camera, which turns a corner's observed row into its blend weight (rolling_frames.py:15-19)."""
+    d = self.desc
+    mats, h = nat.f64(end_pose_matrices), nat.f64(image_heights)
+    assert mats.shape == (d.F, 4, 4) and h.shape == (d.C,)
+    self._ck(self.lib.mcba_set_rolling(self.h, nat.dptr(mats), nat.dptr(h)))
+
+  def get_rolling(self):
+    mats = np.zeros((max(self.desc.F, 1), 4, 4))
+    self._ck(self.lib.mcba_get_rolling(self.h, nat.dptr(mats)))
+    return mats[:self.desc.F]
+
+  def set_hand_eye(self, base_wrt_gripper, world_wrt_base, gripper_wrt_camera):
+    """HandEye: the fixed arm poses f64[F,4,4] and the two optimised transforms f64[4,4] (hand_eye.py:20-33)."""
+    arm, w, g = nat.f64(base_wrt_gripper), nat.f64(world_wrt_base), nat.f64(gripper_wrt_camera)
+    assert arm.shape == (self.desc.F, 4, 4) and w.shape == (4, 4) and g.shape == (4, 4)
+    self._ck(self.lib.mcba_set_hand_eye(self.h, nat.dptr(arm), nat.dptr(w), nat.dptr(g)))
+
+  def get_hand_eye(self):
+    w, g = np.zeros((4, 4)), np.zeros((4, 4))
+    self._ck(self.lib.mcba_get_hand_eye(self.h, nat.dptr(w), nat.dptr(g)))
+    return w, g
+
   def get_params(self):
     d = self.desc
     out = (np.zeros((d.C, 6)), np.zeros((d.B, 6)), np.zeros((max(d.F, 1), 6)), np.zeros((d.C, self.kint)))

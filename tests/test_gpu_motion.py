@@ -1,0 +1,119 @@
+"""GPU (-m gpu): the two non-static motion models through the C-ABI -- RollingFrames (motion/rolling_frames.py:66-150) and
+HandEye (motion/hand_eye.py:14-90), SURVEY.md §8f rank 2 -- against the golden vectors of the running reference
+(tests/golden/rolling_2x6.npz, handeye_2x6.npz) and the oracle.  Same bars as tests/test_gpu_parity.py:
+  parameter layout bit exact; residuals at identical x <= 1e-9 px; J^T J, J^T r vs 3-point FD of the oracle <= 1e-6 relative;
+  converged cost vs scipy's dense exact trust region on the oracle <= 1e-8 relative; never worse than the reference's own run.
+"""
+import numpy as np
+import pytest
+from scipy import optimize
+from scipy.optimize._numdiff import approx_derivative, group_columns
+
+from conftest import load_golden
+from multical_b200 import _native
+from multical_b200.calibration import from_scene
+from multical_b200.motion import HandEye, RollingFrames
+from multical_b200.pose_set import pose_table
+from oracle.ba_oracle import Problem
+
+pytestmark = pytest.mark.gpu
+CASES = ["rolling_2x6", "handeye_2x6"]
+
+
+def make(name):
+  """(golden dict, Calibration on this package's mirrors, oracle Problem) of one motion-model fixture."""
+  scene, z = load_golden(name)
+  enabled = dict(zip((str(k) for k in z["enabled_keys"]), (bool(v) for v in z["enabled_values"])))
+  kw = dict(optimize=enabled, motion=str(z["motion"]), image_size=z["image_size"])
+  for key in ("frame_poses_end", "base_wrt_gripper", "world_wrt_base", "gripper_wrt_camera"):
+    if key in z: kw[key] = z[key]
+  prob = Problem.from_scene(scene, **kw)
+  calib = from_scene(scene)
+  if str(z["motion"]) == "rolling":
+    motion = RollingFrames(z["frame_poses"], z["frame_poses_end"], z["frame_valid"], [str(i) for i in range(scene["F"])])
+  else:
+    motion = HandEye(pose_table(z["base_wrt_gripper"], z["frame_valid"]), z["world_wrt_base"], z["gripper_wrt_camera"])
+  return z, calib.copy(motion=motion).enable(**enabled), prob
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_layout_residuals_and_errors_match_reference_golden(name):
+  z, calib, prob = make(name)
+  assert np.abs(calib.param_vec - z["x0"]).max() < 1e-12              # host mirror: block order and the motion block's own layout
+  eng = calib._upload(calib.inliers)
+  assert eng.N == z["r0"].size // 2 and eng.num_params == z["x0"].size
+  assert np.abs(eng.param_vec - z["x0"]).max() < 1e-12                # device: matrices -> rtvecs, internal -> reference order
+  eng.set_param_vec(z["x1"])
+  assert np.array_equal(eng.param_vec, z["x1"])                       # the permutation round-trips bit exactly
+  eng.set_param_vec(z["x0"])
+  assert np.abs(eng.residuals() - z["r0"]).max() < 1e-9               # vs the running reference
+  r1, cost = eng.residuals(z["x1"], with_cost=True)
+  assert np.abs(r1 - z["r1"]).max() < 1e-9
+  assert np.abs(r1 - prob.residuals(z["x1"])).max() < 1e-9           # vs the oracle
+  assert abs(cost - 0.5 * z["r1"] @ z["r1"]) <= 1e-12 * cost
+  assert np.array_equal(eng.param_vec, z["x0"])                       # evaluating at x1 must not move the state
+  assert np.abs(calib.reprojection_error - z["err_valid"]).max() < 1e-9
+  S = calib.sparsity_matrix.tocsr(); S.sort_indices()
+  assert tuple(S.shape) == tuple(z["sp_shape"]) and np.array_equal(S.indptr, z["sp_indptr"]) and np.array_equal(S.indices, z["sp_indices"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_normal_equations_match_finite_differences(name):
+  z, calib, prob = make(name)
+  eng = calib._upload(calib.inliers)
+  x1 = z["x1"]
+  S = prob.sparsity_matrix()
+  J = approx_derivative(prob.residuals, x1, method="3-point", sparsity=(S, group_columns(S))).toarray()
+  r = prob.residuals(x1)
+  H, g = J.T @ J, J.T @ r
+  JtJ, Jtr, cost = eng.linearize(x1)
+  nrm = np.sqrt(np.outer(np.diag(H), np.diag(H)))
+  live = nrm > 0
+  assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  assert np.abs(JtJ[~live]).max(initial=0.0) == 0.0
+  assert np.abs(Jtr - g).max() < 1e-6 * np.abs(g).max()
+  assert abs(cost - 0.5 * r @ r) < 1e-12 * cost
+  assert np.abs(JtJ - JtJ.T).max() <= 1e-12 * np.abs(JtJ).max()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_converged_solution_matches_dense_exact_oracle(name):
+  z, calib, prob = make(name)
+  out = calib.bundle_adjust()                                          # the reference's defaults (tolerance 1e-4)
+  assert out.last_solve.cost <= float(z["ba_cost"]) * (1 + 1e-6)      # never worse than the reference's own run
+  assert np.abs(prob.residuals(out.param_vec) @ prob.residuals(out.param_vec) * 0.5 - out.last_solve.cost) <= 1e-9 * out.last_solve.cost
+  tight = calib.bundle_adjust(tolerance=1e-14, xtol=1e-14, gtol=1e-12, max_iterations=200)
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac_sparsity=None, x_scale="jac", method="trf", tr_solver="exact",
+                               ftol=1e-14, xtol=1e-14, gtol=1e-12, max_nfev=300)
+  assert abs(tight.last_solve.cost - ref.cost) <= 1e-8 * ref.cost
+  assert np.abs(tight.reprojection_error - Problem.reprojection_error(prob.with_param_vec(ref.x))[0][calib.valid]).max() < 1e-4
+
+
+def test_rolling_projection_without_measurements_iterates_like_the_reference():
+  """`Calibration.projected` (calibration.py:115-121): rows from mid-exposure, then max_iterations re-projections with the rows
+  of the previous projection (rolling_frames.py:115-133); `reprojected` takes the rows of the measurements."""
+  z, calib, prob = make("rolling_2x6")
+  H = float(z["image_size"][1])
+  est = np.zeros_like(prob.points); est[..., 1] = 0.5 * H
+  uv, ok = prob.copy(points=est).reprojected()
+  for _ in range(4): uv, ok = prob.copy(points=uv).reprojected()
+  got = calib.projected
+  assert np.array_equal(np.asarray(got.valid), ok)
+  assert np.abs(np.asarray(got.points)[ok] - uv[ok]).max() < 1e-9
+  uv2, _ = prob.reprojected()
+  assert np.abs(np.asarray(calib.reprojected.points)[ok] - uv2[ok]).max() < 1e-9
+
+
+def test_motion_state_entry_points_refuse_the_wrong_problem():
+  z, calib, prob = make("rolling_2x6")
+  eng = calib._upload(calib.inliers)
+  with pytest.raises(_native.NativeError): eng.set_hand_eye(np.tile(np.eye(4), (eng.desc.F, 1, 1)), np.eye(4), np.eye(4))
+  assert np.abs(eng.get_rolling() - z["frame_poses_end"]).max() < 1e-12
+  with pytest.raises(NotImplementedError): calib.enable(boards=True).bundle_adjust()      # boards=True: static frames only
+  z, calib, prob = make("handeye_2x6")
+  eng = calib._upload(calib.inliers)
+  with pytest.raises(_native.NativeError): eng.set_rolling(np.tile(np.eye(4), (eng.desc.F, 1, 1)), np.ones(eng.desc.C))
+  w, g = eng.get_hand_eye()
+  assert np.abs(w - z["world_wrt_base"]).max() < 1e-12 and np.abs(g - z["gripper_wrt_camera"]).max() < 1e-12
+  frames = eng.get_state_matrices()[2]                                                     # derived: G A_f W
+  assert np.abs(frames - z["gripper_wrt_camera"] @ z["base_wrt_gripper"] @ z["world_wrt_base"]).max() < 1e-12

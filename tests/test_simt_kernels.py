@@ -13,6 +13,7 @@ import pytest
 
 import test_gpu_parity as gp
 import test_gpu_table as gt
+import test_gpu_motion as gm
 from multical_b200 import _native, calibration
 
 
@@ -54,6 +55,13 @@ test_resident_adjust_outliers_equals_host_loop = gt.test_resident_adjust_outlier
 test_table_from_detections_is_make_point_table = gt.test_table_from_detections_is_make_point_table
 test_table_state_machine_refuses_stale_errors = gt.test_table_state_machine_refuses_stale_errors
 test_outlier_steps_match_reference_golden = gt.test_outlier_steps_match_reference_golden
+
+# ---- tests/test_gpu_motion.py on the interpreter (RollingFrames, HandEye)
+test_motion_layout_residuals_and_errors_match_reference_golden = gm.test_layout_residuals_and_errors_match_reference_golden
+test_motion_normal_equations_match_finite_differences = gm.test_normal_equations_match_finite_differences
+test_motion_converged_solution_matches_dense_exact_oracle = gm.test_converged_solution_matches_dense_exact_oracle
+test_rolling_projection_without_measurements_iterates_like_the_reference = gm.test_rolling_projection_without_measurements_iterates_like_the_reference
+test_motion_state_entry_points_refuse_the_wrong_problem = gm.test_motion_state_entry_points_refuse_the_wrong_problem
 
 
 @pytest.mark.parametrize("sms", ["1", "148"])
