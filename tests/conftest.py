@@ -16,6 +16,16 @@ def pytest_configure(config):
   config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+  """Run order under `-x`: tests/test_gpu_motion.py (the motion models added after this round's GPU budget was spent: verified on
+  the SIMT interpreter only, see tests/test_simt_kernels.py) goes after every GPU test that has already run on hardware, so that a
+  hardware-only failure there cannot hide the results of the others."""
+  late = [it for it in items if it.fspath.basename == "test_gpu_motion.py"]
+  if late:
+    rest = [it for it in items if it.fspath.basename != "test_gpu_motion.py"]
+    items[:] = rest + late
+
+
 def load_golden(name):
   """Golden fixture -> (scene dict shaped like multical_b200.synthetic scenes, raw npz dict)."""
   z = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))

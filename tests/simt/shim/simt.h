@@ -150,10 +150,25 @@ inline void run_block() {
     f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = STACK_BYTES; f.ctx.uc_link = nullptr;
     makecontext(&f.ctx, (void (*)())trampoline, 0);
   }
+  // SIMT_ORDER=reverse | shuffle:<seed>: the order in which runnable threads are resumed.  A kernel that is correct on hardware
+  // gives the same result for every order; a missing __syncwarp / __syncthreads between a write and a read by another thread is
+  // hidden by one order and exposed by another.
+  static int order_mode = -1; static unsigned order_seed = 1;
+  if (order_mode < 0) {
+    const char* e = getenv("SIMT_ORDER");
+    order_mode = !e ? 0 : !strcmp(e, "reverse") ? 1 : !strncmp(e, "shuffle", 7) ? 2 : 0;
+    if (order_mode == 2 && e[7] == ':') order_seed = (unsigned)atoi(e + 8) * 2654435761u + 1u;
+  }
+  static std::vector<int> order;
+  order.resize(n);
+  for (int i = 0; i < n; i++) order[i] = order_mode == 1 ? n - 1 - i : i;
   int remaining = n;
   while (remaining > 0) {
     bool progress = false;
-    for (int i = 0; i < n; i++) {
+    if (order_mode == 2)
+      for (int i = n - 1; i > 0; i--) { order_seed = order_seed * 1664525u + 1013904223u; std::swap(order[i], order[(order_seed >> 8) % (unsigned)(i + 1)]); }
+    for (int oi = 0; oi < n; oi++) {
+      const int i = order[oi];
       Fiber& f = fibers[i];
       if (f.done) continue;
       if (f.wait == WAIT_BLOCK && blk.gen == f.wait_gen) continue;
