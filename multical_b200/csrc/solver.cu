@@ -81,6 +81,7 @@ struct mcba_ctx {
   int launches = 0;
   int num_sms = 148;
   bool use_mma = true;    // per-view moments on the fp64 tensor path (MCBA_MOMENTS=fma selects the DFMA kernels)
+  bool chol_blocked = false;   // MCBA_CHOL=blocked: single-CTA blocked reduced solve (k_chol_blocked) instead of k_chol_small; A/B candidate
 
   bool uploaded = false;
   DeviceProblem P{};
@@ -543,6 +544,8 @@ int mcba_create(int device, mcba_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
   { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
+  { const char* e = getenv("MCBA_CHOL"); if (e && std::string(e) == "blocked") ctx->chol_blocked = true; }
+  cudaFuncSetAttribute(k_chol_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #define MMA_ATTR(MODEL) \
   cudaFuncSetAttribute(k_views_mma<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
   cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
@@ -1331,7 +1334,9 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     }
     if (n_s > 0) {
       EXCHANGE(ex_.add(ctx->S.p, (size_t)n_s * n_s, 0); ex_.add(ctx->rhs.p, n_s, 0));
-      if (n_s <= CHOL_SMALL_MAX) {
+      if (n_s <= CHOL_SMALL_MAX && ctx->chol_blocked) {
+        k_chol_blocked<<<1, 256, chol_blocked_smem_doubles(n_s) * sizeof(double), s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); CKL();
+      } else if (n_s <= CHOL_SMALL_MAX) {
         const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
         const int R = (n_s + 15) / 16;
 #define CS(RR) case RR: k_chol_small<RR><<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); break;

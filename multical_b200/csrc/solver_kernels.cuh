@@ -487,6 +487,164 @@ k_chol_small(int n, const double* Sg, const double* rhs, const double* gh, Solve
   }
 }
 
+// k_chol_blocked (opt-in: MCBA_CHOL=blocked, n <= 128): the same reduced solve as k_chol_small with the per-column block
+// barriers taken out of the critical path.  k_chol_small pays two __syncthreads and a shared-memory round trip per COLUMN
+// (profiles/r01_ncu_small_kernels_cfg2.csv: 70 columns x 0.73 us); here a column step of the 16x16 diagonal block is warp-level
+// (lane j holds column j in registers: pivot broadcast, rsqrt, scaled column broadcast by 16 shuffles, rank-1 update on
+// registers -- no barrier), the diagonal block is inverted by the same warp, and the panel (thread per row, in place) and the
+// trailing update (16x16 thread tiling) are plain products between 3 block barriers per 16 columns.  Both substitutions use the
+// inverted diagonal blocks: per block one 16-long product and one row-parallel update.  Matrix (lower triangle) in shared memory.
+constexpr int CB = 16;
+__host__ __device__ inline size_t chol_blocked_smem_doubles(int n) {
+  const int nblk = (n + CB - 1) / CB;
+  return (size_t)n * (n | 1) + (size_t)nblk * CB * CB + (size_t)nblk * CB;
+}
+__global__ void __launch_bounds__(256)
+k_chol_blocked(int n, const double* Sg, const double* rhs, const double* gh, SolverState* st, double* out) {
+  extern __shared__ double cbs[];
+  const int ld = n | 1;                          // odd leading dimension: rows walked by consecutive threads hit different banks
+  const int nblk = (n + CB - 1) / CB;
+  double* A = cbs;                                // [n][ld], lower triangle
+  double* Li = A + (size_t)n * ld;                // [nblk][CB][CB] inverses of the diagonal blocks (row-major, lower triangular)
+  double* b = Li + (size_t)nblk * CB * CB;        // [nblk*CB] right-hand side -> y -> x
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double reg = st->reg;
+  for (int idx = tid; idx < n * n; idx += 256) {
+    const int i = idx / n, j = idx % n;
+    if (j <= i) A[i * ld + j] = Sg[(size_t)i * n + j] + (i == j ? reg : 0.0);
+  }
+  for (int i = tid; i < nblk * CB; i += 256) b[i] = i < n ? rhs[i] + gh[i] : 0.0;
+  __syncthreads();
+
+  for (int kb = 0, blk = 0; kb < n; kb += CB, blk++) {
+    const int nb = min(CB, n - kb);
+    double* Lb = Li + (size_t)blk * CB * CB;
+    if (warp == 0) {
+      // ---- diagonal block: lanes j and j+16 both hold column j (full-mask shuffles stay uniform); identity padding beyond nb
+      const int j = lane & 15;
+      double col[CB], rsd[CB];
+#pragma unroll
+      for (int i = 0; i < CB; i++)
+        col[i] = (i < nb && j < nb) ? (i >= j ? A[(kb + i) * ld + kb + j] : A[(kb + j) * ld + kb + i]) : (i == j ? 1.0 : 0.0);
+#pragma unroll
+      for (int k = 0; k < CB; k++) {
+        const double dkk = __shfl_sync(0xffffffffu, col[k], k);
+        if (lane == 0 && k < nb && !(dkk > 0.0)) st->chol_fail += 1;
+        const double rs = rsqrt(fmax(dkk, 1e-300));
+        rsd[k] = rs;
+        double lik[CB];
+#pragma unroll
+        for (int i = k; i < CB; i++) {
+          double v = col[i];
+          if (j == k) { v *= rs; col[i] = v; }
+          lik[i] = __shfl_sync(0xffffffffu, v, k);
+        }
+        double ljk = 0.0;
+#pragma unroll
+        for (int i = k + 1; i < CB; i++) if (i == j) ljk = lik[i];
+        if (j > k) {
+#pragma unroll
+          for (int i = k + 1; i < CB; i++) col[i] -= lik[i] * ljk;
+        }
+      }
+      if (lane < CB && j < nb) {
+#pragma unroll
+        for (int i = 0; i < CB; i++) if (i >= j && i < nb) A[(kb + i) * ld + kb + j] = col[i];
+      }
+      __syncwarp();
+      // ---- inverse of the diagonal block: lane j solves L z = e_j (1 / L_ii = rsd[i] from the factorisation)
+      if (lane < CB) {
+        double z[CB];
+#pragma unroll
+        for (int i = 0; i < CB; i++) {
+          double sacc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int m = 0; m < i; m++) {
+            const double lim = (i < nb) ? A[(kb + i) * ld + kb + m] : 0.0;     // m < i < nb; padding rows are identity
+            sacc -= lim * z[m];
+          }
+          z[i] = (i >= j) ? sacc * rsd[i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < CB; i++) Lb[i * CB + j] = z[i];
+      }
+    }
+    __syncthreads();
+    // ---- panel: rows below the block, thread per row, in place:  P = A_panel L_kk^-T   (P[i][jj] = sum_{m<=jj} A[i][m] Linv[jj][m])
+    for (int i = kb + nb + tid; i < n; i += 256) {
+      double a[CB];
+#pragma unroll
+      for (int m = 0; m < CB; m++) a[m] = m < nb ? A[i * ld + kb + m] : 0.0;
+#pragma unroll
+      for (int jj = 0; jj < CB; jj++) {
+        if (jj < nb) {
+          double pacc = 0.0;
+#pragma unroll
+          for (int m = 0; m <= jj; m++) pacc += a[m] * Lb[jj * CB + m];
+          A[i * ld + kb + jj] = pacc;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- trailing update (lower triangle): A[i][jj] -= P[i][:] . P[jj][:]
+    {
+      const int base = kb + nb, ty = tid & 15, tx = tid >> 4;
+      for (int i = base + ty; i < n; i += 16) {
+        double pi[CB];
+#pragma unroll
+        for (int m = 0; m < CB; m++) pi[m] = A[i * ld + kb + m];
+        for (int jj = base + tx; jj <= i; jj += 16) {
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < CB; m++) acc += pi[m] * A[jj * ld + kb + m];
+          A[i * ld + jj] -= acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- forward substitution  L y = b, block by block
+  for (int kb = 0, blk = 0; kb < n; kb += CB, blk++) {
+    const int nb = min(CB, n - kb);
+    const double* Lb = Li + (size_t)blk * CB * CB;
+    double yv = 0.0;
+    if (tid < CB) {
+#pragma unroll
+      for (int m = 0; m < CB; m++) if (m <= tid) yv += Lb[tid * CB + m] * b[kb + m];
+    }
+    __syncthreads();
+    if (tid < CB) b[kb + tid] = yv;
+    __syncthreads();
+    for (int i = kb + nb + tid; i < n; i += 256) {
+      double acc = 0.0;
+#pragma unroll
+      for (int m = 0; m < CB; m++) acc += A[i * ld + kb + m] * b[kb + m];       // columns beyond nb only exist in the last block
+      b[i] -= acc;
+    }
+    __syncthreads();
+  }
+  // ---- backward substitution  L^T x = y
+  for (int blk = nblk - 1; blk >= 0; blk--) {
+    const int kb = blk * CB, nb = min(CB, n - kb);
+    const double* Lb = Li + (size_t)blk * CB * CB;
+    double xv = 0.0;
+    if (tid < CB) {
+#pragma unroll
+      for (int m = 0; m < CB; m++) if (m >= tid) xv += Lb[m * CB + tid] * b[kb + m];
+    }
+    __syncthreads();
+    if (tid < CB) b[kb + tid] = xv;
+    __syncthreads();
+    for (int i = tid; i < kb; i += 256) {
+      double acc = 0.0;
+      for (int m = 0; m < nb; m++) acc += A[(kb + m) * ld + i] * b[kb + m];
+      b[i] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += 256) out[i] = b[i];
+}
+
 constexpr int CHOL_NB = 32;
 // add reg to the diagonal (once, before the blocked factorisation)
 __global__ void k_chol_addreg(int n, double* S, const SolverState* st) {
