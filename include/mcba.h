@@ -192,6 +192,19 @@ int  mcba_table_error_ranks(mcba_ctx* ctx, int which, const int64_t* ranks, int3
  * MCBA_ERR_STATE if parameters or selection changed since.  Follow with mcba_table_select(MCBA_TABLE_INLIERS). */
 int  mcba_table_reject(mcba_ctx* ctx, double threshold, int64_t* n_valid, int64_t* n_keep);
 
+/* -- batched board-pose initialisation (what feeds the path) -------------------------------
+ * Replaces the C*F*B calls of board.estimate_pose_points (board/common.py:36-47: camera.undistort_points, then
+ * cv2.solvePnPGeneric with the camera matrix and no distortion) that tables.make_pose_table makes (tables.py:44-66).
+ * Detection lists as for mcba_table_from_detections; intrinsics f64[C][5+nd] (Camera.params); board_grid int32[B][5] =
+ * {id-grid width, height, id divisor (1 ChArUco corner ids, 4 AprilGrid tag corners), min_points, min_rows} of
+ * has_min_detections_grid (board/common.py:30-34; charuco.py:104-106, aprilgrid.py:197-199).
+ * Out, per list w = (c*F+f)*B+b: pose f64[4][4] (board wrt camera), reprojection RMS over the 2n scalar residuals as
+ * solvePnPGeneric reports it, number of corners, valid flag; a view without the minimum detections gets the reference's
+ * invalid_pose (identity, 0, 0, false; tables.py:38).  Does not touch the uploaded problem.                       */
+int  mcba_pnp_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const int64_t* det_start, const int32_t* det_ids,
+                    const double* det_xy, const double* board_points, const double* intrinsics, const int32_t* board_grid,
+                    double* poses, double* errors, int32_t* num_points, uint8_t* valid);
+
 /* -- measurement hooks (bench.py): launch one kernel family on the context stream -------------- */
 enum { MCBA_BENCH_LINEARIZE = 0, MCBA_BENCH_RESIDUAL = 1, MCBA_BENCH_COST = 2,
        MCBA_BENCH_NO_PREPARE = 256 /* or-ed in: reuse the pose tables of the previous call (times the kernel alone) */ };

@@ -28,7 +28,7 @@ EXPORTS = ["mcba_create", "mcba_destroy", "mcba_last_error", "mcba_set_stream", 
            "mcba_num_params", "mcba_get_param_vec", "mcba_set_param_vec", "mcba_residuals",
            "mcba_linearize", "mcba_reprojection_error", "mcba_solve", "mcba_bench_launch", "mcba_bench_info",
            "mcba_table_upload", "mcba_table_from_detections", "mcba_table_download", "mcba_table_set_inliers",
-           "mcba_table_get_inliers", "mcba_table_select", "mcba_table_errors", "mcba_table_error_ranks", "mcba_table_reject"]
+           "mcba_table_get_inliers", "mcba_table_select", "mcba_pnp_views", "mcba_table_errors", "mcba_table_error_ranks", "mcba_table_reject"]
 TABLE_VALID, TABLE_INLIERS = 0, 1
 
 
@@ -104,6 +104,7 @@ def load():
   U8, I64 = C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
   lib.mcba_table_upload.argtypes = [P, C.POINTER(ProblemDesc), U8, D, D, I64]
   lib.mcba_table_from_detections.argtypes = [P, C.POINTER(ProblemDesc), I64, I32, D, D, I64]
+  lib.mcba_pnp_views.argtypes = [P, C.POINTER(ProblemDesc), I64, I32, D, D, D, I32, D, D, I32, U8]
   lib.mcba_table_download.argtypes = [P, U8, D]
   lib.mcba_table_set_inliers.argtypes = [P, U8]
   lib.mcba_table_get_inliers.argtypes = [P, U8]

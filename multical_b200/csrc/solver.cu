@@ -17,6 +17,7 @@
 #include "pack_kernels.cuh"
 #include "table_kernels.cuh"
 #include "peer_allreduce.cuh"
+#include "pnp_kernels.cuh"
 
 using namespace mcba;
 
@@ -834,6 +835,60 @@ int mcba_table_from_detections(mcba_ctx* ctx, const mcba_problem_desc* desc, con
     REQUIRE(!bad, MCBA_ERR_ARG, "detection id outside [0, P)");
   }
   return table_finish(ctx, desc, dense, n_valid);
+}
+
+// Batched board-pose initialisation (pnp_kernels.cuh): one warp per detection list.  Independent of the uploaded problem.
+int mcba_pnp_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const int64_t* det_start, const int32_t* det_ids, const double* det_xy,
+                   const double* board_points, const double* intrinsics, const int32_t* board_grid,
+                   double* poses, double* errors, int32_t* num_points, uint8_t* valid) {
+  if (!ctx || !desc) return MCBA_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  { int r = check_desc(ctx, desc); if (r) return r; }
+  REQUIRE(det_start && board_points && intrinsics && board_grid && poses && errors && num_points && valid, MCBA_ERR_ARG, "null argument");
+  const int nv = desc->C * desc->F * desc->B;
+  if (nv == 0) return MCBA_OK;
+  const int64_t total = det_start[nv];
+  REQUIRE(det_start[0] == 0 && total >= 0 && total < ((int64_t)1 << 31), MCBA_ERR_ARG, "bad detection offsets");
+  REQUIRE(total == 0 || (det_ids && det_xy), MCBA_ERR_ARG, "null detection arrays");
+  for (int w = 0; w < nv; w++) REQUIRE(det_start[w + 1] >= det_start[w], MCBA_ERR_ARG, "detection offsets are not a monotone CSR over C*F*B lists");
+  for (int64_t i = 0; i < total; i++) REQUIRE(det_ids[i] >= 0 && det_ids[i] < desc->P, MCBA_ERR_ARG, "detection id outside [0, P)");
+  for (int b = 0; b < desc->B; b++)
+    REQUIRE(board_grid[5 * b] > 0 && board_grid[5 * b + 1] > 0 && board_grid[5 * b + 2] > 0 && board_grid[5 * b] <= 64 && board_grid[5 * b + 1] <= 64,
+            MCBA_ERR_UNSUPPORTED, "id grids are limited to 64 x 64 (bit masks of the occupied rows / columns)");
+  const int kint = 5 + model_nd(desc->model);
+  cudaStream_t s = ctx->stream;
+  DevBuf<int64_t> d_start; DevBuf<int32_t> d_ids, d_grid, d_n; DevBuf<double2> d_xy, d_und; DevBuf<double> d_bp, d_in, d_pose, d_err; DevBuf<uint8_t> d_ok;
+  const size_t tot = (size_t)std::max<int64_t>(total, 1);
+  CK(d_start.alloc((size_t)nv + 1)); CK(d_ids.alloc(tot)); CK(d_xy.alloc(tot)); CK(d_und.alloc(tot)); CK(d_grid.alloc((size_t)desc->B * 5));
+  CK(d_bp.alloc((size_t)desc->B * desc->P * 3)); CK(d_in.alloc((size_t)desc->C * kint));
+  CK(d_pose.alloc((size_t)nv * 16)); CK(d_err.alloc(nv)); CK(d_n.alloc(nv)); CK(d_ok.alloc(nv));
+  CK(cudaMemcpyAsync(d_start.p, det_start, sizeof(int64_t) * ((size_t)nv + 1), cudaMemcpyHostToDevice, s));
+  if (total) {
+    CK(cudaMemcpyAsync(d_ids.p, det_ids, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_xy.p, det_xy, sizeof(double2) * (size_t)total, cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaMemcpyAsync(d_grid.p, board_grid, sizeof(int32_t) * (size_t)desc->B * 5, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_bp.p, board_points, sizeof(double) * (size_t)desc->B * desc->P * 3, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_in.p, intrinsics, sizeof(double) * (size_t)desc->C * kint, cudaMemcpyHostToDevice, s));
+  PnpArgs a{};
+  a.C = desc->C; a.F = desc->F; a.B = desc->B; a.P = desc->P; a.model = desc->model; a.kint = kint; a.nv = nv;
+  a.det_start = d_start.p; a.det_ids = d_ids.p; a.det_xy = d_xy.p; a.board_pts = d_bp.p; a.intr = d_in.p; a.grid = d_grid.p;
+  a.und = d_und.p; a.poses = d_pose.p; a.err = d_err.p; a.npts = d_n.p; a.valid = d_ok.p; a.max_iters = 50;
+  const int blocks = (nv + PNP_WARPS - 1) / PNP_WARPS;
+  switch (desc->model) {
+    case MODEL_STANDARD: k_pnp_views<MODEL_STANDARD><<<blocks, PNP_WARPS * 32, 0, s>>>(a); break;
+    case MODEL_RATIONAL: k_pnp_views<MODEL_RATIONAL><<<blocks, PNP_WARPS * 32, 0, s>>>(a); break;
+    case MODEL_THIN_PRISM: k_pnp_views<MODEL_THIN_PRISM><<<blocks, PNP_WARPS * 32, 0, s>>>(a); break;
+    case MODEL_TILTED: k_pnp_views<MODEL_TILTED><<<blocks, PNP_WARPS * 32, 0, s>>>(a); break;
+    default: k_pnp_views<MODEL_FISHEYE><<<blocks, PNP_WARPS * 32, 0, s>>>(a); break;
+  }
+  CKL();
+  CK(cudaMemcpyAsync(poses, d_pose.p, sizeof(double) * 16 * (size_t)nv, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(errors, d_err.p, sizeof(double) * (size_t)nv, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(num_points, d_n.p, sizeof(int32_t) * (size_t)nv, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(valid, d_ok.p, (size_t)nv, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return MCBA_OK;
 }
 
 int mcba_table_download(mcba_ctx* ctx, uint8_t* valid, double* points) {

@@ -148,6 +148,27 @@ class Engine:
     self._table_ready(d, model, n.value)
     return n.value
 
+  def pnp_views(self, model, dims, det_start, det_ids, det_xy, board_points, intrinsics, board_grid):
+    """Batched board-pose initialisation (include/mcba.h mcba_pnp_views): list w = (c*F+f)*B+b of detected point ids and pixel
+    corners -> (poses [C,F,B,4,4], reprojection RMS [C,F,B], corner counts [C,F,B], valid [C,F,B])."""
+    Cn, F, B, P = (int(v) for v in dims)
+    nv = Cn * F * B
+    det_start = np.ascontiguousarray(det_start, dtype=np.int64)
+    assert det_start.shape == (nv + 1,), f"expected {nv + 1} list offsets, got {det_start.shape}"
+    det_ids = np.ascontiguousarray(det_ids, dtype=np.int32).reshape(-1)
+    det_xy = nat.f64(det_xy).reshape(-1, 2)
+    assert det_ids.size == det_xy.shape[0] == int(det_start[-1]), "detection arrays do not match the offsets"
+    bp = nat.f64(board_points).reshape(B, P, 3)
+    intr = nat.f64(intrinsics).reshape(Cn, 5 + nat.DIST_SIZES[model])
+    grid = np.ascontiguousarray(board_grid, dtype=np.int32).reshape(B, 5)
+    poses, err = np.zeros((max(nv, 1), 4, 4)), np.zeros(max(nv, 1))
+    npts, ok = np.zeros(max(nv, 1), np.int32), np.zeros(max(nv, 1), np.uint8)
+    d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], 0, 0)
+    self._ck(self.lib.mcba_pnp_views(self.h, C.byref(d), det_start.ctypes.data_as(C.POINTER(C.c_int64)), nat.iptr(det_ids), nat.dptr(det_xy),
+                                     nat.dptr(bp), nat.dptr(intr), nat.iptr(grid), nat.dptr(poses), nat.dptr(err), nat.iptr(npts),
+                                     ok.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return (poses[:nv].reshape(Cn, F, B, 4, 4), err[:nv].reshape(Cn, F, B), npts[:nv].reshape(Cn, F, B), ok[:nv].reshape(Cn, F, B).astype(bool))
+
   def _dense_shape(self):
     d = self.desc
     return (d.C, d.F, d.B, d.P)

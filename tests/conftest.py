@@ -17,13 +17,14 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-  """Run order under `-x`: tests/test_gpu_motion.py (the motion models added after this round's GPU budget was spent: verified on
-  the SIMT interpreter only, see tests/test_simt_kernels.py) goes after every GPU test that has already run on hardware, so that a
+  """Run order under `-x`: the GPU tests of what was added after this round's GPU budget was spent (motion models, batched pose
+  initialisation, opt-in candidates: verified on the SIMT interpreter only, see tests/test_simt_kernels.py) go after every GPU test that has already run on hardware, so that a
   hardware-only failure there cannot hide the results of the others."""
-  late = [it for it in items if it.fspath.basename == "test_gpu_motion.py"]
+  new = ("test_gpu_motion.py", "test_gpu_pnp.py", "test_gpu_candidates.py")
+  late = [it for it in items if it.fspath.basename in new]
   if late:
-    rest = [it for it in items if it.fspath.basename != "test_gpu_motion.py"]
-    items[:] = rest + late
+    rest = [it for it in items if it.fspath.basename not in new]
+    items[:] = rest + sorted(late, key=lambda it: new.index(it.fspath.basename))
 
 
 def load_golden(name):

@@ -127,11 +127,52 @@ def motion_cases(ref, only):
           "rms", data["ba_rms"], os.path.getsize(path) // 1024, "KB")
 
 
+def pnp_cases(ref, only):
+  """Board-pose initialisation: the reference's own tables.make_pose_table (tables.py:44-66) -> extract_pose ->
+  board.estimate_pose_points (board/common.py:36-47) on synthetic detections, with boards that answer `has_min_detections` through the
+  reference's has_min_detections_grid (board/common.py:30-34) exactly as CharucoBoard does (charuco.py:104-109; min_rows=3, min_points=20).
+    pnp_std_3x6      pinhole 5-coefficient cameras, sparse views (some below the minimum -> invalid_pose), 0.3 px noise
+    pnp_fisheye_2x5  fisheye cameras (camera_fisheye.py:108-111 undistortion)
+    pnp_cube_3x4     three 10x10 boards per frame, exclude_bad_poses with a limit that rejects part of the views"""
+  from multical.board.common import estimate_pose_points, has_min_detections_grid
+  from multical import tables
+
+  class GridBoard(ref.SyntheticBoard):
+    def __init__(self, adjusted_points, size, min_points=20, min_rows=3):
+      super().__init__(adjusted_points); self.size, self.min_points, self.min_rows = size, min_points, min_rows
+    def has_min_detections(self, detections):
+      return has_min_detections_grid(self.size, detections.ids, min_points=self.min_points, min_rows=self.min_rows)
+    def estimate_pose_points(self, camera, detections):
+      return estimate_pose_points(self, camera, detections)
+
+  cases = {
+    "pnp_std_3x6": (dict(C=3, F=6, vis=0.08, seed=31, model="standard"), (16, 22), dict()),
+    "pnp_fisheye_2x5": (dict(C=2, F=5, vis=0.3, seed=32, model="fisheye"), (16, 22), dict()),
+    "pnp_cube_3x4": (dict(C=3, F=4, vis=0.5, seed=33, model="standard", boards=("cube", 10, 10, 0.04, 3), rig="dome"), (10, 10),
+                     dict(exclude_bad_poses=True, pose_error_limit=0.305)),
+  }
+  for name, (kw, size, opts) in cases.items():
+    if only and name not in only: continue
+    scene = synthetic.make_scene(**kw)
+    calib = loader.build_calibration(ref, scene, guess=False)
+    boards = [GridBoard(p, size) for p in scene["board_points"]]
+    table = tables.make_pose_table(calib.point_table, boards, calib.cameras, opts.get("exclude_bad_poses", False), opts.get("pose_error_limit", 1.0))
+    data = dict(model=scene["model"], points=scene["points"], valid=scene["valid"], board_points=np.stack(scene["board_points"]),
+                K=scene["gt"]["K"], dist=scene["gt"]["dist"], image_size=np.array(scene["image_size"]), grid=np.array([*size, 1, 20, 3]),
+                exclude_bad_poses=bool(opts.get("exclude_bad_poses", False)), pose_error_limit=float(opts.get("pose_error_limit", 1.0)),
+                poses=table.poses, pose_valid=table.valid, num_points=table.num_points, reprojection_error=table.reprojection_error,
+                view_angles=table.view_angles)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **data)
+    print(name, "views", table.valid.size, "valid", int(table.valid.sum()), "max err", float(np.max(table.reprojection_error)), os.path.getsize(path) // 1024, "KB")
+
+
 def main():
   ref = loader.load()
   only = sys.argv[1:]          # optional: regenerate just the named cases (existing fixtures stay byte-identical)
   if not only or "outliers_3x6" in only: outlier_case(ref)
   if not only or any(n in only for n in ("rolling_2x6", "handeye_2x6")): motion_cases(ref, only)
+  if not only or any(n.startswith("pnp_") for n in only): pnp_cases(ref, only)
   for name, kw in CASES.items():
     if only and name not in only: continue
     scene = synthetic.make_scene(**kw)

@@ -3,6 +3,7 @@
 // against cv2, Rodrigues / twist maps against finite differences, the 2-D trust-region solve against scipy).
 // Not part of libmcba.so and never loaded by multical_b200.
 #include "solver_kernels.cuh"
+#include "pnp_kernels.cuh"
 
 using namespace mcba;
 
@@ -22,7 +23,24 @@ static void project_all(int n, const double* X, const double* k, double* uv, dou
   }
 }
 
+template <int MODEL>
+static void undistort_all(int n, const double* uv, const double* k, double* out) {
+  for (int i = 0; i < n; i++) undistort_pixel<MODEL>(k, uv[2 * i], uv[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
+
 extern "C" {
+int hm_undistort(int model, int n, const double* uv, const double* k, double* out) {
+  switch (model) {
+    case MODEL_STANDARD: undistort_all<MODEL_STANDARD>(n, uv, k, out); return 0;
+    case MODEL_RATIONAL: undistort_all<MODEL_RATIONAL>(n, uv, k, out); return 0;
+    case MODEL_THIN_PRISM: undistort_all<MODEL_THIN_PRISM>(n, uv, k, out); return 0;
+    case MODEL_FISHEYE: undistort_all<MODEL_FISHEYE>(n, uv, k, out); return 0;
+    case MODEL_TILTED: undistort_all<MODEL_TILTED>(n, uv, k, out); return 0;
+  }
+  return 1;
+}
+void hm_pose_from_homography(const double* H, double* R, double* t) { pose_from_homography(H, R, t); }
+int hm_spd_solve8(double* A, double* b) { return spd_solve<8>(A, b) ? 1 : 0; }
 int hm_project(int model, int n, const double* X, const double* k, double* uv, double* J, double* Jk) {
   switch (model) {
     case MODEL_STANDARD: project_all<MODEL_STANDARD>(n, X, k, uv, J, Jk); return 0;

@@ -329,6 +329,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
   return r;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }

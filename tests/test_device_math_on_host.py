@@ -31,6 +31,9 @@ def hm():
                     "-o", so, src], check=True)
   lib = C.CDLL(so)
   lib.hm_project.argtypes = [C.c_int, C.c_int, D, D, D, D, D]
+  lib.hm_undistort.argtypes = [C.c_int, C.c_int, D, D, D]
+  lib.hm_pose_from_homography.argtypes = [D, D, D]
+  lib.hm_spd_solve8.argtypes = [D, D]
   lib.hm_rodrigues.argtypes = [D, D, D]
   lib.hm_twist_map.argtypes = [D, D, D, D]
   lib.hm_matrix_to_rtvec.argtypes = [D, D]
@@ -169,3 +172,48 @@ def test_losses_match_scipy(hm, loss, index):
     r = np.zeros(3)
     hm.hm_loss(index, float(zi), dp(r))
     assert np.allclose(r, rho[:, i], rtol=1e-13, atol=1e-15)
+
+
+# ---- batched pose initialisation (csrc/pnp_kernels.cuh): the pieces whose reference arithmetic is OpenCV's
+@pytest.mark.parametrize("model", [0, 1, 2, 4, 3])
+def test_undistort_pixel_is_cv2_undistort_points(hm, model):
+  """camera.py:119-122 cv2.undistortPoints(pts, K, dist, P=K) (5 fixed-point iterations) and camera_fisheye.py:108-111
+  cv2.fisheye.undistortPoints (Newton on theta); the distorted pixels come from cv2's own projection of points in front of the camera."""
+  K = np.array([[1200.0, 0, 960], [0, 1190.0, 540], [0, 0, 1]])
+  X = points(400, seed=model)
+  if model == 3:
+    dist = np.array([0.02, -0.01, 3e-3, -1e-3])
+    uv = cv2.fisheye.projectPoints(X.reshape(-1, 1, 3), np.zeros(3), np.zeros(3), K, dist)[0].reshape(-1, 2)
+    want = cv2.fisheye.undistortPoints(uv.reshape(-1, 1, 2), K, dist.reshape(4, 1), P=K).reshape(-1, 2)
+  else:
+    dist = DIST[model]
+    uv = cv2.projectPoints(X.reshape(-1, 1, 3), np.zeros(3), np.zeros(3), K, dist)[0].reshape(-1, 2)
+    want = cv2.undistortPoints(uv.reshape(-1, 1, 2), K, dist, P=K).reshape(-1, 2)
+  kvec = np.concatenate([[K[0, 0], K[1, 1], K[0, 2], K[1, 2], 0.0], dist])
+  got = np.zeros_like(uv)
+  uv = np.ascontiguousarray(uv)
+  assert hm.hm_undistort(model, uv.shape[0], dp(uv), dp(kvec), dp(got)) == 0
+  assert np.abs(got - want).max() < 1e-9                                     # same iteration count, same formula: round-off only
+
+
+def test_pose_from_homography_recovers_a_plane_pose(hm):
+  rng = np.random.default_rng(3)
+  for _ in range(50):
+    R = Rotation.from_rotvec(rng.normal(0, 0.6, 3)).as_matrix()
+    t = np.array([rng.normal(0, 0.2), rng.normal(0, 0.2), rng.uniform(0.5, 2.0)])
+    H = np.column_stack([R[:, 0], R[:, 1], t]) * rng.uniform(0.2, 5.0)      # any positive scale
+    Rg, tg = np.zeros((3, 3)), np.zeros(3)
+    Hc = np.ascontiguousarray(H)
+    hm.hm_pose_from_homography(dp(Hc), dp(Rg), dp(tg))
+    assert np.abs(Rg - R).max() < 1e-12 and np.abs(tg - t).max() < 1e-12
+
+
+def test_spd_solve_matches_numpy(hm):
+  rng = np.random.default_rng(4)
+  for _ in range(20):
+    M = rng.normal(size=(12, 8)); A = M.T @ M; b = rng.normal(size=8)
+    Ac, bc = np.ascontiguousarray(A.copy()), b.copy()
+    assert hm.hm_spd_solve8(dp(Ac), dp(bc)) == 1
+    assert np.abs(bc - np.linalg.solve(A, b)).max() < 1e-9 * np.abs(b).max() * np.linalg.cond(A)
+  Z = np.zeros((8, 8)); zb = np.ones(8)
+  assert hm.hm_spd_solve8(dp(Z), dp(zb)) == 0                                 # not positive definite -> reported, never NaN-propagated silently

@@ -71,6 +71,18 @@ def test_oracle_motion_models_match_reference_golden(name):
   assert abs(np.sqrt(np.mean(e2[m2] ** 2)) - float(z["ba_rms"])) < 1e-2
 
 
+@pytest.mark.parametrize("name", ["pnp_std_3x6", "pnp_fisheye_2x5", "pnp_cube_3x4"])
+def test_pnp_oracle_matches_reference_golden(name):
+  """oracle/pnp_oracle.py (board/common.py:30-47 + tables.py:34-66 restated over cv2) against the reference's own make_pose_table."""
+  from oracle import pnp_oracle
+  z = dict(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"), allow_pickle=False))
+  grid = tuple(int(v) for v in z["grid"])
+  poses, ok, npts, err = pnp_oracle.make_pose_table(str(z["model"]), z["K"], z["dist"], z["board_points"], [grid] * z["board_points"].shape[0],
+                                                    z["points"], z["valid"], bool(z["exclude_bad_poses"]), float(z["pose_error_limit"]))
+  assert np.array_equal(ok, z["pose_valid"]) and np.array_equal(npts, z["num_points"])
+  assert np.abs(poses - z["poses"]).max() < 1e-12 and np.abs(err - z["reprojection_error"]).max() < 1e-12   # same OpenCV calls
+
+
 @pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6"])
 def test_oracle_bundle_adjust_close_to_reference_run(name):
   """The reference's TRF+LSMR trajectory is chaotic at the 1e-5 level in final cost, so the

@@ -14,6 +14,7 @@ import pytest
 import test_gpu_parity as gp
 import test_gpu_table as gt
 import test_gpu_motion as gm
+import test_gpu_pnp as gn
 from multical_b200 import _native, calibration
 
 
@@ -62,6 +63,11 @@ test_motion_normal_equations_match_finite_differences = gm.test_normal_equations
 test_motion_converged_solution_matches_dense_exact_oracle = gm.test_converged_solution_matches_dense_exact_oracle
 test_rolling_projection_without_measurements_iterates_like_the_reference = gm.test_rolling_projection_without_measurements_iterates_like_the_reference
 test_motion_state_entry_points_refuse_the_wrong_problem = gm.test_motion_state_entry_points_refuse_the_wrong_problem
+
+# ---- tests/test_gpu_pnp.py on the interpreter (batched board-pose initialisation)
+test_pnp_pose_table_matches_reference_golden = gn.test_pose_table_matches_reference_golden
+test_pnp_every_camera_model_against_opencv = gn.test_every_camera_model_against_opencv
+test_pnp_minimum_detections_rule_and_bad_inputs = gn.test_minimum_detections_rule_and_bad_inputs
 
 
 @pytest.mark.parametrize("sms", ["1", "148"])
