@@ -15,6 +15,7 @@ import test_gpu_parity as gp
 import test_gpu_table as gt
 import test_gpu_motion as gm
 import test_gpu_pnp as gn
+import test_gpu_candidates as gc
 from multical_b200 import _native, calibration
 
 
@@ -68,6 +69,9 @@ test_motion_state_entry_points_refuse_the_wrong_problem = gm.test_motion_state_e
 test_pnp_pose_table_matches_reference_golden = gn.test_pose_table_matches_reference_golden
 test_pnp_every_camera_model_against_opencv = gn.test_every_camera_model_against_opencv
 test_pnp_minimum_detections_rule_and_bad_inputs = gn.test_minimum_detections_rule_and_bad_inputs
+
+# ---- tests/test_gpu_candidates.py on the interpreter (opt-in variants)
+test_blocked_reduced_solve_reproduces_the_default_iterations = gc.test_blocked_reduced_solve_reproduces_the_default_iterations
 
 
 @pytest.mark.parametrize("sms", ["1", "148"])
