@@ -18,7 +18,8 @@ def timed(f, n=3):
   return (time.perf_counter() - t) / n, out
 
 
-scene = synthetic.make_scene(C=4, F=200, vis=0.65, seed=0)
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 200          # cfg2 by default
+scene = synthetic.make_scene(C=4, F=F, vis=0.65, seed=0)
 calib = from_scene(scene).enable(cameras=True)
 t, out = timed(lambda: calib.bundle_adjust())
 print(f"static   : {t * 1e3:8.2f} ms  nfev {out.last_solve.nfev} cost {out.last_solve.cost:.4f} device {out.last_solve.device_ms:.3f} ms launches {out.last_solve.kernel_launches}")
@@ -38,6 +39,6 @@ views = int(np.asarray(tab.valid).size)
 print(f"pnp gpu  : {t * 1e3:8.2f} ms for {views} views ({views / t:.0f} views/s), {int(np.asarray(tab.valid).sum())} valid")
 g = scene["gt"]
 t0 = time.perf_counter()
-poses, ok, npts, err = pnp_oracle.make_pose_table("standard", g["K"], g["dist"], scene["board_points"], [(16, 22, 1, 20, 3)], scene["points"][:, :50], scene["valid"][:, :50])
+poses, ok, npts, err = pnp_oracle.make_pose_table("standard", g["K"], g["dist"], scene["board_points"], [(16, 22, 1, 20, 3)], scene["points"][:, :50], scene["valid"][:, :50])      # at most 50 frames on the host
 t1 = time.perf_counter() - t0
 print(f"pnp cv2  : {t1 * 1e3:8.2f} ms for {ok.size} views ({ok.size / t1:.0f} views/s, one host core)  max|dT| vs gpu {np.abs(poses - np.asarray(tab.poses)[:, :50]).max():.2e}")
