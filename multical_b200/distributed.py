@@ -38,18 +38,44 @@ def init_comm(engine, rank, world, group=None, peer_cap=None):
     engine.peer_import(handles)
 
 
+def _slice_motion(motion, a, b):
+  """Frames [a, b) of a motion model.  StaticFrames: its poses; RollingFrames (rolling_frames.py:66-150): start and end poses;
+  HandEye (hand_eye.py:14-90): the fixed arm poses -- the two optimised transforms are shared parameters, replicated."""
+  from .motion import MOTION_HAND_EYE, MOTION_ROLLING, motion_kind
+  kind = motion_kind(motion)
+  if kind == MOTION_ROLLING:
+    return motion.copy(pose_start=np.asarray(motion.pose_start)[a:b], pose_end=np.asarray(motion.pose_end)[a:b],
+                       valid=np.asarray(motion.valid)[a:b], names=list(motion.names)[a:b])
+  if kind == MOTION_HAND_EYE:
+    arm = motion.base_wrt_gripper
+    return motion.copy(base_wrt_gripper=type(arm).create(poses=np.asarray(arm.poses)[a:b], valid=np.asarray(arm.valid)[a:b]), names=None)
+  mt = motion.pose_table
+  return motion.copy(pose_table=type(mt).create(poses=np.asarray(mt.poses)[a:b], valid=np.asarray(mt.valid)[a:b]), names=None)
+
+
 def shard_calibration(calib, rank, world):
-  """Local view of a Calibration: this rank's frames only (point table, inlier mask, motion poses)."""
+  """Local view of a Calibration: this rank's frames only (point table, inlier mask, the motion model's per-frame state)."""
   F = calib.size.rig_poses
   a, b = frame_range(F, rank, world)
   pt = calib.point_table
   make = getattr(type(pt), "create")
   local_pt = make(points=np.asarray(pt.points)[:, a:b], valid=np.asarray(pt.valid)[:, a:b])
-  mt = calib.motion.pose_table
-  local_motion = calib.motion.copy(pose_table=type(mt).create(poses=np.asarray(mt.poses)[a:b], valid=np.asarray(mt.valid)[a:b]),
-                                   names=None)
   mask = None if calib.inlier_mask is None else calib.inlier_mask[:, a:b]
-  return calib.copy(point_table=local_pt, motion=local_motion, inlier_mask=mask), (a, b)
+  return calib.copy(point_table=local_pt, motion=_slice_motion(calib.motion, a, b), inlier_mask=mask), (a, b)
+
+
+def merge_motion(full_motion, local_motion, F, rank, world, group=None):
+  """The full motion model after a sharded solve: per-frame state all-gathered in frame order, shared state from the local result
+  (every rank solves the shared system redundantly on bit-identical data)."""
+  from .motion import MOTION_HAND_EYE, MOTION_ROLLING, motion_kind
+  kind = motion_kind(full_motion)
+  if kind == MOTION_ROLLING:
+    return full_motion.copy(pose_start=gather_frames(local_motion.pose_start, F, rank, world, group),
+                            pose_end=gather_frames(local_motion.pose_end, F, rank, world, group))
+  if kind == MOTION_HAND_EYE:
+    return full_motion.copy(world_wrt_base=local_motion.world_wrt_base, gripper_wrt_camera=local_motion.gripper_wrt_camera)
+  mt = full_motion.pose_table
+  return full_motion.copy(pose_table=type(mt).create(poses=gather_frames(local_motion.poses, F, rank, world, group), valid=np.asarray(mt.valid)))
 
 
 def gather_frames(local_frame_poses, F, rank, world, group=None):
@@ -73,9 +99,7 @@ def bundle_adjust(calib, group=None, **kwargs):
   if getattr(eng, "world", 1) != world:
     init_comm(eng, rank, world, group)
   out_local = local.bundle_adjust(**kwargs)
-  poses = gather_frames(out_local.motion.poses, calib.size.rig_poses, rank, world, group)
-  mt = calib.motion.pose_table
-  motion = calib.motion.copy(pose_table=type(mt).create(poses=poses, valid=np.asarray(mt.valid)))
+  motion = merge_motion(calib.motion, out_local.motion, calib.size.rig_poses, rank, world, group)
   out = calib.copy(cameras=out_local.cameras, camera_poses=out_local.camera_poses, board_poses=out_local.board_poses, motion=motion)
   out.__dict__["last_solve"] = out_local.last_solve
   return out

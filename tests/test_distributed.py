@@ -40,6 +40,27 @@ def test_shards_cover_every_corner_exactly_once():
   assert total == int(calib.inliers.sum()) and frames == list(range(7))
 
 
+def test_motion_models_shard_by_frame():
+  """RollingFrames: both pose sets are per-frame state (12 parameters per local frame); HandEye: only the arm poses are sliced, the 12
+  optimised parameters are shared and replicated."""
+  from multical_b200.motion import HandEye, RollingFrames
+  from multical_b200.pose_set import pose_table
+  scene = synthetic.make_scene(C=2, F=7, vis=0.5, seed=6)
+  calib = from_scene(scene)
+  end = calib.motion.poses.copy(); end[:, 0, 3] += 0.01
+  roll = calib.copy(motion=RollingFrames(calib.motion.poses, end, calib.motion.valid, [str(i) for i in range(7)]))
+  hand = calib.copy(motion=HandEye(pose_table(calib.motion.poses, calib.motion.valid), np.eye(4), np.eye(4)))
+  for r in range(3):
+    a, b = mdist.frame_range(7, r, 3)
+    lr, _ = mdist.shard_calibration(roll, r, 3)
+    assert np.array_equal(lr.motion.pose_start, roll.motion.pose_start[a:b]) and np.array_equal(lr.motion.pose_end, end[a:b])
+    assert lr.param_vec.size == roll.param_vec.size - 12 * (7 - (b - a)) and lr.motion.names == [str(i) for i in range(a, b)]
+    lh, _ = mdist.shard_calibration(hand, r, 3)
+    assert np.array_equal(lh.motion.base_wrt_gripper.poses, calib.motion.poses[a:b]) and lh.motion.size == b - a
+    assert lh.param_vec.size == hand.param_vec.size                      # nothing per-frame in the hand-eye parameter vector
+    assert np.array_equal(lh.motion.poses, hand.motion.poses[a:b])
+
+
 _GLOO_WORKER = r"""
 import os, sys
 import numpy as np
@@ -59,6 +80,24 @@ expect = np.asarray(calib.motion.poses).copy()
 for r in range(world):
   lo, hi = mdist.frame_range(5, r, world); expect[lo:hi, 0, 3] += 100.0 * (r + 1)
 assert np.array_equal(full, expect)
+# a rolling-shutter model: start and end poses are gathered separately, both in frame order
+from multical_b200.motion import HandEye, RollingFrames
+from multical_b200.pose_set import pose_table
+end = np.asarray(calib.motion.poses).copy(); end[:, 1, 3] += 0.5
+roll = calib.copy(motion=RollingFrames(calib.motion.poses, end, calib.motion.valid, [str(i) for i in range(5)]))
+lroll, _ = mdist.shard_calibration(roll, rank, world)
+moved = lroll.motion.copy(pose_start=mine, pose_end=np.asarray(lroll.motion.pose_end) + (rank + 1))
+merged = mdist.merge_motion(roll.motion, moved, 5, rank, world)
+expect_end = end.copy()
+for r in range(world):
+  lo, hi = mdist.frame_range(5, r, world); expect_end[lo:hi] += r + 1
+assert np.array_equal(merged.pose_start, expect) and np.array_equal(merged.pose_end, expect_end)
+# hand-eye: the optimised pair is shared state, the arm table stays whole
+hand = calib.copy(motion=HandEye(pose_table(calib.motion.poses, calib.motion.valid), np.eye(4), np.eye(4)))
+lhand, _ = mdist.shard_calibration(hand, rank, world)
+W = np.eye(4); W[0, 3] = 0.25
+mh = mdist.merge_motion(hand.motion, lhand.motion.copy(world_wrt_base=W), 5, rank, world)
+assert np.array_equal(mh.world_wrt_base, W) and mh.size == 5
 # the unique-id broadcast used for the NCCL communicator (object broadcast from rank 0)
 uid = [bytes(range(128)) if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)

@@ -104,6 +104,25 @@ def test_rolling_projection_without_measurements_iterates_like_the_reference():
   assert np.abs(np.asarray(calib.reprojected.points)[ok] - uv2[ok]).max() < 1e-9
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_outlier_loop_on_the_resident_table_equals_the_host_loop(name, monkeypatch):
+  """adjust_outliers (calibration.py:254-268) with the table resident on the device must reproduce the host loop for the two motion
+  models too: the motion state has to survive every re-selection of the table (mcba_table_select keeps the parameter state)."""
+  from multical_b200.calibration import select_threshold
+  z, calib, prob = make(name)
+  pts = np.asarray(calib.point_table.points).copy()
+  idx = np.argwhere(calib.valid)
+  rng = np.random.default_rng(7)
+  for c, f, b, p in idx[rng.choice(len(idx), 25, replace=False)]: pts[c, f, b, p] += rng.normal(0, 30.0, 2)     # gross outliers
+  calib = calib.copy(point_table=calib.point_table._extend(points=pts))
+  res = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4))
+  monkeypatch.setenv("MCBA_HOST_OUTLIERS", "1")
+  host = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4))
+  assert np.array_equal(res.inliers, host.inliers) and res.inliers.sum() < calib.valid.sum()
+  assert abs(res.last_solve.cost - host.last_solve.cost) <= 1e-6 * host.last_solve.cost
+  assert np.abs(res.reprojection_error - host.reprojection_error).max() < 1e-2
+
+
 def test_motion_state_entry_points_refuse_the_wrong_problem():
   z, calib, prob = make("rolling_2x6")
   eng = calib._upload(calib.inliers)
