@@ -62,6 +62,7 @@ class NativeError(RuntimeError):
 
 
 _lib = None
+_allow_interpreter = False      # set only by tests/test_simt_kernels.py: the product never runs on the test-suite's CPU interpreter build
 
 
 def load():
@@ -73,6 +74,9 @@ def load():
     raise NativeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(the engine has no CPU fallback)")
   lib = C.CDLL(LIB_PATH)
+  if hasattr(lib, "mcba_simt_build") and not _allow_interpreter:
+    raise NativeError(f"{LIB_PATH} is the SIMT-interpreter build of the test-suite (tests/simt), not the CUDA library: "
+                      "the engine has no CPU path")
   P, D, I32 = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
   lib.mcba_create.argtypes = [C.c_int, C.POINTER(P)]
   lib.mcba_destroy.argtypes = [P]; lib.mcba_destroy.restype = None

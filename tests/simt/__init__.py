@@ -116,7 +116,10 @@ def build(force=False):
     with open(os.path.join(CSRC, f)) as fh: text = translate(fh.read())
     dst = os.path.join(OUT, f[:-3] + ".cpp" if f.endswith(".cu") else f)
     with open(dst, "w") as fh: fh.write(text)
-    if f.endswith(".cu"): main = dst
+    if f.endswith(".cu"):
+      main = dst
+      # marks the library as the interpreter build: multical_b200/_native.py refuses to load it unless a test asked for it
+      with open(dst, "a") as fh: fh.write('\nextern "C" int mcba_simt_build(void) { return 1; }\n')
   cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fno-strict-aliasing", "-w", "-Wno-unknown-pragmas",
          "-I", os.path.join(HERE, "shim"), "-o", LIB, main, "-ldl"]
   subprocess.run(cmd, check=True, cwd=OUT)

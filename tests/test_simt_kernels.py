@@ -30,6 +30,7 @@ def on_the_interpreter(simt_library, monkeypatch):
   """Point the ctypes binding at the interpreter build for one test; engines are per-library, so the cache is swapped as well."""
   monkeypatch.setattr(_native, "LIB_PATH", simt_library)
   monkeypatch.setattr(_native, "_lib", None)
+  monkeypatch.setattr(_native, "_allow_interpreter", True)
   monkeypatch.setattr(calibration, "_engines", {})
   monkeypatch.delenv("SIMT_SMS", raising=False)
   yield
@@ -92,3 +93,11 @@ def test_one_warp_per_view_and_split_view_moment_kernels_agree(sms, monkeypatch)
   assert np.abs(JtJ - JtJ2).max() <= 1e-11 * np.abs(JtJ).max()
   assert np.abs(Jtr - Jtr2).max() <= 1e-11 * np.abs(Jtr).max()
   assert abs(cost - cost2) <= 1e-13 * cost
+
+
+def test_the_product_refuses_the_interpreter_build(simt_library, monkeypatch):
+  """Pointing the product at the interpreter library (e.g. through MCBA_LIB) must fail loudly: there is no CPU path."""
+  monkeypatch.setattr(_native, "_allow_interpreter", False)
+  monkeypatch.setattr(_native, "_lib", None)
+  with pytest.raises(_native.NativeError, match="no CPU path"):
+    _native.load()
