@@ -52,7 +52,7 @@ enum { MCBA_OPT_CAMERA_POSES = 1, MCBA_OPT_BOARD_POSES = 2, MCBA_OPT_MOTION = 4,
  *   MCBA_MOTION_HAND_EYE  HandEye: frame pose f = gripper_wrt_camera @ base_wrt_gripper[f] @ world_wrt_base with the arm
  *                         poses fixed (motion/hand_eye.py:14-90).  motion block = [world_wrt_base 6 | gripper_wrt_camera 6]
  *                         (76-81), shared by every residual (89-90).
- * MCBA_OPT_BOARDS is only implemented for static frames (MCBA_ERR_UNSUPPORTED otherwise). */
+ */
 enum { MCBA_MOTION_ROLLING = 1 << 16, MCBA_MOTION_HAND_EYE = 1 << 17 };
 
 typedef struct {

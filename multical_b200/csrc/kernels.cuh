@@ -603,123 +603,6 @@ __device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int loca
 
 __device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int local);
 
-// k_point_blocks (boards=True only): board points as shared parameters (3 per padded point).  One warp per view, one
-// thread per corner: d r / d X_board = J_proj R_cfb; the point's own 3x3 block, its gradient and its couplings with the
-// camera pose / intrinsics / board pose (H_ss) and the frame pose (W_f) are added with fp64 atomics on top of what the
-// expand kernels wrote.  Replaces the axis-3 column block of the reference's sparsity pattern (calibration.py:188-190).
-template <int MODEL>
-__global__ void __launch_bounds__(VIEW_WARPS * 32)
-k_point_blocks(DeviceProblem p, ViewKernelArgs a, double* Hss, double* W, double* g) {
-  constexpr int ND = model_nd(MODEL);
-  constexpr int KINT = 5 + ND;
-  constexpr int NIN = 4 + ND;
-  __shared__ double maps[VIEW_WARPS][108];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * VIEW_WARPS + warp, nw = gridDim.x * VIEW_WARPS;
-  const int n_s = p.n_s;
-  double* Ac = maps[warp]; double* Af = Ac + 36; double* Ab = Af + 36;
-  for (int v = gw; v < p.V; v += nw) {
-    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
-    const int beg = p.view_start[v], end = p.view_start[v + 1];
-    const PoseT& pc = p.cam_T[c]; const PoseT& pf = p.frame_T[f]; const PoseT& pb = p.board_T[b];
-    ViewPose vp;
-    compose_view(pc, pf, pb, vp);
-    __syncwarp();
-    if (lane < 3) {
-      double Rcf[9], tcf[3];
-      mat3_mul(pc.R, pf.R, Rcf);
-      mat3_vec(pc.R, pf.t, tcf);
-      tcf[0] += pc.t[0]; tcf[1] += pc.t[1]; tcf[2] += pc.t[2];
-      if (lane == 0) { const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
-      else if (lane == 1) twist_map(pc.R, pf.JL, tcf, Af);
-      else twist_map(Rcf, pb.JL, vp.t, Ab);
-    }
-    __syncwarp();
-    double k[KINT];
-#pragma unroll
-    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
-    const double* bp = p.board_pts + (size_t)b * p.P * 3;
-    const int cp = p.off_cp >= 0 ? p.off_cp + 6 * c : -1;
-    const int bpo = p.off_bp >= 0 ? p.off_bp + 6 * b : -1;
-    const int in0 = p.off_in >= 0 ? p.off_in + p.kint * c : -1;
-    for (int idx = beg + lane; idx < end; idx += 32) {
-      const double2 ob = p.obs[idx];
-      const int pi = p.pid[idx];
-      const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
-      double Xc[3];
-      mat3_vec(vp.R, X, Xc);
-      Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
-      double u, w_, Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
-      project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
-      double ru = u - ob.x, rv = w_ - ob.y, wu = 1.0, wv = 1.0;
-      if (a.loss != 0) {
-        const double is = 1.0 / a.f_scale;
-        double zu = ru * is, zv = rv * is;
-        zu *= zu; zv *= zv;
-        double r0u, r1u, r2u, r0v, r1v, r2v;
-        loss_rho(a.loss, zu, r0u, r1u, r2u);
-        loss_rho(a.loss, zv, r0v, r1v, r2v);
-        double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
-        ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
-        jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
-        wu = sqrt(ju); wv = sqrt(jv);
-        ru *= r1u / wu; rv *= r1v / wv;
-      }
-      // local rows: twist (6) then [fx fy cx cy dist] (NIN)
-      double gu[6 + NIN], gv[6 + NIN];
-      gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
-      gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
-#pragma unroll
-      for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
-#pragma unroll
-      for (int i = 0; i < NIN; i++) { gu[6 + i] = 0.0; gv[6 + i] = 0.0; }
-      gu[6] = ku[0] * wu; gu[8] = wu; gv[7] = kv[1] * wv; gv[9] = wv;
-#pragma unroll
-      for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
-      // point rows: d r / d X_board = J_proj R_cfb
-      double xu[3], xv[3];
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        xu[j] = (Ju[0] * vp.R[j] + Ju[1] * vp.R[3 + j] + Ju[2] * vp.R[6 + j]) * wu;
-        xv[j] = (Jv[0] * vp.R[j] + Jv[1] * vp.R[3 + j] + Jv[2] * vp.R[6 + j]) * wv;
-      }
-      const int pt = p.off_pt + 3 * (b * p.P + pi);
-      auto addS = [&](int i, int j, double val) {
-        atomicAdd(&Hss[(size_t)i * n_s + j], val);
-        atomicAdd(&Hss[(size_t)j * n_s + i], val);
-      };
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        atomicAdd(&g[pt + r], xu[r] * ru + xv[r] * rv);
-#pragma unroll
-        for (int q = r; q < 3; q++) {
-          const double val = xu[r] * xu[q] + xv[r] * xv[q];
-          if (q == r) atomicAdd(&Hss[(size_t)(pt + r) * n_s + pt + r], val); else addS(pt + r, pt + q, val);
-        }
-        double Q[6];
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) Q[kk] = xu[r] * gu[kk] + xv[r] * gv[kk];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          double vc = 0.0, vf = 0.0, vb = 0.0;
-#pragma unroll
-          for (int kk = 0; kk < 6; kk++) { vc += Q[kk] * Ac[kk * 6 + j]; vf += Q[kk] * Af[kk * 6 + j]; vb += Q[kk] * Ab[kk * 6 + j]; }
-          if (cp >= 0) addS(pt + r, cp + j, vc);
-          if (bpo >= 0) addS(pt + r, bpo + j, vb);
-          if (p.motion_on) atomicAdd(&W[((size_t)f * n_s + pt + r) * 6 + j], vf);
-        }
-        if (in0 >= 0) {
-#pragma unroll
-          for (int i = 0; i < NIN; i++) {
-            const double val = xu[r] * gu[6 + i] + xv[r] * gv[6 + i];
-            if (val != 0.0) addS(pt + r, in0 + intr_param_index(p, i), val);
-          }
-        }
-      }
-    }
-  }
-}
-
 // Both expand kernels work warp-per-view: a warp pulls one view's moment record (T doubles) into its private shared
 // memory slice, builds the 6x6 twist maps it needs, and does the small products with lane-owned outputs -- only
 // __syncwarp inside the view loop; warps of a CTA run different views concurrently and meet once at the end.
@@ -755,6 +638,174 @@ __device__ __forceinline__ void view_twist_maps(const DeviceProblem& p, int c, i
   mat3_vec(Rcf, pb.t, tb);
   tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
   twist_map(Rcf, pb.JL, tb, Ab + 36 * j);
+}
+
+// hand-eye twist maps of one view into Eh[6][12] = [A_W | A_G] (see k_expand_hand_eye): `role` 0 computes the W half, 1 the G half
+__device__ __forceinline__ void hand_eye_twist_maps(const DeviceProblem& p, int c, int f, int role, double* Eh) {
+  const PoseT& pc = p.cam_T[c];
+  const PoseT& pW = p.he_T[0];
+  const PoseT& pG = p.he_T[1];
+  double A[36];
+  if (role == 0) {           // W: left part T_c G A_f, chain translation up to and including W = t(T_c T_f)
+    const PoseT& pf = p.frame_T[f];
+    const PoseT& pa = p.arm_T[f];
+    double Rcf[9], tcf[3], Rcg[9], Rl[9];
+    view_chain(pc, pf, Rcf, tcf);
+    mat3_mul(pc.R, pG.R, Rcg);
+    mat3_mul(Rcg, pa.R, Rl);
+    twist_map(Rl, pW.JL, tcf, A);
+    for (int kk = 0; kk < 6; kk++) for (int j = 0; j < 6; j++) Eh[kk * 12 + j] = A[kk * 6 + j];
+  } else {                   // G: left part T_c, chain translation up to and including G = R_c t_G + t_c
+    double tcg[3];
+    mat3_vec(pc.R, pG.t, tcg);
+    tcg[0] += pc.t[0]; tcg[1] += pc.t[1]; tcg[2] += pc.t[2];
+    twist_map(pc.R, pG.JL, tcg, A);
+    for (int kk = 0; kk < 6; kk++) for (int j = 0; j < 6; j++) Eh[kk * 12 + 6 + j] = A[kk * 6 + j];
+  }
+}
+
+// k_point_blocks (boards=True only): board points as shared parameters (3 per padded point).  One warp per view, one
+// thread per corner: d r / d X_board = J_proj R_cfb (rolling: the blend (1-tau) R_start + tau R_end); the point's own 3x3 block,
+// its gradient and its couplings with the camera pose / intrinsics / board pose / hand-eye pair (H_ss) and the frame block (W_f)
+// are added with fp64 atomics on top of what the expand kernels wrote.  Replaces the axis-3 column block of the reference's
+// sparsity pattern (calibration.py:188-190).  NP = 2: rolling frames (two twist blocks per row, 12-wide frame block).
+template <int MODEL, int NP>
+__global__ void __launch_bounds__(VIEW_WARPS * 32)
+k_point_blocks(DeviceProblem p, ViewKernelArgs a, double* Hss, double* W, double* g) {
+  constexpr bool ROLL = NP == 2;
+  constexpr int ND = model_nd(MODEL);
+  constexpr int KINT = 5 + ND;
+  constexpr int NIN = 4 + ND;
+  constexpr int KO = 6 * NP, FB = 6 * NP;
+  __shared__ double maps[VIEW_WARPS][36 + 72 * NP + 72];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * VIEW_WARPS + warp, nw = gridDim.x * VIEW_WARPS;
+  const int n_s = p.n_s;
+  double* Ac = maps[warp]; double* Af = Ac + 36; double* Ab = Af + 36 * NP; double* Eh = Ab + 36 * NP;
+  for (int v = gw; v < p.V; v += nw) {
+    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
+    const int beg = p.view_start[v], end = p.view_start[v + 1];
+    ViewPose vp, vpe;
+    compose_views<ROLL>(p, c, f, b, vp, vpe);
+    const double inv_h = ROLL ? 1.0 / p.img_h[c] : 0.0;
+    __syncwarp();
+    view_twist_maps<NP>(p, c, f, b, lane, Ac, Af, Ab);
+    if (p.off_he >= 0 && (lane == 8 || lane == 9)) hand_eye_twist_maps(p, c, f, lane - 8, Eh);
+    __syncwarp();
+    double k[KINT];
+#pragma unroll
+    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
+    const double* bp = p.board_pts + (size_t)b * p.P * 3;
+    const int cp = p.off_cp >= 0 ? p.off_cp + 6 * c : -1;
+    const int bpo = p.off_bp >= 0 ? p.off_bp + 6 * b : -1;
+    const int in0 = p.off_in >= 0 ? p.off_in + p.kint * c : -1;
+    for (int idx = beg + lane; idx < end; idx += 32) {
+      const double2 ob = p.obs[idx];
+      const int pi = p.pid[idx];
+      const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
+      const double tau = ob.y * inv_h;
+      double Xc[3], Xs[3], Xe[3];
+      corner_point<ROLL>(vp, vpe, X, tau, Xc, Xs, Xe);
+      double u, w_, Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
+      project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
+      double ru = u - ob.x, rv = w_ - ob.y, wu = 1.0, wv = 1.0;
+      if (a.loss != 0) {
+        const double is = 1.0 / a.f_scale;
+        double zu = ru * is, zv = rv * is;
+        zu *= zu; zv *= zv;
+        double r0u, r1u, r2u, r0v, r1v, r2v;
+        loss_rho(a.loss, zu, r0u, r1u, r2u);
+        loss_rho(a.loss, zv, r0v, r1v, r2v);
+        double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
+        ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
+        jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
+        wu = sqrt(ju); wv = sqrt(jv);
+        ru *= r1u / wu; rv *= r1v / wv;
+      }
+      // local rows: twist block(s) (KO) then [fx fy cx cy dist] (NIN) -- the layout of k_views_mma
+      double gu[KO + NIN], gv[KO + NIN];
+      if constexpr (!ROLL) {
+        gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
+        gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
+      } else {
+        const double su = (1.0 - tau) * wu, sv = (1.0 - tau) * wv, eu = tau * wu, ev = tau * wv;
+        gu[0] = (Xs[1] * Ju[2] - Xs[2] * Ju[1]) * su; gu[1] = (Xs[2] * Ju[0] - Xs[0] * Ju[2]) * su; gu[2] = (Xs[0] * Ju[1] - Xs[1] * Ju[0]) * su;
+        gv[0] = (Xs[1] * Jv[2] - Xs[2] * Jv[1]) * sv; gv[1] = (Xs[2] * Jv[0] - Xs[0] * Jv[2]) * sv; gv[2] = (Xs[0] * Jv[1] - Xs[1] * Jv[0]) * sv;
+        gu[6] = (Xe[1] * Ju[2] - Xe[2] * Ju[1]) * eu; gu[7] = (Xe[2] * Ju[0] - Xe[0] * Ju[2]) * eu; gu[8] = (Xe[0] * Ju[1] - Xe[1] * Ju[0]) * eu;
+        gv[6] = (Xe[1] * Jv[2] - Xe[2] * Jv[1]) * ev; gv[7] = (Xe[2] * Jv[0] - Xe[0] * Jv[2]) * ev; gv[8] = (Xe[0] * Jv[1] - Xe[1] * Jv[0]) * ev;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * su; gv[3 + i] = Jv[i] * sv; gu[9 + i] = Ju[i] * eu; gv[9 + i] = Jv[i] * ev; }
+      }
+#pragma unroll
+      for (int i = 0; i < NIN; i++) { gu[KO + i] = 0.0; gv[KO + i] = 0.0; }
+      gu[KO] = ku[0] * wu; gu[KO + 2] = wu; gv[KO + 1] = kv[1] * wv; gv[KO + 3] = wv;
+#pragma unroll
+      for (int i = 0; i < ND; i++) { gu[KO + 4 + i] = ku[4 + i] * wu; gv[KO + 4 + i] = kv[4 + i] * wv; }
+      // point rows: d r / d X_board = J_proj R_cfb  (rolling: R = (1 - tau) R_start + tau R_end)
+      double xu[3], xv[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        double r0 = vp.R[j], r1 = vp.R[3 + j], r2 = vp.R[6 + j];
+        if constexpr (ROLL) {
+          r0 = r0 * (1.0 - tau) + vpe.R[j] * tau; r1 = r1 * (1.0 - tau) + vpe.R[3 + j] * tau; r2 = r2 * (1.0 - tau) + vpe.R[6 + j] * tau;
+        }
+        xu[j] = (Ju[0] * r0 + Ju[1] * r1 + Ju[2] * r2) * wu;
+        xv[j] = (Jv[0] * r0 + Jv[1] * r1 + Jv[2] * r2) * wv;
+      }
+      const int pt = p.off_pt + 3 * (b * p.P + pi);
+      auto addS = [&](int i, int j, double val) {
+        atomicAdd(&Hss[(size_t)i * n_s + j], val);
+        atomicAdd(&Hss[(size_t)j * n_s + i], val);
+      };
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        atomicAdd(&g[pt + r], xu[r] * ru + xv[r] * rv);
+#pragma unroll
+        for (int q = r; q < 3; q++) {
+          const double val = xu[r] * xu[q] + xv[r] * xv[q];
+          if (q == r) atomicAdd(&Hss[(size_t)(pt + r) * n_s + pt + r], val); else addS(pt + r, pt + q, val);
+        }
+        double Q[KO];
+#pragma unroll
+        for (int kk = 0; kk < KO; kk++) Q[kk] = xu[r] * gu[kk] + xv[r] * gv[kk];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          double vc = 0.0, vb = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < KO; kk++) { vc += Q[kk] * Ac[(kk % 6) * 6 + j]; vb += Q[kk] * Ab[36 * (kk / 6) + (kk % 6) * 6 + j]; }
+          if (cp >= 0) addS(pt + r, cp + j, vc);
+          if (bpo >= 0) addS(pt + r, bpo + j, vb);
+        }
+        if (p.motion_on) {
+#pragma unroll
+          for (int col = 0; col < FB; col++) {
+            double vf = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 6; kk++) vf += Q[6 * (col / 6) + kk] * Af[36 * (col / 6) + kk * 6 + col % 6];
+            atomicAdd(&W[((size_t)f * n_s + pt + r) * FB + col], vf);
+          }
+        }
+        if (p.off_he >= 0) {
+#pragma unroll
+          for (int j = 0; j < 12; j++) {
+            double vh = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 6; kk++) vh += Q[kk] * Eh[kk * 12 + j];
+            addS(pt + r, p.off_he + j, vh);
+          }
+        }
+        if (in0 >= 0) {
+#pragma unroll
+          for (int i = 0; i < NIN; i++) {
+            const double val = xu[r] * gu[KO + i] + xv[r] * gv[KO + i];
+            if (val != 0.0) addS(pt + r, in0 + intr_param_index(p, i), val);
+          }
+        }
+      }
+    }
+  }
 }
 
 // k_expand_frames: one CTA per frame -> H_ff (FB x FB), g_f (FB) and W_f (n_s x FB), FB = 6 NP.  Warp w owns the cameras
@@ -1084,36 +1135,19 @@ k_expand_hand_eye(DeviceProblem p, SolverBuffers s, int chunks) {
   const int per = (l1 - l0 + chunks - 1) / chunks;
   const int a0 = l0 + chunk * per, a1 = min(l1, a0 + per);
   const PoseT& pc = p.cam_T[c];
-  const PoseT& pW = p.he_T[0];
-  const PoseT& pG = p.he_T[1];
   for (int li = a0 + warp; li < a1; li += EXP_WARPS) {
     const int v = p.cam_view_list[li];
     const int f = p.view_frame[v], b = p.view_board[v];
     for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
-    if (lane < 3) {
+    if (lane < 2) hand_eye_twist_maps(p, c, f, lane, Eh);
+    else if (lane == 2 && p.off_bp >= 0) {
       const PoseT& pf = p.frame_T[f];
-      double Rcf[9], tcf[3], A[36];
+      const PoseT& pb = p.board_T[b];
+      double Rcf[9], tcf[3], tb[3];
       view_chain(pc, pf, Rcf, tcf);
-      if (lane == 0) {           // W
-        const PoseT& pa = p.arm_T[f];
-        double Rcg[9], Rl[9];
-        mat3_mul(pc.R, pG.R, Rcg);
-        mat3_mul(Rcg, pa.R, Rl);
-        twist_map(Rl, pW.JL, tcf, A);
-        for (int kk = 0; kk < 6; kk++) for (int j = 0; j < 6; j++) Eh[kk * 12 + j] = A[kk * 6 + j];
-      } else if (lane == 1) {    // G
-        double tcg[3];
-        mat3_vec(pc.R, pG.t, tcg);
-        tcg[0] += pc.t[0]; tcg[1] += pc.t[1]; tcg[2] += pc.t[2];
-        twist_map(pc.R, pG.JL, tcg, A);
-        for (int kk = 0; kk < 6; kk++) for (int j = 0; j < 6; j++) Eh[kk * 12 + 6 + j] = A[kk * 6 + j];
-      } else if (p.off_bp >= 0) {
-        const PoseT& pb = p.board_T[b];
-        double tb[3];
-        mat3_vec(Rcf, pb.t, tb);
-        tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
-        twist_map(Rcf, pb.JL, tb, Ab);
-      }
+      mat3_vec(Rcf, pb.t, tb);
+      tb[0] += tcf[0]; tb[1] += tcf[1]; tb[2] += tcf[2];
+      twist_map(Rcf, pb.JL, tb, Ab);
     }
     __syncwarp();
     for (int o = lane; o < D * 12; o += 32) {            // Uh = M[:, xi] Eh

@@ -325,13 +325,16 @@ int expand(mcba_ctx* ctx) {
   if (P.off_pt >= 0 && P.V > 0) {         // boards=True: board-point blocks on top (atomics)
     ViewKernelArgs a{}; a.loss = ctx->cur_loss; a.f_scale = ctx->cur_f_scale;
     const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
+#define PB(MODEL) if (roll) k_point_blocks<MODEL, 2><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); \
+                  else k_point_blocks<MODEL, 1><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p);
     switch (P.model) {
-      case MODEL_STANDARD: k_point_blocks<MODEL_STANDARD><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
-      case MODEL_RATIONAL: k_point_blocks<MODEL_RATIONAL><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
-      case MODEL_THIN_PRISM: k_point_blocks<MODEL_THIN_PRISM><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
-      case MODEL_TILTED: k_point_blocks<MODEL_TILTED><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
-      default: k_point_blocks<MODEL_FISHEYE><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); break;
+      case MODEL_STANDARD: PB(MODEL_STANDARD) break;
+      case MODEL_RATIONAL: PB(MODEL_RATIONAL) break;
+      case MODEL_THIN_PRISM: PB(MODEL_THIN_PRISM) break;
+      case MODEL_TILTED: PB(MODEL_TILTED) break;
+      default: PB(MODEL_FISHEYE) break;
     }
+#undef PB
     CKL();
   }
   return MCBA_OK;
@@ -401,7 +404,6 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   P.off_pt = (opt & MCBA_OPT_BOARDS) ? off : -1; if (P.off_pt >= 0) off += 3 * B * Pn;
   P.off_he = (P.motion == MOTION_HAND_EYE && (opt & MCBA_OPT_MOTION)) ? off : -1; if (P.off_he >= 0) off += 12;
   P.n_s = off; P.n_f = P.motion_on ? P.fb * F : 0; P.n = P.n_s + P.n_f;
-  REQUIRE(P.off_pt < 0 || P.motion == MOTION_STATIC, MCBA_ERR_UNSUPPORTED, "boards=True is only implemented for static frames");
   // internal -> canonical permutation: canonical = [cp | bp | motion | cameras]
   ctx->perm.assign((size_t)P.n, 0);
   {

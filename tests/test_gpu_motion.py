@@ -123,12 +123,42 @@ def test_outlier_loop_on_the_resident_table_equals_the_host_loop(name, monkeypat
   assert np.abs(res.reprojection_error - host.reprojection_error).max() < 1e-2
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_board_points_as_parameters_under_a_motion_model(name):
+  """boards=True (board/charuco.py:112-117; sparsity axis 3, calibration.py:188-190) together with rolling / hand-eye frames: the
+  point blocks and their couplings with the 12-wide frame block resp. the hand-eye pair, against finite differences of the oracle."""
+  z, calib, prob = make(name)
+  calib = calib.enable(boards=True)
+  prob = prob.copy(optimize=dict(prob.optimize, boards=True))
+  x0 = prob.param_vec
+  assert np.abs(calib.param_vec - x0).max() < 1e-12
+  eng = calib._upload(calib.inliers)
+  x1 = x0 + np.random.default_rng(3).normal(0, 1e-4, x0.size)
+  assert np.abs(eng.residuals(calib._to_engine_vec(x1)) - prob.residuals(x1)).max() < 1e-9
+  S = prob.sparsity_matrix()
+  J = approx_derivative(prob.residuals, x1, method="3-point", sparsity=(S, group_columns(S))).toarray()
+  r = prob.residuals(x1)
+  H, g = J.T @ J, J.T @ r
+  JtJ_e, Jtr_e, cost = eng.linearize(calib._to_engine_vec(x1))
+  keep = np.ones(JtJ_e.shape[0], bool)
+  keep[-calib._board_block_slices().size:] = calib._board_block_slices()          # padded board slots have no counterpart in the reference vector
+  JtJ, Jtr = JtJ_e[np.ix_(keep, keep)], Jtr_e[keep]
+  nrm = np.sqrt(np.outer(np.diag(H), np.diag(H)))
+  live = nrm > 0
+  assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  assert np.abs(Jtr - g).max() < 1e-6 * np.abs(g).max()
+  assert abs(cost - 0.5 * r @ r) < 1e-12 * cost
+  out = calib.bundle_adjust()
+  assert out.last_solve.cost < 0.5 * z["r0"] @ z["r0"]
+  rr = prob.residuals(out.param_vec)
+  assert abs(0.5 * rr @ rr - out.last_solve.cost) <= 1e-9 * out.last_solve.cost      # the returned objects hold the solved state
+
+
 def test_motion_state_entry_points_refuse_the_wrong_problem():
   z, calib, prob = make("rolling_2x6")
   eng = calib._upload(calib.inliers)
   with pytest.raises(_native.NativeError): eng.set_hand_eye(np.tile(np.eye(4), (eng.desc.F, 1, 1)), np.eye(4), np.eye(4))
   assert np.abs(eng.get_rolling() - z["frame_poses_end"]).max() < 1e-12
-  with pytest.raises(NotImplementedError): calib.enable(boards=True).bundle_adjust()      # boards=True: static frames only
   z, calib, prob = make("handeye_2x6")
   eng = calib._upload(calib.inliers)
   with pytest.raises(_native.NativeError): eng.set_rolling(np.tile(np.eye(4), (eng.desc.F, 1, 1)), np.ones(eng.desc.C))
