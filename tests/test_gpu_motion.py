@@ -115,9 +115,9 @@ def test_outlier_loop_on_the_resident_table_equals_the_host_loop(name, monkeypat
   rng = np.random.default_rng(7)
   for c, f, b, p in idx[rng.choice(len(idx), 25, replace=False)]: pts[c, f, b, p] += rng.normal(0, 30.0, 2)     # gross outliers
   calib = calib.copy(point_table=calib.point_table._extend(points=pts))
-  res = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4))
+  res = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4), max_iterations=6)
   monkeypatch.setenv("MCBA_HOST_OUTLIERS", "1")
-  host = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4))
+  host = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4), max_iterations=6)
   assert np.array_equal(res.inliers, host.inliers) and res.inliers.sum() < calib.valid.sum()
   assert abs(res.last_solve.cost - host.last_solve.cost) <= 1e-6 * host.last_solve.cost
   assert np.abs(res.reprojection_error - host.reprojection_error).max() < 1e-2
@@ -148,7 +148,7 @@ def test_board_points_as_parameters_under_a_motion_model(name):
   assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
   assert np.abs(Jtr - g).max() < 1e-6 * np.abs(g).max()
   assert abs(cost - 0.5 * r @ r) < 1e-12 * cost
-  out = calib.bundle_adjust()
+  out = calib.bundle_adjust(max_iterations=5)                       # a few iterations of the ~1000-parameter system are enough here
   assert out.last_solve.cost < 0.5 * z["r0"] @ z["r0"]
   rr = prob.residuals(out.param_vec)
   assert abs(0.5 * rr @ rr - out.last_solve.cost) <= 1e-9 * out.last_solve.cost      # the returned objects hold the solved state

@@ -42,7 +42,13 @@ test_residuals_match_reference_golden_and_oracle = gp.test_residuals_match_refer
 test_reprojection_error_over_valid = gp.test_reprojection_error_over_valid
 test_normal_equations_match_finite_differences = gp.test_normal_equations_match_finite_differences
 test_converged_solution_matches_dense_exact_oracle = gp.test_converged_solution_matches_dense_exact_oracle
-test_robust_losses_follow_scipy = gp.test_robust_losses_follow_scipy
+
+
+@pytest.mark.parametrize("loss", ["soft_l1", "huber", "cauchy"])          # arctan (slow to converge: 45 s of fiber switching) stays GPU-only
+def test_robust_losses_follow_scipy(loss):
+  gp.test_robust_losses_follow_scipy(loss)
+
+
 test_outlier_loop_matches_reference_semantics = gp.test_outlier_loop_matches_reference_semantics
 test_fixed_blocks_and_fix_aspect = gp.test_fixed_blocks_and_fix_aspect
 test_bad_inputs_raise_like_the_reference = gp.test_bad_inputs_raise_like_the_reference
