@@ -152,8 +152,8 @@ __global__ void k_state_to_matrices(int C, int B, int F, const double* cam_rt, c
 // k_make_trial: trial parameter state = current state with the free blocks replaced by x (internal order), and the
 // pose tables of that state, in one launch.  One thread per pose, then one per camera (intrinsics), per board point, and one
 // for the hand-eye pair (which must be complete before the derived frame poses: those threads recompute it themselves).
-__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o, double* he_o) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void make_trial_item(const DeviceProblem& p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o,
+                                                double* bpts_o, double* he_o, int i) {
   const int nfp = p.F * p.npf;
   const int np = p.C + p.B + nfp;
   if (i < np) {
@@ -200,6 +200,9 @@ __global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, do
     pose_from_rt(v, t);
     p.he_T[j] = t;
   }
+}
+__global__ void k_make_trial(DeviceProblem p, const double* x, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o, double* he_o) {
+  make_trial_item(p, x, cam_o, board_o, frame_o, intr_o, bpts_o, he_o, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // compose T_cfb = T_c T_f T_b for one view (every lane of the warp computes the same small product)

@@ -82,6 +82,7 @@ struct mcba_ctx {
   int launches = 0;
   int num_sms = 148;
   bool use_mma = true;    // per-view moments on the fp64 tensor path (MCBA_MOMENTS=fma selects the DFMA kernels)
+  bool fuse = false;           // MCBA_FUSE=1: k_dots folded into k_quad, k_step + k_make_trial as one launch; A/B candidate
   bool chol_blocked = false;   // MCBA_CHOL=blocked: single-CTA blocked reduced solve (k_chol_blocked) instead of k_chol_small; A/B candidate
 
   bool uploaded = false;
@@ -368,12 +369,20 @@ int trial_cost(mcba_ctx* ctx, int loss, double f_scale, bool trial, int slot) {
 
 // quadratic forms of the scaled Hessian; single-GPU: the last CTA also sums the partials and runs the scalar step that
 // consumes them (finalize 2 = reg, 3 = subspace); multi-GPU: sum only, the caller all-reduces and launches k_reg / k_subspace
-int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int finalize) {
+int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int finalize, bool dots = false) {
   const DeviceProblem& P = ctx->P;
   const int nframe = P.motion_on ? P.F : 0;
   const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
   const int fb = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
   if (fb + nsh == 0) return MCBA_OK;
+  if (dots && two) {
+    if (P.fb == 12) k_quad<12, true><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
+                                                                                  finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
+    else k_quad<6, true><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
+                                                                     finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
+    CKL();
+    return MCBA_OK;
+  }
   if (P.fb == 12) k_quad<12><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
                                                                           finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
   else k_quad<6><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
@@ -445,7 +454,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->S.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1))); CK(ctx->rhs.alloc((size_t)std::max(P.n_s, 1)));
   CK(ctx->Linv.alloc((size_t)((std::max(P.n_s, 1) + CHOL_NB - 1) / CHOL_NB) * CHOL_NB * CHOL_NB));
   CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
-  CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 3));
+  CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 5));
   CK(ctx->state.alloc(1));
   CK(ctx->counter.alloc(4)); CK(cudaMemsetAsync(ctx->counter.p, 0, 4 * sizeof(unsigned), ctx->stream));
   if (!keep_state) {     // a re-selection of the resident table (mcba_table_select) keeps the parameter state
@@ -548,6 +557,7 @@ int mcba_create(int device, mcba_ctx** out) {
   ctx->stream = ctx->own_stream;
   { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
   { const char* e = getenv("MCBA_CHOL"); if (e && std::string(e) == "blocked") ctx->chol_blocked = true; }
+  { const char* e = getenv("MCBA_FUSE"); if (e && std::string(e) == "1") ctx->fuse = true; }
   cudaFuncSetAttribute(k_chol_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #define MMA_ATTR(MODEL) \
   cudaFuncSetAttribute(k_views_mma<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
@@ -1420,17 +1430,22 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       else k_backsub<6><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p);
       CKL();
     }
-    k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL();
-    r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1); if (r) return r;
+    // with no quadratic-form CTA at all (n == 0 is handled above; n_s == 0 and no frames cannot happen here) k_dots stays
+    const bool fuse_dots = ctx->fuse && (n_s > 0 || F > 0);
+    if (!fuse_dots) { k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL(); }
+    r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1, fuse_dots); if (r) return r;
     EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE);   // AGG AGN ANN DOTGN_F GN2_F
 
     // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
     // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.
     bool accepted = false, top_logged = false;
     while (true) {
-      k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
-      {
-        const int nt = P.C + P.B + P.F * P.npf + P.C + P.B * P.P + 2;
+      const int nt = P.C + P.B + P.F * P.npf + P.C + P.B * P.P + 2;
+      if (ctx->fuse) {
+        k_step_trial<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p,
+                                        ctx->P, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p, ctx->he_rt2.p, nt); CKL();
+      } else {
+        k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
         k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p, ctx->he_rt2.p); CKL();
       }
       r = moments_at(ctx, opts->loss, opts->f_scale, true); if (r) return r;

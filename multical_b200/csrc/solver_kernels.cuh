@@ -149,8 +149,10 @@ constexpr int QUAD_THREADS = 128;
 constexpr int QUAD_WARPS = QUAD_THREADS / 32;
 // blocks [0, frame_blocks): one WARP per frame (W_f^T u_s by lane-strided sums + shuffles, then the 6x6 part);
 // remaining blocks: one thread per shared row (column walk of the symmetric H_ss is coalesced).
-// partial[frame or F + shared block][3].  FB = parameters per frame block (6; 12 for RollingFrames' start+end pose)
-template <int FB>
+// partial[frame or F + shared block][QS].  FB = parameters per frame block (6; 12 for RollingFrames' start+end pose).
+// DOTS (opt-in MCBA_FUSE=1, with two != 0): the records also carry u.v and v.v of the same rows (QS = 5), which is what k_dots
+// computes for (gh, gn) in a launch of its own; the last block then fills RED_DOTGN_* / RED_GN2_* as well.
+template <int FB, bool DOTS = false>
 __global__ void __launch_bounds__(QUAD_THREADS)
 k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, const double* W, const double* d,
        const double* u, const double* v, int two, double* partial,
@@ -158,6 +160,7 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
   __shared__ double sm[32];
   __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int QS = DOTS ? 5 : 3;
   const int nframe = motion_on ? F : 0;
   const int frame_blocks = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
   if ((int)blockIdx.x < frame_blocks) {
@@ -191,7 +194,13 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
           uv += uf[i] * hv + uf[i] * tv[i] + vf[i] * tu[i];
           vv += vf[i] * (hv + 2.0 * tv[i]);
         }
-        partial[(size_t)f * 3 + 0] = uu; partial[(size_t)f * 3 + 1] = uv; partial[(size_t)f * 3 + 2] = vv;
+        partial[(size_t)f * QS + 0] = uu; partial[(size_t)f * QS + 1] = uv; partial[(size_t)f * QS + 2] = vv;
+        if constexpr (DOTS) {
+          double dt = 0, g2 = 0;
+#pragma unroll
+          for (int j = 0; j < FB; j++) { const int i = n_s + FB * f + j; dt += u[i] * v[i]; g2 += v[i] * v[i]; }
+          partial[(size_t)f * QS + 3] = dt; partial[(size_t)f * QS + 4] = g2;
+        }
       }
     }
   } else {
@@ -209,9 +218,14 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
       uu = ui * hu; uv = ui * hv; vv = vi * hv;
     }
     double r;
-    r = block_sum(uu, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 0] = r;
-    r = block_sum(uv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 1] = r;
-    r = block_sum(vv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * 3 + 2] = r;
+    r = block_sum(uu, sm); if (tid == 0) partial[(size_t)(nframe + sb) * QS + 0] = r;
+    r = block_sum(uv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * QS + 1] = r;
+    r = block_sum(vv, sm); if (tid == 0) partial[(size_t)(nframe + sb) * QS + 2] = r;
+    if constexpr (DOTS) {
+      const double dt = i < n_s ? u[i] * v[i] : 0.0, g2 = i < n_s ? v[i] * v[i] : 0.0;
+      r = block_sum(dt, sm); if (tid == 0) partial[(size_t)(nframe + sb) * QS + 3] = r;
+      r = block_sum(g2, sm); if (tid == 0) partial[(size_t)(nframe + sb) * QS + 4] = r;
+    }
   }
   if (!finalize) return;
   // last-block reduction: deterministic (index-ordered) sum of all partial records, then the scalar step that needs it
@@ -224,10 +238,22 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
   const int nout = two ? 3 : 1;
   for (int j = 0; j < nout; j++) {
     double acc = 0.0;
-    for (int i = tid; i < nparts; i += QUAD_THREADS) acc += __ldcg(&partial[(size_t)i * 3 + j]);
+    for (int i = tid; i < nparts; i += QUAD_THREADS) acc += __ldcg(&partial[(size_t)i * QS + j]);
     acc = block_sum(acc, sm);
     if (tid == 0) red[RED_AGG + j] = acc;
     __syncthreads();
+  }
+  if constexpr (DOTS) {          // frame records -> the _F slots (summed over ranks), shared records -> the replicated _S slots
+    for (int j = 0; j < 2; j++) {
+      double af = 0.0, as = 0.0;
+      for (int i = tid; i < nparts; i += QUAD_THREADS) { const double val = __ldcg(&partial[(size_t)i * QS + 3 + j]); if (i < nframe) af += val; else as += val; }
+      af = block_sum(af, sm);
+      if (tid == 0) red[j == 0 ? RED_DOTGN_F : RED_GN2_F] = af;
+      __syncthreads();
+      as = block_sum(as, sm);
+      if (tid == 0) red[j == 0 ? RED_DOTGN_S : RED_GN2_S] = as;
+      __syncthreads();
+    }
   }
   if (tid == 0) {
     *counter = 0;
@@ -990,6 +1016,32 @@ __global__ void k_step(int n, int n_s, SolverState* st, const double* x, const d
   r = block_sum(s2f, sm); if (threadIdx.x == 0) red[RED_STEP2_F] = r;
   r = block_sum(x2s, sm); if (threadIdx.x == 0) red[RED_XN2_S] = r;
   r = block_sum(x2f, sm); if (threadIdx.x == 0) red[RED_XN2_F] = r;
+}
+
+// k_step and k_make_trial as ONE single-CTA launch (opt-in MCBA_FUSE=1): the trial state only needs x_new, which this CTA has
+// just written; a few hundred poses are nothing for 1024 threads, and the launch in between disappears.
+__global__ void __launch_bounds__(1024)
+k_step_trial(int n, int n_s, SolverState* st, const double* x, const double* d, const double* gh, const double* gn, double* x_new, double* red,
+             DeviceProblem p, double* cam_o, double* board_o, double* frame_o, double* intr_o, double* bpts_o, double* he_o, int n_items) {
+  __shared__ double sm[32];
+  if (st->done) return;
+  if (threadIdx.x == 0) tr_step_compute(st);
+  __syncthreads();
+  const double al = st->alpha, be = st->beta;
+  double s2s = 0, s2f = 0, x2s = 0, x2f = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double stp = d[i] * (al * gh[i] + be * gn[i]);
+    const double xi = x[i];
+    x_new[i] = xi + stp;
+    if (i < n_s) { s2s += stp * stp; x2s += xi * xi; } else { s2f += stp * stp; x2f += xi * xi; }
+  }
+  double r;
+  r = block_sum(s2s, sm); if (threadIdx.x == 0) red[RED_STEP2_S] = r;
+  r = block_sum(s2f, sm); if (threadIdx.x == 0) red[RED_STEP2_F] = r;
+  r = block_sum(x2s, sm); if (threadIdx.x == 0) red[RED_XN2_S] = r;
+  r = block_sum(x2f, sm); if (threadIdx.x == 0) red[RED_XN2_F] = r;
+  __syncthreads();                      // x_new complete (block-wide visibility of this CTA's global writes)
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) make_trial_item(p, x_new, cam_o, board_o, frame_o, intr_o, bpts_o, he_o, i);
 }
 
 // trf.py inner loop after fun(x_new): actual reduction, update_tr_radius, check_termination.

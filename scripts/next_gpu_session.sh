@@ -2,7 +2,7 @@
 # First GPU call of the next session: everything that was written after the round-1 GPU budget was spent and is so far verified
 # only on the SIMT interpreter (tests/test_simt_kernels.py).  One call, outputs under gpurun_out/.
 #   1. the GPU suite, new files last (tests/conftest.py)          -> gpurun_out/pytest_gpu.log
-#   2. A/B of the opt-in reduced solve (MCBA_CHOL=blocked)         -> gpurun_out/bench_chol_{small,blocked}.json
+#   2. A/B of the opt-in candidates (MCBA_CHOL=blocked, MCBA_FUSE=1) -> gpurun_out/bench_chol_{small,blocked}.json, bench_fuse*.json
 #   3. launch lists of both                                         -> gpurun_out/launches_chol_*.csv
 #   4. timing of the two motion models and of the batched pose initialisation -> gpurun_out/motion_pnp_timing.txt
 mkdir -p gpurun_out
@@ -10,6 +10,8 @@ timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2
 timeout 1200 python -m pytest tests -q -m gpu --tb=short > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
 timeout 300 python bench.py > gpurun_out/bench_chol_small.json 2> gpurun_out/bench_chol_small.err; python scripts/show_bench.py gpurun_out/bench_chol_small.json
 MCBA_CHOL=blocked timeout 300 python bench.py > gpurun_out/bench_chol_blocked.json 2> gpurun_out/bench_chol_blocked.err; python scripts/show_bench.py gpurun_out/bench_chol_blocked.json
+MCBA_FUSE=1 timeout 300 python bench.py > gpurun_out/bench_fuse.json 2> gpurun_out/bench_fuse.err; python scripts/show_bench.py gpurun_out/bench_fuse.json
+MCBA_FUSE=1 MCBA_CHOL=blocked timeout 300 python bench.py > gpurun_out/bench_fuse_blocked.json 2> gpurun_out/bench_fuse_blocked.err; python scripts/show_bench.py gpurun_out/bench_fuse_blocked.json
 for v in small blocked; do
   MCBA_CHOL=$v timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_chol_$v.csv \
     python scripts/profile_one.py cfg2 solve > gpurun_out/ncu_chol_$v.log 2>&1

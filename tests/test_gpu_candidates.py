@@ -1,7 +1,9 @@
 """GPU (-m gpu): opt-in kernel variants that wait for an A/B measurement must at least be exact replacements.
 
 MCBA_CHOL=blocked -- k_chol_blocked, the single-CTA blocked reduced solve with warp-level column steps, instead of k_chol_small: the
-iteration table of a solve must agree with the default kernel's to round-off."""
+iteration table of a solve must agree with the default kernel's to round-off.
+MCBA_FUSE=1 -- two launches fewer per LM iteration (k_dots folded into the second k_quad, k_step + k_make_trial as one single-CTA
+launch): same iterations up to the summation order of two dot products."""
 import numpy as np
 import pytest
 
@@ -11,11 +13,28 @@ from multical_b200 import calibration
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6", "poses_only_2x6"])
+def test_fused_launches_reproduce_the_default_iterations(name, monkeypatch):
+  def solve():
+    scene, z, calib, prob = gp.make(name)
+    return calib.bundle_adjust(tolerance=1e-9, max_iterations=40).last_solve      # away from ties between the ftol and xtol tests
+  ref = solve()
+  monkeypatch.setenv("MCBA_FUSE", "1")                  # read by mcba_create: a fresh context is needed
+  for eng in calibration._engines.values(): eng.close()
+  monkeypatch.setattr(calibration, "_engines", {})
+  got = solve()
+  for eng in calibration._engines.values(): eng.close()
+  calibration._engines.clear()
+  assert got.nfev == ref.nfev and got.status == ref.status
+  assert got.kernel_launches < ref.kernel_launches
+  assert np.allclose(np.array(ref.log, float)[:, 2], np.array(got.log, float)[:, 2], rtol=1e-9, atol=0)
+
+
 @pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6", "fisheye_3x5"])
 def test_blocked_reduced_solve_reproduces_the_default_iterations(name, monkeypatch):
   def solve():
     scene, z, calib, prob = gp.make(name)
-    return calib.bundle_adjust(tolerance=1e-12, max_iterations=40).last_solve
+    return calib.bundle_adjust(tolerance=1e-9, max_iterations=40).last_solve      # away from ties between the ftol and xtol tests
   ref = solve()
   monkeypatch.setenv("MCBA_CHOL", "blocked")            # read by mcba_create: a fresh context is needed
   for eng in calibration._engines.values(): eng.close()
