@@ -588,6 +588,129 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_views_f32 (opt-in MCBA_MOMENTS=f32, 5-coefficient and fisheye models, static / hand-eye frames): the same per-view records
+// with the Gauss-Newton Hessian moments sum G^T G accumulated in FP32 and everything that defines the minimiser -- residual,
+// cost, gradient moments sum G^T r -- in FP64.  k_views_mma is bound by the fp64 pipe that DFMA and DMMA share (DESIGN.md §6:
+// ~384 DMMA-lane FMAs + ~160 DFMA per corner); here the 2 x D(D+1)/2 Hessian FMAs per corner go to the fp32 pipe, which runs
+// beside it, and the fp64 pipe keeps the Jacobian and 2 x (D+1) gradient FMAs.  An inexact Hessian changes the path of the
+// trust-region iteration, not its fixed point (J^T r = 0 is evaluated exactly); measured on the oracle with Jacobians rounded to
+// 24 bits before forming J^T J: same minimum, same number of evaluations within +-1.  One warp per view, one
+// corner per lane and step, per-lane accumulators, transposed shared-memory reduction at the end of the view.
+template <int MODEL>
+__global__ void __launch_bounds__(VIEW_WARPS * 32)
+k_views_f32(DeviceProblem p, ViewKernelArgs a) {
+  constexpr int ND = model_nd(MODEL);
+  constexpr int D = 10 + ND;
+  constexpr int E = D * (D + 1) / 2;
+  constexpr int T = E + D + 1;
+  constexpr int KINT = 5 + ND;
+  static_assert(E <= 136, "per-lane fp32 accumulators: 5-coefficient and fisheye models only");
+  __shared__ float redf[VIEW_WARPS][32 * 33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * VIEW_WARPS + warp, nw = gridDim.x * VIEW_WARPS;
+  for (int v = gw; v < p.V; v += nw) {
+    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
+    const int beg = p.view_start[v], end = p.view_start[v + 1];
+    ViewPose vp;
+    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
+    double k[KINT];
+#pragma unroll
+    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
+    const double* bp = p.board_pts + (size_t)b * p.P * 3;
+    float hacc[E];
+    double gacc[D + 1];
+#pragma unroll
+    for (int i = 0; i < E; i++) hacc[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i <= D; i++) gacc[i] = 0.0;
+    for (int idx = beg + lane; idx < end; idx += 32) {
+      const double2 ob = p.obs[idx];
+      const int pi = p.pid[idx];
+      const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
+      double Xc[3];
+      mat3_vec(vp.R, X, Xc);
+      Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
+      double u, w_, Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
+      project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
+      double ru = u - ob.x, rv = w_ - ob.y, wu = 1.0, wv = 1.0;
+      if (a.loss == 0) {
+        gacc[D] += 0.5 * (ru * ru + rv * rv);
+      } else {
+        const double is = 1.0 / a.f_scale, fs2 = a.f_scale * a.f_scale;
+        double zu = ru * is, zv = rv * is;
+        zu *= zu; zv *= zv;
+        double r0u, r1u, r2u, r0v, r1v, r2v;
+        loss_rho(a.loss, zu, r0u, r1u, r2u);
+        loss_rho(a.loss, zv, r0v, r1v, r2v);
+        gacc[D] += 0.5 * fs2 * (r0u + r0v);
+        double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
+        ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
+        jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
+        wu = sqrt(ju); wv = sqrt(jv);
+        ru *= r1u / wu; rv *= r1v / wv;
+      }
+      double gu[D], gv[D];
+      gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
+      gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
+      gu[6] = ku[0] * wu; gu[7] = 0.0; gu[8] = wu; gu[9] = 0.0;
+      gv[6] = 0.0; gv[7] = kv[1] * wv; gv[8] = 0.0; gv[9] = wv;
+#pragma unroll
+      for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
+      float fu[D], fv[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        fu[i] = (float)gu[i]; fv[i] = (float)gv[i];
+        // gradient moments in fp64 (structural zeros: fx, cx only in the u row; fy, cy only in the v row)
+        double s = gacc[i];
+        if (!(i == 7 || i == 9)) s = fma(gu[i], ru, s);
+        if (!(i == 6 || i == 8)) s = fma(gv[i], rv, s);
+        gacc[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+#pragma unroll
+        for (int j = i; j < D; j++) {
+          const bool iu = !(i == 7 || i == 9), iv = !(i == 6 || i == 8);
+          const bool ju_ = !(j == 7 || j == 9), jv_ = !(j == 6 || j == 8);
+          float s = hacc[tri_index(D, i, j)];
+          if (iu && ju_) s = fmaf(fu[i], fu[j], s);
+          if (iv && jv_) s = fmaf(fv[i], fv[j], s);
+          hacc[tri_index(D, i, j)] = s;
+        }
+      }
+    }
+    // ---- reduce over the lanes: Hessian moments through shared memory (transposed, 32 accumulators per round), the D + 1
+    // fp64 sums by shuffles
+    double* out = a.moments + (size_t)v * T;
+    float* sm = redf[warp];
+#pragma unroll
+    for (int r0 = 0; r0 < E; r0 += 32) {
+#pragma unroll
+      for (int q = 0; q < 32; q++)
+        if (r0 + q < E) sm[q * 33 + lane] = hacc[r0 + q];
+      __syncwarp();
+      if (r0 + lane < E) {
+        float s = 0.0f;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) s += sm[lane * 33 + j];
+        out[r0 + lane] = (double)s;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i <= D; i++) {
+      double s = gacc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) out[E + i] = s;
+    }
+    if (lane == 0 && a.view_cost) a.view_cost[v] = out[T - 1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Block maps shared by the two expand kernels.
 struct SolverBuffers {
   double* moments;   // [V][T]

@@ -80,8 +80,10 @@ struct mcba_ctx {
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
   int launches = 0;
+  bool solving = false;   // inside mcba_solve (the fp32-Hessian candidate is never used by the parity hooks)
   int num_sms = 148;
   bool use_mma = true;    // per-view moments on the fp64 tensor path (MCBA_MOMENTS=fma selects the DFMA kernels)
+  bool moments_f32 = false;    // MCBA_MOMENTS=f32: k_views_f32 (Hessian moments in FP32, gradient / cost in FP64) where it applies; A/B candidate
   bool fuse = false;           // MCBA_FUSE=1: k_dots folded into k_quad, k_step + k_make_trial as one launch; A/B candidate
   bool chol_blocked = false;   // MCBA_CHOL=blocked: single-CTA blocked reduced solve (k_chol_blocked) instead of k_chol_small; A/B candidate
 
@@ -244,6 +246,14 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
 
 int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a) {
   if (!ctx->use_mma) return launch_views<MODE_MOMENTS>(ctx, P, a);
+  if (ctx->moments_f32 && ctx->solving && P.motion != MOTION_ROLLING && (P.model == MODEL_STANDARD || P.model == MODEL_FISHEYE)) {
+    // only inside mcba_solve: the parity hook mcba_linearize always returns the fp64 normal equations
+    const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
+    if (P.model == MODEL_STANDARD) k_views_f32<MODEL_STANDARD><<<blocks, VIEW_WARPS * 32, 0, ctx->stream>>>(P, a);
+    else k_views_f32<MODEL_FISHEYE><<<blocks, VIEW_WARPS * 32, 0, ctx->stream>>>(P, a);
+    CKL();
+    return MCBA_OK;
+  }
   const int th = VIEW_WARPS * 32;
   const bool roll = P.motion == MOTION_ROLLING;
   const int nc = mma_nc(P.model, roll), npair = (nc / 8) * (nc / 8 + 1) / 2;
@@ -555,7 +565,7 @@ int mcba_create(int device, mcba_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
-  { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; }
+  { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; if (e && std::string(e) == "f32") ctx->moments_f32 = true; }
   { const char* e = getenv("MCBA_CHOL"); if (e && std::string(e) == "blocked") ctx->chol_blocked = true; }
   { const char* e = getenv("MCBA_FUSE"); if (e && std::string(e) == "1") ctx->fuse = true; }
   cudaFuncSetAttribute(k_chol_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -1316,6 +1326,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   cudaStream_t s = ctx->stream;
   const int n = P.n, n_s = P.n_s, F = P.motion_on ? P.F : 0;
   memset(result, 0, sizeof(*result));
+  struct SolvingFlag { bool& f; explicit SolvingFlag(bool& r) : f(r) { f = true; } ~SolvingFlag() { f = false; } } solving_flag(ctx->solving);
   ctx->launches = 0;
   ctx->errors_current = false;
   struct EventPair {       // destroyed on every return path
@@ -1533,6 +1544,7 @@ int mcba_bench_launch(mcba_ctx* ctx, int which, int repeats) {
   int r;
   if (!(which & MCBA_BENCH_NO_PREPARE)) { r = prepare(ctx, P); if (r) return r; }
   which &= ~MCBA_BENCH_NO_PREPARE;
+  struct SolvingFlag { bool& f; explicit SolvingFlag(bool& r) : f(r) { f = true; } ~SolvingFlag() { f = false; } } solving_flag(ctx->solving);   // time what a solve runs
   for (int i = 0; i < repeats; i++) {
     ViewKernelArgs a{}; a.loss = 0; a.f_scale = 1.0;
     if (which == MCBA_BENCH_LINEARIZE) { a.moments = ctx->moments.p; r = launch_moments(ctx, P, a); }

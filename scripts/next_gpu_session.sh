@@ -17,4 +17,5 @@ for v in small blocked; do
     python scripts/profile_one.py cfg2 solve > gpurun_out/ncu_chol_$v.log 2>&1
   python scripts/summarize_launches.py gpurun_out/launches_chol_$v.csv 2>/dev/null | head -12
 done
+for m in mma f32; do echo "== moments $m (cfg4: 5.5 M corners)"; MCBA_MOMENTS=$m timeout 300 python scripts/profile_one.py cfg4 time 2>&1 | tail -1; MCBA_MOMENTS=$m timeout 300 python scripts/profile_one.py cfg4 solve 2>&1 | tail -1; done
 timeout 300 python scripts/motion_pnp_timing.py > gpurun_out/motion_pnp_timing.txt 2>&1; cat gpurun_out/motion_pnp_timing.txt

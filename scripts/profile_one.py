@@ -19,6 +19,23 @@ if mode == "kernels":
     eng.bench_launch(0, 1)      # linearise: k_prepare + k_views<MOMENTS> parts
     eng.bench_launch(2, 1)      # trial cost: k_prepare + k_views<COST>
   eng.residuals()
+elif mode == "time":            # CUDA-event time of the linearisation kernel alone (what bench.py reports as roofline.launch_ms)
+  import torch
+  stream = torch.cuda.Stream()
+  eng.lib.mcba_set_stream(eng.h, stream.cuda_stream)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+  eng.bench_launch(0, 3)
+  ts = []
+  with torch.cuda.stream(stream):
+    for _ in range(10):
+      flush.zero_()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(stream); eng.bench_launch(0 | 256, 1); e1.record(stream); e1.synchronize()
+      ts.append(e0.elapsed_time(e1) * 1e3)
+  info = eng.bench_info(0)
+  med = float(np.median(ts))
+  print("moments=%s linearise kernel: median %.1f us (min %.1f) over %d corners -> %.1f GB/s algorithmic" % (
+    os.environ.get("MCBA_MOMENTS", "mma"), med, min(ts), info["corners"], info["bytes_per_launch"] / med / 1e3), flush=True)
 else:
   import torch
   for i in range(3):

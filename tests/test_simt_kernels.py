@@ -82,6 +82,7 @@ test_pnp_minimum_detections_rule_and_bad_inputs = gn.test_minimum_detections_rul
 # ---- tests/test_gpu_candidates.py on the interpreter (opt-in variants)
 test_blocked_reduced_solve_reproduces_the_default_iterations = gc.test_blocked_reduced_solve_reproduces_the_default_iterations
 test_fused_launches_reproduce_the_default_iterations = gc.test_fused_launches_reproduce_the_default_iterations
+test_fp32_hessian_moments_reach_the_same_minimum = gc.test_fp32_hessian_moments_reach_the_same_minimum
 
 
 @pytest.mark.parametrize("sms", ["1", "148"])
