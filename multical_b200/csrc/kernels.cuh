@@ -242,6 +242,19 @@ __device__ __forceinline__ void corner_point(const ViewPose& vp, const ViewPose&
   }
 }
 
+// Optional tails of the linearisation kernels (opt-in MCBA_FUSE=1, single GPU), defined in solver_kernels.cuh: the last CTA to
+// finish runs the scalar step that would otherwise be a launch of its own.  __noinline__: the tails stay calls, so the code of the
+// kernels they hang off (the profiled hot loops) is not re-scheduled around them.
+struct SolverState;
+__device__ __noinline__ void view_accept_epilogue(SolverState* st, double* red, unsigned* counter, const double* view_cost, int V);
+struct ScaleEpilogue {
+  int enabled, n, first, n_cost_part, fb;
+  const double* x; const double* Hff; const double* cost_part;
+  double* sinv; double* d; double* gh; double* red;
+  SolverState* st; unsigned* counter;
+};
+__device__ __noinline__ void scale_epilogue(const ScaleEpilogue& e, int n_s, const double* Hss, const double* g);
+
 struct ViewKernelArgs {
   int loss;
   double f_scale;
@@ -249,6 +262,8 @@ struct ViewKernelArgs {
   double* view_cost;   // MODE_COST   : [V]
   double* resid;       // MODE_RESID  : [2N] canonical order
   double* err;         // MODE_ERROR  : [N]  canonical order
+  // moment kernels, MCBA_FUSE=1: the acceptance test (k_accept) as the tail of the last CTA; null = off
+  SolverState* acc_st; double* acc_red; unsigned* acc_counter;
 };
 enum { MODE_COST = 0, MODE_MOMENTS = 1, MODE_RESID = 2, MODE_ERROR = 3 };
 
@@ -585,6 +600,7 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
     }
     if (lane == 0) { out[T - 1] = cost_acc; if (a.view_cost) a.view_cost[v] = cost_acc; }     // compact copy for the acceptance test
   }
+  if (a.acc_st) view_accept_epilogue(a.acc_st, a.acc_red, a.acc_counter, a.view_cost, p.V);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,6 +724,7 @@ k_views_f32(DeviceProblem p, ViewKernelArgs a) {
     }
     if (lane == 0 && a.view_cost) a.view_cost[v] = out[T - 1];
   }
+  if (a.acc_st) view_accept_epilogue(a.acc_st, a.acc_red, a.acc_counter, a.view_cost, p.V);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1077,7 +1094,7 @@ __host__ __device__ inline int exps_warp_doubles(int T, int D, int B, int NP) { 
 // end and added into H_ss / g_s with fp64 atomics.
 template <int NP>
 __global__ void __launch_bounds__(EXP_THREADS)
-k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
+k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) {
   constexpr int KO = 6 * NP;
   extern __shared__ double sh[];
   const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
@@ -1224,6 +1241,7 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
       if (tid < 6 && gb[b * 6 + tid] != 0.0) atomicAdd(&s.g[bp + tid], gb[b * 6 + tid]);
     }
   }
+  if (ep.enabled) scale_epilogue(ep, n_s, s.Hss, s.g);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -306,15 +306,18 @@ size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((si
 size_t expand_hand_eye_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exph_warp_doubles(P.T, P.D, P.B)); }
 
 // per-view moment records of the (trial or current) state; the pose tables must already describe that state
-int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial) {
+int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial, bool accept_tail = false) {
   ctx->cur_loss = loss; ctx->cur_f_scale = f_scale;
   DeviceProblem P = with_state(ctx, trial);
   ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p; a.view_cost = ctx->view_cost.p;
+  if (accept_tail) { a.acc_st = ctx->state.p; a.acc_red = ctx->red.p; a.acc_counter = ctx->counter.p + 2; }
   return launch_moments(ctx, P, a);
 }
 
 // moment records -> H_ss, g, H_ff, W and the per-CTA cost partials (pose tables = the state the moments were taken at)
-int expand(mcba_ctx* ctx) {
+// scale_first >= 0 (MCBA_FUSE=1, single GPU): the Jacobian scaling / begin-of-iteration step (k_scale) runs as the tail of
+// k_expand_shared when that is the last kernel adding to H_ss; returns through *scaled whether it did
+int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
   DeviceProblem P = with_state(ctx, false);
   SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p};
   cudaStream_t s = ctx->stream;
@@ -327,8 +330,15 @@ int expand(mcba_ctx* ctx) {
     CKL();
   }
   const int nb = P.C * ctx->shared_chunks;
-  if (roll) k_expand_shared<2><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks);
-  else k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks);
+  ScaleEpilogue ep{};
+  if (scale_first >= 0 && P.off_he < 0 && P.off_pt < 0 && P.n > 0) {
+    ep.enabled = 1; ep.n = P.n; ep.first = scale_first; ep.n_cost_part = nb; ep.fb = std::max(P.fb, 1);
+    ep.x = ctx->x.p; ep.Hff = ctx->Hff.p; ep.cost_part = ctx->cost_part.p;
+    ep.sinv = ctx->sinv.p; ep.d = ctx->d.p; ep.gh = ctx->gh.p; ep.red = ctx->red.p; ep.st = ctx->state.p; ep.counter = ctx->counter.p + 3;
+  }
+  if (scaled) *scaled = ep.enabled != 0;
+  if (roll) k_expand_shared<2><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
+  else k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
   CKL();
   if (P.off_he >= 0 && P.V > 0) {         // hand-eye: the 12 shared motion parameters and their couplings on top (atomics)
     k_expand_hand_eye<<<nb, EXP_THREADS, expand_hand_eye_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
@@ -1345,12 +1355,14 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   // x0 from the current state
   if (n) { k_gather_params<<<(n + 255) / 256, 256, 0, s>>>(P, ctx->x.p, P.cam_rt, P.board_rt, P.frame_rt, P.intr); CKL(); }
   r = prepare(ctx, with_state(ctx, false)); if (r) return r;
+  const bool single = ctx->world == 1;
+  const bool fuse_tails = ctx->fuse && single;          // k_scale / k_accept as tails of k_expand_shared / the moment kernel
+  bool scale_done = false;                              // the scaling of the linearisation in flight already ran as a tail
   r = moments_at(ctx, opts->loss, opts->f_scale, false); if (r) return r;
-  r = expand(ctx); if (r) return r;
+  r = expand(ctx, fuse_tails ? 1 : -1, &scale_done); if (r) return r;
 
   // One host synchronisation per trial step: everything from the Jacobian scaling to the acceptance test of the next
   // trial point is queued behind the previous step; k_begin_iteration's `done` flag turns the tail into no-ops.
-  const bool single = ctx->world == 1;
   const int ncp = P.C * ctx->shared_chunks;
   double last_reduction = NAN, last_step = NAN;
   int nlog = 0;
@@ -1364,7 +1376,9 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (log && log_capacity > 0) { log[0] = mcba_log_row{0, 1, h.cost, NAN, NAN, 0.0}; nlog = 1; }
   }
   while (!finished) {
-    if (single) {
+    if (single && scale_done) {
+      scale_done = false;                               // done by the tail of k_expand_shared
+    } else if (single) {
       k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
                                  1, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1)); CKL();
     } else {
@@ -1459,8 +1473,11 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
         k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p, ctx->he_rt2.p); CKL();
       }
-      r = moments_at(ctx, opts->loss, opts->f_scale, true); if (r) return r;
-      if (single) {
+      const bool accept_tail = fuse_tails && ctx->use_mma;
+      r = moments_at(ctx, opts->loss, opts->f_scale, true, accept_tail); if (r) return r;
+      if (accept_tail) {
+        // the acceptance test ran as the tail of the moment kernel
+      } else if (single) {
         // per-view costs: compact array written by the DMMA kernel, or the last entry of each moment record (DFMA kernels)
         if (ctx->use_mma) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->view_cost.p, P.V, 1);
         else k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p + (P.T - 1), P.V, P.T);
@@ -1485,6 +1502,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       if (accepted || h.nfev >= h.max_nfev) break;
     }
     if (finished) break;
+    bool state_sent = false;
     if (accepted) {
       // x = x_new ; cost = cost_new ; J = jac(x)   (trf.py): the trial state, its pose tables and its moments become current
       std::swap(ctx->x.p, ctx->x_new.p);
@@ -1496,7 +1514,13 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       h.cost = h.cost_new;
       h.njev += 1;
       last_reduction = h.actual_reduction; last_step = h.step_norm;
-      r = expand(ctx); if (r) return r;
+      if (fuse_tails) {
+        // the tail of k_expand_shared runs begin_iteration on the device state: the host's copy has to be there first
+        h.iteration += 1; h.accepted = 0;
+        CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+        state_sent = true;
+      }
+      r = expand(ctx, fuse_tails ? 0 : -1, &scale_done); if (r) return r;
     } else {
       last_reduction = 0.0; last_step = 0.0;
       if (h.status == -99 && h.nfev >= h.max_nfev) {
@@ -1504,9 +1528,11 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         r = prepare(ctx, with_state(ctx, false)); if (r) return r;
       }
     }
-    h.iteration += 1;
-    h.accepted = 0;
-    CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    if (!state_sent) {
+      h.iteration += 1;
+      h.accepted = 0;
+      CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    }
   }
   if (!finished || n > 0) {
     // leave the context consistent: pose tables of the final (current) state

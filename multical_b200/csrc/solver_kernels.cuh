@@ -104,15 +104,15 @@ __global__ void k_begin_iteration(SolverState* st, double* red) { begin_iteratio
 // also g_h = d*g, ||g||_inf, ||g_h||^2 and ||x*scale_inv||^2 (initial Delta, trf.py).  Single CTA.
 // Single-GPU fast path (fused != 0): reads diag(H_ss) in place, sums the per-CTA cost partials of k_expand_shared and
 // runs the begin-of-iteration logic itself; with several ranks those three need all-reduces in between.
-__global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss, const double* Hff, const double* g, const double* x,
-                        double* sinv, double* d, double* gh, int first, double* red,
-                        int fused, const double* cost_part, int n_cost_part, SolverState* st, int fb) {
+__device__ __forceinline__ void scale_body(int n, int n_s, const double* diag_s, const double* Hss, const double* Hff, const double* g, const double* x,
+                                           double* sinv, double* d, double* gh, int first, double* red,
+                                           int fused, const double* cost_part, int n_cost_part, SolverState* st, int fb) {
   __shared__ double sm[32];
   if (fused && st->done) return;
   double gh2s = 0, gh2f = 0, gms = 0, gmf = 0, xs2s = 0, xs2f = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double hd;
-    if (i < n_s) hd = fused ? Hss[(size_t)i * n_s + i] : diag_s[i];
+    if (i < n_s) hd = fused ? __ldcg(&Hss[(size_t)i * n_s + i]) : diag_s[i];       // (written by other CTAs' atomics when this runs as an epilogue)
     else { const int f = (i - n_s) / fb, j = (i - n_s) % fb; hd = Hff[(size_t)f * fb * fb + j * (fb + 1)]; }
     double nrm = sqrt(fmax(hd, 0.0));
     double si;
@@ -120,7 +120,7 @@ __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss,
     sinv[i] = si;
     const double di = 1.0 / si;
     d[i] = di;
-    const double gi = g[i], ghi = di * gi, xs = x[i] * si;
+    const double gi = __ldcg(&g[i]), ghi = di * gi, xs = x[i] * si;
     gh[i] = ghi;
     if (i < n_s) { gh2s += ghi * ghi; gms = fmax(gms, fabs(gi)); xs2s += xs * xs; }
     else { gh2f += ghi * ghi; gmf = fmax(gmf, fabs(gi)); xs2f += xs * xs; }
@@ -134,10 +134,26 @@ __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss,
   r = block_sum(xs2f, sm); if (threadIdx.x == 0) red[RED_XS2_F] = r;
   if (fused) {
     double c = 0.0;
-    for (int i = threadIdx.x; i < n_cost_part; i += blockDim.x) c += cost_part[i];
+    for (int i = threadIdx.x; i < n_cost_part; i += blockDim.x) c += __ldcg(&cost_part[i]);
     c = block_sum(c, sm);
     if (threadIdx.x == 0) { red[RED_COST] = c; begin_iteration(st, red); }
   }
+}
+__global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss, const double* Hff, const double* g, const double* x,
+                        double* sinv, double* d, double* gh, int first, double* red,
+                        int fused, const double* cost_part, int n_cost_part, SolverState* st, int fb) {
+  scale_body(n, n_s, diag_s, Hss, Hff, g, x, sinv, d, gh, first, red, fused, cost_part, n_cost_part, st, fb);
+}
+// tail of k_expand_shared (MCBA_FUSE=1, single GPU, no later kernel adds to H_ss): the last CTA to finish does what k_scale does
+__device__ __noinline__ void scale_epilogue(const ScaleEpilogue& e, int n_s, const double* Hss, const double* g) {
+  __shared__ int scale_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { const unsigned t = atomicAdd(e.counter, 1u); scale_is_last = (t == gridDim.x - 1); }
+  __syncthreads();
+  if (!scale_is_last) return;
+  if (threadIdx.x == 0) *e.counter = 0;
+  scale_body(e.n, n_s, nullptr, Hss, e.Hff, g, e.x, e.sinv, e.d, e.gh, e.first, e.red, 1, e.cost_part, e.n_cost_part, e.st, e.fb);
 }
 
 // quadratic forms u^T A v, A = D H D, for (u,u) [, (u,v), (v,v)].  Grid = F frame CTAs + shared CTAs.
@@ -1083,6 +1099,23 @@ __device__ inline void accept_compute(SolverState* st, const double* red) {
   st->status = status;
   if (status == -99) st->Delta = Dn;
   st->accepted = actual > 0.0;
+}
+
+// tail of the moment kernels (MCBA_FUSE=1, single GPU): the last CTA to finish sums the per-view costs and runs the acceptance test
+__device__ __noinline__ void view_accept_epilogue(SolverState* st, double* red, unsigned* counter, const double* view_cost, int V) {
+  __shared__ double acc_sm[32];
+  __shared__ int acc_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { const unsigned t = atomicAdd(counter, 1u); acc_is_last = (t == gridDim.x - 1); }
+  __syncthreads();
+  if (!acc_is_last) return;
+  if (threadIdx.x == 0) *counter = 0;
+  if (st->done) return;
+  double c = 0.0;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) c += __ldcg(&view_cost[v]);
+  c = block_sum(c, acc_sm);
+  if (threadIdx.x == 0) { red[RED_COSTNEW] = c; accept_compute(st, red); }
 }
 
 // single-GPU: the cost sum is done by the same CTA (moments != nullptr); multi-GPU: the sum, the exchange and the test are

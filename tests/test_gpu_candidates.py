@@ -2,8 +2,8 @@
 
 MCBA_CHOL=blocked -- k_chol_blocked, the single-CTA blocked reduced solve with warp-level column steps, instead of k_chol_small: the
 iteration table of a solve must agree with the default kernel's to round-off.
-MCBA_FUSE=1 -- two launches fewer per LM iteration (k_dots folded into the second k_quad, k_step + k_make_trial as one single-CTA
-launch): same iterations up to the summation order of two dot products.
+MCBA_FUSE=1 -- four launches fewer per LM iteration (k_dots folded into the second k_quad, k_step + k_make_trial as one single-CTA
+launch, k_accept / k_scale as tails of the moment kernel / k_expand_shared): same iterations up to the summation order of a few sums.
 MCBA_MOMENTS=f32 -- k_views_f32: Hessian moments in FP32, residual / cost / gradient in FP64.  Not an exact replacement by design:
 the iteration path may differ, the minimiser may not -- converged cost within 1e-10 relative, evaluations within +-2, and the
 parity hook mcba_linearize keeps returning the fp64 normal equations."""
