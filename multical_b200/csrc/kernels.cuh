@@ -736,6 +736,7 @@ struct SolverBuffers {
   double* Hff;       // [F][36]
   double* W;         // [F][n_s][6]   H[shared, frame f]
   double* cost_part; // per-CTA partial costs of k_expand_shared
+  int zero_shared;   // MCBA_FUSE=1: k_expand_frames also clears H_ss and the shared part of g (instead of two memsets in front of it)
 };
 
 __device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int local /*0..3+nd*/) {
@@ -974,6 +975,10 @@ k_expand_frames(DeviceProblem p, SolverBuffers s) {
   double* Wf = s.W + (size_t)f * n_s * FB;
   for (int i = tid; i < n_s * FB; i += EXP_THREADS) Wf[i] = 0.0;
   for (int i = lane; i < B * 6 * FB; i += 32) Wb[i] = 0.0;
+  if (s.zero_shared) {             // k_expand_shared, which accumulates into these, starts after this kernel has finished
+    for (size_t i = (size_t)blockIdx.x * EXP_THREADS + tid; i < (size_t)n_s * n_s; i += (size_t)gridDim.x * EXP_THREADS) s.Hss[i] = 0.0;
+    for (int i = blockIdx.x * EXP_THREADS + tid; i < n_s; i += gridDim.x * EXP_THREADS) s.g[i] = 0.0;
+  }
   __syncthreads();                                   // W_f zeroed before any warp adds its camera rows
 
   const int nin = 4 + p.nd;

@@ -319,10 +319,13 @@ int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial, bool accept_
 // k_expand_shared when that is the last kernel adding to H_ss; returns through *scaled whether it did
 int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
   DeviceProblem P = with_state(ctx, false);
-  SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p};
+  SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p, 0};
   cudaStream_t s = ctx->stream;
-  CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
-  CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
+  sb.zero_shared = (ctx->fuse && P.motion_on && P.F > 0) ? 1 : 0;         // cleared by k_expand_frames itself
+  if (!sb.zero_shared) {
+    CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
+    CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
+  }
   const bool roll = P.motion == MOTION_ROLLING;
   if (P.motion_on && P.F > 0) {
     if (roll) k_expand_frames<2><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
