@@ -89,7 +89,7 @@ def rewrite_asm(m):
 def translate(src):
   src = rewrite_launches(src)
   src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)simt::dyn_smem();", src)
-  src = re.sub(r"\b__shared__\b", "static", src)
+  src = re.sub(r"\b__shared__\b", "static thread_local", src)       # per block, blocks of one rank run one after the other; ranks are host threads
   src = ASM.sub(rewrite_asm, src)
   src = src.replace('#include "../../include/mcba.h"', f'#include "{os.path.join(ROOT, "include", "mcba.h")}"')
   return src

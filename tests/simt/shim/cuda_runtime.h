@@ -3,6 +3,11 @@
 // synchronous, the one reported device calls itself sm_100 so that mcba_create accepts it.  Peer / IPC calls fail.
 #pragma once
 #include <chrono>
+#include <condition_variable>
+#include <dlfcn.h>
+#include <map>
+#include <mutex>
+#include <string>
 #include "simt.h"
 
 typedef int cudaError_t;
@@ -66,6 +71,78 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
   return cudaSuccess;
 }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F*, int, int) { return cudaSuccess; }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+// "IPC": the ranks of a multi-rank interpreter test are host threads of one process, so a handle simply carries the pointer
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// In-process stand-in for the NCCL entry points solver.cu loads with dlopen/dlsym: ranks are host threads, a communicator is a
+// rendezvous keyed by the unique id, an all-reduce reduces in rank order behind two barriers.  Same ABI as the real signatures
+// (the 128-byte unique id travels by value).
+namespace simt_nccl {
+struct UniqueId { char internal[128]; };
+struct Group {
+  int world = 0, joined = 0, arrived = 0; unsigned gen = 0;
+  std::mutex m; std::condition_variable cv;
+  const void* send[16] = {nullptr};
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned g = gen;
+    if (++arrived == world) { arrived = 0; gen++; cv.notify_all(); } else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+struct Comm { Group* g; int rank; };
+inline std::mutex reg_m;
+inline std::map<std::string, Group*> registry;
+inline int GetUniqueId(UniqueId* id) {
+  static int counter = 0;
+  std::lock_guard<std::mutex> lk(reg_m);
+  memset(id, 0, sizeof(*id));
+  snprintf(id->internal, sizeof(id->internal), "simt-nccl-%d", ++counter);
+  return 0;
+}
+inline int CommInitRank(Comm** out, int world, UniqueId id, int rank) {
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) return 4;
+  Group* g;
+  { std::lock_guard<std::mutex> lk(reg_m); Group*& slot = registry[std::string(id.internal, 128)]; if (!slot) { slot = new Group(); slot->world = world; } g = slot; }
+  { std::unique_lock<std::mutex> lk(g->m); g->joined++; g->cv.notify_all(); g->cv.wait(lk, [&] { return g->joined >= world; }); }
+  *out = new Comm{g, rank};
+  return 0;
+}
+inline int CommDestroy(Comm* c) { delete c; return 0; }
+inline int AllReduce(const void* send, void* recv, size_t count, int dtype, int op, Comm* c, cudaStream_t) {
+  if (dtype != 8) return 5;                                   // ncclFloat64 only
+  Group* g = c->g;
+  g->send[c->rank] = send;
+  g->barrier();
+  std::vector<double> acc(count);
+  for (size_t i = 0; i < count; i++) {
+    double a = ((const double*)g->send[0])[i];
+    for (int r = 1; r < g->world; r++) { const double v = ((const double*)g->send[r])[i]; a = op == 0 ? a + v : (op == 2 ? fmax(a, v) : a); }
+    acc[i] = a;
+  }
+  g->barrier();                                               // every rank has read every send buffer (in-place reductions)
+  memcpy(recv, acc.data(), count * sizeof(double));
+  g->barrier();
+  return 0;
+}
+inline const char* GetErrorString(int) { return "simt-nccl error"; }
+inline int GroupStart() { return 0; }
+inline int GroupEnd() { return 0; }
+}  // namespace simt_nccl
+static inline void* simt_dlopen(const char* name, int flags) { return strstr(name, "nccl") ? (void*)&simt_nccl::registry : dlopen(name, flags); }
+static inline void* simt_dlsym(void* h, const char* sym) {
+  if (h != (void*)&simt_nccl::registry) return dlsym(h, sym);
+  const std::string s(sym);
+  if (s == "ncclGetUniqueId") return (void*)&simt_nccl::GetUniqueId;
+  if (s == "ncclCommInitRank") return (void*)&simt_nccl::CommInitRank;
+  if (s == "ncclCommDestroy") return (void*)&simt_nccl::CommDestroy;
+  if (s == "ncclAllReduce") return (void*)&simt_nccl::AllReduce;
+  if (s == "ncclGetErrorString") return (void*)&simt_nccl::GetErrorString;
+  if (s == "ncclGroupStart") return (void*)&simt_nccl::GroupStart;
+  if (s == "ncclGroupEnd") return (void*)&simt_nccl::GroupEnd;
+  return nullptr;
+}
+#define dlopen simt_dlopen
+#define dlsym simt_dlsym

@@ -64,15 +64,16 @@ struct Block {
   size_t dyn_bytes = 0;
 };
 
-inline Fiber* cur = nullptr;
-inline Block blk;
-inline ucontext_t sched_ctx;
-inline std::vector<Fiber> fibers;
-inline std::vector<Warp> warps;
-inline const void* cur_body = nullptr;
-inline void (*cur_invoke)(const void*) = nullptr;
-inline const char* cur_name = "";
-inline long long total_launches = 0;
+// thread_local: several "ranks" (one host thread each, tests/test_simt_multirank.py) may run kernels at the same time
+inline thread_local Fiber* cur = nullptr;
+inline thread_local Block blk;
+inline thread_local ucontext_t sched_ctx;
+inline thread_local std::vector<Fiber> fibers;
+inline thread_local std::vector<Warp> warps;
+inline thread_local const void* cur_body = nullptr;
+inline thread_local void (*cur_invoke)(const void*) = nullptr;
+inline thread_local const char* cur_name = "";
+inline thread_local long long total_launches = 0;
 
 [[noreturn]] inline void die(const char* what) {
   fprintf(stderr, "[simt] %s in kernel %s, block (%u,%u,%u)\n", what, cur_name, blk.idx.x, blk.idx.y, blk.idx.z);
@@ -123,7 +124,7 @@ inline void trampoline() {
 }
 
 inline char* stack_of(int i) {
-  static std::vector<char*> pool;
+  static thread_local std::vector<char*> pool;
   if ((int)pool.size() <= i) pool.resize(i + 1, nullptr);
   if (!pool[i]) {
     void* p = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
@@ -153,13 +154,13 @@ inline void run_block() {
   // SIMT_ORDER=reverse | shuffle:<seed>: the order in which runnable threads are resumed.  A kernel that is correct on hardware
   // gives the same result for every order; a missing __syncwarp / __syncthreads between a write and a read by another thread is
   // hidden by one order and exposed by another.
-  static int order_mode = -1; static unsigned order_seed = 1;
+  static thread_local int order_mode = -1; static thread_local unsigned order_seed = 1;
   if (order_mode < 0) {
     const char* e = getenv("SIMT_ORDER");
     order_mode = !e ? 0 : !strcmp(e, "reverse") ? 1 : !strncmp(e, "shuffle", 7) ? 2 : 0;
     if (order_mode == 2 && e[7] == ':') order_seed = (unsigned)atoi(e + 8) * 2654435761u + 1u;
   }
-  static std::vector<int> order;
+  static thread_local std::vector<int> order;
   order.resize(n);
   for (int i = 0; i < n; i++) order[i] = order_mode == 1 ? n - 1 - i : i;
   int remaining = n;
@@ -223,6 +224,10 @@ inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, const F
   if ((size_t)grid.x * grid.y * grid.z == 0) die("empty grid");
   if (smem > 227 * 1024) die("more than 227 KB of dynamic shared memory");
   total_launches++;
+  // Blocks run one after the other, so a block that spins on a flag another block of the same launch publishes would never return.
+  // k_peer_allreduce (csrc/peer_allreduce.cuh) is such a kernel and is written grid-size agnostic (grid-stride loops, "last block"
+  // by counter): the interpreter runs it with ONE block; its spin on the flags of the OTHER ranks is served by their host threads.
+  if (strstr(name, "k_peer_allreduce")) grid = dim3(1);
   blk.nthreads = (int)n; blk.bdim = block; blk.gdim = grid;
   std::vector<unsigned char> dyn(smem + 64);
   blk.dyn = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
