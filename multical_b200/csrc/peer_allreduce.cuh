@@ -16,7 +16,7 @@
 namespace mcba {
 
 constexpr int PEER_MAX_WORLD = 16;
-constexpr int PEER_MAX_SEG = 4;
+constexpr int PEER_MAX_SEG = 6;
 constexpr int PEER_FLAG_STRIDE = 8;      // doubles (64 B) between flags
 
 struct PeerSeg { double* buf; int count; int op; };     // op 0 = sum, 1 = max

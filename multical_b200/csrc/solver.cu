@@ -1384,6 +1384,16 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     } else if (single) {
       k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
                                  1, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1)); CKL();
+    } else if (ctx->fuse) {
+      // one exchange instead of two: the frame parts of the scaling sums only need local data and travel with g_s / diag / cost
+      k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, ncp, 1, 1, ctx->red.p + RED_COST); CKL();
+      if (n_s > 0) { k_diag<<<(n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, n_s, ctx->diag_s.p); CKL(); }
+      k_scale_part<<<1, 1024, 0, s>>>(1, n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
+                                      ctx->state.p, std::max(P.fb, 1)); CKL();
+      EXCHANGE(ex_.add(ctx->g.p, n_s, 0); ex_.add(ctx->diag_s.p, n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0);
+               ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1));
+      k_scale_part<<<1, 1024, 0, s>>>(2, n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
+                                      ctx->state.p, std::max(P.fb, 1)); CKL();
     } else {
       r = finish_linearization(ctx); if (r) return r;
       k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,

@@ -144,6 +144,36 @@ __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss,
                         int fused, const double* cost_part, int n_cost_part, SolverState* st, int fb) {
   scale_body(n, n_s, diag_s, Hss, Hff, g, x, sinv, d, gh, first, red, fused, cost_part, n_cost_part, st, fb);
 }
+// Multi-GPU with MCBA_FUSE=1: the scaling in two parts around ONE exchange instead of two.  part 1 = the frame entries, which only
+// need local data (H_ff, g_f, x_f): their sinv / d / gh and RED_GH2_F, RED_XS2_F, RED_GMAX_F, which then travel with g_s, diag(H_ss)
+// and the cost; part 2 = the shared entries from the reduced diagonal / gradient, then begin_iteration -- every sum it reads is
+// reduced by then, so the second exchange of the iteration disappears.
+__global__ void k_scale_part(int part, int n, int n_s, const double* diag_s, const double* Hff, const double* g, const double* x,
+                             double* sinv, double* d, double* gh, int first, double* red, SolverState* st, int fb) {
+  __shared__ double sm[32];
+  const int lo = part == 1 ? n_s : 0, hi = part == 1 ? n : n_s;
+  double gh2 = 0, gm = 0, xs2 = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    double hd;
+    if (i < n_s) hd = diag_s[i];
+    else { const int f = (i - n_s) / fb, j = (i - n_s) % fb; hd = Hff[(size_t)f * fb * fb + j * (fb + 1)]; }
+    const double nrm = sqrt(fmax(hd, 0.0));
+    double si;
+    if (first) si = (nrm == 0.0) ? 1.0 : nrm; else si = fmax(nrm, sinv[i]);
+    sinv[i] = si;
+    const double di = 1.0 / si;
+    d[i] = di;
+    const double gi = g[i], ghi = di * gi, xs = x[i] * si;
+    gh[i] = ghi;
+    gh2 += ghi * ghi; gm = fmax(gm, fabs(gi)); xs2 += xs * xs;
+  }
+  double r;
+  r = block_sum(gh2, sm); if (threadIdx.x == 0) red[part == 1 ? RED_GH2_F : RED_GH2_S] = r;
+  r = block_max(gm, sm);  if (threadIdx.x == 0) red[part == 1 ? RED_GMAX_F : RED_GMAX_S] = r;
+  r = block_sum(xs2, sm); if (threadIdx.x == 0) red[part == 1 ? RED_XS2_F : RED_XS2_S] = r;
+  if (part == 2 && threadIdx.x == 0) begin_iteration(st, red);
+}
+
 // tail of k_expand_shared (MCBA_FUSE=1, single GPU, no later kernel adds to H_ss): the last CTA to finish does what k_scale does
 __device__ __noinline__ void scale_epilogue(const ScaleEpilogue& e, int n_s, const double* Hss, const double* g) {
   __shared__ int scale_is_last;

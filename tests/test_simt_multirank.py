@@ -97,3 +97,25 @@ def test_two_ranks_under_the_motion_models(name, monkeypatch):
   for out, res, _ in results:
     assert res.nfev == single.last_solve.nfev
     assert abs(res.cost - single.last_solve.cost) <= 1e-8 * single.last_solve.cost
+
+
+@pytest.mark.parametrize("peer", [True, False])
+def test_two_ranks_with_the_merged_first_exchange(peer, monkeypatch):
+  """MCBA_FUSE=1 on several ranks: the frame parts of the scaling sums travel with g_s / diag(H_ss) / cost (k_scale_part), one
+  exchange per LM iteration fewer; the solve must still be the single-rank solve."""
+  scene, z, calib, prob = gp.make("cube3_3x6")
+  single = calib.bundle_adjust().last_solve                 # default kernels, one rank
+  for eng in calibration._engines.values(): eng.close()
+  calibration._engines.clear()
+  monkeypatch.setenv("MCBA_FUSE", "1")
+  results = sharded_solve(calib, 2, peer, monkeypatch)
+  for out, res, _ in results:
+    assert res.nfev == single.nfev and res.status == single.status
+    assert abs(res.cost - single.cost) <= 1e-9 * single.cost
+  assert results[0][1].cost == results[1][1].cost
+  assert results[0][1].kernel_launches < sharded_solve(calib, 2, peer, monkeypatch_env_off(monkeypatch))[0][1].kernel_launches
+
+
+def monkeypatch_env_off(monkeypatch):
+  monkeypatch.delenv("MCBA_FUSE")
+  return monkeypatch
