@@ -486,8 +486,9 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     CK(cudaMemsetAsync(ctx->frame_rt.p, 0, sizeof(double) * std::max(F, 1) * fbs, ctx->stream));
     CK(cudaMemsetAsync(ctx->intr.p, 0, sizeof(double) * C * P.kint, ctx->stream));
     // motion-model state: identity arm / hand-eye poses, unit image heights until mcba_set_rolling / mcba_set_hand_eye
-    CK(cudaMemsetAsync(ctx->he_rt.p, 0, sizeof(double) * 12, ctx->stream));
-    {
+    // (never read under static frames: no copies, no extra synchronisation on the BASELINE path)
+    if (P.motion != MOTION_STATIC) {
+      CK(cudaMemsetAsync(ctx->he_rt.p, 0, sizeof(double) * 12, ctx->stream));
       std::vector<double> ones((size_t)C, 1.0);
       CK(cudaMemcpyAsync(ctx->img_h.p, ones.data(), sizeof(double) * C, cudaMemcpyHostToDevice, ctx->stream));
       PoseT id{}; id.R[0] = id.R[4] = id.R[8] = 1.0;
