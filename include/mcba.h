@@ -188,6 +188,9 @@ int  mcba_table_select(mcba_ctx* ctx, int which, int64_t* n_corners);
 int  mcba_table_errors(mcba_ctx* ctx, mcba_table_stats* stats);
 /* out[i] = ranks[i]-th smallest error (0-based) of the chosen set -- the order statistics np.quantile interpolates */
 int  mcba_table_error_ranks(mcba_ctx* ctx, int which, const int64_t* ranks, int32_t n, double* out);
+/* counts[i] = number of errors of the chosen set below thresholds[i]: the other half of a quantile over SEVERAL ranks' tables
+ * (frames sharded across GPUs: every rank sorts its own errors; ranks and counts are merged on the host) */
+int  mcba_table_count_below(mcba_ctx* ctx, int which, const double* thresholds, int32_t n, int64_t* counts);
 /* inliers = valid & (error < threshold) (calibration.py:243-244) with the errors of the last mcba_table_errors;
  * MCBA_ERR_STATE if parameters or selection changed since.  Follow with mcba_table_select(MCBA_TABLE_INLIERS). */
 int  mcba_table_reject(mcba_ctx* ctx, double threshold, int64_t* n_valid, int64_t* n_keep);

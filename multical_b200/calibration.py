@@ -379,10 +379,14 @@ class Calibration(Parameters):
     calib.report("Adjust_outliers end:")
     return calib
 
-  def _adjust_outliers_resident(self, num_adjustments, select_scale, select_outliers, **kwargs):
+  def _adjust_outliers_resident(self, num_adjustments, select_scale, select_outliers, comm=None, **kwargs):
     """The same loop with the point table resident on the GPU (include/mcba.h "resident point table"): the dense table is
     uploaded once; each round the host sees the five-number summaries for the log, the order statistics around the selected
-    quantiles and the inlier count.  The error vector, the masks and the repacking stay on the device."""
+    quantiles and the inlier count.  The error vector, the masks and the repacking stay on the device.
+    comm (multical_b200/distributed.py adjust_outliers): `self` is this rank's frame shard; counts and sums of squares are summed
+    over the ranks, quantiles are taken over the union of all ranks' errors (outliers.merged_order_statistics), the solves are the
+    collective solves of the engine's communicator -- thresholds, masks and log lines are those of the unsharded loop."""
+    from .outliers import merged_order_statistics, quantile_from_sorted
     eng = get_engine()
     eng.table_upload(self.engine_model, self._optimize_bits(), self.valid, np.asarray(self.point_table.points),
                      self.board_points.points)
@@ -391,13 +395,26 @@ class Calibration(Parameters):
     if masked: eng.table_set_inliers(np.asarray(self.inlier_mask))
     five = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
 
+    local_n = {}
+
+    def quantile(which, n, q):
+      """np.quantile over the chosen set: this rank's sorted errors, or the union over the ranks (n = global count)."""
+      if comm is None: return eng.table_quantile(which, n, q)
+      return quantile_from_sorted(lambda r: merged_order_statistics(comm, lambda lr: eng.table_error_ranks(which, lr),
+                                                                    lambda v: eng.table_count_below(which, v), local_n[which], r), n, q)
+
     def summary(which, n, sumsq):
       if n == 0:                                   # the reference's guard: an empty vector counts as a single zero
         return struct(mse=0.0, rms=0.0, quantiles=np.zeros(5), n=1)
-      return struct(mse=sumsq / n, rms=float(np.sqrt(sumsq / n)), quantiles=eng.table_quantile(which, n, five), n=n)
+      return struct(mse=sumsq / n, rms=float(np.sqrt(sumsq / n)), quantiles=quantile(which, n, five), n=n)
 
     def report(stage):
       st = eng.table_errors()
+      local_n["valid"], local_n["inliers"] = int(st.n_valid), int(st.n_inliers)
+      if comm is not None:
+        counts = comm.all_reduce_sum(np.array([st.n_valid, st.n_inliers], np.int64))
+        sums = np.sum(comm.all_gather(np.array([st.sumsq_valid, st.sumsq_inliers])), axis=0)       # rank order: the same value everywhere
+        st = type(st)(n_valid=int(counts[0]), n_inliers=int(counts[1]), sumsq_valid=float(sums[0]), sumsq_inliers=float(sums[1]))
       _report_line(stage, summary("valid", st.n_valid, st.sumsq_valid),
                    summary("inliers", st.n_inliers, st.sumsq_inliers) if masked else None)
       return st
@@ -407,11 +424,12 @@ class Calibration(Parameters):
       st = report(f"Adjust_outliers {round_index}:")
       f_scale = 1.0
       if select_scale is not None:
-        f_scale = eng.table_quantile("valid", st.n_valid, select_scale.quantile) * select_scale.factor or 1.0
+        f_scale = quantile("valid", st.n_valid, select_scale.quantile) * select_scale.factor or 1.0
         info(f"Auto scaling for outliers influence at {f_scale:.2f} pixels")
       if select_outliers is not None:
-        threshold = eng.table_quantile("valid", st.n_valid, select_outliers.quantile) * select_outliers.factor
+        threshold = quantile("valid", st.n_valid, select_outliers.quantile) * select_outliers.factor
         n_valid, n_keep = eng.table_reject(threshold)
+        if comm is not None: n_valid, n_keep = (int(v) for v in comm.all_reduce_sum(np.array([n_valid, n_keep], np.int64)))
         masked = True
         info(f"Rejecting {n_valid - n_keep} outliers with error > {threshold:.2f} pixels, "
              f"keeping {n_keep} / {n_valid} inliers, ({100.0 * n_keep / n_valid:.2f}%)")

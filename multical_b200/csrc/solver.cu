@@ -1031,6 +1031,22 @@ int mcba_table_error_ranks(mcba_ctx* ctx, int which, const int64_t* ranks, int32
   return MCBA_OK;
 }
 
+int mcba_table_count_below(mcba_ctx* ctx, int which, const double* thresholds, int32_t n, int64_t* counts) {
+  if (!ctx || (n > 0 && (!thresholds || !counts))) return MCBA_ERR_ARG;
+  REQUIRE(ctx->table && ctx->errors_current, MCBA_ERR_STATE, "mcba_table_errors has not run since the parameters or the selection changed");
+  REQUIRE(which == MCBA_TABLE_VALID || which == MCBA_TABLE_INLIERS, MCBA_ERR_ARG, "unknown table selection");
+  if (n <= 0) return MCBA_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int64_t count = which == MCBA_TABLE_VALID ? ctx->n_valid : ctx->n_inliers;
+  CK(ctx->table_out.alloc((size_t)n)); CK(ctx->table_ranks.alloc((size_t)n));
+  CK(cudaMemcpyAsync(ctx->table_out.p, thresholds, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_count_below<<<(n + 127) / 128, 128, 0, ctx->stream>>>(which == MCBA_TABLE_VALID ? ctx->err_sorted.p : ctx->err_inl_sorted.p, count,
+                                                        ctx->table_out.p, n, ctx->table_ranks.p); CKL();
+  CK(cudaMemcpyAsync(counts, ctx->table_ranks.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MCBA_OK;
+}
+
 int mcba_table_reject(mcba_ctx* ctx, double threshold, int64_t* n_valid, int64_t* n_keep) {
   if (!ctx) return MCBA_ERR_ARG;
   REQUIRE(ctx->table && ctx->errors_current && ctx->table_selected == MCBA_TABLE_VALID, MCBA_ERR_STATE,

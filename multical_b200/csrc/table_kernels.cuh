@@ -101,4 +101,15 @@ __global__ void k_gather_ranks(const double* sorted, const int64_t* ranks, int n
   if (i < n) out[i] = sorted[ranks[i]];
 }
 
+// out[i] = number of entries of sorted[0, count) that are < thresholds[i] (lower bound): with k_gather_ranks this is all a
+// multi-rank quantile needs from each rank's sorted error vector (multical_b200/distributed.py merged_order_statistics)
+__global__ void k_count_below(const double* sorted, int64_t count, const double* thresholds, int n, int64_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = thresholds[i];
+  int64_t lo = 0, hi = count;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < t) lo = mid + 1; else hi = mid; }
+  out[i] = lo;
+}
+
 }  // namespace mcba

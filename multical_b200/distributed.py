@@ -64,25 +64,29 @@ def shard_calibration(calib, rank, world):
   return calib.copy(point_table=local_pt, motion=_slice_motion(calib.motion, a, b), inlier_mask=mask), (a, b)
 
 
-def merge_motion(full_motion, local_motion, F, rank, world, group=None):
+def merge_motion(full_motion, local_motion, F, rank, world, group=None, comm=None):
   """The full motion model after a sharded solve: per-frame state all-gathered in frame order, shared state from the local result
   (every rank solves the shared system redundantly on bit-identical data)."""
   from .motion import MOTION_HAND_EYE, MOTION_ROLLING, motion_kind
   kind = motion_kind(full_motion)
   if kind == MOTION_ROLLING:
-    return full_motion.copy(pose_start=gather_frames(local_motion.pose_start, F, rank, world, group),
-                            pose_end=gather_frames(local_motion.pose_end, F, rank, world, group))
+    return full_motion.copy(pose_start=gather_frames(local_motion.pose_start, F, rank, world, group, comm),
+                            pose_end=gather_frames(local_motion.pose_end, F, rank, world, group, comm))
   if kind == MOTION_HAND_EYE:
     return full_motion.copy(world_wrt_base=local_motion.world_wrt_base, gripper_wrt_camera=local_motion.gripper_wrt_camera)
   mt = full_motion.pose_table
-  return full_motion.copy(pose_table=type(mt).create(poses=gather_frames(local_motion.poses, F, rank, world, group), valid=np.asarray(mt.valid)))
+  return full_motion.copy(pose_table=type(mt).create(poses=gather_frames(local_motion.poses, F, rank, world, group, comm), valid=np.asarray(mt.valid)))
 
 
-def gather_frames(local_frame_poses, F, rank, world, group=None):
-  """All-gather the per-rank frame poses back into the full [F,4,4] table (host side, after the solve)."""
-  import torch.distributed as dist
-  parts = [None] * world
-  dist.all_gather_object(parts, np.asarray(local_frame_poses), group=group)
+def gather_frames(local_frame_poses, F, rank, world, group=None, comm=None):
+  """All-gather the per-rank frame poses back into the full [F,4,4] table (host side, after the solve); through `comm.all_gather`
+  when a communicator object is given (TorchComm below, or the thread communicator of the CPU tests), else torch.distributed."""
+  if comm is not None:
+    parts = comm.all_gather(np.asarray(local_frame_poses))
+  else:
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, np.asarray(local_frame_poses), group=group)
   out = np.concatenate(parts, axis=0)
   assert out.shape[0] == F
   return out
@@ -101,5 +105,45 @@ def bundle_adjust(calib, group=None, **kwargs):
   out_local = local.bundle_adjust(**kwargs)
   motion = merge_motion(calib.motion, out_local.motion, calib.size.rig_poses, rank, world, group)
   out = calib.copy(cameras=out_local.cameras, camera_poses=out_local.camera_poses, board_poses=out_local.board_poses, motion=motion)
+  out.__dict__["last_solve"] = out_local.last_solve
+  return out
+
+
+class TorchComm:
+  """The two host-side collectives of the sharded outlier loop over torch.distributed (small Python objects: a few hundred order
+  statistics per round; the bundle adjustments themselves exchange over NCCL / NVLink inside libmcba)."""
+  def __init__(self, group=None):
+    import torch.distributed as dist
+    self.dist, self.group = dist, group
+    self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+  def all_gather(self, obj):
+    out = [None] * self.world
+    self.dist.all_gather_object(out, obj, group=self.group)
+    return out
+
+  def all_reduce_sum(self, arr):
+    return np.sum(self.all_gather(np.asarray(arr)), axis=0)
+
+
+def adjust_outliers(calib, comm=None, group=None, num_adjustments=3, select_scale=None, select_outliers=None, **kwargs):
+  """Multi-GPU `Calibration.adjust_outliers` (calibration.py:254-268) with every rank's frame shard of the point table resident on
+  its GPU: call on every rank with the same full Calibration; returns the same full, updated Calibration (poses, intrinsics,
+  inlier mask) on every rank.  Selectors must be quantile rules (`select_threshold`) or None."""
+  from .calibration import get_engine
+  comm = comm or TorchComm(group)
+  rank, world = comm.rank, comm.world
+  local, (a, b) = shard_calibration(calib, rank, world)
+  eng = get_engine()
+  if getattr(eng, "world", 1) != world:
+    init_comm(eng, rank, world, group)
+  out_local = local._adjust_outliers_resident(num_adjustments, select_scale, select_outliers, comm=comm, **kwargs)
+  F = calib.size.rig_poses
+  motion = merge_motion(calib.motion, out_local.motion, F, rank, world, group, comm)
+  mask = None
+  if out_local.inlier_mask is not None:
+    mask = np.concatenate(comm.all_gather(np.asarray(out_local.inlier_mask)), axis=1)          # frames are axis 1 of [C,F,B,P]
+  out = calib.copy(cameras=out_local.cameras, camera_poses=out_local.camera_poses, board_poses=out_local.board_poses, motion=motion,
+                   inlier_mask=mask)
   out.__dict__["last_solve"] = out_local.last_solve
   return out

@@ -214,6 +214,14 @@ class Engine:
                                              ranks.ctypes.data_as(C.POINTER(C.c_int64)), ranks.size, nat.dptr(out)))
     return out[:ranks.size]
 
+  def table_count_below(self, which, thresholds):
+    """Number of errors of the chosen set below each threshold (binary search in the sorted errors on the device)."""
+    t = nat.f64(thresholds).reshape(-1)
+    out = np.zeros(max(t.size, 1), np.int64)
+    self._ck(self.lib.mcba_table_count_below(self.h, {"valid": nat.TABLE_VALID, "inliers": nat.TABLE_INLIERS}[which], nat.dptr(t), t.size,
+                                             out.ctypes.data_as(C.POINTER(C.c_int64))))
+    return out[:t.size]
+
   def table_quantile(self, which, n, q):
     """np.quantile(errors of the chosen set, q), computed from order statistics fetched from the device."""
     from .outliers import quantile_from_sorted

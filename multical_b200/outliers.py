@@ -62,3 +62,47 @@ def quantile_from_sorted(fetch, n, q):
   k = ranks.size // 2
   out = lerp(vals[:k], vals[k:], np.atleast_1d(gamma))
   return out.reshape(np.shape(q)) if np.ndim(q) else float(out[0])
+
+
+def merged_order_statistics(comm, fetch_local, count_below_local, n_local, ranks, splitters=256):
+  """Order statistics of the UNION of every rank's error vector, exactly, without moving the vectors: `ranks` (0-based, global) ->
+  values, identical on all ranks.  Every rank holds its own errors sorted on its GPU and answers two questions about them:
+  `fetch_local(local_ranks) -> values` (mcba_table_error_ranks) and `count_below_local(values) -> counts` (mcba_table_count_below).
+    1. all-gather `splitters` evenly spaced local order statistics per rank -> a sorted candidate set V that contains the global max;
+    2. all-reduce the local counts below every candidate -> C(v) = global number of errors < v; the k-th error lies in the gap
+       [v_lo, v_hi) around C(v_lo) <= k < C(v_hi), which holds only ~N / splitters errors;
+    3. all-gather the local errors of those gaps (consecutive local ranks c_r(v_lo) .. c_r(v_hi)), merge, index.
+  `comm`: all_gather(obj) -> list over ranks, all_reduce_sum(int64 array) -> array."""
+  ranks = np.atleast_1d(np.asarray(ranks, dtype=np.int64))
+  # 1. candidates
+  if n_local > 0:
+    pick = np.unique(np.round(np.linspace(0, n_local - 1, min(n_local, splitters))).astype(np.int64))
+    mine = np.asarray(fetch_local(pick), dtype=np.float64)
+  else:
+    mine = np.zeros(0)
+  V = np.unique(np.concatenate(comm.all_gather(mine)))
+  assert V.size > 0, "order statistic of an empty error vector"
+  # 2. global counts below every candidate (and the local ones: they delimit the local share of every gap)
+  c_local = np.asarray(count_below_local(V), dtype=np.int64) if n_local > 0 else np.zeros(V.size, np.int64)
+  C = comm.all_reduce_sum(c_local)
+  total = int(comm.all_reduce_sum(np.array([n_local], np.int64))[0])
+  assert ranks.min() >= 0 and ranks.max() < total, "error rank out of range"
+  lo_idx = np.searchsorted(C, ranks, side="right") - 1            # last candidate with C(v) <= k   (C[0] = 0: V[0] is the global min)
+  # 3. the local errors of each needed gap [V[lo], V[lo+1])  (the last gap is everything >= the global maximum, i.e. copies of it)
+  gaps = np.unique(lo_idx)
+  local_lo = c_local[gaps]
+  local_hi = np.where(gaps + 1 < V.size, c_local[np.minimum(gaps + 1, V.size - 1)], n_local)
+  need = np.concatenate([np.arange(a, b) for a, b in zip(local_lo, local_hi)]) if gaps.size else np.zeros(0, np.int64)
+  vals = np.asarray(fetch_local(need), dtype=np.float64) if need.size else np.zeros(0)
+  sizes = (local_hi - local_lo).astype(np.int64)
+  parts = comm.all_gather((sizes, vals))
+  out = np.zeros(ranks.size)
+  for gi, g in enumerate(gaps):
+    chunks = []
+    for sz, v in parts:
+      off = int(sz[:gi].sum())
+      chunks.append(v[off:off + int(sz[gi])])
+    merged = np.sort(np.concatenate(chunks))
+    sel = lo_idx == g
+    out[sel] = merged[ranks[sel] - C[g]]
+  return out

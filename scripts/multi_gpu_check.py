@@ -36,6 +36,18 @@ for name, kw in [("cfg1", {}), ("cfg1", dict(model="fisheye", C=3, F=11)), ("cfg
       r = calib  # sanity: cost decreased and RMS plausible
       rms = np.sqrt(2 * res.cost / int(calib.inliers.sum()))
       assert 0.3 < rms < 0.5, rms
+# the outlier loop with the point table sharded over the GPUs: same masks and cost as the single-GPU resident loop
+from multical_b200.calibration import select_threshold
+scene = synthetic.make_workload("cfg1", outlier_fraction=0.02)
+calib = from_scene(scene).enable(cameras=True)
+kw = dict(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4), select_scale=select_threshold(quantile=0.5, factor=3), loss="soft_l1")
+get_engine().comm_init(bytes(128), 0, 1)
+single = calib.adjust_outliers(**kw)
+out = mdist.adjust_outliers(calib, **kw)
+same = np.array_equal(out.inlier_mask, single.inlier_mask)
+rel = abs(out.last_solve.cost - single.last_solve.cost) / single.last_solve.cost
+if rank == 0: print(f"sharded adjust_outliers: masks equal {same}, kept {int(out.inlier_mask.sum())} of {int(calib.valid.sum())}, cost rel {rel:.2e}", flush=True)
+assert same and rel < 1e-8, (same, rel)
 dist.barrier()
 if rank == 0: print("MULTI_GPU_OK")
 dist.destroy_process_group()

@@ -119,3 +119,87 @@ def test_two_ranks_with_the_merged_first_exchange(peer, monkeypatch):
 def monkeypatch_env_off(monkeypatch):
   monkeypatch.delenv("MCBA_FUSE")
   return monkeypatch
+
+
+# ---- the outlier loop with the point table sharded over the ranks (multical_b200/distributed.py adjust_outliers) ------------------
+class ThreadComm:
+  """all_gather / all_reduce_sum between the rank threads of one process (what TorchComm does over torch.distributed)."""
+  def __init__(self, world):
+    self.world, self.slots, self.barrier = world, [None] * world, threading.Barrier(world)
+    self.tls = threading.local()
+
+  rank = property(lambda self: self.tls.rank)
+
+  def all_gather(self, obj):
+    self.slots[self.tls.rank] = obj
+    self.barrier.wait()
+    out = list(self.slots)
+    self.barrier.wait()
+    return out
+
+  def all_reduce_sum(self, arr):
+    return np.sum(self.all_gather(np.asarray(arr)), axis=0)
+
+
+def test_merged_order_statistics_are_numpy_on_the_union():
+  """Host logic of the distributed quantile (outliers.merged_order_statistics) with numpy arrays standing in for the device-side sorted
+  errors: exact order statistics of the union for uneven shards, ties, an empty shard and ranks at both ends."""
+  from multical_b200.outliers import merged_order_statistics, quantile_from_sorted
+  rng = np.random.default_rng(0)
+  for world, sizes in [(2, [1000, 37]), (3, [500, 0, 1200]), (4, [64, 64, 64, 64])]:
+    shards = [np.sort(np.round(rng.gamma(2.0, 0.3, n), 2)) for n in sizes]              # rounding makes ties
+    union = np.sort(np.concatenate(shards)); N = union.size
+    ranks = np.array([0, 1, N // 3, N // 2, N - 2, N - 1])
+    comm = ThreadComm(world); results = [None] * world
+    def main(r):
+      comm.tls.rank = r
+      got = merged_order_statistics(comm, lambda lr: shards[r][lr], lambda v: np.searchsorted(shards[r], v, side="left"), sizes[r], ranks, splitters=16)
+      q = quantile_from_sorted(lambda rk: merged_order_statistics(comm, lambda lr: shards[r][lr], lambda v: np.searchsorted(shards[r], v, side="left"),
+                                                                  sizes[r], rk, splitters=16), N, np.array([0.0, 0.25, 0.5, 0.75, 1.0]))
+      results[r] = (got, q)
+    threads = [threading.Thread(target=main, args=(r,), daemon=True) for r in range(world)]
+    for t in threads: t.start()
+    for t in threads: t.join(timeout=60)
+    for got, q in results:
+      assert np.array_equal(got, union[ranks])
+      assert np.array_equal(q, np.quantile(union, [0.0, 0.25, 0.5, 0.75, 1.0]))
+
+
+def test_sharded_outlier_loop_equals_the_single_rank_loop(monkeypatch):
+  from multical_b200 import synthetic
+  from multical_b200.calibration import from_scene, select_threshold
+  scene = synthetic.make_scene(C=3, F=8, vis=0.5, seed=61, outlier_fraction=0.02)
+  calib = from_scene(scene).enable(cameras=True)
+  kw = dict(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4), select_scale=select_threshold(quantile=0.5, factor=3), loss="soft_l1")
+  single = calib.adjust_outliers(**kw)
+  for eng in calibration._engines.values(): eng.close()
+  calibration._engines.clear()
+
+  world = 2
+  comm = ThreadComm(world)
+  tls = threading.local()
+  engines = [Engine(0) for _ in range(world)]
+  uid = engines[0].comm_unique_id()
+  handles, results, errors = [None] * world, [None] * world, []
+  gate = threading.Barrier(world)
+  def rank_main(rank):
+    try:
+      comm.tls.rank = rank
+      tls.engine = eng = engines[rank]
+      eng.comm_init(uid, rank, world)
+      handles[rank] = eng.peer_export(1 << 14); gate.wait(); eng.peer_import(handles)
+      results[rank] = mdist.adjust_outliers(calib, comm=comm, **kw)
+    except BaseException as e:
+      errors.append(e); gate.abort(); comm.barrier.abort(); raise
+  threads = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+  with monkeypatch.context() as m:
+    m.setattr(calibration, "get_engine", lambda device=None: tls.engine)
+    for t in threads: t.start()
+    for t in threads: t.join(timeout=600)
+  assert not errors, errors
+  for eng in engines: eng.close()
+  for out in results:
+    assert np.array_equal(out.inlier_mask, single.inlier_mask) and out.inlier_mask.sum() < calib.valid.sum()
+    assert abs(out.last_solve.cost - single.last_solve.cost) <= 1e-8 * single.last_solve.cost
+    assert np.abs(np.asarray(out.motion.poses) - np.asarray(single.motion.poses)).max() < 1e-6
+    assert np.abs(np.asarray(out.camera_poses.poses) - np.asarray(single.camera_poses.poses)).max() < 1e-6
