@@ -15,28 +15,6 @@
 
 namespace mcba {
 
-constexpr int PEER_MAX_WORLD = 16;
-constexpr int PEER_MAX_SEG = 6;
-constexpr int PEER_FLAG_STRIDE = 8;      // doubles (64 B) between flags
-
-struct PeerSeg { double* buf; int count; int op; };     // op 0 = sum, 1 = max
-struct PeerArgs {
-  PeerSeg seg[PEER_MAX_SEG];
-  int nseg, rank, world, cap;
-  unsigned seq;
-  double* base[PEER_MAX_WORLD];          // peer-mapped base pointer of every rank's buffer (base[rank] = own)
-  unsigned* counter;
-  int epilogue;                          // EPI_* scalar step run by thread 0 after the reduction (single-CTA exchanges only)
-  SolverState* st;
-  double* red;
-};
-
-__host__ __device__ inline size_t peer_flag_off(int world, int parity, int src) { return (size_t)(parity * world + src) * PEER_FLAG_STRIDE; }
-__host__ __device__ inline size_t peer_data_off(int world, int cap, int parity, int src) {
-  return (size_t)2 * world * PEER_FLAG_STRIDE + ((size_t)parity * world + src) * cap;
-}
-__host__ __device__ inline size_t peer_buffer_doubles(int world, int cap) { return (size_t)2 * world * PEER_FLAG_STRIDE + (size_t)2 * world * cap; }
-
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -44,6 +22,47 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// The same exchange executed by ONE CTA as the tail of the kernel that produced the values (MCBA_FUSE=1 on several GPUs): the last
+// CTA of k_quad, the single CTA of k_cost_from_moments / k_scale_exchange.  Reduction -> all-reduce over NVLink -> the scalar
+// trust-region step that consumes it, in one launch.  All threads of the CTA must call it; the values must be visible to the CTA
+// (a __syncthreads after they were written).
+__device__ __noinline__ void peer_allreduce_block(const PeerArgs& a) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int parity = a.seq & 1u;
+  int total = 0;
+  for (int s = 0; s < a.nseg; s++) total += a.seg[s].count;
+  for (int idx = tid; idx < total; idx += nt) {
+    int s = 0, off = idx;
+    while (off >= a.seg[s].count) { off -= a.seg[s].count; s++; }
+    const double v = a.seg[s].buf[off];
+    const size_t o = peer_data_off(a.world, a.cap, parity, a.rank) + idx;
+    for (int p = 0; p < a.world; p++) a.base[p][o] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < a.world)
+    st_volatile_u64(reinterpret_cast<unsigned long long*>(a.base[tid] + peer_flag_off(a.world, parity, a.rank)), (unsigned long long)a.seq);
+  if (tid < a.world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(a.base[a.rank] + peer_flag_off(a.world, parity, tid));
+    while (ld_volatile_u64(f) != (unsigned long long)a.seq) { }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const double* mine = a.base[a.rank];
+  for (int idx = tid; idx < total; idx += nt) {
+    int s = 0, off = idx;
+    while (off >= a.seg[s].count) { off -= a.seg[s].count; s++; }
+    double acc = __ldcv(mine + peer_data_off(a.world, a.cap, parity, 0) + idx);
+    for (int src = 1; src < a.world; src++) {
+      const double v = __ldcv(mine + peer_data_off(a.world, a.cap, parity, src) + idx);
+      acc = a.seg[s].op == 0 ? acc + v : fmax(acc, v);
+    }
+    a.seg[s].buf[off] = acc;
+  }
+  __syncthreads();
+  if (a.epilogue && tid == 0) run_epilogue(a.epilogue, a.st, a.red);
 }
 
 __global__ void __launch_bounds__(256)

@@ -170,6 +170,21 @@ int run_exchange(mcba_ctx* ctx, const Exchange& ex) {
   if (ex.epilogue) { k_epilogue<<<1, 1, 0, ctx->stream>>>(ex.epilogue, ctx->state.p, ctx->red.p); CKL(); }
   return MCBA_OK;
 }
+// The same exchange as the TAIL of the kernel that produces its values (MCBA_FUSE=1, peer buffers, small payload): fills the argument
+// block and consumes the sequence number; false = use run_exchange after the kernel as before.
+bool tail_exchange(mcba_ctx* ctx, const Exchange& ex, PeerArgs* out) {
+  size_t total = 0;
+  for (int i = 0; i < ex.n; i++) total += ex.seg[i].count;
+  if (!(ctx->fuse && ctx->world > 1 && ctx->peer_ready && total > 0 && total <= (size_t)ctx->peer_cap && total <= 4096)) return false;
+  PeerArgs a{};
+  for (int i = 0; i < ex.n; i++) a.seg[i] = ex.seg[i];
+  a.nseg = ex.n; a.rank = ctx->rank; a.world = ctx->world; a.cap = ctx->peer_cap; a.seq = ++ctx->peer_seq;
+  for (int r = 0; r < ctx->world; r++) a.base[r] = ctx->peer_base[r];
+  a.counter = ctx->counter.p + 1;
+  a.epilogue = ex.epilogue; a.st = ctx->state.p; a.red = ctx->red.p;
+  *out = a;
+  return true;
+}
 #define EXCHANGE(...) do { if (ctx->world > 1) { Exchange ex_; __VA_ARGS__; int r_ = run_exchange(ctx, ex_); if (r_) return r_; } } while (0)
 
 int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : model == MODEL_TILTED ? 5 : 2; }
@@ -392,24 +407,19 @@ int trial_cost(mcba_ctx* ctx, int loss, double f_scale, bool trial, int slot) {
 
 // quadratic forms of the scaled Hessian; single-GPU: the last CTA also sums the partials and runs the scalar step that
 // consumes them (finalize 2 = reg, 3 = subspace); multi-GPU: sum only, the caller all-reduces and launches k_reg / k_subspace
-int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int finalize, bool dots = false) {
+int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int finalize, bool dots = false, const PeerArgs& pa = PeerArgs{}) {
   const DeviceProblem& P = ctx->P;
   const int nframe = P.motion_on ? P.F : 0;
   const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
   const int fb = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
   if (fb + nsh == 0) return MCBA_OK;
-  if (dots && two) {
-    if (P.fb == 12) k_quad<12, true><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
-                                                                                  finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
-    else k_quad<6, true><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
-                                                                     finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
-    CKL();
-    return MCBA_OK;
-  }
-  if (P.fb == 12) k_quad<12><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
-                                                                          finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
-  else k_quad<6><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p,
-                                                             finalize, ctx->counter.p, ctx->red.p, ctx->state.p);
+#define QUAD_ARGS P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p, finalize, ctx->counter.p, ctx->red.p, ctx->state.p, pa
+#define QUAD_LAUNCH(FBV, DOTSV, XV) k_quad<FBV, DOTSV, XV><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(QUAD_ARGS)
+  const bool dt = dots && two, xc = finalize == 4;
+  if (P.fb == 12) { if (dt) { if (xc) QUAD_LAUNCH(12, true, true); else QUAD_LAUNCH(12, true, false); } else { if (xc) QUAD_LAUNCH(12, false, true); else QUAD_LAUNCH(12, false, false); } }
+  else            { if (dt) { if (xc) QUAD_LAUNCH(6, true, true); else QUAD_LAUNCH(6, true, false); } else { if (xc) QUAD_LAUNCH(6, false, true); else QUAD_LAUNCH(6, false, false); } }
+#undef QUAD_LAUNCH
+#undef QUAD_ARGS
   CKL();
   return MCBA_OK;
 }
@@ -1395,12 +1405,20 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     result->initial_cost = h.cost; h.status = 1; finished = true;
     if (log && log_capacity > 0) { log[0] = mcba_log_row{0, 1, h.cost, NAN, NAN, 0.0}; nlog = 1; }
   }
+  PeerArgs scale_pa{};
   while (!finished) {
     if (single && scale_done) {
       scale_done = false;                               // done by the tail of k_expand_shared
     } else if (single) {
       k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
                                  1, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1)); CKL();
+    } else if (ctx->fuse && [&] {
+                 Exchange ex_; ex_.add(ctx->g.p, n_s, 0); ex_.add(ctx->diag_s.p, n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0);
+                 ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1);
+                 return tail_exchange(ctx, ex_, &scale_pa); }()) {
+      // cost sum, diag(H_ss), the frame part of the scaling, the exchange and the shared part + begin_iteration: one single-CTA launch
+      k_scale_exchange<<<1, 1024, 0, s>>>(n, n_s, ctx->Hss.p, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first,
+                                          ctx->red.p, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1), scale_pa); CKL();
     } else if (ctx->fuse) {
       // one exchange instead of two: the frame parts of the scaling sums only need local data and travel with g_s / diag / cost
       k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, ncp, 1, 1, ctx->red.p + RED_COST); CKL();
@@ -1430,8 +1448,15 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       break;
     }
 
-    r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, single ? 2 : 1); if (r) return r;
-    EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 1, 0); ex_.epilogue = EPI_REG);
+    {
+      PeerArgs pa{}; Exchange ex_; ex_.add(ctx->red.p + RED_AGG, 1, 0); ex_.epilogue = EPI_REG;
+      if (!single && (n_s > 0 || F > 0) && tail_exchange(ctx, ex_, &pa)) {           // reduction -> all-reduce -> reg, one launch
+        r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, 4, false, pa); if (r) return r;
+      } else {
+        r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, single ? 2 : 1); if (r) return r;
+        EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 1, 0); ex_.epilogue = EPI_REG);
+      }
+    }
     // Schur complement of the frame blocks
     if (n_s > 0 && F == 0) {
       const size_t nn2 = (size_t)n_s * n_s;
@@ -1488,8 +1513,15 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     // with no quadratic-form CTA at all (n == 0 is handled above; n_s == 0 and no frames cannot happen here) k_dots stays
     const bool fuse_dots = ctx->fuse && (n_s > 0 || F > 0);
     if (!fuse_dots) { k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL(); }
-    r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1, fuse_dots); if (r) return r;
-    EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE);   // AGG AGN ANN DOTGN_F GN2_F
+    {
+      PeerArgs pa{}; Exchange ex_; ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE;   // AGG AGN ANN DOTGN_F GN2_F
+      if (!single && fuse_dots && tail_exchange(ctx, ex_, &pa)) {
+        r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, 4, true, pa); if (r) return r;
+      } else {
+        r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1, fuse_dots); if (r) return r;
+        EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE);
+      }
+    }
 
     // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
     // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.
@@ -1513,10 +1545,12 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         else k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p + (P.T - 1), P.V, P.T);
         CKL();
       } else {
-        if (ctx->use_mma) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->view_cost.p, P.V, 1, ctx->red.p);
-        else k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p + (P.T - 1), P.V, P.T, ctx->red.p);
+        PeerArgs pa{}; Exchange exa; exa.add(ctx->red.p + RED_COSTNEW, 3, 0); exa.epilogue = EPI_ACCEPT;   // COSTNEW STEP2_F XN2_F
+        const bool tail = tail_exchange(ctx, exa, &pa);
+        if (ctx->use_mma) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->view_cost.p, P.V, 1, ctx->red.p, pa);
+        else k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p + (P.T - 1), P.V, P.T, ctx->red.p, pa);
         CKL();
-        EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0); ex_.epilogue = EPI_ACCEPT);   // COSTNEW STEP2_F XN2_F
+        if (!tail) EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0); ex_.epilogue = EPI_ACCEPT);
       }
       CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));

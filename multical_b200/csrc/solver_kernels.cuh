@@ -35,6 +35,32 @@ enum {
   RED_COUNT
 };
 
+// ---- NVLink peer-memory exchange (peer_allreduce.cuh): argument block, also taken by the kernels that run an exchange as their tail
+constexpr int PEER_MAX_WORLD = 16;
+constexpr int PEER_MAX_SEG = 6;
+constexpr int PEER_FLAG_STRIDE = 8;      // doubles (64 B) between flags
+
+struct PeerSeg { double* buf; int count; int op; };     // op 0 = sum, 1 = max
+struct SolverState;
+struct PeerArgs {
+  PeerSeg seg[PEER_MAX_SEG];
+  int nseg, rank, world, cap;
+  unsigned seq;
+  double* base[PEER_MAX_WORLD];          // peer-mapped base pointer of every rank's buffer (base[rank] = own)
+  unsigned* counter;
+  int epilogue;                          // EPI_* scalar step run by thread 0 after the reduction (single-CTA exchanges only)
+  SolverState* st;
+  double* red;
+};
+
+__host__ __device__ inline size_t peer_flag_off(int world, int parity, int src) { return (size_t)(parity * world + src) * PEER_FLAG_STRIDE; }
+__host__ __device__ inline size_t peer_data_off(int world, int cap, int parity, int src) {
+  return (size_t)2 * world * PEER_FLAG_STRIDE + ((size_t)parity * world + src) * cap;
+}
+__host__ __device__ inline size_t peer_buffer_doubles(int world, int cap) { return (size_t)2 * world * PEER_FLAG_STRIDE + (size_t)2 * world * cap; }
+
+__device__ void peer_allreduce_block(const PeerArgs& a);
+
 __device__ __forceinline__ double block_sum(double v, double* sm) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -174,6 +200,54 @@ __global__ void k_scale_part(int part, int n, int n_s, const double* diag_s, con
   if (part == 2 && threadIdx.x == 0) begin_iteration(st, red);
 }
 
+// Both parts, the cost sum, diag(H_ss) and the exchange in between as ONE single-CTA launch (MCBA_FUSE=1 with peer buffers).
+__global__ void __launch_bounds__(1024)
+k_scale_exchange(int n, int n_s, const double* Hss, double* diag_s, const double* Hff, const double* g, const double* x, double* sinv, double* d, double* gh,
+                 int first, double* red, const double* cost_part, int n_cost_part, SolverState* st, int fb, PeerArgs pa) {
+  __shared__ double sm[32];
+  double c = 0.0;
+  for (int i = threadIdx.x; i < n_cost_part; i += blockDim.x) c += cost_part[i];
+  c = block_sum(c, sm);
+  if (threadIdx.x == 0) red[RED_COST] = c;
+  for (int i = threadIdx.x; i < n_s; i += blockDim.x) diag_s[i] = Hss[(size_t)i * n_s + i];
+  double gh2 = 0, gm = 0, xs2 = 0;
+  for (int i = n_s + threadIdx.x; i < n; i += blockDim.x) {              // frame entries: local data only
+    const int f = (i - n_s) / fb, j = (i - n_s) % fb;
+    const double nrm = sqrt(fmax(Hff[(size_t)f * fb * fb + j * (fb + 1)], 0.0));
+    double si;
+    if (first) si = (nrm == 0.0) ? 1.0 : nrm; else si = fmax(nrm, sinv[i]);
+    sinv[i] = si;
+    const double di = 1.0 / si;
+    d[i] = di;
+    const double gi = g[i], ghi = di * gi, xs = x[i] * si;
+    gh[i] = ghi;
+    gh2 += ghi * ghi; gm = fmax(gm, fabs(gi)); xs2 += xs * xs;
+  }
+  double r;
+  r = block_sum(gh2, sm); if (threadIdx.x == 0) red[RED_GH2_F] = r;
+  r = block_max(gm, sm);  if (threadIdx.x == 0) red[RED_GMAX_F] = r;
+  r = block_sum(xs2, sm); if (threadIdx.x == 0) red[RED_XS2_F] = r;
+  __syncthreads();
+  peer_allreduce_block(pa);                                              // g_s, diag_s, cost, frame sums (sum) and the frame maximum (max)
+  __syncthreads();
+  gh2 = 0; gm = 0; xs2 = 0;
+  for (int i = threadIdx.x; i < n_s; i += blockDim.x) {                  // shared entries from the reduced diagonal / gradient
+    const double nrm = sqrt(fmax(diag_s[i], 0.0));
+    double si;
+    if (first) si = (nrm == 0.0) ? 1.0 : nrm; else si = fmax(nrm, sinv[i]);
+    sinv[i] = si;
+    const double di = 1.0 / si;
+    d[i] = di;
+    const double gi = g[i], ghi = di * gi, xs = x[i] * si;
+    gh[i] = ghi;
+    gh2 += ghi * ghi; gm = fmax(gm, fabs(gi)); xs2 += xs * xs;
+  }
+  r = block_sum(gh2, sm); if (threadIdx.x == 0) red[RED_GH2_S] = r;
+  r = block_max(gm, sm);  if (threadIdx.x == 0) red[RED_GMAX_S] = r;
+  r = block_sum(xs2, sm); if (threadIdx.x == 0) red[RED_XS2_S] = r;
+  if (threadIdx.x == 0) begin_iteration(st, red);
+}
+
 // tail of k_expand_shared (MCBA_FUSE=1, single GPU, no later kernel adds to H_ss): the last CTA to finish does what k_scale does
 __device__ __noinline__ void scale_epilogue(const ScaleEpilogue& e, int n_s, const double* Hss, const double* g) {
   __shared__ int scale_is_last;
@@ -198,11 +272,13 @@ constexpr int QUAD_WARPS = QUAD_THREADS / 32;
 // partial[frame or F + shared block][QS].  FB = parameters per frame block (6; 12 for RollingFrames' start+end pose).
 // DOTS (opt-in MCBA_FUSE=1, with two != 0): the records also carry u.v and v.v of the same rows (QS = 5), which is what k_dots
 // computes for (gh, gn) in a launch of its own; the last block then fills RED_DOTGN_* / RED_GN2_* as well.
-template <int FB, bool DOTS = false>
+// XCHG (finalize 4, MCBA_FUSE=1 on several GPUs): the last block also all-reduces the sums over the ranks and runs pa.epilogue.
+template <int FB, bool DOTS = false, bool XCHG = false>
 __global__ void __launch_bounds__(QUAD_THREADS)
 k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, const double* W, const double* d,
        const double* u, const double* v, int two, double* partial,
-       int finalize /*0 none, 1 sum, 2 sum+reg, 3 sum+subspace*/, unsigned* counter, double* red, SolverState* st) {
+       int finalize /*0 none, 1 sum, 2 sum+reg, 3 sum+subspace, 4 sum + all-reduce over the ranks + pa.epilogue*/, unsigned* counter, double* red,
+       SolverState* st, PeerArgs pa) {
   __shared__ double sm[32];
   __shared__ int is_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,6 +382,7 @@ k_quad(int n_s, int F, int motion_on, const double* Hss, const double* Hff, cons
     if (finalize == 2) reg_compute(st, red);
     else if (finalize == 3) subspace_compute(st, red);
   }
+  if constexpr (XCHG) { if (finalize == 4) { __syncthreads(); peer_allreduce_block(pa); } }      // the sums of all ranks, then the scalar step, in this launch
 }
 
 // trf.py: reg_term = -ag_value / Delta^2 with ag_value = min over [0, Delta/||g_h||] of a t^2 + b t,
@@ -1092,12 +1169,13 @@ k_step_trial(int n, int n_s, SolverState* st, const double* x, const double* d, 
 
 // trf.py inner loop after fun(x_new): actual reduction, update_tr_radius, check_termination.
 // sum of the per-view cost entries of the moment records (moments[v][T-1]) -> red[RED_COSTNEW]
-__global__ void k_cost_from_moments(const double* moments, int V, int T, double* red) {
+__global__ void k_cost_from_moments(const double* moments, int V, int T, double* red, PeerArgs pa) {
   __shared__ double sm[32];
   double c = 0.0;
   for (int v = threadIdx.x; v < V; v += blockDim.x) c += moments[(size_t)v * T];       // T == 1: compact per-view costs
   c = block_sum(c, sm);
   if (threadIdx.x == 0) red[RED_COSTNEW] = c;
+  if (pa.world > 1) { __syncthreads(); peer_allreduce_block(pa); }       // MCBA_FUSE=1: trial cost and step norms of all ranks + the acceptance test
 }
 
 // trf.py inner loop after fun(x_new): actual reduction, update_tr_radius, check_termination (one thread)
