@@ -89,6 +89,21 @@ def test_two_ranks_reproduce_the_single_rank_solve(name, peer, monkeypatch):
   assert np.abs(frames - np.asarray(single.motion.poses)).max() < 1e-7
 
 
+@pytest.mark.parametrize("fuse", [False, True])
+def test_four_ranks_with_uneven_shards(fuse, monkeypatch):
+  """Six frames over four ranks (2, 2, 1, 1): rank-ordered reductions with more than one peer, with and without the exchange tails."""
+  scene, z, calib, prob = gp.make("cube3_3x6")
+  single = calib.bundle_adjust().last_solve
+  for eng in calibration._engines.values(): eng.close()
+  calibration._engines.clear()
+  if fuse: monkeypatch.setenv("MCBA_FUSE", "1")
+  results = sharded_solve(calib, 4, True, monkeypatch)
+  assert [b - a for _, _, (a, b) in results] == [2, 2, 1, 1]
+  for out, res, _ in results:
+    assert res.nfev == single.nfev and abs(res.cost - single.cost) <= 1e-9 * single.cost
+    assert res.cost == results[0][1].cost
+
+
 @pytest.mark.parametrize("name", gm.CASES)
 def test_two_ranks_under_the_motion_models(name, monkeypatch):
   z, calib, prob = gm.make(name)
