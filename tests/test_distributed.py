@@ -122,12 +122,16 @@ def test_gather_and_broadcast_with_gloo_world2(tmp_path):
 
 
 @pytest.mark.gpu
-def test_two_gpu_solve_matches_single_gpu():
+@pytest.mark.parametrize("fuse", ["0", "1"])
+def test_two_gpu_solve_matches_single_gpu(fuse):
+  """fuse = "1": MCBA_FUSE=1 -- five exchanges per LM iteration, four of them as kernel tails (csrc/peer_allreduce.cuh peer_allreduce_block)."""
   import torch
   if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
   cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
          "--master-port", str(_free_port()), os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
-  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+  env = dict(os.environ); env.pop("MCBA_FUSE", None)
+  if fuse == "1": env["MCBA_FUSE"] = "1"
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
   assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
   assert "MULTI_GPU_OK" in out.stdout
