@@ -110,3 +110,17 @@ def test_the_product_refuses_the_interpreter_build(simt_library, monkeypatch):
   monkeypatch.setattr(_native, "_lib", None)
   with pytest.raises(_native.NativeError, match="no CPU path"):
     _native.load()
+
+
+def test_every_kernel_launch_and_shared_declaration_is_translated(simt_library):
+  """The interpreter build is a textual translation of csrc/: no `<<<`, `__shared__` or inline PTX may survive it, and every launch of
+  the sources must have become exactly one simt::launch."""
+  import os, re
+  import simt
+  n_src = n_out = 0
+  for f in simt.sources():
+    src = open(os.path.join(simt.CSRC, f)).read()
+    out = open(os.path.join(simt.OUT, f[:-3] + ".cpp" if f.endswith(".cu") else f)).read()
+    n_src += src.count("<<<"); n_out += out.count("simt::launch(")
+    assert "<<<" not in out and "asm volatile" not in out and not re.search(r"\b__shared__\b", out), f
+  assert n_src == n_out and n_src > 60
