@@ -154,6 +154,25 @@ def test_board_points_as_parameters_under_a_motion_model(name):
   assert abs(0.5 * rr @ rr - out.last_solve.cost) <= 1e-9 * out.last_solve.cost      # the returned objects hold the solved state
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_mirror_classes_keep_the_reference_semantics(name):
+  """What callers of the reference rely on (calibration.py:99-112,164-171,222-232; rolling_frames.py:95-103; hand_eye.py:54-58): a change
+  of master camera leaves every projection where it was, the parameter vector round-trips, objects pickle with their state keys."""
+  import pickle
+  z, calib, prob = make(name)
+  base = np.asarray(calib.reprojected.points)
+  ok = np.asarray(calib.reprojected.valid)
+  moved = calib.with_master(1)
+  assert np.abs(np.asarray(moved.camera_poses.poses)[1] - np.eye(4)).max() < 1e-12
+  assert np.abs(np.asarray(moved.reprojected.points)[ok] - base[ok]).max() < 1e-8
+  again = calib.with_param_vec(calib.param_vec)
+  assert np.abs(again.param_vec - calib.param_vec).max() < 1e-12
+  assert np.abs(np.asarray(again.reprojected.points)[ok] - base[ok]).max() < 1e-8
+  clone = pickle.loads(pickle.dumps(calib))
+  assert type(clone.motion) is type(calib.motion) and np.array_equal(clone.param_vec, calib.param_vec)
+  assert sorted(clone.motion.__getstate__()) == sorted(calib.motion.__getstate__())
+
+
 def test_motion_state_entry_points_refuse_the_wrong_problem():
   z, calib, prob = make("rolling_2x6")
   eng = calib._upload(calib.inliers)
