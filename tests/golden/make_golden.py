@@ -83,8 +83,8 @@ def motion_cases(ref, only):
     handeye_2x6   HandEye: frame pose = gripper_wrt_camera @ base_wrt_gripper[f] @ world_wrt_base; arm poses constructed so that
                   the scene's frame poses are reproduced exactly, then the two optimised transforms are perturbed; blocks enabled
                   as HandEyeCalibration.initialise leaves them (optimization/hand_eye.py:37)   (motion/hand_eye.py:14-90)"""
-  rng = np.random.default_rng(200)
   for name in ("rolling_2x6", "handeye_2x6"):
+    rng = np.random.default_rng(200)       # per case: a fixture does not depend on which other cases are regenerated with it
     if only and name not in only: continue
     scene = synthetic.make_scene(C=2, F=6, vis=0.5, seed=20 if name.startswith("rolling") else 21, model="standard")
     # hand-eye fixes cameras and camera poses (optimization/hand_eye.py:37), so that case starts from their true values
@@ -121,6 +121,14 @@ def motion_cases(ref, only):
       err_valid=calib.reprojection_error, ba_x=out.param_vec,
       ba_cost=0.5 * float(np.sum(evaluate(out.param_vec) ** 2)),
       ba_rms=float(np.sqrt(np.mean(out.reprojection_error ** 2))), **extra)
+    # the same model with boards=True (board points as parameters, board/charuco.py:112-117): layout and evaluate() at two points
+    cb = calib.enable(boards=True)
+    xb0 = cb.param_vec
+    xb1 = xb0 + np.random.default_rng(102).normal(0, 1e-4, xb0.size)
+    def evaluate_b(x):
+      c = cb.with_param_vec(x)
+      return (c.reprojected.points - c.point_table.points)[inl].ravel()
+    data.update(boards_x0=xb0, boards_x1=xb1, boards_r1=evaluate_b(xb1))
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **data)
     print(name, "N", int(inl.sum()), "n", x0.size, "cost0", 0.5 * float(np.sum(data["r0"] ** 2)), "cost", data["ba_cost"],

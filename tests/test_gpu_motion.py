@@ -131,8 +131,9 @@ def test_board_points_as_parameters_under_a_motion_model(name):
   calib = calib.enable(boards=True)
   prob = prob.copy(optimize=dict(prob.optimize, boards=True))
   x0 = prob.param_vec
-  assert np.abs(calib.param_vec - x0).max() < 1e-12
+  assert np.abs(calib.param_vec - x0).max() < 1e-12 and np.abs(x0 - z["boards_x0"]).max() < 1e-12       # layout of the running reference
   eng = calib._upload(calib.inliers)
+  assert np.abs(eng.residuals(calib._to_engine_vec(z["boards_x1"])) - z["boards_r1"]).max() < 1e-9        # evaluate() of the running reference
   x1 = x0 + np.random.default_rng(3).normal(0, 1e-4, x0.size)
   assert np.abs(eng.residuals(calib._to_engine_vec(x1)) - prob.residuals(x1)).max() < 1e-9
   S = prob.sparsity_matrix()

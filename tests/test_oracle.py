@@ -65,6 +65,8 @@ def test_oracle_motion_models_match_reference_golden(name):
   assert np.array_equal(S.indptr, z["sp_indptr"]) and np.array_equal(S.indices, z["sp_indices"])
   err, mask = prob.reprojection_error()
   assert np.abs(err[mask] - z["err_valid"]).max() < 1e-9
+  pb = prob.copy(optimize=dict(prob.optimize, boards=True))             # boards=True under the same motion model
+  assert np.abs(pb.param_vec - z["boards_x0"]).max() < 1e-12 and np.abs(pb.residuals(z["boards_x1"]) - z["boards_r1"]).max() < 1e-9
   out, res = prob.bundle_adjust()
   assert abs(res.cost - float(z["ba_cost"])) / float(z["ba_cost"]) < 1e-3
   e2, m2 = out.reprojection_error()
