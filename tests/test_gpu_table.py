@@ -176,3 +176,19 @@ def test_outlier_steps_match_reference_golden():
   out = calib.adjust_outliers(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=5.0))
   assert np.array_equal(out.inlier_mask, z["adj_inliers"])
   assert abs(np.sqrt(np.mean(out.reprojection_inliers ** 2)) - float(z["adj_rms"])) < 2e-3
+
+
+def test_workspace_calibrate_is_enable_plus_the_outlier_loop():
+  """multical_b200/workspace.py calibrate = Workspace.calibrate (workspace.py:228-247): the blocks it enables and the selectors it builds."""
+  from multical_b200 import workspace
+  scene, calib = scene_and_calib()
+  base = from_scene(scene)                                   # default blocks: poses only
+  out = workspace.calibrate(base, cameras=True, loss="soft_l1", auto_scale=3.0, num_adjustments=2)
+  want = base.enable(cameras=True, boards=False, camera_poses=True, motion=True, board_poses=True).adjust_outliers(
+    loss="soft_l1", tolerance=1e-4, num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=5.0),
+    select_scale=select_threshold(quantile=0.75, factor=3.0))
+  assert out.optimize == want.optimize and out.optimize["cameras"] is True
+  assert np.array_equal(out.inliers, want.inliers) and out.inliers.sum() < calib.valid.sum()
+  assert abs(out.last_solve.cost - want.last_solve.cost) <= 1e-12 * want.last_solve.cost
+  fixed = workspace.optimize(base, fix_intrinsic=True, fix_board_poses=True)
+  assert fixed.optimize["cameras"] is False and fixed.optimize["board_poses"] is False and fixed.optimize["motion"] is True

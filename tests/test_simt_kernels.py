@@ -64,6 +64,7 @@ test_resident_adjust_outliers_equals_host_loop = gt.test_resident_adjust_outlier
 test_table_from_detections_is_make_point_table = gt.test_table_from_detections_is_make_point_table
 test_table_state_machine_refuses_stale_errors = gt.test_table_state_machine_refuses_stale_errors
 test_outlier_steps_match_reference_golden = gt.test_outlier_steps_match_reference_golden
+test_workspace_calibrate_is_enable_plus_the_outlier_loop = gt.test_workspace_calibrate_is_enable_plus_the_outlier_loop
 
 # ---- tests/test_gpu_motion.py on the interpreter (RollingFrames, HandEye)
 test_motion_layout_residuals_and_errors_match_reference_golden = gm.test_layout_residuals_and_errors_match_reference_golden
