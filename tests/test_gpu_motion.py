@@ -174,6 +174,26 @@ def test_mirror_classes_keep_the_reference_semantics(name):
   assert sorted(clone.motion.__getstate__()) == sorted(calib.motion.__getstate__())
 
 
+def test_hand_eye_calibration_wrapper_from_arm_poses():
+  """HandEyeCalibration (optimization/hand_eye.py:13-97): robot-world initialisation from the arm's poses, then the GPU bundle adjustment
+  over the 12 hand-eye parameters (+ board poses); the known transforms of the fixture are recovered."""
+  from multical_b200.hand_eye import HandEyeCalibration
+  z, calib, prob = make("handeye_2x6")
+  static = from_scene(load_golden("handeye_2x6")[0])                                      # StaticFrames over the same frame poses
+  gripper_wrt_base = np.linalg.inv(z["base_wrt_gripper"])
+  he = HandEyeCalibration.initialise(static, gripper_wrt_base)
+  assert he.calib.optimize["cameras"] is False and he.calib.optimize["camera_poses"] is False and he.calib.optimize["motion"] is True
+  # the fixture's arm poses reproduce its frame poses exactly under the TRUE transforms (make_golden.py): the initialisation, which sees
+  # the perturbed start values' frames, must land within the perturbation (5 mm / 0.3 deg) of them
+  frames_true = np.asarray(static.motion.poses)
+  assert np.abs(np.asarray(he.calib.motion.poses) - frames_true).max() < 5e-2
+  before = 0.5 * float(np.sum((np.asarray(he.calib.reprojected.points) - np.asarray(he.calib.point_table.points))[he.calib.inliers] ** 2))
+  out = he.bundle_adjust()
+  assert isinstance(out, HandEyeCalibration) and out.calib.last_solve.cost < before
+  assert out.calib.last_solve.cost <= float(z["ba_cost"]) * (1 + 1e-3)                    # as good as the reference's run from its own start
+  assert set(out.cameras_wrt_gripper) == set(out.calib.cameras.names)
+
+
 def test_motion_state_entry_points_refuse_the_wrong_problem():
   z, calib, prob = make("rolling_2x6")
   eng = calib._upload(calib.inliers)
