@@ -127,3 +127,43 @@ def test_every_kernel_launch_and_shared_declaration_is_translated(simt_library):
     n_src += src.count("<<<"); n_out += out.count("simt::launch(")
     assert "<<<" not in out and "asm volatile" not in out and not re.search(r"\b__shared__\b", out), f
   assert n_src == n_out and n_src > 60
+
+
+# ---- the duck-typing claim: multical_b200.calibration.Calibration over the REFERENCE's own objects (build container only) ------------
+def _reference():
+  import os, sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim"))
+  import loader
+  return loader if loader.available() else None
+
+
+@pytest.mark.skipif(_reference() is None, reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("motion", ["static", "rolling", "hand_eye"])
+def test_calibration_over_the_reference_objects(motion):
+  """swapping the class is enough -- the reference's ParamList / Camera / PoseSet / Table / motion-model objects go into
+  this package's Calibration unchanged; projections equal the reference's own, and bundle_adjust returns reference objects again."""
+  import numpy as np
+  from multical_b200 import synthetic
+  from multical_b200.calibration import Calibration
+  loader = _reference()
+  ref = loader.load()
+  scene = synthetic.make_scene(C=2, F=5, vis=0.4, seed=77)
+  spec = None
+  if motion == "rolling":
+    end = scene["init"]["frame_poses"].copy(); end[:, :3, 3] += 0.005
+    spec = ("rolling", end)
+  elif motion == "hand_eye":
+    spec = ("hand_eye", scene["init"]["frame_poses"], np.eye(4), np.eye(4))          # arm poses = frame estimates, identity hand-eye pair
+  rc = loader.build_calibration(ref, scene, motion=spec)
+  if motion == "hand_eye": rc = rc.enable(camera_poses=False, cameras=False)
+  else: rc = rc.enable(cameras=True)
+  mine = Calibration(rc.cameras, rc.boards, rc.point_table, rc.camera_poses, rc.board_poses, rc.motion, optimize=rc.optimize)
+  assert np.abs(np.asarray(mine.param_vec) - np.asarray(rc.param_vec)).max() < 1e-12
+  ok = np.asarray(rc.reprojected.valid) & np.asarray(rc.point_table.valid)
+  assert np.abs(np.asarray(mine.reprojected.points)[ok] - np.asarray(rc.reprojected.points)[ok]).max() < 1e-9
+  assert np.abs(np.asarray(mine.reprojection_error) - np.asarray(rc.reprojection_error)).max() < 1e-9
+  out = mine.bundle_adjust(max_iterations=10)
+  assert type(out.motion) is type(rc.motion) and type(out.cameras[0]) is type(rc.cameras[0])
+  r = (np.asarray(out.reprojected.points) - np.asarray(out.point_table.points))[np.asarray(out.inliers)]
+  assert abs(0.5 * float(np.sum(r ** 2)) - out.last_solve.cost) <= 1e-9 * out.last_solve.cost
+  assert out.last_solve.cost < 0.5 * float(np.sum(((np.asarray(rc.reprojected.points) - np.asarray(rc.point_table.points))[np.asarray(rc.inliers)]) ** 2))
