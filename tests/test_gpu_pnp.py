@@ -58,6 +58,24 @@ def test_every_camera_model_against_opencv(model):
   assert np.abs(np.asarray(got.poses) - T_true).max() < 5e-3             # and it is the pose the scene was rendered from (0.3 px noise)
 
 
+def test_april_grid_style_ids_use_the_tag_grid():
+  """AprilGrid boards (aprilgrid.py:197-199): four corner ids per tag, the minimum-detections rule looks at tag ids = corner id // 4 on the
+  tag grid.  Sparse views around the thresholds: the device's verdict per view must be the oracle's (and poses agree where valid)."""
+  scene = synthetic.make_scene(C=2, F=6, vis=0.07, seed=43)
+  gt = scene["gt"]
+  calib = from_scene(scene, guess=False)
+  grid = (9, 9, 4, 18, 4)                                      # 315 corner ids -> tag ids 0..78 on a 9 x 9 grid
+  boards = [Board(p, size=(9, 9), min_points=18, min_rows=4, id_divisor=4) for p in scene["board_points"]]
+  got = make_pose_table(calib.point_table, boards, calib.cameras)
+  poses, ok, npts, err = pnp_oracle.make_pose_table("standard", gt["K"], gt["dist"], scene["board_points"], [grid] * scene["B"], scene["points"], scene["valid"])
+  assert 0 < ok.sum() < ok.size                                # the scene straddles the rule
+  assert np.array_equal(np.asarray(got.valid), ok) and np.array_equal(np.asarray(got.num_points), npts)
+  assert np.abs(np.asarray(got.poses) - poses).max() < 1e-6
+  for c, f, b in np.argwhere(ok | ~ok):                        # and the host mirror of the rule says the same
+    ids = np.flatnonzero(scene["valid"][c, f, b])
+    assert boards[b].has_min_detections(Table.create(ids=ids)) == bool(ok[c, f, b])
+
+
 def test_minimum_detections_rule_and_bad_inputs():
   scene = synthetic.make_scene(C=2, F=3, vis=0.5, seed=42)
   calib = from_scene(scene, guess=False)

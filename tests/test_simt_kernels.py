@@ -81,6 +81,7 @@ test_motion_outlier_loop_on_the_resident_table_equals_the_host_loop = gm.test_ou
 test_pnp_pose_table_matches_reference_golden = gn.test_pose_table_matches_reference_golden
 test_pnp_every_camera_model_against_opencv = gn.test_every_camera_model_against_opencv
 test_pnp_minimum_detections_rule_and_bad_inputs = gn.test_minimum_detections_rule_and_bad_inputs
+test_pnp_april_grid_style_ids_use_the_tag_grid = gn.test_april_grid_style_ids_use_the_tag_grid
 
 # ---- tests/test_gpu_candidates.py on the interpreter (opt-in variants)
 test_blocked_reduced_solve_reproduces_the_default_iterations = gc.test_blocked_reduced_solve_reproduces_the_default_iterations
