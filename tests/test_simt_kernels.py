@@ -168,3 +168,23 @@ def test_calibration_over_the_reference_objects(motion):
   r = (np.asarray(out.reprojected.points) - np.asarray(out.point_table.points))[np.asarray(out.inliers)]
   assert abs(0.5 * float(np.sum(r ** 2)) - out.last_solve.cost) <= 1e-9 * out.last_solve.cost
   assert out.last_solve.cost < 0.5 * float(np.sum(((np.asarray(rc.reprojected.points) - np.asarray(rc.point_table.points))[np.asarray(rc.inliers)]) ** 2))
+
+
+def test_cfg1_the_reference_cpu_case_end_to_end():
+  """BASELINE.json configs[0] (2 cameras x 20 frames of charuco_16x22, ~5k corners: the case the reference itself runs on the CPU):
+  Calibration.bundle_adjust through the C-ABI against the reference algorithm (oracle: dense numpy evaluate + the identical scipy call)."""
+  import numpy as np
+  from multical_b200 import synthetic
+  from multical_b200.calibration import from_scene
+  from oracle.ba_oracle import Problem
+  scene = synthetic.make_workload("cfg1")
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  assert np.array_equal(calib.param_vec, prob.param_vec)                                   # indexing / layout: bit exact
+  eng = calib._upload(calib.inliers)
+  assert 4000 < eng.N < 8000 and np.abs(eng.residuals() - prob.residuals()).max() < 1e-9
+  out = calib.bundle_adjust()
+  _, ref = prob.bundle_adjust()
+  assert out.last_solve.cost <= ref.cost * (1 + 1e-6) and out.last_solve.nfev <= ref.nfev
+  rms = np.sqrt(np.mean(out.reprojection_error ** 2))
+  assert abs(rms - np.sqrt(2 * ref.cost / eng.N)) < 1e-3 and 0.3 < rms < 0.5              # 0.3 px noise per coordinate
