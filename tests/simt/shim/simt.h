@@ -21,6 +21,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <map>
+#include <string>
 #include <vector>
 
 struct uint3 { unsigned x, y, z; };
@@ -74,6 +76,20 @@ inline thread_local const void* cur_body = nullptr;
 inline thread_local void (*cur_invoke)(const void*) = nullptr;
 inline thread_local const char* cur_name = "";
 inline thread_local long long total_launches = 0;
+// per-kernel dynamic counts (SIMT_STATS=<file>: appended at process exit): launches, block barriers completed, warp collectives
+// (shuffles / ballots / mma fragments exchanged) -- the serialisation points of a kernel, independent of any clock
+struct KernelStats { long long launches = 0, blocks = 0, block_barriers = 0, warp_collectives = 0; };
+inline std::map<std::string, KernelStats>& stats() { static std::map<std::string, KernelStats> m; return m; }
+inline thread_local KernelStats* cur_stats = nullptr;
+inline bool stats_on() { static const bool on = getenv("SIMT_STATS") != nullptr; return on; }
+inline void dump_stats() {
+  const char* path = getenv("SIMT_STATS");
+  FILE* f = path ? fopen(path, "a") : nullptr;
+  if (!f) return;
+  for (auto& kv : stats())
+    fprintf(f, "%s\t%lld\t%lld\t%lld\t%lld\n", kv.first.c_str(), kv.second.launches, kv.second.blocks, kv.second.block_barriers, kv.second.warp_collectives);
+  fclose(f);
+}
 
 [[noreturn]] inline void die(const char* what) {
   fprintf(stderr, "[simt] %s in kernel %s, block (%u,%u,%u)\n", what, cur_name, blk.idx.x, blk.idx.y, blk.idx.z);
@@ -84,7 +100,7 @@ inline void yield() { swapcontext(&cur->ctx, &sched_ctx); }
 inline void block_barrier() {
   Fiber* f = cur;
   blk.arrived++;
-  if (blk.arrived >= blk.alive) { blk.arrived = 0; blk.gen++; return; }
+  if (blk.arrived >= blk.alive) { blk.arrived = 0; blk.gen++; if (cur_stats) cur_stats->block_barriers++; return; }
   f->wait = WAIT_BLOCK; f->wait_gen = blk.gen;
   yield();
   f->wait = WAIT_NONE;
@@ -106,6 +122,7 @@ inline unsigned char (*exchange(const void* src, size_t n))[16] {
   const int par = f->xcount & 1;
   f->xcount++;
   memcpy(w.xbuf[par][f->lane], src, n);
+  if (cur_stats && f->lane == 0) cur_stats->warp_collectives++;
   warp_barrier();
   return w.xbuf[par];
 }
@@ -233,6 +250,12 @@ inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, const F
   blk.dyn = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
   blk.dyn_bytes = smem;
   cur_body = &body; cur_invoke = &invoke_body<F>;
+  if (stats_on()) {          // single-rank runs only (the map is not locked)
+    static bool registered = false;
+    if (!registered) { registered = true; stats(); atexit(dump_stats); }      // the map first: it must outlive the exit handler
+    cur_stats = &stats()[name];
+    cur_stats->launches++; cur_stats->blocks += (long long)grid.x * grid.y * grid.z;
+  } else cur_stats = nullptr;
   for (unsigned z = 0; z < grid.z; z++)
     for (unsigned y = 0; y < grid.y; y++)
       for (unsigned x = 0; x < grid.x; x++) {
