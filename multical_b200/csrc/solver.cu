@@ -119,6 +119,10 @@ struct mcba_ctx {
   DevBuf<double> err_valid, err_sorted, err_inl, err_inl_sorted, table_part, table_out;
   DevBuf<int64_t> table_ranks;
   DevBuf<unsigned char> sort_tmp;
+  // batched pose initialisation (mcba_pnp_views): buffers kept between calls
+  struct PnpBuffers {
+    DevBuf<int64_t> start; DevBuf<int32_t> ids, grid, n; DevBuf<double2> xy, und; DevBuf<double> bp, in, pose, err; DevBuf<uint8_t> ok;
+  } pnp;
 };
 
 #define CK(call)                                                                                   \
@@ -903,7 +907,8 @@ int mcba_pnp_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const int64_t* 
             MCBA_ERR_UNSUPPORTED, "id grids are limited to 64 x 64 (bit masks of the occupied rows / columns)");
   const int kint = 5 + model_nd(desc->model);
   cudaStream_t s = ctx->stream;
-  DevBuf<int64_t> d_start; DevBuf<int32_t> d_ids, d_grid, d_n; DevBuf<double2> d_xy, d_und; DevBuf<double> d_bp, d_in, d_pose, d_err; DevBuf<uint8_t> d_ok;
+  auto& d_start = ctx->pnp.start; auto& d_ids = ctx->pnp.ids; auto& d_grid = ctx->pnp.grid; auto& d_n = ctx->pnp.n; auto& d_xy = ctx->pnp.xy; auto& d_und = ctx->pnp.und;
+  auto& d_bp = ctx->pnp.bp; auto& d_in = ctx->pnp.in; auto& d_pose = ctx->pnp.pose; auto& d_err = ctx->pnp.err; auto& d_ok = ctx->pnp.ok;
   const size_t tot = (size_t)std::max<int64_t>(total, 1);
   CK(d_start.alloc((size_t)nv + 1)); CK(d_ids.alloc(tot)); CK(d_xy.alloc(tot)); CK(d_und.alloc(tot)); CK(d_grid.alloc((size_t)desc->B * 5));
   CK(d_bp.alloc((size_t)desc->B * desc->P * 3)); CK(d_in.alloc((size_t)desc->C * kint));
