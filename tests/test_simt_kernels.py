@@ -70,6 +70,7 @@ test_workspace_calibrate_is_enable_plus_the_outlier_loop = gt.test_workspace_cal
 test_motion_layout_residuals_and_errors_match_reference_golden = gm.test_layout_residuals_and_errors_match_reference_golden
 test_motion_normal_equations_match_finite_differences = gm.test_normal_equations_match_finite_differences
 test_motion_converged_solution_matches_dense_exact_oracle = gm.test_converged_solution_matches_dense_exact_oracle
+test_motion_iteration_table_matches_the_trf_model = gm.test_iteration_table_matches_the_trf_model
 test_rolling_projection_without_measurements_iterates_like_the_reference = gm.test_rolling_projection_without_measurements_iterates_like_the_reference
 test_motion_state_entry_points_refuse_the_wrong_problem = gm.test_motion_state_entry_points_refuse_the_wrong_problem
 test_motion_mirror_classes_keep_the_reference_semantics = gm.test_mirror_classes_keep_the_reference_semantics
