@@ -784,6 +784,60 @@ __device__ __forceinline__ void view_twist_maps(const DeviceProblem& p, int c, i
   twist_map(Rcf, pb.JL, tb, Ab + 36 * j);
 }
 
+// The same maps computed by the WHOLE warp (opt-in MCBA_EXPAND=parallel): view_twist_maps leaves 3 (5) lanes with ~300 dependent
+// flops each while 29 wait, once per view -- the longest serial piece of the expand kernels, which at 80 views per frame (cfg4) cost
+// more than the moment kernel.  Three short phases instead: chain products (R_c R_f, t_cf) / R·J_L products and t_b / the 36 entries
+// of every map, each entry by one lane from at most two products.  scr: 33 NP doubles of shared memory per warp.
+//   A = twist_map(Rl, JL, t):  rows 0-2 = [Rl JL | 0],  rows 3-5 = [t x (Rl JL) columns | Rl]
+template <int NP>
+__device__ __forceinline__ void view_twist_maps_par(const DeviceProblem& p, int c, int f, int b, int lane, double* Ac, double* Af, double* Ab, double* scr) {
+  const PoseT& pc = p.cam_T[c];
+  const PoseT& pb = p.board_T[b];
+  double* Rcf = scr;                    // [NP][9]
+  double* tcf = Rcf + 9 * NP;           // [NP][3]
+  double* tb = tcf + 3 * NP;            // [NP][3]
+  double* RJf = tb + 3 * NP;            // [NP][9]  R_c JL_f
+  double* RJb = RJf + 9 * NP;           // [NP][9]  R_cf JL_b
+  // phase A: the chain up to the frame pose(s)
+  for (int o = lane; o < 12 * NP; o += 32) {
+    const int j = o / 12, e = o % 12;
+    const PoseT& pf = p.frame_T[f * NP + j];
+    if (e < 9) { const int r = e / 3, cc = e % 3; Rcf[9 * j + e] = pc.R[3 * r] * pf.R[cc] + pc.R[3 * r + 1] * pf.R[3 + cc] + pc.R[3 * r + 2] * pf.R[6 + cc]; }
+    else { const int r = e - 9; tcf[3 * j + r] = pc.R[3 * r] * pf.t[0] + pc.R[3 * r + 1] * pf.t[1] + pc.R[3 * r + 2] * pf.t[2] + pc.t[r]; }
+  }
+  __syncwarp();
+  // phase B: R J_L products and the chain translation up to the board pose
+  for (int o = lane; o < 21 * NP; o += 32) {
+    const int j = o / 21, e = o % 21;
+    const PoseT& pf = p.frame_T[f * NP + j];
+    const double* Rc = Rcf + 9 * j;
+    if (e < 9) { const int r = e / 3, cc = e % 3; RJf[9 * j + e] = pc.R[3 * r] * pf.JL[cc] + pc.R[3 * r + 1] * pf.JL[3 + cc] + pc.R[3 * r + 2] * pf.JL[6 + cc]; }
+    else if (e < 18) { const int q = e - 9, r = q / 3, cc = q % 3; RJb[9 * j + q] = Rc[3 * r] * pb.JL[cc] + Rc[3 * r + 1] * pb.JL[3 + cc] + Rc[3 * r + 2] * pb.JL[6 + cc]; }
+    else { const int r = e - 18; tb[3 * j + r] = Rc[3 * r] * pb.t[0] + Rc[3 * r + 1] * pb.t[1] + Rc[3 * r + 2] * pb.t[2] + tcf[3 * j + r]; }
+  }
+  __syncwarp();
+  // phase C: map entries.  m = 0: camera pose (Rl = I, RJ = JL_c, t = t_c); 1 .. NP: frame pose j; NP+1 .. 2NP: board pose through chain j
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int o = lane; o < 36 * (1 + 2 * NP); o += 32) {
+    const int m = o / 36, e = o % 36, kk = e / 6, col = e % 6;
+    const double* RJ; const double* Rl; const double* t; double* out;
+    if (m == 0) { RJ = pc.JL; Rl = I3; t = pc.t; out = Ac; }
+    else if (m <= NP) { const int j = m - 1; RJ = RJf + 9 * j; Rl = pc.R; t = tcf + 3 * j; out = Af ? Af + 36 * j : nullptr; }
+    else { const int j = m - 1 - NP; RJ = RJb + 9 * j; Rl = Rcf + 9 * j; t = tb + 3 * j; out = Ab ? Ab + 36 * j : nullptr; }
+    if (!out) continue;
+    double val;
+    if (kk < 3) val = col < 3 ? RJ[3 * kk + col] : 0.0;
+    else {
+      const int r = kk - 3;
+      if (col < 3) {
+        const double a0 = RJ[col], a1 = RJ[3 + col], a2 = RJ[6 + col];
+        val = r == 0 ? t[1] * a2 - t[2] * a1 : r == 1 ? t[2] * a0 - t[0] * a2 : t[0] * a1 - t[1] * a0;
+      } else val = Rl[3 * r + col - 3];
+    }
+    out[e] = val;
+  }
+}
+
 // hand-eye twist maps of one view into Eh[6][12] = [A_W | A_G] (see k_expand_hand_eye): `role` 0 computes the W half, 1 the G half
 __device__ __forceinline__ void hand_eye_twist_maps(const DeviceProblem& p, int c, int f, int role, double* Eh) {
   const PoseT& pc = p.cam_T[c];
@@ -955,7 +1009,7 @@ k_point_blocks(DeviceProblem p, ViewKernelArgs a, double* Hss, double* W, double
 // k_expand_frames: one CTA per frame -> H_ff (FB x FB), g_f (FB) and W_f (n_s x FB), FB = 6 NP.  Warp w owns the cameras
 // c == w (mod EXP_WARPS): the camera-pose and intrinsics rows of W_f are written by exactly one warp (registers, flushed when
 // the camera changes); board-pose rows, H_ff and g_f are per-warp partials summed at the end.
-template <int NP>
+template <int NP, bool PAR = false>
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand_frames(DeviceProblem p, SolverBuffers s) {
   constexpr int FB = 6 * NP, KO = 6 * NP;
@@ -1017,7 +1071,8 @@ k_expand_frames(DeviceProblem p, SolverBuffers s) {
     const int b = p.view_board[v];
     if (c != cur_cam) { flush_camera(cur_cam); cur_cam = c; }
     for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
-    view_twist_maps<NP>(p, c, f, b, lane, Ac, Af, Ab);
+    if constexpr (PAR) { __shared__ double scr[EXP_WARPS][33 * NP]; view_twist_maps_par<NP>(p, c, f, b, lane, Ac, Af, Ab, scr[warp]); }
+    else view_twist_maps<NP>(p, c, f, b, lane, Ac, Af, Ab);
     __syncwarp();
     for (int o = lane; o < D * FB; o += 32) {         // Tm[:, 6j+k] = M[:, xi_j] Af_j
       const int i = o / FB, col = o % FB, j = col / 6, k = col % 6; double acc = 0.0;
@@ -1097,7 +1152,7 @@ __host__ __device__ inline int exps_warp_doubles(int T, int D, int B, int NP) { 
 // plain sum of moment records (its twist map does not depend on the view) kept lane-distributed in registers; the
 // camera-board and board-board blocks need the per-view board twist map(s).  Per-warp partials are summed once at the
 // end and added into H_ss / g_s with fp64 atomics.
-template <int NP>
+template <int NP, bool PAR = false>
 __global__ void __launch_bounds__(EXP_THREADS)
 k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) {
   constexpr int KO = 6 * NP;
@@ -1135,7 +1190,8 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) 
       if (i < T) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; macc[q] += m; }
     }
     if (p.off_bp >= 0) {
-      view_twist_maps<NP>(p, c, f, b, lane, nullptr, nullptr, Ab);
+      if constexpr (PAR) { __shared__ double scr[EXP_WARPS][33 * NP]; view_twist_maps_par<NP>(p, c, f, b, lane, nullptr, nullptr, Ab, scr[warp]); }
+      else view_twist_maps<NP>(p, c, f, b, lane, nullptr, nullptr, Ab);
       __syncwarp();
       for (int o = lane; o < D * 6; o += 32) {           // Um = sum_a M[:, xi_a] Ab_a
         const int i = o / 6, j = o % 6; double acc = 0.0;

@@ -84,6 +84,7 @@ struct mcba_ctx {
   int num_sms = 148;
   bool use_mma = true;    // per-view moments on the fp64 tensor path (MCBA_MOMENTS=fma selects the DFMA kernels)
   bool moments_f32 = false;    // MCBA_MOMENTS=f32: k_views_f32 (Hessian moments in FP32, gradient / cost in FP64) where it applies; A/B candidate
+  bool expand_par = false;     // MCBA_EXPAND=parallel: the per-view twist maps of the expand kernels computed by the whole warp; A/B candidate
   bool fuse = false;           // MCBA_FUSE=1: k_dots folded into k_quad, k_step + k_make_trial as one launch; A/B candidate
   bool chol_blocked = false;   // MCBA_CHOL=blocked: single-CTA blocked reduced solve (k_chol_blocked) instead of k_chol_small; A/B candidate
 
@@ -347,8 +348,13 @@ int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
   }
   const bool roll = P.motion == MOTION_ROLLING;
   if (P.motion_on && P.F > 0) {
-    if (roll) k_expand_frames<2><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
-    else k_expand_frames<1><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+    if (ctx->expand_par) {
+      if (roll) k_expand_frames<2, true><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+      else k_expand_frames<1, true><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+    } else {
+      if (roll) k_expand_frames<2><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+      else k_expand_frames<1><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+    }
     CKL();
   }
   const int nb = P.C * ctx->shared_chunks;
@@ -359,8 +365,13 @@ int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
     ep.sinv = ctx->sinv.p; ep.d = ctx->d.p; ep.gh = ctx->gh.p; ep.red = ctx->red.p; ep.st = ctx->state.p; ep.counter = ctx->counter.p + 3;
   }
   if (scaled) *scaled = ep.enabled != 0;
-  if (roll) k_expand_shared<2><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
-  else k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
+  if (ctx->expand_par) {
+    if (roll) k_expand_shared<2, true><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
+    else k_expand_shared<1, true><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
+  } else {
+    if (roll) k_expand_shared<2><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
+    else k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
+  }
   CKL();
   if (P.off_he >= 0 && P.V > 0) {         // hand-eye: the 12 shared motion parameters and their couplings on top (atomics)
     k_expand_hand_eye<<<nb, EXP_THREADS, expand_hand_eye_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
@@ -596,6 +607,11 @@ int mcba_create(int device, mcba_ctx** out) {
   { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; if (e && std::string(e) == "f32") ctx->moments_f32 = true; }
   { const char* e = getenv("MCBA_CHOL"); if (e && std::string(e) == "blocked") ctx->chol_blocked = true; }
   { const char* e = getenv("MCBA_FUSE"); if (e && std::string(e) == "1") ctx->fuse = true; }
+  { const char* e = getenv("MCBA_EXPAND"); if (e && std::string(e) == "parallel") ctx->expand_par = true; }
+  cudaFuncSetAttribute(k_expand_frames<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_frames<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_shared<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_expand_shared<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_chol_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 #define MMA_ATTR(MODEL) \
   cudaFuncSetAttribute(k_views_mma<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \

@@ -17,6 +17,7 @@ for v in small blocked; do
     python scripts/profile_one.py cfg2 solve > gpurun_out/ncu_chol_$v.log 2>&1
   python scripts/summarize_launches.py gpurun_out/launches_chol_$v.csv 2>/dev/null | head -12
 done
+for e in serial parallel; do echo "== expand maps $e (cfg4)"; MCBA_EXPAND=$e timeout 300 python scripts/profile_one.py cfg4 solve 2>&1 | tail -1; done
 for m in mma f32; do echo "== moments $m (cfg4: 5.5 M corners)"; MCBA_MOMENTS=$m timeout 300 python scripts/profile_one.py cfg4 time 2>&1 | tail -1; MCBA_MOMENTS=$m timeout 300 python scripts/profile_one.py cfg4 solve 2>&1 | tail -1; done
 timeout 300 python scripts/motion_pnp_timing.py > gpurun_out/motion_pnp_timing.txt 2>&1; cat gpurun_out/motion_pnp_timing.txt
 # 5. (needs --gpus 2 or more) the same A/B on several GPUs: scripts/run_ngpu_ab.sh with MCBA_FUSE=1 (five exchanges per iteration instead of six)

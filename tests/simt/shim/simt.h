@@ -82,6 +82,11 @@ struct KernelStats { long long launches = 0, blocks = 0, block_barriers = 0, war
 inline std::map<std::string, KernelStats>& stats() { static std::map<std::string, KernelStats> m; return m; }
 inline thread_local KernelStats* cur_stats = nullptr;
 inline bool stats_on() { static const bool on = getenv("SIMT_STATS") != nullptr; return on; }
+inline void dump_stats();
+inline void register_stats_dump() {       // once per process (launch<> is a template: a static in there exists once per launch site)
+  static bool registered = false;
+  if (!registered) { registered = true; stats(); atexit(dump_stats); }      // the map first: it must outlive the exit handler
+}
 inline void dump_stats() {
   const char* path = getenv("SIMT_STATS");
   FILE* f = path ? fopen(path, "a") : nullptr;
@@ -251,8 +256,7 @@ inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, const F
   blk.dyn_bytes = smem;
   cur_body = &body; cur_invoke = &invoke_body<F>;
   if (stats_on()) {          // single-rank runs only (the map is not locked)
-    static bool registered = false;
-    if (!registered) { registered = true; stats(); atexit(dump_stats); }      // the map first: it must outlive the exit handler
+    register_stats_dump();
     cur_stats = &stats()[name];
     cur_stats->launches++; cur_stats->blocks += (long long)grid.x * grid.y * grid.z;
   } else cur_stats = nullptr;

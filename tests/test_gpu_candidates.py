@@ -6,7 +6,9 @@ MCBA_FUSE=1 -- four launches fewer per LM iteration (k_dots folded into the seco
 launch, k_accept / k_scale as tails of the moment kernel / k_expand_shared): same iterations up to the summation order of a few sums.
 MCBA_MOMENTS=f32 -- k_views_f32: Hessian moments in FP32, residual / cost / gradient in FP64.  Not an exact replacement by design:
 the iteration path may differ, the minimiser may not -- converged cost within 1e-10 relative, evaluations within +-2, and the
-parity hook mcba_linearize keeps returning the fp64 normal equations."""
+parity hook mcba_linearize keeps returning the fp64 normal equations.
+MCBA_EXPAND=parallel -- the per-view twist maps of the expand kernels computed by the whole warp in three short phases instead of by
+3 (5) lanes with ~300 dependent flops each: the same products in the same order, so the normal equations must be IDENTICAL."""
 import numpy as np
 import pytest
 
@@ -71,3 +73,18 @@ def test_fp32_hessian_moments_reach_the_same_minimum(name, monkeypatch):
   assert np.array_equal(H, H32)                                               # the hook is not affected
   assert abs(got.cost - ref.cost) <= 1e-10 * ref.cost and abs(got.nfev - ref.nfev) <= 2
   assert abs(got4.cost - ref4.cost) <= 1e-6 * ref4.cost and abs(got4.nfev - ref4.nfev) <= 2      # the reference's default tolerance
+
+
+@pytest.mark.parametrize("name", ["standard_2x6", "cube3_3x6", "invalid_poses_3x6", "tilted_2x5"])
+def test_warp_parallel_twist_maps_give_identical_normal_equations(name, monkeypatch):
+  def linearise():
+    scene, z, calib, prob = gp.make(name)
+    return calib._upload(calib.inliers).linearize(z["x1"])
+  H, g, c = linearise()
+  monkeypatch.setenv("MCBA_EXPAND", "parallel")         # read by mcba_create: a fresh context is needed
+  for eng in calibration._engines.values(): eng.close()
+  monkeypatch.setattr(calibration, "_engines", {})
+  H2, g2, c2 = linearise()
+  for eng in calibration._engines.values(): eng.close()
+  calibration._engines.clear()
+  assert np.abs(H - H2).max() <= 1e-13 * np.abs(H).max() and np.abs(g - g2).max() <= 1e-13 * np.abs(g).max() and c == c2

@@ -88,6 +88,7 @@ test_pnp_april_grid_style_ids_use_the_tag_grid = gn.test_april_grid_style_ids_us
 test_blocked_reduced_solve_reproduces_the_default_iterations = gc.test_blocked_reduced_solve_reproduces_the_default_iterations
 test_fused_launches_reproduce_the_default_iterations = gc.test_fused_launches_reproduce_the_default_iterations
 test_fp32_hessian_moments_reach_the_same_minimum = gc.test_fp32_hessian_moments_reach_the_same_minimum
+test_warp_parallel_twist_maps_give_identical_normal_equations = gc.test_warp_parallel_twist_maps_give_identical_normal_equations
 
 
 @pytest.mark.parametrize("sms", ["1", "148"])
