@@ -67,20 +67,20 @@ struct Block {
 };
 
 // thread_local: several "ranks" (one host thread each, tests/test_simt_multirank.py) may run kernels at the same time
-inline thread_local Fiber* cur = nullptr;
-inline thread_local Block blk;
-inline thread_local ucontext_t sched_ctx;
-inline thread_local std::vector<Fiber> fibers;
-inline thread_local std::vector<Warp> warps;
-inline thread_local const void* cur_body = nullptr;
-inline thread_local void (*cur_invoke)(const void*) = nullptr;
-inline thread_local const char* cur_name = "";
-inline thread_local long long total_launches = 0;
+static thread_local Fiber* cur = nullptr;
+static thread_local Block blk;
+static thread_local ucontext_t sched_ctx;
+static thread_local std::vector<Fiber> fibers;
+static thread_local std::vector<Warp> warps;
+static thread_local const void* cur_body = nullptr;
+static thread_local void (*cur_invoke)(const void*) = nullptr;
+static thread_local const char* cur_name = "";
+static thread_local long long total_launches = 0;
 // per-kernel dynamic counts (SIMT_STATS=<file>: appended at process exit): launches, block barriers completed, warp collectives
 // (shuffles / ballots / mma fragments exchanged) -- the serialisation points of a kernel, independent of any clock
 struct KernelStats { long long launches = 0, blocks = 0, block_barriers = 0, warp_collectives = 0; };
 inline std::map<std::string, KernelStats>& stats() { static std::map<std::string, KernelStats> m; return m; }
-inline thread_local KernelStats* cur_stats = nullptr;
+static thread_local KernelStats* cur_stats = nullptr;
 inline bool stats_on() { static const bool on = getenv("SIMT_STATS") != nullptr; return on; }
 inline void dump_stats();
 inline void register_stats_dump() {       // once per process (launch<> is a template: a static in there exists once per launch site)
