@@ -284,7 +284,7 @@ def run_ours(args):
                           params=n_params if world == 1 else None, frames_per_gpu=base["F"], camera_model=scene["model"],
                           solver="TRF semantics (ftol=1e-4, x_scale=jac, max_nfev=100), exact Schur inner solve",
                           l2="flushed between timed iterations (256 MiB write)", seed=args.seed,
-                          kernel_variant=(" ".join(f"{k}={os.environ[k]}" for k in ("MCBA_MOMENTS", "MCBA_CHOL", "MCBA_FUSE", "MCBA_PEER") if k in os.environ) or "default")),
+                          kernel_variant=(" ".join(f"{k}={os.environ[k]}" for k in ("MCBA_MOMENTS", "MCBA_CHOL", "MCBA_FUSE", "MCBA_EXPAND", "MCBA_PEER") if k in os.environ) or "default")),
               lm_iters_per_sec=njev / (t_dev * 1e-3), nfev_plus_njev_per_step=evals / args.steps,
               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1e3 * t_e2e / args.steps,
                        lm_iters_per_sec=njev / t_e2e),
