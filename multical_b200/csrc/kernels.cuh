@@ -1065,11 +1065,27 @@ k_expand_frames(DeviceProblem p, SolverBuffers s) {
   };
 
   const int v0 = p.frame_view_start[f], v1 = p.frame_view_start[f + 1];
+  // PAR: the next record of this warp is fetched into registers while the current one is worked on (the load latency of a 1 KB record
+  // from L2 / HBM is otherwise paid once per view, serially)
+  constexpr int MR = NP == 1 ? 11 : 16;                // ceil(T / 32), T <= 325 (tilted) / 496 (rolling tilted)
+  double pre[PAR ? MR : 1];
+  auto next_view = [&](int from) { int v = from; while (v < v1 && p.view_cam[v] % EXP_WARPS != warp) v++; return v; };
+  auto fetch = [&](int v) {
+#pragma unroll
+    for (int q = 0; q < (PAR ? MR : 1); q++) { const int i = lane + 32 * q; if (i < T) pre[q] = s.moments[(size_t)v * T + i]; }
+  };
+  if constexpr (PAR) { const int vf = next_view(v0); if (vf < v1) fetch(vf); }
   for (int v = v0; v < v1; v++) {
     const int c = p.view_cam[v];
     if (c % EXP_WARPS != warp) continue;
     const int b = p.view_board[v];
     if (c != cur_cam) { flush_camera(cur_cam); cur_cam = c; }
+    if constexpr (PAR) {
+#pragma unroll
+      for (int q = 0; q < MR; q++) { const int i = lane + 32 * q; if (i < T) Ms[i] = pre[q]; }
+      const int vn = next_view(v + 1);
+      if (vn < v1) fetch(vn);
+    } else
     for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
     if constexpr (PAR) { __shared__ double scr[EXP_WARPS][33 * NP]; view_twist_maps_par<NP>(p, c, f, b, lane, Ac, Af, Ab, scr[warp]); }
     else view_twist_maps<NP>(p, c, f, b, lane, Ac, Af, Ab);
@@ -1181,13 +1197,26 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) 
   const int per = (l1 - l0 + chunks - 1) / chunks;
   const int a0 = l0 + chunk * per, a1 = min(l1, a0 + per);
   const PoseT& pc = p.cam_T[c];
+  double pre[PAR ? MAXT : 1];
+  auto fetch = [&](int li) {
+    const int v = p.cam_view_list[li];
+#pragma unroll
+    for (int q = 0; q < (PAR ? MAXT : 1); q++) { const int i = lane + 32 * q; if (i < T) pre[q] = s.moments[(size_t)v * T + i]; }
+  };
+  if constexpr (PAR) { if (a0 + warp < a1) fetch(a0 + warp); }
   for (int li = a0 + warp; li < a1; li += EXP_WARPS) {
     const int v = p.cam_view_list[li];
     const int f = p.view_frame[v], b = p.view_board[v];
+    if constexpr (PAR) {
+#pragma unroll
+      for (int q = 0; q < MAXT; q++) { const int i = lane + 32 * q; if (i < T) { const double m = pre[q]; Ms[i] = m; macc[q] += m; } }
+      if (li + EXP_WARPS < a1) fetch(li + EXP_WARPS);            // the next record of this warp, in flight during the work below
+    } else {
 #pragma unroll
     for (int q = 0; q < MAXT; q++) {
       const int i = lane + 32 * q;
       if (i < T) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; macc[q] += m; }
+    }
     }
     if (p.off_bp >= 0) {
       if constexpr (PAR) { __shared__ double scr[EXP_WARPS][33 * NP]; view_twist_maps_par<NP>(p, c, f, b, lane, nullptr, nullptr, Ab, scr[warp]); }
