@@ -120,9 +120,11 @@ def build(force=False):
       main = dst
       # marks the library as the interpreter build: multical_b200/_native.py refuses to load it unless a test asked for it
       with open(dst, "a") as fh: fh.write('\nextern "C" int mcba_simt_build(void) { return 1; }\n')
+  tmp = LIB + f".{os.getpid()}.tmp"            # never overwrite a library that a running test process may have mapped
   cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fno-strict-aliasing", "-w", "-Wno-unknown-pragmas",
-         "-I", os.path.join(HERE, "shim"), "-o", LIB, main, "-ldl"]
+         "-I", os.path.join(HERE, "shim"), "-o", tmp, main, "-ldl"]
   subprocess.run(cmd, check=True, cwd=OUT)
+  os.replace(tmp, LIB)
   return LIB
 
 
