@@ -81,7 +81,9 @@ ASM = re.compile(r"asm\s+volatile\s*\((.*?)\)\s*;", re.S)
 def rewrite_asm(m):
   body = m.group(1)
   if "mma.sync.aligned.m8n8k4" in body: return "simt::dmma884(c0, c1, a, b);"
-  if "ld.volatile.global.u64" in body: return "v = *(volatile const unsigned long long*)p;"
+  # a volatile load is how the kernels poll a flag written by another rank: let the other threads of the block run between polls (on
+  # hardware every lane makes progress; a fiber that spins without yielding would starve the lanes that publish this rank's own flags)
+  if "ld.volatile.global.u64" in body: return "v = *(volatile const unsigned long long*)p; simt::spin_yield();"
   if "st.volatile.global.u64" in body: return "*(volatile unsigned long long*)p = v;"
   raise ValueError("inline PTX without a host meaning: " + body[:80])
 

@@ -101,6 +101,7 @@ inline void dump_stats() {
   abort();
 }
 inline void yield() { swapcontext(&cur->ctx, &sched_ctx); }
+inline void spin_yield() { if (cur) yield(); }          // stays runnable: the scheduler comes back to it after the other fibers
 
 inline void block_barrier() {
   Fiber* f = cur;

@@ -72,7 +72,7 @@ def check_against_single(calib, results):
   for out, res, (a, b) in results:
     assert res.nfev == ref.nfev and res.status == ref.status
     assert abs(res.cost - ref.cost) <= 1e-9 * ref.cost
-    assert np.abs(np.asarray(out.camera_poses.poses) - np.asarray(single.camera_poses.poses)).max() < 1e-7      # shared blocks: every rank has them
+    assert np.abs(np.asarray(out.camera_poses.poses) - np.asarray(single.camera_poses.poses)).max() < 1e-6      # shared blocks: every rank has them (ftol 1e-4 solves)
     assert np.abs(np.stack([c.param_vec for c in out.cameras]) - np.stack([c.param_vec for c in single.cameras])).max() < 1e-6
   r0, r1 = results[0][1], results[1][1]
   assert r0.cost == r1.cost and np.array_equal(np.array(r0.log, float), np.array(r1.log, float), equal_nan=True)       # bit-identical scalar logic on every rank
@@ -86,7 +86,7 @@ def test_two_ranks_reproduce_the_single_rank_solve(name, peer, monkeypatch):
   results = sharded_solve(calib, 2, peer, monkeypatch)
   single = check_against_single(calib, results)
   frames = np.concatenate([np.asarray(out.motion.poses) for out, _, _ in results])
-  assert np.abs(frames - np.asarray(single.motion.poses)).max() < 1e-7
+  assert np.abs(frames - np.asarray(single.motion.poses)).max() < 1e-6
 
 
 @pytest.mark.parametrize("fuse", [False, True])
