@@ -43,16 +43,42 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   p->totalGlobalMem = (size_t)8 << 30;
   return cudaSuccess;
 }
-// device allocations are poisoned (0xFF bytes: NaN doubles, -1 integers) like uninitialised HBM may be
+// device allocations are poisoned (0xFF bytes: NaN doubles, -1 integers) like uninitialised HBM may be, and fenced: 64 canary bytes on
+// either side, checked when the buffer is freed -- a kernel writing just outside a buffer aborts the test instead of corrupting a neighbour
+namespace simt_mem {
+constexpr size_t GUARD = 64;
+inline std::mutex m;
+inline std::map<void*, size_t> sizes;
+inline void check(void* user, size_t bytes) {
+  const unsigned char* base = (const unsigned char*)user - GUARD;
+  for (size_t i = 0; i < GUARD; i++)
+    if (base[i] != 0xA5 || base[GUARD + bytes + i] != 0xA5) {
+      fprintf(stderr, "[simt] out-of-bounds write %s a device buffer of %zu bytes (canary at offset %zd)\n", base[i] != 0xA5 ? "before" : "after", bytes,
+              base[i] != 0xA5 ? (ssize_t)i - (ssize_t)GUARD : (ssize_t)(bytes + i));
+      abort();
+    }
+}
+}  // namespace simt_mem
 template <class T>
 static inline cudaError_t cudaMalloc(T** p, size_t bytes) {
-  void* q = malloc(bytes ? bytes : 1);
+  unsigned char* q = (unsigned char*)malloc(bytes + 2 * simt_mem::GUARD);
   if (!q) return cudaErrorMemoryAllocation;
-  memset(q, 0xFF, bytes);
-  *p = (T*)q;
+  memset(q, 0xA5, simt_mem::GUARD);
+  memset(q + simt_mem::GUARD, 0xFF, bytes);
+  memset(q + simt_mem::GUARD + bytes, 0xA5, simt_mem::GUARD);
+  { std::lock_guard<std::mutex> lk(simt_mem::m); simt_mem::sizes[q + simt_mem::GUARD] = bytes; }
+  *p = (T*)(q + simt_mem::GUARD);
   return cudaSuccess;
 }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) {
+  if (!p) return cudaSuccess;
+  size_t bytes;
+  { std::lock_guard<std::mutex> lk(simt_mem::m); auto it = simt_mem::sizes.find(p); if (it == simt_mem::sizes.end()) { fprintf(stderr, "[simt] cudaFree of an unknown pointer\n"); abort(); }
+    bytes = it->second; simt_mem::sizes.erase(it); }
+  simt_mem::check(p, bytes);
+  free((unsigned char*)p - simt_mem::GUARD);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
