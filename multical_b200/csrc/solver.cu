@@ -14,6 +14,7 @@
 
 #include "../../include/mcba.h"
 #include "solver_kernels.cuh"
+#include "linearize.cuh"
 #include "pack_kernels.cuh"
 #include "table_kernels.cuh"
 #include "peer_allreduce.cuh"
@@ -102,6 +103,10 @@ struct mcba_ctx {
   DevBuf<double> img_h, he_rt, he_rt2; DevBuf<PoseT> he_T, arm_T;
   // solver buffers
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
+  // fused linearisation (linearize.cuh): per-(CTA, camera) records of the shared blocks, per-camera board partials, per-frame costs
+  DevBuf<double> spart, bpart, frame_cost;
+  int lin_grid = 1, lin_split = 1;
+  bool fused_lin = true;       // false for hand-eye frames: per-view moment records + the round-1 expand kernels (they carry the 12 shared motion parameters)
   DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
   DevBuf<SolverState> state;
   DevBuf<unsigned> counter;
@@ -296,6 +301,56 @@ int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& 
   return MCBA_OK;
 }
 
+
+// ---------------------------------------------------------------- fused linearisation (linearize.cuh)
+template <int MODEL, bool ROLL>
+size_t lin_smem_bytes(const DeviceProblem& P, int split) {
+  using S = LinShape<MODEL, ROLL>;
+  return sizeof(double) * lin_smem_doubles(S::NC, S::T, S::D, S::FB, S::NIN, P.B, S::NP, S::NPAIR, split);
+}
+size_t lin_smem_for(const DeviceProblem& P, int split) {
+  const bool roll = P.motion == MOTION_ROLLING;
+#define LS(MODEL) return roll ? lin_smem_bytes<MODEL, true>(P, split) : lin_smem_bytes<MODEL, false>(P, split);
+  switch (P.model) {
+    case MODEL_STANDARD: LS(MODEL_STANDARD)
+    case MODEL_RATIONAL: LS(MODEL_RATIONAL)
+    case MODEL_THIN_PRISM: LS(MODEL_THIN_PRISM)
+    case MODEL_TILTED: LS(MODEL_TILTED)
+    default: LS(MODEL_FISHEYE)
+  }
+#undef LS
+}
+// one launch: H_ff, g_f, W_f, frame costs and the per-CTA records of the shared blocks at the (trial or current) state
+int launch_linearize(mcba_ctx* ctx, const DeviceProblem& P, int loss, double f_scale) {
+  if (P.F == 0) return MCBA_OK;
+  LinArgs a{}; a.loss = loss; a.f_scale = f_scale; a.split = ctx->lin_split;
+  a.Hff = ctx->Hff.p; a.g = ctx->g.p; a.W = ctx->W.p; a.spart = ctx->spart.p; a.frame_cost = ctx->frame_cost.p;
+  const size_t sm = lin_smem_for(P, ctx->lin_split);
+  const bool roll = P.motion == MOTION_ROLLING;
+  cudaStream_t s = ctx->stream;
+#define LL(MODEL) if (roll) k_linearize<MODEL, true><<<ctx->lin_grid, LIN_THREADS, sm, s>>>(P, a); else k_linearize<MODEL, false><<<ctx->lin_grid, LIN_THREADS, sm, s>>>(P, a);
+  switch (P.model) {
+    case MODEL_STANDARD: LL(MODEL_STANDARD) break;
+    case MODEL_RATIONAL: LL(MODEL_RATIONAL) break;
+    case MODEL_THIN_PRISM: LL(MODEL_THIN_PRISM) break;
+    case MODEL_TILTED: LL(MODEL_TILTED) break;
+    default: LL(MODEL_FISHEYE) break;
+  }
+#undef LL
+  CKL();
+  return MCBA_OK;
+}
+// per-CTA records -> H_ss, g_s, cost (stores, fixed summation order)
+int launch_reduce_shared(mcba_ctx* ctx, const DeviceProblem& P) {
+  ReduceArgs r{}; r.spart = ctx->spart.p; r.nparts = P.F > 0 ? ctx->lin_grid : 0; r.Hss = ctx->Hss.p; r.g = ctx->g.p; r.bpart = ctx->bpart.p;
+  r.frame_cost = ctx->frame_cost.p; r.F = P.F; r.cost_out = ctx->red.p + RED_COST; r.counter = ctx->counter.p + 3;
+  const size_t sm = sizeof(double) * reduce_smem_doubles(P.T, P.D, P.B);
+  if (P.motion == MOTION_ROLLING) k_reduce_shared<2><<<P.C, RED_THREADS, sm, ctx->stream>>>(P, r);
+  else k_reduce_shared<1><<<P.C, RED_THREADS, sm, ctx->stream>>>(P, r);
+  CKL();
+  return MCBA_OK;
+}
+
 // DeviceProblem view whose parameter pointers are the trial state
 DeviceProblem with_state(const mcba_ctx* ctx, bool trial) {
   DeviceProblem P = ctx->P;
@@ -329,6 +384,7 @@ size_t expand_hand_eye_smem(const DeviceProblem& P) { return sizeof(double) * ((
 int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial, bool accept_tail = false) {
   ctx->cur_loss = loss; ctx->cur_f_scale = f_scale;
   DeviceProblem P = with_state(ctx, trial);
+  if (ctx->fused_lin) return launch_linearize(ctx, P, loss, f_scale);
   ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p; a.view_cost = ctx->view_cost.p;
   if (accept_tail) { a.acc_st = ctx->state.p; a.acc_red = ctx->red.p; a.acc_counter = ctx->counter.p + 2; }
   return launch_moments(ctx, P, a);
@@ -341,6 +397,31 @@ int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
   DeviceProblem P = with_state(ctx, false);
   SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p, 0};
   cudaStream_t s = ctx->stream;
+  if (ctx->fused_lin) {
+    if (scaled) *scaled = false;
+    if (P.off_pt >= 0) {       // boards=True: k_point_blocks adds the point rows / columns on top (atomics): they start at zero
+      CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
+      CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n_s, 1), s));
+    }
+    int r = launch_reduce_shared(ctx, P); if (r) return r;
+    if (P.off_pt >= 0 && P.V > 0) {
+      const bool roll = P.motion == MOTION_ROLLING;
+      ViewKernelArgs a{}; a.loss = ctx->cur_loss; a.f_scale = ctx->cur_f_scale;
+      const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
+#define PB(MODEL) if (roll) k_point_blocks<MODEL, 2><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); \
+                  else k_point_blocks<MODEL, 1><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p);
+      switch (P.model) {
+        case MODEL_STANDARD: PB(MODEL_STANDARD) break;
+        case MODEL_RATIONAL: PB(MODEL_RATIONAL) break;
+        case MODEL_THIN_PRISM: PB(MODEL_THIN_PRISM) break;
+        case MODEL_TILTED: PB(MODEL_TILTED) break;
+        default: PB(MODEL_FISHEYE) break;
+      }
+#undef PB
+      CKL();
+    }
+    return MCBA_OK;
+  }
   sb.zero_shared = (ctx->fuse && P.motion_on && P.F > 0) ? 1 : 0;         // cleared by k_expand_frames itself
   if (!sb.zero_shared) {
     CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
@@ -399,7 +480,7 @@ int finish_linearization(mcba_ctx* ctx) {
   const DeviceProblem& P = ctx->P;
   cudaStream_t s = ctx->stream;
   const int nb = P.C * ctx->shared_chunks;
-  k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL();
+  if (!ctx->fused_lin) { k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL(); }      // fused: k_reduce_shared wrote it
   if (P.n_s > 0) { k_diag<<<(P.n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, P.n_s, ctx->diag_s.p); CKL(); }
   EXCHANGE(ex_.add(ctx->g.p, P.n_s, 0); ex_.add(ctx->diag_s.p, P.n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0));
   return MCBA_OK;
@@ -488,9 +569,27 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   // solver buffers
   ctx->shared_chunks = std::max(1, std::min(32, (ctx->num_sms * 2) / std::max(C, 1)));
   if (V / std::max(C, 1) < 64) ctx->shared_chunks = 1;
-  CK(ctx->moments.alloc((size_t)std::max(V, 1) * P.T));
+  ctx->fused_lin = P.motion != MOTION_HAND_EYE;
+  if (ctx->fused_lin) {
+    // static frame -> CTA map (bit-reproducible partial sums): the smallest grid that keeps every CTA at ceil(F / resident CTAs) frames
+    const int max_grid = ctx->num_sms * 2;
+    const int per = (std::max(F, 1) + max_grid - 1) / max_grid;
+    ctx->lin_grid = std::max(1, (std::max(F, 1) + per - 1) / per);
+    int split = 1;
+    while (split < LIN_WARPS && C * split * 2 <= LIN_WARPS) split *= 2;      // few cameras: several warps share a view
+    ctx->lin_split = split;
+    REQUIRE(lin_smem_for(P, split) <= 220 * 1024, MCBA_ERR_UNSUPPORTED, "too many boards for the linearisation kernel's shared memory");
+    CK(ctx->spart.alloc((size_t)ctx->lin_grid * C * lin_record_doubles(P.T, P.D, B)));
+    CK(ctx->bpart.alloc((size_t)C * B * 42));
+    CK(ctx->frame_cost.alloc((size_t)std::max(F, 1)));
+    CK(ctx->moments.alloc(1));
+  } else {
+    CK(ctx->moments.alloc((size_t)std::max(V, 1) * P.T));
+  }
   CK(ctx->Hss.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1)));
+  CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1), ctx->stream));      // blocks no kernel writes (camera x other camera ...) stay zero
   CK(ctx->g.alloc((size_t)std::max(P.n, 1)));
+  CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), ctx->stream));
   CK(ctx->Hff.alloc((size_t)std::max(F, 1) * fbs * fbs));
   CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * fbs));
   CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * fbs));
@@ -504,7 +603,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
   CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 5));
   CK(ctx->state.alloc(1));
-  CK(ctx->counter.alloc(4)); CK(cudaMemsetAsync(ctx->counter.p, 0, 4 * sizeof(unsigned), ctx->stream));
+  CK(ctx->counter.alloc(8)); CK(cudaMemsetAsync(ctx->counter.p, 0, 8 * sizeof(unsigned), ctx->stream));
   if (!keep_state) {     // a re-selection of the resident table (mcba_table_select) keeps the parameter state
     CK(cudaMemsetAsync(ctx->cam_rt.p, 0, sizeof(double) * C * 6, ctx->stream));
     CK(cudaMemsetAsync(ctx->board_rt.p, 0, sizeof(double) * B * 6, ctx->stream));
@@ -620,6 +719,13 @@ int mcba_create(int device, mcba_ctx** out) {
   cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   MMA_ATTR(MODEL_STANDARD) MMA_ATTR(MODEL_RATIONAL) MMA_ATTR(MODEL_THIN_PRISM) MMA_ATTR(MODEL_FISHEYE) MMA_ATTR(MODEL_TILTED)
 #undef MMA_ATTR
+#define LIN_ATTR(MODEL) \
+  cudaFuncSetAttribute(k_linearize<MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+  cudaFuncSetAttribute(k_linearize<MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  LIN_ATTR(MODEL_STANDARD) LIN_ATTR(MODEL_RATIONAL) LIN_ATTR(MODEL_THIN_PRISM) LIN_ATTR(MODEL_FISHEYE) LIN_ATTR(MODEL_TILTED)
+#undef LIN_ATTR
+  cudaFuncSetAttribute(k_reduce_shared<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_reduce_shared<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_frames<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_frames<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_shared<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1414,7 +1520,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
 
   // One host synchronisation per trial step: everything from the Jacobian scaling to the acceptance test of the next
   // trial point is queued behind the previous step; k_begin_iteration's `done` flag turns the tail into no-ops.
-  const int ncp = P.C * ctx->shared_chunks;
+  const int ncp = ctx->fused_lin ? 0 : P.C * ctx->shared_chunks;      // fused linearisation: the cost is already summed (k_reduce_shared)
   double last_reduction = NAN, last_step = NAN;
   int nlog = 0;
   int first = 1;
@@ -1427,8 +1533,11 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (log && log_capacity > 0) { log[0] = mcba_log_row{0, 1, h.cost, NAN, NAN, 0.0}; nlog = 1; }
   }
   PeerArgs scale_pa{};
+  bool lin_current = true;        // H, g describe the current x (false after a rejected last trial: the fused pass overwrote the frame blocks)
   while (!finished) {
-    if (single && scale_done) {
+    if (!lin_current) {
+      // nothing to rescale: the loop is about to end (rejected step and no evaluations / a termination test fired); the gradient norm of the unchanged x is in the state
+    } else if (single && scale_done) {
       scale_done = false;                               // done by the tail of k_expand_shared
     } else if (single) {
       k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
@@ -1460,8 +1569,10 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
     if (h.status != -99 || h.nfev >= h.max_nfev) {
       // the host already knows this is the last pass of the outer loop (termination test fired or out of evaluations):
       // only the gradient norm of the final point is still needed for the last table row
-      CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
+      if (lin_current) {
+        CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+      }
       if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; return MCBA_ERR_NONFINITE; }
       if (h.iteration == 0) result->initial_cost = h.cost;
       if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.nfev, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
@@ -1562,13 +1673,15 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
         // the acceptance test ran as the tail of the moment kernel
       } else if (single) {
         // per-view costs: compact array written by the DMMA kernel, or the last entry of each moment record (DFMA kernels)
-        if (ctx->use_mma) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->view_cost.p, P.V, 1);
+        if (ctx->fused_lin) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->frame_cost.p, P.F, 1);
+        else if (ctx->use_mma) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->view_cost.p, P.V, 1);
         else k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p + (P.T - 1), P.V, P.T);
         CKL();
       } else {
         PeerArgs pa{}; Exchange exa; exa.add(ctx->red.p + RED_COSTNEW, 3, 0); exa.epilogue = EPI_ACCEPT;   // COSTNEW STEP2_F XN2_F
         const bool tail = tail_exchange(ctx, exa, &pa);
-        if (ctx->use_mma) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->view_cost.p, P.V, 1, ctx->red.p, pa);
+        if (ctx->fused_lin) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->frame_cost.p, P.F, 1, ctx->red.p, pa);
+        else if (ctx->use_mma) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->view_cost.p, P.V, 1, ctx->red.p, pa);
         else k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p + (P.T - 1), P.V, P.T, ctx->red.p, pa);
         CKL();
         if (!tail) EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0); ex_.epilogue = EPI_ACCEPT);
@@ -1608,6 +1721,7 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
       r = expand(ctx, fuse_tails ? 0 : -1, &scale_done); if (r) return r;
     } else {
       last_reduction = 0.0; last_step = 0.0;
+      if (ctx->fused_lin) lin_current = false;
       if (h.status == -99 && h.nfev >= h.max_nfev) {
         // out of evaluations on a rejected step: the pose tables describe the rejected point, restore them
         r = prepare(ctx, with_state(ctx, false)); if (r) return r;
@@ -1658,7 +1772,7 @@ int mcba_bench_launch(mcba_ctx* ctx, int which, int repeats) {
   struct SolvingFlag { bool& f; explicit SolvingFlag(bool& r) : f(r) { f = true; } ~SolvingFlag() { f = false; } } solving_flag(ctx->solving);   // time what a solve runs
   for (int i = 0; i < repeats; i++) {
     ViewKernelArgs a{}; a.loss = 0; a.f_scale = 1.0;
-    if (which == MCBA_BENCH_LINEARIZE) { a.moments = ctx->moments.p; r = launch_moments(ctx, P, a); }
+    if (which == MCBA_BENCH_LINEARIZE) { if (ctx->fused_lin) r = launch_linearize(ctx, P, 0, 1.0); else { a.moments = ctx->moments.p; r = launch_moments(ctx, P, a); } }
     else if (which == MCBA_BENCH_COST) { a.view_cost = ctx->view_cost.p; r = launch_views<MODE_COST>(ctx, P, a); }
     else { ctx->err = "unsupported bench kernel"; return MCBA_ERR_ARG; }
     if (r) return r;

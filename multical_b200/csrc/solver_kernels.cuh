@@ -162,7 +162,7 @@ __device__ __forceinline__ void scale_body(int n, int n_s, const double* diag_s,
     double c = 0.0;
     for (int i = threadIdx.x; i < n_cost_part; i += blockDim.x) c += __ldcg(&cost_part[i]);
     c = block_sum(c, sm);
-    if (threadIdx.x == 0) { red[RED_COST] = c; begin_iteration(st, red); }
+    if (threadIdx.x == 0) { if (n_cost_part > 0) red[RED_COST] = c; begin_iteration(st, red); }      // no partials: the cost is already in place
   }
 }
 __global__ void k_scale(int n, int n_s, const double* diag_s, const double* Hss, const double* Hff, const double* g, const double* x,

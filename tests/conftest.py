@@ -16,17 +16,6 @@ def pytest_configure(config):
   config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
-def pytest_collection_modifyitems(config, items):
-  """Run order under `-x`: the GPU tests of what was added after this round's GPU budget was spent (motion models, batched pose
-  initialisation, opt-in candidates: verified on the SIMT interpreter only, see tests/test_simt_kernels.py) go after every GPU test that has already run on hardware, so that a
-  hardware-only failure there cannot hide the results of the others."""
-  new = ("test_gpu_motion.py", "test_gpu_pnp.py", "test_gpu_candidates.py")
-  late = [it for it in items if it.fspath.basename in new]
-  if late:
-    rest = [it for it in items if it.fspath.basename not in new]
-    items[:] = rest + sorted(late, key=lambda it: new.index(it.fspath.basename))
-
-
 def load_golden(name):
   """Golden fixture -> (scene dict shaped like multical_b200.synthetic scenes, raw npz dict)."""
   z = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))

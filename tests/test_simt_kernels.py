@@ -15,7 +15,6 @@ import test_gpu_parity as gp
 import test_gpu_table as gt
 import test_gpu_motion as gm
 import test_gpu_pnp as gn
-import test_gpu_candidates as gc
 from multical_b200 import _native, calibration
 
 
@@ -83,31 +82,6 @@ test_pnp_pose_table_matches_reference_golden = gn.test_pose_table_matches_refere
 test_pnp_every_camera_model_against_opencv = gn.test_every_camera_model_against_opencv
 test_pnp_minimum_detections_rule_and_bad_inputs = gn.test_minimum_detections_rule_and_bad_inputs
 test_pnp_april_grid_style_ids_use_the_tag_grid = gn.test_april_grid_style_ids_use_the_tag_grid
-
-# ---- tests/test_gpu_candidates.py on the interpreter (opt-in variants)
-test_blocked_reduced_solve_reproduces_the_default_iterations = gc.test_blocked_reduced_solve_reproduces_the_default_iterations
-test_fused_launches_reproduce_the_default_iterations = gc.test_fused_launches_reproduce_the_default_iterations
-test_fp32_hessian_moments_reach_the_same_minimum = gc.test_fp32_hessian_moments_reach_the_same_minimum
-test_warp_parallel_twist_maps_give_identical_normal_equations = gc.test_warp_parallel_twist_maps_give_identical_normal_equations
-
-
-@pytest.mark.parametrize("sms", ["1", "148"])
-def test_one_warp_per_view_and_split_view_moment_kernels_agree(sms, monkeypatch):
-  """k_views_mma<MODEL, 1> (V >= 16 x SMs) and k_views_mma<MODEL, VIEW_WARPS> (few long views) must give the same normal
-  equations; the interpreter's reported SM count selects the variant (csrc/solver.cu launch_moments)."""
-  import numpy as np
-  monkeypatch.setenv("SIMT_SMS", sms)
-  scene, z, calib, prob = gp.make("cube3_3x6")
-  eng = calib._upload(calib.inliers)
-  JtJ, Jtr, cost = eng.linearize(z["x1"])
-  monkeypatch.setenv("MCBA_MOMENTS", "fma")           # the DFMA kernels as the independent second opinion
-  monkeypatch.setattr(calibration, "_engines", {})
-  eng2 = calib._upload(calib.inliers)
-  JtJ2, Jtr2, cost2 = eng2.linearize(z["x1"])
-  eng2.close()
-  assert np.abs(JtJ - JtJ2).max() <= 1e-11 * np.abs(JtJ).max()
-  assert np.abs(Jtr - Jtr2).max() <= 1e-11 * np.abs(Jtr).max()
-  assert abs(cost - cost2) <= 1e-13 * cost
 
 
 def test_the_product_refuses_the_interpreter_build(simt_library, monkeypatch):
