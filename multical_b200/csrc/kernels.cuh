@@ -165,7 +165,7 @@ __device__ __forceinline__ void make_trial_item(const DeviceProblem& p, const do
       if (p.motion == MOTION_HAND_EYE) {
         double he[12];
 #pragma unroll
-        for (int j = 0; j < 12; j++) he[j] = p.off_he >= 0 ? x[p.off_he + j] : p.he_rt[j];
+        for (int j = 0; j < 12; j++) he[j] = p.off_he >= 0 ? __ldcg(&x[p.off_he + j]) : p.he_rt[j];
         PoseT t; hand_eye_frame(he, p.arm_T[q], t); p.frame_T[q] = t;
         return;
       }
@@ -174,7 +174,7 @@ __device__ __forceinline__ void make_trial_item(const DeviceProblem& p, const do
     if (!src) src = cur;
     double v[6];
 #pragma unroll
-    for (int j = 0; j < 6; j++) { v[j] = src[j]; dst[j] = v[j]; }
+    for (int j = 0; j < 6; j++) { v[j] = __ldcg(&src[j]); dst[j] = v[j]; }      // (x may have been written by another CTA of the same launch: k_lm)
     PoseT t;
     pose_from_rt(v, t);
     *tab = t;
@@ -182,20 +182,20 @@ __device__ __forceinline__ void make_trial_item(const DeviceProblem& p, const do
     const int c = i - np;
     const double* src = p.off_in >= 0 ? x + p.off_in + p.kint * c : p.intr + p.kint * c;
     for (int j = 0; j < p.kint; j++) {
-      double v = src[j];
-      if (j == 1 && p.fix_aspect && p.off_in >= 0) v = src[0];      // fy follows fx (camera.py:159-160)
+      double v = __ldcg(&src[j]);
+      if (j == 1 && p.fix_aspect && p.off_in >= 0) v = __ldcg(&src[0]);      // fy follows fx (camera.py:159-160)
       intr_o[p.kint * c + j] = v;
     }
   } else if (i < np + p.C + p.B * p.P) {
     const int q = i - np - p.C;                                       // padded board point index b*P + p
     const double* src = p.off_pt >= 0 ? x + p.off_pt + 3 * q : p.board_pts + 3 * q;
-    bpts_o[3 * q] = src[0]; bpts_o[3 * q + 1] = src[1]; bpts_o[3 * q + 2] = src[2];
+    bpts_o[3 * q] = __ldcg(&src[0]); bpts_o[3 * q + 1] = __ldcg(&src[1]); bpts_o[3 * q + 2] = __ldcg(&src[2]);
   } else if (i < np + p.C + p.B * p.P + 2 && p.motion == MOTION_HAND_EYE) {
     const int j = i - np - p.C - p.B * p.P;
     const double* src = p.off_he >= 0 ? x + p.off_he + 6 * j : p.he_rt + 6 * j;
     double v[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) { v[k] = src[k]; he_o[6 * j + k] = v[k]; }
+    for (int k = 0; k < 6; k++) { v[k] = __ldcg(&src[k]); he_o[6 * j + k] = v[k]; }
     PoseT t;
     pose_from_rt(v, t);
     p.he_T[j] = t;
@@ -242,19 +242,6 @@ __device__ __forceinline__ void corner_point(const ViewPose& vp, const ViewPose&
   }
 }
 
-// Optional tails of the linearisation kernels (opt-in MCBA_FUSE=1, single GPU), defined in solver_kernels.cuh: the last CTA to
-// finish runs the scalar step that would otherwise be a launch of its own.  __noinline__: the tails stay calls, so the code of the
-// kernels they hang off (the profiled hot loops) is not re-scheduled around them.
-struct SolverState;
-__device__ __noinline__ void view_accept_epilogue(SolverState* st, double* red, unsigned* counter, const double* view_cost, int V);
-struct ScaleEpilogue {
-  int enabled, n, first, n_cost_part, fb;
-  const double* x; const double* Hff; const double* cost_part;
-  double* sinv; double* d; double* gh; double* red;
-  SolverState* st; unsigned* counter;
-};
-__device__ __noinline__ void scale_epilogue(const ScaleEpilogue& e, int n_s, const double* Hss, const double* g);
-
 struct ViewKernelArgs {
   int loss;
   double f_scale;
@@ -262,8 +249,6 @@ struct ViewKernelArgs {
   double* view_cost;   // MODE_COST   : [V]
   double* resid;       // MODE_RESID  : [2N] canonical order
   double* err;         // MODE_ERROR  : [N]  canonical order
-  // moment kernels, MCBA_FUSE=1: the acceptance test (k_accept) as the tail of the last CTA; null = off
-  SolverState* acc_st; double* acc_red; unsigned* acc_counter;
 };
 enum { MODE_COST = 0, MODE_MOMENTS = 1, MODE_RESID = 2, MODE_ERROR = 3 };
 
@@ -272,32 +257,19 @@ constexpr double SCIPY_EPS = 2.220446049250313e-16;
 constexpr double TRIGGS_FLOOR = 0.1;
 
 // k_views: one warp per view, lanes stride over the view's corners (one thread per corner per step).
-//   MODE_COST    -> 0.5*sum rho(f)                         (trial-point evaluation, trf.py cost_new)
+//   MODE_COST    -> 0.5*sum rho(f) per view               (cost hook of mcba_residuals)
 //   MODE_RESID   -> residual vector in canonical order     (calibration.py:204-206)
 //   MODE_ERROR   -> per-corner ||proj - obs||              (tables.py:244-249)
-//   MODE_MOMENTS -> per-view sum of G^T G, G^T r, cost with G = d r / d[camera-frame twist | intrinsics]
-//                   (replaces scipy's 2-point FD Jacobian; entries [PART*CH, (PART+1)*CH) of the T moments)
-template <int MODEL, int MODE, int PART, int NPARTS, bool ROLL = false>
+// (the linearisation -- residuals + analytic Jacobian + normal equations -- is k_linearize, linearize.cuh)
+template <int MODEL, int MODE, bool ROLL = false>
 __global__ void __launch_bounds__(VIEW_WARPS * 32)
 k_views(DeviceProblem p, ViewKernelArgs a) {
-  static_assert(!(ROLL && MODE == MODE_MOMENTS), "rolling frames are linearised by k_views_mma only");
   constexpr int ND = model_nd(MODEL);
-  constexpr int D = 10 + ND;
-  constexpr int E = D * (D + 1) / 2;
-  constexpr int T = E + D + 1;
-  constexpr int CH = (T + NPARTS - 1) / NPARTS;
-  constexpr int LO = PART * CH;
-  constexpr int HI = (LO + CH < T) ? LO + CH : T;
-  constexpr int NACC = (MODE == MODE_MOMENTS) ? (HI - LO) : 1;
   constexpr int KINT = 5 + ND;
-
-  __shared__ double red[(MODE == MODE_MOMENTS) ? VIEW_WARPS * 32 * 33 : 1];
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * VIEW_WARPS + warp;
   const int nw = gridDim.x * VIEW_WARPS;
-
   for (int v = gw; v < p.V; v += nw) {
     const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
     const int beg = p.view_start[v], end = p.view_start[v + 1];
@@ -308,11 +280,7 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
 #pragma unroll
     for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
     const double* bp = p.board_pts + (size_t)b * p.P * 3;
-
-    double acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
-
+    double acc = 0.0;
     for (int idx = beg + lane; idx < end; idx += 32) {
       const double2 ob = p.obs[idx];
       const int pi = p.pid[idx];
@@ -321,9 +289,8 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
       corner_point<ROLL>(vp, vpe, X, ob.y * inv_h, Xc, Xs, Xe);
       double u, w_;
       double Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
-      project<MODEL, MODE == MODE_MOMENTS>(Xc, k, u, w_, Ju, Jv, ku, kv);
-      double ru = u - ob.x, rv = w_ - ob.y;           // projected - observed (calibration.py:206)
-
+      project<MODEL, false>(Xc, k, u, w_, Ju, Jv, ku, kv);
+      const double ru = u - ob.x, rv = w_ - ob.y;           // projected - observed (calibration.py:206)
       if constexpr (MODE == MODE_RESID) {
         const uint32_t o = p.orig[idx];
         a.resid[2 * (size_t)o] = ru;
@@ -332,98 +299,22 @@ k_views(DeviceProblem p, ViewKernelArgs a) {
         a.err[p.orig[idx]] = sqrt(ru * ru + rv * rv);
       } else {
         // robust loss per scalar residual (least_squares.py construct_loss_function, common.py:720-731)
-        double cost, wu = 1.0, wv = 1.0;
-        if (a.loss == 0) {
-          cost = 0.5 * (ru * ru + rv * rv);
-        } else {
+        if (a.loss == 0) acc += 0.5 * (ru * ru + rv * rv);
+        else {
           const double is = 1.0 / a.f_scale, fs2 = a.f_scale * a.f_scale;
           double zu = ru * is, zv = rv * is;
           zu *= zu; zv *= zv;
           double r0u, r1u, r2u, r0v, r1v, r2v;
           loss_rho(a.loss, zu, r0u, r1u, r2u);
           loss_rho(a.loss, zv, r0v, r1v, r2v);
-          cost = 0.5 * fs2 * (r0u + r0v);
-          if constexpr (MODE == MODE_MOMENTS) {
-            // rho[2] /= f_scale^2 ; J_scale = rho1 + 2 rho2 f^2 = rho1 + 2 rho2' z
-            // scipy floors the Triggs-corrected row scale at machine epsilon (common.py:727), which removes all
-            // curvature of residuals beyond the loss's inflection point and stalls an exact inner solve when most
-            // rows are there (poor initial guess).  We floor it at TRIGGS_FLOOR*rho' instead (a damped IRLS
-            // weight): the gradient J'^T f' = rho' J^T f, hence the minimiser, is the same for any positive floor.
-            double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
-            ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
-            jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
-            wu = sqrt(ju); wv = sqrt(jv);
-            ru *= r1u / wu; rv *= r1v / wv;
-          }
-        }
-        if constexpr (MODE == MODE_COST) {
-          acc[0] += cost;
-        } else {
-          // local Jacobian rows: [omega(3) v(3) fx fy cx cy dist(ND)]
-          double gu[D], gv[D];
-          gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
-          gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
-#pragma unroll
-          for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
-          gu[6] = ku[0] * wu; gu[7] = 0.0; gu[8] = wu; gu[9] = 0.0;
-          gv[6] = 0.0; gv[7] = kv[1] * wv; gv[8] = 0.0; gv[9] = wv;
-#pragma unroll
-          for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
-          // structural zeros: fx(6),cx(8) only in the u row; fy(7),cy(9) only in the v row
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-#pragma unroll
-            for (int j = i; j < D; j++) {
-              const int e = tri_index(D, i, j);
-              if (e >= LO && e < HI) {
-                const bool iu = !(i == 7 || i == 9), iv = !(i == 6 || i == 8);
-                const bool ju_ = !(j == 7 || j == 9), jv_ = !(j == 6 || j == 8);
-                double s = acc[e - LO];
-                if (iu && ju_) s = fma(gu[i], gu[j], s);
-                if (iv && jv_) s = fma(gv[i], gv[j], s);
-                acc[e - LO] = s;
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            const int e = E + i;
-            if (e >= LO && e < HI) {
-              double s = acc[e - LO];
-              if (!(i == 7 || i == 9)) s = fma(gu[i], ru, s);
-              if (!(i == 6 || i == 8)) s = fma(gv[i], rv, s);
-              acc[e - LO] = s;
-            }
-          }
-          if (T - 1 >= LO && T - 1 < HI) acc[T - 1 - LO] += cost;
+          acc += 0.5 * fs2 * (r0u + r0v);
         }
       }
     }
-
     if constexpr (MODE == MODE_COST) {
-      double s = acc[0];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) a.view_cost[v] = s;
-    } else if constexpr (MODE == MODE_MOMENTS) {
-      // transposed warp reduction through shared memory, 32 accumulators per round:
-      // lane l writes its value of accumulator q to [q*33 + l]; then lane q sums row q.
-      double* sm = red + warp * 32 * 33;
-      double* out = a.moments + (size_t)v * T + LO;
-#pragma unroll
-      for (int r0 = 0; r0 < NACC; r0 += 32) {
-#pragma unroll
-        for (int q = 0; q < 32; q++)
-          if (r0 + q < NACC) sm[q * 33 + lane] = acc[r0 + q];
-        __syncwarp();
-        if (r0 + lane < NACC) {
-          double s = 0.0;
-#pragma unroll 8
-          for (int j = 0; j < 32; j++) s += sm[lane * 33 + j];
-          out[r0 + lane] = s;
-        }
-        __syncwarp();
-      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) a.view_cost[v] = acc;
     }
   }
 }
@@ -600,131 +491,6 @@ k_views_mma(DeviceProblem p, ViewKernelArgs a) {
     }
     if (lane == 0) { out[T - 1] = cost_acc; if (a.view_cost) a.view_cost[v] = cost_acc; }     // compact copy for the acceptance test
   }
-  if (a.acc_st) view_accept_epilogue(a.acc_st, a.acc_red, a.acc_counter, a.view_cost, p.V);
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_views_f32 (opt-in MCBA_MOMENTS=f32, 5-coefficient and fisheye models, static / hand-eye frames): the same per-view records
-// with the Gauss-Newton Hessian moments sum G^T G accumulated in FP32 and everything that defines the minimiser -- residual,
-// cost, gradient moments sum G^T r -- in FP64.  k_views_mma is bound by the fp64 pipe that DFMA and DMMA share (DESIGN.md §6:
-// ~384 DMMA-lane FMAs + ~160 DFMA per corner); here the 2 x D(D+1)/2 Hessian FMAs per corner go to the fp32 pipe, which runs
-// beside it, and the fp64 pipe keeps the Jacobian and 2 x (D+1) gradient FMAs.  An inexact Hessian changes the path of the
-// trust-region iteration, not its fixed point (J^T r = 0 is evaluated exactly); measured on the oracle with Jacobians rounded to
-// 24 bits before forming J^T J: same minimum, same number of evaluations within +-1.  One warp per view, one
-// corner per lane and step, per-lane accumulators, transposed shared-memory reduction at the end of the view.
-template <int MODEL>
-__global__ void __launch_bounds__(VIEW_WARPS * 32)
-k_views_f32(DeviceProblem p, ViewKernelArgs a) {
-  constexpr int ND = model_nd(MODEL);
-  constexpr int D = 10 + ND;
-  constexpr int E = D * (D + 1) / 2;
-  constexpr int T = E + D + 1;
-  constexpr int KINT = 5 + ND;
-  static_assert(E <= 136, "per-lane fp32 accumulators: 5-coefficient and fisheye models only");
-  __shared__ float redf[VIEW_WARPS][32 * 33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * VIEW_WARPS + warp, nw = gridDim.x * VIEW_WARPS;
-  for (int v = gw; v < p.V; v += nw) {
-    const int c = p.view_cam[v], f = p.view_frame[v], b = p.view_board[v];
-    const int beg = p.view_start[v], end = p.view_start[v + 1];
-    ViewPose vp;
-    compose_view(p.cam_T[c], p.frame_T[f], p.board_T[b], vp);
-    double k[KINT];
-#pragma unroll
-    for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
-    const double* bp = p.board_pts + (size_t)b * p.P * 3;
-    float hacc[E];
-    double gacc[D + 1];
-#pragma unroll
-    for (int i = 0; i < E; i++) hacc[i] = 0.0f;
-#pragma unroll
-    for (int i = 0; i <= D; i++) gacc[i] = 0.0;
-    for (int idx = beg + lane; idx < end; idx += 32) {
-      const double2 ob = p.obs[idx];
-      const int pi = p.pid[idx];
-      const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
-      double Xc[3];
-      mat3_vec(vp.R, X, Xc);
-      Xc[0] += vp.t[0]; Xc[1] += vp.t[1]; Xc[2] += vp.t[2];
-      double u, w_, Ju[3], Jv[3], ku[4 + ND], kv[4 + ND];
-      project<MODEL, true>(Xc, k, u, w_, Ju, Jv, ku, kv);
-      double ru = u - ob.x, rv = w_ - ob.y, wu = 1.0, wv = 1.0;
-      if (a.loss == 0) {
-        gacc[D] += 0.5 * (ru * ru + rv * rv);
-      } else {
-        const double is = 1.0 / a.f_scale, fs2 = a.f_scale * a.f_scale;
-        double zu = ru * is, zv = rv * is;
-        zu *= zu; zv *= zv;
-        double r0u, r1u, r2u, r0v, r1v, r2v;
-        loss_rho(a.loss, zu, r0u, r1u, r2u);
-        loss_rho(a.loss, zv, r0v, r1v, r2v);
-        gacc[D] += 0.5 * fs2 * (r0u + r0v);
-        double ju = r1u + 2.0 * r2u * zu, jv = r1v + 2.0 * r2v * zv;
-        ju = fmax(fmax(ju, TRIGGS_FLOOR * r1u), SCIPY_EPS);
-        jv = fmax(fmax(jv, TRIGGS_FLOOR * r1v), SCIPY_EPS);
-        wu = sqrt(ju); wv = sqrt(jv);
-        ru *= r1u / wu; rv *= r1v / wv;
-      }
-      double gu[D], gv[D];
-      gu[0] = (Xc[1] * Ju[2] - Xc[2] * Ju[1]) * wu; gu[1] = (Xc[2] * Ju[0] - Xc[0] * Ju[2]) * wu; gu[2] = (Xc[0] * Ju[1] - Xc[1] * Ju[0]) * wu;
-      gv[0] = (Xc[1] * Jv[2] - Xc[2] * Jv[1]) * wv; gv[1] = (Xc[2] * Jv[0] - Xc[0] * Jv[2]) * wv; gv[2] = (Xc[0] * Jv[1] - Xc[1] * Jv[0]) * wv;
-#pragma unroll
-      for (int i = 0; i < 3; i++) { gu[3 + i] = Ju[i] * wu; gv[3 + i] = Jv[i] * wv; }
-      gu[6] = ku[0] * wu; gu[7] = 0.0; gu[8] = wu; gu[9] = 0.0;
-      gv[6] = 0.0; gv[7] = kv[1] * wv; gv[8] = 0.0; gv[9] = wv;
-#pragma unroll
-      for (int i = 0; i < ND; i++) { gu[10 + i] = ku[4 + i] * wu; gv[10 + i] = kv[4 + i] * wv; }
-      float fu[D], fv[D];
-#pragma unroll
-      for (int i = 0; i < D; i++) {
-        fu[i] = (float)gu[i]; fv[i] = (float)gv[i];
-        // gradient moments in fp64 (structural zeros: fx, cx only in the u row; fy, cy only in the v row)
-        double s = gacc[i];
-        if (!(i == 7 || i == 9)) s = fma(gu[i], ru, s);
-        if (!(i == 6 || i == 8)) s = fma(gv[i], rv, s);
-        gacc[i] = s;
-      }
-#pragma unroll
-      for (int i = 0; i < D; i++) {
-#pragma unroll
-        for (int j = i; j < D; j++) {
-          const bool iu = !(i == 7 || i == 9), iv = !(i == 6 || i == 8);
-          const bool ju_ = !(j == 7 || j == 9), jv_ = !(j == 6 || j == 8);
-          float s = hacc[tri_index(D, i, j)];
-          if (iu && ju_) s = fmaf(fu[i], fu[j], s);
-          if (iv && jv_) s = fmaf(fv[i], fv[j], s);
-          hacc[tri_index(D, i, j)] = s;
-        }
-      }
-    }
-    // ---- reduce over the lanes: Hessian moments through shared memory (transposed, 32 accumulators per round), the D + 1
-    // fp64 sums by shuffles
-    double* out = a.moments + (size_t)v * T;
-    float* sm = redf[warp];
-#pragma unroll
-    for (int r0 = 0; r0 < E; r0 += 32) {
-#pragma unroll
-      for (int q = 0; q < 32; q++)
-        if (r0 + q < E) sm[q * 33 + lane] = hacc[r0 + q];
-      __syncwarp();
-      if (r0 + lane < E) {
-        float s = 0.0f;
-#pragma unroll 8
-        for (int j = 0; j < 32; j++) s += sm[lane * 33 + j];
-        out[r0 + lane] = (double)s;
-      }
-      __syncwarp();
-    }
-#pragma unroll
-    for (int i = 0; i <= D; i++) {
-      double s = gacc[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) out[E + i] = s;
-    }
-    if (lane == 0 && a.view_cost) a.view_cost[v] = out[T - 1];
-  }
-  if (a.acc_st) view_accept_epilogue(a.acc_st, a.acc_red, a.acc_counter, a.view_cost, p.V);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -736,7 +502,7 @@ struct SolverBuffers {
   double* Hff;       // [F][36]
   double* W;         // [F][n_s][6]   H[shared, frame f]
   double* cost_part; // per-CTA partial costs of k_expand_shared
-  int zero_shared;   // MCBA_FUSE=1: k_expand_frames also clears H_ss and the shared part of g (instead of two memsets in front of it)
+  int zero_shared;   // unused
 };
 
 __device__ __forceinline__ int intr_param_index(const DeviceProblem& p, int local /*0..3+nd*/) {
@@ -1006,161 +772,6 @@ k_point_blocks(DeviceProblem p, ViewKernelArgs a, double* Hss, double* W, double
   }
 }
 
-// k_expand_frames: one CTA per frame -> H_ff (FB x FB), g_f (FB) and W_f (n_s x FB), FB = 6 NP.  Warp w owns the cameras
-// c == w (mod EXP_WARPS): the camera-pose and intrinsics rows of W_f are written by exactly one warp (registers, flushed when
-// the camera changes); board-pose rows, H_ff and g_f are per-warp partials summed at the end.
-template <int NP, bool PAR = false>
-__global__ void __launch_bounds__(EXP_THREADS)
-k_expand_frames(DeviceProblem p, SolverBuffers s) {
-  constexpr int FB = 6 * NP, KO = 6 * NP;
-  constexpr int NHF = FB * FB + FB;                  // H_ff | g_f outputs
-  extern __shared__ double sh[];
-  const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
-  const int E = D * (D + 1) / 2;
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wd = expf_warp_doubles(T, D, B, NP);
-  double* Ms = sh + (size_t)warp * wd;
-  double* Tm = Ms + T;                               // [D][FB]: column block j = M[:, xi_j] Af_j
-  double* Ac = Tm + D * FB;
-  double* Af = Ac + 36;
-  double* Ab = Af + 36 * NP;
-  double* Wb = Ab + 36 * NP;                         // [B][6][FB] partial board rows of this warp
-  double* red = sh + (size_t)EXP_WARPS * wd;        // [EXP_WARPS][NHF]  H_ff | g_f partials
-  double* Wf = s.W + (size_t)f * n_s * FB;
-  for (int i = tid; i < n_s * FB; i += EXP_THREADS) Wf[i] = 0.0;
-  for (int i = lane; i < B * 6 * FB; i += 32) Wb[i] = 0.0;
-  if (s.zero_shared) {             // k_expand_shared, which accumulates into these, starts after this kernel has finished
-    for (size_t i = (size_t)blockIdx.x * EXP_THREADS + tid; i < (size_t)n_s * n_s; i += (size_t)gridDim.x * EXP_THREADS) s.Hss[i] = 0.0;
-    for (int i = blockIdx.x * EXP_THREADS + tid; i < n_s; i += gridDim.x * EXP_THREADS) s.g[i] = 0.0;
-  }
-  __syncthreads();                                   // W_f zeroed before any warp adds its camera rows
-
-  const int nin = 4 + p.nd;
-  const int ncam_out = (6 + nin) * FB;               // camera pose (6 x FB) + intrinsics (nin x FB) rows of W_f
-  constexpr int MAXOUT = ((6 + 16) * FB + 31) / 32;
-  constexpr int NH = (NHF + 31) / 32;
-  double hacc[NH];                                   // lane-owned H_ff | g_f outputs: o = lane + 32 q
-  double wacc[MAXOUT];
-#pragma unroll
-  for (int i = 0; i < NH; i++) hacc[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < MAXOUT; i++) wacc[i] = 0.0;
-  int cur_cam = -1;
-
-  auto flush_camera = [&](int c) {
-    if (c < 0) return;
-#pragma unroll
-    for (int q = 0; q < MAXOUT; q++) {
-      const int o = lane + 32 * q;
-      if (o < ncam_out) {
-        const double val = wacc[q];
-        if (o < 6 * FB) { if (p.off_cp >= 0) Wf[(p.off_cp + 6 * c + o / FB) * FB + o % FB] = val; }
-        else if (p.off_in >= 0) {
-          const int i = (o - 6 * FB) / FB, j = (o - 6 * FB) % FB;
-          if (!(p.fix_aspect && i == 1)) Wf[(p.off_in + p.kint * c + intr_param_index(p, i)) * FB + j] = val;
-        }
-      }
-      wacc[q] = 0.0;
-    }
-  };
-
-  const int v0 = p.frame_view_start[f], v1 = p.frame_view_start[f + 1];
-  // PAR: the next record of this warp is fetched into registers while the current one is worked on (the load latency of a 1 KB record
-  // from L2 / HBM is otherwise paid once per view, serially)
-  constexpr int MR = NP == 1 ? 11 : 16;                // ceil(T / 32), T <= 325 (tilted) / 496 (rolling tilted)
-  double pre[PAR ? MR : 1];
-  auto next_view = [&](int from) { int v = from; while (v < v1 && p.view_cam[v] % EXP_WARPS != warp) v++; return v; };
-  auto fetch = [&](int v) {
-#pragma unroll
-    for (int q = 0; q < (PAR ? MR : 1); q++) { const int i = lane + 32 * q; if (i < T) pre[q] = s.moments[(size_t)v * T + i]; }
-  };
-  if constexpr (PAR) { const int vf = next_view(v0); if (vf < v1) fetch(vf); }
-  for (int v = v0; v < v1; v++) {
-    const int c = p.view_cam[v];
-    if (c % EXP_WARPS != warp) continue;
-    const int b = p.view_board[v];
-    if (c != cur_cam) { flush_camera(cur_cam); cur_cam = c; }
-    if constexpr (PAR) {
-#pragma unroll
-      for (int q = 0; q < MR; q++) { const int i = lane + 32 * q; if (i < T) Ms[i] = pre[q]; }
-      const int vn = next_view(v + 1);
-      if (vn < v1) fetch(vn);
-    } else
-    for (int i = lane; i < T; i += 32) Ms[i] = s.moments[(size_t)v * T + i];
-    if constexpr (PAR) { __shared__ double scr[EXP_WARPS][33 * NP]; view_twist_maps_par<NP>(p, c, f, b, lane, Ac, Af, Ab, scr[warp]); }
-    else view_twist_maps<NP>(p, c, f, b, lane, Ac, Af, Ab);
-    __syncwarp();
-    for (int o = lane; o < D * FB; o += 32) {         // Tm[:, 6j+k] = M[:, xi_j] Af_j
-      const int i = o / FB, col = o % FB, j = col / 6, k = col % 6; double acc = 0.0;
-#pragma unroll
-      for (int kk = 0; kk < 6; kk++) acc += msym(Ms, D, i, 6 * j + kk) * Af[36 * j + kk * 6 + k];
-      Tm[o] = acc;
-    }
-    __syncwarp();
-    // H_ff[6a+i, col] += Af_a^T Tm[xi_a rows, col] ; g_f[6a+i] += Af_a^T g_xi_a
-#pragma unroll
-    for (int q = 0; q < NH; q++) {
-      const int o = lane + 32 * q;
-      if (o < FB * FB) {
-        const int r = o / FB, col = o % FB, a = r / 6, i = r % 6; double acc = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Af[36 * a + kk * 6 + i] * Tm[(6 * a + kk) * FB + col];
-        hacc[q] += acc;
-      } else if (o < NHF) {
-        const int r = o - FB * FB, a = r / 6, i = r % 6; double acc = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 6; kk++) acc += Af[36 * a + kk * 6 + i] * Ms[E + 6 * a + kk];
-        hacc[q] += acc;
-      }
-    }
-    // camera rows: sum_a Ac^T Tm[xi_a rows] (6 x FB) | Tm_k (nin x FB, fix_aspect folds fy onto fx)
-#pragma unroll
-    for (int q = 0; q < MAXOUT; q++) {
-      const int o = lane + 32 * q;
-      if (o < 6 * FB) {
-        const int i = o / FB, col = o % FB; double acc = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < KO; kk++) acc += Ac[(kk % 6) * 6 + i] * Tm[kk * FB + col];
-        wacc[q] += acc;
-      } else if (o < ncam_out) {
-        const int i = (o - 6 * FB) / FB, col = (o - 6 * FB) % FB;
-        double val = Tm[(KO + i) * FB + col];
-        if (p.fix_aspect && i == 0) val += Tm[(KO + 1) * FB + col];
-        wacc[q] += val;
-      }
-    }
-    // board rows (shared between cameras): per-warp partial
-    if (p.off_bp >= 0) {
-      for (int o = lane; o < 6 * FB; o += 32) {
-        const int i = o / FB, col = o % FB; double acc = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < KO; kk++) acc += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Tm[kk * FB + col];
-        Wb[b * 6 * FB + o] += acc;
-      }
-    }
-    __syncwarp();
-  }
-  flush_camera(cur_cam);
-  // ---- meet: sum the per-warp partials
-#pragma unroll
-  for (int q = 0; q < NH; q++) { const int o = lane + 32 * q; if (o < NHF) red[warp * NHF + o] = hacc[q]; }
-  __syncthreads();
-  for (int o = tid; o < NHF; o += EXP_THREADS) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < EXP_WARPS; w++) acc += red[w * NHF + o];
-    if (o < FB * FB) s.Hff[(size_t)f * FB * FB + o] = acc; else s.g[n_s + FB * f + o - FB * FB] = acc;
-  }
-  if (p.off_bp >= 0)
-    for (int o = tid; o < B * 6 * FB; o += EXP_THREADS) {
-      double acc = 0.0;
-#pragma unroll
-      for (int w = 0; w < EXP_WARPS; w++) acc += sh[(size_t)w * wd + T + D * FB + 36 + 72 * NP + o];
-      const int b = o / (6 * FB), i = (o % (6 * FB)) / FB, j = o % FB;
-      Wf[(p.off_bp + 6 * b + i) * FB + j] = acc;
-    }
-}
-
 // per-warp shared slice of k_expand_shared: Ms[T] | Um[D*6] | Ab[NP*36] | Ub[B*D*6] | Hbb[B*36] | gb[B*6]
 __host__ __device__ inline int exps_warp_doubles(int T, int D, int B, int NP) { return T + D * 6 + 36 * NP + B * (D * 6 + 42); }
 
@@ -1168,9 +779,9 @@ __host__ __device__ inline int exps_warp_doubles(int T, int D, int B, int NP) { 
 // plain sum of moment records (its twist map does not depend on the view) kept lane-distributed in registers; the
 // camera-board and board-board blocks need the per-view board twist map(s).  Per-warp partials are summed once at the
 // end and added into H_ss / g_s with fp64 atomics.
-template <int NP, bool PAR = false>
+template <int NP>
 __global__ void __launch_bounds__(EXP_THREADS)
-k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) {
+k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks) {
   constexpr int KO = 6 * NP;
   extern __shared__ double sh[];
   const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
@@ -1197,30 +808,16 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) 
   const int per = (l1 - l0 + chunks - 1) / chunks;
   const int a0 = l0 + chunk * per, a1 = min(l1, a0 + per);
   const PoseT& pc = p.cam_T[c];
-  double pre[PAR ? MAXT : 1];
-  auto fetch = [&](int li) {
-    const int v = p.cam_view_list[li];
-#pragma unroll
-    for (int q = 0; q < (PAR ? MAXT : 1); q++) { const int i = lane + 32 * q; if (i < T) pre[q] = s.moments[(size_t)v * T + i]; }
-  };
-  if constexpr (PAR) { if (a0 + warp < a1) fetch(a0 + warp); }
   for (int li = a0 + warp; li < a1; li += EXP_WARPS) {
     const int v = p.cam_view_list[li];
     const int f = p.view_frame[v], b = p.view_board[v];
-    if constexpr (PAR) {
-#pragma unroll
-      for (int q = 0; q < MAXT; q++) { const int i = lane + 32 * q; if (i < T) { const double m = pre[q]; Ms[i] = m; macc[q] += m; } }
-      if (li + EXP_WARPS < a1) fetch(li + EXP_WARPS);            // the next record of this warp, in flight during the work below
-    } else {
 #pragma unroll
     for (int q = 0; q < MAXT; q++) {
       const int i = lane + 32 * q;
       if (i < T) { const double m = s.moments[(size_t)v * T + i]; Ms[i] = m; macc[q] += m; }
     }
-    }
     if (p.off_bp >= 0) {
-      if constexpr (PAR) { __shared__ double scr[EXP_WARPS][33 * NP]; view_twist_maps_par<NP>(p, c, f, b, lane, nullptr, nullptr, Ab, scr[warp]); }
-      else view_twist_maps<NP>(p, c, f, b, lane, nullptr, nullptr, Ab);
+      view_twist_maps<NP>(p, c, f, b, lane, nullptr, nullptr, Ab);
       __syncwarp();
       for (int o = lane; o < D * 6; o += 32) {           // Um = sum_a M[:, xi_a] Ab_a
         const int i = o / 6, j = o % 6; double acc = 0.0;
@@ -1331,7 +928,6 @@ k_expand_shared(DeviceProblem p, SolverBuffers s, int chunks, ScaleEpilogue ep) 
       if (tid < 6 && gb[b * 6 + tid] != 0.0) atomicAdd(&s.g[bp + tid], gb[b * 6 + tid]);
     }
   }
-  if (ep.enabled) scale_epilogue(ep, n_s, s.Hss, s.g);
 }
 
 // ------------------------------------------------------------------------------------------------

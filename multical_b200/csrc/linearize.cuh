@@ -134,14 +134,15 @@ struct LinArgs {
 __host__ __device__ inline int lin_record_doubles(int T, int D, int B) { return T + B * (D * 6 + 42); }
 // dynamic shared memory of k_linearize in doubles
 __host__ __device__ inline size_t lin_warp_doubles(int NC, int T, int D, int FB, int nin, int B, int NP) {
-  return (size_t)NC * MMA_KPAD            // stage (chunk loop) = Ms | Tf | Tb (epilogue)
-       + 36 + 72 * NP + 33 * NP           // Ac | Af | Ab | map scratch
+  (void)NP;
+  return ((size_t)NC * MMA_KPAD           // stage (chunk loop) = Ms | Tf | Tb | Ac | Af | Ab | map scratch (epilogue)
        + (size_t)B * 6 * FB               // Wb: this warp's partial board rows of W_f
        + FB * FB + FB                     // hacc: H_ff | g_f partial
        + (6 + nin) * FB                   // wacc: camera-pose and intrinsics rows of W_f (current camera)
        + T                                // macc: raw moment sum of the current camera
        + (D * 6 + 42)                     // ub: board coupling of the current (camera, board)
-       + 2;                               // cost of this frame's views | pad
+       + 2                                // cost of this frame's views | pad
+       + 1) & ~(size_t)1;                 // even: every warp's stage buffer takes 16-byte stores
 }
 __host__ __device__ inline size_t lin_smem_doubles(int NC, int T, int D, int FB, int nin, int B, int NP, int npair, int split) {
   (void)npair; (void)split;      // split > 1: a warp's fragments meet in its own stage buffer, (2 npair + 1) x 32 <= NC x MMA_KPAD doubles
@@ -167,11 +168,12 @@ k_linearize(DeviceProblem p, LinArgs a) {
   double* Ms = stage;                         // [NC][NC] full symmetric, column D = G^T r (epilogue view of the stage buffer)
   double* Tf = Ms + NC * NC;                  // [D][FB]   M[:, xi_a] Af_a
   double* Tb = Tf + D * FB;                   // [D][6]    sum_a M[:, xi_a] Ab_a
-  double* Ac = stage + (size_t)NC * MMA_KPAD;
+  double* Ac = Tb + D * 6;                    // twist maps of the view, also inside the stage buffer
   double* Af = Ac + 36;
   double* Ab = Af + 36 * NP;
   double* scr = Ab + 36 * NP;
-  double* Wb = scr + 33 * NP;                 // [B][6][FB]
+  static_assert(NC * NC + D * FB + D * 6 + 36 + 72 * NP + 33 * NP <= NC * MMA_KPAD, "the epilogue's scratch must fit the stage buffer");
+  double* Wb = stage + (size_t)NC * MMA_KPAD; // [B][6][FB]
   double* hacc = Wb + (size_t)B * 6 * FB;     // [NHF]
   double* wacc = hacc + NHF;                  // [NWC]
   double* macc = wacc + NWC;                  // [T]
@@ -418,18 +420,24 @@ k_linearize(DeviceProblem p, LinArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_reduce_shared: one CTA per camera.  Sums the camera's per-CTA records in CTA order, applies the camera's own twist map (it does
-// not depend on the view) and STORES the camera's blocks of H_ss / g_s: (pose | intrinsics) x (pose | intrinsics), x every board pose.
-// Board x board blocks and board gradients are sums over the cameras: per-camera partials, summed in camera order by the last CTA.
-// No atomics anywhere: two runs give bit-identical normal equations.
-constexpr int RED_THREADS = 128;
+// k_reduce_shared: the per-CTA records of k_linearize -> H_ss, g_s, cost.  No atomics on data: two runs give bit-identical results.
+//   step 1  grid = cameras x slices of 32 record entries; 256 threads = 32 entries x 8 groups: group g adds records g, g+8, ... in
+//           order, the 8 group sums are added in order -> the camera's summed record (global scratch `sred`)
+//   step 2  the LAST slice CTA of a camera (arrival counter) applies the camera's own twist map (it does not depend on the view) and
+//           STORES the camera's blocks of H_ss / g_s: (pose | intrinsics) x (pose | intrinsics), and x every board pose
+//   step 3  board x board blocks and board gradients are sums over the cameras: the last camera to finish step 2 adds the per-camera
+//           partials in camera order, and the per-frame costs in frame order
+constexpr int RED_THREADS = 256;
+constexpr int RED_ENT = 32, RED_GROUPS = RED_THREADS / RED_ENT;
 struct ReduceArgs {
   const double* spart; int nparts;            // [nparts][C][rec]
+  double* sred;                               // [C][rec]
   double* Hss; double* g;
   double* bpart;                              // [C][B][42]
   const double* frame_cost; int F; double* cost_out;
-  unsigned* counter;
+  unsigned* cam_counter;                      // [C + 1]: slices done per camera | cameras done
 };
+__host__ __device__ inline int reduce_slices(int rec) { return (rec + RED_ENT - 1) / RED_ENT; }
 __host__ __device__ inline size_t reduce_smem_doubles(int T, int D, int B) { return (size_t)lin_record_doubles(T, D, B) + D * 6 + 36; }
 
 template <int NP>
@@ -438,21 +446,50 @@ k_reduce_shared(DeviceProblem p, ReduceArgs a) {
   constexpr int KO = 6 * NP;
   extern __shared__ double rsm[];
   __shared__ double sm[32];
+  __shared__ double gsum[RED_GROUPS][RED_ENT];
   __shared__ int is_last;
   const int D = p.D, T = p.T, B = p.B, n_s = p.n_s;
   const int E = D * (D + 1) / 2;
   const int UB = D * 6 + 42;
   const int rec = lin_record_doubles(T, D, B);
-  const int c = blockIdx.x, tid = threadIdx.x;
+  const int nsl = reduce_slices(rec);
+  const int c = blockIdx.x / nsl, slice = blockIdx.x % nsl, tid = threadIdx.x;
+  // ---- step 1
+  {
+    const int e = slice * RED_ENT + (tid % RED_ENT), grp = tid / RED_ENT;
+    double s = 0.0;
+    if (e < rec) {
+      const double* src = a.spart + (size_t)c * rec + e;
+      const size_t stride = (size_t)p.C * rec;
+      int q = grp;
+      for (; q + 3 * RED_GROUPS < a.nparts; q += 4 * RED_GROUPS) {       // four loads in flight, added in record order
+        const double v0 = src[(size_t)q * stride], v1 = src[(size_t)(q + RED_GROUPS) * stride];
+        const double v2 = src[(size_t)(q + 2 * RED_GROUPS) * stride], v3 = src[(size_t)(q + 3 * RED_GROUPS) * stride];
+        s = (((s + v0) + v1) + v2) + v3;
+      }
+      for (; q < a.nparts; q += RED_GROUPS) s += src[(size_t)q * stride];
+    }
+    gsum[grp][tid % RED_ENT] = s;
+    __syncthreads();
+    if (tid < RED_ENT && slice * RED_ENT + tid < rec) {
+      double t = 0.0;
+#pragma unroll
+      for (int gq = 0; gq < RED_GROUPS; gq++) t += gsum[gq][tid];
+      a.sred[(size_t)c * rec + slice * RED_ENT + tid] = t;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) { const unsigned t = atomicAdd(a.cam_counter + c, 1u); is_last = (t == (unsigned)nsl - 1); }
+  __syncthreads();
+  if (!is_last) return;
+  if (tid == 0) a.cam_counter[c] = 0;
+  __threadfence();
+  // ---- step 2: this camera's blocks
   double* Msum = rsm;                         // [T] then per board [UB]
   double* Um = rsm + rec;                     // [D][6]
   double* Ac = Um + D * 6;                    // 36
-  for (int i = tid; i < rec; i += RED_THREADS) {
-    double s = 0.0;
-    const double* src = a.spart + (size_t)c * rec + i;
-    for (int q = 0; q < a.nparts; q++) s += src[(size_t)q * p.C * rec];
-    Msum[i] = s;
-  }
+  for (int i = tid; i < rec; i += RED_THREADS) Msum[i] = __ldcg(&a.sred[(size_t)c * rec + i]);
   if (tid == 0) { const PoseT& pc = p.cam_T[c]; const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; twist_map(I3, pc.JL, pc.t, Ac); }
   __syncthreads();
   for (int o = tid; o < D * 6; o += RED_THREADS) {       // Um = sum_a Msum[:, xi_a] Ac  (the camera's map is the same for every chain)
@@ -464,7 +501,6 @@ k_reduce_shared(DeviceProblem p, ReduceArgs a) {
   const int nin = 4 + p.nd;
   const int cp = p.off_cp >= 0 ? p.off_cp + 6 * c : -1;
   const int in0 = p.off_in >= 0 ? p.off_in + p.kint * c : -1;
-  // fix_aspect folds fy onto fx: both local rows land on the same parameter -> accumulate those entries instead of storing
   auto put = [&](int i, int j, double val) { a.Hss[(size_t)i * n_s + j] = val; a.Hss[(size_t)j * n_s + i] = val; };
   if (cp >= 0) {
     for (int o = tid; o < 36; o += RED_THREADS) {
@@ -481,7 +517,7 @@ k_reduce_shared(DeviceProblem p, ReduceArgs a) {
     }
   }
   if (in0 >= 0) {
-    // one thread per TARGET parameter pair so that folded rows (fix_aspect) are summed in a fixed order
+    // one thread per TARGET parameter pair: rows folded onto one parameter (fix_aspect: fy onto fx, camera.py:159-160) are added in a fixed order
     const int kint = p.kint;
     if (cp >= 0)
       for (int o = tid; o < kint * 6; o += RED_THREADS) {
@@ -523,13 +559,13 @@ k_reduce_shared(DeviceProblem p, ReduceArgs a) {
       for (int o = tid; o < 42; o += RED_THREADS) a.bpart[((size_t)c * B + b) * 42 + o] = U[D * 6 + o];
     }
   }
-  // ---- last CTA: board x board blocks, board gradients (camera order) and the cost (frame order)
+  // ---- step 3 (last camera): board x board blocks, board gradients (camera order) and the cost (frame order)
   __threadfence();
   __syncthreads();
-  if (tid == 0) { const unsigned t = atomicAdd(a.counter, 1u); is_last = (t == gridDim.x - 1); }
+  if (tid == 0) { const unsigned t = atomicAdd(a.cam_counter + p.C, 1u); is_last = (t == (unsigned)p.C - 1); }
   __syncthreads();
   if (!is_last) return;
-  if (tid == 0) *a.counter = 0;
+  if (tid == 0) a.cam_counter[p.C] = 0;
   __threadfence();
   if (p.off_bp >= 0)
     for (int o = tid; o < B * 42; o += RED_THREADS) {

@@ -1,0 +1,985 @@
+// lm_kernel.cuh — the trust-region iteration as ONE persistent cooperative kernel per trial step.
+//
+// Round 1 ran the solver phase of an LM iteration as ~12 launches (k_scale, k_quad, k_schur_frames, k_schur_syrk, k_chol_small,
+// k_backsub, k_dots, k_quad, k_step, k_make_trial, k_accept ...) of 5-50 us each, every one a chain of a few dependent L2 round trips,
+// plus one host synchronisation per trial.  k_lm does all of it in one launch: the grid (<= one CTA per SM, all co-resident) walks the
+// phases below separated by grid barriers (an arrive counter and a generation word in L2, ~1 us), the scalar trust-region logic of
+// scipy's trf_no_bounds runs REPLICATED in every CTA on a shared-memory copy of the state (identical inputs, identical arithmetic:
+// no broadcast needed), and the accept / reject decision, the iteration log and the loop condition stay on the device.  The host
+// enqueues  [k_linearize -> k_reduce_shared -> k_lm]  as the body of a CUDA-graph WHILE node and reads the result once per SOLVE.
+//
+//   phase A  accept / reject the pending trial (cost from the per-frame costs of the fused linearisation at the trial point)
+//   phase B  Jacobian scaling (x_scale='jac'), g_h, ||g||_inf                        -> barrier -> begin-of-iteration (termination tests, log row)
+//   phase C  g_h^T A g_h on the block structure                                     -> barrier -> damping `reg` (1-D Cauchy model)
+//   phase D  per frame: L L^T = D H_ff D + reg I, Y_f, z_f ; S = D H_ss D           -> barrier
+//   phase E  S -= sum_f Y_f Y_f^T, rhs -= sum_f Y_f z_f: tile x frame-chunk partials -> barrier -> fixed-order sum over the chunks -> barrier
+//   phase F  reduced solve (S + reg I) gn_s = rhs + g_h,s                            -> barrier
+//   phase G  per frame: back-substitution gn_f, then the quadratic forms / dots of the 2-D subspace {g_h, gn}    -> barrier -> 2x2 model
+//   phase I  trust-region step in the subspace, x_new                                -> barrier -> trial parameter state + pose tables
+// Several GPUs (frames sharded): the four exchanges of an iteration (trial cost + next gradient/diagonal | g_h^T A g_h | S, rhs |
+// subspace sums) run INSIDE the kernel over NVLink peer memory (exchange() below), in rank order -> identical values on every rank.
+#pragma once
+#include "solver_kernels.cuh"
+
+namespace mcba {
+
+constexpr int LM_THREADS = 256;
+constexpr int LM_WARPS = LM_THREADS / 32;
+constexpr int LM_MAX_SEG = 8;
+
+__device__ __forceinline__ unsigned long long lm_ld_volatile(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lm_st_volatile(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Grid barrier: bar[0] = arrive counter, bar[1] = generation.  All CTAs of the launch are co-resident (cooperative launch, grid <= SMs).
+// `spins` bounds the wait (a rank that left the solve early must not hang its peers' GPUs): on overflow *err is set and the wait ends.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0 && nblocks > 1) {
+    __threadfence();
+    const unsigned long long g = lm_ld_volatile(bar + 1);
+    const unsigned long long t = atomicAdd(bar, 1ull);
+    if (t == (unsigned long long)nblocks - 1) {
+      atomicExch(bar, 0ull);
+      __threadfence();
+      lm_st_volatile(bar + 1, g + 1);
+    } else {
+      while (lm_ld_volatile(bar + 1) == g) { }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct LmPeer {                      // NVLink peer-memory exchange (one buffer per rank, IPC-mapped into every rank; layout of peer_allreduce.cuh)
+  int rank, world, cap;
+  double* base[PEER_MAX_WORLD];
+  unsigned long long* seq;           // device counter of the exchanges done so far (same on every rank)
+  long long timeout_cycles;          // bound on the wait for a peer's flag
+};
+
+struct LmArgs {
+  DeviceProblem P;                   // parameter pointers = the CURRENT state; pose tables = the state last linearised (the trial)
+  double *cam_rt2, *board_rt2, *frame_rt2, *intr2, *board_pts2, *he_rt2;      // TRIAL parameter state (what k_linearize reads)
+  int n, n_s, F, fb, n_items;
+  // linearisation at the trial point (k_linearize + k_reduce_shared [+ add-on kernels])
+  const double* Hss; const double* Hff; const double* W; const double* g; const double* frame_cost; const double* lin_cost;
+  // iteration vectors
+  double *x, *x_new, *sinv, *d, *gh, *gn;
+  // Schur complement
+  double *Y, *Lf, *zf, *S, *rhs, *Spart, *rpart, *Linv;
+  int syrk_chunks, syrk_cf;
+  // partial sums (indexed by frame / virtual block: independent of the grid size where it matters for reproducibility)
+  double *part_scale, *part_quad, *part_step;
+  SolverState* st;
+  mcba_log_row* log; int log_cap;
+  unsigned long long* bar;
+  int opt_loss;                      // unused by the kernel (the linearisation kernels apply the loss); kept for the log
+  LmPeer peer;
+  unsigned long long cond_handle; int use_cond;      // CUDA-graph WHILE node: the kernel sets the loop condition itself
+};
+
+// ---------------------------------------------------------------- replicated block-wide sums
+// deterministic: fixed thread -> element map, fixed tree.  Result valid in EVERY thread (broadcast through shared memory).
+__device__ __forceinline__ double block_sum_all(double v, double* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i < LM_WARPS; i++) r += sm[i];
+  return r;
+}
+__device__ __forceinline__ double block_max_all(double v, double* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i < LM_WARPS; i++) r = fmax(r, sm[i]);
+  return r;
+}
+// sum of count records part[i*stride + j] over i, every CTA in the same order
+__device__ __forceinline__ double sum_records(const double* part, int count, int stride, int j, double* sm) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += LM_THREADS) s += __ldcg(&part[(size_t)i * stride + j]);
+  return block_sum_all(s, sm);
+}
+__device__ __forceinline__ double max_records(const double* part, int count, int stride, int j, double* sm) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < count; i += LM_THREADS) s = fmax(s, __ldcg(&part[(size_t)i * stride + j]));
+  return block_max_all(s, sm);
+}
+
+// ---------------------------------------------------------------- in-kernel all-reduce over NVLink peer memory
+// All CTAs of all ranks call it with the same segment list.  push (slice-parallel remote stores into my slot on every rank) -> grid
+// barrier -> one thread publishes this rank's sequence flag on every rank -> every CTA waits for all ranks' flags -> reduce in rank
+// order (slice-parallel) -> grid barrier.  Two parities of slots: a rank cannot start exchange k+2 before every rank finished k.
+struct XSeg { double* buf; int count; int op; };      // op 0 = sum, 1 = max
+__device__ inline void exchange(const LmArgs& a, const XSeg* seg, int nseg, unsigned long long seq, int* err) {
+  const LmPeer& pr = a.peer;
+  const int parity = (int)(seq & 1ull);
+  int total = 0;
+  for (int s = 0; s < nseg; s++) total += seg[s].count;
+  const size_t slot = peer_data_off(pr.world, pr.cap, parity, pr.rank);
+  for (int idx = blockIdx.x * LM_THREADS + threadIdx.x; idx < total; idx += gridDim.x * LM_THREADS) {
+    int s = 0, off = idx;
+    while (off >= seg[s].count) { off -= seg[s].count; s++; }
+    const double v = __ldcg(seg[s].buf + off);
+    for (int p = 0; p < pr.world; p++) pr.base[p][slot + idx] = v;
+  }
+  __threadfence_system();
+  grid_barrier(a.bar, gridDim.x);
+  if (blockIdx.x == 0 && threadIdx.x < pr.world) {
+    __threadfence_system();
+    lm_st_volatile(reinterpret_cast<unsigned long long*>(pr.base[threadIdx.x] + peer_flag_off(pr.world, parity, pr.rank)), seq);
+  }
+  if (threadIdx.x < pr.world) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(pr.base[pr.rank] + peer_flag_off(pr.world, parity, threadIdx.x));
+    const long long t0 = clock64();
+    while (lm_ld_volatile(f) != seq) {
+      if (pr.timeout_cycles > 0 && clock64() - t0 > pr.timeout_cycles) { *err = 1; break; }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const double* mine = pr.base[pr.rank];
+  for (int idx = blockIdx.x * LM_THREADS + threadIdx.x; idx < total; idx += gridDim.x * LM_THREADS) {
+    int s = 0, off = idx;
+    while (off >= seg[s].count) { off -= seg[s].count; s++; }
+    double acc = __ldcv(mine + peer_data_off(pr.world, pr.cap, parity, 0) + idx);
+    for (int src = 1; src < pr.world; src++) {
+      const double v = __ldcv(mine + peer_data_off(pr.world, pr.cap, parity, src) + idx);
+      acc = seg[s].op == 0 ? acc + v : fmax(acc, v);
+    }
+    seg[s].buf[off] = acc;
+  }
+  __threadfence();
+  grid_barrier(a.bar, gridDim.x);
+}
+
+// ---------------------------------------------------------------- phase bodies
+// per frame (one warp): L L^T = D_f H_ff D_f + reg I ; Y_f = (D_s W_f D_f) L^-T ; z_f = L^-1 gh_f
+template <int FB>
+__device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, int lane, double* Lw /*[FB*FB + FB] shared, per warp*/) {
+  const int n_s = a.n_s;
+  double* L = Lw; double* df = Lw + FB * FB;
+  if (lane == 0) {
+    const double* H = a.Hff + (size_t)f * FB * FB;
+    double A[FB * FB];
+#pragma unroll
+    for (int j = 0; j < FB; j++) df[j] = a.d[n_s + FB * f + j];
+#pragma unroll
+    for (int i = 0; i < FB; i++)
+#pragma unroll
+      for (int j = 0; j < FB; j++) A[i * FB + j] = df[i] * df[j] * H[i * FB + j] + (i == j ? reg : 0.0);
+#pragma unroll
+    for (int j = 0; j < FB; j++) {
+      double s = A[j * FB + j];
+#pragma unroll
+      for (int k = 0; k < FB; k++) if (k < j) s -= L[j * FB + k] * L[j * FB + k];
+      const double piv = sqrt(fmax(s, 1e-300));
+      L[j * FB + j] = piv;
+#pragma unroll
+      for (int i = 0; i < FB; i++) {
+        if (i > j) {
+          double t = A[i * FB + j];
+#pragma unroll
+          for (int k = 0; k < FB; k++) if (k < j) t -= L[i * FB + k] * L[j * FB + k];
+          L[i * FB + j] = t / piv;
+        } else if (i < j) L[i * FB + j] = 0.0;
+      }
+    }
+    double z[FB];
+#pragma unroll
+    for (int i = 0; i < FB; i++) {
+      double t = a.gh[n_s + FB * f + i];
+#pragma unroll
+      for (int k = 0; k < FB; k++) if (k < i) t -= L[i * FB + k] * z[k];
+      z[i] = t / L[i * FB + i];
+      a.zf[(size_t)f * FB + i] = z[i];
+    }
+#pragma unroll
+    for (int i = 0; i < FB * FB; i++) a.Lf[(size_t)f * FB * FB + i] = L[i];
+  }
+  __syncwarp();
+  const double* Wf = a.W + (size_t)f * n_s * FB;
+  double* Yf = a.Y + (size_t)f * n_s * FB;
+  for (int s = lane; s < n_s; s += 32) {
+    const double ds = a.d[s];
+    double y[FB];
+#pragma unroll
+    for (int i = 0; i < FB; i++) {
+      double t = ds * Wf[s * FB + i] * df[i];
+#pragma unroll
+      for (int k = 0; k < FB; k++) if (k < i) t -= L[i * FB + k] * y[k];
+      y[i] = t / L[i * FB + i];
+    }
+#pragma unroll
+    for (int i = 0; i < FB; i++) Yf[s * FB + i] = y[i];
+  }
+  __syncwarp();
+}
+
+// one 32x32 tile (ti <= tj) of sum_f Y_f Y_f^T over a frame chunk -> Spart[chunk], diagonal tiles also sum_f Y_f z_f -> rpart[chunk]
+template <int FB>
+__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* 2 * SYRK_FR*32*FB doubles */) {
+  constexpr int SYRK_FR = syrk_fr(FB);
+  const int n_s = a.n_s, F = a.F;
+  double (*Yi)[SYRK_TILE][FB] = reinterpret_cast<double (*)[SYRK_TILE][FB]>(sh);
+  double (*Yj)[SYRK_TILE][FB] = reinterpret_cast<double (*)[SYRK_TILE][FB]>(sh + SYRK_FR * SYRK_TILE * FB);
+  const int f0 = chunk * a.syrk_cf, f1 = min(F, f0 + a.syrk_cf);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  double racc = 0.0;
+  __syncthreads();
+  for (int fbase = f0; fbase < f1; fbase += SYRK_FR) {
+    const int nf = min(SYRK_FR, f1 - fbase);
+    for (int o = threadIdx.x; o < SYRK_FR * SYRK_TILE * FB; o += LM_THREADS) {
+      const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
+      const int gi = ti * SYRK_TILE + r, gj = tj * SYRK_TILE + r;
+      (&Yi[0][0][0])[o] = (ff < nf && gi < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gi) * FB + k] : 0.0;
+      (&Yj[0][0][0])[o] = (ff < nf && gj < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gj) * FB + k] : 0.0;
+    }
+    __syncthreads();
+    for (int ff = 0; ff < nf; ff++) {
+#pragma unroll
+      for (int k = 0; k < FB; k++) {
+        const double a0 = Yi[ff][ty][k], a1 = Yi[ff][ty + 16][k], b0 = Yj[ff][tx][k], b1 = Yj[ff][tx + 16][k];
+        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+      }
+    }
+    if (ti == tj && threadIdx.x < SYRK_TILE) {
+      for (int ff = 0; ff < nf; ff++) {
+        const double* z = a.zf + (size_t)(fbase + ff) * FB;
+#pragma unroll
+        for (int k = 0; k < FB; k++) racc += Yi[ff][threadIdx.x][k] * z[k];
+      }
+    }
+    __syncthreads();
+  }
+  double* Sp = a.Spart + (size_t)chunk * n_s * n_s;
+  if (ti == tj && threadIdx.x < SYRK_TILE) {
+    const int i = ti * SYRK_TILE + threadIdx.x;
+    if (i < n_s) a.rpart[(size_t)chunk * n_s + i] = racc;
+  }
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = ti * SYRK_TILE + ty + 16 * p, j = tj * SYRK_TILE + tx + 16 * q;
+      if (i < n_s && j < n_s) Sp[(size_t)i * n_s + j] = acc[p][q];
+    }
+}
+
+// reduced solve, n_s <= CHOL_SMALL_MAX: one CTA, matrix cyclically distributed in registers (the round-1 k_chol_small scheme)
+template <int R>
+__device__ __forceinline__ void chol_small_body(int n, const double* Sg, const double* rhs, const double* gh, double reg, int* chol_fail, double* out, double* shm) {
+  const int ld = n | 1;
+  double* Lm = shm;
+  double* colbuf = Lm + (size_t)n * ld;
+  double* invd = colbuf + n;
+  double* piv = invd + n;
+  const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+  double a[R][R];
+#pragma unroll
+  for (int p = 0; p < R; p++)
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      a[p][q] = (i < n && j < n) ? __ldcg(&Sg[(size_t)j * n + i]) + (i == j ? reg : 0.0) : 0.0;
+    }
+  __syncthreads();
+  if (tid == 0) piv[0] = a[0][0];
+  __syncthreads();
+  for (int k = 0; k < n; k++) {
+    const int kq = k >> 4, kt = k & 15;
+    if (tx == kt) {
+      const double akk = piv[0];
+      if (ty == kt && !(akk > 0.0)) *chol_fail += 1;
+      const double rs = rsqrt(fmax(akk, 1e-300));
+      if (ty == kt) invd[k] = rs;
+#define MCBA_SCALE_Q(Q) case Q: if constexpr (Q < R) { _Pragma("unroll") for (int p = 0; p < R; p++) { const int i = ty + 16 * p; \
+        if (i >= k && i < n) { const double l = a[p][Q < R ? Q : 0] * rs; a[p][Q < R ? Q : 0] = l; colbuf[i] = l; } } } break;
+      switch (kq) { MCBA_SCALE_Q(0) MCBA_SCALE_Q(1) MCBA_SCALE_Q(2) MCBA_SCALE_Q(3) MCBA_SCALE_Q(4) MCBA_SCALE_Q(5) MCBA_SCALE_Q(6) MCBA_SCALE_Q(7) }
+#undef MCBA_SCALE_Q
+    }
+    __syncthreads();
+    double ci[R], cj[R];
+#pragma unroll
+    for (int p = 0; p < R; p++) { const int i = ty + 16 * p; ci[p] = (i > k && i < n) ? colbuf[i] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < R; q++) { const int j = tx + 16 * q; cj[q] = (j > k && j < n) ? colbuf[j] : 0.0; }
+#pragma unroll
+    for (int p = 0; p < R; p++)
+#pragma unroll
+      for (int q = 0; q < R; q++) a[p][q] -= ci[p] * cj[q];
+    {
+      const int k1 = k + 1, q1 = k1 >> 4, t1 = k1 & 15;
+      if (k1 < n && ty == t1 && tx == t1) {
+#pragma unroll
+        for (int p = 0; p < R; p++) if (p == q1) piv[0] = a[p][p];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < R; p++)
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      if (i < n && j <= i) Lm[i * ld + j] = a[p][q];
+    }
+  __syncthreads();
+  if (tid < 32) {
+    constexpr int RS = (R * 16 + 31) / 32;
+    const int lane = tid;
+    double bs[RS];
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; bs[s2] = i < n ? __ldcg(&rhs[i]) + gh[i] : 0.0; }
+#pragma unroll
+    for (int s1 = 0; s1 < RS; s1++) {
+      for (int kk = 0; kk < 32; kk++) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) break;
+        const double yk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = yk;
+#pragma unroll
+        for (int s2 = s1; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i > k && i < n) bs[s2] -= Lm[i * ld + k] * yk; }
+      }
+    }
+#pragma unroll
+    for (int s1 = RS - 1; s1 >= 0; s1--) {
+      for (int kk = 31; kk >= 0; kk--) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) continue;
+        const double xk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = xk;
+#pragma unroll
+        for (int s2 = 0; s2 <= s1; s2++) { const int i = lane + 32 * s2; if (i < k) bs[s2] -= Lm[k * ld + i] * xk; }
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i < n) out[i] = bs[s2]; }
+  }
+  __syncthreads();
+}
+
+// ---- blocked right-looking Cholesky for n_s > CHOL_SMALL_MAX, NB = 32 panels, the grid cooperating between barriers.
+// The right-hand side rides along as row n of the matrix (forward substitution comes out of the panel solves for free).
+__device__ __forceinline__ void chol_diag_body(int n, int kb, double* S, double* Linv_all, int* chol_fail, double* sh) {
+  double (*Lm)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
+  double* colbuf = sh + CHOL_NB * (CHOL_NB + 1);
+  double* invd = colbuf + CHOL_NB;
+  double* piv = invd + CHOL_NB;
+  const int nb = min(CHOL_NB, n - kb);
+  const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+  double a[2][2];
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      a[p][q] = (i < nb && j < nb) ? (j <= i ? __ldcg(&S[(size_t)(kb + i) * n + kb + j]) : __ldcg(&S[(size_t)(kb + j) * n + kb + i])) : (i == j ? 1.0 : 0.0);
+    }
+  __syncthreads();
+  if (tid == 0) piv[0] = a[0][0];
+  __syncthreads();
+  for (int k = 0; k < CHOL_NB; k++) {
+    const int kq = k >> 4, kt = k & 15;
+    if (tx == kt) {
+      const double akk = piv[0];
+      if (ty == kt && k < nb && !(akk > 0.0)) *chol_fail += 1;
+      const double rs = rsqrt(fmax(akk, 1e-300));
+      if (ty == kt) invd[k] = rs;
+#pragma unroll
+      for (int p = 0; p < 2; p++) {
+        const int i = ty + 16 * p;
+        if (i >= k) {
+          if (kq == 0) { const double l = a[p][0] * rs; a[p][0] = l; colbuf[i] = l; }
+          else { const double l = a[p][1] * rs; a[p][1] = l; colbuf[i] = l; }
+        }
+      }
+    }
+    __syncthreads();
+    double ci[2], cj[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) { const int i = ty + 16 * p; ci[p] = i > k ? colbuf[i] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < 2; q++) { const int j = tx + 16 * q; cj[q] = j > k ? colbuf[j] : 0.0; }
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) a[p][q] -= ci[p] * cj[q];
+    {
+      const int k1 = k + 1, q1 = k1 >> 4, t1 = k1 & 15;
+      if (k1 < CHOL_NB && ty == t1 && tx == t1) piv[0] = q1 == 0 ? a[0][0] : a[1][1];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      Lm[i][j] = j <= i ? a[p][q] : 0.0;
+      if (i < nb && j <= i) S[(size_t)(kb + i) * n + kb + j] = a[p][q];
+    }
+  __syncthreads();
+  if (tid < CHOL_NB) {
+    const int j = tid;
+    double z[CHOL_NB];
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; i++) {
+      double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k2 = 0; k2 < CHOL_NB; k2++) if (k2 < i) t -= Lm[i][k2] * z[k2];
+      z[i] = (i >= j) ? t * invd[i] : 0.0;
+    }
+    double* Li = Linv_all + (size_t)(kb / CHOL_NB) * CHOL_NB * CHOL_NB;
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; i++) Li[i * CHOL_NB + j] = z[i];
+  }
+  __syncthreads();
+}
+// panel rows [i0, i0+32) below the diagonal block at kb: X = A[:, kb:kb+nb] L_kk^-T; row n (the right-hand side, stored in `bvec`) included
+// as the last virtual row block.  Mirrors X into the upper triangle so that L^T is readable row-wise.
+__device__ __forceinline__ void chol_trsm_body(int n, int kb, int vb, double* S, const double* Linv_all, double* bvec, double* sh) {
+  double (*Li)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
+  double (*At)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + CHOL_NB * (CHOL_NB + 1));
+  const int nb = min(CHOL_NB, n - kb);
+  const double* Lg = Linv_all + (size_t)(kb / CHOL_NB) * CHOL_NB * CHOL_NB;
+  const int i0 = kb + nb + vb * CHOL_NB;
+  __syncthreads();
+  for (int o = threadIdx.x; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
+    const int r = o / CHOL_NB, c = o % CHOL_NB;
+    Li[r][c] = __ldcg(&Lg[o]);
+    At[r][c] = (i0 + r < n && c < nb) ? __ldcg(&S[(size_t)(i0 + r) * n + kb + c]) : 0.0;
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  double x[4] = {0, 0, 0, 0};
+#pragma unroll 8
+  for (int k = 0; k < CHOL_NB; k++) {
+    const double av = At[r][k];
+#pragma unroll
+    for (int q = 0; q < 4; q++) x[q] += av * Li[cg * 4 + q][k];
+  }
+  if (i0 + r < n) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int j = cg * 4 + q;
+      if (j < nb) { S[(size_t)(i0 + r) * n + kb + j] = x[q]; S[(size_t)(kb + j) * n + i0 + r] = x[q]; }
+    }
+  }
+  (void)bvec;
+}
+__device__ __forceinline__ void chol_syrk_body(int n, int kb, int ti, int tj, double* S, double* sh) {
+  double (*Li)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
+  double (*Lj)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + CHOL_NB * (CHOL_NB + 1));
+  const int nb = min(CHOL_NB, n - kb);
+  const int base = kb + nb;
+  const int i0 = base + ti * 32, j0 = base + tj * 32;
+  __syncthreads();
+  for (int o = threadIdx.x; o < 32 * nb; o += LM_THREADS) {
+    const int r = o / nb, k = o % nb;
+    Li[r][k] = (i0 + r < n) ? __ldcg(&S[(size_t)(i0 + r) * n + kb + k]) : 0.0;
+    Lj[r][k] = (j0 + r < n) ? __ldcg(&S[(size_t)(j0 + r) * n + kb + k]) : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int k = 0; k < nb; k++) {
+    const double a0 = Li[ty][k], a1 = Li[ty + 16][k], b0 = Lj[tx][k], b1 = Lj[tx + 16][k];
+    acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+  }
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = i0 + ty + 16 * p, j = j0 + tx + 16 * q;
+      if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[p][q];
+    }
+}
+// both substitutions by one CTA with the factor in global memory (lower = L, strict upper = L^T mirror) and the inverted diagonal blocks
+__device__ __forceinline__ void chol_substitute_body(int n, const double* L, const double* Linv_all, const double* rhs, const double* gh, double* out, double* bsh) {
+  double* yb = bsh + ((n + CHOL_NB - 1) / CHOL_NB) * CHOL_NB;
+  const int tid = threadIdx.x;
+  const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
+  __syncthreads();
+  for (int i = tid; i < nblk * CHOL_NB; i += LM_THREADS) bsh[i] = i < n ? __ldcg(&rhs[i]) + gh[i] : 0.0;
+  __syncthreads();
+  for (int blk = 0; blk < nblk; blk++) {
+    const int kb = blk * CHOL_NB;
+    const double* Li = Linv_all + (size_t)blk * CHOL_NB * CHOL_NB;
+    if (tid < CHOL_NB) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_NB; k++) acc += __ldcg(&Li[tid * CHOL_NB + k]) * bsh[kb + k];
+      yb[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
+    for (int i = kb + CHOL_NB + tid; i < n; i += LM_THREADS) {
+      const double* row = L + (size_t)i * n + kb;
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_NB; k++) acc += __ldcg(&row[k]) * yb[k];
+      bsh[i] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int blk = nblk - 1; blk >= 0; blk--) {
+    const int kb = blk * CHOL_NB;
+    const double* Li = Linv_all + (size_t)blk * CHOL_NB * CHOL_NB;
+    if (tid < CHOL_NB) {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k < CHOL_NB; k++) acc += __ldcg(&Li[k * CHOL_NB + tid]) * bsh[kb + k];
+      yb[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
+    const int nbv = min(CHOL_NB, n - kb);
+    for (int i = tid; i < kb; i += LM_THREADS) {
+      const double* row = L + (size_t)i * n + kb;
+      double acc = 0.0;
+      for (int k = 0; k < nbv; k++) acc += __ldcg(&row[k]) * yb[k];
+      bsh[i] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += LM_THREADS) out[i] = bsh[i];
+  __syncthreads();
+}
+
+// shared memory of k_lm in doubles
+__host__ __device__ inline size_t lm_smem_doubles(int n_s, int fb) {
+  const size_t small = n_s <= CHOL_SMALL_MAX ? (size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2 : 0;
+  const size_t big = n_s > CHOL_SMALL_MAX ? (size_t)((n_s + CHOL_NB - 1) / CHOL_NB + 1) * CHOL_NB : 0;
+  const size_t syrk = 2 * (size_t)syrk_fr(fb > 0 ? fb : 6) * SYRK_TILE * (fb > 0 ? fb : 6);
+  const size_t chol_tiles = 2 * (size_t)CHOL_NB * (CHOL_NB + 1) + 3 * CHOL_NB;
+  const size_t frames = (size_t)LM_WARPS * (12 * 12 + 12);
+  size_t m = small;
+  if (big > m) m = big;
+  if (syrk > m) m = syrk;
+  if (chol_tiles > m) m = chol_tiles;
+  if (frames > m) m = frames;
+  return m + 64;
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int FB>
+__global__ void __launch_bounds__(LM_THREADS, 1)
+k_lm(LmArgs a) {
+  extern __shared__ double ksm[];
+  __shared__ SolverState S;
+  __shared__ double sm[32];
+  __shared__ int xerr, chol_fail_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n, n_s = a.n_s;
+  const int F = a.P.motion_on ? a.F : 0;              // frames with a free block
+  const int nblk = gridDim.x;
+  const int gthread = blockIdx.x * LM_THREADS + tid, gstride = nblk * LM_THREADS;
+  const int gwarp = blockIdx.x * LM_WARPS + warp, gwarps = nblk * LM_WARPS;
+  const bool multi = a.peer.world > 1;
+  const bool writer = blockIdx.x == 0 && tid == 0;
+  double* work = ksm + 64;
+
+  if (tid == 0) { S = *a.st; xerr = 0; chol_fail_s = 0; }
+#ifdef MCBA_SIMT_BUILD
+#define LMPH(x) simt::set_mark(x);
+#else
+#define LMPH(x)
+#endif
+  __syncthreads();
+  if (S.done) {
+    if (writer && a.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond_handle, 0);
+    return;
+  }
+  unsigned long long xseq = 0;
+  if (multi) xseq = *a.peer.seq;                       // exchanges done so far (every CTA reads the same value: written at the end of the previous launch)
+
+  auto log_row = [&](int it, int nfev, double cost, double red, double step, double opt) {
+    if (writer && S.nlog < a.log_cap) a.log[S.nlog] = mcba_log_row{it, nfev, cost, red, step, opt};
+    if (tid == 0) S.nlog += 1;
+  };
+
+  // ------------------------------------------------------------------------------------------ phase A: the pending trial
+  LMPH(1)
+  bool need_solve = true;
+  double first_cost = 0.0;                              // several GPUs: cost of the first linearisation summed over the ranks
+  if (S.pending) {
+    double cost_new = sum_records(a.frame_cost, a.F, 1, 0, sm);
+    double s2f = sum_records(a.part_step, S.step_parts, 2, 0, sm);
+    double x2f = sum_records(a.part_step, S.step_parts, 2, 1, sm);
+    if (multi) {
+      // one exchange: trial cost and step norms (frame parts) of all ranks, and -- the trial is linearised speculatively -- the shared
+      // gradient / diagonal / cost of its normal equations, which the next iteration starts from if the step is accepted
+      if (writer) { a.part_quad[0] = cost_new; a.part_quad[1] = s2f; a.part_quad[2] = x2f; }
+      grid_barrier(a.bar, nblk);
+      XSeg seg[3] = {{a.part_quad, 3, 0}, {const_cast<double*>(a.g), n_s, 0}, {a.S, n_s, 0}};
+      // diag(H_ss) travels in the first n_s entries of S (S is rebuilt in phase D)
+      for (int i = gthread; i < n_s; i += gstride) a.S[i] = a.Hss[(size_t)i * n_s + i];
+      grid_barrier(a.bar, nblk);
+      exchange(a, seg, 3, ++xseq, &xerr);
+      cost_new = __ldcg(&a.part_quad[0]); s2f = __ldcg(&a.part_quad[1]); x2f = __ldcg(&a.part_quad[2]);
+    }
+    if (tid == 0) {
+      double red[RED_COUNT];
+      red[RED_COSTNEW] = cost_new; red[RED_STEP2_S] = S.step2_s; red[RED_STEP2_F] = s2f; red[RED_XN2_S] = S.xn2_s; red[RED_XN2_F] = x2f;
+      accept_compute(&S, red);
+    }
+    __syncthreads();
+    const bool accepted = S.accepted != 0, may_retry = S.status == -99 && S.nfev < S.max_nfev;
+    __syncthreads();                                    // thread 0 updates S below: every thread has its copy of the decision first
+    if (accepted) {
+      // x = x_new ; cost = cost_new ; J = jac(x)  (trf.py): the trial state becomes the current one
+      for (int i = gthread; i < n; i += gstride) a.x[i] = a.x_new[i];
+      const DeviceProblem& p = a.P;
+      for (int i = gthread; i < 6 * p.C; i += gstride) p.cam_rt[i] = a.cam_rt2[i];
+      for (int i = gthread; i < 6 * p.B; i += gstride) p.board_rt[i] = a.board_rt2[i];
+      for (int i = gthread; i < p.F * (p.fb > 0 ? p.fb : 6) && p.motion != MOTION_HAND_EYE; i += gstride) p.frame_rt[i] = a.frame_rt2[i];
+      for (int i = gthread; i < p.kint * p.C; i += gstride) p.intr[i] = a.intr2[i];
+      for (int i = gthread; i < 3 * p.B * p.P && p.off_pt >= 0; i += gstride) p.board_pts[i] = a.board_pts2[i];
+      for (int i = gthread; i < 12 && p.motion == MOTION_HAND_EYE; i += gstride) p.he_rt[i] = a.he_rt2[i];
+      if (tid == 0) {
+        S.cost = S.cost_new; S.njev += 1; S.last_reduction = S.actual_reduction; S.last_step_norm = S.step_norm;
+        S.iteration += 1; S.accepted = 0; S.pending = 0;
+      }
+    } else if (may_retry) {
+      need_solve = false;                                 // shrink the radius and try again from the same model (trf.py inner loop)
+    } else {
+      // out of evaluations, or a termination test fired on a step that did not reduce the cost: the loop ends at the unchanged x
+      if (tid == 0) { S.iteration += 1; S.last_reduction = 0.0; S.last_step_norm = 0.0; S.done = 1; S.pending = 0; }
+      __syncthreads();
+      log_row(S.iteration, S.nfev, S.cost, 0.0, 0.0, S.g_norm);
+      __syncthreads();
+      if (writer) { *a.st = S; if (multi) *a.peer.seq = xseq; if (a.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond_handle, 0); }
+      return;
+    }
+    __syncthreads();
+  } else if (multi) {
+    // first linearisation: shared gradient, diagonal and cost of all ranks
+    for (int i = gthread; i < n_s; i += gstride) a.S[i] = a.Hss[(size_t)i * n_s + i];
+    if (writer) a.part_quad[0] = *a.lin_cost;
+    grid_barrier(a.bar, nblk);
+    XSeg seg[3] = {{a.part_quad, 1, 0}, {const_cast<double*>(a.g), n_s, 0}, {a.S, n_s, 0}};
+    exchange(a, seg, 3, ++xseq, &xerr);
+    first_cost = __ldcg(&a.part_quad[0]);
+  }
+
+  if (need_solve) {
+    LMPH(2)
+    // ---------------------------------------------------------------------------------------- phase B: scaling, g_h, norms
+    {
+      double gh2s = 0, gh2f = 0, gms = 0, gmf = 0, xs2s = 0, xs2f = 0;
+      const int first = S.first_scale;
+      for (int i = gthread; i < n; i += gstride) {
+        double hd;
+        if (i < n_s) hd = multi ? __ldcg(&a.S[i]) : a.Hss[(size_t)i * n_s + i];
+        else { const int f = (i - n_s) / FB, j = (i - n_s) % FB; hd = a.Hff[(size_t)f * FB * FB + j * (FB + 1)]; }
+        const double nrm = sqrt(fmax(hd, 0.0));
+        double si;
+        if (first) si = (nrm == 0.0) ? 1.0 : nrm; else si = fmax(nrm, a.sinv[i]);
+        a.sinv[i] = si;
+        const double di = 1.0 / si;
+        a.d[i] = di;
+        const double gi = a.g[i], ghi = di * gi, xs = a.x[i] * si;
+        a.gh[i] = ghi;
+        if (i < n_s) { gh2s += ghi * ghi; gms = fmax(gms, fabs(gi)); xs2s += xs * xs; }
+        else { gh2f += ghi * ghi; gmf = fmax(gmf, fabs(gi)); xs2f += xs * xs; }
+      }
+      const double r0 = block_sum_all(gh2s, sm), r1 = block_sum_all(gh2f, sm), r2 = block_max_all(gms, sm), r3 = block_max_all(gmf, sm);
+      const double r4 = block_sum_all(xs2s, sm), r5 = block_sum_all(xs2f, sm);
+      if (tid == 0) { double* q = a.part_scale + (size_t)blockIdx.x * 6; q[0] = r0; q[1] = r1; q[2] = r2; q[3] = r3; q[4] = r4; q[5] = r5; }
+    }
+    grid_barrier(a.bar, nblk);
+    {
+      double gh2s = sum_records(a.part_scale, nblk, 6, 0, sm), gh2f = sum_records(a.part_scale, nblk, 6, 1, sm);
+      double gms = max_records(a.part_scale, nblk, 6, 2, sm), gmf = max_records(a.part_scale, nblk, 6, 3, sm);
+      double xs2s = sum_records(a.part_scale, nblk, 6, 4, sm), xs2f = sum_records(a.part_scale, nblk, 6, 5, sm);
+      double lin_cost = __ldcg(a.lin_cost);
+      if (multi) {
+        // the shared entries are replicated (identical on every rank after the first exchange): only the frame parts travel
+        if (writer) { a.part_quad[0] = gh2f; a.part_quad[1] = xs2f; a.part_quad[2] = gmf; }
+        grid_barrier(a.bar, nblk);
+        XSeg seg[2] = {{a.part_quad, 2, 0}, {a.part_quad + 2, 1, 1}};
+        exchange(a, seg, 2, ++xseq, &xerr);
+        gh2f = __ldcg(&a.part_quad[0]); xs2f = __ldcg(&a.part_quad[1]); gmf = __ldcg(&a.part_quad[2]);
+      }
+      if (tid == 0) {
+        double red[RED_COUNT];
+        red[RED_GH2_S] = gh2s; red[RED_GH2_F] = gh2f; red[RED_GMAX_S] = gms; red[RED_GMAX_F] = gmf; red[RED_XS2_S] = xs2s; red[RED_XS2_F] = xs2f;
+        red[RED_COST] = multi ? first_cost : lin_cost;                    // only read on the first call (begin_iteration)
+        begin_iteration(&S, red);
+        if (!isfinite(S.cost)) { S.done = 1; S.status = -2; }          // non-finite residuals at the initial point (scipy raises ValueError)
+      }
+      __syncthreads();
+      log_row(S.iteration, S.nfev, S.cost, S.iteration == 0 ? NAN : S.last_reduction, S.iteration == 0 ? NAN : S.last_step_norm, S.g_norm);
+      __syncthreads();
+      if (S.done) {
+        if (writer) { *a.st = S; if (multi) *a.peer.seq = xseq; if (a.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond_handle, 0); }
+        return;
+      }
+    }
+    // ---------------------------------------------------------------------------------------- phase C: g_h^T A g_h -> reg
+    const int nsh = (n_s + LM_THREADS - 1) / LM_THREADS;           // virtual blocks of shared rows
+    auto quad_pass = [&](const double* u, const double* v, int two, double* partial /*[F + nsh][5]*/) {
+      for (int f = gwarp; f < F; f += gwarps) {
+        const double* Wf = a.W + (size_t)f * n_s * FB;
+        double tu[FB], tv[FB];
+#pragma unroll
+        for (int j = 0; j < FB; j++) { tu[j] = 0.0; tv[j] = 0.0; }
+        for (int s = lane; s < n_s; s += 32) {
+          const double us = a.d[s] * u[s], vs = two ? a.d[s] * v[s] : 0.0;
+#pragma unroll
+          for (int j = 0; j < FB; j++) { const double w = Wf[s * FB + j]; tu[j] += w * us; tv[j] += w * vs; }
+        }
+#pragma unroll
+        for (int j = 0; j < FB; j++) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { tu[j] += __shfl_xor_sync(0xffffffffu, tu[j], o); tv[j] += __shfl_xor_sync(0xffffffffu, tv[j], o); }
+        }
+        if (lane == 0) {
+          double uf[FB], vf[FB], uu = 0, uv = 0, vv = 0, dt = 0, g2 = 0;
+#pragma unroll
+          for (int j = 0; j < FB; j++) { const int i = n_s + FB * f + j; uf[j] = a.d[i] * u[i]; vf[j] = two ? a.d[i] * v[i] : 0.0; if (two) { dt += u[i] * v[i]; g2 += v[i] * v[i]; } }
+          const double* H = a.Hff + (size_t)f * FB * FB;
+#pragma unroll
+          for (int i = 0; i < FB; i++) {
+            double hu = 0, hv = 0;
+#pragma unroll
+            for (int j = 0; j < FB; j++) { hu += H[i * FB + j] * uf[j]; hv += H[i * FB + j] * vf[j]; }
+            uu += uf[i] * (hu + 2.0 * tu[i]);
+            uv += uf[i] * hv + uf[i] * tv[i] + vf[i] * tu[i];
+            vv += vf[i] * (hv + 2.0 * tv[i]);
+          }
+          double* q = partial + (size_t)f * 5;
+          q[0] = uu; q[1] = uv; q[2] = vv; q[3] = dt; q[4] = g2;
+        }
+      }
+      for (int sb = blockIdx.x; sb < nsh; sb += nblk) {
+        const int i = sb * LM_THREADS + tid;
+        double uu = 0, uv = 0, vv = 0, dt = 0, g2 = 0;
+        if (i < n_s) {
+          double hu = 0, hv = 0;
+          for (int j = 0; j < n_s; j++) {
+            const double h = a.Hss[(size_t)j * n_s + i];
+            hu += h * a.d[j] * u[j];
+            if (two) hv += h * a.d[j] * v[j];
+          }
+          const double ui = a.d[i] * u[i], vi = two ? a.d[i] * v[i] : 0.0;
+          uu = ui * hu; uv = ui * hv; vv = vi * hv;
+          if (two) { dt = u[i] * v[i]; g2 = v[i] * v[i]; }
+        }
+        const double r0 = block_sum_all(uu, sm), r1 = block_sum_all(uv, sm), r2 = block_sum_all(vv, sm), r3 = block_sum_all(dt, sm), r4 = block_sum_all(g2, sm);
+        if (tid == 0) { double* q = partial + (size_t)(F + sb) * 5; q[0] = r0; q[1] = r1; q[2] = r2; q[3] = r3; q[4] = r4; }
+      }
+    };
+    LMPH(3)
+    quad_pass(a.gh, a.gh, 0, a.part_quad + 8);
+    grid_barrier(a.bar, nblk);
+    {
+      double agg = sum_records(a.part_quad + 8, F + nsh, 5, 0, sm);
+      if (multi) {
+        // H_ss is this rank's local part: its quadratic form sums over the ranks like the frame parts
+        if (writer) a.part_quad[0] = agg;
+        grid_barrier(a.bar, nblk);
+        XSeg seg[1] = {{a.part_quad, 1, 0}};
+        exchange(a, seg, 1, ++xseq, &xerr);
+        agg = __ldcg(&a.part_quad[0]);
+      }
+      if (tid == 0) { double red[RED_COUNT]; red[RED_AGG] = agg; reg_compute(&S, red); S.agg = agg; }
+      __syncthreads();
+    }
+    LMPH(4)
+    const double reg = S.reg;
+    // ---------------------------------------------------------------------------------------- phase D: frames out, S in
+    for (size_t idx = gthread; idx < (size_t)n_s * n_s; idx += gstride) {
+      const int i = idx / n_s, j = idx % n_s;
+      a.S[idx] = a.d[i] * a.d[j] * a.Hss[idx];
+    }
+    if (F > 0) {
+      double* Lw = work + (size_t)warp * (FB * FB + FB);
+      for (int f = gwarp; f < F; f += gwarps) schur_frame<FB>(a, f, reg, lane, Lw);
+    }
+    grid_barrier(a.bar, nblk);
+    // ---------------------------------------------------------------------------------------- phase E: S -= sum_f Y_f Y_f^T
+    LMPH(5)
+    if (F > 0 && n_s > 0) {
+      const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
+      const int npair = tiles * (tiles + 1) / 2;
+      for (int vb = blockIdx.x; vb < npair * a.syrk_chunks; vb += nblk) {
+        const int chunk = vb / npair; int pr = vb % npair;
+        int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
+        const int tj = ti + pr;
+        syrk_tile<FB>(a, ti, tj, chunk, work);
+      }
+      grid_barrier(a.bar, nblk);
+      // fixed-order sum over the frame chunks; tiles hold the upper triangle (ti <= tj), S is kept full
+      for (size_t idx = gthread; idx < (size_t)n_s * n_s; idx += gstride) {
+        const int i = idx / n_s, j = idx % n_s;
+        const int ii = min(i, j), jj = max(i, j);
+        // inside a diagonal tile both triangles were computed; everywhere else take the (ii, jj) entry
+        double s = 0.0;
+        for (int c = 0; c < a.syrk_chunks; c++) s += __ldcg(&a.Spart[(size_t)c * n_s * n_s + (size_t)ii * n_s + jj]);
+        a.S[idx] -= s;
+      }
+      for (int i = gthread; i < n_s; i += gstride) {
+        double s = 0.0;
+        for (int c = 0; c < a.syrk_chunks; c++) s += __ldcg(&a.rpart[(size_t)c * n_s + i]);
+        a.rhs[i] = -s;
+      }
+    } else {
+      for (int i = gthread; i < n_s; i += gstride) a.rhs[i] = 0.0;
+    }
+    grid_barrier(a.bar, nblk);
+    if (multi && n_s > 0) {
+      XSeg seg[2] = {{a.S, n_s * n_s, 0}, {a.rhs, n_s, 0}};
+      exchange(a, seg, 2, ++xseq, &xerr);
+    }
+    // ---------------------------------------------------------------------------------------- phase F: reduced solve
+    LMPH(6)
+    if (n_s > 0) {
+      if (n_s <= CHOL_SMALL_MAX) {
+        if (blockIdx.x == 0) {
+          const int R = (n_s + 15) / 16;
+#define CS(RR) case RR: chol_small_body<RR>(n_s, a.S, a.rhs, a.gh, reg, &chol_fail_s, a.gn, work); break;
+          switch (R) { CS(1) CS(2) CS(3) CS(4) CS(5) CS(6) CS(7) CS(8) }
+#undef CS
+        }
+      } else {
+        for (int i = gthread; i < n_s; i += gstride) a.S[(size_t)i * n_s + i] += reg;
+        grid_barrier(a.bar, nblk);
+        for (int kb = 0; kb < n_s; kb += CHOL_NB) {
+          if (blockIdx.x == 0) chol_diag_body(n_s, kb, a.S, a.Linv, &chol_fail_s, work);
+          grid_barrier(a.bar, nblk);
+          const int rem = n_s - kb - CHOL_NB;
+          if (rem > 0) {
+            const int t = (rem + 31) / 32;
+            for (int vb = blockIdx.x; vb < t; vb += nblk) chol_trsm_body(n_s, kb, vb, a.S, a.Linv, nullptr, work);
+            grid_barrier(a.bar, nblk);
+            const int ntile = t * (t + 1) / 2;
+            for (int vb = blockIdx.x; vb < ntile; vb += nblk) {
+              int ti = 0, pr = vb; while (pr > ti) { pr -= ti + 1; ti++; }        // lower triangle: ti >= tj = pr
+              chol_syrk_body(n_s, kb, ti, pr, a.S, work);
+            }
+            grid_barrier(a.bar, nblk);
+          }
+        }
+        if (blockIdx.x == 0) {
+          chol_substitute_body(n_s, a.S, a.Linv, a.rhs, a.gh, a.gn, work);
+        }
+      }
+    }
+    grid_barrier(a.bar, nblk);
+    // ---------------------------------------------------------------------------------------- phase G: back-substitution + subspace forms
+    LMPH(7)
+    for (int f = gwarp; f < F; f += gwarps) {
+      const double* Yf = a.Y + (size_t)f * n_s * FB;
+      double t[FB];
+#pragma unroll
+      for (int k = 0; k < FB; k++) t[k] = 0.0;
+      for (int s = lane; s < n_s; s += 32) {
+        const double ps = __ldcg(&a.gn[s]);
+#pragma unroll
+        for (int k = 0; k < FB; k++) t[k] += Yf[s * FB + k] * ps;
+      }
+#pragma unroll
+      for (int k = 0; k < FB; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+      }
+      if (lane == 0) {
+        const double* L = a.Lf + (size_t)f * FB * FB;
+        double y[FB];
+#pragma unroll
+        for (int i = 0; i < FB; i++) y[i] = a.zf[(size_t)f * FB + i] - t[i];
+#pragma unroll
+        for (int i = FB - 1; i >= 0; i--) {
+          double v = y[i];
+#pragma unroll
+          for (int k = 0; k < FB; k++) if (k > i) v -= L[k * FB + i] * y[k];
+          y[i] = v / L[i * FB + i];
+        }
+#pragma unroll
+        for (int i = 0; i < FB; i++) a.gn[n_s + FB * f + i] = y[i];
+      }
+      __syncwarp();
+    }
+    __syncthreads();      // a warp's gn_f stores are read by the same warp below (same frame -> same warp: gwarp stride is identical)
+    LMPH(8)
+    quad_pass(a.gh, a.gn, 1, a.part_quad + 8);
+    grid_barrier(a.bar, nblk);
+    {
+      double agn = sum_records(a.part_quad + 8, F + nsh, 5, 1, sm), ann = sum_records(a.part_quad + 8, F + nsh, 5, 2, sm);
+      double dtf = sum_records(a.part_quad + 8, F, 5, 3, sm), g2f = sum_records(a.part_quad + 8, F, 5, 4, sm);
+      const double dts = sum_records(a.part_quad + 8 + (size_t)F * 5, nsh, 5, 3, sm), g2s = sum_records(a.part_quad + 8 + (size_t)F * 5, nsh, 5, 4, sm);
+      if (multi) {
+        if (writer) { a.part_quad[0] = agn; a.part_quad[1] = ann; a.part_quad[2] = dtf; a.part_quad[3] = g2f; }
+        grid_barrier(a.bar, nblk);
+        XSeg seg[1] = {{a.part_quad, 4, 0}};
+        exchange(a, seg, 1, ++xseq, &xerr);
+        agn = __ldcg(&a.part_quad[0]); ann = __ldcg(&a.part_quad[1]); dtf = __ldcg(&a.part_quad[2]); g2f = __ldcg(&a.part_quad[3]);
+      }
+      if (tid == 0) {
+        double red[RED_COUNT];
+        red[RED_AGG] = S.agg; red[RED_AGN] = agn; red[RED_ANN] = ann;
+        red[RED_DOTGN_S] = dts; red[RED_DOTGN_F] = dtf; red[RED_GN2_S] = g2s; red[RED_GN2_F] = g2f;
+        subspace_compute(&S, red);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------ phase I: step and trial state
+  LMPH(9)
+  if (tid == 0) tr_step_compute(&S);
+  __syncthreads();
+  {
+    const double al = S.alpha, be = S.beta;
+    double s2s = 0, s2f = 0, x2s = 0, x2f = 0;
+    for (int i = gthread; i < n; i += gstride) {
+      const double stp = a.d[i] * (al * a.gh[i] + be * __ldcg(&a.gn[i]));
+      const double xi = a.x[i];
+      a.x_new[i] = xi + stp;
+      if (i < n_s) { s2s += stp * stp; x2s += xi * xi; } else { s2f += stp * stp; x2f += xi * xi; }
+    }
+    // the shared entries are few (n_s): every CTA sums them itself (replicated); the frame parts go to per-CTA records for the next launch
+    double ss = 0, xs = 0;
+    for (int i = tid; i < n_s; i += LM_THREADS) {
+      const double stp = a.d[i] * (al * a.gh[i] + be * __ldcg(&a.gn[i]));
+      const double xi = __ldcg(&a.x[i]);                   // copied by another CTA in phase A of this launch
+      ss += stp * stp; xs += xi * xi;
+    }
+    ss = block_sum_all(ss, sm); xs = block_sum_all(xs, sm);
+    const double r0 = block_sum_all(s2f, sm), r1 = block_sum_all(x2f, sm);
+    (void)s2s; (void)x2s;
+    if (tid == 0) { a.part_step[(size_t)blockIdx.x * 2] = r0; a.part_step[(size_t)blockIdx.x * 2 + 1] = r1; S.step2_s = ss; S.xn2_s = xs; S.step_parts = nblk; S.pending = 1; }
+  }
+  grid_barrier(a.bar, nblk);
+  for (int i = gthread; i < a.n_items; i += gstride)
+    make_trial_item(a.P, a.x_new, a.cam_rt2, a.board_rt2, a.frame_rt2, a.intr2, a.board_pts2, a.he_rt2, i);
+  __syncthreads();
+  if (writer) {
+    if (xerr) { S.done = 1; S.status = -3; }
+    S.chol_fail += chol_fail_s;
+    *a.st = S;
+    if (multi) *a.peer.seq = xseq;
+    if (a.use_cond) cudaGraphSetConditional((cudaGraphConditionalHandle)a.cond_handle, S.done ? 0 : 1);
+  }
+}
+
+}  // namespace mcba

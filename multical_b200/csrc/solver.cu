@@ -15,9 +15,9 @@
 #include "../../include/mcba.h"
 #include "solver_kernels.cuh"
 #include "linearize.cuh"
+#include "lm_kernel.cuh"
 #include "pack_kernels.cuh"
 #include "table_kernels.cuh"
-#include "peer_allreduce.cuh"
 #include "pnp_kernels.cuh"
 
 using namespace mcba;
@@ -83,11 +83,6 @@ struct mcba_ctx {
   int launches = 0;
   bool solving = false;   // inside mcba_solve (the fp32-Hessian candidate is never used by the parity hooks)
   int num_sms = 148;
-  bool use_mma = true;    // per-view moments on the fp64 tensor path (MCBA_MOMENTS=fma selects the DFMA kernels)
-  bool moments_f32 = false;    // MCBA_MOMENTS=f32: k_views_f32 (Hessian moments in FP32, gradient / cost in FP64) where it applies; A/B candidate
-  bool expand_par = false;     // MCBA_EXPAND=parallel: the per-view twist maps of the expand kernels computed by the whole warp; A/B candidate
-  bool fuse = false;           // MCBA_FUSE=1: k_dots folded into k_quad, k_step + k_make_trial as one launch; A/B candidate
-  bool chol_blocked = false;   // MCBA_CHOL=blocked: single-CTA blocked reduced solve (k_chol_blocked) instead of k_chol_small; A/B candidate
 
   bool uploaded = false;
   DeviceProblem P{};
@@ -104,16 +99,25 @@ struct mcba_ctx {
   // solver buffers
   DevBuf<double> moments, Hss, g, Hff, W, cost_part, view_cost, diag_s;
   // fused linearisation (linearize.cuh): per-(CTA, camera) records of the shared blocks, per-camera board partials, per-frame costs
-  DevBuf<double> spart, bpart, frame_cost;
+  DevBuf<double> spart, bpart, frame_cost, sred;
+  DevBuf<unsigned> cam_counter;
+  // device-resident trust-region loop (lm_kernel.cuh)
+  DevBuf<double> Spart, rpart, part_scale, part_quad, part_step;
+  DevBuf<unsigned long long> lm_bar, peer_seq_dev;
+  DevBuf<mcba_log_row> dev_log;
+  int lm_grid = 1, syrk_chunks = 1, syrk_cf = 8;
+  bool use_graph = true;       // MCBA_GRAPH=0: the host launches one loop body at a time and reads the state after each
+  struct SolveGraph { cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr; std::vector<char> key; cudaStream_t stream = nullptr; int body_launches = 0; } sg;
+  bool graph_launched = false;
   int lin_grid = 1, lin_split = 1;
   bool fused_lin = true;       // false for hand-eye frames: per-view moment records + the round-1 expand kernels (they carry the 12 shared motion parameters)
-  DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, quad_part, Linv;
+  DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, Linv;
   DevBuf<SolverState> state;
   DevBuf<unsigned> counter;
   int shared_chunks = 1;
   int cur_loss = 0; double cur_f_scale = 1.0;     // loss of the linearisation in flight (k_point_blocks re-derives the row weights)
   // peer-memory all-reduce (peer_allreduce.cuh)
-  double* peer_own = nullptr; int peer_cap = 0; bool peer_ready = false; unsigned peer_seq = 0;
+  double* peer_own = nullptr; int peer_cap = 0; bool peer_ready = false;
   double* peer_base[PEER_MAX_WORLD] = {nullptr};
   std::vector<void*> peer_opened;
   std::vector<int> perm;   // internal index -> canonical param_vec index
@@ -149,53 +153,6 @@ struct mcba_ctx {
   do { if (!(cond)) { ctx->err = msg; return code; } } while (0)
 
 namespace {
-
-// One exchange step = up to PEER_MAX_SEG (buffer, count, op) segments reduced across ranks.  Over NVLink peer memory when
-// the communicator has peer buffers and the payload fits a slot (one kernel, ~one-way latency); NCCL otherwise.
-struct Exchange {
-  PeerSeg seg[PEER_MAX_SEG]; int n = 0; int epilogue = 0;
-  void add(double* buf, size_t count, int op) { if (count) { seg[n].buf = buf; seg[n].count = (int)count; seg[n].op = op; n++; } }
-};
-int run_exchange(mcba_ctx* ctx, const Exchange& ex) {
-  if (ctx->world == 1) return MCBA_OK;
-  size_t total = 0;
-  for (int i = 0; i < ex.n; i++) total += ex.seg[i].count;
-  if (ctx->peer_ready && total > 0 && total <= (size_t)ctx->peer_cap && (!ex.epilogue || total <= 256)) {
-    PeerArgs a{};
-    for (int i = 0; i < ex.n; i++) a.seg[i] = ex.seg[i];
-    a.nseg = ex.n; a.rank = ctx->rank; a.world = ctx->world; a.cap = ctx->peer_cap; a.seq = ++ctx->peer_seq;
-    for (int r = 0; r < ctx->world; r++) a.base[r] = ctx->peer_base[r];
-    a.counter = ctx->counter.p + 1;
-    a.epilogue = ex.epilogue; a.st = ctx->state.p; a.red = ctx->red.p;
-    const int blocks = (int)std::min<size_t>(32, (total + 255) / 256);
-    k_peer_allreduce<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(a); CKL();
-    return MCBA_OK;
-  }
-  if (g_nccl.GroupStart) g_nccl.GroupStart();
-  int rc = 0;
-  for (int i = 0; i < ex.n && rc == 0; i++)
-    rc = g_nccl.AllReduce(ex.seg[i].buf, ex.seg[i].buf, ex.seg[i].count, NCCL_FLOAT64, ex.seg[i].op == 0 ? NCCL_SUM : NCCL_MAX, ctx->comm, ctx->stream);
-  if (g_nccl.GroupEnd) g_nccl.GroupEnd();
-  if (rc != 0) { ctx->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); return MCBA_ERR_NCCL; }
-  if (ex.epilogue) { k_epilogue<<<1, 1, 0, ctx->stream>>>(ex.epilogue, ctx->state.p, ctx->red.p); CKL(); }
-  return MCBA_OK;
-}
-// The same exchange as the TAIL of the kernel that produces its values (MCBA_FUSE=1, peer buffers, small payload): fills the argument
-// block and consumes the sequence number; false = use run_exchange after the kernel as before.
-bool tail_exchange(mcba_ctx* ctx, const Exchange& ex, PeerArgs* out) {
-  size_t total = 0;
-  for (int i = 0; i < ex.n; i++) total += ex.seg[i].count;
-  if (!(ctx->fuse && ctx->world > 1 && ctx->peer_ready && total > 0 && total <= (size_t)ctx->peer_cap && total <= 4096)) return false;
-  PeerArgs a{};
-  for (int i = 0; i < ex.n; i++) a.seg[i] = ex.seg[i];
-  a.nseg = ex.n; a.rank = ctx->rank; a.world = ctx->world; a.cap = ctx->peer_cap; a.seq = ++ctx->peer_seq;
-  for (int r = 0; r < ctx->world; r++) a.base[r] = ctx->peer_base[r];
-  a.counter = ctx->counter.p + 1;
-  a.epilogue = ex.epilogue; a.st = ctx->state.p; a.red = ctx->red.p;
-  *out = a;
-  return true;
-}
-#define EXCHANGE(...) do { if (ctx->world > 1) { Exchange ex_; __VA_ARGS__; int r_ = run_exchange(ctx, ex_); if (r_) return r_; } } while (0)
 
 int nparts_for(int model) { return model == MODEL_STANDARD ? 2 : model == MODEL_RATIONAL ? 3 : model == MODEL_THIN_PRISM ? 4 : model == MODEL_TILTED ? 5 : 2; }
 
@@ -234,61 +191,29 @@ int launch_views(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a)
   const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
   const int th = VIEW_WARPS * 32;
   cudaStream_t s = ctx->stream;
-#define LV(MODEL, PART, NP) k_views<MODEL, MODE, PART, NP><<<blocks, th, 0, s>>>(P, a); CKL();
-#define LR(MODEL) k_views<MODEL, MODE, 0, 1, true><<<blocks, th, 0, s>>>(P, a); CKL();
-  if constexpr (MODE != MODE_MOMENTS) {
-    if (P.motion == MOTION_ROLLING) {
-      switch (P.model) {
-        case MODEL_STANDARD: LR(MODEL_STANDARD) break;
-        case MODEL_RATIONAL: LR(MODEL_RATIONAL) break;
-        case MODEL_THIN_PRISM: LR(MODEL_THIN_PRISM) break;
-        case MODEL_TILTED: LR(MODEL_TILTED) break;
-        default: LR(MODEL_FISHEYE) break;
-      }
-      return MCBA_OK;
-    }
-    switch (P.model) {
-      case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 1) break;
-      case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 1) break;
-      case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM, 0, 1) break;
-      case MODEL_TILTED: LV(MODEL_TILTED, 0, 1) break;
-      default: LV(MODEL_FISHEYE, 0, 1) break;
-    }
-  } else {
-    if (P.motion == MOTION_ROLLING) { ctx->err = "rolling frames are only linearised on the DMMA path (unset MCBA_MOMENTS=fma)"; return MCBA_ERR_UNSUPPORTED; }
-    switch (P.model) {
-      case MODEL_STANDARD: LV(MODEL_STANDARD, 0, 2) LV(MODEL_STANDARD, 1, 2) break;
-      case MODEL_RATIONAL: LV(MODEL_RATIONAL, 0, 3) LV(MODEL_RATIONAL, 1, 3) LV(MODEL_RATIONAL, 2, 3) break;
-      case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM, 0, 4) LV(MODEL_THIN_PRISM, 1, 4) LV(MODEL_THIN_PRISM, 2, 4) LV(MODEL_THIN_PRISM, 3, 4) break;
-      case MODEL_TILTED: ctx->err = "the tilted model is only available on the DMMA path (unset MCBA_MOMENTS=fma)"; return MCBA_ERR_UNSUPPORTED;
-      default: LV(MODEL_FISHEYE, 0, 2) LV(MODEL_FISHEYE, 1, 2) break;
-    }
+#define LV(MODEL) if (P.motion == MOTION_ROLLING) k_views<MODEL, MODE, true><<<blocks, th, 0, s>>>(P, a); else k_views<MODEL, MODE, false><<<blocks, th, 0, s>>>(P, a);
+  switch (P.model) {
+    case MODEL_STANDARD: LV(MODEL_STANDARD) break;
+    case MODEL_RATIONAL: LV(MODEL_RATIONAL) break;
+    case MODEL_THIN_PRISM: LV(MODEL_THIN_PRISM) break;
+    case MODEL_TILTED: LV(MODEL_TILTED) break;
+    default: LV(MODEL_FISHEYE) break;
   }
 #undef LV
-#undef LR
+  CKL();
   return MCBA_OK;
 }
 
+// per-view moment records (hand-eye frames only: the fused pass of linearize.cuh covers static and rolling frames)
 int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& a) {
-  if (!ctx->use_mma) return launch_views<MODE_MOMENTS>(ctx, P, a);
-  if (ctx->moments_f32 && ctx->solving && P.motion != MOTION_ROLLING && (P.model == MODEL_STANDARD || P.model == MODEL_FISHEYE)) {
-    // only inside mcba_solve: the parity hook mcba_linearize always returns the fp64 normal equations
-    const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
-    if (P.model == MODEL_STANDARD) k_views_f32<MODEL_STANDARD><<<blocks, VIEW_WARPS * 32, 0, ctx->stream>>>(P, a);
-    else k_views_f32<MODEL_FISHEYE><<<blocks, VIEW_WARPS * 32, 0, ctx->stream>>>(P, a);
-    CKL();
-    return MCBA_OK;
-  }
   const int th = VIEW_WARPS * 32;
-  const bool roll = P.motion == MOTION_ROLLING;
-  const int nc = mma_nc(P.model, roll), npair = (nc / 8) * (nc / 8 + 1) / 2;
+  const int nc = mma_nc(P.model, false), npair = (nc / 8) * (nc / 8 + 1) / 2;
   const size_t sm = ((size_t)VIEW_WARPS * nc * MMA_KPAD + (size_t)VIEW_WARPS * (2 * npair + 1) * 32) * sizeof(double);
   cudaStream_t s = ctx->stream;
-  // few long views (cfg2: 800 views of ~200 corners): let the 4 warps of a CTA share one view
+  // few long views: let the 4 warps of a CTA share one view
   const bool split = P.V < ctx->num_sms * 16;
   const int blocks = split ? std::max(1, P.V) : std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 16));
-#define LM(MODEL) if (roll) { if (split) k_views_mma<MODEL, VIEW_WARPS, true><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1, true><<<blocks, th, sm, s>>>(P, a); } \
-                  else { if (split) k_views_mma<MODEL, VIEW_WARPS><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1><<<blocks, th, sm, s>>>(P, a); }
+#define LM(MODEL) if (split) k_views_mma<MODEL, VIEW_WARPS><<<blocks, th, sm, s>>>(P, a); else k_views_mma<MODEL, 1><<<blocks, th, sm, s>>>(P, a);
   switch (P.model) {
     case MODEL_STANDARD: LM(MODEL_STANDARD) break;
     case MODEL_RATIONAL: LM(MODEL_RATIONAL) break;
@@ -300,7 +225,6 @@ int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& 
   CKL();
   return MCBA_OK;
 }
-
 
 // ---------------------------------------------------------------- fused linearisation (linearize.cuh)
 template <int MODEL, bool ROLL>
@@ -343,10 +267,11 @@ int launch_linearize(mcba_ctx* ctx, const DeviceProblem& P, int loss, double f_s
 // per-CTA records -> H_ss, g_s, cost (stores, fixed summation order)
 int launch_reduce_shared(mcba_ctx* ctx, const DeviceProblem& P) {
   ReduceArgs r{}; r.spart = ctx->spart.p; r.nparts = P.F > 0 ? ctx->lin_grid : 0; r.Hss = ctx->Hss.p; r.g = ctx->g.p; r.bpart = ctx->bpart.p;
-  r.frame_cost = ctx->frame_cost.p; r.F = P.F; r.cost_out = ctx->red.p + RED_COST; r.counter = ctx->counter.p + 3;
+  r.frame_cost = ctx->frame_cost.p; r.F = P.F; r.cost_out = ctx->red.p + RED_COST; r.cam_counter = ctx->cam_counter.p; r.sred = ctx->sred.p;
   const size_t sm = sizeof(double) * reduce_smem_doubles(P.T, P.D, P.B);
-  if (P.motion == MOTION_ROLLING) k_reduce_shared<2><<<P.C, RED_THREADS, sm, ctx->stream>>>(P, r);
-  else k_reduce_shared<1><<<P.C, RED_THREADS, sm, ctx->stream>>>(P, r);
+  const int grid = P.C * reduce_slices(lin_record_doubles(P.T, P.D, P.B));
+  if (P.motion == MOTION_ROLLING) k_reduce_shared<2><<<grid, RED_THREADS, sm, ctx->stream>>>(P, r);
+  else k_reduce_shared<1><<<grid, RED_THREADS, sm, ctx->stream>>>(P, r);
   CKL();
   return MCBA_OK;
 }
@@ -376,88 +301,41 @@ int set_state_from_x(mcba_ctx* ctx, const double* x, bool trial) {
   return prepare(ctx, P);
 }
 
-size_t expand_frames_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * expf_warp_doubles(P.T, P.D, P.B, P.npf) + EXP_WARPS * (P.fb * P.fb + P.fb)); }
 size_t expand_shared_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exps_warp_doubles(P.T, P.D, P.B, P.npf) + P.T + 36); }
 size_t expand_hand_eye_smem(const DeviceProblem& P) { return sizeof(double) * ((size_t)EXP_WARPS * exph_warp_doubles(P.T, P.D, P.B)); }
 
 // per-view moment records of the (trial or current) state; the pose tables must already describe that state
-int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial, bool accept_tail = false) {
+int moments_at(mcba_ctx* ctx, int loss, double f_scale, bool trial) {
   ctx->cur_loss = loss; ctx->cur_f_scale = f_scale;
   DeviceProblem P = with_state(ctx, trial);
   if (ctx->fused_lin) return launch_linearize(ctx, P, loss, f_scale);
   ViewKernelArgs a{}; a.loss = loss; a.f_scale = f_scale; a.moments = ctx->moments.p; a.view_cost = ctx->view_cost.p;
-  if (accept_tail) { a.acc_st = ctx->state.p; a.acc_red = ctx->red.p; a.acc_counter = ctx->counter.p + 2; }
   return launch_moments(ctx, P, a);
 }
 
-// moment records -> H_ss, g, H_ff, W and the per-CTA cost partials (pose tables = the state the moments were taken at)
-// scale_first >= 0 (MCBA_FUSE=1, single GPU): the Jacobian scaling / begin-of-iteration step (k_scale) runs as the tail of
-// k_expand_shared when that is the last kernel adding to H_ss; returns through *scaled whether it did
-int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
-  DeviceProblem P = with_state(ctx, false);
-  SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p, 0};
+// records of the fused pass (or, hand-eye frames, per-view moment records) -> H_ss, g_s [, H_ff, W, g_f] and the cost partials;
+// pose tables = the state the pass ran at (trial: the trial parameter arrays)
+int expand(mcba_ctx* ctx, bool trial = false) {
+  DeviceProblem P = with_state(ctx, trial);
   cudaStream_t s = ctx->stream;
+  const bool roll = P.motion == MOTION_ROLLING;
   if (ctx->fused_lin) {
-    if (scaled) *scaled = false;
     if (P.off_pt >= 0) {       // boards=True: k_point_blocks adds the point rows / columns on top (atomics): they start at zero
       CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
       CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n_s, 1), s));
     }
     int r = launch_reduce_shared(ctx, P); if (r) return r;
-    if (P.off_pt >= 0 && P.V > 0) {
-      const bool roll = P.motion == MOTION_ROLLING;
-      ViewKernelArgs a{}; a.loss = ctx->cur_loss; a.f_scale = ctx->cur_f_scale;
-      const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
-#define PB(MODEL) if (roll) k_point_blocks<MODEL, 2><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); \
-                  else k_point_blocks<MODEL, 1><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p);
-      switch (P.model) {
-        case MODEL_STANDARD: PB(MODEL_STANDARD) break;
-        case MODEL_RATIONAL: PB(MODEL_RATIONAL) break;
-        case MODEL_THIN_PRISM: PB(MODEL_THIN_PRISM) break;
-        case MODEL_TILTED: PB(MODEL_TILTED) break;
-        default: PB(MODEL_FISHEYE) break;
-      }
-#undef PB
-      CKL();
-    }
-    return MCBA_OK;
-  }
-  sb.zero_shared = (ctx->fuse && P.motion_on && P.F > 0) ? 1 : 0;         // cleared by k_expand_frames itself
-  if (!sb.zero_shared) {
+  } else {
+    SolverBuffers sb{ctx->moments.p, ctx->Hss.p, ctx->g.p, ctx->Hff.p, ctx->W.p, ctx->cost_part.p, 0};
     CK(cudaMemsetAsync(ctx->Hss.p, 0, sizeof(double) * (size_t)P.n_s * P.n_s, s));
     CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), s));
-  }
-  const bool roll = P.motion == MOTION_ROLLING;
-  if (P.motion_on && P.F > 0) {
-    if (ctx->expand_par) {
-      if (roll) k_expand_frames<2, true><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
-      else k_expand_frames<1, true><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
-    } else {
-      if (roll) k_expand_frames<2><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
-      else k_expand_frames<1><<<P.F, EXP_THREADS, expand_frames_smem(P), s>>>(P, sb);
+    const int nb = P.C * ctx->shared_chunks;
+    k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
+    if (P.off_he >= 0 && P.V > 0) {         // hand-eye: the 12 shared motion parameters and their couplings on top (atomics)
+      k_expand_hand_eye<<<nb, EXP_THREADS, expand_hand_eye_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
     }
-    CKL();
   }
-  const int nb = P.C * ctx->shared_chunks;
-  ScaleEpilogue ep{};
-  if (scale_first >= 0 && P.off_he < 0 && P.off_pt < 0 && P.n > 0) {
-    ep.enabled = 1; ep.n = P.n; ep.first = scale_first; ep.n_cost_part = nb; ep.fb = std::max(P.fb, 1);
-    ep.x = ctx->x.p; ep.Hff = ctx->Hff.p; ep.cost_part = ctx->cost_part.p;
-    ep.sinv = ctx->sinv.p; ep.d = ctx->d.p; ep.gh = ctx->gh.p; ep.red = ctx->red.p; ep.st = ctx->state.p; ep.counter = ctx->counter.p + 3;
-  }
-  if (scaled) *scaled = ep.enabled != 0;
-  if (ctx->expand_par) {
-    if (roll) k_expand_shared<2, true><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
-    else k_expand_shared<1, true><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
-  } else {
-    if (roll) k_expand_shared<2><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
-    else k_expand_shared<1><<<nb, EXP_THREADS, expand_shared_smem(P), s>>>(P, sb, ctx->shared_chunks, ep);
-  }
-  CKL();
-  if (P.off_he >= 0 && P.V > 0) {         // hand-eye: the 12 shared motion parameters and their couplings on top (atomics)
-    k_expand_hand_eye<<<nb, EXP_THREADS, expand_hand_eye_smem(P), s>>>(P, sb, ctx->shared_chunks); CKL();
-  }
-  if (P.off_pt >= 0 && P.V > 0) {         // boards=True: board-point blocks on top (atomics)
+  if (P.off_pt >= 0 && P.V > 0) {           // boards=True: board-point blocks on top (atomics)
     ViewKernelArgs a{}; a.loss = ctx->cur_loss; a.f_scale = ctx->cur_f_scale;
     const int blocks = std::max(1, std::min((P.V + VIEW_WARPS - 1) / VIEW_WARPS, ctx->num_sms * 8));
 #define PB(MODEL) if (roll) k_point_blocks<MODEL, 2><<<blocks, VIEW_WARPS * 32, 0, s>>>(P, a, ctx->Hss.p, ctx->W.p, ctx->g.p); \
@@ -475,15 +353,18 @@ int expand(mcba_ctx* ctx, int scale_first = -1, bool* scaled = nullptr) {
   return MCBA_OK;
 }
 
-// cost sum, diag(H_ss) and their all-reduces as separate steps (multi-GPU path and the mcba_linearize hook)
+// the cost of the linearisation -> red[RED_COST] (the fused pass has it there already)
 int finish_linearization(mcba_ctx* ctx) {
-  const DeviceProblem& P = ctx->P;
-  cudaStream_t s = ctx->stream;
-  const int nb = P.C * ctx->shared_chunks;
-  if (!ctx->fused_lin) { k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL(); }      // fused: k_reduce_shared wrote it
-  if (P.n_s > 0) { k_diag<<<(P.n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, P.n_s, ctx->diag_s.p); CKL(); }
-  EXCHANGE(ex_.add(ctx->g.p, P.n_s, 0); ex_.add(ctx->diag_s.p, P.n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0));
+  if (!ctx->fused_lin) {
+    const int nb = ctx->P.C * ctx->shared_chunks;
+    k_sum_partials<<<1, 256, 0, ctx->stream>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL();
+  }
   return MCBA_OK;
+}
+
+// legacy (hand-eye) pass: the trial cost as a one-entry "per-frame cost" list for k_lm
+__global__ void k_copy_view_costs(const double* cost, double* frame_cost, int F) {
+  for (int f = 0; f < F; f++) frame_cost[f] = f == 0 ? *cost : 0.0;
 }
 
 int linearize(mcba_ctx* ctx, int loss, double f_scale) {
@@ -501,22 +382,122 @@ int trial_cost(mcba_ctx* ctx, int loss, double f_scale, bool trial, int slot) {
   return MCBA_OK;
 }
 
-// quadratic forms of the scaled Hessian; single-GPU: the last CTA also sums the partials and runs the scalar step that
-// consumes them (finalize 2 = reg, 3 = subspace); multi-GPU: sum only, the caller all-reduces and launches k_reg / k_subspace
-int quad_forms(mcba_ctx* ctx, const double* u, const double* v, int two, int finalize, bool dots = false, const PeerArgs& pa = PeerArgs{}) {
+// ---------------------------------------------------------------- the device-resident trust-region loop (lm_kernel.cuh)
+// trial parameter state := current state
+int copy_state_to_trial(mcba_ctx* ctx) {
   const DeviceProblem& P = ctx->P;
-  const int nframe = P.motion_on ? P.F : 0;
-  const int nsh = (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS;
-  const int fb = (nframe + QUAD_WARPS - 1) / QUAD_WARPS;
-  if (fb + nsh == 0) return MCBA_OK;
-#define QUAD_ARGS P.n_s, P.F, P.motion_on, ctx->Hss.p, ctx->Hff.p, ctx->W.p, ctx->d.p, u, v, two, ctx->quad_part.p, finalize, ctx->counter.p, ctx->red.p, ctx->state.p, pa
-#define QUAD_LAUNCH(FBV, DOTSV, XV) k_quad<FBV, DOTSV, XV><<<fb + nsh, QUAD_THREADS, 0, ctx->stream>>>(QUAD_ARGS)
-  const bool dt = dots && two, xc = finalize == 4;
-  if (P.fb == 12) { if (dt) { if (xc) QUAD_LAUNCH(12, true, true); else QUAD_LAUNCH(12, true, false); } else { if (xc) QUAD_LAUNCH(12, false, true); else QUAD_LAUNCH(12, false, false); } }
-  else            { if (dt) { if (xc) QUAD_LAUNCH(6, true, true); else QUAD_LAUNCH(6, true, false); } else { if (xc) QUAD_LAUNCH(6, false, true); else QUAD_LAUNCH(6, false, false); } }
-#undef QUAD_LAUNCH
-#undef QUAD_ARGS
+  cudaStream_t s = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->cam_rt2.p, ctx->cam_rt.p, sizeof(double) * P.C * 6, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(ctx->board_rt2.p, ctx->board_rt.p, sizeof(double) * P.B * 6, cudaMemcpyDeviceToDevice, s));
+  if (P.F && P.fb) CK(cudaMemcpyAsync(ctx->frame_rt2.p, ctx->frame_rt.p, sizeof(double) * P.F * P.fb, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(ctx->he_rt2.p, ctx->he_rt.p, sizeof(double) * 12, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(ctx->intr2.p, ctx->intr.p, sizeof(double) * P.C * P.kint, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(ctx->board_pts2.p, ctx->board_pts.p, sizeof(double) * P.B * P.P * 3, cudaMemcpyDeviceToDevice, s));
+  return MCBA_OK;
+}
+
+LmArgs make_lm_args(mcba_ctx* ctx, int log_cap) {
+  const DeviceProblem& P = ctx->P;
+  LmArgs a{};
+  a.P = P;
+  a.cam_rt2 = ctx->cam_rt2.p; a.board_rt2 = ctx->board_rt2.p; a.frame_rt2 = ctx->frame_rt2.p; a.intr2 = ctx->intr2.p;
+  a.board_pts2 = ctx->board_pts2.p; a.he_rt2 = ctx->he_rt2.p;
+  a.n = P.n; a.n_s = P.n_s; a.F = P.F; a.fb = P.fb;
+  a.n_items = P.C + P.B + P.F * P.npf + P.C + P.B * P.P + 2;
+  a.Hss = ctx->Hss.p; a.Hff = ctx->Hff.p; a.W = ctx->W.p; a.g = ctx->g.p;
+  a.frame_cost = ctx->frame_cost.p; a.lin_cost = ctx->red.p + RED_COST;
+  a.x = ctx->x.p; a.x_new = ctx->x_new.p; a.sinv = ctx->sinv.p; a.d = ctx->d.p; a.gh = ctx->gh.p; a.gn = ctx->gn.p;
+  a.Y = ctx->Y.p; a.Lf = ctx->Lf.p; a.zf = ctx->zf.p; a.S = ctx->S.p; a.rhs = ctx->rhs.p; a.Spart = ctx->Spart.p; a.rpart = ctx->rpart.p; a.Linv = ctx->Linv.p;
+  a.syrk_chunks = ctx->syrk_chunks; a.syrk_cf = ctx->syrk_cf;
+  a.part_scale = ctx->part_scale.p; a.part_quad = ctx->part_quad.p; a.part_step = ctx->part_step.p;
+  a.st = ctx->state.p; a.log = ctx->dev_log.p; a.log_cap = log_cap; a.bar = ctx->lm_bar.p;
+  a.peer.rank = ctx->rank; a.peer.world = ctx->world; a.peer.cap = ctx->peer_cap; a.peer.seq = ctx->peer_seq_dev.p;
+  a.peer.timeout_cycles = (long long)40e9;          // ~20 s at 2 GHz: a rank that left the solve must not hang its peers' GPUs
+  for (int r = 0; r < ctx->world && r < PEER_MAX_WORLD; r++) a.peer.base[r] = ctx->peer_base[r];
+  return a;
+}
+
+// The trial state's normal equations: fused pass (+ the kernels that add the board-point / hand-eye blocks), H_ss, g_s and the cost.
+// With hand-eye frames the pass is the round-1 pipeline (per-view moment records, then the expand kernels).
+int linearize_trial(mcba_ctx* ctx, int loss, double f_scale) {
+  int r = moments_at(ctx, loss, f_scale, true); if (r) return r;
+  r = expand(ctx, true); if (r) return r;
+  if (!ctx->fused_lin) {
+    const int nb = ctx->P.C * ctx->shared_chunks;
+    k_sum_partials<<<1, 256, 0, ctx->stream>>>(ctx->cost_part.p, nb, 1, 1, ctx->red.p + RED_COST); CKL();
+    k_copy_view_costs<<<1, 1, 0, ctx->stream>>>(ctx->red.p + RED_COST, ctx->frame_cost.p, ctx->P.F); CKL();
+  }
+  return MCBA_OK;
+}
+
+int launch_lm(mcba_ctx* ctx, const LmArgs& a) {
+  const size_t sm = sizeof(double) * lm_smem_doubles(ctx->P.n_s, ctx->P.fb);
+  LmArgs args = a;
+#ifdef MCBA_SIMT_BUILD
+  if (ctx->P.fb == 12) k_lm<12><<<ctx->lm_grid, LM_THREADS, sm, ctx->stream>>>(args); else k_lm<6><<<ctx->lm_grid, LM_THREADS, sm, ctx->stream>>>(args);
   CKL();
+#else
+  // cooperative launch: every CTA of the grid is resident for the whole kernel (the grid barriers spin)
+  void* params[] = {&args};
+  const void* fn = ctx->P.fb == 12 ? (const void*)k_lm<12> : (const void*)k_lm<6>;
+  CK(cudaLaunchCooperativeKernel(fn, dim3(ctx->lm_grid), dim3(LM_THREADS), params, sm, ctx->stream));
+  ctx->launches++;
+#endif
+  return MCBA_OK;
+}
+
+// one pass of the loop body: linearise the trial state, then accept / solve / step (k_lm)
+int lm_body(mcba_ctx* ctx, int loss, double f_scale, const LmArgs& a) {
+  int r = linearize_trial(ctx, loss, f_scale); if (r) return r;
+  return launch_lm(ctx, a);
+}
+
+int run_lm_loop(mcba_ctx* ctx, int loss, double f_scale, int log_cap) {
+  cudaStream_t s = ctx->stream;
+  LmArgs a = make_lm_args(ctx, log_cap);
+#ifndef MCBA_SIMT_BUILD
+  if (ctx->use_graph) {
+    // key of the cached graph: every launch parameter of the body (pointers, sizes, loss): the same problem solved again reuses it
+    std::vector<char> key(sizeof(LmArgs) + sizeof(int) * 4 + sizeof(double));
+    memcpy(key.data(), &a, sizeof(LmArgs));
+    { char* q = key.data() + sizeof(LmArgs); memcpy(q, &loss, 4); memcpy(q + 4, &ctx->lin_grid, 4); memcpy(q + 8, &ctx->lm_grid, 4); memcpy(q + 12, &ctx->lin_split, 4); memcpy(q + 16, &f_scale, 8); }
+    const int before = ctx->launches;
+    if (!ctx->sg.exec || ctx->sg.key != key || ctx->sg.stream != s) {
+      if (ctx->sg.exec) { cudaGraphExecDestroy(ctx->sg.exec); ctx->sg.exec = nullptr; }
+      if (ctx->sg.graph) { cudaGraphDestroy(ctx->sg.graph); ctx->sg.graph = nullptr; }
+      cudaGraph_t g; CK(cudaGraphCreate(&g, 0));
+      ctx->sg.graph = g;
+      cudaGraphConditionalHandle handle;
+      CK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+      cudaGraphNode_t node; CK(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      a.cond_handle = (unsigned long long)handle; a.use_cond = 1;
+      CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      int r = lm_body(ctx, loss, f_scale, a);
+      cudaError_t e = cudaStreamEndCapture(s, nullptr);
+      if (r) return r;
+      if (e != cudaSuccess) { ctx->err = std::string("graph capture of the loop body: ") + cudaGetErrorString(e); return MCBA_ERR_CUDA; }
+      CK(cudaGraphInstantiate(&ctx->sg.exec, g, 0));
+      ctx->sg.key = key; ctx->sg.stream = s;
+      ctx->sg.body_launches = ctx->launches - before;
+    }
+    ctx->launches = before;
+    CK(cudaGraphLaunch(ctx->sg.exec, s));
+    ctx->graph_launched = true;
+    return MCBA_OK;
+  }
+#endif
+  // host-driven loop (the SIMT interpreter build; MCBA_GRAPH=0): same kernels, one state read per body
+  ctx->graph_launched = false;
+  SolverState h{};
+  for (int it = 0; it < log_cap + 8; it++) {
+    int r = lm_body(ctx, loss, f_scale, a); if (r) return r;
+    CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h.done) break;
+  }
   return MCBA_OK;
 }
 
@@ -581,6 +562,8 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     REQUIRE(lin_smem_for(P, split) <= 220 * 1024, MCBA_ERR_UNSUPPORTED, "too many boards for the linearisation kernel's shared memory");
     CK(ctx->spart.alloc((size_t)ctx->lin_grid * C * lin_record_doubles(P.T, P.D, B)));
     CK(ctx->bpart.alloc((size_t)C * B * 42));
+    CK(ctx->sred.alloc((size_t)C * lin_record_doubles(P.T, P.D, B)));
+    CK(ctx->cam_counter.alloc((size_t)C + 1)); CK(cudaMemsetAsync(ctx->cam_counter.p, 0, sizeof(unsigned) * ((size_t)C + 1), ctx->stream));
     CK(ctx->frame_cost.alloc((size_t)std::max(F, 1)));
     CK(ctx->moments.alloc(1));
   } else {
@@ -601,7 +584,26 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(ctx->S.alloc((size_t)std::max(P.n_s, 1) * std::max(P.n_s, 1))); CK(ctx->rhs.alloc((size_t)std::max(P.n_s, 1)));
   CK(ctx->Linv.alloc((size_t)((std::max(P.n_s, 1) + CHOL_NB - 1) / CHOL_NB) * CHOL_NB * CHOL_NB));
   CK(ctx->red.alloc(RED_COUNT)); CK(cudaMemsetAsync(ctx->red.p, 0, sizeof(double) * RED_COUNT, ctx->stream));
-  CK(ctx->quad_part.alloc((size_t)(F + (P.n_s + QUAD_THREADS - 1) / QUAD_THREADS + 1) * 5));
+  // persistent trust-region kernel (lm_kernel.cuh): grid, frame chunks of the Schur SYRK, partial-sum records, barrier words
+  {
+    const int F_free = P.motion_on ? F : 0;
+    ctx->lm_grid = std::max(1, std::min(ctx->num_sms, std::max(4, (F_free + LM_WARPS - 1) / LM_WARPS + (int)(((size_t)P.n_s * P.n_s) / (LM_THREADS * 16)))));
+    const int fbq = std::max(P.fb, 6), fr = syrk_fr(fbq);
+    const int tiles = (std::max(P.n_s, 1) + SYRK_TILE - 1) / SYRK_TILE, npair = tiles * (tiles + 1) / 2;
+    int chunks = std::max(1, std::min((F_free + fr - 1) / fr, ctx->lm_grid / std::max(1, npair)));
+    const int cf = std::max(fr, ((std::max(F_free, 1) + chunks - 1) / chunks + fr - 1) / fr * fr);
+    chunks = std::max(1, (F_free + cf - 1) / cf);
+    ctx->syrk_chunks = chunks; ctx->syrk_cf = cf;
+    REQUIRE(sizeof(double) * lm_smem_doubles(P.n_s, P.fb) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "reduced system too large for the trust-region kernel's shared memory");
+    CK(ctx->Spart.alloc((size_t)chunks * std::max(P.n_s, 1) * std::max(P.n_s, 1)));
+    CK(ctx->rpart.alloc((size_t)chunks * std::max(P.n_s, 1)));
+    CK(ctx->part_scale.alloc((size_t)ctx->num_sms * 6));
+    CK(ctx->part_step.alloc((size_t)ctx->num_sms * 2));
+    CK(ctx->part_quad.alloc(8 + (size_t)(F + (P.n_s + LM_THREADS - 1) / LM_THREADS + 2) * 5));
+    CK(ctx->lm_bar.alloc(2)); CK(cudaMemsetAsync(ctx->lm_bar.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (!ctx->peer_seq_dev.p) { CK(ctx->peer_seq_dev.alloc(1)); CK(cudaMemsetAsync(ctx->peer_seq_dev.p, 0, sizeof(unsigned long long), ctx->stream)); }
+    CK(ctx->frame_cost.alloc((size_t)std::max(F, 1)));
+  }
   CK(ctx->state.alloc(1));
   CK(ctx->counter.alloc(8)); CK(cudaMemsetAsync(ctx->counter.p, 0, 8 * sizeof(unsigned), ctx->stream));
   if (!keep_state) {     // a re-selection of the resident table (mcba_table_select) keeps the parameter state
@@ -630,7 +632,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   P.cam_T = ctx->cam_T.p; P.frame_T = ctx->frame_T.p; P.board_T = ctx->board_T.p;
   P.img_h = ctx->img_h.p; P.he_rt = ctx->he_rt.p; P.he_T = ctx->he_T.p; P.arm_T = ctx->arm_T.p;
   REQUIRE(expand_hand_eye_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the hand-eye expand kernel");
-  REQUIRE(expand_frames_smem(P) <= 200 * 1024 && expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
+  REQUIRE(expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
   return MCBA_OK;
 }
 int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
@@ -703,42 +705,20 @@ int mcba_create(int device, mcba_ctx** out) {
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
-  { const char* e = getenv("MCBA_MOMENTS"); if (e && std::string(e) == "fma") ctx->use_mma = false; if (e && std::string(e) == "f32") ctx->moments_f32 = true; }
-  { const char* e = getenv("MCBA_CHOL"); if (e && std::string(e) == "blocked") ctx->chol_blocked = true; }
-  { const char* e = getenv("MCBA_FUSE"); if (e && std::string(e) == "1") ctx->fuse = true; }
-  { const char* e = getenv("MCBA_EXPAND"); if (e && std::string(e) == "parallel") ctx->expand_par = true; }
-  cudaFuncSetAttribute(k_expand_frames<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_frames<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_shared<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_shared<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_chol_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  { const char* e = getenv("MCBA_GRAPH"); if (e && std::string(e) == "0") ctx->use_graph = false; }
 #define MMA_ATTR(MODEL) \
   cudaFuncSetAttribute(k_views_mma<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
   cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
-  cudaFuncSetAttribute(k_views_mma<MODEL, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
-  cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  MMA_ATTR(MODEL_STANDARD) MMA_ATTR(MODEL_RATIONAL) MMA_ATTR(MODEL_THIN_PRISM) MMA_ATTR(MODEL_FISHEYE) MMA_ATTR(MODEL_TILTED)
-#undef MMA_ATTR
-#define LIN_ATTR(MODEL) \
   cudaFuncSetAttribute(k_linearize<MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
   cudaFuncSetAttribute(k_linearize<MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  LIN_ATTR(MODEL_STANDARD) LIN_ATTR(MODEL_RATIONAL) LIN_ATTR(MODEL_THIN_PRISM) LIN_ATTR(MODEL_FISHEYE) LIN_ATTR(MODEL_TILTED)
-#undef LIN_ATTR
+  MMA_ATTR(MODEL_STANDARD) MMA_ATTR(MODEL_RATIONAL) MMA_ATTR(MODEL_THIN_PRISM) MMA_ATTR(MODEL_FISHEYE) MMA_ATTR(MODEL_TILTED)
+#undef MMA_ATTR
   cudaFuncSetAttribute(k_reduce_shared<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_reduce_shared<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_frames<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_frames<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_shared<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_expand_shared<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_expand_hand_eye, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_chol_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-  cudaFuncSetAttribute(k_chol_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_lm<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_lm<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   *out = ctx;
   return MCBA_OK;
 }
@@ -747,6 +727,10 @@ void mcba_destroy(mcba_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+#ifndef MCBA_SIMT_BUILD
+  if (ctx->sg.exec) cudaGraphExecDestroy(ctx->sg.exec);
+  if (ctx->sg.graph) cudaGraphDestroy(ctx->sg.graph);
+#endif
   for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
   if (ctx->peer_own) cudaFree(ctx->peer_own);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
@@ -788,7 +772,7 @@ int mcba_comm_init(mcba_ctx* ctx, const char id_[128], int rank, int world) {
 int mcba_peer_export(mcba_ctx* ctx, int64_t cap_doubles, char out_handle[64]) {
   if (!ctx || !out_handle) return MCBA_ERR_ARG;
   REQUIRE(ctx->world > 1 && ctx->world <= PEER_MAX_WORLD, MCBA_ERR_STATE, "peer buffers need an initialised communicator with 2..16 ranks");
-  REQUIRE(cap_doubles > 0 && cap_doubles < ((int64_t)1 << 28), MCBA_ERR_ARG, "bad peer slot capacity");
+  REQUIRE(cap_doubles > 0 && cap_doubles < ((int64_t)1 << 30), MCBA_ERR_ARG, "bad peer slot capacity");
   REQUIRE(sizeof(cudaIpcMemHandle_t) == 64, MCBA_ERR_UNSUPPORTED, "unexpected cudaIpcMemHandle_t size");
   CK(cudaSetDevice(ctx->device));
   if (ctx->peer_own) { cudaFree(ctx->peer_own); ctx->peer_own = nullptr; }
@@ -814,7 +798,9 @@ int mcba_peer_import(mcba_ctx* ctx, const char* handles /* world x 64 bytes, ran
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     ctx->peer_base[r] = (double*)p; ctx->peer_opened.push_back(p);
   }
-  ctx->peer_seq = 0;
+  // sequence number of the in-kernel exchanges (lm_kernel.cuh): starts at zero on every rank, advanced on the device
+  CK(ctx->peer_seq_dev.alloc(1));
+  CK(cudaMemset(ctx->peer_seq_dev.p, 0, sizeof(unsigned long long)));
   ctx->peer_ready = true;
   return MCBA_OK;
 }
@@ -1488,261 +1474,70 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   REQUIRE(opts->loss >= 0 && opts->loss <= 4, MCBA_ERR_ARG, "unknown loss");
   REQUIRE(opts->max_nfev > 0, MCBA_ERR_ARG, "max_nfev must be positive");
   REQUIRE(opts->f_scale > 0, MCBA_ERR_ARG, "f_scale must be positive");
+  REQUIRE(ctx->world == 1 || ctx->peer_ready, MCBA_ERR_STATE, "several ranks: the exchanges run over NVLink peer memory (mcba_peer_export / mcba_peer_import first)");
   CK(cudaSetDevice(ctx->device));
   const DeviceProblem& P = ctx->P;
   cudaStream_t s = ctx->stream;
-  const int n = P.n, n_s = P.n_s, F = P.motion_on ? P.F : 0;
+  const int n = P.n;
   memset(result, 0, sizeof(*result));
   struct SolvingFlag { bool& f; explicit SolvingFlag(bool& r) : f(r) { f = true; } ~SolvingFlag() { f = false; } } solving_flag(ctx->solving);
   ctx->launches = 0;
   ctx->errors_current = false;
+  ctx->cur_loss = opts->loss; ctx->cur_f_scale = opts->f_scale;
   struct EventPair {       // destroyed on every return path
     cudaEvent_t a = nullptr, b = nullptr;
     ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
   } ev;
   CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
-  cudaEvent_t ev0 = ev.a, ev1 = ev.b;
-  CK(cudaEventRecord(ev0, s));
+  CK(cudaEventRecord(ev.a, s));
 
   SolverState h{};
   h.ftol = opts->ftol; h.xtol = opts->xtol; h.gtol = opts->gtol; h.reg_floor = 1e-12; h.max_nfev = opts->max_nfev;
   h.nfev = 1; h.njev = 1; h.iteration = 0; h.status = -99; h.first_scale = 1;
-  CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   int r;
-  // x0 from the current state
-  if (n) { k_gather_params<<<(n + 255) / 256, 256, 0, s>>>(P, ctx->x.p, P.cam_rt, P.board_rt, P.frame_rt, P.intr); CKL(); }
-  r = prepare(ctx, with_state(ctx, false)); if (r) return r;
-  const bool single = ctx->world == 1;
-  const bool fuse_tails = ctx->fuse && single;          // k_scale / k_accept as tails of k_expand_shared / the moment kernel
-  bool scale_done = false;                              // the scaling of the linearisation in flight already ran as a tail
-  r = moments_at(ctx, opts->loss, opts->f_scale, false); if (r) return r;
-  r = expand(ctx, fuse_tails ? 1 : -1, &scale_done); if (r) return r;
-
-  // One host synchronisation per trial step: everything from the Jacobian scaling to the acceptance test of the next
-  // trial point is queued behind the previous step; k_begin_iteration's `done` flag turns the tail into no-ops.
-  const int ncp = ctx->fused_lin ? 0 : P.C * ctx->shared_chunks;      // fused linearisation: the cost is already summed (k_reduce_shared)
-  double last_reduction = NAN, last_step = NAN;
-  int nlog = 0;
-  int first = 1;
-  bool finished = false;
   if (n == 0) {      // nothing to optimise: report the cost and leave
-    r = finish_linearization(ctx); if (r) return r;
+    r = prepare(ctx, with_state(ctx, false)); if (r) return r;
+    r = linearize(ctx, opts->loss, opts->f_scale); if (r) return r;
+    if (ctx->world > 1) {       // one number: the host's collective is the simplest exchange (no solver state involved)
+      ctx->err = "nothing to optimise on several ranks: sum mcba_residuals' cost on the host"; return MCBA_ERR_UNSUPPORTED;
+    }
     CK(cudaMemcpyAsync(&h.cost, ctx->red.p + RED_COST, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    result->initial_cost = h.cost; h.status = 1; finished = true;
-    if (log && log_capacity > 0) { log[0] = mcba_log_row{0, 1, h.cost, NAN, NAN, 0.0}; nlog = 1; }
+    result->initial_cost = h.cost; result->cost = h.cost; result->nfev = 1; result->njev = 1; result->status = 1;
+    if (log && log_capacity > 0) { log[0] = mcba_log_row{0, 1, h.cost, NAN, NAN, 0.0}; result->n_log = 1; }
+    CK(cudaEventRecord(ev.b, s)); CK(cudaEventSynchronize(ev.b));
+    float ms0 = 0; cudaEventElapsedTime(&ms0, ev.a, ev.b);
+    result->device_ms = ms0; result->kernel_launches = ctx->launches;
+    return MCBA_OK;
   }
-  PeerArgs scale_pa{};
-  bool lin_current = true;        // H, g describe the current x (false after a rejected last trial: the fused pass overwrote the frame blocks)
-  while (!finished) {
-    if (!lin_current) {
-      // nothing to rescale: the loop is about to end (rejected step and no evaluations / a termination test fired); the gradient norm of the unchanged x is in the state
-    } else if (single && scale_done) {
-      scale_done = false;                               // done by the tail of k_expand_shared
-    } else if (single) {
-      k_scale<<<1, 1024, 0, s>>>(n, n_s, nullptr, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
-                                 1, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1)); CKL();
-    } else if (ctx->fuse && [&] {
-                 Exchange ex_; ex_.add(ctx->g.p, n_s, 0); ex_.add(ctx->diag_s.p, n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0);
-                 ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1);
-                 return tail_exchange(ctx, ex_, &scale_pa); }()) {
-      // cost sum, diag(H_ss), the frame part of the scaling, the exchange and the shared part + begin_iteration: one single-CTA launch
-      k_scale_exchange<<<1, 1024, 0, s>>>(n, n_s, ctx->Hss.p, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first,
-                                          ctx->red.p, ctx->cost_part.p, ncp, ctx->state.p, std::max(P.fb, 1), scale_pa); CKL();
-    } else if (ctx->fuse) {
-      // one exchange instead of two: the frame parts of the scaling sums only need local data and travel with g_s / diag / cost
-      k_sum_partials<<<1, 256, 0, s>>>(ctx->cost_part.p, ncp, 1, 1, ctx->red.p + RED_COST); CKL();
-      if (n_s > 0) { k_diag<<<(n_s + 127) / 128, 128, 0, s>>>(ctx->Hss.p, n_s, ctx->diag_s.p); CKL(); }
-      k_scale_part<<<1, 1024, 0, s>>>(1, n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
-                                      ctx->state.p, std::max(P.fb, 1)); CKL();
-      EXCHANGE(ex_.add(ctx->g.p, n_s, 0); ex_.add(ctx->diag_s.p, n_s, 0); ex_.add(ctx->red.p + RED_COST, 1, 0);
-               ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1));
-      k_scale_part<<<1, 1024, 0, s>>>(2, n, n_s, ctx->diag_s.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
-                                      ctx->state.p, std::max(P.fb, 1)); CKL();
-    } else {
-      r = finish_linearization(ctx); if (r) return r;
-      k_scale<<<1, 1024, 0, s>>>(n, n_s, ctx->diag_s.p, ctx->Hss.p, ctx->Hff.p, ctx->g.p, ctx->x.p, ctx->sinv.p, ctx->d.p, ctx->gh.p, first, ctx->red.p,
-                                 0, nullptr, 0, ctx->state.p, std::max(P.fb, 1)); CKL();
-      EXCHANGE(ex_.add(ctx->red.p + RED_GH2_F, 2, 0); ex_.add(ctx->red.p + RED_GMAX_F, 1, 1); ex_.epilogue = EPI_BEGIN);
-    }
-    first = 0;
-    if (h.status != -99 || h.nfev >= h.max_nfev) {
-      // the host already knows this is the last pass of the outer loop (termination test fired or out of evaluations):
-      // only the gradient norm of the final point is still needed for the last table row
-      if (lin_current) {
-        CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-      }
-      if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; return MCBA_ERR_NONFINITE; }
-      if (h.iteration == 0) result->initial_cost = h.cost;
-      if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.nfev, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
-      finished = true;
-      break;
-    }
+  CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  // x0 and the trial state := the current state; its pose tables
+  k_gather_params<<<(n + 255) / 256, 256, 0, s>>>(P, ctx->x.p, P.cam_rt, P.board_rt, P.frame_rt, P.intr); CKL();
+  CK(cudaMemcpyAsync(ctx->x_new.p, ctx->x.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  r = copy_state_to_trial(ctx); if (r) return r;
+  r = prepare(ctx, with_state(ctx, true)); if (r) return r;
+  const int cap = std::max(8, opts->max_nfev + 4);
+  CK(ctx->dev_log.alloc((size_t)cap));
 
-    {
-      PeerArgs pa{}; Exchange ex_; ex_.add(ctx->red.p + RED_AGG, 1, 0); ex_.epilogue = EPI_REG;
-      if (!single && (n_s > 0 || F > 0) && tail_exchange(ctx, ex_, &pa)) {           // reduction -> all-reduce -> reg, one launch
-        r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, 4, false, pa); if (r) return r;
-      } else {
-        r = quad_forms(ctx, ctx->gh.p, ctx->gh.p, 0, single ? 2 : 1); if (r) return r;
-        EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 1, 0); ex_.epilogue = EPI_REG);
-      }
-    }
-    // Schur complement of the frame blocks
-    if (n_s > 0 && F == 0) {
-      const size_t nn2 = (size_t)n_s * n_s;
-      k_schur_init<<<(unsigned)((nn2 + 255) / 256), 256, 0, s>>>(n_s, ctx->Hss.p, ctx->d.p, ctx->S.p, ctx->rhs.p); CKL();
-    }
-    if (F > 0) {
-      if (P.fb == 12) k_schur_frames<12><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p,
-                                                                      ctx->Hss.p, ctx->S.p, ctx->rhs.p);
-      else k_schur_frames<6><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Hff.p, ctx->W.p, ctx->d.p, ctx->gh.p, ctx->state.p, ctx->Y.p, ctx->Lf.p, ctx->zf.p,
-                                                         ctx->Hss.p, ctx->S.p, ctx->rhs.p);
-      CKL();
-      if (n_s > 0) {
-        const int SYRK_FR = syrk_fr(P.fb);
-        const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
-        int chunks = std::max(1, std::min((F + SYRK_FR - 1) / SYRK_FR, (ctx->num_sms * 4) / std::max(1, tiles * (tiles + 1) / 2)));
-        const int cf = ((F + chunks - 1) / chunks + SYRK_FR - 1) / SYRK_FR * SYRK_FR;
-        chunks = (F + cf - 1) / cf;
-        if (P.fb == 12) k_schur_syrk<12><<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p, ctx->zf.p, ctx->rhs.p);
-        else k_schur_syrk<6><<<dim3(tiles, tiles, chunks), 256, 0, s>>>(n_s, F, cf, ctx->Y.p, ctx->S.p, ctx->zf.p, ctx->rhs.p);
-        CKL();
-      }
-    }
-    if (n_s > 0) {
-      EXCHANGE(ex_.add(ctx->S.p, (size_t)n_s * n_s, 0); ex_.add(ctx->rhs.p, n_s, 0));
-      if (n_s <= CHOL_SMALL_MAX && ctx->chol_blocked) {
-        k_chol_blocked<<<1, 256, chol_blocked_smem_doubles(n_s) * sizeof(double), s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); CKL();
-      } else if (n_s <= CHOL_SMALL_MAX) {
-        const size_t sm = ((size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2) * sizeof(double);
-        const int R = (n_s + 15) / 16;
-#define CS(RR) case RR: k_chol_small<RR><<<1, CHOL_SMALL_THREADS, sm, s>>>(n_s, ctx->S.p, ctx->rhs.p, ctx->gh.p, ctx->state.p, ctx->gn.p); break;
-        switch (R) { CS(1) CS(2) CS(3) CS(4) CS(5) CS(6) CS(7) CS(8) }
-#undef CS
-        CKL();
-      } else {
-        k_chol_addreg<<<(n_s + 127) / 128, 128, 0, s>>>(n_s, ctx->S.p, ctx->state.p); CKL();
-        for (int kb = 0; kb < n_s; kb += CHOL_NB) {
-          k_chol_diag<<<1, 256, 0, s>>>(n_s, kb, ctx->S.p, ctx->Linv.p, ctx->state.p); CKL();
-          const int rem = n_s - kb - CHOL_NB;
-          if (rem > 0) {
-            const int t = (rem + 31) / 32;
-            k_chol_trsm<<<t, 256, 0, s>>>(n_s, kb, ctx->S.p, ctx->Linv.p); CKL();
-            k_chol_syrk<<<dim3(t, t), 256, 0, s>>>(n_s, kb, ctx->S.p); CKL();
-          }
-        }
-        const int nblk = (n_s + CHOL_NB - 1) / CHOL_NB;
-        k_chol_substitute<<<1, 512, (size_t)nblk * CHOL_NB * sizeof(double), s>>>(n_s, ctx->S.p, ctx->Linv.p, ctx->rhs.p, ctx->gh.p, ctx->gn.p); CKL();
-      }
-    }
-    if (F > 0) {
-      if (P.fb == 12) k_backsub<12><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p);
-      else k_backsub<6><<<F, SCHUR_THREADS, 0, s>>>(n_s, ctx->Y.p, ctx->Lf.p, ctx->zf.p, ctx->gn.p);
-      CKL();
-    }
-    // with no quadratic-form CTA at all (n == 0 is handled above; n_s == 0 and no frames cannot happen here) k_dots stays
-    const bool fuse_dots = ctx->fuse && (n_s > 0 || F > 0);
-    if (!fuse_dots) { k_dots<<<1, 1024, 0, s>>>(n, n_s, ctx->gh.p, ctx->gn.p, ctx->red.p); CKL(); }
-    {
-      PeerArgs pa{}; Exchange ex_; ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE;   // AGG AGN ANN DOTGN_F GN2_F
-      if (!single && fuse_dots && tail_exchange(ctx, ex_, &pa)) {
-        r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, 4, true, pa); if (r) return r;
-      } else {
-        r = quad_forms(ctx, ctx->gh.p, ctx->gn.p, 1, single ? 3 : 1, fuse_dots); if (r) return r;
-        EXCHANGE(ex_.add(ctx->red.p + RED_AGG, 5, 0); ex_.epilogue = EPI_SUBSPACE);
-      }
-    }
+  r = run_lm_loop(ctx, opts->loss, opts->f_scale, cap); if (r) return r;
 
-    // inner loop: shrink the radius until the cost decreases (trf.py).  The trial point is linearised speculatively:
-    // its moment records give the cost for the acceptance test and, if accepted, the next normal equations.
-    bool accepted = false, top_logged = false;
-    while (true) {
-      const int nt = P.C + P.B + P.F * P.npf + P.C + P.B * P.P + 2;
-      if (ctx->fuse) {
-        k_step_trial<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p,
-                                        ctx->P, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p, ctx->he_rt2.p, nt); CKL();
-      } else {
-        k_step<<<1, 1024, 0, s>>>(n, n_s, ctx->state.p, ctx->x.p, ctx->d.p, ctx->gh.p, ctx->gn.p, ctx->x_new.p, ctx->red.p); CKL();
-        k_make_trial<<<(nt + 127) / 128, 128, 0, s>>>(ctx->P, ctx->x_new.p, ctx->cam_rt2.p, ctx->board_rt2.p, ctx->frame_rt2.p, ctx->intr2.p, ctx->board_pts2.p, ctx->he_rt2.p); CKL();
-      }
-      const bool accept_tail = fuse_tails && ctx->use_mma;
-      r = moments_at(ctx, opts->loss, opts->f_scale, true, accept_tail); if (r) return r;
-      if (accept_tail) {
-        // the acceptance test ran as the tail of the moment kernel
-      } else if (single) {
-        // per-view costs: compact array written by the DMMA kernel, or the last entry of each moment record (DFMA kernels)
-        if (ctx->fused_lin) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->frame_cost.p, P.F, 1);
-        else if (ctx->use_mma) k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->view_cost.p, P.V, 1);
-        else k_accept<<<1, 1024, 0, s>>>(ctx->state.p, ctx->red.p, ctx->moments.p + (P.T - 1), P.V, P.T);
-        CKL();
-      } else {
-        PeerArgs pa{}; Exchange exa; exa.add(ctx->red.p + RED_COSTNEW, 3, 0); exa.epilogue = EPI_ACCEPT;   // COSTNEW STEP2_F XN2_F
-        const bool tail = tail_exchange(ctx, exa, &pa);
-        if (ctx->fused_lin) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->frame_cost.p, P.F, 1, ctx->red.p, pa);
-        else if (ctx->use_mma) k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->view_cost.p, P.V, 1, ctx->red.p, pa);
-        else k_cost_from_moments<<<1, 1024, 0, s>>>(ctx->moments.p + (P.T - 1), P.V, P.T, ctx->red.p, pa);
-        CKL();
-        if (!tail) EXCHANGE(ex_.add(ctx->red.p + RED_COSTNEW, 3, 0); ex_.epilogue = EPI_ACCEPT);
-      }
-      CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      if (!top_logged) {      // the row scipy prints at the top of this outer iteration
-        if (!std::isfinite(h.cost)) { ctx->err = "Residuals are not finite in the initial point."; return MCBA_ERR_NONFINITE; }
-        if (h.iteration == 0) result->initial_cost = h.cost;
-        if (log && nlog < log_capacity) { log[nlog] = mcba_log_row{h.iteration, h.done ? h.nfev : h.nfev - 1, h.cost, last_reduction, last_step, h.g_norm}; nlog++; }
-        top_logged = true;
-      }
-      if (h.done) { finished = true; break; }
-      accepted = h.accepted != 0;
-      if (h.status != -99) break;
-      if (accepted || h.nfev >= h.max_nfev) break;
-    }
-    if (finished) break;
-    bool state_sent = false;
-    if (accepted) {
-      // x = x_new ; cost = cost_new ; J = jac(x)   (trf.py): the trial state, its pose tables and its moments become current
-      std::swap(ctx->x.p, ctx->x_new.p);
-      std::swap(ctx->cam_rt.p, ctx->cam_rt2.p); std::swap(ctx->board_rt.p, ctx->board_rt2.p);
-      std::swap(ctx->frame_rt.p, ctx->frame_rt2.p); std::swap(ctx->intr.p, ctx->intr2.p); std::swap(ctx->board_pts.p, ctx->board_pts2.p);
-      std::swap(ctx->he_rt.p, ctx->he_rt2.p); ctx->P.he_rt = ctx->he_rt.p;
-      ctx->P.board_pts = ctx->board_pts.p;
-      ctx->P.cam_rt = ctx->cam_rt.p; ctx->P.board_rt = ctx->board_rt.p; ctx->P.frame_rt = ctx->frame_rt.p; ctx->P.intr = ctx->intr.p;
-      h.cost = h.cost_new;
-      h.njev += 1;
-      last_reduction = h.actual_reduction; last_step = h.step_norm;
-      if (fuse_tails) {
-        // the tail of k_expand_shared runs begin_iteration on the device state: the host's copy has to be there first
-        h.iteration += 1; h.accepted = 0;
-        CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-        state_sent = true;
-      }
-      r = expand(ctx, fuse_tails ? 0 : -1, &scale_done); if (r) return r;
-    } else {
-      last_reduction = 0.0; last_step = 0.0;
-      if (ctx->fused_lin) lin_current = false;
-      if (h.status == -99 && h.nfev >= h.max_nfev) {
-        // out of evaluations on a rejected step: the pose tables describe the rejected point, restore them
-        r = prepare(ctx, with_state(ctx, false)); if (r) return r;
-      }
-    }
-    if (!state_sent) {
-      h.iteration += 1;
-      h.accepted = 0;
-      CK(cudaMemcpyAsync(ctx->state.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    }
-  }
-  if (!finished || n > 0) {
-    // leave the context consistent: pose tables of the final (current) state
-    r = prepare(ctx, with_state(ctx, false)); if (r) return r;
-  }
-
-  CK(cudaEventRecord(ev1, s));
-  CK(cudaEventSynchronize(ev1));
-  float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+  CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h.status == -2) { ctx->err = "Residuals are not finite in the initial point."; return MCBA_ERR_NONFINITE; }
+  if (h.status == -3) { ctx->err = "a peer rank did not answer an in-kernel exchange (timeout): the ranks left mcba_solve out of step"; return MCBA_ERR_NCCL; }
+  const int nlog = std::min(h.nlog, cap);
+  std::vector<mcba_log_row> rows((size_t)std::max(nlog, 1));
+  if (nlog > 0) CK(cudaMemcpyAsync(rows.data(), ctx->dev_log.p, sizeof(mcba_log_row) * nlog, cudaMemcpyDeviceToHost, s));
+  // leave the context consistent: pose tables of the final (current) state
+  r = prepare(ctx, with_state(ctx, false)); if (r) return r;
+  CK(cudaEventRecord(ev.b, s));
+  CK(cudaEventSynchronize(ev.b));
+  float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
+  if (nlog > 0) result->initial_cost = rows[0].cost;
+  if (log) for (int i = 0; i < nlog && i < log_capacity; i++) log[i] = rows[(size_t)i];
   result->cost = h.cost; result->optimality = h.g_norm; result->nfev = h.nfev; result->njev = h.njev;
-  result->status = h.status == -99 ? 0 : h.status; result->n_log = nlog; result->device_ms = ms;
+  result->status = h.status == -99 ? 0 : h.status; result->n_log = std::min(nlog, (int)log_capacity); result->device_ms = ms;
+  if (ctx->graph_launched) ctx->launches += ctx->sg.body_launches * h.nfev;      // the WHILE node ran the body once per evaluation
   result->kernel_launches = ctx->launches; result->chol_retries = h.chol_fail;
   return MCBA_OK;
 }
@@ -1753,7 +1548,7 @@ int mcba_bench_info(mcba_ctx* ctx, int which, int64_t* corners, int64_t* bytes, 
   const DeviceProblem& P = ctx->P;
   const int np = nparts_for(P.model);
   int64_t per_corner = 18, per_view = 16, l = 1;
-  if (which == MCBA_BENCH_LINEARIZE) { l = ctx->use_mma ? 1 : np; }
+  if (which == MCBA_BENCH_LINEARIZE) { l = 1; (void)np; }
   else if (which == MCBA_BENCH_RESIDUAL) { per_corner = 18 + 4 + 16; }
   if (corners) *corners = P.N;
   if (bytes) *bytes = per_corner * P.N + per_view * P.V;      // per LAUNCH (each PART re-reads the corners)

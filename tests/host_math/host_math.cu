@@ -3,7 +3,6 @@
 // against cv2, Rodrigues / twist maps against finite differences, the 2-D trust-region solve against scipy).
 // Not part of libmcba.so and never loaded by multical_b200.
 #include "solver_kernels.cuh"
-#include "peer_allreduce.cuh"      // defines peer_allreduce_block, which kernels of solver_kernels.cuh call
 #include "pnp_kernels.cuh"
 
 using namespace mcba;

@@ -10,12 +10,18 @@
 #include <string>
 #include "simt.h"
 
+#define MCBA_SIMT_BUILD 1      // solver.cu: plain launches instead of cooperative launches / CUDA graphs (host-driven loop)
+
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
 struct CUstream_st;
 typedef CUstream_st* cudaStream_t;
 struct SimtEvent { std::chrono::steady_clock::time_point t; };
 typedef SimtEvent* cudaEvent_t;
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+typedef unsigned long long cudaGraphConditionalHandle;
+static inline void cudaGraphSetConditional(cudaGraphConditionalHandle, unsigned) {}
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaStreamNonBlocking = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };

@@ -30,7 +30,7 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-struct double2 { double x, y; };
+struct alignas(16) double2 { double x, y; };      // 16-byte vector accesses fault on hardware when misaligned: let the host build use aligned moves too
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct int2 { int x, y; };
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
@@ -55,6 +55,7 @@ struct Fiber {
   int wait = WAIT_NONE;
   unsigned wait_gen = 0;
   unsigned xcount = 0;
+  int mark = 0;                 // debugging aid: set by set_mark(), reported with a deadlock
   char* stack = nullptr;
 };
 struct Block {
@@ -76,6 +77,7 @@ static thread_local const void* cur_body = nullptr;
 static thread_local void (*cur_invoke)(const void*) = nullptr;
 static thread_local const char* cur_name = "";
 static thread_local long long total_launches = 0;
+inline void set_mark(int m);
 // per-kernel dynamic counts (SIMT_STATS=<file>: appended at process exit): launches, block barriers completed, warp collectives
 // (shuffles / ballots / mma fragments exchanged) -- the serialisation points of a kernel, independent of any clock
 struct KernelStats { long long launches = 0, blocks = 0, block_barriers = 0, warp_collectives = 0; };
@@ -101,6 +103,7 @@ inline void dump_stats() {
   abort();
 }
 inline void yield() { swapcontext(&cur->ctx, &sched_ctx); }
+inline void set_mark(int m) { if (cur) cur->mark = m; }
 inline void spin_yield() { if (cur) yield(); }          // stays runnable: the scheduler comes back to it after the other fibers
 
 inline void block_barrier() {
@@ -168,7 +171,7 @@ inline void run_block() {
     Fiber& f = fibers[i];
     f.tid.x = i % blk.bdim.x; f.tid.y = (i / blk.bdim.x) % blk.bdim.y; f.tid.z = i / (blk.bdim.x * blk.bdim.y);
     f.lane = i & 31; f.warp = &warps[i >> 5];
-    f.done = false; f.wait = WAIT_NONE; f.xcount = 0;
+    f.done = false; f.wait = WAIT_NONE; f.xcount = 0; f.mark = 0;
     f.stack = stack_of(i);
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = STACK_BYTES; f.ctx.uc_link = nullptr;
@@ -202,7 +205,18 @@ inline void run_block() {
       progress = true;
       if (f.done) remaining--;
     }
-    if (!progress) die("deadlock: every live thread waits on a barrier that cannot complete");
+    if (!progress) {
+      // who waits where: block barrier (arrived / alive) and every warp's barrier
+      fprintf(stderr, "[simt] block barrier: %d arrived of %d alive\n", blk.arrived, blk.alive);
+      for (int w = 0; w < nw; w++) {
+        int nb = 0, nwp = 0, nd = 0;
+        for (int i = 32 * w; i < std::min(n, 32 * w + 32); i++) { if (fibers[i].done) nd++; else if (fibers[i].wait == WAIT_BLOCK) nb++; else if (fibers[i].wait == WAIT_WARP) nwp++; }
+        fprintf(stderr, "[simt]   warp %d: %d at the block barrier, %d at a warp barrier / collective, %d finished; marks:", w, nb, nwp, nd);
+        for (int i = 32 * w; i < std::min(n, 32 * w + 32); i++) fprintf(stderr, " %d%s", fibers[i].mark, fibers[i].wait == WAIT_WARP ? "w" : "");
+        fprintf(stderr, "\n");
+      }
+      die("deadlock: every live thread waits on a barrier that cannot complete");
+    }
   }
   cur = nullptr;
 }
@@ -250,7 +264,8 @@ inline void launch(const char* name, dim3 grid, dim3 block, size_t smem, const F
   // Blocks run one after the other, so a block that spins on a flag another block of the same launch publishes would never return.
   // k_peer_allreduce (csrc/peer_allreduce.cuh) is such a kernel and is written grid-size agnostic (grid-stride loops, "last block"
   // by counter): the interpreter runs it with ONE block; its spin on the flags of the OTHER ranks is served by their host threads.
-  if (strstr(name, "k_peer_allreduce")) grid = dim3(1);
+  // k_lm (csrc/lm_kernel.cuh) walks virtual blocks between grid barriers and is grid-size agnostic the same way.
+  if (strstr(name, "k_lm")) grid = dim3(1);
   blk.nthreads = (int)n; blk.bdim = block; blk.gdim = grid;
   std::vector<unsigned char> dyn(smem + 64);
   blk.dyn = (unsigned char*)(((uintptr_t)dyn.data() + 63) & ~(uintptr_t)63);
@@ -371,6 +386,7 @@ template <class T> static inline T __ldcv(const T* p) { return *(const volatile 
 
 // blocks run one after the other and fibers only switch at barriers / collectives, so plain read-modify-write is atomic
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+static inline long long clock64() { return 0; }
 static inline unsigned atomicAdd(unsigned* p, int v) { unsigned o = *p; *p = o + (unsigned)v; return o; }
 template <class T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
