@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py — reprojection residuals/sec and LM iterations/sec of the bundle-adjustment hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4] [--impl ours|reference]
 
-One "step" = one full `bundle_adjust()` (calibration.py:199-212 semantics: ftol=1e-4, max_nfev=100, linear
-loss) over one synthetic scene of the BASELINE.json configuration `--workload` (default cfg2 = configs[1],
-4 cameras x 200 frames x charuco_16x22, ~160k corners).  Metric (both arms, same definition):
+One "step" = one full `bundle_adjust()` (calibration.py:199-212 semantics: ftol=1e-4, max_nfev=100, linear loss) over one
+synthetic scene of the BASELINE.json configuration `--workload`.  Default workload at EVERY N: cfg4 = configs[3] (16 cameras x
+1000 frames x 5 cube boards, 5.5 M corners) -- the largest configuration that fits one GPU and the one BASELINE names for 2/4/8
+GPUs; with N > 1 the SAME scene is sharded by frame (strong scaling), and rank 0 also solves it alone and asserts that the sharded
+solve ends at the same cost.  Secondary blocks in the same JSON line: cfg2 and cfg3 at N = 1, weak scaling (cfg2 per GPU) at N > 1.
+Metric (both arms, same definition):
     residuals/s = N_corners * (nfev + njev) / time      1 residual = one inlier corner (2 scalars),
-    nfev/njev = cost and Jacobian evaluations as the solver reports them (scipy's res.nfev/res.njev for the
-    reference arm; its finite-difference sub-evaluations are NOT counted, they are an artefact of its Jacobian).
-`value`  : solves timed on the device with the packed problem already resident in HBM (CUDA events).
-`e2e`    : the same through the public API `Calibration.bundle_adjust()` from host numpy buffers: packing,
-           H2D, solve, D2H of the parameter vector all inside the timed region (wall clock, device synced).
-`--impl reference` times the reference's CPU algorithm (oracle/ba_oracle.py: dense numpy evaluate + the identical
-scipy.optimize.least_squares call) on a bounded frame-subsample of the same workload.
+    nfev/njev = cost and Jacobian evaluations as the solver reports them (scipy's res.nfev/res.njev for the reference arm; its
+    finite-difference sub-evaluations are NOT counted, they are an artefact of its Jacobian).
+`value`  : solves timed on the device with the packed problem already resident in HBM (CUDA events on the solver's stream).
+`e2e`    : the same through the public API `Calibration.bundle_adjust()` from pinned host numpy buffers: packing, H2D, solve, D2H of
+           the solved parameters all inside the timed region (wall clock, device synchronised).
+`--impl reference` times the reference's CPU path on the host cores on a bounded frame-subsample of the same workload: the
+unmodified reference (through tests/refshim) where /root/reference exists (the build container), else its numpy + scipy restatement
+oracle/ba_oracle.py (the GPU box: the reference is pure Python and cannot travel); `cpu_baseline.kind` says which.
 """
 import argparse
 import json
@@ -30,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC, UNIT = "reprojection_residuals_per_sec", "residuals/s"
 BA_KW = dict(tolerance=1e-4, max_iterations=100, loss="linear", f_scale=1.0)
+REF_FRAMES = {"cfg1": 20, "cfg2": 20, "cfg3": 12, "cfg4": 4, "cfg5": 2}      # CPU sample: ~10-40 s of scipy TRF + finite differences
 
 
 def subsample_frames(scene, frames):
@@ -42,15 +47,53 @@ def subsample_frames(scene, frames):
   return s
 
 
-def cpu_reference_step(scene):
-  """One bundle_adjust of the reference algorithm (oracle port) on the host cores."""
+def reference_available():
+  return os.path.isdir("/root/reference/multical")
+
+
+def cpu_reference_step(scene, use_reference):
+  """One bundle_adjust of the reference's CPU path on the host cores: (residuals/s, seconds, nfev, njev, corners, kind)."""
+  if use_reference:
+    sys.path.insert(0, os.path.join(ROOT, "tests", "refshim"))
+    import loader
+    ref = loader.load()
+    calib = loader.build_calibration(ref, scene).enable(cameras=True)
+    n = int(calib.inliers.sum())
+    count = {"n": 0}
+    import scipy.optimize as so
+    real = so.least_squares
+    res_box = {}
+    def spy(*a, **k):
+      r = real(*a, **k); res_box["r"] = r; return r
+    so.least_squares = spy                    # only to read res.nfev / res.njev: the reference discards the result object
+    try:
+      t = time.perf_counter()
+      calib.bundle_adjust(tolerance=BA_KW["tolerance"], max_iterations=BA_KW["max_iterations"], loss=BA_KW["loss"])      # incl. its sparsity_matrix build
+      dt = time.perf_counter() - t
+    finally:
+      so.least_squares = real
+    r = res_box["r"]
+    return n * (r.nfev + r.njev) / dt, dt, int(r.nfev), int(r.njev), n, "reference"
   from oracle.ba_oracle import Problem
   prob = Problem.from_scene(scene, optimize=dict(cameras=True))
   t = time.perf_counter()
   _, res = prob.bundle_adjust(tolerance=BA_KW["tolerance"], max_iterations=BA_KW["max_iterations"], loss=BA_KW["loss"])
   dt = time.perf_counter() - t
   n = int(prob.inliers.sum())
-  return n * (res.nfev + res.njev) / dt, dt, res, n
+  return n * (res.nfev + res.njev) / dt, dt, int(res.nfev), int(res.njev), n, "port"
+
+
+def cpu_baseline_block(scene, workload, frames):
+  """The CPU baseline on the first `frames` frames of the workload, after a small warm-up call (imports, caches)."""
+  use_ref = reference_available()
+  nf = min(scene["F"], frames)
+  cpu_reference_step(subsample_frames(scene, np.arange(min(2, nf))), use_ref)
+  v, dt, nfev, njev, n, kind = cpu_reference_step(subsample_frames(scene, np.arange(nf)), use_ref)
+  what = ("unmodified reference Calibration.bundle_adjust through tests/refshim (incl. its sparsity_matrix build)" if kind == "reference"
+          else "oracle/ba_oracle.py: numpy restatement of evaluate + the identical scipy.optimize.least_squares call (the reference is absent on this box)")
+  return dict(value=v, unit=UNIT, cores=1, kind=kind,
+              sample=f"{workload}: first {nf} of {scene['F']} frames ({n} corners), one full bundle_adjust ({nfev} nfev, {njev} njev, {dt:.1f} s); "
+                     f"{what}; host has {os.cpu_count()} cores, the scipy/numpy path is single threaded"), dt, nfev, njev, n
 
 
 class ClockSampler(threading.Thread):
@@ -122,23 +165,30 @@ def run_reference(args):
   if rank != 0:
     return
   scene = synthetic.make_workload(args.workload, seed=args.seed)
-  nf = min(scene["F"], args.ref_frames)
+  frames = args.ref_frames or REF_FRAMES.get(args.workload, 4)
+  use_ref = reference_available()
+  nf = min(scene["F"], frames)
   sample = subsample_frames(scene, np.arange(nf))
-  for _ in range(args.warmup):
-    cpu_reference_step(subsample_frames(scene, np.arange(min(4, nf))))
+  for _ in range(max(1, min(args.warmup, 2))):
+    cpu_reference_step(subsample_frames(scene, np.arange(min(2, nf))), use_ref)
   tot_res, tot_t, nfev, njev = 0.0, 0.0, 0, 0
+  t_start = time.perf_counter()
+  steps_done = 0
   for _ in range(args.steps):
-    v, dt, res, n = cpu_reference_step(sample)
-    tot_res += n * (res.nfev + res.njev); tot_t += dt; nfev += res.nfev; njev += res.njev
+    v, dt, nf_, nj_, n, kind = cpu_reference_step(sample, use_ref)
+    tot_res += n * (nf_ + nj_); tot_t += dt; nfev += nf_; njev += nj_; steps_done += 1
+    if time.perf_counter() - t_start > args.ref_budget_s: break          # bounded: the whole run ends within minutes
   value = tot_res / tot_t
-  line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-              ms_per_step=1e3 * tot_t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+  what = "unmodified reference through tests/refshim" if kind == "reference" else "oracle/ba_oracle.py (numpy + the identical scipy call)"
+  line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps_done, warmup=args.warmup,
+              ms_per_step=1e3 * tot_t / steps_done, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
               data="synthetic", impl="reference",
-              config=dict(workload=args.workload, sample=f"first {nf} of {scene['F']} frames, full bundle_adjust per step", corners=n),
+              config=dict(workload=args.workload, sample=f"first {nf} of {scene['F']} frames, full bundle_adjust per step", corners=n,
+                          steps_requested=args.steps, steps_run=steps_done, budget_s=args.ref_budget_s),
               lm_iters_per_sec=njev / tot_t,
-              cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind="port",
-                                sample=f"{args.workload}: first {nf} of {scene['F']} frames ({n} corners), scipy TRF+LSMR with 2-point FD Jacobian, "
-                                       f"host has {os.cpu_count()} cores, numpy/scipy path is single threaded"),
+              cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind=kind,
+                                sample=f"{args.workload}: first {nf} of {scene['F']} frames ({n} corners), {what}: scipy TRF + LSMR with 2-point "
+                                       f"finite-difference Jacobian; host has {os.cpu_count()} cores, the numpy/scipy path is single threaded"),
               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
   emit(line)
 
@@ -148,6 +198,7 @@ def run_ours(args):
   import torch.distributed as dist
   from multical_b200 import synthetic
   from multical_b200.calibration import from_scene, get_engine
+  from multical_b200.engine import Engine
   from multical_b200 import distributed as mdist
 
   rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -156,139 +207,164 @@ def run_ours(args):
   os.environ["MCBA_DEVICE"] = str(local)
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-  # weak scaling: every rank holds the workload's frame count; cameras/boards (shared parameters) are common
-  base = dict(synthetic.WORKLOADS[args.workload])
-  scene = synthetic.make_scene(seed=args.seed, **{**base, "F": base["F"] * world})
-  F_total = scene["F"]
-  my_frames = mdist.frame_range(F_total, rank, world)
-  local_scene = subsample_frames(scene, np.arange(*my_frames)) if world > 1 else scene
-  # the step's inputs live in pinned host memory (the e2e timed region copies them to the device every step)
-  for key in ("points", "valid"):
-    pinned = torch.from_numpy(np.ascontiguousarray(local_scene[key])).pin_memory()
-    local_scene[key] = pinned.numpy()
-  calib = from_scene(local_scene).enable(cameras=True)
-  eng = get_engine(local)
   stream = torch.cuda.current_stream()
-  eng.lib.mcba_set_stream(eng.h, stream.cuda_stream)
-  if world > 1:
-    mdist.init_comm(eng, rank, world)
-  n_local = int(calib.inliers.sum())
-  n_total = n_local
-  if world > 1:
-    t = torch.tensor([n_local], dtype=torch.int64, device="cuda"); dist.all_reduce(t); n_total = int(t.item())
-
   flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-  state0 = calib._state_arrays()
+  peak, peak_src = measured_peak()
+  NO_PREPARE = 256
 
   def barrier():
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
 
-  # ---- device-resident solves ------------------------------------------------------------------
-  calib._upload(calib.inliers)
-  def solve_resident():
-    eng.set_params(*state0)
-    flush.zero_()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    res = eng.solve(ftol=BA_KW["tolerance"], max_nfev=BA_KW["max_iterations"], loss=BA_KW["loss"], f_scale=BA_KW["f_scale"])
-    e1.record(stream); e1.synchronize()
-    return res, e0.elapsed_time(e1)
-  for _ in range(args.warmup): solve_resident()
-  sampler = ClockSampler(local); sampler.start()
-  barrier()
-  t_dev, evals, njev, launches = 0.0, 0, 0, 0
-  for _ in range(args.steps):
-    res, ms = solve_resident()
-    t_dev += ms; evals += res.nfev + res.njev; njev += res.njev; launches += res.kernel_launches
-  barrier()
-  tt = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
-  if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-  t_dev = float(tt.item())
-  value = n_total * evals / (t_dev * 1e-3)
+  def allmax(x):
+    tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
 
-  # ---- end to end through the public API ---------------------------------------------------------
-  def solve_e2e():
-    c = from_scene(local_scene).enable(cameras=True)      # fresh object: nothing cached on host or device
-    t0 = time.perf_counter()
-    out = c.bundle_adjust(**BA_KW)          # returns after the device->host read of the solved parameter vector
-    _ = out.last_solve.cost
-    torch.cuda.synchronize()
-    return out.last_solve, time.perf_counter() - t0
-  for _ in range(args.warmup): solve_e2e()
-  barrier()
-  t_e2e, evals_e = 0.0, 0
-  for _ in range(args.steps):
-    flush.zero_(); torch.cuda.synchronize()
-    res, dt = solve_e2e(); t_e2e += dt; evals_e += res.nfev + res.njev
-  barrier()
-  tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-  if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-  t_e2e = float(tt.item())
-  e2e_value = n_total * evals_e / t_e2e
+  def allsum_int(x):
+    tt = torch.tensor([x], dtype=torch.int64, device="cuda")
+    if world > 1: dist.all_reduce(tt)
+    return int(tt.item())
+
+  def pin(scene):
+    # the step's inputs live in pinned host memory (the e2e timed region copies them to the device every step)
+    for key in ("points", "valid"):
+      scene[key] = torch.from_numpy(np.ascontiguousarray(scene[key])).pin_memory().numpy()
+    return scene
+
+  eng = get_engine(local)
+  eng.lib.mcba_set_stream(eng.h, stream.cuda_stream)
+  if world > 1:
+    mdist.init_comm(eng, rank, world)
+
+  def measure(local_scene, steps, warmup, e2e=True, roofline=True):
+    """Device-resident solves, end-to-end solves and the linearisation kernel's roofline point for one (sharded) scene."""
+    calib = from_scene(local_scene).enable(cameras=True)
+    n_total = allsum_int(int(calib.inliers.sum()))
+    state0 = calib._state_arrays()
+    calib._upload(calib.inliers)
+
+    def solve_resident():
+      eng.set_params(*state0)
+      flush.zero_()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record(stream)
+      res = eng.solve(ftol=BA_KW["tolerance"], max_nfev=BA_KW["max_iterations"], loss=BA_KW["loss"], f_scale=BA_KW["f_scale"])
+      e1.record(stream); e1.synchronize()
+      return res, e0.elapsed_time(e1)
+    for _ in range(warmup): solve_resident()
+    barrier()
+    t_dev, evals, njev, launches, last = 0.0, 0, 0, 0, None
+    for _ in range(steps):
+      res, ms = solve_resident()
+      t_dev += ms; evals += res.nfev + res.njev; njev += res.njev; launches += res.kernel_launches; last = res
+    barrier()
+    t_dev = allmax(t_dev)
+    out = dict(corners=n_total, ms_per_step=t_dev / steps, value=n_total * evals / (t_dev * 1e-3), lm_iters_per_sec=njev / (t_dev * 1e-3),
+               nfev_plus_njev_per_step=evals / steps, gpu_launches=launches, cost=last.cost, nfev=last.nfev, params=eng.num_params)
+    if e2e:
+      def solve_e2e():
+        c = from_scene(local_scene).enable(cameras=True)      # fresh object: nothing cached on host or device
+        t0 = time.perf_counter()
+        o = c.bundle_adjust(**BA_KW)          # returns after the device->host read of the solved parameters
+        _ = o.last_solve.cost
+        torch.cuda.synchronize()
+        return o.last_solve, time.perf_counter() - t0
+      for _ in range(warmup): solve_e2e()
+      barrier()
+      t_e2e, evals_e, njev_e = 0.0, 0, 0
+      for _ in range(steps):
+        flush.zero_(); torch.cuda.synchronize()
+        res, dt = solve_e2e(); t_e2e += dt; evals_e += res.nfev + res.njev; njev_e += res.njev
+      barrier()
+      t_e2e = allmax(t_e2e)
+      # dense upload: mask (1 B/entry) + observations (16 B/entry) of the [C,F,B,P] table, board points, parameter state
+      h2d = int(calib.inliers.size) * (1 + 16) + int(np.prod(calib.board_points.points.shape)) * 8 + sum(a.size for a in state0) * 8
+      out["e2e"] = dict(value=n_total * evals_e / t_e2e, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=eng.num_params * 8 + 64,
+                        ms_per_step=1e3 * t_e2e / steps, lm_iters_per_sec=njev_e / t_e2e)
+    if roofline:
+      calib._upload(calib.inliers)
+      info = eng.bench_info(0)
+      eng.bench_launch(0, 3)                      # builds the pose tables, warms up
+      times = []
+      for _ in range(10):
+        flush.zero_()                             # evict the inputs between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); eng.bench_launch(0 | NO_PREPARE, 1); e1.record(stream); e1.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+      dur = float(np.mean(times))
+      ach = info["bytes_per_launch"] / dur / 1e9
+      out["roofline"] = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, bytes_per_launch=info["bytes_per_launch"],
+                             launch_ms=dur * 1e3, launches_per_step=out["nfev_plus_njev_per_step"] / 2.0)
+    return out, calib
+
+  sampler = ClockSampler(local); sampler.start()
+  # ---- main workload: the same scene at every N, frames sharded over the ranks ----------------------------------------------
+  scene = synthetic.make_workload(args.workload, seed=args.seed)
+  my = mdist.frame_range(scene["F"], rank, world)
+  local_scene = pin(subsample_frames(scene, np.arange(*my)) if world > 1 else scene)
+  main, calib = measure(local_scene, args.steps, args.warmup)
+
+  others = {}
+  parity = None
+  if world == 1 and args.secondary:
+    for wl in ("cfg2", "cfg3"):
+      if wl == args.workload: continue
+      o, _ = measure(pin(synthetic.make_workload(wl, seed=args.seed)), max(3, args.steps // 2), args.warmup)
+      o.pop("cost", None)
+      others[wl] = o
+  if world > 1:
+    # the sharded solve must be the single-GPU solve: rank 0 solves the whole scene alone on a second context
+    if rank == 0:
+      from multical_b200 import calibration as _cal
+      solo = Engine(local, stream=stream.cuda_stream)            # second context on this GPU: no communicator, the whole scene
+      saved = _cal._engines.get(local)
+      _cal._engines[local] = solo
+      try:
+        ref_res = from_scene(scene).enable(cameras=True).bundle_adjust(**BA_KW).last_solve
+      finally:
+        _cal._engines[local] = saved
+        solo.close()
+      rel = abs(main["cost"] - ref_res.cost) / ref_res.cost
+      parity = dict(single_gpu_cost=ref_res.cost, sharded_cost=main["cost"], rel_diff=rel, single_gpu_nfev=ref_res.nfev, sharded_nfev=main["nfev"])
+      assert rel <= 1e-9 and ref_res.nfev == main["nfev"], f"the {world}-rank solve differs from the single-GPU solve: {parity}"
+    barrier()
+    if args.secondary:
+      # weak scaling: cfg2's 200 frames per GPU, cameras / boards (shared parameters) common
+      base = dict(synthetic.WORKLOADS["cfg2"])
+      wscene = synthetic.make_scene(seed=args.seed, **{**base, "F": base["F"] * world})
+      wmy = mdist.frame_range(wscene["F"], rank, world)
+      o, _ = measure(pin(subsample_frames(wscene, np.arange(*wmy))), max(3, args.steps // 2), args.warmup, e2e=False, roofline=False)
+      o.pop("cost", None)
+      others["weak_cfg2_per_gpu"] = dict(o, scaling="weak", frames_per_gpu=base["F"])
   sampler.stop_flag = True; sampler.join(timeout=2)
-  n_params = eng.num_params
-  # dense upload: mask (1 B/entry) + observations (16 B/entry) of the [C,F,B,P] table, board points, parameter state
-  h2d = int(calib.inliers.size) * (1 + 16) + int(np.prod(calib.board_points.points.shape)) * 8 + sum(a.size for a in state0) * 8
-  d2h = n_params * 8 + 64
 
   if rank != 0:
     if world > 1: dist.destroy_process_group()
     return
 
-  # ---- roofline of the dominant kernel (per-view moment accumulation, k_views_mma) ----------------
-  NO_PREPARE = 256
+  roofline = dict(main["roofline"], traffic=ncu_traffic(args.workload), peak_source=peak_src,
+                  kernel="k_linearize (fused: residuals + analytic Jacobian + per-view moment SYRK on the fp64 tensor path + twist-map expansion into "
+                         "H_ff / W / shared records; reads every corner once, writes nothing per corner or per view)",
+                  algorithmic_bytes="18 B/corner (16 B observation f64x2 + 2 B point index) + 16 B/view, one launch per evaluation",
+                  note="the contract bound is HBM; the pass needs ~160 DFMA + 12 DMMA(m8n8k4) per corner against 18 B (~60 flop/B vs an fp64 ridge of "
+                       "~6 flop/B on B200), so the fp64 pipe bounds it: see profiles/ for sm__inst_executed_pipe_fp64 / pipe_fp64 cycles of the same launch")
 
-  def time_moments_kernel(iters=20):
-    info = eng.bench_info(0)
-    eng.bench_launch(0, 3)                      # builds the pose tables, warms up
-    times = []
-    for _ in range(iters):
-      flush.zero_()                             # inputs are smaller than L2 at cfg2: evict them between timed launches
-      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      e0.record(stream); eng.bench_launch(0 | NO_PREPARE, 1); e1.record(stream); e1.synchronize()
-      times.append(e0.elapsed_time(e1) * 1e-3 / info["launches_per_call"])
-    return info, float(np.mean(times))
+  # ---- CPU baseline: the reference's path on a bounded sample of the same workload ---------------------------------------------
+  cpu_baseline, *_ = cpu_baseline_block(scene, args.workload, args.ref_frames or REF_FRAMES.get(args.workload, 4))
 
-  calib._upload(calib.inliers)
-  info, dur = time_moments_kernel()
-  peak, which = measured_peak()
-  achieved = info["bytes_per_launch"] / dur / 1e9
-  roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=ncu_traffic(args.workload),
-                  kernel="k_views_mma (per-view moment SYRK on the fp64 tensor path, %d launch per linearisation)" % info["launches_per_call"],
-                  bytes_per_launch=info["bytes_per_launch"], launch_ms=dur * 1e3, peak_source=which,
-                  note="fp64-pipe bound, not HBM bound: ~160 DFMA + 12 DMMA(m8n8k4) per corner against 18 B; ncu at 5.5M corners: "
-                       "fp64+DMMA shared pipe 70% active, DRAM 5% (profiles/); below ~1M corners launch latency dominates")
-  if world == 1 and args.at_scale:
-    # the same kernel where it is not launch-latency bound: BASELINE configs[3] (16 cam x 1000 frames x 5 boards, ~5.5M corners)
-    big = from_scene(synthetic.make_workload("cfg4", seed=args.seed)).enable(cameras=True)
-    big._upload(big.inliers)
-    binfo, bdur = time_moments_kernel(10)
-    bach = binfo["bytes_per_launch"] / bdur / 1e9
-    roofline["at_scale"] = dict(workload="cfg4", corners=binfo["corners"], bytes_per_launch=binfo["bytes_per_launch"], launch_ms=bdur * 1e3,
-                                achieved=bach, frac=bach / peak)
-    calib._upload(calib.inliers)
-
-  # ---- CPU baseline: the oracle port on a bounded sample of the same workload --------------------
-  nf = min(local_scene["F"], args.ref_frames)
-  cpu_v, cpu_dt, cpu_res, cpu_n = cpu_reference_step(subsample_frames(local_scene, np.arange(nf)))
-  cpu_baseline = dict(value=cpu_v, unit=UNIT, cores=1, kind="port",
-                      sample=f"{args.workload}: first {nf} of {local_scene['F']} frames ({cpu_n} corners), one full bundle_adjust "
-                             f"({cpu_res.nfev} nfev, {cpu_dt:.1f} s); host has {os.cpu_count()} cores, scipy/numpy path single threaded")
-
-  line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-              ms_per_step=t_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+  line = dict(metric=METRIC, value=main["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+              ms_per_step=main["ms_per_step"], higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
               data="synthetic",
-              config=dict(workload=args.workload, cameras=scene["C"], frames=F_total, boards=scene["B"], corners=n_total,
-                          params=n_params if world == 1 else None, frames_per_gpu=base["F"], camera_model=scene["model"],
-                          solver="TRF semantics (ftol=1e-4, x_scale=jac, max_nfev=100), exact Schur inner solve",
+              config=dict(workload=args.workload, cameras=scene["C"], frames=scene["F"], boards=scene["B"], corners=main["corners"],
+                          params=main["params"] if world == 1 else None, frames_per_gpu=my[1] - my[0], camera_model=scene["model"],
+                          solver="TRF semantics (ftol=1e-4, x_scale=jac, max_nfev=100), exact Schur inner solve; device-resident loop (CUDA-graph WHILE)",
                           l2="flushed between timed iterations (256 MiB write)", seed=args.seed,
-                          kernel_variant=(" ".join(f"{k}={os.environ[k]}" for k in ("MCBA_MOMENTS", "MCBA_CHOL", "MCBA_FUSE", "MCBA_EXPAND", "MCBA_PEER") if k in os.environ) or "default")),
-              lm_iters_per_sec=njev / (t_dev * 1e-3), nfev_plus_njev_per_step=evals / args.steps,
-              e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1e3 * t_e2e / args.steps,
-                       lm_iters_per_sec=njev / t_e2e),
-              gpu_launches=launches, clocks=sampler.summary(), roofline=roofline, cpu_baseline=cpu_baseline)
+                          parallelism=f"frames sharded over {world} GPU(s); in-kernel NVLink peer-memory exchanges" if world > 1 else "1 GPU"),
+              lm_iters_per_sec=main["lm_iters_per_sec"], nfev_plus_njev_per_step=main["nfev_plus_njev_per_step"],
+              e2e=main["e2e"], gpu_launches=main["gpu_launches"], clocks=sampler.summary(), roofline=roofline, cpu_baseline=cpu_baseline)
+  if others: line["other_workloads"] = others
+  if parity: line["parity_vs_single_gpu"] = parity
   emit(line)
   if world > 1: dist.destroy_process_group()
 
@@ -313,10 +389,11 @@ def main():
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--workload", default="cfg2")
+  ap.add_argument("--workload", default="cfg4")
   ap.add_argument("--seed", type=int, default=0)
-  ap.add_argument("--ref-frames", type=int, default=20, help="frames in the CPU-baseline sample")
-  ap.add_argument("--no-at-scale", dest="at_scale", action="store_false", help="skip the extra roofline point at cfg4 size")
+  ap.add_argument("--ref-frames", type=int, default=0, help="frames in the CPU-baseline sample (0: per-workload default)")
+  ap.add_argument("--ref-budget-s", type=float, default=240.0, help="the reference arm stops taking steps after this many seconds")
+  ap.add_argument("--no-secondary", dest="secondary", action="store_false", help="skip the secondary workload blocks")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

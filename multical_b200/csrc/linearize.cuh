@@ -17,8 +17,10 @@
 
 namespace mcba {
 
-constexpr int LIN_WARPS = 8;
+constexpr int LIN_WARPS = 8;           // at most; the host takes fewer when two CTAs of 8 would not fit an SM's shared memory
 constexpr int LIN_THREADS = LIN_WARPS * 32;
+constexpr int LIN_MAXV = 96;           // views of a frame staged in shared memory (more: the list is read from global memory)
+constexpr int LIN_MAXB = 8;            // board pose tables staged per frame (more boards: the tables are read from global memory)
 
 // compile-time shape of a residual row's local Jacobian [twist block(s) | fx fy cx cy dist | r]
 template <int MODEL, bool ROLL>
@@ -134,113 +136,333 @@ struct LinArgs {
 __host__ __device__ inline int lin_record_doubles(int T, int D, int B) { return T + B * (D * 6 + 42); }
 // dynamic shared memory of k_linearize in doubles
 __host__ __device__ inline size_t lin_warp_doubles(int NC, int T, int D, int FB, int nin, int B, int NP) {
-  (void)NP;
-  return ((size_t)NC * MMA_KPAD           // stage (chunk loop) = Ms | Tf | Tb | Ac | Af | Ab | map scratch (epilogue)
+  (void)nin;
+  const int KO = 6 * NP, PC = 6 * (NP + 1);
+  return ((size_t)NC * MMA_KPAD           // stage (chunk loop) = Ms | T^t | map scratch (epilogue)
+       + KO * PC + 12 * NP                // E: twist maps of the view [KO][PC] | chain cache R_cf, t_cf
        + (size_t)B * 6 * FB               // Wb: this warp's partial board rows of W_f
        + FB * FB + FB                     // hacc: H_ff | g_f partial
-       + (6 + nin) * FB                   // wacc: camera-pose and intrinsics rows of W_f (current camera)
+       + D * FB                           // wacc: sum over the camera's boards of M[:, xi] Af
        + T                                // macc: raw moment sum of the current camera
        + (D * 6 + 42)                     // ub: board coupling of the current (camera, board)
-       + 2                                // cost of this frame's views | pad
+       + 6                                // cost of this frame's views | cur_cam | cur_board | wdirty | chain frame | pad
        + 1) & ~(size_t)1;                 // even: every warp's stage buffer takes 16-byte stores
 }
-__host__ __device__ inline size_t lin_smem_doubles(int NC, int T, int D, int FB, int nin, int B, int NP, int npair, int split) {
-  (void)npair; (void)split;      // split > 1: a warp's fragments meet in its own stage buffer, (2 npair + 1) x 32 <= NC x MMA_KPAD doubles
-  return (size_t)LIN_WARPS * lin_warp_doubles(NC, T, D, FB, nin, B, NP);
+// dynamic shared memory of a CTA of `warps` warps: the warps' slices, then the pose tables staged per frame (frame [NP] | boards [min(B, LIN_MAXB)])
+__host__ __device__ inline size_t lin_smem_doubles(int NC, int T, int D, int FB, int nin, int B, int NP, int warps) {
+  return (size_t)warps * lin_warp_doubles(NC, T, D, FB, nin, B, NP) + (size_t)24 * (NP + (B < LIN_MAXB ? B : LIN_MAXB));
 }
+
+// fire-and-forget fp64 add to global memory.  Every address of a CTA's records is only ever updated by ONE lane of ONE warp of that CTA,
+// and a thread's operations on one address are applied in program order: the sums are as reproducible as with load-add-store, without
+// paying the L2 round trip per update (the records live in L2; nothing waits for them until k_reduce_shared).
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// per-warp shared-memory layout of k_linearize (doubles from the warp's base).  The epilogue's per-view scratch aliases the stage
+// buffer of the chunk loop; what must survive from view to view lies behind it.
+template <int MODEL, bool ROLL>
+struct LinLayout {
+  using S = LinShape<MODEL, ROLL>;
+  static constexpr int PC = 6 * (S::NP + 1);                    // columns of the map matrix E: frame-pose block(s) | board-pose block
+  static constexpr int PT = (PC + 7) / 8;                       // 8-row tiles of T^t = E^T M[xi, :]
+  static constexpr int KS = (S::KO + 3) / 4;                    // k-steps over the twist components
+  static constexpr int Ms = 0;                                  // [NC][NC] full symmetric, column D = G^T r
+  static constexpr int Tt = Ms + S::NC * S::NC;                 // [8 PT][NC]   T^t = E^T M[xi, :]
+  static constexpr int scr = Tt + 8 * PT * S::NC;               // 24 NP doubles: R J_L products and chain translations while a map is built
+  static constexpr int stage_end = S::NC * MMA_KPAD;
+  static_assert(scr + 24 * S::NP <= stage_end, "the epilogue's scratch must fit the stage buffer");
+  static_assert((2 * S::NPAIR + 1) * 32 <= stage_end, "the fragments of a view part must fit the warp's stage buffer");
+  static constexpr int NHF = S::FB * S::FB + S::FB;             // H_ff | g_f
+  static constexpr int NWC = S::D * S::FB;                      // sum over the camera's boards of Tf = M[:, xi] Af (D x FB)
+  // after the stage buffer: E [KO][PC] | chain cache (R_cf 9 NP, t_cf 3 NP) | Wb [B][6][FB] | hacc [NHF] | wacc [NWC] | macc [T] | ub [UB] | tail [4]
+  static constexpr int E = stage_end;
+  static constexpr int chain = E + S::KO * PC;
+  static constexpr int Wb = chain + 12 * S::NP;
+  __device__ static int hacc(int B) { return Wb + B * 6 * S::FB; }
+  __device__ static int wacc(int B) { return hacc(B) + NHF; }
+  __device__ static int macc(int B) { return wacc(B) + NWC; }
+  __device__ static int ub(int B) { return macc(B) + S::T; }
+  __device__ static int tail(int B) { return ub(B) + S::UB; }      // [0] frame cost of this warp's views, [1] cur_cam, [2] cur_board, [3] wdirty, [4] frame the chain cache belongs to
+};
+
+// one entry e = kk*6 + col of the 6x6 twist map of a pose (geometry.cuh twist_map): RJ = R_left J_L, Rl = R_left, t = chain translation
+__device__ __forceinline__ double twist_entry(const double* RJ, const double* Rl, const double* t, int kk, int col) {
+  if (kk < 3) return col < 3 ? RJ[3 * kk + col] : 0.0;
+  const int r = kk - 3;
+  if (col >= 3) return Rl[3 * r + col - 3];
+  const double a0 = RJ[col], a1 = RJ[3 + col], a2 = RJ[6 + col];
+  return r == 0 ? t[1] * a2 - t[2] * a1 : r == 1 ? t[2] * a0 - t[0] * a2 : t[0] * a1 - t[1] * a0;
+}
+
+// running sums -> this CTA's records / this frame's W_f rows (leader warps)
+template <int MODEL, bool ROLL>
+__device__ __forceinline__ void lin_flush_ub(const DeviceProblem& p, double* w, double* myrec, int lane) {
+  using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
+  const int B = p.B;
+  double* tl = w + L::tail(B);
+  const int cam = (int)tl[1], board = (int)tl[2];
+  if (cam < 0 || board < 0 || p.off_bp < 0) return;
+  double* ub = w + L::ub(B);
+  double* r = myrec + (size_t)cam * lin_record_doubles(S::T, S::D, B) + S::T + (size_t)board * S::UB;
+  for (int i = lane; i < S::UB; i += 32) { red_add(r + i, ub[i]); ub[i] = 0.0; }
+}
+template <int MODEL, bool ROLL>
+__device__ __forceinline__ void lin_flush_macc(const DeviceProblem& p, double* w, double* myrec, int lane) {
+  using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
+  const int B = p.B;
+  const int cam = (int)(w + L::tail(B))[1];
+  if (cam < 0) return;
+  double* macc = w + L::macc(B);
+  double* r = myrec + (size_t)cam * lin_record_doubles(S::T, S::D, B);
+  for (int i = lane; i < S::T; i += 32) { red_add(r + i, macc[i]); macc[i] = 0.0; }
+}
+// camera rows of W_f: pose rows = sum_a Ac^T wacc[xi_a rows] (the camera's own map does not depend on the view: applied once per
+// camera and frame), intrinsics rows = wacc[kappa rows]
+template <int MODEL, bool ROLL>
+__device__ __forceinline__ void lin_flush_wacc(const DeviceProblem& p, const LinArgs& a, double* w, int f, int lane) {
+  using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
+  constexpr int FB = S::FB, KO = S::KO, NIN = S::NIN;
+  const int B = p.B;
+  double* tl = w + L::tail(B);
+  const int cam = (int)tl[1];
+  if (cam < 0 || !p.motion_on || tl[3] == 0.0) return;
+  __syncwarp();
+  if (lane == 0) tl[3] = 0.0;
+  double* wacc = w + L::wacc(B);
+  double* Wf = a.W + (size_t)f * p.n_s * FB;
+  if (p.off_cp >= 0) {
+    const PoseT& pc = p.cam_T[cam];
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int o = lane; o < 6 * FB; o += 32) {
+      const int i = o / FB, col = o % FB;
+      double s = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KO; kk++) s += twist_entry(pc.JL, I3, pc.t, kk % 6, i) * wacc[kk * FB + col];
+      Wf[(size_t)(p.off_cp + 6 * cam + i) * FB + col] = s;
+    }
+  }
+  if (p.off_in >= 0) {
+    for (int o = lane; o < NIN * FB; o += 32) {
+      const int i = o / FB, col = o % FB;
+      if (p.fix_aspect && i == 1) continue;                            // fy follows fx (camera.py:159-160): its row is folded onto fx
+      const double val = wacc[(KO + i) * FB + col];
+      const double v2 = (p.fix_aspect && i == 0) ? val + wacc[(KO + 1) * FB + col] : val;
+      Wf[(size_t)(p.off_in + p.kint * cam + intr_param_index(p, i)) * FB + col] = v2;
+    }
+  }
+  __syncwarp();
+  for (int o = lane; o < L::NWC; o += 32) wacc[o] = 0.0;
+}
+
+// Epilogue of one view (camera c, frame f, board b), leader warp.  In: the view's moment matrix in Ms (both triangles, column D = G^T r)
+// and its cost.  With E = [Af_0 .. | Ab] the 6 x 6 twist maps of the view stacked by columns (rows = twist components):
+//     T^t = E^T M[xi, :]      rows f: Tf^t (-> W_f camera / intrinsics rows, g_f)      rows b: Tb^t (-> camera x board blocks, board gradient)
+//     P   = T^t[:, xi] E      (f,f) -> H_ff      (b,f) -> W_f board rows      (b,b) -> board x board block
+// both products on the fp64 tensor path (mma.m8n8k4, 8 + 8 instructions for the 5-coefficient model); the C fragments are added
+// straight into the warp's running sums.  A call, not inlined: the chunk loop of the kernel keeps its registers.
+template <int MODEL, bool ROLL>
+__device__ __noinline__ void lin_view_epilogue(const DeviceProblem& p, const LinArgs& a, double* w, double* myrec, const PoseT* ftab, const PoseT* btab, int c, int f, int b, double cost_acc) {
+  using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
+  constexpr int NP = S::NP, KO = S::KO, D = S::D, E_ = S::E, T = S::T, NC = S::NC, NT = S::NT, FB = S::FB;
+  constexpr int PC = L::PC, PT = L::PT, KS = L::KS;
+  const int lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
+  const int B = p.B;
+  const bool frames_on = p.motion_on != 0, boards_on = p.off_bp >= 0;
+  double* Ms = w + L::Ms; double* Tt = w + L::Tt; double* scr = w + L::scr;
+  double* Em = w + L::E; double* chain = w + L::chain;
+  double* Wb = w + L::Wb; double* hacc = w + L::hacc(B); double* wacc = w + L::wacc(B); double* macc = w + L::macc(B); double* ub = w + L::ub(B);
+  double* tl = w + L::tail(B);
+  // ftab: this frame's pose table(s) [NP], btab: the board tables [B] (staged in shared memory by the CTA)
+  const bool cam_changed = c != (int)tl[1];
+  if (cam_changed) {
+    lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane); lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane); lin_flush_macc<MODEL, ROLL>(p, w, myrec, lane);
+    __syncwarp();
+    if (lane == 0) { tl[1] = c; tl[2] = -1.0; }
+    __syncwarp();
+  }
+  if (b != (int)tl[2]) {
+    lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane);
+    __syncwarp();
+    if (lane == 0) tl[2] = b;
+  }
+  // ---- twist maps.  The chain up to the frame pose(s) and the frame block(s) of E change with (camera, frame); the board block per view.
+  const PoseT& pc = p.cam_T[c];
+  if (frames_on || boards_on) {
+    // (camera, frame) part: recomputed when the warp meets the pair for the first time
+    const bool new_chain = cam_changed || (int)tl[4] != f;
+    if (new_chain) {
+      for (int o = lane; o < 21 * NP; o += 32) {
+        const int j = o / 21, e = o % 21;
+        const PoseT& pf = ftab[j];
+        if (e < 9) { const int r = e / 3, cc = e % 3; chain[12 * j + e] = pc.R[3 * r] * pf.R[cc] + pc.R[3 * r + 1] * pf.R[3 + cc] + pc.R[3 * r + 2] * pf.R[6 + cc]; }
+        else if (e < 12) { const int r = e - 9; chain[12 * j + 9 + r] = pc.R[3 * r] * pf.t[0] + pc.R[3 * r + 1] * pf.t[1] + pc.R[3 * r + 2] * pf.t[2] + pc.t[r]; }
+        else { const int q = e - 12, r = q / 3, cc = q % 3; scr[9 * j + q] = pc.R[3 * r] * pf.JL[cc] + pc.R[3 * r + 1] * pf.JL[3 + cc] + pc.R[3 * r + 2] * pf.JL[6 + cc]; }      // R_c J_L(frame)
+      }
+      __syncwarp();
+      if (frames_on)
+        for (int o = lane; o < 36 * NP; o += 32) {
+          const int j = o / 36, e = o % 36, kk = e / 6, col = e % 6;
+          const double val = twist_entry(scr + 9 * j, pc.R, chain + 12 * j + 9, kk, col);
+          // block j of the twist components only reaches frame pose j
+#pragma unroll
+          for (int jj = 0; jj < NP; jj++) Em[(6 * jj + kk) * PC + 6 * j + col] = jj == j ? val : 0.0;
+        }
+      __syncwarp();
+    }
+    if (boards_on) {
+      const PoseT& pb = btab[b];
+      for (int o = lane; o < 12 * NP; o += 32) {
+        const int j = o / 12, e = o % 12;
+        const double* Rc = chain + 12 * j;
+        if (e < 9) { const int r = e / 3, cc = e % 3; scr[12 * j + e] = Rc[3 * r] * pb.JL[cc] + Rc[3 * r + 1] * pb.JL[3 + cc] + Rc[3 * r + 2] * pb.JL[6 + cc]; }
+        else { const int r = e - 9; scr[12 * j + 9 + r] = Rc[3 * r] * pb.t[0] + Rc[3 * r + 1] * pb.t[1] + Rc[3 * r + 2] * pb.t[2] + chain[12 * j + 9 + r]; }
+      }
+      __syncwarp();
+      for (int o = lane; o < 36 * NP; o += 32) {
+        const int j = o / 36, e = o % 36, kk = e / 6, col = e % 6;
+        Em[(6 * j + kk) * PC + 6 * NP + col] = twist_entry(scr + 12 * j, chain + 12 * j, scr + 12 * j + 9, kk, col);
+      }
+    } else {
+      for (int o = lane; o < KO * 6; o += 32) Em[(o / 6) * PC + 6 * NP + o % 6] = 0.0;
+    }
+    if (!frames_on && new_chain)
+      for (int o = lane; o < KO * 6 * NP; o += 32) Em[(o / (6 * NP)) * PC + o % (6 * NP)] = 0.0;
+  }
+  // the camera's raw moment sum: upper triangle | G^T r | cost
+  for (int o = lane; o < D * (D + 1); o += 32) {
+    const int i = o / (D + 1), j = o % (D + 1);
+    if (j == D) macc[E_ + i] += Ms[i * NC + D];
+    else if (i <= j) macc[tri_index(D, i, j)] += Ms[i * NC + j];
+  }
+  if (lane == 0) { macc[T - 1] += cost_acc; tl[0] += cost_acc; tl[3] = 1.0; tl[4] = f; }
+  __syncwarp();
+  if (!(frames_on || boards_on)) return;
+  // ---- T^t = E^T M[xi, :]
+#pragma unroll
+  for (int I = 0; I < PT; I++) {
+    double fa[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) { const int pp = 8 * I + grp, kk = 4 * ks + tig; fa[ks] = (pp < PC && kk < KO) ? Em[kk * PC + pp] : 0.0; }
+#pragma unroll
+    for (int J = 0; J < NT; J++) {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) { const int kk = 4 * ks + tig; const double fb = kk < KO ? Ms[kk * NC + 8 * J + grp] : 0.0; dmma884(c0, c1, fa[ks], fb); }
+      const int pp = 8 * I + grp;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int j = 8 * J + 2 * tig + h;
+        const double val = h == 0 ? c0 : c1;
+        Tt[pp * NC + j] = val;
+        if (pp < 6 * NP) {                                  // frame rows: Tf^t
+          if (frames_on) { if (j < D) wacc[j * FB + pp] += val; else if (j == D) hacc[FB * FB + pp] += val; }
+        } else if (pp < PC) {                               // board rows: Tb^t
+          if (boards_on) { const int r = pp - 6 * NP; if (j < D) ub[j * 6 + r] += val; else if (j == D) ub[D * 6 + 36 + r] += val; }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // ---- P = T^t[:, xi] E
+#pragma unroll
+  for (int I = 0; I < PT; I++) {
+    double fa[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) { const int kk = 4 * ks + tig; fa[ks] = kk < KO ? Tt[(8 * I + grp) * NC + kk] : 0.0; }
+#pragma unroll
+    for (int J = 0; J < PT; J++) {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ks++) { const int kk = 4 * ks + tig, q = 8 * J + grp; const double fb = (kk < KO && q < PC) ? Em[kk * PC + q] : 0.0; dmma884(c0, c1, fa[ks], fb); }
+      const int pp = 8 * I + grp;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int q = 8 * J + 2 * tig + h;
+        const double val = h == 0 ? c0 : c1;
+        if (pp < FB) { if (frames_on && q < FB) hacc[pp * FB + q] += val; }
+        else if (pp < PC && boards_on) {
+          const int r = pp - FB;
+          if (q < FB) { if (frames_on) Wb[(size_t)b * 6 * FB + r * FB + q] += val; }
+          else if (q < PC) ub[D * 6 + r * 6 + (q - FB)] += val;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 
 template <int MODEL, bool ROLL>
 __global__ void __launch_bounds__(LIN_THREADS, 2)
 k_linearize(DeviceProblem p, LinArgs a) {
-  using S = LinShape<MODEL, ROLL>;
-  constexpr int NP = S::NP, KO = S::KO, NIN = S::NIN, D = S::D, E = S::E, T = S::T, NC = S::NC, NT = S::NT, NPAIR = S::NPAIR, KINT = S::KINT, FB = S::FB, UB = S::UB;
-  constexpr int NHF = FB * FB + FB;
-  constexpr int NWC = (6 + NIN) * FB;
+  using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
+  constexpr int NIN = S::NIN, D = S::D, T = S::T, NC = S::NC, NT = S::NT, NPAIR = S::NPAIR, KINT = S::KINT, FB = S::FB, NP = S::NP;
   extern __shared__ double lsm[];
+  __shared__ int fv_cam[LIN_MAXV], fv_board[LIN_MAXV], fv_start[LIN_MAXV + 1];
+  __shared__ int any_view;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int grp = lane >> 2, tig = lane & 3;
   const int B = p.B, n_s = p.n_s;
-  const int split = a.split, slots = LIN_WARPS / split, slot = warp / split, sub = warp % split;
+  const int split = a.split, slots = nwarps / split, slot = warp / split, sub = warp % split;
   const bool leader = sub == 0;
   const bool frames_on = p.motion_on != 0;
   const size_t wd = lin_warp_doubles(NC, T, D, FB, NIN, B, NP);
-  double* stage = lsm + (size_t)warp * wd;
-  double* Ms = stage;                         // [NC][NC] full symmetric, column D = G^T r (epilogue view of the stage buffer)
-  double* Tf = Ms + NC * NC;                  // [D][FB]   M[:, xi_a] Af_a
-  double* Tb = Tf + D * FB;                   // [D][6]    sum_a M[:, xi_a] Ab_a
-  double* Ac = Tb + D * 6;                    // twist maps of the view, also inside the stage buffer
-  double* Af = Ac + 36;
-  double* Ab = Af + 36 * NP;
-  double* scr = Ab + 36 * NP;
-  static_assert(NC * NC + D * FB + D * 6 + 36 + 72 * NP + 33 * NP <= NC * MMA_KPAD, "the epilogue's scratch must fit the stage buffer");
-  double* Wb = stage + (size_t)NC * MMA_KPAD; // [B][6][FB]
-  double* hacc = Wb + (size_t)B * 6 * FB;     // [NHF]
-  double* wacc = hacc + NHF;                  // [NWC]
-  double* macc = wacc + NWC;                  // [T]
-  double* ub = macc + T;                      // [UB]
-  double* wcost = ub + UB;                    // [1]
-  static_assert((2 * NPAIR + 1) * 32 <= NC * MMA_KPAD, "the fragments of a view part must fit the warp's stage buffer");
+  double* w = lsm + (size_t)warp * wd;          // this warp's slice; w[0 .. NC*MMA_KPAD) is the stage buffer of the chunk loop
+  // pose tables staged in shared memory: this frame's [NP], then the boards' (they do not change during the launch)
+  PoseT* ftab = reinterpret_cast<PoseT*>(lsm + (size_t)nwarps * wd);
+  const bool boards_staged = B <= LIN_MAXB;
+  const PoseT* btab = boards_staged ? ftab + NP : p.board_T;
   const int rec = lin_record_doubles(T, D, B);
   double* myrec = a.spart + (size_t)blockIdx.x * p.C * rec;
 
   // this CTA's records start at zero; the leader warps' running sums too
-  for (int i = tid; i < p.C * rec; i += LIN_THREADS) myrec[i] = 0.0;
-  if (leader) {
-    for (int i = lane; i < NWC + T + UB; i += 32) wacc[i] = 0.0;       // wacc | macc | ub are contiguous
+  for (int i = tid; i < p.C * rec; i += nthreads) myrec[i] = 0.0;
+  if (boards_staged) {
+    double* dst = reinterpret_cast<double*>(ftab + NP);
+    const double* src = reinterpret_cast<const double*>(p.board_T);
+    for (int i = tid; i < 24 * B; i += nthreads) dst[i] = src[i];
   }
-  int cur_cam = -1, cur_board = -1;           // what macc / wacc (camera) and ub (camera, board) currently hold   (leader warps)
-  bool wdirty = false;                        // wacc holds rows of cur_cam for the frame in progress
+  if (leader) {
+    for (int i = L::E + lane; i < L::tail(B); i += 32) w[i] = 0.0;       // E | chain | Wb | hacc | wacc | macc | ub
+    if (lane == 0) { double* tl = w + L::tail(B); tl[0] = 0.0; tl[1] = -1.0; tl[2] = -1.0; tl[3] = 0.0; tl[4] = -1.0; }
+  }
   __syncthreads();
-
-  auto flush_ub = [&]() {                     // ub -> record of (cur_cam, cur_board)
-    if (cur_cam < 0 || cur_board < 0 || p.off_bp < 0) return;
-    double* r = myrec + (size_t)cur_cam * rec + T + (size_t)cur_board * UB;
-    for (int i = lane; i < UB; i += 32) { r[i] = r[i] + ub[i]; ub[i] = 0.0; }
-  };
-  auto flush_macc = [&]() {
-    if (cur_cam < 0) return;
-    double* r = myrec + (size_t)cur_cam * rec;
-    for (int i = lane; i < T; i += 32) { r[i] = r[i] + macc[i]; macc[i] = 0.0; }
-  };
-  auto flush_wacc = [&](int f) {              // camera rows of W_f (complete for this frame: one warp owns a camera)
-    if (cur_cam < 0 || !frames_on || !wdirty) return;
-    wdirty = false;
-    double* Wf = a.W + (size_t)f * n_s * FB;
-    for (int o = lane; o < NWC; o += 32) {
-      const double val = wacc[o];
-      const int row = o / FB, col = o % FB;
-      if (row < 6) { if (p.off_cp >= 0) Wf[(size_t)(p.off_cp + 6 * cur_cam + row) * FB + col] = val; }
-      else if (p.off_in >= 0) {
-        const int i = row - 6;
-        if (p.fix_aspect && i == 1) continue;                            // fy follows fx (camera.py:159-160): its row is folded below
-        const double v2 = (p.fix_aspect && i == 0) ? val + wacc[(6 + 1) * FB + col] : val;
-        Wf[(size_t)(p.off_in + p.kint * cur_cam + intr_param_index(p, i)) * FB + col] = v2;
-      }
-    }
-    __syncwarp();
-    for (int o = lane; o < NWC; o += 32) wacc[o] = 0.0;
-  };
 
   for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
     const int v0 = p.frame_view_start[f], v1 = p.frame_view_start[f + 1];
+    const bool staged = v1 - v0 <= LIN_MAXV;
+    if (staged) {
+      for (int i = tid; i <= v1 - v0; i += nthreads) {
+        fv_start[i] = p.view_start[v0 + i];
+        if (i < v1 - v0) { fv_cam[i] = p.view_cam[v0 + i]; fv_board[i] = p.view_board[v0 + i]; }
+      }
+    }
+    {
+      double* dst = reinterpret_cast<double*>(ftab);
+      const double* src = reinterpret_cast<const double*>(p.frame_T + (size_t)f * NP);
+      for (int i = tid; i < 24 * NP; i += nthreads) dst[i] = src[i];
+    }
     if (frames_on) {
       double* Wf = a.W + (size_t)f * n_s * FB;
-      for (int i = tid; i < n_s * FB; i += LIN_THREADS) Wf[i] = 0.0;
+      for (int i = tid; i < n_s * FB; i += nthreads) Wf[i] = 0.0;
     }
     if (leader) {
-      for (int i = lane; i < B * 6 * FB + NHF; i += 32) Wb[i] = 0.0;     // Wb | hacc are contiguous
-      if (lane == 0) wcost[0] = 0.0;
+      for (int i = L::Wb + lane; i < L::wacc(B); i += 32) w[i] = 0.0;      // Wb | hacc
+      if (lane == 0) (w + L::tail(B))[0] = 0.0;
     }
     __syncthreads();
 
     int v = v0;
     while (true) {
-      while (v < v1 && (p.view_cam[v] % slots) != slot) v++;
+      if (staged) { while (v < v1 && (fv_cam[v - v0] % slots) != slot) v++; }
+      else { while (v < v1 && (p.view_cam[v] % slots) != slot) v++; }
       const bool have = v < v1;
       if (split == 1) { if (!have) break; }
       else {
         // the warps of a slot walk the same views; the CTA meets twice per round, so every warp runs the same number of rounds
-        __shared__ int any_view;
         if (tid == 0) any_view = 0;
         __syncthreads();
         if (have && lane == 0 && leader) any_view = 1;
@@ -253,8 +475,8 @@ k_linearize(DeviceProblem p, LinArgs a) {
       double cost_acc = 0.0;
       int c = 0, b = 0;
       if (have) {
-        c = p.view_cam[v]; b = p.view_board[v];
-        const int beg = p.view_start[v], end = p.view_start[v + 1];
+        c = staged ? fv_cam[v - v0] : p.view_cam[v]; b = staged ? fv_board[v - v0] : p.view_board[v];
+        const int beg = staged ? fv_start[v - v0] : p.view_start[v], end = staged ? fv_start[v - v0 + 1] : p.view_start[v + 1];
         ViewPose vp, vpe;
         compose_views<ROLL>(p, c, f, b, vp, vpe);
         const double inv_h = ROLL ? 1.0 / p.img_h[c] : 0.0;
@@ -263,21 +485,21 @@ k_linearize(DeviceProblem p, LinArgs a) {
         for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
         const double* bp = p.board_pts + (size_t)b * p.P * 3;
         for (int base = beg + 32 * sub; base < end; base += 32 * split)
-          view_chunk<MODEL, ROLL>(p, a.loss, a.f_scale, vp, vpe, k, bp, inv_h, base, end, lane, stage, acc, cost_acc);
+          view_chunk<MODEL, ROLL>(p, a.loss, a.f_scale, vp, vpe, k, bp, inv_h, base, end, lane, w, acc, cost_acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
       }
       if (split > 1) {        // meet: the slot's leader adds the other warps' fragments in warp order (same lane -> same matrix element)
         if (have && !leader) {
-          double* xr = stage;                  // this warp's stage buffer is free between two views
+          double* xr = w;                      // this warp's stage buffer is free between two views
 #pragma unroll
           for (int t = 0; t < NPAIR; t++) { xr[(2 * t) * 32 + lane] = acc[t][0]; xr[(2 * t + 1) * 32 + lane] = acc[t][1]; }
           if (lane == 0) xr[2 * NPAIR * 32] = cost_acc;
         }
         __syncthreads();
         if (have && leader) {
-          for (int w = 1; w < split; w++) {
-            const double* xr = lsm + (size_t)(warp + w) * wd;
+          for (int q = 1; q < split; q++) {
+            const double* xr = lsm + (size_t)(warp + q) * wd;
 #pragma unroll
             for (int t = 0; t < NPAIR; t++) { acc[t][0] += xr[(2 * t) * 32 + lane]; acc[t][1] += xr[(2 * t + 1) * 32 + lane]; }
             cost_acc += xr[2 * NPAIR * 32];
@@ -285,125 +507,40 @@ k_linearize(DeviceProblem p, LinArgs a) {
         }
       }
       if (have && leader) {
-        // ---------------------------------------------------------------- epilogue of one view (camera c, frame f, board b)
-        if (c != cur_cam) { flush_ub(); flush_wacc(f); flush_macc(); cur_cam = c; cur_board = -1; }
-        if (b != cur_board) { flush_ub(); cur_board = b; }
-        __syncwarp();
-        // fragments -> Ms (both triangles) and the camera's raw moment sum
-        {
-          int t = 0;
+        // fragments -> Ms (both triangles), then the epilogue works from shared memory
+        double* Ms = w + L::Ms;
+        int t = 0;
 #pragma unroll
-          for (int I = 0; I < NT; I++)
+        for (int I = 0; I < NT; I++)
 #pragma unroll
-            for (int J = I; J < NT; J++) {
+          for (int J = I; J < NT; J++) {
 #pragma unroll
-              for (int h = 0; h < 2; h++) {
-                const int i = 8 * I + grp, j = 8 * J + 2 * tig + h;
-                const double val = acc[t][h];
-                Ms[i * NC + j] = val;
-                if (I != J) Ms[j * NC + i] = val;
-                if (i < D && j < D && i <= j) macc[tri_index(D, i, j)] += val;
-                else if (i < D && j == D) macc[E + i] += val;
-              }
-              t++;
+            for (int h = 0; h < 2; h++) {
+              const int i = 8 * I + grp, j = 8 * J + 2 * tig + h;
+              Ms[i * NC + j] = acc[t][h];
+              if (I != J) Ms[j * NC + i] = acc[t][h];
             }
-          if (lane == 0) { macc[T - 1] += cost_acc; wcost[0] += cost_acc; }
-        }
-        view_twist_maps_par<NP>(p, c, f, b, lane, Ac, frames_on ? Af : nullptr, p.off_bp >= 0 ? Ab : nullptr, scr);
+            t++;
+          }
         __syncwarp();
-        if (frames_on) {
-          for (int o = lane; o < D * FB; o += 32) {           // Tf[:, 6a+k] = M[:, xi_a] Af_a
-            const int i = o / FB, col = o % FB, ablk = col / 6, kk0 = col % 6;
-            double s = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 6; kk++) s += Ms[i * NC + 6 * ablk + kk] * Af[36 * ablk + kk * 6 + kk0];
-            Tf[o] = s;
-          }
-        }
-        if (p.off_bp >= 0) {
-          for (int o = lane; o < D * 6; o += 32) {            // Tb = sum_a M[:, xi_a] Ab_a
-            const int i = o / 6, j = o % 6;
-            double s = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < KO; kk++) s += Ms[i * NC + kk] * Ab[36 * (kk / 6) + (kk % 6) * 6 + j];
-            Tb[o] = s;
-          }
-        }
-        __syncwarp();
-        if (frames_on) {
-          // H_ff[6a+i, col] += Af_a^T Tf[xi_a rows, col] ; g_f[6a+i] += Af_a^T g_xi_a
-          for (int o = lane; o < NHF; o += 32) {
-            double s = 0.0;
-            if (o < FB * FB) {
-              const int r = o / FB, col = o % FB, ablk = r / 6, i = r % 6;
-#pragma unroll
-              for (int kk = 0; kk < 6; kk++) s += Af[36 * ablk + kk * 6 + i] * Tf[(6 * ablk + kk) * FB + col];
-            } else {
-              const int r = o - FB * FB, ablk = r / 6, i = r % 6;
-#pragma unroll
-              for (int kk = 0; kk < 6; kk++) s += Af[36 * ablk + kk * 6 + i] * Ms[(6 * ablk + kk) * NC + D];
-            }
-            hacc[o] += s;
-          }
-          // camera rows of W_f: sum_a Ac^T Tf[xi_a rows] (6 x FB) | Tf[kappa rows] (NIN x FB)
-          for (int o = lane; o < NWC; o += 32) {
-            const int row = o / FB, col = o % FB;
-            double s = 0.0;
-            if (row < 6) {
-#pragma unroll
-              for (int kk = 0; kk < KO; kk++) s += Ac[(kk % 6) * 6 + row] * Tf[kk * FB + col];
-            } else s = Tf[(KO + row - 6) * FB + col];
-            wacc[o] += s;
-          }
-          wdirty = true;
-          // board rows of W_f (shared between cameras): this warp's partial
-          if (p.off_bp >= 0) {
-            for (int o = lane; o < 6 * FB; o += 32) {
-              const int i = o / FB, col = o % FB;
-              double s = 0.0;
-#pragma unroll
-              for (int kk = 0; kk < KO; kk++) s += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Tf[kk * FB + col];
-              Wb[(size_t)b * 6 * FB + o] += s;
-            }
-          }
-        }
-        if (p.off_bp >= 0) {
-          // shared blocks that need this view's board map: (camera | intrinsics) x board pose, board x board, board gradient
-          for (int o = lane; o < UB; o += 32) {
-            double s;
-            if (o < D * 6) s = Tb[o];
-            else if (o < D * 6 + 36) {
-              const int q = o - D * 6, i = q / 6, j = q % 6;
-              s = 0.0;
-#pragma unroll
-              for (int kk = 0; kk < KO; kk++) s += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Tb[kk * 6 + j];
-            } else {
-              const int i = o - D * 6 - 36;
-              s = 0.0;
-#pragma unroll
-              for (int kk = 0; kk < KO; kk++) s += Ab[36 * (kk / 6) + (kk % 6) * 6 + i] * Ms[kk * NC + D];
-            }
-            ub[o] += s;
-          }
-        }
-        __syncwarp();
+        lin_view_epilogue<MODEL, ROLL>(p, a, w, myrec, ftab, btab, c, f, b, cost_acc);
       }
       if (have) v++;
     }
     // ---- end of the frame: camera rows out, then the CTA sums the slots' partials in slot order
-    if (leader) { flush_wacc(f); }
+    if (leader) lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane);
     __syncthreads();
     if (frames_on) {
-      for (int o = tid; o < NHF; o += LIN_THREADS) {
+      for (int o = tid; o < L::NHF; o += nthreads) {
         double s = 0.0;
-        for (int w = 0; w < slots; w++) s += lsm[(size_t)(w * split) * wd + (hacc - stage) + o];
+        for (int q = 0; q < slots; q++) s += lsm[(size_t)(q * split) * wd + L::hacc(B) + o];
         if (o < FB * FB) a.Hff[(size_t)f * FB * FB + o] = s; else a.g[n_s + FB * f + o - FB * FB] = s;
       }
       if (p.off_bp >= 0) {
         double* Wf = a.W + (size_t)f * n_s * FB;
-        for (int o = tid; o < B * 6 * FB; o += LIN_THREADS) {
+        for (int o = tid; o < B * 6 * FB; o += nthreads) {
           double s = 0.0;
-          for (int w = 0; w < slots; w++) s += lsm[(size_t)(w * split) * wd + (Wb - stage) + o];
+          for (int q = 0; q < slots; q++) s += lsm[(size_t)(q * split) * wd + L::Wb + o];
           const int bb = o / (6 * FB), i = (o % (6 * FB)) / FB, j = o % FB;
           Wf[(size_t)(p.off_bp + 6 * bb + i) * FB + j] = s;
         }
@@ -411,12 +548,12 @@ k_linearize(DeviceProblem p, LinArgs a) {
     }
     if (tid == 0) {
       double s = 0.0;
-      for (int w = 0; w < slots; w++) s += lsm[(size_t)(w * split) * wd + (wcost - stage)];
+      for (int q = 0; q < slots; q++) s += lsm[(size_t)(q * split) * wd + L::tail(B)];
       a.frame_cost[f] = s;
     }
     __syncthreads();
   }
-  if (leader) { flush_ub(); flush_macc(); }
+  if (leader) { lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane); lin_flush_macc<MODEL, ROLL>(p, w, myrec, lane); }
 }
 
 // ------------------------------------------------------------------------------------------------

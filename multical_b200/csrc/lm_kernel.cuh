@@ -82,6 +82,7 @@ struct LmArgs {
   int opt_loss;                      // unused by the kernel (the linearisation kernels apply the loss); kept for the log
   LmPeer peer;
   unsigned long long cond_handle; int use_cond;      // CUDA-graph WHILE node: the kernel sets the loop condition itself
+  unsigned long long* prof;          // MCBA_PROF=1: %globaltimer at the phase boundaries of the last launch (CTA 0), else null
 };
 
 // ---------------------------------------------------------------- replicated block-wide sums
@@ -173,6 +174,7 @@ __device__ inline void exchange(const LmArgs& a, const XSeg* seg, int nseg, unsi
 // per frame (one warp): L L^T = D_f H_ff D_f + reg I ; Y_f = (D_s W_f D_f) L^-T ; z_f = L^-1 gh_f
 template <int FB>
 __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, int lane, double* Lw /*[FB*FB + FB] shared, per warp*/) {
+  // the stored factor keeps 1 / L_ii on its diagonal: every substitution below (and the back-substitution of phase G) multiplies
   const int n_s = a.n_s;
   double* L = Lw; double* df = Lw + FB * FB;
   if (lane == 0) {
@@ -184,21 +186,22 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
     for (int i = 0; i < FB; i++)
 #pragma unroll
       for (int j = 0; j < FB; j++) A[i * FB + j] = df[i] * df[j] * H[i * FB + j] + (i == j ? reg : 0.0);
+    double Lr[FB * FB];
 #pragma unroll
     for (int j = 0; j < FB; j++) {
       double s = A[j * FB + j];
 #pragma unroll
-      for (int k = 0; k < FB; k++) if (k < j) s -= L[j * FB + k] * L[j * FB + k];
-      const double piv = sqrt(fmax(s, 1e-300));
-      L[j * FB + j] = piv;
+      for (int k = 0; k < FB; k++) if (k < j) s -= Lr[j * FB + k] * Lr[j * FB + k];
+      const double rs = rsqrt(fmax(s, 1e-300));
+      Lr[j * FB + j] = rs;                                  // 1 / L_jj
 #pragma unroll
       for (int i = 0; i < FB; i++) {
         if (i > j) {
           double t = A[i * FB + j];
 #pragma unroll
-          for (int k = 0; k < FB; k++) if (k < j) t -= L[i * FB + k] * L[j * FB + k];
-          L[i * FB + j] = t / piv;
-        } else if (i < j) L[i * FB + j] = 0.0;
+          for (int k = 0; k < FB; k++) if (k < j) t -= Lr[i * FB + k] * Lr[j * FB + k];
+          Lr[i * FB + j] = t * rs;
+        } else if (i < j) Lr[i * FB + j] = 0.0;
       }
     }
     double z[FB];
@@ -206,12 +209,12 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
     for (int i = 0; i < FB; i++) {
       double t = a.gh[n_s + FB * f + i];
 #pragma unroll
-      for (int k = 0; k < FB; k++) if (k < i) t -= L[i * FB + k] * z[k];
-      z[i] = t / L[i * FB + i];
+      for (int k = 0; k < FB; k++) if (k < i) t -= Lr[i * FB + k] * z[k];
+      z[i] = t * Lr[i * FB + i];
       a.zf[(size_t)f * FB + i] = z[i];
     }
 #pragma unroll
-    for (int i = 0; i < FB * FB; i++) a.Lf[(size_t)f * FB * FB + i] = L[i];
+    for (int i = 0; i < FB * FB; i++) { L[i] = Lr[i]; a.Lf[(size_t)f * FB * FB + i] = Lr[i]; }
   }
   __syncwarp();
   const double* Wf = a.W + (size_t)f * n_s * FB;
@@ -224,7 +227,7 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
       double t = ds * Wf[s * FB + i] * df[i];
 #pragma unroll
       for (int k = 0; k < FB; k++) if (k < i) t -= L[i * FB + k] * y[k];
-      y[i] = t / L[i * FB + i];
+      y[i] = t * L[i * FB + i];
     }
 #pragma unroll
     for (int i = 0; i < FB; i++) Yf[s * FB + i] = y[i];
@@ -243,16 +246,32 @@ __device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int c
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   double acc[2][2] = {{0, 0}, {0, 0}};
   double racc = 0.0;
-  __syncthreads();
-  for (int fbase = f0; fbase < f1; fbase += SYRK_FR) {
+  // software pipeline: the tiles of step s+1 are loaded into registers while step s is multiplied out of shared memory
+  constexpr int PER = (SYRK_FR * SYRK_TILE * FB + LM_THREADS - 1) / LM_THREADS;
+  double pi[PER], pj[PER];
+  auto fetch = [&](int fbase) {
     const int nf = min(SYRK_FR, f1 - fbase);
-    for (int o = threadIdx.x; o < SYRK_FR * SYRK_TILE * FB; o += LM_THREADS) {
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int o = threadIdx.x + q * LM_THREADS;
       const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
       const int gi = ti * SYRK_TILE + r, gj = tj * SYRK_TILE + r;
-      (&Yi[0][0][0])[o] = (ff < nf && gi < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gi) * FB + k] : 0.0;
-      (&Yj[0][0][0])[o] = (ff < nf && gj < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gj) * FB + k] : 0.0;
+      const bool in = o < SYRK_FR * SYRK_TILE * FB && ff < nf;
+      pi[q] = (in && gi < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gi) * FB + k] : 0.0;
+      pj[q] = (in && gj < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gj) * FB + k] : 0.0;
+    }
+  };
+  __syncthreads();
+  if (f0 < f1) fetch(f0);
+  for (int fbase = f0; fbase < f1; fbase += SYRK_FR) {
+    const int nf = min(SYRK_FR, f1 - fbase);
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int o = threadIdx.x + q * LM_THREADS;
+      if (o < SYRK_FR * SYRK_TILE * FB) { (&Yi[0][0][0])[o] = pi[q]; (&Yj[0][0][0])[o] = pj[q]; }
     }
     __syncthreads();
+    if (fbase + SYRK_FR < f1) fetch(fbase + SYRK_FR);
     for (int ff = 0; ff < nf; ff++) {
 #pragma unroll
       for (int k = 0; k < FB; k++) {
@@ -598,10 +617,11 @@ k_lm(LmArgs a) {
   double* work = ksm + 64;
 
   if (tid == 0) { S = *a.st; xerr = 0; chol_fail_s = 0; }
+  if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[0] = 0;
 #ifdef MCBA_SIMT_BUILD
-#define LMPH(x) simt::set_mark(x);
+#define LMPH(ID_) simt::set_mark(ID_);
 #else
-#define LMPH(x)
+#define LMPH(ID_) if (a.prof && blockIdx.x == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.prof[ID_] = t_; }
 #endif
   __syncthreads();
   if (S.done) {
@@ -912,7 +932,7 @@ k_lm(LmArgs a) {
           double v = y[i];
 #pragma unroll
           for (int k = 0; k < FB; k++) if (k > i) v -= L[k * FB + i] * y[k];
-          y[i] = v / L[i * FB + i];
+          y[i] = v * L[i * FB + i];                            // the stored diagonal is 1 / L_ii
         }
 #pragma unroll
         for (int i = 0; i < FB; i++) a.gn[n_s + FB * f + i] = y[i];
@@ -973,6 +993,7 @@ k_lm(LmArgs a) {
   for (int i = gthread; i < a.n_items; i += gstride)
     make_trial_item(a.P, a.x_new, a.cam_rt2, a.board_rt2, a.frame_rt2, a.intr2, a.board_pts2, a.he_rt2, i);
   __syncthreads();
+  LMPH(10)
   if (writer) {
     if (xerr) { S.done = 1; S.status = -3; }
     S.chol_fail += chol_fail_s;

@@ -103,13 +103,14 @@ struct mcba_ctx {
   DevBuf<unsigned> cam_counter;
   // device-resident trust-region loop (lm_kernel.cuh)
   DevBuf<double> Spart, rpart, part_scale, part_quad, part_step;
-  DevBuf<unsigned long long> lm_bar, peer_seq_dev;
+  DevBuf<unsigned long long> lm_bar, peer_seq_dev, prof;
+  bool profiling = false;      // MCBA_PROF=1 (with MCBA_GRAPH=0): phase timestamps of every k_lm launch on stderr
   DevBuf<mcba_log_row> dev_log;
   int lm_grid = 1, syrk_chunks = 1, syrk_cf = 8;
   bool use_graph = true;       // MCBA_GRAPH=0: the host launches one loop body at a time and reads the state after each
   struct SolveGraph { cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr; std::vector<char> key; cudaStream_t stream = nullptr; int body_launches = 0; } sg;
   bool graph_launched = false;
-  int lin_grid = 1, lin_split = 1;
+  int lin_grid = 1, lin_split = 1, lin_warps = LIN_WARPS;
   bool fused_lin = true;       // false for hand-eye frames: per-view moment records + the round-1 expand kernels (they carry the 12 shared motion parameters)
   DevBuf<double> x, x_new, sinv, d, gh, gn, Y, Lf, zf, S, rhs, red, Linv;
   DevBuf<SolverState> state;
@@ -228,13 +229,13 @@ int launch_moments(mcba_ctx* ctx, const DeviceProblem& P, const ViewKernelArgs& 
 
 // ---------------------------------------------------------------- fused linearisation (linearize.cuh)
 template <int MODEL, bool ROLL>
-size_t lin_smem_bytes(const DeviceProblem& P, int split) {
+size_t lin_smem_bytes(const DeviceProblem& P, int warps) {
   using S = LinShape<MODEL, ROLL>;
-  return sizeof(double) * lin_smem_doubles(S::NC, S::T, S::D, S::FB, S::NIN, P.B, S::NP, S::NPAIR, split);
+  return sizeof(double) * lin_smem_doubles(S::NC, S::T, S::D, S::FB, S::NIN, P.B, S::NP, warps);
 }
-size_t lin_smem_for(const DeviceProblem& P, int split) {
+size_t lin_smem_for(const DeviceProblem& P, int warps) {
   const bool roll = P.motion == MOTION_ROLLING;
-#define LS(MODEL) return roll ? lin_smem_bytes<MODEL, true>(P, split) : lin_smem_bytes<MODEL, false>(P, split);
+#define LS(MODEL) return roll ? lin_smem_bytes<MODEL, true>(P, warps) : lin_smem_bytes<MODEL, false>(P, warps);
   switch (P.model) {
     case MODEL_STANDARD: LS(MODEL_STANDARD)
     case MODEL_RATIONAL: LS(MODEL_RATIONAL)
@@ -249,10 +250,11 @@ int launch_linearize(mcba_ctx* ctx, const DeviceProblem& P, int loss, double f_s
   if (P.F == 0) return MCBA_OK;
   LinArgs a{}; a.loss = loss; a.f_scale = f_scale; a.split = ctx->lin_split;
   a.Hff = ctx->Hff.p; a.g = ctx->g.p; a.W = ctx->W.p; a.spart = ctx->spart.p; a.frame_cost = ctx->frame_cost.p;
-  const size_t sm = lin_smem_for(P, ctx->lin_split);
+  const size_t sm = lin_smem_for(P, ctx->lin_warps);
   const bool roll = P.motion == MOTION_ROLLING;
+  const int th = ctx->lin_warps * 32;
   cudaStream_t s = ctx->stream;
-#define LL(MODEL) if (roll) k_linearize<MODEL, true><<<ctx->lin_grid, LIN_THREADS, sm, s>>>(P, a); else k_linearize<MODEL, false><<<ctx->lin_grid, LIN_THREADS, sm, s>>>(P, a);
+#define LL(MODEL) if (roll) k_linearize<MODEL, true><<<ctx->lin_grid, th, sm, s>>>(P, a); else k_linearize<MODEL, false><<<ctx->lin_grid, th, sm, s>>>(P, a);
   switch (P.model) {
     case MODEL_STANDARD: LL(MODEL_STANDARD) break;
     case MODEL_RATIONAL: LL(MODEL_RATIONAL) break;
@@ -412,6 +414,7 @@ LmArgs make_lm_args(mcba_ctx* ctx, int log_cap) {
   a.part_scale = ctx->part_scale.p; a.part_quad = ctx->part_quad.p; a.part_step = ctx->part_step.p;
   a.st = ctx->state.p; a.log = ctx->dev_log.p; a.log_cap = log_cap; a.bar = ctx->lm_bar.p;
   a.peer.rank = ctx->rank; a.peer.world = ctx->world; a.peer.cap = ctx->peer_cap; a.peer.seq = ctx->peer_seq_dev.p;
+  a.prof = ctx->profiling ? ctx->prof.p : nullptr;
   a.peer.timeout_cycles = (long long)40e9;          // ~20 s at 2 GHz: a rank that left the solve must not hang its peers' GPUs
   for (int r = 0; r < ctx->world && r < PEER_MAX_WORLD; r++) a.peer.base[r] = ctx->peer_base[r];
   return a;
@@ -460,7 +463,7 @@ int run_lm_loop(mcba_ctx* ctx, int loss, double f_scale, int log_cap) {
     // key of the cached graph: every launch parameter of the body (pointers, sizes, loss): the same problem solved again reuses it
     std::vector<char> key(sizeof(LmArgs) + sizeof(int) * 4 + sizeof(double));
     memcpy(key.data(), &a, sizeof(LmArgs));
-    { char* q = key.data() + sizeof(LmArgs); memcpy(q, &loss, 4); memcpy(q + 4, &ctx->lin_grid, 4); memcpy(q + 8, &ctx->lm_grid, 4); memcpy(q + 12, &ctx->lin_split, 4); memcpy(q + 16, &f_scale, 8); }
+    { char* q = key.data() + sizeof(LmArgs); memcpy(q, &loss, 4); memcpy(q + 4, &ctx->lin_grid, 4); memcpy(q + 8, &ctx->lm_grid, 4); { const int sw = ctx->lin_split * 16 + ctx->lin_warps; memcpy(q + 12, &sw, 4); } memcpy(q + 16, &f_scale, 8); }
     const int before = ctx->launches;
     if (!ctx->sg.exec || ctx->sg.key != key || ctx->sg.stream != s) {
       if (ctx->sg.exec) { cudaGraphExecDestroy(ctx->sg.exec); ctx->sg.exec = nullptr; }
@@ -496,6 +499,14 @@ int run_lm_loop(mcba_ctx* ctx, int loss, double f_scale, int log_cap) {
     int r = lm_body(ctx, loss, f_scale, a); if (r) return r;
     CK(cudaMemcpyAsync(&h, ctx->state.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (ctx->profiling) {
+      unsigned long long t[16];
+      CK(cudaMemcpy(t, ctx->prof.p, sizeof(t), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[k_lm phases, us since phase A]");
+      for (int q = 2; q <= 10; q++) fprintf(stderr, " %d:%.1f", q, t[q] >= t[1] && t[1] ? (t[q] - t[1]) * 1e-3 : -1.0);
+      fprintf(stderr, "\n");
+      CK(cudaMemset(ctx->prof.p, 0, sizeof(t)));
+    }
     if (h.done) break;
   }
   return MCBA_OK;
@@ -559,7 +570,12 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     int split = 1;
     while (split < LIN_WARPS && C * split * 2 <= LIN_WARPS) split *= 2;      // few cameras: several warps share a view
     ctx->lin_split = split;
-    REQUIRE(lin_smem_for(P, split) <= 220 * 1024, MCBA_ERR_UNSUPPORTED, "too many boards for the linearisation kernel's shared memory");
+    // warps per CTA: 8 when two such CTAs fit an SM's shared memory (227 KB minus 1 KB per CTA and the kernel's static 2 KB), else fewer
+    // -- two CTAs of 7 hide more latency than one of 8 -- but a power of two when warps share views
+    int warps = LIN_WARPS;
+    if (split == 1) while (warps > 4 && 2 * (lin_smem_for(P, warps) + 3 * 1024) > 227 * 1024) warps--;
+    ctx->lin_warps = warps;
+    REQUIRE(lin_smem_for(P, warps) <= 220 * 1024, MCBA_ERR_UNSUPPORTED, "too many boards for the linearisation kernel's shared memory");
     CK(ctx->spart.alloc((size_t)ctx->lin_grid * C * lin_record_doubles(P.T, P.D, B)));
     CK(ctx->bpart.alloc((size_t)C * B * 42));
     CK(ctx->sred.alloc((size_t)C * lin_record_doubles(P.T, P.D, B)));
@@ -587,7 +603,8 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   // persistent trust-region kernel (lm_kernel.cuh): grid, frame chunks of the Schur SYRK, partial-sum records, barrier words
   {
     const int F_free = P.motion_on ? F : 0;
-    ctx->lm_grid = std::max(1, std::min(ctx->num_sms, std::max(4, (F_free + LM_WARPS - 1) / LM_WARPS + (int)(((size_t)P.n_s * P.n_s) / (LM_THREADS * 16)))));
+    // the whole machine except for toy problems: a phase's latency falls with the CTAs that share it, a grid barrier costs ~1 us either way
+    ctx->lm_grid = (size_t)std::max(F_free, 1) * std::max(P.n_s, 1) >= 4096 ? ctx->num_sms : std::max(1, std::min(ctx->num_sms, 8));
     const int fbq = std::max(P.fb, 6), fr = syrk_fr(fbq);
     const int tiles = (std::max(P.n_s, 1) + SYRK_TILE - 1) / SYRK_TILE, npair = tiles * (tiles + 1) / 2;
     int chunks = std::max(1, std::min((F_free + fr - 1) / fr, ctx->lm_grid / std::max(1, npair)));
@@ -600,6 +617,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     CK(ctx->part_scale.alloc((size_t)ctx->num_sms * 6));
     CK(ctx->part_step.alloc((size_t)ctx->num_sms * 2));
     CK(ctx->part_quad.alloc(8 + (size_t)(F + (P.n_s + LM_THREADS - 1) / LM_THREADS + 2) * 5));
+    CK(ctx->prof.alloc(16)); CK(cudaMemsetAsync(ctx->prof.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     CK(ctx->lm_bar.alloc(2)); CK(cudaMemsetAsync(ctx->lm_bar.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (!ctx->peer_seq_dev.p) { CK(ctx->peer_seq_dev.alloc(1)); CK(cudaMemsetAsync(ctx->peer_seq_dev.p, 0, sizeof(unsigned long long), ctx->stream)); }
     CK(ctx->frame_cost.alloc((size_t)std::max(F, 1)));
@@ -706,6 +724,7 @@ int mcba_create(int device, mcba_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { g_create_error = "cudaStreamCreate failed"; delete ctx; return MCBA_ERR_CUDA; }
   ctx->stream = ctx->own_stream;
   { const char* e = getenv("MCBA_GRAPH"); if (e && std::string(e) == "0") ctx->use_graph = false; }
+  { const char* e = getenv("MCBA_PROF"); if (e && std::string(e) == "1") { ctx->profiling = true; ctx->use_graph = false; } }
 #define MMA_ATTR(MODEL) \
   cudaFuncSetAttribute(k_views_mma<MODEL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
   cudaFuncSetAttribute(k_views_mma<MODEL, VIEW_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
@@ -1477,6 +1496,8 @@ int mcba_solve(mcba_ctx* ctx, const mcba_solve_opts* opts, mcba_solve_result* re
   REQUIRE(ctx->world == 1 || ctx->peer_ready, MCBA_ERR_STATE, "several ranks: the exchanges run over NVLink peer memory (mcba_peer_export / mcba_peer_import first)");
   CK(cudaSetDevice(ctx->device));
   const DeviceProblem& P = ctx->P;
+  REQUIRE(ctx->world == 1 || (size_t)P.n_s * P.n_s + 2 * (size_t)P.n_s + 16 <= (size_t)ctx->peer_cap, MCBA_ERR_STATE,
+          "the reduced normal equations do not fit the NVLink exchange slots: export larger peer buffers (mcba_peer_export cap >= n_s^2 + 2 n_s + 16)");
   cudaStream_t s = ctx->stream;
   const int n = P.n;
   memset(result, 0, sizeof(*result));

@@ -23,19 +23,55 @@ def frame_owner(F, world):
 
 
 def init_comm(engine, rank, world, group=None, peer_cap=None):
-  """Create the engine's communicator: rank 0 makes the NCCL unique id, torch.distributed broadcasts it; then every rank
-  exports an NVLink exchange buffer (IPC handle) and imports everyone else's, so that the latency-bound exchanges of an
-  LM iteration run as one-shot peer-memory all-reduces (csrc/peer_allreduce.cuh).  MCBA_PEER=0 keeps everything on NCCL."""
+  """Create the engine's communicator: rank and world, then every rank exports an NVLink exchange buffer (IPC handle) and imports
+  everyone else's -- the exchanges of an LM iteration run inside the solver kernel over these peer mappings (csrc/lm_kernel.cuh:
+  exchange()).  `peer_cap` = doubles per slot: it must hold the reduced normal equations, n_s^2 + n_s (default 2 Mi doubles:
+  n_s up to ~1400, i.e. 64 cameras with their intrinsics; 2 x world slots of that size per rank)."""
   import os
   import torch.distributed as dist
   uid = [engine.comm_unique_id() if rank == 0 else None]
   dist.broadcast_object_list(uid, src=0, group=group)
   engine.comm_init(uid[0], rank, world)
-  if world > 1 and os.environ.get("MCBA_PEER", "1") != "0":
-    cap = int(os.environ.get("MCBA_PEER_CAP", peer_cap or (1 << 16)))
+  if world > 1:
+    cap = int(os.environ.get("MCBA_PEER_CAP", peer_cap or (1 << 21)))
     handles = [None] * world
     dist.all_gather_object(handles, engine.peer_export(cap), group=group)
     engine.peer_import(handles)
+
+
+_dist_engines = {}       # (device, world, group id) -> Engine with a communicator and peer buffers; never the process-wide single-GPU engine
+
+
+class _sharded_engine:
+  """Context manager: a DEDICATED engine (own C-ABI context, communicator, NVLink exchange buffers) stands in for the process-wide
+  one while a sharded call runs, and is taken out again afterwards -- a later plain `Calibration.bundle_adjust()` on this process
+  must not find a context that still exchanges with the other ranks (it would wait for peers that never call)."""
+  def __init__(self, rank, world, group=None, engine=None):
+    self.rank, self.world, self.group, self.engine = rank, world, group, engine
+
+  def __enter__(self):
+    from . import calibration
+    from .engine import Engine
+    dev = calibration.default_device()
+    self.dev, self.saved = dev, calibration._engines.get(dev)
+    if self.engine is None:
+      if getattr(self.saved, "world", 1) == self.world:
+        self.engine = self.saved             # the caller installed a communicating engine itself (bench.py, tests)
+      else:
+        key = (dev, self.world, id(self.group))
+        if key not in _dist_engines:
+          eng = Engine(dev)
+          init_comm(eng, self.rank, self.world, self.group)
+          _dist_engines[key] = eng
+        self.engine = _dist_engines[key]
+    calibration._engines[dev] = self.engine
+    return self.engine
+
+  def __exit__(self, *exc):
+    from . import calibration
+    if self.saved is None: calibration._engines.pop(self.dev, None)
+    else: calibration._engines[self.dev] = self.saved
+    return False
 
 
 def _slice_motion(motion, a, b):
@@ -96,13 +132,10 @@ def bundle_adjust(calib, group=None, **kwargs):
   """Multi-GPU `Calibration.bundle_adjust`: call on every rank with the same full Calibration; returns the same
   full, updated Calibration on every rank."""
   import torch.distributed as dist
-  from .calibration import get_engine
   rank, world = dist.get_rank(group), dist.get_world_size(group)
   local, (a, b) = shard_calibration(calib, rank, world)
-  eng = get_engine()
-  if getattr(eng, "world", 1) != world:
-    init_comm(eng, rank, world, group)
-  out_local = local.bundle_adjust(**kwargs)
+  with _sharded_engine(rank, world, group):
+    out_local = local.bundle_adjust(**kwargs)
   motion = merge_motion(calib.motion, out_local.motion, calib.size.rig_poses, rank, world, group)
   out = calib.copy(cameras=out_local.cameras, camera_poses=out_local.camera_poses, board_poses=out_local.board_poses, motion=motion)
   out.__dict__["last_solve"] = out_local.last_solve
@@ -135,9 +168,11 @@ def adjust_outliers(calib, comm=None, group=None, num_adjustments=3, select_scal
   rank, world = comm.rank, comm.world
   local, (a, b) = shard_calibration(calib, rank, world)
   eng = get_engine()
-  if getattr(eng, "world", 1) != world:
-    init_comm(eng, rank, world, group)
-  out_local = local._adjust_outliers_resident(num_adjustments, select_scale, select_outliers, comm=comm, **kwargs)
+  if getattr(eng, "world", 1) == world:        # the caller's engine already talks to the other ranks (thread ranks of the CPU tests, bench.py)
+    out_local = local._adjust_outliers_resident(num_adjustments, select_scale, select_outliers, comm=comm, **kwargs)
+  else:
+    with _sharded_engine(rank, world, group):
+      out_local = local._adjust_outliers_resident(num_adjustments, select_scale, select_outliers, comm=comm, **kwargs)
   F = calib.size.rig_poses
   motion = merge_motion(calib.motion, out_local.motion, F, rank, world, group, comm)
   mask = None

@@ -122,6 +122,42 @@ def test_converged_solution_matches_dense_exact_oracle(name):
   assert np.allclose(out.motion.poses[~ok_f], calib.motion.poses[~ok_f], atol=1e-12)
 
 
+def test_many_cameras_use_the_cooperative_blocked_reduced_solve():
+  """n_s > 128 (BASELINE configs[3], configs[4]: 16 and 64 cameras): the reduced system is factored by the grid (32-wide panels, diagonal
+  blocks by one warp, csrc/lm_kernel.cuh) instead of by one CTA.  Nine cameras with their intrinsics give n_s = 54 + 6 + 90 = 150:
+  normal equations against finite differences of the oracle, converged cost against scipy's dense exact trust region, and two
+  identical solves must agree bit for bit (no atomics on data anywhere on this path)."""
+  from multical_b200 import synthetic
+  scene = synthetic.make_scene(C=9, F=4, vis=0.12, seed=11, rig="dome")
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  eng = calib._upload(calib.inliers)
+  assert eng.num_params == prob.param_vec.size and 6 * 9 + 6 + 10 * 9 == 150
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14,
+                               max_nfev=300, method="trf", tr_solver="exact")
+  out = calib.bundle_adjust(tolerance=1e-13, xtol=1e-13, gtol=1e-13, max_iterations=200)
+  assert abs(out.last_solve.cost - ref.cost) <= 1e-8 * ref.cost, (out.last_solve.cost, ref.cost)
+  a, b = calib.bundle_adjust().last_solve, calib.bundle_adjust().last_solve
+  assert a.cost == b.cost and np.array_equal(np.array(a.log, float), np.array(b.log, float), equal_nan=True) and a.chol_retries == 0
+
+
+def test_two_identical_solves_agree_bit_for_bit():
+  """The reference is bit-reproducible run to run (single-threaded numpy / scipy, calibration.py:204-212).  So is this engine on the
+  standard path: fixed-order sums everywhere (per-CTA records, frame-chunk partials, rank-ordered exchanges), no atomics on data."""
+  scene, z, calib, prob = make("cube3_3x6")
+  runs = [calib.bundle_adjust(tolerance=1e-9, max_iterations=30) for _ in range(3)]
+  for r in runs[1:]:
+    assert r.last_solve.cost == runs[0].last_solve.cost
+    assert np.array_equal(np.array(r.last_solve.log, float), np.array(runs[0].last_solve.log, float), equal_nan=True)
+    assert np.array_equal(r.param_vec, runs[0].param_vec)
+  eng = calib._upload(calib.inliers)
+  H0, g0, c0 = eng.linearize(z["x1"])
+  H1, g1, c1 = eng.linearize(z["x1"])
+  assert np.array_equal(H0, H1) and np.array_equal(g0, g1) and c0 == c1
+
+
 @pytest.mark.parametrize("loss", ["soft_l1", "huber", "cauchy", "arctan"])
 def test_robust_losses_follow_scipy(loss):
   scene = synthetic.make_scene(C=2, F=6, vis=0.5, seed=31, outlier_fraction=0.03)

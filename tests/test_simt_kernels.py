@@ -56,6 +56,8 @@ test_empty_and_ragged_inputs = gp.test_empty_and_ragged_inputs
 test_board_points_as_parameters = gp.test_board_points_as_parameters
 test_iteration_table_matches_the_trf_model = gp.test_iteration_table_matches_the_trf_model
 test_degenerate_block_selections = gp.test_degenerate_block_selections
+test_many_cameras_use_the_cooperative_blocked_reduced_solve = gp.test_many_cameras_use_the_cooperative_blocked_reduced_solve
+test_two_identical_solves_agree_bit_for_bit = gp.test_two_identical_solves_agree_bit_for_bit
 
 # ---- tests/test_gpu_table.py on the interpreter
 test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors = gt.test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors
