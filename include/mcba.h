@@ -90,12 +90,16 @@ const char* mcba_last_error(const mcba_ctx* ctx);   /* ctx may be NULL: returns 
 int  mcba_set_stream(mcba_ctx* ctx, void* cuda_stream);   /* e.g. torch.cuda.current_stream().cuda_stream */
 int  mcba_version(void);
 
-/* -- multi-GPU: one context per process/GPU; frames are sharded across ranks ---- */
-int  mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]);      /* rank 0, then broadcast by the host   */
+/* -- multi-GPU: one context per process/GPU; frames are sharded across ranks ----
+ * mcba_comm_init records (rank, world <= 16); mcba_comm_unique_id is kept for the usual bootstrap shape (rank 0 makes an id, the host
+ * broadcasts it) and returns a constant tag.  The exchanges of a solve -- shared gradient / diagonal / cost, g_h^T A g_h, the reduced
+ * normal equations S and rhs, the subspace sums: four per LM iteration -- run INSIDE the solver kernel over NVLink peer memory
+ * (push to every rank's slot, sequence flag, reduce in rank order: bit-identical results on every rank; csrc/lm_kernel.cuh exchange()).
+ * Every rank exports one buffer as an IPC handle (64 bytes), the host all-gathers the handles (torch.distributed / NCCL is the
+ * bootstrap), every rank imports all of them.  cap_doubles per slot must hold n_s^2 + 2 n_s + 16; a rank that stops answering makes
+ * its peers' solves fail with MCBA_ERR_NCCL after a bounded wait instead of hanging their GPUs. */
+int  mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]);
 int  mcba_comm_init(mcba_ctx* ctx, const char id[128], int rank, int world);
-
-/* Optional: exchange steps over NVLink peer memory instead of NCCL (payloads up to cap_doubles per step; larger ones keep
- * using NCCL).  Every rank exports one IPC handle (64 bytes), the host all-gathers them, every rank imports all of them. */
 int  mcba_peer_export(mcba_ctx* ctx, int64_t cap_doubles, char out_handle[64]);
 int  mcba_peer_import(mcba_ctx* ctx, const char* handles /* world x 64 bytes in rank order */);
 

@@ -19,6 +19,7 @@ namespace mcba {
 
 constexpr int LIN_WARPS = 8;           // at most; the host takes fewer when two CTAs of 8 would not fit an SM's shared memory
 constexpr int LIN_THREADS = LIN_WARPS * 32;
+constexpr int LIN_KPAD = 36;           // 32 staged residual rows + 4: (column stride mod 16 doubles) == 4 -> conflict-free fragment loads
 constexpr int LIN_MAXV = 96;           // views of a frame staged in shared memory (more: the list is read from global memory)
 constexpr int LIN_MAXB = 8;            // board pose tables staged per frame (more boards: the tables are read from global memory)
 
@@ -45,7 +46,7 @@ struct LinShape {
 template <int MODEL, bool ROLL>
 __device__ __forceinline__ void view_chunk(const DeviceProblem& p, int loss, double f_scale, const ViewPose& vp, const ViewPose& vpe, const double* k,
                                            const double* bp, double inv_h, int base, int end, int lane, double* stage,
-                                           double (&acc)[LinShape<MODEL, ROLL>::NPAIR][2], double& cost_acc) {
+                                           double (&acc)[LinShape<MODEL, ROLL>::NPAIR][2], double& cost_acc, double2 ob, int pi) {
   using S = LinShape<MODEL, ROLL>;
   constexpr int ND = S::ND, KO = S::KO, D = S::D, NC = S::NC, NT = S::NT;
   const int grp = lane >> 2, tig = lane & 3;
@@ -54,8 +55,6 @@ __device__ __forceinline__ void view_chunk(const DeviceProblem& p, int loss, dou
 #pragma unroll
   for (int i = 0; i < NC; i++) { gu[i] = 0.0; gv[i] = 0.0; }
   if (idx < end) {
-    const double2 ob = p.obs[idx];
-    const int pi = p.pid[idx];
     const double X[3] = {bp[3 * pi], bp[3 * pi + 1], bp[3 * pi + 2]};
     const double tau = ob.y * inv_h;
     double Xc[3], Xs[3], Xe[3];
@@ -102,25 +101,34 @@ __device__ __forceinline__ void view_chunk(const DeviceProblem& p, int loss, dou
     for (int i = 0; i < ND; i++) { gu[KO + 4 + i] = ku[4 + i] * wu; gv[KO + 4 + i] = kv[4 + i] * wv; }
     gu[D] = ru; gv[D] = rv;                      // residual column: Gt^T Gt then carries G^T r as well
   }
-  // stage: rows 2*lane (u) and 2*lane+1 (v); one 16-byte store per column, consecutive lanes -> consecutive addresses
+  // The 64 residual rows of the chunk go through the stage buffer in two halves of 32 (lanes 0-15, then lanes 16-31): half the shared
+  // memory per warp, so that twice the warps fit an SM (the pass is latency-bound per warp: resident warps are what hides it).
+  // rows 2*l (u) and 2*l+1 (v) of a half; one 16-byte store per column, consecutive lanes -> consecutive addresses.
+  const int cnt = min(32, end - base);
 #pragma unroll
-  for (int j = 0; j < NC; j++)
-    *reinterpret_cast<double2*>(stage + j * MMA_KPAD + 2 * lane) = make_double2(gu[j], gv[j]);
-  __syncwarp();
-  // k-steps of 4 residual rows; fragment of column tile I = Gt[k0 + tig][8 I + grp] serves as A (row tile) and B (col tile)
-  const int ksteps = (2 * min(32, end - base) + 3) >> 2;       // ragged last chunk: skip all-zero row groups
+  for (int half = 0; half < 2; half++) {
+    if ((lane >> 4) == half) {
+#pragma unroll
+      for (int j = 0; j < NC; j++)
+        *reinterpret_cast<double2*>(stage + j * LIN_KPAD + 2 * (lane & 15)) = make_double2(gu[j], gv[j]);
+    }
+    __syncwarp();
+    // k-steps of 4 residual rows; fragment of column tile I = Gt[k0 + tig][8 I + grp] serves as A (row tile) and B (col tile)
+    const int rows = 2 * max(0, min(16, cnt - 16 * half));
+    const int ksteps = (rows + 3) >> 2;                          // ragged last chunk: skip all-zero row groups
 #pragma unroll 4
-  for (int ks = 0; ks < ksteps; ks++) {
-    double fr[NT];
+    for (int ks = 0; ks < ksteps; ks++) {
+      double fr[NT];
 #pragma unroll
-    for (int I = 0; I < NT; I++) fr[I] = stage[(8 * I + grp) * MMA_KPAD + 4 * ks + tig];
-    int t = 0;
+      for (int I = 0; I < NT; I++) fr[I] = stage[(8 * I + grp) * LIN_KPAD + 4 * ks + tig];
+      int t = 0;
 #pragma unroll
-    for (int I = 0; I < NT; I++)
+      for (int I = 0; I < NT; I++)
 #pragma unroll
-      for (int J = I; J < NT; J++) { dmma884(acc[t][0], acc[t][1], fr[I], fr[J]); t++; }
+        for (int J = I; J < NT; J++) { dmma884(acc[t][0], acc[t][1], fr[I], fr[J]); t++; }
+    }
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 struct LinArgs {
@@ -138,7 +146,9 @@ __host__ __device__ inline int lin_record_doubles(int T, int D, int B) { return 
 __host__ __device__ inline size_t lin_warp_doubles(int NC, int T, int D, int FB, int nin, int B, int NP) {
   (void)nin;
   const int KO = 6 * NP, PC = 6 * (NP + 1);
-  return ((size_t)NC * MMA_KPAD           // stage (chunk loop) = Ms | T^t | map scratch (epilogue)
+  const int PT = (PC + 7) / 8;
+  const int need = NC * NC + 8 * PT * NC + 24 * NP, chunk = NC * LIN_KPAD;
+  return ((size_t)(((chunk > need ? chunk : need) + 1) & ~1)      // stage (chunk loop, 32 rows at a time) = Ms | T^t | map scratch (epilogue)
        + KO * PC + 12 * NP                // E: twist maps of the view [KO][PC] | chain cache R_cf, t_cf
        + (size_t)B * 6 * FB               // Wb: this warp's partial board rows of W_f
        + FB * FB + FB                     // hacc: H_ff | g_f partial
@@ -150,7 +160,7 @@ __host__ __device__ inline size_t lin_warp_doubles(int NC, int T, int D, int FB,
 }
 // dynamic shared memory of a CTA of `warps` warps: the warps' slices, then the pose tables staged per frame (frame [NP] | boards [min(B, LIN_MAXB)])
 __host__ __device__ inline size_t lin_smem_doubles(int NC, int T, int D, int FB, int nin, int B, int NP, int warps) {
-  return (size_t)warps * lin_warp_doubles(NC, T, D, FB, nin, B, NP) + (size_t)24 * (NP + (B < LIN_MAXB ? B : LIN_MAXB));
+  return (size_t)warps * lin_warp_doubles(NC, T, D, FB, nin, B, NP) + (size_t)24 * (2 * NP + (B < LIN_MAXB ? B : LIN_MAXB));      // frame table x 2 (double buffer) | board tables
 }
 
 // fire-and-forget fp64 add to global memory.  Every address of a CTA's records is only ever updated by ONE lane of ONE warp of that CTA,
@@ -159,6 +169,26 @@ __host__ __device__ inline size_t lin_smem_doubles(int NC, int T, int D, int FB,
 __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+
+// ---- bulk asynchronous copies (the 1-D form of the Tensor Memory Accelerator, cp.async.bulk) with an mbarrier as completion signal:
+// the small parameter blocks a CTA needs -- the frame's pose table(s), the board tables -- travel HBM/L2 -> shared memory without
+// passing through registers, and the NEXT frame's table is in flight while the current frame is worked on.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile("{ .reg .pred p_; MBW_: mbarrier.try_wait.parity.shared::cta.b64 p_, [%0], %1; @p_ bra.uni MBD_; bra.uni MBW_; MBD_: }"
+               ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // per-warp shared-memory layout of k_linearize (doubles from the warp's base).  The epilogue's per-view scratch aliases the stage
 // buffer of the chunk loop; what must survive from view to view lies behind it.
@@ -171,8 +201,8 @@ struct LinLayout {
   static constexpr int Ms = 0;                                  // [NC][NC] full symmetric, column D = G^T r
   static constexpr int Tt = Ms + S::NC * S::NC;                 // [8 PT][NC]   T^t = E^T M[xi, :]
   static constexpr int scr = Tt + 8 * PT * S::NC;               // 24 NP doubles: R J_L products and chain translations while a map is built
-  static constexpr int stage_end = S::NC * MMA_KPAD;
-  static_assert(scr + 24 * S::NP <= stage_end, "the epilogue's scratch must fit the stage buffer");
+  static constexpr int stage_need = scr + 24 * S::NP;           // what the epilogue needs
+  static constexpr int stage_end = ((S::NC * LIN_KPAD > stage_need ? S::NC * LIN_KPAD : stage_need) + 1) & ~1;
   static_assert((2 * S::NPAIR + 1) * 32 <= stage_end, "the fragments of a view part must fit the warp's stage buffer");
   static constexpr int NHF = S::FB * S::FB + S::FB;             // H_ff | g_f
   static constexpr int NWC = S::D * S::FB;                      // sum over the camera's boards of Tf = M[:, xi] Af (D x FB)
@@ -331,11 +361,16 @@ __device__ __noinline__ void lin_view_epilogue(const DeviceProblem& p, const Lin
       for (int o = lane; o < KO * 6 * NP; o += 32) Em[(o / (6 * NP)) * PC + o % (6 * NP)] = 0.0;
   }
   // the camera's raw moment sum: upper triangle | G^T r | cost
-  for (int o = lane; o < D * (D + 1); o += 32) {
-    const int i = o / (D + 1), j = o % (D + 1);
-    if (j == D) macc[E_ + i] += Ms[i * NC + D];
-    else if (i <= j) macc[tri_index(D, i, j)] += Ms[i * NC + j];
-  }
+#pragma unroll
+  for (int I = 0; I < NT; I++)
+#pragma unroll
+    for (int J = I; J < NT; J++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {                     // the fragment positions of the upper-triangle tiles: every element exactly once
+        const int i = 8 * I + grp, j = 8 * J + 2 * tig + h;
+        if (i < D && j < D && i <= j) macc[tri_index(D, i, j)] += Ms[i * NC + j];
+        else if (i < D && j == D) macc[E_ + i] += Ms[i * NC + D];
+      }
   if (lane == 0) { macc[T - 1] += cost_acc; tl[0] += cost_acc; tl[3] = 1.0; tl[4] = f; }
   __syncwarp();
   if (!(frames_on || boards_on)) return;
@@ -411,27 +446,37 @@ k_linearize(DeviceProblem p, LinArgs a) {
   const bool frames_on = p.motion_on != 0;
   const size_t wd = lin_warp_doubles(NC, T, D, FB, NIN, B, NP);
   double* w = lsm + (size_t)warp * wd;          // this warp's slice; w[0 .. NC*MMA_KPAD) is the stage buffer of the chunk loop
-  // pose tables staged in shared memory: this frame's [NP], then the boards' (they do not change during the launch)
-  PoseT* ftab = reinterpret_cast<PoseT*>(lsm + (size_t)nwarps * wd);
+  // pose tables staged in shared memory by bulk asynchronous copies: the frame's [NP] (double buffered: the next frame's is in flight
+  // while this one is worked on), then the boards' (they do not change during the launch)
+  __shared__ __align__(8) unsigned long long tbar[3];
+  PoseT* ftab2 = reinterpret_cast<PoseT*>(lsm + (size_t)nwarps * wd);       // [2][NP]
   const bool boards_staged = B <= LIN_MAXB;
-  const PoseT* btab = boards_staged ? ftab + NP : p.board_T;
+  const PoseT* btab = boards_staged ? ftab2 + 2 * NP : p.board_T;
+  if (tid == 0) { mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1); mbar_init(&tbar[2], 1); fence_barrier_init(); }
   const int rec = lin_record_doubles(T, D, B);
   double* myrec = a.spart + (size_t)blockIdx.x * p.C * rec;
 
   // this CTA's records start at zero; the leader warps' running sums too
   for (int i = tid; i < p.C * rec; i += nthreads) myrec[i] = 0.0;
-  if (boards_staged) {
-    double* dst = reinterpret_cast<double*>(ftab + NP);
-    const double* src = reinterpret_cast<const double*>(p.board_T);
-    for (int i = tid; i < 24 * B; i += nthreads) dst[i] = src[i];
-  }
   if (leader) {
     for (int i = L::E + lane; i < L::tail(B); i += 32) w[i] = 0.0;       // E | chain | Wb | hacc | wacc | macc | ub
     if (lane == 0) { double* tl = w + L::tail(B); tl[0] = 0.0; tl[1] = -1.0; tl[2] = -1.0; tl[3] = 0.0; tl[4] = -1.0; }
   }
   __syncthreads();
+  if (tid == 0) {
+    if (boards_staged) { mbar_expect_tx(&tbar[2], (unsigned)(sizeof(PoseT) * B)); bulk_g2s(ftab2 + 2 * NP, p.board_T, (unsigned)(sizeof(PoseT) * B), &tbar[2]); }
+    if ((int)blockIdx.x < p.F) { mbar_expect_tx(&tbar[0], (unsigned)(sizeof(PoseT) * NP)); bulk_g2s(ftab2, p.frame_T + (size_t)blockIdx.x * NP, (unsigned)(sizeof(PoseT) * NP), &tbar[0]); }
+  }
+  if (boards_staged) mbar_wait(&tbar[2], 0);
 
-  for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
+  int it = 0;
+  for (int f = blockIdx.x; f < p.F; f += gridDim.x, it++) {
+    const PoseT* ftab = ftab2 + (it & 1) * NP;
+    if (tid == 0 && f + (int)gridDim.x < p.F) {       // the next frame's table -> the other buffer (every warp left it at the end of the previous frame)
+      unsigned long long* nb = &tbar[(it + 1) & 1];
+      mbar_expect_tx(nb, (unsigned)(sizeof(PoseT) * NP));
+      bulk_g2s(ftab2 + ((it + 1) & 1) * NP, p.frame_T + (size_t)(f + gridDim.x) * NP, (unsigned)(sizeof(PoseT) * NP), nb);
+    }
     const int v0 = p.frame_view_start[f], v1 = p.frame_view_start[f + 1];
     const bool staged = v1 - v0 <= LIN_MAXV;
     if (staged) {
@@ -440,15 +485,11 @@ k_linearize(DeviceProblem p, LinArgs a) {
         if (i < v1 - v0) { fv_cam[i] = p.view_cam[v0 + i]; fv_board[i] = p.view_board[v0 + i]; }
       }
     }
-    {
-      double* dst = reinterpret_cast<double*>(ftab);
-      const double* src = reinterpret_cast<const double*>(p.frame_T + (size_t)f * NP);
-      for (int i = tid; i < 24 * NP; i += nthreads) dst[i] = src[i];
-    }
     if (frames_on) {
       double* Wf = a.W + (size_t)f * n_s * FB;
       for (int i = tid; i < n_s * FB; i += nthreads) Wf[i] = 0.0;
     }
+    mbar_wait(&tbar[it & 1], (unsigned)((it >> 1) & 1));       // this frame's pose table(s) have landed
     if (leader) {
       for (int i = L::Wb + lane; i < L::wacc(B); i += 32) w[i] = 0.0;      // Wb | hacc
       if (lane == 0) (w + L::tail(B))[0] = 0.0;
@@ -484,8 +525,16 @@ k_linearize(DeviceProblem p, LinArgs a) {
 #pragma unroll
         for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
         const double* bp = p.board_pts + (size_t)b * p.P * 3;
-        for (int base = beg + 32 * sub; base < end; base += 32 * split)
-          view_chunk<MODEL, ROLL>(p, a.loss, a.f_scale, vp, vpe, k, bp, inv_h, base, end, lane, w, acc, cost_acc);
+        // the next chunk's observation / point id are in flight while this chunk is computed (one L2 round trip less per chunk on the
+        // dependent chain  point id -> board point -> projection)
+        double2 ob_n = make_double2(0.0, 0.0); int pi_n = 0;
+        { const int i0 = beg + 32 * sub + lane; if (i0 < end) { ob_n = p.obs[i0]; pi_n = p.pid[i0]; } }
+        for (int base = beg + 32 * sub; base < end; base += 32 * split) {
+          const double2 ob = ob_n; const int pi = pi_n;
+          const int i1 = base + 32 * split + lane;
+          if (i1 < end) { ob_n = p.obs[i1]; pi_n = p.pid[i1]; }
+          view_chunk<MODEL, ROLL>(p, a.loss, a.f_scale, vp, vpe, k, bp, inv_h, base, end, lane, w, acc, cost_acc, ob, pi);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
       }

@@ -56,6 +56,17 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned n
   __syncthreads();
 }
 
+// 1/sqrt(x) for x in [1e-30, 1e30]: single-precision seed + two Newton steps in double (relative error ~1e-7 -> ~2e-14 -> < 1e-16).
+// A dozen instructions on the critical path of a Cholesky column instead of the ~40 of the library routine (measured: the pivot warp's
+// INSTRUCTION COUNT, at ~5 cycles per dependent issue, is what a column costs -- not the fp64 latencies).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r = (double)rsqrtf((float)x);
+  double e = fma(-x * r, r, 1.0);
+  r = fma(0.5 * r, e, r);
+  e = fma(-x * r, r, 1.0);
+  return fma(0.5 * r, e, r);
+}
+
 struct LmPeer {                      // NVLink peer-memory exchange (one buffer per rank, IPC-mapped into every rank; layout of peer_allreduce.cuh)
   int rank, world, cap;
   double* base[PEER_MAX_WORLD];
@@ -192,7 +203,7 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
       double s = A[j * FB + j];
 #pragma unroll
       for (int k = 0; k < FB; k++) if (k < j) s -= Lr[j * FB + k] * Lr[j * FB + k];
-      const double rs = rsqrt(fmax(s, 1e-300));
+      const double rs = fast_rsqrt(fmin(fmax(s, 1e-30), 1e30));
       Lr[j * FB + j] = rs;                                  // 1 / L_jj
 #pragma unroll
       for (int i = 0; i < FB; i++) {
@@ -420,7 +431,7 @@ __device__ __forceinline__ void chol_diag_body(int n, int kb, double* S, double*
     if (tx == kt) {
       const double akk = piv[0];
       if (ty == kt && k < nb && !(akk > 0.0)) *chol_fail += 1;
-      const double rs = rsqrt(fmax(akk, 1e-300));
+      const double rs = fast_rsqrt(fmin(fmax(akk, 1e-30), 1e30));
       if (ty == kt) invd[k] = rs;
 #pragma unroll
       for (int p = 0; p < 2; p++) {
@@ -472,6 +483,213 @@ __device__ __forceinline__ void chol_diag_body(int n, int kb, double* S, double*
   }
   __syncthreads();
 }
+// ---- reduced solve, n <= 128: one CTA of 16 x 16 threads, matrix cyclically distributed in registers: thread (ty,tx) owns
+// A[ty + 16 p][tx + 16 q].  After every 16 columns the register tile is ROTATED (a[p][q] <- a[p+1][q+1]) so that the active pivot
+// block is always a[0][0] / column block q = 0: every register index on the pivot path is static, the path is ~45 instructions
+// (round 1's switch over the column block: ~150).  The factor goes to shared memory column by column as it is produced.
+template <int R>
+__device__ __forceinline__ void chol_rot_body(int n, const double* Sg, const double* rhs, const double* gh, double reg, int* chol_fail, double* out, double* shm) {
+  const int ld = n | 1;
+  double* Lm = shm;                       // n x ld factor
+  double* colbuf = Lm + (size_t)n * ld;   // n (+16 pad)
+  double* invd = colbuf + n + 16;         // n
+  double* piv = invd + n;                 // 2
+  const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+  double a[R][R];
+#pragma unroll
+  for (int p = 0; p < R; p++)
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int i = ty + 16 * p, j = tx + 16 * q;
+      a[p][q] = (i < n && j < n) ? __ldcg(&Sg[(size_t)j * n + i]) + (i == j ? reg : 0.0) : 0.0;     // S is symmetric: coalesced read
+    }
+  __syncthreads();
+  if (tid == 0) piv[0] = a[0][0];
+  __syncthreads();
+  const int nblk = (n + 15) >> 4;
+  for (int kb = 0; kb < nblk; kb++) {
+    const int k0 = 16 * kb;
+    const int kend = min(16, n - k0);
+    for (int kt = 0; kt < kend; kt++) {
+      const int k = k0 + kt;
+      if (tx == kt) {                      // the 16 threads that hold column k (block column 0 of the rotated tile)
+        const double akk = piv[0];
+        const double rs = fast_rsqrt(fmin(fmax(akk, 1e-30), 1e30));
+        if (ty == kt) { invd[k] = rs; if (!(akk > 0.0)) *chol_fail += 1; }
+#pragma unroll
+        for (int p = 0; p < R; p++) {
+          const int i = k0 + ty + 16 * p;
+          if (i >= k && i < n) { const double lv = a[p][0] * rs; colbuf[i] = lv; Lm[i * ld + k] = lv; }
+        }
+      }
+      __syncthreads();
+      double ci[R], cj[R];
+#pragma unroll
+      for (int p = 0; p < R; p++) { const int i = k0 + ty + 16 * p; ci[p] = (i > k && i < n) ? colbuf[i] : 0.0; }
+#pragma unroll
+      for (int q = 0; q < R; q++) { const int j = k0 + tx + 16 * q; cj[q] = (j > k && j < n) ? colbuf[j] : 0.0; }
+#pragma unroll
+      for (int p = 0; p < R; p++)
+#pragma unroll
+        for (int q = 0; q < R; q++) a[p][q] -= ci[p] * cj[q];       // (also touches the unused upper triangle: harmless)
+      // publish the next pivot: thread (kt+1, kt+1) of this block, or (0,0) of the next block (its a[1][1] before the rotation)
+      if (kt + 1 < 16) { if (ty == kt + 1 && tx == kt + 1) piv[0] = a[0][0]; }
+      else if (R > 1) { if (ty == 0 && tx == 0) piv[0] = a[R > 1 ? 1 : 0][R > 1 ? 1 : 0]; }
+      __syncthreads();
+    }
+    // rotate: the next 16 x 16 pivot block moves to a[0][0]
+#pragma unroll
+    for (int p = 0; p < R; p++)
+#pragma unroll
+      for (int q = 0; q < R; q++) a[p][q] = (p + 1 < R && q + 1 < R) ? a[p + 1 < R ? p + 1 : p][q + 1 < R ? q + 1 : q] : 0.0;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    constexpr int RS = (R * 16 + 31) / 32;       // rows per lane
+    const int lane = tid;
+    double bs[RS];
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; bs[s2] = i < n ? __ldcg(&rhs[i]) + gh[i] : 0.0; }
+    // forward: L y = b
+#pragma unroll
+    for (int s1 = 0; s1 < RS; s1++) {
+      for (int kk = 0; kk < 32; kk++) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) break;
+        const double yk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = yk;
+#pragma unroll
+        for (int s2 = s1; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i > k && i < n) bs[s2] -= Lm[i * ld + k] * yk; }
+      }
+    }
+    // backward: L^T x = y
+#pragma unroll
+    for (int s1 = RS - 1; s1 >= 0; s1--) {
+      for (int kk = 31; kk >= 0; kk--) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) continue;
+        const double xk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = xk;
+#pragma unroll
+        for (int s2 = 0; s2 <= s1; s2++) { const int i = lane + 32 * s2; if (i < k) bs[s2] -= Lm[k * ld + i] * xk; }
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i < n) out[i] = bs[s2]; }
+  }
+  __syncthreads();
+}
+
+// ---- reduced solve, n <= CHOL_V3_MAX: one CTA, ONE block barrier per column.  Warp w owns the columns j == w (mod 8), lane l the rows
+// i == l (mod 32); the matrix lives in registers (a[q][r] = A[l + 32 r][w + 8 q]).  Per column k: every thread applies the rank-1
+// update of the scaled column k (read from shared memory), but the warp that owns column k+1 updates THAT column first, takes its
+// pivot, scales it and publishes it in the other half of the double-buffered column store -- so the next step can start right after
+// the barrier (look-ahead), and the remaining updates are off the critical path.  The right-hand side rides along as row n (forward
+// substitution for free); the backward substitution is done by warp 0 from the factor in shared memory.
+constexpr int CHOL_V3_MAX = 127;
+__host__ __device__ inline size_t chol_v3_smem_doubles(int n) { return (size_t)n * (n | 1) + 2 * 160 + 160; }
+template <int CQ>
+__device__ __forceinline__ void chol_v3_body(int n, const double* Sg, const double* rhs, const double* gh, double reg, int* chol_fail, double* out, double* shm) {
+  const int ld = n | 1;
+  double* Lm = shm;                                   // [n][ld] factor, written at the end
+  double* colbuf = Lm + (size_t)n * ld;               // [2][160] scaled columns (rows 0..n)
+  double* invd = colbuf + 2 * 160;                    // [160] 1 / L_kk
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  double a[CQ][4];
+#pragma unroll
+  for (int q = 0; q < CQ; q++)
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int i = l + 32 * r, j = w + 8 * q;
+      double v = 0.0;
+      if (j < n) {
+        if (i < n) { if (i >= j) v = __ldcg(&Sg[(size_t)i * n + j]) + (i == j ? reg : 0.0); }
+        else if (i == n) v = __ldcg(&rhs[j]) + gh[j];
+      }
+      a[q][r] = v;
+    }
+  // scale column k (held in slot q of this warp) and publish it in colbuf[buf]: executed by the owning warp only (warp-uniform)
+#define V3_SCALE_CASE(Q) case Q: if constexpr (Q < CQ) { \
+    const double pv = rk == 0 ? a[Q < CQ ? Q : 0][0] : rk == 1 ? a[Q < CQ ? Q : 0][1] : rk == 2 ? a[Q < CQ ? Q : 0][2] : a[Q < CQ ? Q : 0][3]; \
+    const double piv = __shfl_sync(0xffffffffu, pv, lk); \
+    if (l == 0 && !(piv > 0.0)) *chol_fail += 1; \
+    const double rs = rsqrt(fmax(piv, 1e-300)); \
+    if (l == 0) invd[k1] = rs; \
+    _Pragma("unroll") for (int r = 0; r < 4; r++) { const int i = l + 32 * r; if (i >= k1 && i <= n) { const double v = a[Q < CQ ? Q : 0][r] * rs; a[Q < CQ ? Q : 0][r] = v; cb[i] = v; } } } break;
+#define V3_UPDATE_CASE(Q) case Q: if constexpr (Q < CQ) { _Pragma("unroll") for (int r = 0; r < 4; r++) a[Q < CQ ? Q : 0][r] -= ci[r] * cjn; } break;
+  {
+    __syncthreads();
+    if (w == 0) {
+      const int k1 = 0, rk = 0, lk = 0; double* cb = colbuf;
+      switch (0) { V3_SCALE_CASE(0) }
+    }
+    __syncthreads();
+  }
+  for (int k = 0; k < n; k++) {
+    const double* cur = colbuf + (k & 1) * 160;
+    double ci[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { const int i = l + 32 * r; ci[r] = (i > k && i <= n) ? cur[i] : 0.0; }
+    const int k1 = k + 1;
+    const int q1 = k1 >> 3;
+    const bool owner = k1 < n && (k1 & 7) == w;
+    if (owner) {
+      // look-ahead: column k+1 first, then its pivot / scaling / publication
+      const double cjn = cur[k1];
+      switch (q1) { V3_UPDATE_CASE(0) V3_UPDATE_CASE(1) V3_UPDATE_CASE(2) V3_UPDATE_CASE(3) V3_UPDATE_CASE(4) V3_UPDATE_CASE(5) V3_UPDATE_CASE(6) V3_UPDATE_CASE(7)
+                    V3_UPDATE_CASE(8) V3_UPDATE_CASE(9) V3_UPDATE_CASE(10) V3_UPDATE_CASE(11) V3_UPDATE_CASE(12) V3_UPDATE_CASE(13) V3_UPDATE_CASE(14) V3_UPDATE_CASE(15) }
+      const int rk = k1 >> 5, lk = k1 & 31; double* cb = colbuf + (k1 & 1) * 160;
+      switch (q1) { V3_SCALE_CASE(0) V3_SCALE_CASE(1) V3_SCALE_CASE(2) V3_SCALE_CASE(3) V3_SCALE_CASE(4) V3_SCALE_CASE(5) V3_SCALE_CASE(6) V3_SCALE_CASE(7)
+                    V3_SCALE_CASE(8) V3_SCALE_CASE(9) V3_SCALE_CASE(10) V3_SCALE_CASE(11) V3_SCALE_CASE(12) V3_SCALE_CASE(13) V3_SCALE_CASE(14) V3_SCALE_CASE(15) }
+    }
+    // the other columns j > k of this warp (column k+1 is done if this warp owns it)
+#pragma unroll
+    for (int q = 0; q < CQ; q++) {
+      const int j = w + 8 * q;
+      if (j > k && j < n && !(owner && q == q1)) {
+        const double cj = cur[j];
+#pragma unroll
+        for (int r = 0; r < 4; r++) a[q][r] -= ci[r] * cj;
+      }
+    }
+    __syncthreads();
+  }
+#undef V3_SCALE_CASE
+#undef V3_UPDATE_CASE
+  // factor -> shared memory (lower triangle incl. the diagonal), y = row n
+#pragma unroll
+  for (int q = 0; q < CQ; q++)
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int i = l + 32 * r, j = w + 8 * q;
+      if (j < n && i < n && i >= j) Lm[i * ld + j] = a[q][r];
+      if (j < n && i == n) colbuf[j] = a[q][r];          // y = L^-1 b
+    }
+  __syncthreads();
+  if (tid < 32) {
+    constexpr int RS = 4;
+    const int lane = tid;
+    double bs[RS];
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; bs[s2] = i < n ? colbuf[i] : 0.0; }
+    // backward: L^T x = y
+#pragma unroll
+    for (int s1 = RS - 1; s1 >= 0; s1--) {
+      for (int kk = 31; kk >= 0; kk--) {
+        const int k = 32 * s1 + kk;
+        if (k >= n) continue;
+        const double xk = __shfl_sync(0xffffffffu, bs[s1] * invd[k], kk);
+        if (lane == kk) bs[s1] = xk;
+#pragma unroll
+        for (int s2 = 0; s2 <= s1; s2++) { const int i = lane + 32 * s2; if (i < k) bs[s2] -= Lm[k * ld + i] * xk; }
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < RS; s2++) { const int i = lane + 32 * s2; if (i < n) out[i] = bs[s2]; }
+  }
+  __syncthreads();
+}
+
 // panel rows [i0, i0+32) below the diagonal block at kb: X = A[:, kb:kb+nb] L_kk^-T; row n (the right-hand side, stored in `bvec`) included
 // as the last virtual row block.  Mirrors X into the upper triangle so that L^T is readable row-wise.
 __device__ __forceinline__ void chol_trsm_body(int n, int kb, int vb, double* S, const double* Linv_all, double* bvec, double* sh) {
@@ -585,7 +803,7 @@ __device__ __forceinline__ void chol_substitute_body(int n, const double* L, con
 
 // shared memory of k_lm in doubles
 __host__ __device__ inline size_t lm_smem_doubles(int n_s, int fb) {
-  const size_t small = n_s <= CHOL_SMALL_MAX ? (size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 2 : 0;
+  const size_t small = n_s <= CHOL_SMALL_MAX ? (size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 32 : 0;
   const size_t big = n_s > CHOL_SMALL_MAX ? (size_t)((n_s + CHOL_NB - 1) / CHOL_NB + 1) * CHOL_NB : 0;
   const size_t syrk = 2 * (size_t)syrk_fr(fb > 0 ? fb : 6) * SYRK_TILE * (fb > 0 ? fb : 6);
   const size_t chol_tiles = 2 * (size_t)CHOL_NB * (CHOL_NB + 1) + 3 * CHOL_NB;
@@ -876,7 +1094,7 @@ k_lm(LmArgs a) {
       if (n_s <= CHOL_SMALL_MAX) {
         if (blockIdx.x == 0) {
           const int R = (n_s + 15) / 16;
-#define CS(RR) case RR: chol_small_body<RR>(n_s, a.S, a.rhs, a.gh, reg, &chol_fail_s, a.gn, work); break;
+#define CS(RR) case RR: chol_rot_body<RR>(n_s, a.S, a.rhs, a.gh, reg, &chol_fail_s, a.gn, work); break;
           switch (R) { CS(1) CS(2) CS(3) CS(4) CS(5) CS(6) CS(7) CS(8) }
 #undef CS
         }

@@ -3,7 +3,6 @@
 // kernels of kernels.cuh / solver_kernels.cuh.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
-#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -25,37 +24,6 @@ using namespace mcba;
 namespace {
 
 thread_local std::string g_create_error;
-
-// ---------------------------------------------------------------- NCCL through dlopen (torch's copy if loaded)
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-struct NcclApi {
-  void* lib = nullptr;
-  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  int (*CommDestroy)(ncclComm_t) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-  int (*GroupStart)() = nullptr;
-  int (*GroupEnd)() = nullptr;
-  bool load(std::string& err) {
-    if (lib) return true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
-    if (!lib) { err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
-    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
-    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
-    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
-    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
-    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-    GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
-    GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
-    if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl is missing symbols"; return false; }
-    return true;
-  }
-};
-NcclApi g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
 
 template <typename T>
 struct DevBuf {
@@ -79,7 +47,6 @@ struct mcba_ctx {
   cudaStream_t own_stream = nullptr;   // created by mcba_create; `stream` differs after mcba_set_stream
   std::string err;
   int rank = 0, world = 1;
-  ncclComm_t comm = nullptr;
   int launches = 0;
   bool solving = false;   // inside mcba_solve (the fp32-Hessian candidate is never used by the parity hooks)
   int num_sms = 148;
@@ -564,17 +531,32 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   ctx->fused_lin = P.motion != MOTION_HAND_EYE;
   if (ctx->fused_lin) {
     // static frame -> CTA map (bit-reproducible partial sums): the smallest grid that keeps every CTA at ceil(F / resident CTAs) frames
-    const int max_grid = ctx->num_sms * 2;
-    const int per = (std::max(F, 1) + max_grid - 1) / max_grid;
-    ctx->lin_grid = std::max(1, (std::max(F, 1) + per - 1) / per);
     int split = 1;
     while (split < LIN_WARPS && C * split * 2 <= LIN_WARPS) split *= 2;      // few cameras: several warps share a view
     ctx->lin_split = split;
-    // warps per CTA: 8 when two such CTAs fit an SM's shared memory (227 KB minus 1 KB per CTA and the kernel's static 2 KB), else fewer
-    // -- two CTAs of 7 hide more latency than one of 8 -- but a power of two when warps share views
+    // warps per CTA in {8, 4, 2}: the choice that keeps most warps resident per SM (shared memory: 227 KB minus ~4 KB per CTA;
+    // registers: 128 per thread -> 16 warps) times how evenly the cameras spread over the CTA's warps (a warp owns cameras c == w mod warps;
+    // the CTA meets at the end of every frame).  16 cameras x 5 boards: 4 CTAs of 4 warps instead of 1 of 8.
     int warps = LIN_WARPS;
-    if (split == 1) while (warps > 4 && 2 * (lin_smem_for(P, warps) + 3 * 1024) > 227 * 1024) warps--;
+    if (split == 1) {
+      double best = -1.0;
+      for (int wc = LIN_WARPS; wc >= 2; wc /= 2) {
+        const size_t per_cta = lin_smem_for(P, wc) + 4 * 1024;
+        const int occ = (int)std::min<size_t>((227 * 1024) / per_cta, (size_t)(16 / wc));
+        if (occ < 1) continue;
+        const double balance = (double)C / (double)(((C + wc - 1) / wc) * wc);
+        const double score = occ * wc * balance;
+        if (score > best + 1e-9) { best = score; warps = wc; }
+      }
+    }
     ctx->lin_warps = warps;
+    {
+      const size_t per_cta = lin_smem_for(P, warps) + 4 * 1024;
+      const int occ = std::max(1, (int)std::min<size_t>((227 * 1024) / per_cta, (size_t)(16 / warps)));
+      const int max_grid = ctx->num_sms * occ;
+      const int per = (std::max(F, 1) + max_grid - 1) / max_grid;
+      ctx->lin_grid = std::max(1, (std::max(F, 1) + per - 1) / per);
+    }
     REQUIRE(lin_smem_for(P, warps) <= 220 * 1024, MCBA_ERR_UNSUPPORTED, "too many boards for the linearisation kernel's shared memory");
     CK(ctx->spart.alloc((size_t)ctx->lin_grid * C * lin_record_doubles(P.T, P.D, B)));
     CK(ctx->bpart.alloc((size_t)C * B * 42));
@@ -752,7 +734,6 @@ void mcba_destroy(mcba_ctx* ctx) {
 #endif
   for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
   if (ctx->peer_own) cudaFree(ctx->peer_own);
-  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   cudaStream_t own = ctx->own_stream;
   delete ctx;                            // device buffers are freed by their destructors
   if (own) cudaStreamDestroy(own);
@@ -767,24 +748,18 @@ int mcba_set_stream(mcba_ctx* ctx, void* stream) {
 }
 
 int mcba_comm_unique_id(mcba_ctx* ctx, char out_id[128]) {
+  // kept for the shape of the API (rank 0 makes an id, the host broadcasts it): the exchanges of a solve run inside the solver kernel over
+  // NVLink peer mappings (mcba_peer_export / mcba_peer_import), there is no library communicator to create
   if (!ctx || !out_id) return MCBA_ERR_ARG;
-  if (!g_nccl.load(ctx->err)) return MCBA_ERR_NCCL;
-  ncclUniqueId id;
-  if (g_nccl.GetUniqueId(&id) != 0) { ctx->err = "ncclGetUniqueId failed"; return MCBA_ERR_NCCL; }
-  memcpy(out_id, id.internal, 128);
+  memset(out_id, 0, 128);
+  snprintf(out_id, 128, "mcba-peer-group");
   return MCBA_OK;
 }
 
 int mcba_comm_init(mcba_ctx* ctx, const char id_[128], int rank, int world) {
   if (!ctx || !id_) return MCBA_ERR_ARG;
-  REQUIRE(world >= 1 && rank >= 0 && rank < world, MCBA_ERR_ARG, "bad rank/world");
+  REQUIRE(world >= 1 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world, MCBA_ERR_ARG, "bad rank/world (1..16 ranks)");
   ctx->rank = rank; ctx->world = world; ctx->peer_ready = false;
-  if (world == 1) return MCBA_OK;
-  if (!g_nccl.load(ctx->err)) return MCBA_ERR_NCCL;
-  CK(cudaSetDevice(ctx->device));
-  ncclUniqueId id; memcpy(id.internal, id_, 128);
-  int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
-  if (r != 0) { ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); return MCBA_ERR_NCCL; }
   return MCBA_OK;
 }
 

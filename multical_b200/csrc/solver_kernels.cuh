@@ -128,7 +128,7 @@ __device__ inline void reg_compute(SolverState* st, const double* red) {
 // shapes shared by the phases of lm_kernel.cuh
 constexpr int SYRK_TILE = 32;
 __host__ __device__ constexpr int syrk_fr(int fb) { return 48 / fb; }       // frames staged per step: 2 x 12 KB of shared memory
-constexpr int CHOL_SMALL_MAX = 128;      // reduced systems up to this size are factored by one CTA with the matrix in registers
+constexpr int CHOL_SMALL_MAX = 127;      // reduced systems up to this size are factored by one CTA with the matrix in registers (row n = right-hand side)
 constexpr int CHOL_NB = 32;              // panel width of the cooperative blocked factorisation above it
 
 // trf.py: S = qr([g_h, gn_h]); B_S = (J_h S)^T (J_h S); g_S = S^T g_h   -- expressed through Gram-Schmidt

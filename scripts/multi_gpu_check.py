@@ -15,9 +15,8 @@ for name, kw in [("cfg1", {}), ("cfg1", dict(model="fisheye", C=3, F=11)), ("cfg
                  ("cfg1", dict(boards=("cube", 10, 10, 0.04, 3), rig="dome", C=5, F=33))]:
   scene = synthetic.make_workload(name, **kw)
   calib = from_scene(scene).enable(cameras=True)
-  # single-GPU reference solve: detach the engine from the communicator (world=1), every rank solves redundantly
-  eng = get_engine()
-  eng.comm_init(bytes(128), 0, 1)
+  # single-GPU reference solve on the process-wide engine (no communicator: every rank solves the whole scene redundantly);
+  # the sharded solve runs on the dedicated engine of multical_b200.distributed
   single = calib.bundle_adjust()
   ref = [dict(cost=single.last_solve.cost, nfev=single.last_solve.nfev, x=single.param_vec)]
   t = time.time()
@@ -41,7 +40,6 @@ from multical_b200.calibration import select_threshold
 scene = synthetic.make_workload("cfg1", outlier_fraction=0.02)
 calib = from_scene(scene).enable(cameras=True)
 kw = dict(num_adjustments=2, select_outliers=select_threshold(quantile=0.75, factor=4), select_scale=select_threshold(quantile=0.5, factor=3), loss="soft_l1")
-get_engine().comm_init(bytes(128), 0, 1)
 single = calib.adjust_outliers(**kw)
 out = mdist.adjust_outliers(calib, **kw)
 same = np.array_equal(out.inlier_mask, single.inlier_mask)

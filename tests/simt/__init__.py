@@ -86,7 +86,10 @@ def rewrite_asm(m):
   if "ld.volatile.global.u64" in body: return "v = *(volatile const unsigned long long*)p; simt::spin_yield();"
   if "st.volatile.global.u64" in body: return "*(volatile unsigned long long*)p = v;"
   if "globaltimer" in body: return "t_ = 0;"                       # profiling timestamps: no clock on the interpreter
-  if "red.global.add.f64" in body: return "*p += v;"                # fire-and-forget fp64 add to an address only this thread updates
+  if "red.global.add.f64" in body: return "*p += v;"
+  # bulk asynchronous copies + mbarrier (csrc/linearize.cuh): the interpreter copies synchronously, the barrier has nothing left to wait for
+  if "cp.async.bulk.shared" in body: return "memcpy(dst, src, bytes);"
+  if "mbarrier." in body or "fence.mbarrier_init" in body: return ";"                # fire-and-forget fp64 add to an address only this thread updates
   raise ValueError("inline PTX without a host meaning: " + body[:80])
 
 

@@ -387,6 +387,8 @@ template <class T> static inline T __ldcv(const T* p) { return *(const volatile 
 // blocks run one after the other and fibers only switch at barriers / collectives, so plain read-modify-write is atomic
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline long long clock64() { return 0; }
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+#define __align__(n) __attribute__((aligned(n)))
 static inline unsigned atomicAdd(unsigned* p, int v) { unsigned o = *p; *p = o + (unsigned)v; return o; }
 template <class T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
@@ -394,6 +396,7 @@ template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *
 template <class T> static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
