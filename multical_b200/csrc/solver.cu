@@ -444,9 +444,15 @@ int run_lm_loop(mcba_ctx* ctx, int loss, double f_scale, int log_cap) {
       cudaGraphNode_t node; CK(cudaGraphAddNode(&node, g, nullptr, 0, &np));
       cudaGraph_t body = np.conditional.phGraph_out[0];
       a.cond_handle = (unsigned long long)handle; a.use_cond = 1;
-      CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      // captured on the context's own stream (the caller's may be the legacy default stream, which cannot capture); the graph is
+      // launched on the caller's stream
+      cudaStream_t cap = ctx->own_stream;
+      CK(cudaStreamSynchronize(s));
+      CK(cudaStreamBeginCaptureToGraph(cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      ctx->stream = cap;
       int r = lm_body(ctx, loss, f_scale, a);
-      cudaError_t e = cudaStreamEndCapture(s, nullptr);
+      ctx->stream = s;
+      cudaError_t e = cudaStreamEndCapture(cap, nullptr);
       if (r) return r;
       if (e != cudaSuccess) { ctx->err = std::string("graph capture of the loop body: ") + cudaGetErrorString(e); return MCBA_ERR_CUDA; }
       CK(cudaGraphInstantiate(&ctx->sg.exec, g, 0));

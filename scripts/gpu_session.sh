@@ -1,11 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I multical_b200/csrc -diag-suppress 550 -o /tmp/chol_bench scripts/chol_bench.cu && /tmp/chol_bench | tee gpurun_out/chol_bench.txt
-timeout 120 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -2
-timeout 1500 python -m pytest tests -q -m gpu --tb=short -x > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
-for wl in cfg2 cfg3 cfg4; do
-  timeout 300 python scripts/profile_one.py $wl time 2>&1 | tail -1
-  timeout 300 python scripts/profile_one.py $wl solve 2>&1 | tail -1
-  MCBA_PROF=1 timeout 300 python scripts/profile_one.py $wl solve 2>&1 | grep "k_lm phases" | tail -3 | head -1
-done
-MCBA_GRAPH=0 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_linearize -s 1 -c 1 -o gpurun_out/ncu_linearize_cfg4 python scripts/profile_one.py cfg4 solve > gpurun_out/ncu_full_cfg4.log 2>&1; tail -1 gpurun_out/ncu_full_cfg4.log
+t0=$(date +%s)
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$? $(( $(date +%s) - t0 ))s"; tail -3 gpurun_out/bench_n1.err
+python scripts/show_bench.py gpurun_out/bench_n1.json
+t0=$(date +%s)
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$? $(( $(date +%s) - t0 ))s"; tail -1 gpurun_out/bench_ref.json | cut -c1-400
