@@ -246,28 +246,35 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
   __syncwarp();
 }
 
-// one 32x32 tile (ti <= tj) of sum_f Y_f Y_f^T over a frame chunk -> Spart[chunk], diagonal tiles also sum_f Y_f z_f -> rpart[chunk]
+// one 32x32 tile (ti <= tj) of sum_f Y_f Y_f^T over a frame chunk -> Spart[chunk], diagonal tiles also sum_f Y_f z_f -> rpart[chunk].
+// On the fp64 tensor path: 48 k-columns (8 frames x 6, or 4 x 12) are staged per step as two [32][SYRK_KP] operand tiles; warp w owns
+// the 8x8 output tiles (row tile w/2, column tiles 2 (w&1), 2 (w&1) + 1): 3 shared-memory fragment loads feed 2 DMMAs = 512 FMAs
+// (the 2x2-per-thread DFMA version needed one load per FMA and was bound by shared-memory bandwidth: 126 us at n_s = 286, 1000 frames).
+// The next step's operands are fetched into registers while this step is multiplied.
+constexpr int SYRK_K = 48;
+constexpr int SYRK_KP = 52;           // row stride in doubles: 52 mod 32 = 4 x odd -> the 8 x 4 fragment lanes hit 32 distinct banks
 template <int FB>
-__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* 2 * SYRK_FR*32*FB doubles */) {
+__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* 2 * 32 * SYRK_KP doubles */) {
   constexpr int SYRK_FR = syrk_fr(FB);
+  static_assert(SYRK_FR * FB == SYRK_K, "a step stages 48 k-columns");
   const int n_s = a.n_s, F = a.F;
-  double (*Yi)[SYRK_TILE][FB] = reinterpret_cast<double (*)[SYRK_TILE][FB]>(sh);
-  double (*Yj)[SYRK_TILE][FB] = reinterpret_cast<double (*)[SYRK_TILE][FB]>(sh + SYRK_FR * SYRK_TILE * FB);
+  double* Yi = sh;
+  double* Yj = sh + SYRK_TILE * SYRK_KP;
   const int f0 = chunk * a.syrk_cf, f1 = min(F, f0 + a.syrk_cf);
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[2][2] = {{0, 0}, {0, 0}};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, tig = lane & 3;
+  const int I = warp >> 1, J0 = 2 * (warp & 1);
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
   double racc = 0.0;
-  // software pipeline: the tiles of step s+1 are loaded into registers while step s is multiplied out of shared memory
-  constexpr int PER = (SYRK_FR * SYRK_TILE * FB + LM_THREADS - 1) / LM_THREADS;
+  constexpr int PER = (SYRK_TILE * SYRK_K + LM_THREADS - 1) / LM_THREADS;      // 6
   double pi[PER], pj[PER];
   auto fetch = [&](int fbase) {
     const int nf = min(SYRK_FR, f1 - fbase);
 #pragma unroll
     for (int q = 0; q < PER; q++) {
-      const int o = threadIdx.x + q * LM_THREADS;
+      const int o = tid + q * LM_THREADS;                   // (frame ff, row r, k): k fastest -> consecutive addresses within a row
       const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
       const int gi = ti * SYRK_TILE + r, gj = tj * SYRK_TILE + r;
-      const bool in = o < SYRK_FR * SYRK_TILE * FB && ff < nf;
+      const bool in = ff < nf;
       pi[q] = (in && gi < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gi) * FB + k] : 0.0;
       pj[q] = (in && gj < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gj) * FB + k] : 0.0;
     }
@@ -278,39 +285,45 @@ __device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int c
     const int nf = min(SYRK_FR, f1 - fbase);
 #pragma unroll
     for (int q = 0; q < PER; q++) {
-      const int o = threadIdx.x + q * LM_THREADS;
-      if (o < SYRK_FR * SYRK_TILE * FB) { (&Yi[0][0][0])[o] = pi[q]; (&Yj[0][0][0])[o] = pj[q]; }
+      const int o = tid + q * LM_THREADS;
+      const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
+      Yi[r * SYRK_KP + ff * FB + k] = pi[q];
+      Yj[r * SYRK_KP + ff * FB + k] = pj[q];
     }
     __syncthreads();
     if (fbase + SYRK_FR < f1) fetch(fbase + SYRK_FR);
-    for (int ff = 0; ff < nf; ff++) {
 #pragma unroll
-      for (int k = 0; k < FB; k++) {
-        const double a0 = Yi[ff][ty][k], a1 = Yi[ff][ty + 16][k], b0 = Yj[ff][tx][k], b1 = Yj[ff][tx + 16][k];
-        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-      }
+    for (int ks = 0; ks < SYRK_K / 4; ks++) {
+      const double fa = Yi[(8 * I + grp) * SYRK_KP + 4 * ks + tig];
+      const double fb0 = Yj[(8 * J0 + grp) * SYRK_KP + 4 * ks + tig];
+      const double fb1 = Yj[(8 * (J0 + 1) + grp) * SYRK_KP + 4 * ks + tig];
+      dmma884(c00, c01, fa, fb0);
+      dmma884(c10, c11, fa, fb1);
     }
-    if (ti == tj && threadIdx.x < SYRK_TILE) {
+    if (ti == tj && tid < SYRK_TILE) {
       for (int ff = 0; ff < nf; ff++) {
         const double* z = a.zf + (size_t)(fbase + ff) * FB;
 #pragma unroll
-        for (int k = 0; k < FB; k++) racc += Yi[ff][threadIdx.x][k] * z[k];
+        for (int k = 0; k < FB; k++) racc += Yi[tid * SYRK_KP + ff * FB + k] * z[k];
       }
     }
     __syncthreads();
   }
   double* Sp = a.Spart + (size_t)chunk * n_s * n_s;
-  if (ti == tj && threadIdx.x < SYRK_TILE) {
-    const int i = ti * SYRK_TILE + threadIdx.x;
+  if (ti == tj && tid < SYRK_TILE) {
+    const int i = ti * SYRK_TILE + tid;
     if (i < n_s) a.rpart[(size_t)chunk * n_s + i] = racc;
   }
-#pragma unroll
-  for (int p = 0; p < 2; p++)
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int i = ti * SYRK_TILE + ty + 16 * p, j = tj * SYRK_TILE + tx + 16 * q;
-      if (i < n_s && j < n_s) Sp[(size_t)i * n_s + j] = acc[p][q];
+  {
+    const int i = ti * SYRK_TILE + 8 * I + grp;
+    const int j0 = tj * SYRK_TILE + 8 * J0 + 2 * tig, j1 = j0 + 8;
+    if (i < n_s) {
+      if (j0 < n_s) Sp[(size_t)i * n_s + j0] = c00;
+      if (j0 + 1 < n_s) Sp[(size_t)i * n_s + j0 + 1] = c01;
+      if (j1 < n_s) Sp[(size_t)i * n_s + j1] = c10;
+      if (j1 + 1 < n_s) Sp[(size_t)i * n_s + j1 + 1] = c11;
     }
+  }
 }
 
 // reduced solve, n_s <= CHOL_SMALL_MAX: one CTA, matrix cyclically distributed in registers (the round-1 k_chol_small scheme)
@@ -416,6 +429,7 @@ __device__ __forceinline__ void chol_diag_body(int n, int kb, double* S, double*
   const int nb = min(CHOL_NB, n - kb);
   const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
   double a[2][2];
+  __syncthreads();                       // the block may just have been updated by this CTA (look-ahead tile of the previous panel)
 #pragma unroll
   for (int p = 0; p < 2; p++)
 #pragma unroll
@@ -690,65 +704,63 @@ __device__ __forceinline__ void chol_v3_body(int n, const double* Sg, const doub
   __syncthreads();
 }
 
-// panel rows [i0, i0+32) below the diagonal block at kb: X = A[:, kb:kb+nb] L_kk^-T; row n (the right-hand side, stored in `bvec`) included
-// as the last virtual row block.  Mirrors X into the upper triangle so that L^T is readable row-wise.
-__device__ __forceinline__ void chol_trsm_body(int n, int kb, int vb, double* S, const double* Linv_all, double* bvec, double* sh) {
+// One 32x32 tile (ti >= tj) of the trailing update of panel p, with the panel solve folded in: X_i = A[rows_i, panel] L_pp^-T (a product
+// with the inverted diagonal block), X_j likewise, A[rows_i, cols_j] -= X_i X_j^T.  The tiles of block column 0 also store X_i as the
+// finished factor -- TRANSPOSED, into the strict upper triangle (row kbp + k, column i): the lower triangle stays the working matrix that
+// every other tile of this update still reads, the upper triangle collects L^T for the substitutions.  sh: 5 x 32 x 33 doubles.
+__device__ __forceinline__ void chol_fused_tile(int n, int p, int ti, int tj, double* S, const double* Linv_all, double* sh) {
   double (*Li)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
-  double (*At)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + CHOL_NB * (CHOL_NB + 1));
-  const int nb = min(CHOL_NB, n - kb);
-  const double* Lg = Linv_all + (size_t)(kb / CHOL_NB) * CHOL_NB * CHOL_NB;
-  const int i0 = kb + nb + vb * CHOL_NB;
+  double (*Ai)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 1 * CHOL_NB * (CHOL_NB + 1));
+  double (*Aj)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 2 * CHOL_NB * (CHOL_NB + 1));
+  double (*Xi)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 3 * CHOL_NB * (CHOL_NB + 1));
+  double (*Xj)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 4 * CHOL_NB * (CHOL_NB + 1));
+  const int kbp = CHOL_NB * p, base = kbp + CHOL_NB;
+  const int i0 = base + CHOL_NB * ti, j0 = base + CHOL_NB * tj;
+  const double* Lg = Linv_all + (size_t)p * CHOL_NB * CHOL_NB;
+  const int tid = threadIdx.x;
   __syncthreads();
-  for (int o = threadIdx.x; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
+  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
     const int r = o / CHOL_NB, c = o % CHOL_NB;
     Li[r][c] = __ldcg(&Lg[o]);
-    At[r][c] = (i0 + r < n && c < nb) ? __ldcg(&S[(size_t)(i0 + r) * n + kb + c]) : 0.0;
+    Ai[r][c] = (i0 + r < n) ? __ldcg(&S[(size_t)(i0 + r) * n + kbp + c]) : 0.0;
+    Aj[r][c] = (j0 + r < n) ? __ldcg(&S[(size_t)(j0 + r) * n + kbp + c]) : 0.0;
   }
   __syncthreads();
-  const int r = threadIdx.x >> 3, cg = threadIdx.x & 7;
-  double x[4] = {0, 0, 0, 0};
+  {
+    const int r = tid >> 3, cg = tid & 7;
+    double xi[4] = {0, 0, 0, 0}, xj[4] = {0, 0, 0, 0};
 #pragma unroll 8
-  for (int k = 0; k < CHOL_NB; k++) {
-    const double av = At[r][k];
+    for (int k = 0; k < CHOL_NB; k++) {
+      const double av = Ai[r][k], bv = Aj[r][k];
 #pragma unroll
-    for (int q = 0; q < 4; q++) x[q] += av * Li[cg * 4 + q][k];
-  }
-  if (i0 + r < n) {
+      for (int q = 0; q < 4; q++) { const double l = Li[cg * 4 + q][k]; xi[q] += av * l; xj[q] += bv * l; }      // X[i][j] = sum_k A[i][k] Linv[j][k]
+    }
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const int j = cg * 4 + q;
-      if (j < nb) { S[(size_t)(i0 + r) * n + kb + j] = x[q]; S[(size_t)(kb + j) * n + i0 + r] = x[q]; }
+    for (int q = 0; q < 4; q++) { Xi[r][cg * 4 + q] = xi[q]; Xj[r][cg * 4 + q] = xj[q]; }
+    if (tj == 0 && i0 + r < n) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) S[(size_t)(kbp + cg * 4 + q) * n + i0 + r] = xi[q];            // L^T into the upper triangle
     }
   }
-  (void)bvec;
-}
-__device__ __forceinline__ void chol_syrk_body(int n, int kb, int ti, int tj, double* S, double* sh) {
-  double (*Li)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
-  double (*Lj)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + CHOL_NB * (CHOL_NB + 1));
-  const int nb = min(CHOL_NB, n - kb);
-  const int base = kb + nb;
-  const int i0 = base + ti * 32, j0 = base + tj * 32;
   __syncthreads();
-  for (int o = threadIdx.x; o < 32 * nb; o += LM_THREADS) {
-    const int r = o / nb, k = o % nb;
-    Li[r][k] = (i0 + r < n) ? __ldcg(&S[(size_t)(i0 + r) * n + kb + k]) : 0.0;
-    Lj[r][k] = (j0 + r < n) ? __ldcg(&S[(size_t)(j0 + r) * n + kb + k]) : 0.0;
-  }
-  __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[2][2] = {{0, 0}, {0, 0}};
-  for (int k = 0; k < nb; k++) {
-    const double a0 = Li[ty][k], a1 = Li[ty + 16][k], b0 = Lj[tx][k], b1 = Lj[tx + 16][k];
-    acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
-  }
-#pragma unroll
-  for (int p = 0; p < 2; p++)
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int i = i0 + ty + 16 * p, j = j0 + tx + 16 * q;
-      if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[p][q];
+  {
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll 8
+    for (int k = 0; k < CHOL_NB; k++) {
+      const double a0 = Xi[ty][k], a1 = Xi[ty + 16][k], b0 = Xj[tx][k], b1 = Xj[tx + 16][k];
+      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
     }
+#pragma unroll
+    for (int pp = 0; pp < 2; pp++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int i = i0 + ty + 16 * pp, j = j0 + tx + 16 * q;
+        if (i < n && j < n && j <= i) S[(size_t)i * n + j] = __ldcg(&S[(size_t)i * n + j]) - acc[pp][q];      // last written by another CTA (previous panel): read it from L2
+      }
+  }
 }
+
 // both substitutions by one CTA with the factor in global memory (lower = L, strict upper = L^T mirror) and the inverted diagonal blocks
 __device__ __forceinline__ void chol_substitute_body(int n, const double* L, const double* Linv_all, const double* rhs, const double* gh, double* out, double* bsh) {
   double* yb = bsh + ((n + CHOL_NB - 1) / CHOL_NB) * CHOL_NB;
@@ -768,11 +780,11 @@ __device__ __forceinline__ void chol_substitute_body(int n, const double* L, con
     }
     __syncthreads();
     if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
+    const int nbf = min(CHOL_NB, n - kb);
     for (int i = kb + CHOL_NB + tid; i < n; i += LM_THREADS) {
-      const double* row = L + (size_t)i * n + kb;
       double acc = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < CHOL_NB; k++) acc += __ldcg(&row[k]) * yb[k];
+      for (int k = 0; k < nbf; k++) acc += __ldcg(&L[(size_t)(kb + k) * n + i]) * yb[k];       // L[i][kb+k] from the transposed factor (coalesced over i)
       bsh[i] -= acc;
     }
     __syncthreads();
@@ -805,8 +817,8 @@ __device__ __forceinline__ void chol_substitute_body(int n, const double* L, con
 __host__ __device__ inline size_t lm_smem_doubles(int n_s, int fb) {
   const size_t small = n_s <= CHOL_SMALL_MAX ? (size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 32 : 0;
   const size_t big = n_s > CHOL_SMALL_MAX ? (size_t)((n_s + CHOL_NB - 1) / CHOL_NB + 1) * CHOL_NB : 0;
-  const size_t syrk = 2 * (size_t)syrk_fr(fb > 0 ? fb : 6) * SYRK_TILE * (fb > 0 ? fb : 6);
-  const size_t chol_tiles = 2 * (size_t)CHOL_NB * (CHOL_NB + 1) + 3 * CHOL_NB;
+  const size_t syrk = 2 * (size_t)SYRK_TILE * SYRK_KP;
+  const size_t chol_tiles = 5 * (size_t)CHOL_NB * (CHOL_NB + 1) + 3 * CHOL_NB;
   const size_t frames = (size_t)LM_WARPS * (12 * 12 + 12);
   size_t m = small;
   if (big > m) m = big;
@@ -1101,21 +1113,26 @@ k_lm(LmArgs a) {
       } else {
         for (int i = gthread; i < n_s; i += gstride) a.S[(size_t)i * n_s + i] += reg;
         grid_barrier(a.bar, nblk);
-        for (int kb = 0; kb < n_s; kb += CHOL_NB) {
-          if (blockIdx.x == 0) chol_diag_body(n_s, kb, a.S, a.Linv, &chol_fail_s, work);
-          grid_barrier(a.bar, nblk);
-          const int rem = n_s - kb - CHOL_NB;
-          if (rem > 0) {
-            const int t = (rem + 31) / 32;
-            for (int vb = blockIdx.x; vb < t; vb += nblk) chol_trsm_body(n_s, kb, vb, a.S, a.Linv, nullptr, work);
-            grid_barrier(a.bar, nblk);
-            const int ntile = t * (t + 1) / 2;
-            for (int vb = blockIdx.x; vb < ntile; vb += nblk) {
-              int ti = 0, pr = vb; while (pr > ti) { pr -= ti + 1; ti++; }        // lower triangle: ti >= tj = pr
-              chol_syrk_body(n_s, kb, ti, pr, a.S, work);
-            }
-            grid_barrier(a.bar, nblk);
+        // one barrier per panel: CTA 0 finishes the next diagonal block's tile of the previous trailing update first and factors it
+        // (look-ahead) while the other CTAs work off the rest of that update
+        const int npan = (n_s + CHOL_NB - 1) / CHOL_NB;
+        for (int b = 0; b < npan; b++) {
+          const int kb = CHOL_NB * b;
+          const int rem = b > 0 ? n_s - kb : 0;                       // rows of the trailing matrix of panel b-1
+          const int t = (rem + CHOL_NB - 1) / CHOL_NB, ntile = t * (t + 1) / 2;
+          if (blockIdx.x == 0) {
+            if (b > 0) chol_fused_tile(n_s, b - 1, 0, 0, a.S, a.Linv, work);
+            chol_diag_body(n_s, kb, a.S, a.Linv, &chol_fail_s, work);
           }
+          if (b > 0) {
+            const int first = nblk > 1 ? (int)blockIdx.x - 1 : 0, step = nblk > 1 ? nblk - 1 : 1;
+            if (nblk == 1 || blockIdx.x > 0)
+              for (int vb = 1 + first; vb < ntile; vb += step) {
+                int ti = 0, pr = vb; while (pr > ti) { pr -= ti + 1; ti++; }        // lower triangle: ti >= tj = pr
+                chol_fused_tile(n_s, b - 1, ti, pr, a.S, a.Linv, work);
+              }
+          }
+          grid_barrier(a.bar, nblk);
         }
         if (blockIdx.x == 0) {
           chol_substitute_body(n_s, a.S, a.Linv, a.rhs, a.gh, a.gn, work);

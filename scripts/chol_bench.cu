@@ -51,6 +51,64 @@ __global__ void __launch_bounds__(LM_THREADS, 1) k_v3(int n, const double* S, co
   const long long t1 = clock64();
   if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = fail; }
 }
+
+// candidate: the 32x32 diagonal block by ONE warp (block in registers, lane i = row i), then its inverse
+__device__ __forceinline__ void warp_potrf32_inverse(double (*Lm)[CHOL_NB + 1], double (*Liv)[CHOL_NB + 1], int lane, int nb, int* fail) {
+  double a[CHOL_NB], rsd[CHOL_NB];
+#pragma unroll
+  for (int j = 0; j < CHOL_NB; j++) a[j] = j <= lane ? Lm[lane][j] : 0.0;
+#pragma unroll
+  for (int k = 0; k < CHOL_NB; k++) {
+    const double akk = __shfl_sync(0xffffffffu, a[k], k);
+    if (lane == 0 && k < nb && !(akk > 0.0)) *fail += 1;
+    const double rs = fast_rsqrt(fmin(fmax(akk, 1e-30), 1e30));
+    rsd[k] = rs;
+    const double l = lane >= k ? a[k] * rs : 0.0;
+    a[k] = l;
+#pragma unroll
+    for (int j = k + 1; j < CHOL_NB; j++) { const double ljk = __shfl_sync(0xffffffffu, l, j); a[j] -= l * ljk; }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < CHOL_NB; j++) Lm[lane][j] = j <= lane ? a[j] : 0.0;
+  __syncwarp();
+  double z[CHOL_NB];
+#pragma unroll
+  for (int i = 0; i < CHOL_NB; i++) {
+    double t0 = (i == lane) ? 1.0 : 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+    for (int m = 0; m < CHOL_NB; m += 4) {
+      if (m < i) t0 -= Lm[i][m] * z[m];
+      if (m + 1 < i) t1 -= Lm[i][m + 1] * z[m + 1];
+      if (m + 2 < i) t2 -= Lm[i][m + 2] * z[m + 2];
+      if (m + 3 < i) t3 -= Lm[i][m + 3] * z[m + 3];
+    }
+    z[i] = (i >= lane) ? ((t0 + t1) + (t2 + t3)) * rsd[i] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < CHOL_NB; i++) Liv[i][lane] = z[i];
+  __syncwarp();
+}
+__global__ void __launch_bounds__(LM_THREADS, 1) k_diag_warp(int n, double* S, double* Linv, long long* cyc) {
+  extern __shared__ double sm[];
+  __shared__ int fail;
+  double (*Lm)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sm);
+  double (*Liv)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sm + CHOL_NB * (CHOL_NB + 1));
+  const int tid = threadIdx.x;
+  if (tid == 0) fail = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) { const int i = o / CHOL_NB, j = o % CHOL_NB; Lm[i][j] = j <= i ? __ldcg(&S[(size_t)i * n + j]) : 0.0; }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid < 32) warp_potrf32_inverse(Lm, Liv, tid, 32, &fail);
+  __syncthreads();
+  const long long t2 = clock64();
+  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) { const int i = o / CHOL_NB, j = o % CHOL_NB; if (j <= i) S[(size_t)i * n + j] = Lm[i][j]; Linv[o] = Liv[i][j]; }
+  __syncthreads();
+  const long long t3 = clock64();
+  if (tid == 0) { cyc[0] = t3 - t0; cyc[1] = fail; cyc[2] = t2 - t1; }
+}
 #ifdef HAVE_CTA
 __global__ void __launch_bounds__(LM_THREADS, 1) k_cta(int n, const double* S, const double* rhs, const double* gh, double* out, long long* cyc) {
   extern __shared__ double sm[];
@@ -109,6 +167,10 @@ int main() {
       for (int rep = 0; rep < 2; rep++) { cudaMemcpy(dS, A.data(), A.size() * 8, cudaMemcpyHostToDevice); k_diag<<<1, LM_THREADS, smsz>>>(n, dS, dLi, dc); cudaDeviceSynchronize(); }
       long long c[2]; cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost);
       printf("n= 32 chol_diag_body %8lld cycles (%.2f us)\n", c[0], c[0] / 1965.0);
+      cudaFuncSetAttribute(k_diag_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smsz);
+      for (int rep = 0; rep < 2; rep++) { cudaMemcpy(dS, A.data(), A.size() * 8, cudaMemcpyHostToDevice); k_diag_warp<<<1, LM_THREADS, smsz>>>(n, dS, dLi, dc); cudaDeviceSynchronize(); }
+      long long c3[3]; cudaMemcpy(c3, dc, 24, cudaMemcpyDeviceToHost);
+      printf("n= 32 diag_warp      %8lld cycles (%.2f us), factor+inverse alone %lld cycles (%.2f us) fail=%lld [%s]\n", c3[0], c3[0] / 1965.0, c3[2], c3[2] / 1965.0, c3[1], cudaGetErrorString(cudaGetLastError()));
     }
   }
   return 0;
