@@ -21,6 +21,7 @@ constexpr int LIN_WARPS = 8;           // at most; the host takes fewer when two
 constexpr int LIN_THREADS = LIN_WARPS * 32;
 constexpr int LIN_KPAD = 36;           // 32 staged residual rows + 4: (column stride mod 16 doubles) == 4 -> conflict-free fragment loads
 constexpr int LIN_MAXV = 96;           // views of a frame staged in shared memory (more: the list is read from global memory)
+constexpr int LIN_MAXC = 1024;         // cameras tracked by the per-frame presence mask (more: W_f is zero-filled first)
 constexpr int LIN_MAXB = 8;            // board pose tables staged per frame (more boards: the tables are read from global memory)
 
 // compile-time shape of a residual row's local Jacobian [twist block(s) | fx fy cx cy dist | r]
@@ -170,26 +171,6 @@ __device__ __forceinline__ void red_add(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-// ---- bulk asynchronous copies (the 1-D form of the Tensor Memory Accelerator, cp.async.bulk) with an mbarrier as completion signal:
-// the small parameter blocks a CTA needs -- the frame's pose table(s), the board tables -- travel HBM/L2 -> shared memory without
-// passing through registers, and the NEXT frame's table is in flight while the current frame is worked on.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-  asm volatile("{ .reg .pred p_; MBW_: mbarrier.try_wait.parity.shared::cta.b64 p_, [%0], %1; @p_ bra.uni MBD_; bra.uni MBW_; MBD_: }"
-               ::"r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
 // per-warp shared-memory layout of k_linearize (doubles from the warp's base).  The epilogue's per-view scratch aliases the stage
 // buffer of the chunk loop; what must survive from view to view lies behind it.
 template <int MODEL, bool ROLL>
@@ -251,7 +232,7 @@ __device__ __forceinline__ void lin_flush_macc(const DeviceProblem& p, double* w
 // camera rows of W_f: pose rows = sum_a Ac^T wacc[xi_a rows] (the camera's own map does not depend on the view: applied once per
 // camera and frame), intrinsics rows = wacc[kappa rows]
 template <int MODEL, bool ROLL>
-__device__ __forceinline__ void lin_flush_wacc(const DeviceProblem& p, const LinArgs& a, double* w, int f, int lane) {
+__device__ __forceinline__ void lin_flush_wacc(const DeviceProblem& p, const LinArgs& a, double* w, int f, int lane, unsigned* seen) {
   using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
   constexpr int FB = S::FB, KO = S::KO, NIN = S::NIN;
   const int B = p.B;
@@ -276,12 +257,14 @@ __device__ __forceinline__ void lin_flush_wacc(const DeviceProblem& p, const Lin
   if (p.off_in >= 0) {
     for (int o = lane; o < NIN * FB; o += 32) {
       const int i = o / FB, col = o % FB;
-      if (p.fix_aspect && i == 1) continue;                            // fy follows fx (camera.py:159-160): its row is folded onto fx
       const double val = wacc[(KO + i) * FB + col];
+      if (p.fix_aspect && i == 1) { Wf[(size_t)(p.off_in + p.kint * cam + 1) * FB + col] = 0.0; continue; }      // fy follows fx (camera.py:159-160): folded onto fx, its own row is dead
       const double v2 = (p.fix_aspect && i == 0) ? val + wacc[(KO + 1) * FB + col] : val;
       Wf[(size_t)(p.off_in + p.kint * cam + intr_param_index(p, i)) * FB + col] = v2;
     }
+    for (int col = lane; col < FB; col += 32) Wf[(size_t)(p.off_in + p.kint * cam + 4) * FB + col] = 0.0;             // skew: ignored by cv2.projectPoints, dead column
   }
+  if (lane == 0) atomicOr(&seen[cam >> 5], 1u << (cam & 31));
   __syncwarp();
   for (int o = lane; o < L::NWC; o += 32) wacc[o] = 0.0;
 }
@@ -293,7 +276,7 @@ __device__ __forceinline__ void lin_flush_wacc(const DeviceProblem& p, const Lin
 // both products on the fp64 tensor path (mma.m8n8k4, 8 + 8 instructions for the 5-coefficient model); the C fragments are added
 // straight into the warp's running sums.  A call, not inlined: the chunk loop of the kernel keeps its registers.
 template <int MODEL, bool ROLL>
-__device__ __noinline__ void lin_view_epilogue(const DeviceProblem& p, const LinArgs& a, double* w, double* myrec, const PoseT* ftab, const PoseT* btab, int c, int f, int b, double cost_acc) {
+__device__ __noinline__ void lin_view_epilogue(const DeviceProblem& p, const LinArgs& a, double* w, double* myrec, const PoseT* ftab, const PoseT* btab, unsigned* seen, int c, int f, int b, double cost_acc) {
   using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
   constexpr int NP = S::NP, KO = S::KO, D = S::D, E_ = S::E, T = S::T, NC = S::NC, NT = S::NT, FB = S::FB;
   constexpr int PC = L::PC, PT = L::PT, KS = L::KS;
@@ -307,7 +290,7 @@ __device__ __noinline__ void lin_view_epilogue(const DeviceProblem& p, const Lin
   // ftab: this frame's pose table(s) [NP], btab: the board tables [B] (staged in shared memory by the CTA)
   const bool cam_changed = c != (int)tl[1];
   if (cam_changed) {
-    lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane); lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane); lin_flush_macc<MODEL, ROLL>(p, w, myrec, lane);
+    lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane); lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane, seen); lin_flush_macc<MODEL, ROLL>(p, w, myrec, lane);
     __syncwarp();
     if (lane == 0) { tl[1] = c; tl[2] = -1.0; }
     __syncwarp();
@@ -437,6 +420,7 @@ k_linearize(DeviceProblem p, LinArgs a) {
   extern __shared__ double lsm[];
   __shared__ int fv_cam[LIN_MAXV], fv_board[LIN_MAXV], fv_start[LIN_MAXV + 1];
   __shared__ int any_view;
+  __shared__ unsigned cam_seen[LIN_MAXC / 32];       // cameras with a view in the frame in progress (their W_f rows are written by the owning warp)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int grp = lane >> 2, tig = lane & 3;
@@ -485,10 +469,14 @@ k_linearize(DeviceProblem p, LinArgs a) {
         if (i < v1 - v0) { fv_cam[i] = p.view_cam[v0 + i]; fv_board[i] = p.view_board[v0 + i]; }
       }
     }
-    if (frames_on) {
+    // W_f is written once: camera rows by the warp that owns the camera, board rows at the end of the frame, zeros only where nobody writes
+    // (cameras without a view in this frame; board points as parameters: k_point_blocks adds to zeroed rows afterwards)
+    const bool fill_all = frames_on && (p.C > LIN_MAXC || p.off_pt >= 0);
+    if (fill_all) {
       double* Wf = a.W + (size_t)f * n_s * FB;
       for (int i = tid; i < n_s * FB; i += nthreads) Wf[i] = 0.0;
     }
+    for (int i = tid; i < LIN_MAXC / 32; i += nthreads) cam_seen[i] = 0u;
     mbar_wait(&tbar[it & 1], (unsigned)((it >> 1) & 1));       // this frame's pose table(s) have landed
     if (leader) {
       for (int i = L::Wb + lane; i < L::wacc(B); i += 32) w[i] = 0.0;      // Wb | hacc
@@ -572,13 +560,21 @@ k_linearize(DeviceProblem p, LinArgs a) {
             t++;
           }
         __syncwarp();
-        lin_view_epilogue<MODEL, ROLL>(p, a, w, myrec, ftab, btab, c, f, b, cost_acc);
+        lin_view_epilogue<MODEL, ROLL>(p, a, w, myrec, ftab, btab, cam_seen, c, f, b, cost_acc);
       }
       if (have) v++;
     }
     // ---- end of the frame: camera rows out, then the CTA sums the slots' partials in slot order
-    if (leader) lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane);
+    if (leader) lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane, cam_seen);
     __syncthreads();
+    if (frames_on && !fill_all) {
+      double* Wf = a.W + (size_t)f * n_s * FB;
+      for (int c = 0; c < p.C; c++) {
+        if (cam_seen[c >> 5] & (1u << (c & 31))) continue;
+        if (p.off_cp >= 0) for (int i = tid; i < 6 * FB; i += nthreads) Wf[(size_t)(p.off_cp + 6 * c) * FB + i] = 0.0;
+        if (p.off_in >= 0) for (int i = tid; i < p.kint * FB; i += nthreads) Wf[(size_t)(p.off_in + p.kint * c) * FB + i] = 0.0;
+      }
+    }
     if (frames_on) {
       for (int o = tid; o < L::NHF; o += nthreads) {
         double s = 0.0;

@@ -247,72 +247,83 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
 }
 
 // one 32x32 tile (ti <= tj) of sum_f Y_f Y_f^T over a frame chunk -> Spart[chunk], diagonal tiles also sum_f Y_f z_f -> rpart[chunk].
-// On the fp64 tensor path: 48 k-columns (8 frames x 6, or 4 x 12) are staged per step as two [32][SYRK_KP] operand tiles; warp w owns
-// the 8x8 output tiles (row tile w/2, column tiles 2 (w&1), 2 (w&1) + 1): 3 shared-memory fragment loads feed 2 DMMAs = 512 FMAs
-// (the 2x2-per-thread DFMA version needed one load per FMA and was bound by shared-memory bandwidth: 126 us at n_s = 286, 1000 frames).
-// The next step's operands are fetched into registers while this step is multiplied.
+// Operands: the 32 rows of a tile are CONTIGUOUS in Y per frame (32 x FB doubles = 1.5 KB), so a step (48 k-columns: 8 frames x 6, or
+// 4 x 12) is 2 x SYRK_FR bulk asynchronous copies (cp.async.bulk + mbarrier) straight into shared memory; SYRK_STAGES steps are in flight
+// per CTA (the register-prefetched version had one: 2.2 us per step = one HBM/L2 round trip, 94 us at n_s = 286 x 1000 frames).
+// Product on the fp64 tensor path: warp w owns the 8x8 output tiles (row tile w/2, column tiles 2 (w&1), 2 (w&1) + 1); per k-step 3
+// fragment loads feed 2 DMMAs = 512 FMAs (the first version, 2x2 outputs per thread with DFMA, needed one shared-memory load per FMA).
 constexpr int SYRK_K = 48;
-constexpr int SYRK_KP = 52;           // row stride in doubles: 52 mod 32 = 4 x odd -> the 8 x 4 fragment lanes hit 32 distinct banks
+constexpr int SYRK_STAGES = 4;
+template <int FB> __host__ __device__ constexpr int syrk_stage_doubles() { return 2 * SYRK_K * SYRK_TILE; }      // Yi | Yj, each [SYRK_FR][32][FB]
 template <int FB>
-__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* 2 * 32 * SYRK_KP doubles */) {
+__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* SYRK_STAGES * 2 * 48 * 32 doubles */, unsigned long long* sbar, unsigned& phases) {
   constexpr int SYRK_FR = syrk_fr(FB);
-  static_assert(SYRK_FR * FB == SYRK_K, "a step stages 48 k-columns");
+  static_assert(SYRK_FR * FB == SYRK_K && SYRK_FR <= LM_WARPS, "a step stages 48 k-columns; one warp per frame slot for the rhs");
+  constexpr int FR_DOUBLES = SYRK_TILE * FB;                 // one frame's rows of a tile
+  constexpr int STAGE = 2 * SYRK_K * SYRK_TILE;
   const int n_s = a.n_s, F = a.F;
-  double* Yi = sh;
-  double* Yj = sh + SYRK_TILE * SYRK_KP;
   const int f0 = chunk * a.syrk_cf, f1 = min(F, f0 + a.syrk_cf);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, tig = lane & 3;
   const int I = warp >> 1, J0 = 2 * (warp & 1);
+  const int rows_i = min(SYRK_TILE, n_s - ti * SYRK_TILE), rows_j = min(SYRK_TILE, n_s - tj * SYRK_TILE);
+  const int nsteps = (f1 - f0 + SYRK_FR - 1) / SYRK_FR;
   double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
   double racc = 0.0;
-  constexpr int PER = (SYRK_TILE * SYRK_K + LM_THREADS - 1) / LM_THREADS;      // 6
-  double pi[PER], pj[PER];
-  auto fetch = [&](int fbase) {
-    const int nf = min(SYRK_FR, f1 - fbase);
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-      const int o = tid + q * LM_THREADS;                   // (frame ff, row r, k): k fastest -> consecutive addresses within a row
-      const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
-      const int gi = ti * SYRK_TILE + r, gj = tj * SYRK_TILE + r;
-      const bool in = ff < nf;
-      pi[q] = (in && gi < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gi) * FB + k] : 0.0;
-      pj[q] = (in && gj < n_s) ? a.Y[((size_t)(fbase + ff) * n_s + gj) * FB + k] : 0.0;
+  __syncthreads();                                            // every warp has left the previous tile's stages
+  // rows beyond n_s (last row tile) and frames beyond the chunk are never copied: they must read as zero
+  if (rows_i < SYRK_TILE || rows_j < SYRK_TILE || (f1 - f0) % SYRK_FR != 0)
+    for (int o = tid; o < SYRK_STAGES * STAGE; o += LM_THREADS) sh[o] = 0.0;
+  fence_proxy_async();                                        // (also orders the previous phase's plain stores to this buffer before the copies)
+  __syncthreads();
+  auto issue = [&](int step) {                                // thread 0: the copies of one step into stage step % SYRK_STAGES
+    const int st = step % SYRK_STAGES;
+    const int fbase = f0 + step * SYRK_FR, nf = min(SYRK_FR, f1 - fbase);
+    double* Yi = sh + (size_t)st * STAGE; double* Yj = Yi + SYRK_K * SYRK_TILE;
+    mbar_expect_tx(&sbar[st], (unsigned)(nf * (rows_i + rows_j) * FB * sizeof(double)));
+    for (int ff = 0; ff < nf; ff++) {
+      bulk_g2s(Yi + ff * FR_DOUBLES, a.Y + ((size_t)(fbase + ff) * n_s + (size_t)ti * SYRK_TILE) * FB, (unsigned)(rows_i * FB * sizeof(double)), &sbar[st]);
+      bulk_g2s(Yj + ff * FR_DOUBLES, a.Y + ((size_t)(fbase + ff) * n_s + (size_t)tj * SYRK_TILE) * FB, (unsigned)(rows_j * FB * sizeof(double)), &sbar[st]);
     }
   };
-  __syncthreads();
-  if (f0 < f1) fetch(f0);
-  for (int fbase = f0; fbase < f1; fbase += SYRK_FR) {
-    const int nf = min(SYRK_FR, f1 - fbase);
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-      const int o = tid + q * LM_THREADS;
-      const int ff = o / (SYRK_TILE * FB), rem = o % (SYRK_TILE * FB), r = rem / FB, k = rem % FB;
-      Yi[r * SYRK_KP + ff * FB + k] = pi[q];
-      Yj[r * SYRK_KP + ff * FB + k] = pj[q];
-    }
-    __syncthreads();
-    if (fbase + SYRK_FR < f1) fetch(fbase + SYRK_FR);
+  if (tid == 0) for (int s0 = 0; s0 < SYRK_STAGES - 1 && s0 < nsteps; s0++) issue(s0);
+  for (int step = 0; step < nsteps; step++) {
+    const int st = step % SYRK_STAGES;
+    if (tid == 0 && step + SYRK_STAGES - 1 < nsteps) issue(step + SYRK_STAGES - 1);      // its stage was consumed in step - 1 (barrier below)
+    mbar_wait(&sbar[st], (phases >> st) & 1u);
+    phases ^= 1u << st;
+    const double* Yi = sh + (size_t)st * STAGE; const double* Yj = Yi + SYRK_K * SYRK_TILE;
+    const int fbase = f0 + step * SYRK_FR, nf = min(SYRK_FR, f1 - fbase);
 #pragma unroll
     for (int ks = 0; ks < SYRK_K / 4; ks++) {
-      const double fa = Yi[(8 * I + grp) * SYRK_KP + 4 * ks + tig];
-      const double fb0 = Yj[(8 * J0 + grp) * SYRK_KP + 4 * ks + tig];
-      const double fb1 = Yj[(8 * (J0 + 1) + grp) * SYRK_KP + 4 * ks + tig];
+      const int kidx = 4 * ks + tig, ff = kidx / FB, k = kidx % FB;          // k-column -> (frame of the step, component)
+      const double fa = Yi[ff * FR_DOUBLES + (8 * I + grp) * FB + k];
+      const double fb0 = Yj[ff * FR_DOUBLES + (8 * J0 + grp) * FB + k];
+      const double fb1 = Yj[ff * FR_DOUBLES + (8 * (J0 + 1) + grp) * FB + k];
       dmma884(c00, c01, fa, fb0);
       dmma884(c10, c11, fa, fb1);
     }
-    if (ti == tj && tid < SYRK_TILE) {
-      for (int ff = 0; ff < nf; ff++) {
+    if (ti == tj) {                                           // rhs: thread (row = tid % 32, frame slot = tid / 32 (+ 8 for 4-frame steps: none))
+      const int r = tid & 31, ff = tid >> 5;
+      if (ff < nf) {
         const double* z = a.zf + (size_t)(fbase + ff) * FB;
 #pragma unroll
-        for (int k = 0; k < FB; k++) racc += Yi[tid * SYRK_KP + ff * FB + k] * z[k];
+        for (int k = 0; k < FB; k++) racc += Yi[ff * FR_DOUBLES + r * FB + k] * z[k];
       }
     }
-    __syncthreads();
+    __syncthreads();                                          // the stage may be refilled
   }
   double* Sp = a.Spart + (size_t)chunk * n_s * n_s;
-  if (ti == tj && tid < SYRK_TILE) {
-    const int i = ti * SYRK_TILE + tid;
-    if (i < n_s) a.rpart[(size_t)chunk * n_s + i] = racc;
+  if (ti == tj) {                                             // the frame slots' partial sums, added in slot order
+    __syncthreads();
+    sh[tid] = racc;
+    __syncthreads();
+    if (tid < SYRK_TILE) {
+      double r8 = 0.0;
+#pragma unroll
+      for (int q = 0; q < LM_WARPS; q++) r8 += sh[q * 32 + tid];
+      const int i = ti * SYRK_TILE + tid;
+      if (i < n_s) a.rpart[(size_t)chunk * n_s + i] = r8;
+    }
   }
   {
     const int i = ti * SYRK_TILE + 8 * I + grp;
@@ -817,7 +828,7 @@ __device__ __forceinline__ void chol_substitute_body(int n, const double* L, con
 __host__ __device__ inline size_t lm_smem_doubles(int n_s, int fb) {
   const size_t small = n_s <= CHOL_SMALL_MAX ? (size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 32 : 0;
   const size_t big = n_s > CHOL_SMALL_MAX ? (size_t)((n_s + CHOL_NB - 1) / CHOL_NB + 1) * CHOL_NB : 0;
-  const size_t syrk = 2 * (size_t)SYRK_TILE * SYRK_KP;
+  const size_t syrk = (size_t)SYRK_STAGES * 2 * SYRK_K * SYRK_TILE;
   const size_t chol_tiles = 5 * (size_t)CHOL_NB * (CHOL_NB + 1) + 3 * CHOL_NB;
   const size_t frames = (size_t)LM_WARPS * (12 * 12 + 12);
   size_t m = small;
@@ -836,6 +847,8 @@ k_lm(LmArgs a) {
   __shared__ SolverState S;
   __shared__ double sm[32];
   __shared__ int xerr, chol_fail_s;
+  __shared__ __align__(8) unsigned long long sbar[SYRK_STAGES];      // mbarriers of the SYRK operand pipeline
+  unsigned sphases = 0;                                               // their phase parities (same in every thread)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, n_s = a.n_s;
   const int F = a.P.motion_on ? a.F : 0;              // frames with a free block
@@ -846,7 +859,7 @@ k_lm(LmArgs a) {
   const bool writer = blockIdx.x == 0 && tid == 0;
   double* work = ksm + 64;
 
-  if (tid == 0) { S = *a.st; xerr = 0; chol_fail_s = 0; }
+  if (tid == 0) { S = *a.st; xerr = 0; chol_fail_s = 0; for (int q = 0; q < SYRK_STAGES; q++) mbar_init(&sbar[q], 1); fence_barrier_init(); }
   if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[0] = 0;
 #ifdef MCBA_SIMT_BUILD
 #define LMPH(ID_) simt::set_mark(ID_);
@@ -1075,7 +1088,7 @@ k_lm(LmArgs a) {
         const int chunk = vb / npair; int pr = vb % npair;
         int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
         const int tj = ti + pr;
-        syrk_tile<FB>(a, ti, tj, chunk, work);
+        syrk_tile<FB>(a, ti, tj, chunk, work, sbar, sphases);
       }
       grid_barrier(a.bar, nblk);
       // fixed-order sum over the frame chunks; tiles hold the upper triangle (ti <= tj), S is kept full

@@ -88,8 +88,13 @@ def rewrite_asm(m):
   if "globaltimer" in body: return "t_ = 0;"                       # profiling timestamps: no clock on the interpreter
   if "red.global.add.f64" in body: return "*p += v;"
   # bulk asynchronous copies + mbarrier (csrc/linearize.cuh): the interpreter copies synchronously, the barrier has nothing left to wait for
+  # bulk asynchronous copies + mbarrier (csrc/solver_kernels.cuh): the copy is synchronous here, so a phase completes when the producer
+  # arms it (the word counts completed phases); a consumer waiting for parity P yields until the count's parity differs from P
   if "cp.async.bulk.shared" in body: return "memcpy(dst, src, bytes);"
-  if "mbarrier." in body or "fence.mbarrier_init" in body: return ";"                # fire-and-forget fp64 add to an address only this thread updates
+  if "mbarrier.init" in body: return "*bar = 0ull;"
+  if "mbarrier.arrive.expect_tx" in body: return "*(volatile unsigned long long*)bar = *bar + 1ull;"
+  if "mbarrier.try_wait" in body: return "while ((*(volatile unsigned long long*)bar & 1ull) == (unsigned long long)phase) simt::spin_yield();"
+  if "fence.mbarrier_init" in body or "fence.proxy.async" in body: return ";"                # fire-and-forget fp64 add to an address only this thread updates
   raise ValueError("inline PTX without a host meaning: " + body[:80])
 
 
