@@ -23,6 +23,9 @@ constexpr int LIN_KPAD = 36;           // 32 staged residual rows + 4: (column s
 constexpr int LIN_MAXV = 96;           // views of a frame staged in shared memory (more: the list is read from global memory)
 constexpr int LIN_MAXC = 1024;         // cameras tracked by the per-frame presence mask (more: W_f is zero-filled first)
 constexpr int LIN_MAXB = 8;            // board pose tables staged per frame (more boards: the tables are read from global memory)
+constexpr int LIN_TSTR = 12;           // row stride of T^t in the epilogue (stride mod 16 == 12: conflict-free fragment loads)
+constexpr int LIN_VC = 44;             // per-warp view constants: 12 doubles per chain + the intrinsics
+constexpr int LIN_WB_FLAG = 0x4000;    // scatter-table entry: add the view's board offset (rows of W_f that belong to board b)
 
 // compile-time shape of a residual row's local Jacobian [twist block(s) | fx fy cx cy dist | r]
 template <int MODEL, bool ROLL>
@@ -147,16 +150,17 @@ __host__ __device__ inline int lin_record_doubles(int T, int D, int B) { return 
 __host__ __device__ inline size_t lin_warp_doubles(int NC, int T, int D, int FB, int nin, int B, int NP) {
   (void)nin;
   const int KO = 6 * NP, PC = 6 * (NP + 1);
-  const int PT = (PC + 7) / 8;
-  const int need = NC * NC + 8 * PT * NC + 24 * NP, chunk = NC * LIN_KPAD;
-  return ((size_t)(((chunk > need ? chunk : need) + 1) & ~1)      // stage (chunk loop, 32 rows at a time) = Ms | T^t | map scratch (epilogue)
-       + KO * PC + 12 * NP                // E: twist maps of the view [KO][PC] | chain cache R_cf, t_cf
+  const int PT = (PC + 7) / 8, EK = 4 * ((KO + 3) / 4), EP = 8 * PT + 4, MR = 8 * ((EK + 7) / 8);
+  const int need = MR * (NC + 4) + 8 * PT * LIN_TSTR, chunk = NC * LIN_KPAD;
+  return ((size_t)(((chunk > need ? chunk : need) + 1) & ~1)      // stage (chunk loop, 32 rows at a time) = Ms | T^t (epilogue)
+       + EK * EP + 12 * NP                // E: twist maps of the view [EK][EP], zero padded | chain R_cf, t_cf
        + (size_t)B * 6 * FB               // Wb: this warp's partial board rows of W_f
        + FB * FB + FB                     // hacc: H_ff | g_f partial
        + D * FB                           // wacc: sum over the camera's boards of M[:, xi] Af
        + T                                // macc: raw moment sum of the current camera
        + (D * 6 + 42)                     // ub: board coupling of the current (camera, board)
-       + 6                                // cost of this frame's views | cur_cam | cur_board | wdirty | chain frame | pad
+       + 6                                // cost of this frame's views | cur_cam | cur_board | wdirty | chain frame | chain camera
+       + LIN_VC                           // pose and intrinsics of the view in progress
        + 1) & ~(size_t)1;                 // even: every warp's stage buffer takes 16-byte stores
 }
 // dynamic shared memory of a CTA of `warps` warps: the warps' slices, then the pose tables staged per frame (frame [NP] | boards [min(B, LIN_MAXB)])
@@ -179,23 +183,30 @@ struct LinLayout {
   static constexpr int PC = 6 * (S::NP + 1);                    // columns of the map matrix E: frame-pose block(s) | board-pose block
   static constexpr int PT = (PC + 7) / 8;                       // 8-row tiles of T^t = E^T M[xi, :]
   static constexpr int KS = (S::KO + 3) / 4;                    // k-steps over the twist components
-  static constexpr int Ms = 0;                                  // [NC][NC] full symmetric, column D = G^T r
-  static constexpr int Tt = Ms + S::NC * S::NC;                 // [8 PT][NC]   T^t = E^T M[xi, :]
-  static constexpr int scr = Tt + 8 * PT * S::NC;               // 24 NP doubles: R J_L products and chain translations while a map is built
-  static constexpr int stage_need = scr + 24 * S::NP;           // what the epilogue needs
+  static constexpr int EK = 4 * KS;                             // rows of E (twist components), zero padded to the k-steps
+  static constexpr int EP = 8 * PT + 4;                         // row stride of E; strides mod 16 == 4 or 12: the mma fragment loads
+  static constexpr int MSTR = S::NC + 4;                        //   (address = 4-lane group x stride + lane in group) hit 16 different banks
+  static constexpr int MR = 8 * ((EK + 7) / 8);                 // rows of M the epilogue multiplies with: the twist rows
+  static constexpr int Ms = 0;                                  // [MR][MSTR] rows xi of the view's moment matrix, column D = G^T r
+  static constexpr int Tt = Ms + MR * MSTR;                     // [8 PT][LIN_TSTR]   T^t[:, xi]
+  static constexpr int stage_need = Tt + 8 * PT * LIN_TSTR;     // what the epilogue needs
   static constexpr int stage_end = ((S::NC * LIN_KPAD > stage_need ? S::NC * LIN_KPAD : stage_need) + 1) & ~1;
   static_assert((2 * S::NPAIR + 1) * 32 <= stage_end, "the fragments of a view part must fit the warp's stage buffer");
+  static_assert(EK <= LIN_TSTR && (MSTR % 16 == 4 || MSTR % 16 == 12) && (EP % 16 == 4 || EP % 16 == 12), "fragment strides");
   static constexpr int NHF = S::FB * S::FB + S::FB;             // H_ff | g_f
   static constexpr int NWC = S::D * S::FB;                      // sum over the camera's boards of Tf = M[:, xi] Af (D x FB)
-  // after the stage buffer: E [KO][PC] | chain cache (R_cf 9 NP, t_cf 3 NP) | Wb [B][6][FB] | hacc [NHF] | wacc [NWC] | macc [T] | ub [UB] | tail [4]
+  // scatter tables (per CTA, one entry per lane): where the C fragments of the epilogue's products and of the moment tiles are added
+  static constexpr int NTT = PT * S::NT * 2, NTP = PT * PT * 2, NTM = S::NPAIR * 2;
+  // after the stage buffer: E [EK][EP] | chain (R_cf 9, t_cf 3) x NP | Wb [B][6][FB] | hacc [NHF] | wacc [NWC] | macc [T] | ub [UB] | tail [6]
   static constexpr int E = stage_end;
-  static constexpr int chain = E + S::KO * PC;
+  static constexpr int chain = E + EK * EP;
   static constexpr int Wb = chain + 12 * S::NP;
   __device__ static int hacc(int B) { return Wb + B * 6 * S::FB; }
   __device__ static int wacc(int B) { return hacc(B) + NHF; }
   __device__ static int macc(int B) { return wacc(B) + NWC; }
   __device__ static int ub(int B) { return macc(B) + S::T; }
-  __device__ static int tail(int B) { return ub(B) + S::UB; }      // [0] frame cost of this warp's views, [1] cur_cam, [2] cur_board, [3] wdirty, [4] frame the chain cache belongs to
+  __device__ static int tail(int B) { return ub(B) + S::UB; }      // [0] frame cost of this warp's views, [1] cur_cam, [2] cur_board, [3] wdirty, [4] [5] frame / camera of the chain cache
+  __device__ static int vc(int B) { return tail(B) + 6; }          // constants of the view in progress: pose R, t [12 NP] | intrinsics [KINT]  (LIN_VC doubles)
 };
 
 // one entry e = kk*6 + col of the 6x6 twist map of a pose (geometry.cuh twist_map): RJ = R_left J_L, Rl = R_left, t = chain translation
@@ -269,143 +280,109 @@ __device__ __forceinline__ void lin_flush_wacc(const DeviceProblem& p, const Lin
   for (int o = lane; o < L::NWC; o += 32) wacc[o] = 0.0;
 }
 
-// Epilogue of one view (camera c, frame f, board b), leader warp.  In: the view's moment matrix in Ms (both triangles, column D = G^T r)
-// and its cost.  With E = [Af_0 .. | Ab] the 6 x 6 twist maps of the view stacked by columns (rows = twist components):
+// entry (r, c) of the 3x3 product A B
+__device__ __forceinline__ double mat3_entry(const double* A, const double* B, int r, int c) {
+  return A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+}
+// The 27 structurally non-zero entries of a 6x6 twist map (geometry.cuh twist_map) with R_left = Rl, left Jacobian JL and chain translation
+// t, one per lane: e < 9 -> (rotation rows, rotation columns) = Rl JL, e < 18 -> (translation rows, translation columns) = Rl,
+// else (translation rows, rotation columns) = t x (Rl JL).  Returns the value, row kk and column col.
+__device__ __forceinline__ double twist_nonzero(const double* Rl, const double* JL, const double* t, int e, int& kk, int& col) {
+  if (e < 9) { kk = e / 3; col = e % 3; return mat3_entry(Rl, JL, kk, col); }
+  if (e < 18) { const int q = e - 9; kk = 3 + q / 3; col = 3 + q % 3; return Rl[q]; }
+  const int q = e - 18, r = q / 3;
+  col = q % 3; kk = 3 + r;
+  const double a0 = mat3_entry(Rl, JL, 0, col), a1 = mat3_entry(Rl, JL, 1, col), a2 = mat3_entry(Rl, JL, 2, col);
+  return r == 0 ? t[1] * a2 - t[2] * a1 : r == 1 ? t[2] * a0 - t[0] * a2 : t[0] * a1 - t[1] * a0;
+}
+
+// The noinline helpers below take the problem description by POINTER to the CTA's copy in shared memory: a reference to the kernel's own
+// parameter would force the compiler to keep a local-memory copy of it and to reach every table of the kernel through that copy.
+// what: 1 = board coupling of the current (camera, board), 2 = the camera's rows of W_f, 4 = the camera's raw moment sum
+template <int MODEL, bool ROLL>
+__device__ __noinline__ void lin_flush(const DeviceProblem* p, const LinArgs* a, double* w, double* myrec, unsigned* seen, int f, int what) {
+  const int lane = threadIdx.x & 31;
+  if (what & 1) lin_flush_ub<MODEL, ROLL>(*p, w, myrec, lane);
+  if (what & 2) lin_flush_wacc<MODEL, ROLL>(*p, *a, w, f, lane, seen);
+  if (what & 4) lin_flush_macc<MODEL, ROLL>(*p, w, myrec, lane);
+  __syncwarp();
+}
+
+// Epilogue of one view (camera c, frame f, board b), leader warp.  In: rows xi of the view's moment matrix in Ms (column D = G^T r), the
+// chain R_cf, t_cf of (camera, frame) in the warp's slice.  With E = [Af_0 .. | Ab] the 6 x 6 twist maps of the view stacked by columns
+// (rows = twist components):
 //     T^t = E^T M[xi, :]      rows f: Tf^t (-> W_f camera / intrinsics rows, g_f)      rows b: Tb^t (-> camera x board blocks, board gradient)
 //     P   = T^t[:, xi] E      (f,f) -> H_ff      (b,f) -> W_f board rows      (b,b) -> board x board block
-// both products on the fp64 tensor path (mma.m8n8k4, 8 + 8 instructions for the 5-coefficient model); the C fragments are added
-// straight into the warp's running sums.  A call, not inlined: the chunk loop of the kernel keeps its registers.
+// both products on the fp64 tensor path (mma.m8n8k4, 8 + 8 instructions for the 5-coefficient model); every lane adds its C fragments
+// to the warp's running sums at offsets it reads from the CTA's scatter tables (no index arithmetic, no branches on the element's role).
+// A call, not inlined: the chunk loop of the kernel keeps its registers.
 template <int MODEL, bool ROLL>
-__device__ __noinline__ void lin_view_epilogue(const DeviceProblem& p, const LinArgs& a, double* w, double* myrec, const PoseT* ftab, const PoseT* btab, unsigned* seen, int c, int f, int b, double cost_acc) {
+__device__ __noinline__ void lin_view_epilogue(int B, bool frames_on, bool boards_on, const PoseT* pcam, double* w, const PoseT* ftab, const PoseT* btab,
+                                               const short (*tabT)[32], const short (*tabP)[32], int b, double cost_acc, bool new_chain) {
   using S = LinShape<MODEL, ROLL>; using L = LinLayout<MODEL, ROLL>;
-  constexpr int NP = S::NP, KO = S::KO, D = S::D, E_ = S::E, T = S::T, NC = S::NC, NT = S::NT, FB = S::FB;
-  constexpr int PC = L::PC, PT = L::PT, KS = L::KS;
+  constexpr int NP = S::NP, T = S::T, NT = S::NT, FB = S::FB;
+  constexpr int PT = L::PT, KS = L::KS, EP = L::EP, MSTR = L::MSTR, EK = L::EK;
   const int lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
-  const int B = p.B;
-  const bool frames_on = p.motion_on != 0, boards_on = p.off_bp >= 0;
-  double* Ms = w + L::Ms; double* Tt = w + L::Tt; double* scr = w + L::scr;
-  double* Em = w + L::E; double* chain = w + L::chain;
-  double* Wb = w + L::Wb; double* hacc = w + L::hacc(B); double* wacc = w + L::wacc(B); double* macc = w + L::macc(B); double* ub = w + L::ub(B);
+  double* Ms = w + L::Ms; double* Tt = w + L::Tt;
+  double* Em = w + L::E; const double* chain = w + L::chain;
   double* tl = w + L::tail(B);
-  // ftab: this frame's pose table(s) [NP], btab: the board tables [B] (staged in shared memory by the CTA)
-  const bool cam_changed = c != (int)tl[1];
-  if (cam_changed) {
-    lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane); lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane, seen); lin_flush_macc<MODEL, ROLL>(p, w, myrec, lane);
-    __syncwarp();
-    if (lane == 0) { tl[1] = c; tl[2] = -1.0; }
-    __syncwarp();
-  }
-  if (b != (int)tl[2]) {
-    lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane);
-    __syncwarp();
-    if (lane == 0) tl[2] = b;
-  }
-  // ---- twist maps.  The chain up to the frame pose(s) and the frame block(s) of E change with (camera, frame); the board block per view.
-  const PoseT& pc = p.cam_T[c];
-  if (frames_on || boards_on) {
-    // (camera, frame) part: recomputed when the warp meets the pair for the first time
-    const bool new_chain = cam_changed || (int)tl[4] != f;
-    if (new_chain) {
-      for (int o = lane; o < 21 * NP; o += 32) {
-        const int j = o / 21, e = o % 21;
-        const PoseT& pf = ftab[j];
-        if (e < 9) { const int r = e / 3, cc = e % 3; chain[12 * j + e] = pc.R[3 * r] * pf.R[cc] + pc.R[3 * r + 1] * pf.R[3 + cc] + pc.R[3 * r + 2] * pf.R[6 + cc]; }
-        else if (e < 12) { const int r = e - 9; chain[12 * j + 9 + r] = pc.R[3 * r] * pf.t[0] + pc.R[3 * r + 1] * pf.t[1] + pc.R[3 * r + 2] * pf.t[2] + pc.t[r]; }
-        else { const int q = e - 12, r = q / 3, cc = q % 3; scr[9 * j + q] = pc.R[3 * r] * pf.JL[cc] + pc.R[3 * r + 1] * pf.JL[3 + cc] + pc.R[3 * r + 2] * pf.JL[6 + cc]; }      // R_c J_L(frame)
-      }
-      __syncwarp();
-      if (frames_on)
-        for (int o = lane; o < 36 * NP; o += 32) {
-          const int j = o / 36, e = o % 36, kk = e / 6, col = e % 6;
-          const double val = twist_entry(scr + 9 * j, pc.R, chain + 12 * j + 9, kk, col);
-          // block j of the twist components only reaches frame pose j
-#pragma unroll
-          for (int jj = 0; jj < NP; jj++) Em[(6 * jj + kk) * PC + 6 * j + col] = jj == j ? val : 0.0;
-        }
-      __syncwarp();
+  if (lane == 0) { (w + L::macc(B))[T - 1] += cost_acc; tl[0] += cost_acc; tl[3] = 1.0; }
+  if (!(frames_on || boards_on)) { __syncwarp(); return; }
+  // ---- twist maps: the frame block(s) of E change with (camera, frame), the board block with the view.  Entries that are structurally
+  // zero (and the blocks of parameter groups that are switched off) were zeroed when the kernel started and are never written.
+  const PoseT& pc = *pcam;
+  if (frames_on && new_chain)
+    for (int o = lane; o < 27 * NP; o += 32) {
+      const int j = o / 27; int kk, col;
+      const double val = twist_nonzero(pc.R, ftab[j].JL, chain + 12 * j + 9, o % 27, kk, col);
+      Em[(6 * j + kk) * EP + 6 * j + col] = val;            // block j of the twist components only reaches frame pose j
     }
-    if (boards_on) {
-      const PoseT& pb = btab[b];
-      for (int o = lane; o < 12 * NP; o += 32) {
-        const int j = o / 12, e = o % 12;
-        const double* Rc = chain + 12 * j;
-        if (e < 9) { const int r = e / 3, cc = e % 3; scr[12 * j + e] = Rc[3 * r] * pb.JL[cc] + Rc[3 * r + 1] * pb.JL[3 + cc] + Rc[3 * r + 2] * pb.JL[6 + cc]; }
-        else { const int r = e - 9; scr[12 * j + 9 + r] = Rc[3 * r] * pb.t[0] + Rc[3 * r + 1] * pb.t[1] + Rc[3 * r + 2] * pb.t[2] + chain[12 * j + 9 + r]; }
-      }
-      __syncwarp();
-      for (int o = lane; o < 36 * NP; o += 32) {
-        const int j = o / 36, e = o % 36, kk = e / 6, col = e % 6;
-        Em[(6 * j + kk) * PC + 6 * NP + col] = twist_entry(scr + 12 * j, chain + 12 * j, scr + 12 * j + 9, kk, col);
-      }
-    } else {
-      for (int o = lane; o < KO * 6; o += 32) Em[(o / 6) * PC + 6 * NP + o % 6] = 0.0;
+  if (boards_on) {
+    const PoseT& pb = btab[b];
+    for (int o = lane; o < 27 * NP; o += 32) {
+      const int j = o / 27; int kk, col;
+      const double* Rc = chain + 12 * j;
+      double t[3];
+      mat3_vec(Rc, pb.t, t);
+      t[0] += Rc[9]; t[1] += Rc[10]; t[2] += Rc[11];
+      const double val = twist_nonzero(Rc, pb.JL, t, o % 27, kk, col);
+      Em[(6 * j + kk) * EP + 6 * NP + col] = val;
     }
-    if (!frames_on && new_chain)
-      for (int o = lane; o < KO * 6 * NP; o += 32) Em[(o / (6 * NP)) * PC + o % (6 * NP)] = 0.0;
   }
-  // the camera's raw moment sum: upper triangle | G^T r | cost
-#pragma unroll
-  for (int I = 0; I < NT; I++)
-#pragma unroll
-    for (int J = I; J < NT; J++)
-#pragma unroll
-      for (int h = 0; h < 2; h++) {                     // the fragment positions of the upper-triangle tiles: every element exactly once
-        const int i = 8 * I + grp, j = 8 * J + 2 * tig + h;
-        if (i < D && j < D && i <= j) macc[tri_index(D, i, j)] += Ms[i * NC + j];
-        else if (i < D && j == D) macc[E_ + i] += Ms[i * NC + D];
-      }
-  if (lane == 0) { macc[T - 1] += cost_acc; tl[0] += cost_acc; tl[3] = 1.0; tl[4] = f; }
   __syncwarp();
-  if (!(frames_on || boards_on)) return;
   // ---- T^t = E^T M[xi, :]
 #pragma unroll
   for (int I = 0; I < PT; I++) {
     double fa[KS];
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++) { const int pp = 8 * I + grp, kk = 4 * ks + tig; fa[ks] = (pp < PC && kk < KO) ? Em[kk * PC + pp] : 0.0; }
+    for (int ks = 0; ks < KS; ks++) fa[ks] = Em[(4 * ks + tig) * EP + 8 * I + grp];
 #pragma unroll
     for (int J = 0; J < NT; J++) {
       double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < KS; ks++) { const int kk = 4 * ks + tig; const double fb = kk < KO ? Ms[kk * NC + 8 * J + grp] : 0.0; dmma884(c0, c1, fa[ks], fb); }
-      const int pp = 8 * I + grp;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int j = 8 * J + 2 * tig + h;
-        const double val = h == 0 ? c0 : c1;
-        Tt[pp * NC + j] = val;
-        if (pp < 6 * NP) {                                  // frame rows: Tf^t
-          if (frames_on) { if (j < D) wacc[j * FB + pp] += val; else if (j == D) hacc[FB * FB + pp] += val; }
-        } else if (pp < PC) {                               // board rows: Tb^t
-          if (boards_on) { const int r = pp - 6 * NP; if (j < D) ub[j * 6 + r] += val; else if (j == D) ub[D * 6 + 36 + r] += val; }
-        }
-      }
+      for (int ks = 0; ks < KS; ks++) dmma884(c0, c1, fa[ks], Ms[(4 * ks + tig) * MSTR + 8 * J + grp]);
+      if (8 * J < EK) { if (8 * J + 2 * tig < EK) *reinterpret_cast<double2*>(Tt + (8 * I + grp) * LIN_TSTR + 8 * J + 2 * tig) = make_double2(c0, c1); }
+      const int o0 = tabT[(I * NT + J) * 2][lane], o1 = tabT[(I * NT + J) * 2 + 1][lane];
+      if (o0 >= 0) w[o0] += c0;
+      if (o1 >= 0) w[o1] += c1;
     }
   }
   __syncwarp();
   // ---- P = T^t[:, xi] E
+  const int wb = b * 6 * FB;
 #pragma unroll
   for (int I = 0; I < PT; I++) {
     double fa[KS];
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++) { const int kk = 4 * ks + tig; fa[ks] = kk < KO ? Tt[(8 * I + grp) * NC + kk] : 0.0; }
+    for (int ks = 0; ks < KS; ks++) fa[ks] = Tt[(8 * I + grp) * LIN_TSTR + 4 * ks + tig];
 #pragma unroll
     for (int J = 0; J < PT; J++) {
       double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-      for (int ks = 0; ks < KS; ks++) { const int kk = 4 * ks + tig, q = 8 * J + grp; const double fb = (kk < KO && q < PC) ? Em[kk * PC + q] : 0.0; dmma884(c0, c1, fa[ks], fb); }
-      const int pp = 8 * I + grp;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int q = 8 * J + 2 * tig + h;
-        const double val = h == 0 ? c0 : c1;
-        if (pp < FB) { if (frames_on && q < FB) hacc[pp * FB + q] += val; }
-        else if (pp < PC && boards_on) {
-          const int r = pp - FB;
-          if (q < FB) { if (frames_on) Wb[(size_t)b * 6 * FB + r * FB + q] += val; }
-          else if (q < PC) ub[D * 6 + r * 6 + (q - FB)] += val;
-        }
-      }
+      for (int ks = 0; ks < KS; ks++) dmma884(c0, c1, fa[ks], Em[(4 * ks + tig) * EP + 8 * J + grp]);
+      const int o0 = tabP[(I * PT + J) * 2][lane], o1 = tabP[(I * PT + J) * 2 + 1][lane];
+      if (o0 >= 0) w[(o0 & (LIN_WB_FLAG - 1)) + ((o0 & LIN_WB_FLAG) ? wb : 0)] += c0;
+      if (o1 >= 0) w[(o1 & (LIN_WB_FLAG - 1)) + ((o1 & LIN_WB_FLAG) ? wb : 0)] += c1;
     }
   }
   __syncwarp();
@@ -420,6 +397,8 @@ k_linearize(DeviceProblem p, LinArgs a) {
   extern __shared__ double lsm[];
   __shared__ int fv_cam[LIN_MAXV], fv_board[LIN_MAXV], fv_start[LIN_MAXV + 1];
   __shared__ int any_view;
+  __shared__ DeviceProblem ps;                       // copies for the noinline helpers (lin_flush)
+  __shared__ LinArgs as_;
   __shared__ unsigned cam_seen[LIN_MAXC / 32];       // cameras with a view in the frame in progress (their W_f rows are written by the owning warp)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -436,16 +415,52 @@ k_linearize(DeviceProblem p, LinArgs a) {
   PoseT* ftab2 = reinterpret_cast<PoseT*>(lsm + (size_t)nwarps * wd);       // [2][NP]
   const bool boards_staged = B <= LIN_MAXB;
   const PoseT* btab = boards_staged ? ftab2 + 2 * NP : p.board_T;
-  if (tid == 0) { mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1); mbar_init(&tbar[2], 1); fence_barrier_init(); }
+  if (tid == 0) { mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1); mbar_init(&tbar[2], 1); fence_barrier_init(); ps = p; as_ = a; }
+  static_assert(12 * NP + KINT <= LIN_VC, "view constants");
+  // scatter tables: for every C-fragment slot of the epilogue's two products and of the moment tiles, the offset (from the warp's
+  // slice) of the running sum the lane's element belongs to, or -1
+  __shared__ short tabT[L::NTT][32], tabP[L::NTP][32], tabM[L::NTM][32];
+  {
+    constexpr int PC = L::PC, PT = L::PT, E_ = S::E;
+    const bool boards_on = p.off_bp >= 0;
+    for (int o = tid; o < L::NTT * 32; o += nthreads) {
+      const int e = o >> 5, l = o & 31, I = e / (NT * 2), J = (e >> 1) % NT, h = e & 1;
+      const int pp = 8 * I + (l >> 2), j = 8 * J + 2 * (l & 3) + h;
+      int off = -1;
+      if (pp < 6 * NP) { if (frames_on) { if (j < D) off = L::wacc(B) + j * FB + pp; else if (j == D) off = L::hacc(B) + FB * FB + pp; } }
+      else if (pp < PC && boards_on) { const int r = pp - 6 * NP; if (j < D) off = L::ub(B) + j * 6 + r; else if (j == D) off = L::ub(B) + D * 6 + 36 + r; }
+      tabT[e][l] = (short)off;
+    }
+    for (int o = tid; o < L::NTP * 32; o += nthreads) {
+      const int e = o >> 5, l = o & 31, I = e / (PT * 2), J = (e >> 1) % PT, h = e & 1;
+      const int pp = 8 * I + (l >> 2), q = 8 * J + 2 * (l & 3) + h;
+      int off = -1;
+      if (pp < FB) { if (frames_on && q < FB) off = L::hacc(B) + pp * FB + q; }
+      else if (pp < PC && boards_on) {
+        const int r = pp - FB;
+        if (q < FB) { if (frames_on) off = (L::Wb + r * FB + q) | LIN_WB_FLAG; }
+        else if (q < PC) off = L::ub(B) + D * 6 + r * 6 + (q - FB);
+      }
+      tabP[e][l] = (short)off;
+    }
+    for (int o = tid; o < L::NTM * 32; o += nthreads) {
+      const int e = o >> 5, l = o & 31, h = e & 1;
+      int t = e >> 1, I = 0;
+      while (t >= NT - I) { t -= NT - I; I++; }
+      const int J = I + t, i = 8 * I + (l >> 2), j = 8 * J + 2 * (l & 3) + h;
+      int off = -1;
+      if (i < D && j < D && i <= j) off = L::macc(B) + tri_index(D, i, j);
+      else if (i < D && j == D) off = L::macc(B) + E_ + i;
+      tabM[e][l] = (short)off;
+    }
+  }
   const int rec = lin_record_doubles(T, D, B);
   double* myrec = a.spart + (size_t)blockIdx.x * p.C * rec;
 
   // this CTA's records start at zero; the leader warps' running sums too
   for (int i = tid; i < p.C * rec; i += nthreads) myrec[i] = 0.0;
-  if (leader) {
-    for (int i = L::E + lane; i < L::tail(B); i += 32) w[i] = 0.0;       // E | chain | Wb | hacc | wacc | macc | ub
-    if (lane == 0) { double* tl = w + L::tail(B); tl[0] = 0.0; tl[1] = -1.0; tl[2] = -1.0; tl[3] = 0.0; tl[4] = -1.0; }
-  }
+  if (leader) for (int i = L::E + lane; i < L::tail(B); i += 32) w[i] = 0.0;       // E | chain | Wb | hacc | wacc | macc | ub
+  if (lane == 0) { double* tl = w + L::tail(B); tl[0] = 0.0; tl[1] = -1.0; tl[2] = -1.0; tl[3] = 0.0; tl[4] = -1.0; tl[5] = -1.0; }
   __syncthreads();
   if (tid == 0) {
     if (boards_staged) { mbar_expect_tx(&tbar[2], (unsigned)(sizeof(PoseT) * B)); bulk_g2s(ftab2 + 2 * NP, p.board_T, (unsigned)(sizeof(PoseT) * B), &tbar[2]); }
@@ -503,15 +518,44 @@ k_linearize(DeviceProblem p, LinArgs a) {
       for (int i = 0; i < NPAIR; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
       double cost_acc = 0.0;
       int c = 0, b = 0;
+      bool new_chain = false;
       if (have) {
         c = staged ? fv_cam[v - v0] : p.view_cam[v]; b = staged ? fv_board[v - v0] : p.view_board[v];
         const int beg = staged ? fv_start[v - v0] : p.view_start[v], end = staged ? fv_start[v - v0 + 1] : p.view_start[v + 1];
-        ViewPose vp, vpe;
-        compose_views<ROLL>(p, c, f, b, vp, vpe);
+        // R_cf, t_cf of (camera, frame): kept in the warp's slice while the warp stays with the pair (all boards of the frame)
+        double* chain = w + L::chain; double* tl = w + L::tail(B);
+        new_chain = (int)tl[4] != f || (int)tl[5] != c;
+        if (new_chain) {
+          const PoseT& pc = p.cam_T[c];
+          __syncwarp();
+          for (int o = lane; o < 12 * NP; o += 32) {
+            const int j = o / 12, e = o % 12;
+            const PoseT& pf = ftab[j];
+            if (e < 9) chain[12 * j + e] = mat3_entry(pc.R, pf.R, e / 3, e % 3);
+            else { const int r = e - 9; chain[12 * j + e] = pc.R[3 * r] * pf.t[0] + pc.R[3 * r + 1] * pf.t[1] + pc.R[3 * r + 2] * pf.t[2] + pc.t[r]; }
+          }
+          if (lane == 0) { tl[4] = f; tl[5] = c; }
+          __syncwarp();
+        }
+        // the view's constants -- pose(s) T_c T_f T_b and the camera's intrinsics -- go to the warp's slice: the chunk loop reads them from
+        // shared memory where it needs them instead of holding 22 doubles in registers (they would be spilled to local memory)
+        double* vc = w + L::vc(B);
+        {
+          const PoseT& pb = btab[b];
+          for (int o = lane; o < 12 * NP + KINT; o += 32) {
+            if (o < 12 * NP) {
+              const int j = o / 12, e = o % 12;
+              const double* Rc = chain + 12 * j;
+              if (e < 9) vc[o] = mat3_entry(Rc, pb.R, e / 3, e % 3);
+              else { const int r = e - 9; vc[o] = Rc[3 * r] * pb.t[0] + Rc[3 * r + 1] * pb.t[1] + Rc[3 * r + 2] * pb.t[2] + Rc[9 + r]; }
+            } else vc[o] = p.intr[c * KINT + o - 12 * NP];
+          }
+          __syncwarp();
+        }
+        const ViewPose& vp = *reinterpret_cast<const ViewPose*>(vc);
+        const ViewPose& vpe = *reinterpret_cast<const ViewPose*>(vc + (ROLL ? 12 : 0));
+        const double* k = vc + 12 * NP;
         const double inv_h = ROLL ? 1.0 / p.img_h[c] : 0.0;
-        double k[KINT];
-#pragma unroll
-        for (int i = 0; i < KINT; i++) k[i] = p.intr[c * KINT + i];
         const double* bp = p.board_pts + (size_t)b * p.P * 3;
         // the next chunk's observation / point id are in flight while this chunk is computed (one L2 round trip less per chunk on the
         // dependent chain  point id -> board point -> projection)
@@ -544,7 +588,19 @@ k_linearize(DeviceProblem p, LinArgs a) {
         }
       }
       if (have && leader) {
-        // fragments -> Ms (both triangles), then the epilogue works from shared memory
+        {   // the warp moves on to a view of camera c / board b: running sums of the previous camera / board go out first
+          double* tl = w + L::tail(B);
+          if (c != (int)tl[1]) {
+            lin_flush<MODEL, ROLL>(&ps, &as_, w, myrec, cam_seen, f, 7);
+            if (lane == 0) { tl[1] = c; tl[2] = b; }
+            __syncwarp();
+          } else if (b != (int)tl[2]) {
+            lin_flush<MODEL, ROLL>(&ps, &as_, w, myrec, cam_seen, f, 1);
+            if (lane == 0) tl[2] = b;
+            __syncwarp();
+          }
+        }
+        // the camera's raw moment sum (upper triangle | G^T r) straight from the fragments; rows xi of M -> Ms for the epilogue's products
         double* Ms = w + L::Ms;
         int t = 0;
 #pragma unroll
@@ -553,19 +609,21 @@ k_linearize(DeviceProblem p, LinArgs a) {
           for (int J = I; J < NT; J++) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
+              const int o = tabM[2 * t + h][lane];
+              if (o >= 0) w[o] += acc[t][h];
               const int i = 8 * I + grp, j = 8 * J + 2 * tig + h;
-              Ms[i * NC + j] = acc[t][h];
-              if (I != J) Ms[j * NC + i] = acc[t][h];
+              if (8 * I < L::EK) Ms[i * L::MSTR + j] = acc[t][h];
+              if (I != J && 8 * J < L::EK) Ms[j * L::MSTR + i] = acc[t][h];
             }
             t++;
           }
         __syncwarp();
-        lin_view_epilogue<MODEL, ROLL>(p, a, w, myrec, ftab, btab, cam_seen, c, f, b, cost_acc);
+        lin_view_epilogue<MODEL, ROLL>(B, frames_on, p.off_bp >= 0, p.cam_T + c, w, ftab, btab, tabT, tabP, b, cost_acc, new_chain);
       }
       if (have) v++;
     }
     // ---- end of the frame: camera rows out, then the CTA sums the slots' partials in slot order
-    if (leader) lin_flush_wacc<MODEL, ROLL>(p, a, w, f, lane, cam_seen);
+    if (leader) lin_flush<MODEL, ROLL>(&ps, &as_, w, myrec, cam_seen, f, 2);
     __syncthreads();
     if (frames_on && !fill_all) {
       double* Wf = a.W + (size_t)f * n_s * FB;
@@ -598,7 +656,7 @@ k_linearize(DeviceProblem p, LinArgs a) {
     }
     __syncthreads();
   }
-  if (leader) { lin_flush_ub<MODEL, ROLL>(p, w, myrec, lane); lin_flush_macc<MODEL, ROLL>(p, w, myrec, lane); }
+  if (leader) lin_flush<MODEL, ROLL>(&ps, &as_, w, myrec, cam_seen, 0, 5);
 }
 
 // ------------------------------------------------------------------------------------------------

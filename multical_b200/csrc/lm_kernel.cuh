@@ -508,6 +508,66 @@ __device__ __forceinline__ void chol_diag_body(int n, int kb, double* S, double*
   }
   __syncthreads();
 }
+// The same diagonal block by ONE warp: lane i keeps row i in registers, a column is one shuffle of the pivot, one rsqrt and a
+// shuffle per trailing column -- no block barrier on the column path (scripts/chol_bench.cu: 9.2 us against 12.9 us for the
+// 256-thread version, whose column costs two __syncthreads).  The inverse of the factor follows in the same warp, lane j solving
+// for column j with four independent partial sums per row.
+__device__ __noinline__ void chol_diag_warp_body(int n, int kb, double* S, double* Linv_all, int* chol_fail, double* sh) {
+  double (*Lm)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
+  double (*Liv)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + CHOL_NB * (CHOL_NB + 1));
+  const int nb = min(CHOL_NB, n - kb);
+  const int tid = threadIdx.x;
+  __syncthreads();                       // the block may just have been updated by this CTA (look-ahead tile of the previous panel)
+  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
+    const int i = o / CHOL_NB, j = o % CHOL_NB;
+    Lm[i][j] = (i < nb && j < nb) ? (j <= i ? __ldcg(&S[(size_t)(kb + i) * n + kb + j]) : 0.0) : (i == j ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    double a[CHOL_NB], rsd[CHOL_NB];
+#pragma unroll
+    for (int j = 0; j < CHOL_NB; j++) a[j] = j <= lane ? Lm[lane][j] : 0.0;
+#pragma unroll
+    for (int k = 0; k < CHOL_NB; k++) {
+      const double akk = __shfl_sync(0xffffffffu, a[k], k);
+      if (lane == 0 && k < nb && !(akk > 0.0)) *chol_fail += 1;
+      const double rs = fast_rsqrt(fmin(fmax(akk, 1e-30), 1e30));
+      rsd[k] = rs;
+      const double l = lane >= k ? a[k] * rs : 0.0;
+      a[k] = l;
+#pragma unroll
+      for (int j = k + 1; j < CHOL_NB; j++) { const double ljk = __shfl_sync(0xffffffffu, l, j); a[j] -= l * ljk; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CHOL_NB; j++) Lm[lane][j] = j <= lane ? a[j] : 0.0;
+    __syncwarp();
+    double z[CHOL_NB];
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; i++) {
+      double t0 = (i == lane) ? 1.0 : 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+      for (int m = 0; m < CHOL_NB; m += 4) {
+        if (m < i) t0 -= Lm[i][m] * z[m];
+        if (m + 1 < i) t1 -= Lm[i][m + 1] * z[m + 1];
+        if (m + 2 < i) t2 -= Lm[i][m + 2] * z[m + 2];
+        if (m + 3 < i) t3 -= Lm[i][m + 3] * z[m + 3];
+      }
+      z[i] = (i >= lane) ? ((t0 + t1) + (t2 + t3)) * rsd[i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < CHOL_NB; i++) Liv[i][lane] = z[i];
+  }
+  __syncthreads();
+  double* Li = Linv_all + (size_t)(kb / CHOL_NB) * CHOL_NB * CHOL_NB;
+  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
+    const int i = o / CHOL_NB, j = o % CHOL_NB;
+    if (i < nb && j <= i) S[(size_t)(kb + i) * n + kb + j] = Lm[i][j];
+    Li[o] = Liv[i][j];
+  }
+  __syncthreads();
+}
 // ---- reduced solve, n <= 128: one CTA of 16 x 16 threads, matrix cyclically distributed in registers: thread (ty,tx) owns
 // A[ty + 16 p][tx + 16 q].  After every 16 columns the register tile is ROTATED (a[p][q] <- a[p+1][q+1]) so that the active pivot
 // block is always a[0][0] / column block q = 0: every register index on the pivot path is static, the path is ~45 instructions
@@ -1135,7 +1195,7 @@ k_lm(LmArgs a) {
           const int t = (rem + CHOL_NB - 1) / CHOL_NB, ntile = t * (t + 1) / 2;
           if (blockIdx.x == 0) {
             if (b > 0) chol_fused_tile(n_s, b - 1, 0, 0, a.S, a.Linv, work);
-            chol_diag_body(n_s, kb, a.S, a.Linv, &chol_fail_s, work);
+            chol_diag_warp_body(n_s, kb, a.S, a.Linv, &chol_fail_s, work);
           }
           if (b > 0) {
             const int first = nblk > 1 ? (int)blockIdx.x - 1 : 0, step = nblk > 1 ? nblk - 1 : 1;

@@ -143,6 +143,26 @@ def test_many_cameras_use_the_cooperative_blocked_reduced_solve():
   assert a.cost == b.cost and np.array_equal(np.array(a.log, float), np.array(b.log, float), equal_nan=True) and a.chol_retries == 0
 
 
+def test_sixty_four_cameras_configs4_shape():
+  """BASELINE configs[4]'s shape (64-camera dome, one board, cameras + intrinsics optimised: n_s = 6*64 + 6 + 10*64 = 1030, 33 panels of
+  the cooperative factorisation, eight cameras per warp of the linearisation) at a frame count the dense oracle can hold: converged cost
+  against scipy's exact trust region on the oracle's residuals, bit-identical repeat."""
+  from multical_b200 import synthetic
+  scene = synthetic.make_scene(C=64, F=4, vis=0.10, seed=5, rig="dome")
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  eng = calib._upload(calib.inliers)
+  assert eng.num_params == prob.param_vec.size and eng.num_params - 6 * 4 == 1030
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-12, xtol=1e-12, gtol=1e-12,
+                               max_nfev=60, method="trf", tr_solver="exact")
+  out = calib.bundle_adjust(tolerance=1e-12, xtol=1e-12, gtol=1e-12, max_iterations=60)
+  assert abs(out.last_solve.cost - ref.cost) <= 1e-8 * ref.cost, (out.last_solve.cost, ref.cost)
+  a, b = calib.bundle_adjust().last_solve, calib.bundle_adjust().last_solve
+  assert a.cost == b.cost and np.array_equal(np.array(a.log, float), np.array(b.log, float), equal_nan=True)
+
+
 def test_two_identical_solves_agree_bit_for_bit():
   """The reference is bit-reproducible run to run (single-threaded numpy / scipy, calibration.py:204-212).  So is this engine on the
   standard path: fixed-order sums everywhere (per-CTA records, frame-chunk partials, rank-ordered exchanges), no atomics on data."""
