@@ -117,6 +117,12 @@ int  mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc,
  * order seen through mcba_residuals is still np.argwhere(mask) order.                                              */
 int  mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* mask, const double* points,
                        const double* board_points, int64_t* n_corners);
+/* The same with the mask in the two parts the reference builds it from (calibration.py:73-81: `valid` = point_table.valid &
+ * pose validity broadcast over the points): valid uint8[C][F][B][P] = point_table.valid as detected, view_valid uint8[C][F][B] =
+ * camera_poses.valid x motion.valid x board_poses.valid (may be NULL: all views valid).  The conjunction is taken on the device, so
+ * the caller hands over the detection table untouched (no 1-byte-per-point host pass before the copy).                          */
+int  mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid,
+                             const double* points, const double* board_points, int64_t* n_corners);
 
 /* full parameter state (also the values of disabled/fixed blocks):
  * cam_rt f64[C][6], board_rt f64[B][6], frame_rt f64[F][6] (PoseSet.params, pose_set.py:51-53),

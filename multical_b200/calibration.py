@@ -153,12 +153,20 @@ class Calibration(Parameters):
     head = xe.size - keep.size
     return np.concatenate([xe[:head], xe[head:][keep]])
 
-  def _upload(self, mask, points=None, device=None):
+  def _upload(self, mask, points=None, device=None, view_valid=None):
     eng = get_engine(device)
     pts = np.asarray(self.point_table.points) if points is None else points
-    eng.upload_dense(self.engine_model, self._optimize_bits(), mask, pts, self.board_points.points)
+    eng.upload_dense(self.engine_model, self._optimize_bits(), mask, pts, self.board_points.points, view_valid=view_valid)
     self._push_state(eng)
     return eng
+
+  def _upload_inliers(self, device=None):
+    """`_upload(self.inliers)` without building `valid` on the host when no inlier mask is set (and `valid` has not been asked for
+    yet): the detection table goes over as it is, the pose validity of the views ([C,F,B]) beside it, and the device takes the
+    conjunction (calibration.py:73-81)."""
+    if self.inlier_mask is None and "valid" not in self.__dict__ and "inliers" not in self.__dict__:
+      return self._upload(np.asarray(self.point_table.valid), view_valid=self.pose_valid, device=device)
+    return self._upload(self.inliers, device=device)
 
   def _push_state(self, eng):
     # poses go over as 4x4 matrices: the matrix -> rotation-vector conversion (transform/rtvec.py:29-32) runs on the device
@@ -313,7 +321,7 @@ class Calibration(Parameters):
   def bundle_adjust(self, tolerance=1e-4, f_scale=1.0, max_iterations=100, loss="linear", xtol=1e-8, gtol=1e-8):
     """Non-linear least squares on point reprojection error (calibration.py:199-212), solved on the GPU
     with scipy-TRF semantics: ftol=tolerance, max_nfev=max_iterations, x_scale='jac', robust `loss`."""
-    eng = self._upload(self.inliers)
+    eng = self._upload_inliers()
     res = self._solve_logged(eng, tolerance, f_scale, max_iterations, loss, xtol, gtol)
     out = self._with_engine_state(eng)
     out.__dict__["last_solve"] = res

@@ -499,10 +499,29 @@ k_linearize(DeviceProblem p, LinArgs a) {
     }
     __syncthreads();
 
-    int v = v0;
+    // next view (at or after `from`) of this warp's cameras (c == slot mod slots; slots is a power of two): 32 views per look
+    auto next_view = [&](int from) {
+      while (from < v1) {
+        const int q = from + lane;
+        const int cq = q < v1 ? (staged ? fv_cam[q - v0] : p.view_cam[q]) : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, q < v1 && (cq & (slots - 1)) == slot);
+        if (m) return from + __ffs(m) - 1;
+        from += 32;
+      }
+      return v1;
+    };
+    // first chunk of a view: observation and point id of this lane's corner.  Requested one view ahead (before the previous view's
+    // epilogue), so that the DRAM round trip of a view's first corners is not on the warp's critical path
+    double2 ob_n = make_double2(0.0, 0.0); int pi_n = 0;
+    auto prefetch_view = [&](int vv) {
+      if (vv >= v1) return;
+      const int beg = staged ? fv_start[vv - v0] : p.view_start[vv], end = staged ? fv_start[vv - v0 + 1] : p.view_start[vv + 1];
+      const int i0 = beg + 32 * sub + lane;
+      if (i0 < end) { ob_n = p.obs[i0]; pi_n = p.pid[i0]; }
+    };
+    int v = next_view(v0);
+    prefetch_view(v);
     while (true) {
-      if (staged) { while (v < v1 && (fv_cam[v - v0] % slots) != slot) v++; }
-      else { while (v < v1 && (p.view_cam[v] % slots) != slot) v++; }
       const bool have = v < v1;
       if (split == 1) { if (!have) break; }
       else {
@@ -559,8 +578,6 @@ k_linearize(DeviceProblem p, LinArgs a) {
         const double* bp = p.board_pts + (size_t)b * p.P * 3;
         // the next chunk's observation / point id are in flight while this chunk is computed (one L2 round trip less per chunk on the
         // dependent chain  point id -> board point -> projection)
-        double2 ob_n = make_double2(0.0, 0.0); int pi_n = 0;
-        { const int i0 = beg + 32 * sub + lane; if (i0 < end) { ob_n = p.obs[i0]; pi_n = p.pid[i0]; } }
         for (int base = beg + 32 * sub; base < end; base += 32 * split) {
           const double2 ob = ob_n; const int pi = pi_n;
           const int i1 = base + 32 * split + lane;
@@ -570,6 +587,8 @@ k_linearize(DeviceProblem p, LinArgs a) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
       }
+      const int v_next = have ? next_view(v + 1) : v1;
+      prefetch_view(v_next);
       if (split > 1) {        // meet: the slot's leader adds the other warps' fragments in warp order (same lane -> same matrix element)
         if (have && !leader) {
           double* xr = w;                      // this warp's stage buffer is free between two views
@@ -620,7 +639,7 @@ k_linearize(DeviceProblem p, LinArgs a) {
         __syncwarp();
         lin_view_epilogue<MODEL, ROLL>(B, frames_on, p.off_bp >= 0, p.cam_T + c, w, ftab, btab, tabT, tabP, b, cost_acc, new_chain);
       }
-      if (have) v++;
+      v = v_next;
     }
     // ---- end of the frame: camera rows out, then the CTA sums the slots' partials in slot order
     if (leader) lin_flush<MODEL, ROLL>(&ps, &as_, w, myrec, cam_seen, f, 2);

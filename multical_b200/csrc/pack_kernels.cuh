@@ -9,13 +9,15 @@
 namespace mcba {
 
 // one warp per view (c,f,b): number of selected points; written in canonical (c,f,b) and frame-major (f,c,b) order
-__global__ void k_pack_count(const uint8_t* mask, int C, int F, int B, int P, int* cnt_can, int* cnt_fm, int* flag_can, int* flag_fm) {
+// view_valid (may be null): views whose camera / frame / board pose is invalid select nothing (calibration.py:73-79)
+__global__ void k_pack_count(const uint8_t* mask, const uint8_t* view_valid, int C, int F, int B, int P, int* cnt_can, int* cnt_fm, int* flag_can, int* flag_fm) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= C * F * B) return;
   const int b = w % B, f = (w / B) % F, c = w / (B * F);
   const uint8_t* m = mask + (size_t)w * P;
   int n = 0;
-  for (int p = lane; p < P; p += 32) n += m[p] ? 1 : 0;
+  if (!view_valid || view_valid[w])
+    for (int p = lane; p < P; p += 32) n += m[p] ? 1 : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if (lane == 0) {

@@ -57,7 +57,8 @@ struct mcba_ctx {
   DevBuf<double2> obs; DevBuf<uint16_t> pid; DevBuf<uint32_t> orig;
   DevBuf<int> view_start, view_cam, view_frame, view_board, frame_view_start, cam_view_start, cam_view_list;
   DevBuf<double> board_pts, cam_rt, board_rt, frame_rt, intr;
-  DevBuf<uint8_t> dense_mask; DevBuf<double2> dense_pts; DevBuf<int> scan;
+  DevBuf<uint8_t> dense_mask, view_valid; DevBuf<double2> dense_pts; DevBuf<int> scan;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr, copy_go = nullptr;      // observations of mcba_upload_dense* in flight beside the view count
   DevBuf<PoseT> cam_T, frame_T, board_T;
   // trial parameter state
   DevBuf<double> cam_rt2, board_rt2, frame_rt2, intr2, board_pts2, pose_mats;
@@ -651,7 +652,10 @@ int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
 }
 
 // pack the resident dense table (ctx->dense_pts) under a device mask into the frame-major corner arrays the kernels read
-int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_mask, bool keep_state, int64_t* n_corners) {
+// points_ready: event after which dense_pts holds the observations (they may still be in flight on the copy stream while the views are
+// counted and scanned), or null
+int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_mask, bool keep_state, int64_t* n_corners,
+               const uint8_t* d_view_valid = nullptr, cudaEvent_t points_ready = nullptr) {
   const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
   const int nv = C * F * B;
   cudaStream_t s = ctx->stream;
@@ -659,7 +663,7 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
   int* cnt_can = ctx->scan.p; int* cnt_fm = cnt_can + (nv + 1); int* flag_can = cnt_fm + (nv + 1); int* flag_fm = flag_can + (nv + 1);
   int totals[2] = {0, 0};
   if (nv > 0) {
-    k_pack_count<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_mask, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
+    k_pack_count<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_mask, d_view_valid, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
     k_scan_exclusive<<<4, 1024, 0, s>>>(cnt_can, nv, nv + 1); CKL();      // cnt_can | cnt_fm | flag_can | flag_fm
     CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -669,6 +673,7 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
   CK(ctx->obs.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->pid.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->orig.alloc((size_t)std::max<int64_t>(N, 1)));
   CK(ctx->view_start.alloc((size_t)V + 1)); CK(ctx->view_cam.alloc((size_t)std::max(V, 1))); CK(ctx->view_frame.alloc((size_t)std::max(V, 1))); CK(ctx->view_board.alloc((size_t)std::max(V, 1)));
   CK(ctx->frame_view_start.alloc((size_t)F + 1)); CK(ctx->cam_view_start.alloc((size_t)C + 1)); CK(ctx->cam_view_list.alloc((size_t)std::max(V, 1)));
+  if (points_ready) CK(cudaStreamWaitEvent(s, points_ready, 0));
   if (nv > 0) {
     PackOut o{ctx->obs.p, ctx->pid.p, ctx->orig.p, ctx->view_start.p, ctx->view_cam.p, ctx->view_frame.p, ctx->view_board.p,
               ctx->frame_view_start.p, ctx->cam_view_start.p, ctx->cam_view_list.p};
@@ -740,6 +745,9 @@ void mcba_destroy(mcba_ctx* ctx) {
 #endif
   for (void* p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
   if (ctx->peer_own) cudaFree(ctx->peer_own);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+  if (ctx->copy_go) cudaEventDestroy(ctx->copy_go);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStream_t own = ctx->own_stream;
   delete ctx;                            // device buffers are freed by their destructors
   if (own) cudaStreamDestroy(own);
@@ -875,26 +883,41 @@ int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam
 
 // Dense variant: the [C,F,B,P] inlier mask and [C,F,B,P,2] observations go to the device as they are and the
 // packing (frame-major order, view records, canonical index map) happens there (pack_kernels.cuh).
-int mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* mask, const double* points,
-                      const double* board_points, int64_t* n_corners) {
+int mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid, const double* points,
+                            const double* board_points, int64_t* n_corners) {
   if (!ctx || !desc) return MCBA_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   { int r = check_desc(ctx, desc); if (r) return r; }
-  REQUIRE(mask && points && board_points, MCBA_ERR_ARG, "null dense table");
+  REQUIRE(valid && points && board_points, MCBA_ERR_ARG, "null dense table");
   const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
   const int nv = C * F * B;
   const size_t dense = (size_t)nv * Pn;
   cudaStream_t s = ctx->stream;
   CK(ctx->dense_mask.alloc(std::max<size_t>(dense, 1))); CK(ctx->dense_pts.alloc(std::max<size_t>(dense, 1)));
+  CK(ctx->view_valid.alloc(std::max<size_t>((size_t)nv, 1)));
   CK(ctx->scan.alloc((size_t)4 * (nv + 1)));
-  if (dense) {
-    CK(cudaMemcpyAsync(ctx->dense_mask.p, mask, dense, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, s));
-  }
   CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
+  cudaEvent_t ready = nullptr;
+  if (dense) {
+    // the mask (1 B/point) goes first on the solver's stream; the observations (16 B/point) follow on the copy stream while the views
+    // are counted and scanned, and the scatter waits for them
+    CK(cudaMemcpyAsync(ctx->dense_mask.p, valid, dense, cudaMemcpyHostToDevice, s));
+    if (view_valid) CK(cudaMemcpyAsync(ctx->view_valid.p, view_valid, (size_t)nv, cudaMemcpyHostToDevice, s));
+    if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->copy_go, cudaEventDisableTiming)); }
+    CK(cudaEventRecord(ctx->copy_go, s));                          // work queued on `s` before this call may still read dense_pts
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_go, 0));
+    CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    ready = ctx->copy_done;
+  }
   CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
   ctx->table = false; ctx->table_selected = -1; ctx->errors_current = false;
-  return pack_dense(ctx, desc, ctx->dense_mask.p, false, n_corners);
+  return pack_dense(ctx, desc, ctx->dense_mask.p, false, n_corners, view_valid ? ctx->view_valid.p : nullptr, ready);
+}
+
+int mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* mask, const double* points,
+                      const double* board_points, int64_t* n_corners) {
+  return mcba_upload_dense_views(ctx, desc, mask, nullptr, points, board_points, n_corners);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -91,19 +91,27 @@ class Engine:
     self.kint = 5 + nat.DIST_SIZES[model]
     self.N = idx.shape[0]
 
-  def upload_dense(self, model, optimize_bits, mask, points, board_points):
+  def upload_dense(self, model, optimize_bits, mask, points, board_points, view_valid=None):
     """Dense [C,F,B,P] mask + [C,F,B,P,2] observations as the reference holds them (point_table, inliers);
-    the packing into frame-major corner arrays happens on the device (csrc/pack_kernels.cuh)."""
+    the packing into frame-major corner arrays happens on the device (csrc/pack_kernels.cuh).  With `view_valid` ([C,F,B]) the
+    selection is mask & view_valid[..., None], the conjunction taken on the device (calibration.py:73-81 without the host pass)."""
     mask = np.ascontiguousarray(mask)
     Cn, F, B, P = mask.shape
-    m8 = mask.view(np.uint8) if mask.dtype == np.bool_ else np.ascontiguousarray(mask, dtype=np.uint8)
+    u8 = lambda a: a.view(np.uint8) if a.dtype == np.bool_ else np.ascontiguousarray(a, dtype=np.uint8)
+    m8 = u8(mask)
     pts = nat.f64(points)
     assert pts.shape == (Cn, F, B, P, 2), f"points {pts.shape} do not match mask {mask.shape}"
     bp = nat.f64(board_points).reshape(B, P, 3)
     d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], int(optimize_bits), 0)
     n = C.c_int64()
-    self._ck(self.lib.mcba_upload_dense(self.h, C.byref(d), m8.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts),
-                                        nat.dptr(bp), C.byref(n)))
+    if view_valid is None:
+      self._ck(self.lib.mcba_upload_dense(self.h, C.byref(d), m8.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts),
+                                          nat.dptr(bp), C.byref(n)))
+    else:
+      v8 = u8(np.ascontiguousarray(view_valid))
+      assert v8.shape == (Cn, F, B), f"view_valid {v8.shape} does not match mask {mask.shape}"
+      self._ck(self.lib.mcba_upload_dense_views(self.h, C.byref(d), m8.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                v8.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts), nat.dptr(bp), C.byref(n)))
     d.N = n.value
     self.desc = d
     self.model = model

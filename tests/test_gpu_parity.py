@@ -293,6 +293,12 @@ def test_device_packing_equals_host_packing(name):
   assert np.array_equal(eng.residuals(z["x1"]), r_dense)
   H, g, _ = eng.linearize(z["x1"])
   assert np.allclose(H, H_dense, rtol=1e-12, atol=0) and np.allclose(g, g_dense, rtol=1e-10, atol=1e-9)
+  # the two-part mask (detections as they are + pose validity per view, conjunction on the device: what bundle_adjust uploads)
+  fresh = from_scene(scene).enable(cameras=True)
+  assert "valid" not in fresh.__dict__
+  eng = fresh._upload_inliers()
+  assert "valid" not in fresh.__dict__ and eng.N == idx.shape[0]
+  assert np.array_equal(eng.residuals(z["x1"]), r_dense)
 
 
 def test_empty_and_ragged_inputs():
