@@ -229,19 +229,27 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
   }
   __syncwarp();
   const double* Wf = a.W + (size_t)f * n_s * FB;
-  double* Yf = a.Y + (size_t)f * n_s * FB;
+  double* Yf = a.Y + (size_t)f * SYRK_TILE * FB;        // tile-major: row s of frame f at y_offset(F, FB, f, s)
+  const size_t ytile = (size_t)a.F * SYRK_TILE * FB;
+#pragma unroll 2
   for (int s = lane; s < n_s; s += 32) {
     const double ds = a.d[s];
-    double y[FB];
+    double y[FB], wr[FB];
+    {
+      const double2* w2 = reinterpret_cast<const double2*>(Wf + (size_t)s * FB);
+#pragma unroll
+      for (int i = 0; i < FB / 2; i++) { const double2 w = w2[i]; wr[2 * i] = w.x; wr[2 * i + 1] = w.y; }
+    }
 #pragma unroll
     for (int i = 0; i < FB; i++) {
-      double t = ds * Wf[s * FB + i] * df[i];
+      double t = ds * wr[i] * df[i];
 #pragma unroll
       for (int k = 0; k < FB; k++) if (k < i) t -= L[i * FB + k] * y[k];
       y[i] = t * L[i * FB + i];
     }
+    double2* y2 = reinterpret_cast<double2*>(Yf + (size_t)(s >> 5) * ytile + (size_t)(s & 31) * FB);
 #pragma unroll
-    for (int i = 0; i < FB; i++) Yf[s * FB + i] = y[i];
+    for (int i = 0; i < FB / 2; i++) y2[i] = make_double2(y[2 * i], y[2 * i + 1]);
   }
   __syncwarp();
 }
@@ -254,24 +262,24 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
 // fragment loads feed 2 DMMAs = 512 FMAs (the first version, 2x2 outputs per thread with DFMA, needed one shared-memory load per FMA).
 constexpr int SYRK_K = 48;
 constexpr int SYRK_STAGES = 4;
+constexpr int SYRK_OWN = 4;                          // tiles whose C fragments a CTA keeps in registers while it walks the frame slabs
+constexpr size_t SYRK_SLAB_BYTES = 12u << 20;        // of Y per slab: resident in L2 while the whole grid works on it
 template <int FB> __host__ __device__ constexpr int syrk_stage_doubles() { return 2 * SYRK_K * SYRK_TILE; }      // Yi | Yj, each [SYRK_FR][32][FB]
+// syrk_tile_acc: the products of frames [f0, f1) added to the caller's C fragments (c) and rhs partial (racc); syrk_tile_store: fragments ->
+// Spart[chunk] / rpart[chunk].  syrk_tile = one (tile, frame chunk) unit from zero.
 template <int FB>
-__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* SYRK_STAGES * 2 * 48 * 32 doubles */, unsigned long long* sbar, unsigned& phases) {
+__device__ __forceinline__ void syrk_tile_acc(const LmArgs& a, int ti, int tj, int f0, int f1, double* sh /* SYRK_STAGES * 2 * 48 * 32 doubles */, unsigned long long* sbar,
+                                              unsigned& phases, double& c00, double& c01, double& c10, double& c11, double& racc) {
   constexpr int SYRK_FR = syrk_fr(FB);
   static_assert(SYRK_FR * FB == SYRK_K && SYRK_FR <= LM_WARPS, "a step stages 48 k-columns; one warp per frame slot for the rhs");
   constexpr int FR_DOUBLES = SYRK_TILE * FB;                 // one frame's rows of a tile
   constexpr int STAGE = 2 * SYRK_K * SYRK_TILE;
-  const int n_s = a.n_s, F = a.F;
-  const int f0 = chunk * a.syrk_cf, f1 = min(F, f0 + a.syrk_cf);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, tig = lane & 3;
   const int I = warp >> 1, J0 = 2 * (warp & 1);
-  const int rows_i = min(SYRK_TILE, n_s - ti * SYRK_TILE), rows_j = min(SYRK_TILE, n_s - tj * SYRK_TILE);
   const int nsteps = (f1 - f0 + SYRK_FR - 1) / SYRK_FR;
-  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-  double racc = 0.0;
   __syncthreads();                                            // every warp has left the previous tile's stages
-  // rows beyond n_s (last row tile) and frames beyond the chunk are never copied: they must read as zero
-  if (rows_i < SYRK_TILE || rows_j < SYRK_TILE || (f1 - f0) % SYRK_FR != 0)
+  // frames beyond the chunk are never copied: they must read as zero (rows beyond n_s are zero in Y itself)
+  if ((f1 - f0) % SYRK_FR != 0)
     for (int o = tid; o < SYRK_STAGES * STAGE; o += LM_THREADS) sh[o] = 0.0;
   fence_proxy_async();                                        // (also orders the previous phase's plain stores to this buffer before the copies)
   __syncthreads();
@@ -279,11 +287,13 @@ __device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int c
     const int st = step % SYRK_STAGES;
     const int fbase = f0 + step * SYRK_FR, nf = min(SYRK_FR, f1 - fbase);
     double* Yi = sh + (size_t)st * STAGE; double* Yj = Yi + SYRK_K * SYRK_TILE;
-    mbar_expect_tx(&sbar[st], (unsigned)(nf * (rows_i + rows_j) * FB * sizeof(double)));
-    for (int ff = 0; ff < nf; ff++) {
-      bulk_g2s(Yi + ff * FR_DOUBLES, a.Y + ((size_t)(fbase + ff) * n_s + (size_t)ti * SYRK_TILE) * FB, (unsigned)(rows_i * FB * sizeof(double)), &sbar[st]);
-      bulk_g2s(Yj + ff * FR_DOUBLES, a.Y + ((size_t)(fbase + ff) * n_s + (size_t)tj * SYRK_TILE) * FB, (unsigned)(rows_j * FB * sizeof(double)), &sbar[st]);
-    }
+    // Y is tile-major ([row tile][frame][32][FB], rows beyond n_s zero): the frames of a step are ONE contiguous piece per operand.
+    // (Frame-major Y needed a copy per frame and operand, 16 per step, and the step then cost what the copy unit takes to work off 16
+    // requests -- about 1.2 us whatever their size -- not what the products cost: 1.3 ms of SYRK at n_s = 1030.)
+    const unsigned bytes = (unsigned)(nf * FR_DOUBLES * sizeof(double));
+    mbar_expect_tx(&sbar[st], 2 * bytes);
+    bulk_g2s(Yi, a.Y + ((size_t)ti * a.F + fbase) * FR_DOUBLES, bytes, &sbar[st]);
+    bulk_g2s(Yj, a.Y + ((size_t)tj * a.F + fbase) * FR_DOUBLES, bytes, &sbar[st]);
   };
   if (tid == 0) for (int s0 = 0; s0 < SYRK_STAGES - 1 && s0 < nsteps; s0++) issue(s0);
   for (int step = 0; step < nsteps; step++) {
@@ -312,6 +322,12 @@ __device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int c
     }
     __syncthreads();                                          // the stage may be refilled
   }
+}
+template <int FB>
+__device__ __forceinline__ void syrk_tile_store(const LmArgs& a, int ti, int tj, int chunk, double* sh, double c00, double c01, double c10, double c11, double racc) {
+  const int n_s = a.n_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, tig = lane & 3;
+  const int I = warp >> 1, J0 = 2 * (warp & 1);
   double* Sp = a.Spart + (size_t)chunk * n_s * n_s;
   if (ti == tj) {                                             // the frame slots' partial sums, added in slot order
     __syncthreads();
@@ -335,6 +351,13 @@ __device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int c
       if (j1 + 1 < n_s) Sp[(size_t)i * n_s + j1 + 1] = c11;
     }
   }
+}
+template <int FB>
+__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh, unsigned long long* sbar, unsigned& phases) {
+  const int f0 = chunk * a.syrk_cf, f1 = min(a.F, f0 + a.syrk_cf);
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, racc = 0.0;
+  syrk_tile_acc<FB>(a, ti, tj, f0, f1, sh, sbar, phases, c00, c01, c10, c11, racc);
+  syrk_tile_store<FB>(a, ti, tj, chunk, sh, c00, c01, c10, c11, racc);
 }
 
 // reduced solve, n_s <= CHOL_SMALL_MAX: one CTA, matrix cyclically distributed in registers (the round-1 k_chol_small scheme)
@@ -832,52 +855,106 @@ __device__ __forceinline__ void chol_fused_tile(int n, int p, int ti, int tj, do
   }
 }
 
-// both substitutions by one CTA with the factor in global memory (lower = L, strict upper = L^T mirror) and the inverted diagonal blocks
-__device__ __forceinline__ void chol_substitute_body(int n, const double* L, const double* Linv_all, const double* rhs, const double* gh, double* out, double* bsh) {
-  double* yb = bsh + ((n + CHOL_NB - 1) / CHOL_NB) * CHOL_NB;
+constexpr int SUBST_HALF = 16, SUBST_UN = 8;
+// Both substitutions by one CTA with the factor in global memory (lower = working matrix, strict upper = L^T collected by the tiles) and
+// the inverted diagonal blocks.  What a block needs from the factor does not depend on the solution, so nothing of it may sit on the
+// critical path behind an L2 round trip more than once: the inverted diagonal block of the NEXT block is fetched while this one is worked
+// on (shared memory, double buffered), and the block's panel of L^T -- rows 32 j .. 32 j + 31, each contiguous -- is read with all the
+// loads of a thread in flight at once: forward in axpy form (thread = column i: b_i -= sum_k L^T[k][i] y_k, 32 loads per column, the
+// next block's rows first), backward over the SAME panels in dot form (thread = (rows k, k + 16; column slice): 16 loads in flight, the 16
+// slices of a row reduced by shuffles).  Fixed order everywhere.  History (profiles/r02_k_lm_phases_*): two dependent L2 round trips
+// per block and direction, 8-deep load batches: 70 us at n_s = 286, 540 us at n_s = 1030; the panels through a 4-stage ring of bulk
+// asynchronous copies (16 requests of 2 KB per stage): 41 / 298 us -- a stage cost what the copy unit takes for 16 requests, ~1 us.
+__host__ __device__ inline size_t subst_smem_doubles(int n) {
+  return (size_t)((n + CHOL_NB - 1) / CHOL_NB) * CHOL_NB + 2 * CHOL_NB * (CHOL_NB + 1) + 64;
+}
+__device__ __noinline__ void chol_substitute_body(int n, const double* L, const double* Linv_all, const double* rhs, const double* gh, double* out, double* sh) {
+  constexpr int LVS = CHOL_NB + 1;
   const int tid = threadIdx.x;
-  const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
+  const int nblk = (n + CHOL_NB - 1) / CHOL_NB, npad = nblk * CHOL_NB;
+  double* bsh = sh;                                   // [npad]  b -> y -> x
+  double* Lv = bsh + npad;                            // [2][32][33]  inverted diagonal blocks, double buffered
+  double* tv = Lv + 2 * CHOL_NB * LVS;                // [64]  y of the block in progress | reduced dots
   __syncthreads();
-  for (int i = tid; i < nblk * CHOL_NB; i += LM_THREADS) bsh[i] = i < n ? __ldcg(&rhs[i]) + gh[i] : 0.0;
-  __syncthreads();
-  for (int blk = 0; blk < nblk; blk++) {
-    const int kb = blk * CHOL_NB;
+  for (int i = tid; i < npad; i += LM_THREADS) bsh[i] = i < n ? __ldcg(&rhs[i]) + gh[i] : 0.0;
+  auto load_linv = [&](int blk, double (&r)[4]) {
     const double* Li = Linv_all + (size_t)blk * CHOL_NB * CHOL_NB;
+#pragma unroll
+    for (int q = 0; q < 4; q++) r[q] = __ldcg(&Li[tid + LM_THREADS * q]);
+  };
+  auto store_linv = [&](int blk, const double (&r)[4]) {
+    double* dst = Lv + (size_t)(blk & 1) * CHOL_NB * LVS;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { const int o = tid + LM_THREADS * q; dst[(o >> 5) * LVS + (o & 31)] = r[q]; }
+  };
+  double lr[4];
+  load_linv(0, lr); store_linv(0, lr);
+  __syncthreads();
+  // ---- forward: L y = b
+  for (int blk = 0; blk < nblk; blk++) {
+    const int kb = CHOL_NB * blk;
+    const bool has_next = blk + 1 < nblk;
+    if (has_next) load_linv(blk + 1, lr);             // in flight while this block is worked on
+    const double* Lb = Lv + (size_t)(blk & 1) * CHOL_NB * LVS;
     if (tid < CHOL_NB) {
-      double acc = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < CHOL_NB; k++) acc += __ldcg(&Li[tid * CHOL_NB + k]) * bsh[kb + k];
-      yb[tid] = acc;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < CHOL_NB; k += 4) {
+        a0 += Lb[tid * LVS + k] * bsh[kb + k]; a1 += Lb[tid * LVS + k + 1] * bsh[kb + k + 1];
+        a2 += Lb[tid * LVS + k + 2] * bsh[kb + k + 2]; a3 += Lb[tid * LVS + k + 3] * bsh[kb + k + 3];
+      }
+      tv[tid] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
-    if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
-    const int nbf = min(CHOL_NB, n - kb);
+    if (tid < CHOL_NB) bsh[kb + tid] = tv[tid];
     for (int i = kb + CHOL_NB + tid; i < n; i += LM_THREADS) {
-      double acc = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < nbf; k++) acc += __ldcg(&L[(size_t)(kb + k) * n + i]) * yb[k];       // L[i][kb+k] from the transposed factor (coalesced over i)
-      bsh[i] -= acc;
+      const double* col = L + (size_t)kb * n + i;     // L^T[kb + k][i], k = 0..31: coalesced over i
+      double l[CHOL_NB];
+#pragma unroll
+      for (int k = 0; k < CHOL_NB; k++) l[k] = __ldcg(col + (size_t)k * n);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < CHOL_NB; k += 4) { a0 += l[k] * tv[k]; a1 += l[k + 1] * tv[k + 1]; a2 += l[k + 2] * tv[k + 2]; a3 += l[k + 3] * tv[k + 3]; }
+      bsh[i] -= (a0 + a1) + (a2 + a3);
     }
+    if (has_next) store_linv(blk + 1, lr);
     __syncthreads();
   }
+  // ---- backward: L^T x = y.  The last block's inverse is still in its buffer.
+  const int kk = tid >> 4, sl = tid & 15;
   for (int blk = nblk - 1; blk >= 0; blk--) {
-    const int kb = blk * CHOL_NB;
-    const double* Li = Linv_all + (size_t)blk * CHOL_NB * CHOL_NB;
-    if (tid < CHOL_NB) {
-      double acc = 0.0;
-#pragma unroll 8
-      for (int k = 0; k < CHOL_NB; k++) acc += __ldcg(&Li[k * CHOL_NB + tid]) * bsh[kb + k];
-      yb[tid] = acc;
+    const int kb = CHOL_NB * blk;
+    const bool has_next = blk > 0;
+    if (has_next) load_linv(blk - 1, lr);
+    const double* Lb = Lv + (size_t)(blk & 1) * CHOL_NB * LVS;
+    // t_k = sum_{i >= kb + 32} L^T[kb + k][i] x_i: thread (kk, sl) -> rows kk, kk + 16, columns == sl (mod 16)
+    double p0 = 0.0, p1 = 0.0;
+    {
+      const double* r0 = L + (size_t)(kb + kk) * n, *r1 = r0 + (size_t)SUBST_HALF * n;
+      for (int i0 = kb + CHOL_NB + sl; i0 < n; i0 += 16 * SUBST_UN) {
+        double l0[SUBST_UN], l1[SUBST_UN];
+#pragma unroll
+        for (int u = 0; u < SUBST_UN; u++) { const int i = i0 + 16 * u; const bool on = i < n; l0[u] = on ? __ldcg(r0 + i) : 0.0; l1[u] = on ? __ldcg(r1 + i) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < SUBST_UN; u++) { const int i = i0 + 16 * u; const double xv = i < n ? bsh[i] : 0.0; p0 += l0[u] * xv; p1 += l1[u] * xv; }
+      }
     }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+    if (sl == 0) { tv[kk] = p0; tv[SUBST_HALF + kk] = p1; }
     __syncthreads();
-    if (tid < CHOL_NB) bsh[kb + tid] = yb[tid];
-    const int nbv = min(CHOL_NB, n - kb);
-    for (int i = tid; i < kb; i += LM_THREADS) {
-      const double* row = L + (size_t)i * n + kb;
-      double acc = 0.0;
-      for (int k = 0; k < nbv; k++) acc += __ldcg(&row[k]) * yb[k];
-      bsh[i] -= acc;
+    if (tid < CHOL_NB) tv[32 + tid] = bsh[kb + tid] - tv[tid];
+    __syncthreads();
+    if (tid < CHOL_NB) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < CHOL_NB; k += 4) {
+        a0 += Lb[k * LVS + tid] * tv[32 + k]; a1 += Lb[(k + 1) * LVS + tid] * tv[32 + k + 1];
+        a2 += Lb[(k + 2) * LVS + tid] * tv[32 + k + 2]; a3 += Lb[(k + 3) * LVS + tid] * tv[32 + k + 3];
+      }
+      bsh[kb + tid] = (a0 + a1) + (a2 + a3);
     }
+    if (has_next) store_linv(blk - 1, lr);
     __syncthreads();
   }
   for (int i = tid; i < n; i += LM_THREADS) out[i] = bsh[i];
@@ -887,7 +964,7 @@ __device__ __forceinline__ void chol_substitute_body(int n, const double* L, con
 // shared memory of k_lm in doubles
 __host__ __device__ inline size_t lm_smem_doubles(int n_s, int fb) {
   const size_t small = n_s <= CHOL_SMALL_MAX ? (size_t)n_s * (n_s | 1) + 2 * (size_t)n_s + 32 : 0;
-  const size_t big = n_s > CHOL_SMALL_MAX ? (size_t)((n_s + CHOL_NB - 1) / CHOL_NB + 1) * CHOL_NB : 0;
+  const size_t big = n_s > CHOL_SMALL_MAX ? subst_smem_doubles(n_s) : 0;
   const size_t syrk = (size_t)SYRK_STAGES * 2 * SYRK_K * SYRK_TILE;
   const size_t chol_tiles = 5 * (size_t)CHOL_NB * (CHOL_NB + 1) + 3 * CHOL_NB;
   const size_t frames = (size_t)LM_WARPS * (12 * 12 + 12);
@@ -1065,10 +1142,13 @@ k_lm(LmArgs a) {
         double tu[FB], tv[FB];
 #pragma unroll
         for (int j = 0; j < FB; j++) { tu[j] = 0.0; tv[j] = 0.0; }
+        // a lane's FB doubles of a row are 16-byte aligned (FB even): double2 loads, four rows in flight per lane
+#pragma unroll 4
         for (int s = lane; s < n_s; s += 32) {
           const double us = a.d[s] * u[s], vs = two ? a.d[s] * v[s] : 0.0;
+          const double2* w2 = reinterpret_cast<const double2*>(Wf + (size_t)s * FB);
 #pragma unroll
-          for (int j = 0; j < FB; j++) { const double w = Wf[s * FB + j]; tu[j] += w * us; tv[j] += w * vs; }
+          for (int j = 0; j < FB / 2; j++) { const double2 w = w2[j]; tu[2 * j] += w.x * us; tv[2 * j] += w.x * vs; tu[2 * j + 1] += w.y * us; tv[2 * j + 1] += w.y * vs; }
         }
 #pragma unroll
         for (int j = 0; j < FB; j++) {
@@ -1144,6 +1224,35 @@ k_lm(LmArgs a) {
     if (F > 0 && n_s > 0) {
       const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
       const int npair = tiles * (tiles + 1) / 2;
+      if (npair > nblk && a.syrk_chunks == 1) {
+        // more tiles than CTAs (n_s = 1030: 561): a CTA keeps the C fragments of SYRK_OWN of its tiles in registers and walks the frames in
+        // slabs small enough to stay in L2 (SYRK_SLAB_BYTES of Y) while every CTA of the grid works on the same slab; with one pass over
+        // all frames per tile the 99 MB of Y (n_s = 1030 x 2000 frames) come from HBM once per tile row
+        const int slab = max(SYRK_K / FB, (int)(SYRK_SLAB_BYTES / ((size_t)n_s * FB * sizeof(double))) / (SYRK_K / FB) * (SYRK_K / FB));
+        for (int v0 = blockIdx.x; v0 < npair; v0 += SYRK_OWN * nblk) {
+          double cc[SYRK_OWN][4], rr[SYRK_OWN];
+#pragma unroll
+          for (int t = 0; t < SYRK_OWN; t++) { cc[t][0] = cc[t][1] = cc[t][2] = cc[t][3] = 0.0; rr[t] = 0.0; }
+          for (int f0 = 0; f0 < F; f0 += slab) {
+#pragma unroll
+            for (int t = 0; t < SYRK_OWN; t++) {
+              int pr = v0 + t * nblk;
+              if (pr < npair) {
+                int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
+                syrk_tile_acc<FB>(a, ti, ti + pr, f0, min(F, f0 + slab), work, sbar, sphases, cc[t][0], cc[t][1], cc[t][2], cc[t][3], rr[t]);
+              }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < SYRK_OWN; t++) {
+            int pr = v0 + t * nblk;
+            if (pr < npair) {
+              int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
+              syrk_tile_store<FB>(a, ti, ti + pr, 0, work, cc[t][0], cc[t][1], cc[t][2], cc[t][3], rr[t]);
+            }
+          }
+        }
+      } else
       for (int vb = blockIdx.x; vb < npair * a.syrk_chunks; vb += nblk) {
         const int chunk = vb / npair; int pr = vb % npair;
         int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
@@ -1207,23 +1316,28 @@ k_lm(LmArgs a) {
           }
           grid_barrier(a.bar, nblk);
         }
+        LMPH(11)
         if (blockIdx.x == 0) {
           chol_substitute_body(n_s, a.S, a.Linv, a.rhs, a.gh, a.gn, work);
         }
+        LMPH(12)
       }
     }
     grid_barrier(a.bar, nblk);
     // ---------------------------------------------------------------------------------------- phase G: back-substitution + subspace forms
     LMPH(7)
     for (int f = gwarp; f < F; f += gwarps) {
-      const double* Yf = a.Y + (size_t)f * n_s * FB;
+      const double* Yf = a.Y + (size_t)f * SYRK_TILE * FB;
+      const size_t ytile = (size_t)a.F * SYRK_TILE * FB;
       double t[FB];
 #pragma unroll
       for (int k = 0; k < FB; k++) t[k] = 0.0;
+#pragma unroll 4
       for (int s = lane; s < n_s; s += 32) {
         const double ps = __ldcg(&a.gn[s]);
+        const double2* y2 = reinterpret_cast<const double2*>(Yf + (size_t)(s >> 5) * ytile + (size_t)(s & 31) * FB);
 #pragma unroll
-        for (int k = 0; k < FB; k++) t[k] += Yf[s * FB + k] * ps;
+        for (int k = 0; k < FB / 2; k++) { const double2 y = y2[k]; t[2 * k] += y.x * ps; t[2 * k + 1] += y.y * ps; }
       }
 #pragma unroll
       for (int k = 0; k < FB; k++) {

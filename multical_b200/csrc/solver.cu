@@ -477,7 +477,7 @@ int run_lm_loop(mcba_ctx* ctx, int loss, double f_scale, int log_cap) {
       unsigned long long t[16];
       CK(cudaMemcpy(t, ctx->prof.p, sizeof(t), cudaMemcpyDeviceToHost));
       fprintf(stderr, "[k_lm phases, us since phase A]");
-      for (int q = 2; q <= 10; q++) fprintf(stderr, " %d:%.1f", q, t[q] >= t[1] && t[1] ? (t[q] - t[1]) * 1e-3 : -1.0);
+      for (int q = 2; q <= 12; q++) fprintf(stderr, " %d:%.1f", q, t[q] >= t[1] && t[1] ? (t[q] - t[1]) * 1e-3 : -1.0);      // 11, 12: blocked Cholesky done, substitutions done
       fprintf(stderr, "\n");
       CK(cudaMemset(ctx->prof.p, 0, sizeof(t)));
     }
@@ -580,7 +580,10 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   CK(cudaMemsetAsync(ctx->g.p, 0, sizeof(double) * (size_t)std::max(P.n, 1), ctx->stream));
   CK(ctx->Hff.alloc((size_t)std::max(F, 1) * fbs * fbs));
   CK(ctx->W.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * fbs));
-  CK(ctx->Y.alloc((size_t)std::max(F, 1) * std::max(P.n_s, 1) * fbs));
+  {   // Y tile-major [row tile][frame][32][fb], rows beyond n_s stay zero (lm_kernel.cuh syrk_tile_acc)
+    const size_t ny = (size_t)((std::max(P.n_s, 1) + SYRK_TILE - 1) / SYRK_TILE) * std::max(F, 1) * SYRK_TILE * fbs;
+    CK(ctx->Y.alloc(ny)); CK(cudaMemsetAsync(ctx->Y.p, 0, sizeof(double) * ny, ctx->stream));
+  }
   CK(ctx->Lf.alloc((size_t)std::max(F, 1) * fbs * fbs)); CK(ctx->zf.alloc((size_t)std::max(F, 1) * fbs));
   CK(ctx->cost_part.alloc((size_t)C * ctx->shared_chunks)); CK(ctx->view_cost.alloc((size_t)std::max(V, 1)));
   CK(ctx->diag_s.alloc((size_t)std::max(P.n_s, 1)));
