@@ -255,45 +255,45 @@ __device__ __forceinline__ void schur_frame(const LmArgs& a, int f, double reg, 
 }
 
 // one 32x32 tile (ti <= tj) of sum_f Y_f Y_f^T over a frame chunk -> Spart[chunk], diagonal tiles also sum_f Y_f z_f -> rpart[chunk].
-// Operands: the 32 rows of a tile are CONTIGUOUS in Y per frame (32 x FB doubles = 1.5 KB), so a step (48 k-columns: 8 frames x 6, or
-// 4 x 12) is 2 x SYRK_FR bulk asynchronous copies (cp.async.bulk + mbarrier) straight into shared memory; SYRK_STAGES steps are in flight
-// per CTA (the register-prefetched version had one: 2.2 us per step = one HBM/L2 round trip, 94 us at n_s = 286 x 1000 frames).
-// Product on the fp64 tensor path: warp w owns the 8x8 output tiles (row tile w/2, column tiles 2 (w&1), 2 (w&1) + 1); per k-step 3
-// fragment loads feed 2 DMMAs = 512 FMAs (the first version, 2x2 outputs per thread with DFMA, needed one shared-memory load per FMA).
+// Operands: Y is tile-major ([row tile][frame][32][FB], rows beyond n_s zero), so the frames of a step (48 k-columns: 8 frames x 6, or
+// 4 x 12) are ONE contiguous piece per operand: a step is two bulk asynchronous copies (cp.async.bulk + mbarrier) of 12 KB straight into
+// shared memory, SYRK_STAGES steps in flight per CTA.  (Frame-major Y needed a copy per frame and operand, 16 per step, and a step then
+// cost what the copy unit takes to work off 16 requests -- about 1.2 us whatever their size: 1.3 ms of SYRK at n_s = 1030 x 2000 frames;
+// before that, register-prefetched operands: one HBM/L2 round trip per step.)
+// Product on the fp64 tensor path, bound by the fragment loads from shared memory, not by the DMMAs: warp w owns the 16 x 16 block
+// (w & 3) of the tile and every second k-step (w >> 2) -- 4 fragment loads feed 4 DMMAs (8 x 16 blocks over all k-steps: 3 loads per 2)
+// -- and the rows a lane group reads are permuted (group g -> row 2 (g & 3) + (g >> 2)) so that with 6 doubles per row the 16 lanes of a
+// half-warp hit 16 different 8-byte banks (rows 0..3 of a plain fragment collide two ways).  The two k-halves are added in a fixed order.
 constexpr int SYRK_K = 48;
 constexpr int SYRK_STAGES = 4;
-constexpr int SYRK_OWN = 4;                          // tiles whose C fragments a CTA keeps in registers while it walks the frame slabs
-constexpr size_t SYRK_SLAB_BYTES = 12u << 20;        // of Y per slab: resident in L2 while the whole grid works on it
 template <int FB> __host__ __device__ constexpr int syrk_stage_doubles() { return 2 * SYRK_K * SYRK_TILE; }      // Yi | Yj, each [SYRK_FR][32][FB]
-// syrk_tile_acc: the products of frames [f0, f1) added to the caller's C fragments (c) and rhs partial (racc); syrk_tile_store: fragments ->
-// Spart[chunk] / rpart[chunk].  syrk_tile = one (tile, frame chunk) unit from zero.
 template <int FB>
-__device__ __forceinline__ void syrk_tile_acc(const LmArgs& a, int ti, int tj, int f0, int f1, double* sh /* SYRK_STAGES * 2 * 48 * 32 doubles */, unsigned long long* sbar,
-                                              unsigned& phases, double& c00, double& c01, double& c10, double& c11, double& racc) {
+__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh /* SYRK_STAGES * 2 * 48 * 32 doubles */, unsigned long long* sbar, unsigned& phases) {
   constexpr int SYRK_FR = syrk_fr(FB);
   static_assert(SYRK_FR * FB == SYRK_K && SYRK_FR <= LM_WARPS, "a step stages 48 k-columns; one warp per frame slot for the rhs");
   constexpr int FR_DOUBLES = SYRK_TILE * FB;                 // one frame's rows of a tile
   constexpr int STAGE = 2 * SYRK_K * SYRK_TILE;
+  const int n_s = a.n_s, F = a.F;
+  const int f0 = chunk * a.syrk_cf, f1 = min(F, f0 + a.syrk_cf);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, tig = lane & 3;
-  const int I = warp >> 1, J0 = 2 * (warp & 1);
+  const int qd = warp & 3, I2 = qd >> 1, J2 = qd & 1, kh = warp >> 2;
+  const int pg = 2 * (grp & 3) + (grp >> 2);                 // row of the 8-row fragment this lane group reads
   const int nsteps = (f1 - f0 + SYRK_FR - 1) / SYRK_FR;
+  double c[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) c[q] = 0.0;
+  double racc = 0.0;
   __syncthreads();                                            // every warp has left the previous tile's stages
-  // frames beyond the chunk are never copied: they must read as zero (rows beyond n_s are zero in Y itself)
-  if ((f1 - f0) % SYRK_FR != 0)
-    for (int o = tid; o < SYRK_STAGES * STAGE; o += LM_THREADS) sh[o] = 0.0;
   fence_proxy_async();                                        // (also orders the previous phase's plain stores to this buffer before the copies)
   __syncthreads();
   auto issue = [&](int step) {                                // thread 0: the copies of one step into stage step % SYRK_STAGES
     const int st = step % SYRK_STAGES;
     const int fbase = f0 + step * SYRK_FR, nf = min(SYRK_FR, f1 - fbase);
     double* Yi = sh + (size_t)st * STAGE; double* Yj = Yi + SYRK_K * SYRK_TILE;
-    // Y is tile-major ([row tile][frame][32][FB], rows beyond n_s zero): the frames of a step are ONE contiguous piece per operand.
-    // (Frame-major Y needed a copy per frame and operand, 16 per step, and the step then cost what the copy unit takes to work off 16
-    // requests -- about 1.2 us whatever their size -- not what the products cost: 1.3 ms of SYRK at n_s = 1030.)
     const unsigned bytes = (unsigned)(nf * FR_DOUBLES * sizeof(double));
     mbar_expect_tx(&sbar[st], 2 * bytes);
-    bulk_g2s(Yi, a.Y + ((size_t)ti * a.F + fbase) * FR_DOUBLES, bytes, &sbar[st]);
-    bulk_g2s(Yj, a.Y + ((size_t)tj * a.F + fbase) * FR_DOUBLES, bytes, &sbar[st]);
+    bulk_g2s(Yi, a.Y + ((size_t)ti * F + fbase) * FR_DOUBLES, bytes, &sbar[st]);
+    bulk_g2s(Yj, a.Y + ((size_t)tj * F + fbase) * FR_DOUBLES, bytes, &sbar[st]);
   };
   if (tid == 0) for (int s0 = 0; s0 < SYRK_STAGES - 1 && s0 < nsteps; s0++) issue(s0);
   for (int step = 0; step < nsteps; step++) {
@@ -304,13 +304,18 @@ __device__ __forceinline__ void syrk_tile_acc(const LmArgs& a, int ti, int tj, i
     const double* Yi = sh + (size_t)st * STAGE; const double* Yj = Yi + SYRK_K * SYRK_TILE;
     const int fbase = f0 + step * SYRK_FR, nf = min(SYRK_FR, f1 - fbase);
 #pragma unroll
-    for (int ks = 0; ks < SYRK_K / 4; ks++) {
+    for (int ks2 = 0; ks2 < SYRK_K / 8; ks2++) {
+      const int ks = 2 * ks2 + kh;
       const int kidx = 4 * ks + tig, ff = kidx / FB, k = kidx % FB;          // k-column -> (frame of the step, component)
-      const double fa = Yi[ff * FR_DOUBLES + (8 * I + grp) * FB + k];
-      const double fb0 = Yj[ff * FR_DOUBLES + (8 * J0 + grp) * FB + k];
-      const double fb1 = Yj[ff * FR_DOUBLES + (8 * (J0 + 1) + grp) * FB + k];
-      dmma884(c00, c01, fa, fb0);
-      dmma884(c10, c11, fa, fb1);
+      const double* yi = Yi + ff * FR_DOUBLES + (16 * I2 + pg) * FB + k;
+      const double* yj = Yj + ff * FR_DOUBLES + (16 * J2 + pg) * FB + k;
+      // a chunk's last step may hold fewer frames than a stage: what lies behind them is a previous step's data, not zeros
+      const bool on = ff < nf;
+      const double fa0 = on ? yi[0] : 0.0, fa1 = on ? yi[8 * FB] : 0.0, fb0 = on ? yj[0] : 0.0, fb1 = on ? yj[8 * FB] : 0.0;
+      dmma884(c[0], c[1], fa0, fb0);
+      dmma884(c[2], c[3], fa0, fb1);
+      dmma884(c[4], c[5], fa1, fb0);
+      dmma884(c[6], c[7], fa1, fb1);
     }
     if (ti == tj) {                                           // rhs: thread (row = tid % 32, frame slot = tid / 32 (+ 8 for 4-frame steps: none))
       const int r = tid & 31, ff = tid >> 5;
@@ -322,15 +327,8 @@ __device__ __forceinline__ void syrk_tile_acc(const LmArgs& a, int ti, int tj, i
     }
     __syncthreads();                                          // the stage may be refilled
   }
-}
-template <int FB>
-__device__ __forceinline__ void syrk_tile_store(const LmArgs& a, int ti, int tj, int chunk, double* sh, double c00, double c01, double c10, double c11, double racc) {
-  const int n_s = a.n_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, tig = lane & 3;
-  const int I = warp >> 1, J0 = 2 * (warp & 1);
   double* Sp = a.Spart + (size_t)chunk * n_s * n_s;
   if (ti == tj) {                                             // the frame slots' partial sums, added in slot order
-    __syncthreads();
     sh[tid] = racc;
     __syncthreads();
     if (tid < SYRK_TILE) {
@@ -340,24 +338,30 @@ __device__ __forceinline__ void syrk_tile_store(const LmArgs& a, int ti, int tj,
       const int i = ti * SYRK_TILE + tid;
       if (i < n_s) a.rpart[(size_t)chunk * n_s + i] = r8;
     }
+    __syncthreads();
   }
-  {
-    const int i = ti * SYRK_TILE + 8 * I + grp;
-    const int j0 = tj * SYRK_TILE + 8 * J0 + 2 * tig, j1 = j0 + 8;
-    if (i < n_s) {
-      if (j0 < n_s) Sp[(size_t)i * n_s + j0] = c00;
-      if (j0 + 1 < n_s) Sp[(size_t)i * n_s + j0 + 1] = c01;
-      if (j1 < n_s) Sp[(size_t)i * n_s + j1] = c10;
-      if (j1 + 1 < n_s) Sp[(size_t)i * n_s + j1 + 1] = c11;
-    }
+  // the second k-half's fragments go through shared memory to the warp that owns the same block and are added there
+  if (kh == 1) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) sh[(qd * 8 + q) * 32 + lane] = c[q];
   }
-}
-template <int FB>
-__device__ __forceinline__ void syrk_tile(const LmArgs& a, int ti, int tj, int chunk, double* sh, unsigned long long* sbar, unsigned& phases) {
-  const int f0 = chunk * a.syrk_cf, f1 = min(a.F, f0 + a.syrk_cf);
-  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0, racc = 0.0;
-  syrk_tile_acc<FB>(a, ti, tj, f0, f1, sh, sbar, phases, c00, c01, c10, c11, racc);
-  syrk_tile_store<FB>(a, ti, tj, chunk, sh, c00, c01, c10, c11, racc);
+  __syncthreads();
+  if (kh == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) c[q] += sh[(qd * 8 + q) * 32 + lane];
+    const int p0 = 2 * ((2 * tig) & 3) + ((2 * tig) >> 2), p1 = 2 * ((2 * tig + 1) & 3) + ((2 * tig + 1) >> 2);      // columns of the C fragment's two entries
+#pragma unroll
+    for (int ra = 0; ra < 2; ra++)
+#pragma unroll
+      for (int cb = 0; cb < 2; cb++) {
+        const int i = ti * SYRK_TILE + 16 * I2 + 8 * ra + pg;
+        const int jb = tj * SYRK_TILE + 16 * J2 + 8 * cb;
+        if (i < n_s) {
+          if (jb + p0 < n_s) Sp[(size_t)i * n_s + jb + p0] = c[(2 * ra + cb) * 2];
+          if (jb + p1 < n_s) Sp[(size_t)i * n_s + jb + p1] = c[(2 * ra + cb) * 2 + 1];
+        }
+      }
+  }
 }
 
 // reduced solve, n_s <= CHOL_SMALL_MAX: one CTA, matrix cyclically distributed in registers (the round-1 k_chol_small scheme)
@@ -1224,35 +1228,6 @@ k_lm(LmArgs a) {
     if (F > 0 && n_s > 0) {
       const int tiles = (n_s + SYRK_TILE - 1) / SYRK_TILE;
       const int npair = tiles * (tiles + 1) / 2;
-      if (npair > nblk && a.syrk_chunks == 1) {
-        // more tiles than CTAs (n_s = 1030: 561): a CTA keeps the C fragments of SYRK_OWN of its tiles in registers and walks the frames in
-        // slabs small enough to stay in L2 (SYRK_SLAB_BYTES of Y) while every CTA of the grid works on the same slab; with one pass over
-        // all frames per tile the 99 MB of Y (n_s = 1030 x 2000 frames) come from HBM once per tile row
-        const int slab = max(SYRK_K / FB, (int)(SYRK_SLAB_BYTES / ((size_t)n_s * FB * sizeof(double))) / (SYRK_K / FB) * (SYRK_K / FB));
-        for (int v0 = blockIdx.x; v0 < npair; v0 += SYRK_OWN * nblk) {
-          double cc[SYRK_OWN][4], rr[SYRK_OWN];
-#pragma unroll
-          for (int t = 0; t < SYRK_OWN; t++) { cc[t][0] = cc[t][1] = cc[t][2] = cc[t][3] = 0.0; rr[t] = 0.0; }
-          for (int f0 = 0; f0 < F; f0 += slab) {
-#pragma unroll
-            for (int t = 0; t < SYRK_OWN; t++) {
-              int pr = v0 + t * nblk;
-              if (pr < npair) {
-                int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
-                syrk_tile_acc<FB>(a, ti, ti + pr, f0, min(F, f0 + slab), work, sbar, sphases, cc[t][0], cc[t][1], cc[t][2], cc[t][3], rr[t]);
-              }
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < SYRK_OWN; t++) {
-            int pr = v0 + t * nblk;
-            if (pr < npair) {
-              int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }
-              syrk_tile_store<FB>(a, ti, ti + pr, 0, work, cc[t][0], cc[t][1], cc[t][2], cc[t][3], rr[t]);
-            }
-          }
-        }
-      } else
       for (int vb = blockIdx.x; vb < npair * a.syrk_chunks; vb += nblk) {
         const int chunk = vb / npair; int pr = vb % npair;
         int ti = 0; while (pr >= tiles - ti) { pr -= tiles - ti; ti++; }

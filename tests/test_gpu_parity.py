@@ -143,6 +143,22 @@ def test_many_cameras_use_the_cooperative_blocked_reduced_solve():
   assert a.cost == b.cost and np.array_equal(np.array(a.log, float), np.array(b.log, float), equal_nan=True) and a.chol_retries == 0
 
 
+def test_frame_count_that_ends_a_syrk_chunk_in_a_partial_step():
+  """The Schur SYRK stages 8 frames per step in a 4-stage ring: a chunk whose frame count is not a multiple of 8 ends in a partial step,
+  and after more than 4 steps that step lands in a stage that still holds an earlier step's frames behind its own (75 frames, 2 chunks:
+  40 + 35 -> the second chunk's 5th step holds 3 frames).  Converged cost against scipy's dense exact trust region."""
+  from multical_b200 import synthetic
+  scene = synthetic.make_scene(C=2, F=75, vis=0.2, seed=23)
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-13, xtol=1e-13, gtol=1e-13,
+                               max_nfev=200, method="trf", tr_solver="exact")
+  out = calib.bundle_adjust(tolerance=1e-13, xtol=1e-13, gtol=1e-13, max_iterations=200)
+  assert abs(out.last_solve.cost - ref.cost) <= 1e-8 * ref.cost, (out.last_solve.cost, ref.cost)
+
+
 def test_sixty_four_cameras_configs4_shape():
   """BASELINE configs[4]'s shape (64-camera dome, one board, cameras + intrinsics optimised: n_s = 6*64 + 6 + 10*64 = 1030, 33 panels of
   the cooperative factorisation, eight cameras per warp of the linearisation) at a frame count the dense oracle can hold: converged cost

@@ -58,6 +58,7 @@ test_board_points_as_parameters = gp.test_board_points_as_parameters
 test_iteration_table_matches_the_trf_model = gp.test_iteration_table_matches_the_trf_model
 test_degenerate_block_selections = gp.test_degenerate_block_selections
 test_many_cameras_use_the_cooperative_blocked_reduced_solve = gp.test_many_cameras_use_the_cooperative_blocked_reduced_solve
+test_frame_count_that_ends_a_syrk_chunk_in_a_partial_step = gp.test_frame_count_that_ends_a_syrk_chunk_in_a_partial_step
 if os.environ.get("MCBA_SIMT_FULL") == "1":      # three minutes on the interpreter (n_s = 1030): opt-in, the GPU suite always runs it
   test_sixty_four_cameras_configs4_shape = gp.test_sixty_four_cameras_configs4_shape
 test_two_identical_solves_agree_bit_for_bit = gp.test_two_identical_solves_agree_bit_for_bit
