@@ -7,7 +7,7 @@ One "step" = one full `bundle_adjust()` (calibration.py:199-212 semantics: ftol=
 synthetic scene of the BASELINE.json configuration `--workload`.  Default workload at EVERY N: cfg4 = configs[3] (16 cameras x
 1000 frames x 5 cube boards, 5.5 M corners) -- the largest configuration that fits one GPU and the one BASELINE names for 2/4/8
 GPUs; with N > 1 the SAME scene is sharded by frame (strong scaling), and rank 0 also solves it alone and asserts that the sharded
-solve ends at the same cost.  Secondary blocks in the same JSON line: cfg2 and cfg3 at N = 1, weak scaling (cfg2 per GPU) at N > 1.
+solve ends at the same cost.  Secondary blocks in the same JSON line: cfg2, cfg3 and cfg5 at N = 1, weak scaling (cfg2 per GPU) at N > 1.
 Metric (both arms, same definition):
     residuals/s = N_corners * (nfev + njev) / time      1 residual = one inlier corner (2 scalars),
     nfev/njev = cost and Jacobian evaluations as the solver reports them (scipy's res.nfev/res.njev for the reference arm; its
@@ -309,7 +309,7 @@ def run_ours(args):
   others = {}
   parity = None
   if world == 1 and args.secondary:
-    for wl in ("cfg2", "cfg3"):
+    for wl in ("cfg2", "cfg3", "cfg5"):      # cfg5 = BASELINE configs[4] (64 cameras x 2000 frames, 50.8 M corners, n_s = 1030): it fits one GPU as well
       if wl == args.workload: continue
       o, _ = measure(pin(synthetic.make_workload(wl, seed=args.seed)), max(3, args.steps // 2), args.warmup)
       o.pop("cost", None)
