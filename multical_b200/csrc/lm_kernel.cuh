@@ -545,9 +545,17 @@ __device__ __noinline__ void chol_diag_warp_body(int n, int kb, double* S, doubl
   const int nb = min(CHOL_NB, n - kb);
   const int tid = threadIdx.x;
   __syncthreads();                       // the block may just have been updated by this CTA (look-ahead tile of the previous panel)
-  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
-    const int i = o / CHOL_NB, j = o % CHOL_NB;
-    Lm[i][j] = (i < nb && j < nb) ? (j <= i ? __ldcg(&S[(size_t)(kb + i) * n + kb + j]) : 0.0) : (i == j ? 1.0 : 0.0);
+  {
+    // all of a thread's loads first, then the stores: through the generic pointers of this function the compiler has to keep a load behind
+    // the shared-memory store that precedes it, and the four L2 round trips would queue up one behind the other
+    double v[CHOL_NB * CHOL_NB / LM_THREADS];
+#pragma unroll
+    for (int q = 0; q < CHOL_NB * CHOL_NB / LM_THREADS; q++) {
+      const int o = tid + LM_THREADS * q, i = o / CHOL_NB, j = o % CHOL_NB;
+      v[q] = (i < nb && j < nb) ? (j <= i ? __ldcg(&S[(size_t)(kb + i) * n + kb + j]) : 0.0) : (i == j ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < CHOL_NB * CHOL_NB / LM_THREADS; q++) { const int o = tid + LM_THREADS * q; Lm[o / CHOL_NB][o % CHOL_NB] = v[q]; }
   }
   __syncthreads();
   if (tid < 32) {
@@ -803,50 +811,81 @@ __device__ __forceinline__ void chol_v3_body(int n, const double* Sg, const doub
 }
 
 // One 32x32 tile (ti >= tj) of the trailing update of panel p, with the panel solve folded in: X_i = A[rows_i, panel] L_pp^-T (a product
-// with the inverted diagonal block), X_j likewise, A[rows_i, cols_j] -= X_i X_j^T.  The tiles of block column 0 also store X_i as the
-// finished factor -- TRANSPOSED, into the strict upper triangle (row kbp + k, column i): the lower triangle stays the working matrix that
-// every other tile of this update still reads, the upper triangle collects L^T for the substitutions.  sh: 5 x 32 x 33 doubles.
+// with the inverted diagonal block -- lower triangular: output column c needs k <= c only), X_j likewise (the same thing on a diagonal
+// tile), A[rows_i, cols_j] -= X_i X_j^T.  The tiles of block column 0 also store X_i as the finished factor -- TRANSPOSED, into the strict
+// upper triangle (row kbp + k, column i): the lower triangle stays the working matrix that every other tile of this update still reads,
+// the upper triangle collects L^T for the substitutions.  Every group of global loads is issued as a whole before anything is stored (the
+// pointers are generic: a load cannot pass the store in front of it, and the L2 round trips would add up).  sh: 5 x 32 x 33 doubles.
 __device__ __forceinline__ void chol_fused_tile(int n, int p, int ti, int tj, double* S, const double* Linv_all, double* sh) {
-  double (*Li)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh);
-  double (*Ai)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 1 * CHOL_NB * (CHOL_NB + 1));
-  double (*Aj)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 2 * CHOL_NB * (CHOL_NB + 1));
-  double (*Xi)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 3 * CHOL_NB * (CHOL_NB + 1));
-  double (*Xj)[CHOL_NB + 1] = reinterpret_cast<double (*)[CHOL_NB + 1]>(sh + 4 * CHOL_NB * (CHOL_NB + 1));
+  constexpr int LD = CHOL_NB + 1, PER = CHOL_NB * CHOL_NB / LM_THREADS;
+  double* Li = sh;
+  double* Ai = sh + 1 * CHOL_NB * LD;
+  double* Aj = sh + 2 * CHOL_NB * LD;
+  double* Xi = sh + 3 * CHOL_NB * LD;
+  double* Xj = sh + 4 * CHOL_NB * LD;
+  const bool same = ti == tj;
   const int kbp = CHOL_NB * p, base = kbp + CHOL_NB;
   const int i0 = base + CHOL_NB * ti, j0 = base + CHOL_NB * tj;
   const double* Lg = Linv_all + (size_t)p * CHOL_NB * CHOL_NB;
   const int tid = threadIdx.x;
   __syncthreads();
-  for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {
-    const int r = o / CHOL_NB, c = o % CHOL_NB;
-    Li[r][c] = __ldcg(&Lg[o]);
-    Ai[r][c] = (i0 + r < n) ? __ldcg(&S[(size_t)(i0 + r) * n + kbp + c]) : 0.0;
-    Aj[r][c] = (j0 + r < n) ? __ldcg(&S[(size_t)(j0 + r) * n + kbp + c]) : 0.0;
+  {
+    double vl[PER], va[PER], vb[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int o = tid + LM_THREADS * q, r = o / CHOL_NB, c = o % CHOL_NB;
+      vl[q] = __ldcg(&Lg[o]);
+      va[q] = (i0 + r < n) ? __ldcg(&S[(size_t)(i0 + r) * n + kbp + c]) : 0.0;
+      vb[q] = (!same && j0 + r < n) ? __ldcg(&S[(size_t)(j0 + r) * n + kbp + c]) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int o = tid + LM_THREADS * q, r = o / CHOL_NB, c = o % CHOL_NB;
+      Li[r * LD + c] = vl[q]; Ai[r * LD + c] = va[q];
+      if (!same) Aj[r * LD + c] = vb[q];
+    }
   }
   __syncthreads();
   {
+    // thread (r, cg) -> X[r][cg + 8 q], q = 0..3: interleaved columns (8 different shared-memory banks per row of the inverse) and balanced
+    // triangular k loops: the k in [8 s, 8 s + 8) only reach the columns with q >= s
     const int r = tid >> 3, cg = tid & 7;
     double xi[4] = {0, 0, 0, 0}, xj[4] = {0, 0, 0, 0};
-#pragma unroll 8
-    for (int k = 0; k < CHOL_NB; k++) {
-      const double av = Ai[r][k], bv = Aj[r][k];
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const double l = Li[cg * 4 + q][k]; xi[q] += av * l; xj[q] += bv * l; }      // X[i][j] = sum_k A[i][k] Linv[j][k]
+    for (int s4 = 0; s4 < 4; s4++) {
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        const int k = 8 * s4 + kk;
+        const double av = Ai[r * LD + k], bv = same ? 0.0 : Aj[r * LD + k];
+#pragma unroll
+        for (int q = s4; q < 4; q++) { const double l = Li[(cg + 8 * q) * LD + k]; xi[q] += av * l; xj[q] += bv * l; }      // X[i][j] = sum_k A[i][k] Linv[j][k]
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++) { Xi[r][cg * 4 + q] = xi[q]; Xj[r][cg * 4 + q] = xj[q]; }
-    if (tj == 0 && i0 + r < n) {
-#pragma unroll
-      for (int q = 0; q < 4; q++) S[(size_t)(kbp + cg * 4 + q) * n + i0 + r] = xi[q];            // L^T into the upper triangle
-    }
+    for (int q = 0; q < 4; q++) { Xi[r * LD + cg + 8 * q] = xi[q]; if (!same) Xj[r * LD + cg + 8 * q] = xj[q]; }
   }
   __syncthreads();
+  if (same) Xj = Xi;
+  if (tj == 0)
+    for (int o = tid; o < CHOL_NB * CHOL_NB; o += LM_THREADS) {      // L^T into the upper triangle, coalesced over the factor's rows
+      const int c = o >> 5, r = o & 31;
+      if (i0 + r < n) S[(size_t)(kbp + c) * n + i0 + r] = Xi[r * LD + c];
+    }
   {
     const int tx = tid & 15, ty = tid >> 4;
+    // the tile's old values: in flight while the product runs (last written by another CTA in the previous panel: from L2)
+    double old[2][2];
+#pragma unroll
+    for (int pp = 0; pp < 2; pp++)
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int i = i0 + ty + 16 * pp, j = j0 + tx + 16 * q;
+        old[pp][q] = (i < n && j < n && j <= i) ? __ldcg(&S[(size_t)i * n + j]) : 0.0;
+      }
     double acc[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll 8
     for (int k = 0; k < CHOL_NB; k++) {
-      const double a0 = Xi[ty][k], a1 = Xi[ty + 16][k], b0 = Xj[tx][k], b1 = Xj[tx + 16][k];
+      const double a0 = Xi[ty * LD + k], a1 = Xi[(ty + 16) * LD + k], b0 = Xj[tx * LD + k], b1 = Xj[(tx + 16) * LD + k];
       acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
     }
 #pragma unroll
@@ -854,7 +893,7 @@ __device__ __forceinline__ void chol_fused_tile(int n, int p, int ti, int tj, do
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const int i = i0 + ty + 16 * pp, j = j0 + tx + 16 * q;
-        if (i < n && j < n && j <= i) S[(size_t)i * n + j] = __ldcg(&S[(size_t)i * n + j]) - acc[pp][q];      // last written by another CTA (previous panel): read it from L2
+        if (i < n && j < n && j <= i) S[(size_t)i * n + j] = old[pp][q] - acc[pp][q];
       }
   }
 }
@@ -1139,8 +1178,8 @@ k_lm(LmArgs a) {
       }
     }
     // ---------------------------------------------------------------------------------------- phase C: g_h^T A g_h -> reg
-    const int nsh = (n_s + LM_THREADS - 1) / LM_THREADS;           // virtual blocks of shared rows
-    auto quad_pass = [&](const double* u, const double* v, int two, double* partial /*[F + nsh][5]*/) {
+    const int nsh = n_s;                                           // records of the shared rows (one per row)
+    auto quad_pass = [&](const double* u, const double* v, int two, double* partial /*[F + n_s][5]*/) {
       for (int f = gwarp; f < F; f += gwarps) {
         const double* Wf = a.W + (size_t)f * n_s * FB;
         double tu[FB], tv[FB];
@@ -1177,22 +1216,24 @@ k_lm(LmArgs a) {
           q[0] = uu; q[1] = uv; q[2] = vv; q[3] = dt; q[4] = g2;
         }
       }
-      for (int sb = blockIdx.x; sb < nsh; sb += nblk) {
-        const int i = sb * LM_THREADS + tid;
-        double uu = 0, uv = 0, vv = 0, dt = 0, g2 = 0;
-        if (i < n_s) {
-          double hu = 0, hv = 0;
-          for (int j = 0; j < n_s; j++) {
-            const double h = a.Hss[(size_t)j * n_s + i];
-            hu += h * a.d[j] * u[j];
-            if (two) hv += h * a.d[j] * v[j];
-          }
-          const double ui = a.d[i] * u[i], vi = two ? a.d[i] * v[i] : 0.0;
-          uu = ui * hu; uv = ui * hv; vv = vi * hv;
-          if (two) { dt = u[i] * v[i]; g2 = v[i] * v[i]; }
+      // shared rows: a warp per row of H_ss (contiguous: coalesced), one record per row.  (A thread per COLUMN walking all rows had only
+      // ceil(n_s / 256) CTAs at work on a serial chain of n_s L2 round trips: most of phase C at n_s = 286 and 1030.)
+      for (int j = gwarp; j < n_s; j += gwarps) {
+        const double* Hr = a.Hss + (size_t)j * n_s;
+        double hu = 0.0, hv = 0.0;
+#pragma unroll 4
+        for (int i = lane; i < n_s; i += 32) {
+          const double h = Hr[i], di = a.d[i];
+          hu += h * (di * u[i]);
+          if (two) hv += h * (di * v[i]);
         }
-        const double r0 = block_sum_all(uu, sm), r1 = block_sum_all(uv, sm), r2 = block_sum_all(vv, sm), r3 = block_sum_all(dt, sm), r4 = block_sum_all(g2, sm);
-        if (tid == 0) { double* q = partial + (size_t)(F + sb) * 5; q[0] = r0; q[1] = r1; q[2] = r2; q[3] = r3; q[4] = r4; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { hu += __shfl_xor_sync(0xffffffffu, hu, o); hv += __shfl_xor_sync(0xffffffffu, hv, o); }
+        if (lane == 0) {
+          const double uj = a.d[j] * u[j], vj = two ? a.d[j] * v[j] : 0.0;
+          double* q = partial + (size_t)(F + j) * 5;
+          q[0] = uj * hu; q[1] = uj * hv; q[2] = vj * hv; q[3] = two ? u[j] * v[j] : 0.0; q[4] = two ? v[j] * v[j] : 0.0;
+        }
       }
     };
     LMPH(3)

@@ -608,7 +608,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     CK(ctx->rpart.alloc((size_t)chunks * std::max(P.n_s, 1)));
     CK(ctx->part_scale.alloc((size_t)ctx->num_sms * 6));
     CK(ctx->part_step.alloc((size_t)ctx->num_sms * 2));
-    CK(ctx->part_quad.alloc(8 + (size_t)(F + (P.n_s + LM_THREADS - 1) / LM_THREADS + 2) * 5));
+    CK(ctx->part_quad.alloc(8 + (size_t)(F + P.n_s + 2) * 5));
     CK(ctx->prof.alloc(16)); CK(cudaMemsetAsync(ctx->prof.p, 0, 16 * sizeof(unsigned long long), ctx->stream));
     CK(ctx->lm_bar.alloc(2)); CK(cudaMemsetAsync(ctx->lm_bar.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (!ctx->peer_seq_dev.p) { CK(ctx->peer_seq_dev.alloc(1)); CK(cudaMemsetAsync(ctx->peer_seq_dev.p, 0, sizeof(unsigned long long), ctx->stream)); }

@@ -31,10 +31,12 @@ class FakeEngine(Engine):
     self.mask, self.points = np.array(mask, bool), np.array(points, np.float64)
     self.board_points = np.array(board_points, np.float64).reshape(B, P, 3)
 
-  def upload_dense(self, model, optimize_bits, mask, points, board_points):
+  def upload_dense(self, model, optimize_bits, mask, points, board_points, view_valid=None):
     self.calls.append("upload_dense")
     self.table = None
-    self._set_problem(model, optimize_bits, np.asarray(mask), points, board_points)
+    mask = np.asarray(mask)
+    if view_valid is not None: mask = mask & np.asarray(view_valid)[..., None]      # the conjunction the device takes (mcba_upload_dense_views)
+    self._set_problem(model, optimize_bits, mask, points, board_points)
 
   def set_state_matrices(self, pose_matrices, intrinsics):
     self.calls.append("set_state_matrices")
