@@ -306,6 +306,31 @@ def run_ours(args):
   local_scene = pin(subsample_frames(scene, np.arange(*my)) if world > 1 else scene)
   main, calib = measure(local_scene, args.steps, args.warmup)
 
+  # the same end-to-end call over a float32 table: make_point_table keeps the dtype of the detector's corners (tables.py:15-17; cv2 returns
+  # float32), so for real detections THIS is the reference's table.  The scene is the main scene rounded to float32 (8 B per entry over the link).
+  e2e_f32 = None
+  if args.secondary:
+    scene32 = dict(local_scene)
+    scene32["points"] = torch.from_numpy(np.ascontiguousarray(local_scene["points"], dtype=np.float32)).pin_memory().numpy()
+    def solve_e2e32():
+      c = from_scene(scene32).enable(cameras=True)
+      t0 = time.perf_counter()
+      o = c.bundle_adjust(**BA_KW)
+      _ = o.last_solve.cost
+      torch.cuda.synchronize()
+      return o.last_solve, time.perf_counter() - t0
+    for _ in range(args.warmup): solve_e2e32()
+    barrier()
+    t32, ev32 = 0.0, 0
+    for _ in range(args.steps):
+      flush.zero_(); torch.cuda.synchronize()
+      r32, dt = solve_e2e32(); t32 += dt; ev32 += r32.nfev + r32.njev
+    barrier()
+    t32 = allmax(t32)
+    e2e_f32 = dict(value=main["corners"] * ev32 / t32, unit=UNIT, ms_per_step=1e3 * t32 / args.steps,
+                   h2d_bytes_per_step=int(calib.inliers.size) * (1 + 8) + int(np.prod(calib.board_points.points.shape)) * 8 + sum(a.size for a in calib._state_arrays()) * 8,
+                   note="point table as float32 (the dtype the reference's make_point_table keeps for cv2 detections); `e2e` above is the float64 table")
+
   others = {}
   parity = None
   if world == 1 and args.secondary:
@@ -364,6 +389,7 @@ def run_ours(args):
                           parallelism=f"frames sharded over {world} GPU(s); in-kernel NVLink peer-memory exchanges" if world > 1 else "1 GPU"),
               lm_iters_per_sec=main["lm_iters_per_sec"], nfev_plus_njev_per_step=main["nfev_plus_njev_per_step"],
               e2e=main["e2e"], gpu_launches=main["gpu_launches"], clocks=sampler.summary(), roofline=roofline, cpu_baseline=cpu_baseline)
+  if e2e_f32: line["e2e_float32_table"] = e2e_f32
   if others: line["other_workloads"] = others
   if parity: line["parity_vs_single_gpu"] = parity
   emit(line)

@@ -123,6 +123,11 @@ int  mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8
  * the caller hands over the detection table untouched (no 1-byte-per-point host pass before the copy).                          */
 int  mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid,
                              const double* points, const double* board_points, int64_t* n_corners);
+/* The same for a float32 table, points f32[C][F][B][P][2]: make_point_table keeps the dtype of the detector's corners (tables.py:15-17
+ * fill_sparse: `dtype=values.dtype`; cv2's aruco / charuco detectors return float32), so this IS the reference's table for real
+ * detections -- half the bytes over the link and no float64 copy of the table on the host.  The packed observations are f64 (exact). */
+int  mcba_upload_dense_views_f32(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid,
+                                 const float* points, const double* board_points, int64_t* n_corners);
 
 /* full parameter state (also the values of disabled/fixed blocks):
  * cam_rt f64[C][6], board_rt f64[B][6], frame_rt f64[F][6] (PoseSet.params, pose_set.py:51-53),

@@ -23,7 +23,7 @@ STATUS_MESSAGES = {
   4: "Both `ftol` and `xtol` termination conditions are satisfied.",
 }
 EXPORTS = ["mcba_create", "mcba_destroy", "mcba_last_error", "mcba_set_stream", "mcba_version",
-           "mcba_comm_unique_id", "mcba_comm_init", "mcba_peer_export", "mcba_peer_import", "mcba_upload", "mcba_upload_dense", "mcba_upload_dense_views", "mcba_set_params", "mcba_get_params", "mcba_set_state_matrices", "mcba_get_state_matrices",
+           "mcba_comm_unique_id", "mcba_comm_init", "mcba_peer_export", "mcba_peer_import", "mcba_upload", "mcba_upload_dense", "mcba_upload_dense_views", "mcba_upload_dense_views_f32", "mcba_set_params", "mcba_get_params", "mcba_set_state_matrices", "mcba_get_state_matrices",
            "mcba_set_rolling", "mcba_get_rolling", "mcba_set_hand_eye", "mcba_get_hand_eye",
            "mcba_num_params", "mcba_get_param_vec", "mcba_set_param_vec", "mcba_residuals",
            "mcba_linearize", "mcba_reprojection_error", "mcba_solve", "mcba_bench_launch", "mcba_bench_info",
@@ -89,6 +89,7 @@ def load():
   lib.mcba_upload.argtypes = [P, C.POINTER(ProblemDesc), I32, I32, I32, I32, D, D]
   lib.mcba_upload_dense.argtypes = [P, C.POINTER(ProblemDesc), C.POINTER(C.c_uint8), D, D, C.POINTER(C.c_int64)]
   lib.mcba_upload_dense_views.argtypes = [P, C.POINTER(ProblemDesc), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), D, D, C.POINTER(C.c_int64)]
+  lib.mcba_upload_dense_views_f32.argtypes = [P, C.POINTER(ProblemDesc), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.POINTER(C.c_float), D, C.POINTER(C.c_int64)]
   lib.mcba_set_params.argtypes = [P, D, D, D, D]
   lib.mcba_get_params.argtypes = [P, D, D, D, D]
   lib.mcba_set_state_matrices.argtypes = [P, D, D]

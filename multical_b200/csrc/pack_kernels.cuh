@@ -65,7 +65,10 @@ struct PackOut {
 };
 
 // one warp per view: scatter the selected corners to their frame-major slot; lane 0 emits the view record
-__global__ void k_pack_scatter(const uint8_t* mask, const double2* points, int C, int F, int B, int P,
+// PT = double2, or float2: the reference's table keeps the dtype of the detector's corners (tables.py:15-17 fill_sparse; cv2 returns
+// float32), the packed observations are f64 either way (exact)
+template <typename PT>
+__global__ void k_pack_scatter(const uint8_t* mask, const PT* points, int C, int F, int B, int P,
                                const int* off_can, const int* off_fm, const int* vid_can, const int* vid_fm, PackOut o) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nv = C * F * B;
@@ -86,7 +89,7 @@ __global__ void k_pack_scatter(const uint8_t* mask, const double2* points, int C
     o.cam_view_list[vid_can[w]] = vid;
   }
   const uint8_t* m = mask + (size_t)w * P;
-  const double2* pt = points + (size_t)w * P;
+  const PT* pt = points + (size_t)w * P;
   int running = 0;
   for (int p0 = 0; p0 < P; p0 += 32) {
     const int p = p0 + lane;
@@ -94,7 +97,8 @@ __global__ void k_pack_scatter(const uint8_t* mask, const double2* points, int C
     const unsigned bal = __ballot_sync(0xffffffffu, on);
     if (on) {
       const int r = running + __popc(bal & ((1u << lane) - 1u));
-      o.obs[base_fm + r] = pt[p];
+      const PT q = pt[p];
+      o.obs[base_fm + r] = make_double2((double)q.x, (double)q.y);
       o.pid[base_fm + r] = (uint16_t)p;
       o.orig[base_fm + r] = (uint32_t)(base_can + r);
     }

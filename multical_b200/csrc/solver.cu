@@ -57,7 +57,7 @@ struct mcba_ctx {
   DevBuf<double2> obs; DevBuf<uint16_t> pid; DevBuf<uint32_t> orig;
   DevBuf<int> view_start, view_cam, view_frame, view_board, frame_view_start, cam_view_start, cam_view_list;
   DevBuf<double> board_pts, cam_rt, board_rt, frame_rt, intr;
-  DevBuf<uint8_t> dense_mask, view_valid; DevBuf<double2> dense_pts; DevBuf<int> scan;
+  DevBuf<uint8_t> dense_mask, view_valid; DevBuf<double2> dense_pts; DevBuf<float2> dense_pts32; DevBuf<int> scan;
   cudaStream_t copy_stream = nullptr; cudaEvent_t copy_done = nullptr, copy_go = nullptr;      // observations of mcba_upload_dense* in flight beside the view count
   DevBuf<PoseT> cam_T, frame_T, board_T;
   // trial parameter state
@@ -658,7 +658,7 @@ int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
 // points_ready: event after which dense_pts holds the observations (they may still be in flight on the copy stream while the views are
 // counted and scanned), or null
 int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_mask, bool keep_state, int64_t* n_corners,
-               const uint8_t* d_view_valid = nullptr, cudaEvent_t points_ready = nullptr) {
+               const uint8_t* d_view_valid = nullptr, cudaEvent_t points_ready = nullptr, bool points_f32 = false) {
   const int C = desc->C, F = desc->F, B = desc->B, Pn = desc->P;
   const int nv = C * F * B;
   cudaStream_t s = ctx->stream;
@@ -680,7 +680,9 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
   if (nv > 0) {
     PackOut o{ctx->obs.p, ctx->pid.p, ctx->orig.p, ctx->view_start.p, ctx->view_cam.p, ctx->view_frame.p, ctx->view_board.p,
               ctx->frame_view_start.p, ctx->cam_view_start.p, ctx->cam_view_list.p};
-    k_pack_scatter<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_mask, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL();
+    const unsigned blocks = (unsigned)(((size_t)nv * 32 + 255) / 256);
+    if (points_f32) { k_pack_scatter<float2><<<blocks, 256, 0, s>>>(d_mask, (const float2*)ctx->dense_pts32.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL(); }
+    else { k_pack_scatter<double2><<<blocks, 256, 0, s>>>(d_mask, (const double2*)ctx->dense_pts.p, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm, o); CKL(); }
   } else {
     CK(cudaMemsetAsync(ctx->view_start.p, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctx->frame_view_start.p, 0, sizeof(int) * (F + 1), s));
     CK(cudaMemsetAsync(ctx->cam_view_start.p, 0, sizeof(int) * (C + 1), s));
@@ -886,8 +888,9 @@ int mcba_upload(mcba_ctx* ctx, const mcba_problem_desc* desc, const int32_t* cam
 
 // Dense variant: the [C,F,B,P] inlier mask and [C,F,B,P,2] observations go to the device as they are and the
 // packing (frame-major order, view records, canonical index map) happens there (pack_kernels.cuh).
-int mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid, const double* points,
-                            const double* board_points, int64_t* n_corners) {
+namespace {
+int upload_dense_any(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid, const void* points, bool points_f32,
+                     const double* board_points, int64_t* n_corners) {
   if (!ctx || !desc) return MCBA_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   { int r = check_desc(ctx, desc); if (r) return r; }
@@ -896,7 +899,8 @@ int mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const 
   const int nv = C * F * B;
   const size_t dense = (size_t)nv * Pn;
   cudaStream_t s = ctx->stream;
-  CK(ctx->dense_mask.alloc(std::max<size_t>(dense, 1))); CK(ctx->dense_pts.alloc(std::max<size_t>(dense, 1)));
+  CK(ctx->dense_mask.alloc(std::max<size_t>(dense, 1)));
+  if (points_f32) CK(ctx->dense_pts32.alloc(std::max<size_t>(dense, 1))); else CK(ctx->dense_pts.alloc(std::max<size_t>(dense, 1)));
   CK(ctx->view_valid.alloc(std::max<size_t>((size_t)nv, 1)));
   CK(ctx->scan.alloc((size_t)4 * (nv + 1)));
   CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
@@ -909,13 +913,25 @@ int mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const 
     if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->copy_go, cudaEventDisableTiming)); }
     CK(cudaEventRecord(ctx->copy_go, s));                          // work queued on `s` before this call may still read dense_pts
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_go, 0));
-    CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (points_f32) CK(cudaMemcpyAsync(ctx->dense_pts32.p, points, dense * sizeof(float2), cudaMemcpyHostToDevice, ctx->copy_stream));
+    else CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, ctx->copy_stream));
     CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     ready = ctx->copy_done;
   }
   CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
   ctx->table = false; ctx->table_selected = -1; ctx->errors_current = false;
-  return pack_dense(ctx, desc, ctx->dense_mask.p, false, n_corners, view_valid ? ctx->view_valid.p : nullptr, ready);
+  return pack_dense(ctx, desc, ctx->dense_mask.p, false, n_corners, view_valid ? ctx->view_valid.p : nullptr, ready, points_f32);
+}
+}  // namespace
+
+int mcba_upload_dense_views(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid, const double* points,
+                            const double* board_points, int64_t* n_corners) {
+  return upload_dense_any(ctx, desc, valid, view_valid, points, false, board_points, n_corners);
+}
+
+int mcba_upload_dense_views_f32(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* valid, const uint8_t* view_valid, const float* points,
+                                const double* board_points, int64_t* n_corners) {
+  return upload_dense_any(ctx, desc, valid, view_valid, points, true, board_points, n_corners);
 }
 
 int mcba_upload_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* mask, const double* points,

@@ -99,12 +99,19 @@ class Engine:
     Cn, F, B, P = mask.shape
     u8 = lambda a: a.view(np.uint8) if a.dtype == np.bool_ else np.ascontiguousarray(a, dtype=np.uint8)
     m8 = u8(mask)
-    pts = nat.f64(points)
+    # a float32 table (what make_point_table yields for cv2's float32 corners, tables.py:15-17) goes over as it is; anything else as f64
+    f32 = np.asarray(points).dtype == np.float32
+    pts = np.ascontiguousarray(points) if f32 else nat.f64(points)
     assert pts.shape == (Cn, F, B, P, 2), f"points {pts.shape} do not match mask {mask.shape}"
     bp = nat.f64(board_points).reshape(B, P, 3)
     d = nat.ProblemDesc(Cn, F, B, P, nat.MODEL_IDS[model], int(optimize_bits), 0)
     n = C.c_int64()
-    if view_valid is None:
+    if f32:
+      v8 = None if view_valid is None else u8(np.ascontiguousarray(view_valid))
+      self._ck(self.lib.mcba_upload_dense_views_f32(self.h, C.byref(d), m8.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                    None if v8 is None else v8.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                    pts.ctypes.data_as(C.POINTER(C.c_float)), nat.dptr(bp), C.byref(n)))
+    elif view_valid is None:
       self._ck(self.lib.mcba_upload_dense(self.h, C.byref(d), m8.ctypes.data_as(C.POINTER(C.c_uint8)), nat.dptr(pts),
                                           nat.dptr(bp), C.byref(n)))
     else:

@@ -30,7 +30,8 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-struct alignas(16) double2 { double x, y; };      // 16-byte vector accesses fault on hardware when misaligned: let the host build use aligned moves too
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) float2 { float x, y; };      // 16-byte vector accesses fault on hardware when misaligned: let the host build use aligned moves too
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct int2 { int x, y; };
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }

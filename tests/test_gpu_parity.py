@@ -315,6 +315,14 @@ def test_device_packing_equals_host_packing(name):
   eng = fresh._upload_inliers()
   assert "valid" not in fresh.__dict__ and eng.N == idx.shape[0]
   assert np.array_equal(eng.residuals(z["x1"]), r_dense)
+  # a float32 table (the dtype make_point_table keeps for cv2's corners) goes over as float32 and must be the float64 table of the same values
+  pts32 = np.asarray(calib.point_table.points).astype(np.float32)
+  eng = calib._upload(calib.inliers, points=pts32.astype(np.float64))
+  r_64 = eng.residuals(z["x1"]).copy()
+  eng = calib._upload(calib.inliers, points=pts32)
+  assert eng.N == idx.shape[0] and np.array_equal(eng.residuals(z["x1"]), r_64)
+  eng = calib._upload(np.asarray(calib.point_table.valid), points=pts32, view_valid=calib.pose_valid)
+  assert eng.N == idx.shape[0] and np.array_equal(eng.residuals(z["x1"]), r_64)
 
 
 def test_empty_and_ragged_inputs():

@@ -14,7 +14,7 @@ from oracle.ba_oracle import Problem
 
 def test_cabi_library_exports_every_declared_symbol(build_lib):
   header = open(os.path.join(ROOT, "include", "mcba.h")).read()
-  declared = sorted(set(re.findall(r"\b(mcba_[a-z_]+)\s*\(", header)))
+  declared = sorted(set(re.findall(r"\b(mcba_[a-z0-9_]+)\s*\(", header)))
   assert len(declared) >= 15
   lib = _native.load()
   for sym in declared:
