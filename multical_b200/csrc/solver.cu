@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/mcba.h"
@@ -645,6 +646,12 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
   REQUIRE(expand_shared_smem(P) <= 200 * 1024, MCBA_ERR_UNSUPPORTED, "shared-parameter block too large for the expand kernels");
   return MCBA_OK;
 }
+// MCBA_PROF=1: host wall clock at checkpoints of the upload path, on stderr (no synchronisation is added: it times what the host waits for)
+struct UploadClock {
+  bool on; std::chrono::steady_clock::time_point t0;
+  explicit UploadClock(bool enabled) : on(enabled), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) { if (on) fprintf(stderr, "[upload] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
 int check_desc(mcba_ctx* ctx, const mcba_problem_desc* desc) {
   REQUIRE(desc->C > 0 && desc->F >= 0 && desc->B > 0 && desc->P > 0, MCBA_ERR_ARG, "bad problem dimensions");
   REQUIRE(desc->P <= 65535, MCBA_ERR_UNSUPPORTED, "more than 65535 points per board");
@@ -665,12 +672,15 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
   CK(ctx->scan.alloc((size_t)4 * (nv + 1)));
   int* cnt_can = ctx->scan.p; int* cnt_fm = cnt_can + (nv + 1); int* flag_can = cnt_fm + (nv + 1); int* flag_fm = flag_can + (nv + 1);
   int totals[2] = {0, 0};
+  UploadClock clk(ctx->profiling);
   if (nv > 0) {
     k_pack_count<<<(unsigned)(((size_t)nv * 32 + 255) / 256), 256, 0, s>>>(d_mask, d_view_valid, C, F, B, Pn, cnt_can, cnt_fm, flag_can, flag_fm); CKL();
     k_scan_exclusive<<<4, 1024, 0, s>>>(cnt_can, nv, nv + 1); CKL();      // cnt_can | cnt_fm | flag_can | flag_fm
     CK(cudaMemcpyAsync(&totals[0], cnt_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&totals[1], flag_can + nv, sizeof(int), cudaMemcpyDeviceToHost, s));
+    clk.mark("pack: count/scan/d2h issued");
     CK(cudaStreamSynchronize(s));
+    clk.mark("pack: totals on the host");
   }
   const int64_t N = totals[0]; const int V = totals[1];
   CK(ctx->obs.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->pid.alloc((size_t)std::max<int64_t>(N, 1))); CK(ctx->orig.alloc((size_t)std::max<int64_t>(N, 1)));
@@ -687,8 +697,11 @@ int pack_dense(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t* d_ma
     CK(cudaMemsetAsync(ctx->view_start.p, 0, sizeof(int), s)); CK(cudaMemsetAsync(ctx->frame_view_start.p, 0, sizeof(int) * (F + 1), s));
     CK(cudaMemsetAsync(ctx->cam_view_start.p, 0, sizeof(int) * (C + 1), s));
   }
+  clk.mark("pack: scatter issued");
   { int r = setup_problem(ctx, desc, N, V, keep_state); if (r) return r; }
+  clk.mark("pack: setup_problem done");
   CK(cudaStreamSynchronize(s));
+  clk.mark("pack: final synchronise");
   if (n_corners) *n_corners = N;
   ctx->uploaded = true;
   return MCBA_OK;
@@ -905,11 +918,15 @@ int upload_dense_any(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t
   CK(ctx->scan.alloc((size_t)4 * (nv + 1)));
   CK(ctx->board_pts.alloc((size_t)B * Pn * 3));
   cudaEvent_t ready = nullptr;
+  UploadClock clk(ctx->profiling);
   if (dense) {
     // the mask (1 B/point) goes first on the solver's stream; the observations (16 B/point) follow on the copy stream while the views
     // are counted and scanned, and the scatter waits for them
     CK(cudaMemcpyAsync(ctx->dense_mask.p, valid, dense, cudaMemcpyHostToDevice, s));
     if (view_valid) CK(cudaMemcpyAsync(ctx->view_valid.p, view_valid, (size_t)nv, cudaMemcpyHostToDevice, s));
+    // the small copies from pageable memory go BEFORE the table: such a copy returns when it is done, and behind 100 MB on the copy engine
+    // it would hold the host back until the table has crossed the link -- with it the count / scan kernels that should run beside it
+    CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
     if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->copy_go, cudaEventDisableTiming)); }
     CK(cudaEventRecord(ctx->copy_go, s));                          // work queued on `s` before this call may still read dense_pts
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_go, 0));
@@ -917,8 +934,10 @@ int upload_dense_any(mcba_ctx* ctx, const mcba_problem_desc* desc, const uint8_t
     else CK(cudaMemcpyAsync(ctx->dense_pts.p, points, dense * sizeof(double2), cudaMemcpyHostToDevice, ctx->copy_stream));
     CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     ready = ctx->copy_done;
+    clk.mark("upload: copies issued");
+  } else {
+    CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
   }
-  CK(cudaMemcpyAsync(ctx->board_pts.p, board_points, sizeof(double) * (size_t)B * Pn * 3, cudaMemcpyHostToDevice, s));
   ctx->table = false; ctx->table_selected = -1; ctx->errors_current = false;
   return pack_dense(ctx, desc, ctx->dense_mask.p, false, n_corners, view_valid ? ctx->view_valid.p : nullptr, ready, points_f32);
 }

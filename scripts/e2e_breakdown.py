@@ -25,7 +25,14 @@ T("inliers (valid mask)", lambda: from_scene(scene).inliers)
 T("board_points", lambda: from_scene(scene).board_points)
 T("_optimize_bits + engine_model", lambda: (from_scene(scene).enable(cameras=True)._optimize_bits(), from_scene(scene).engine_model))
 m, pts, bp = calib.inliers, np.asarray(calib.point_table.points), calib.board_points.points
-T("upload_dense", lambda: eng.upload_dense(calib.engine_model, calib._optimize_bits(), m, pts, bp))
+T("upload_dense (inliers built on the host)", lambda: eng.upload_dense(calib.engine_model, calib._optimize_bits(), m, pts, bp))
+pv, vv = calib.pose_valid, np.asarray(calib.point_table.valid)
+T("upload_dense (valid + view_valid, f64)", lambda: eng.upload_dense(calib.engine_model, calib._optimize_bits(), vv, pts, bp, view_valid=pv))
+pts32 = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float32)).pin_memory().numpy()
+T("upload_dense (valid + view_valid, f32 table)", lambda: eng.upload_dense(calib.engine_model, calib._optimize_bits(), vv, pts32, bp, view_valid=pv))
+t_ = torch.empty(pts.nbytes, dtype=torch.uint8, device="cuda"); src_ = torch.from_numpy(pts.view(np.uint8).reshape(-1))
+T("plain H2D of the f64 table (torch, pinned)", lambda: t_.copy_(src_, non_blocking=True))
+eng.upload_dense(calib.engine_model, calib._optimize_bits(), m, pts, bp)
 mats = np.concatenate([calib.camera_poses.poses, calib.board_poses.poses, calib.motion.poses])
 intr = np.stack([c.param_vec for c in calib.cameras])
 T("set_state_matrices", lambda: eng.set_state_matrices(mats, intr))
