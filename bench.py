@@ -206,17 +206,6 @@ def run_ours(args):
   assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
   torch.cuda.set_device(local)
   os.environ["MCBA_DEVICE"] = str(local)
-  # Pin this process to the CPUs next to its GPU before any pinned host buffer is allocated: on a two-socket host a pinned table that lands
-  # on the far socket crosses the link at 22 GB/s instead of 55 (measured, profiles/r02_upload_timing.txt) -- the numactl a deployment would use.
-  # Undone before the CPU baseline leg, which gets every core.
-  affinity = None
-  try:
-    import pynvml
-    pynvml.nvmlInit()
-    pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-    affinity = f"GPU-local CPUs ({len(os.sched_getaffinity(0))} of {os.cpu_count()}, nvmlDeviceSetCpuAffinity) while the host tables are allocated and copied"
-  except Exception:
-    pass
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
   stream = torch.cuda.current_stream()
@@ -388,8 +377,6 @@ def run_ours(args):
                        "~6 flop/B on B200), so the fp64 pipe bounds it: see profiles/ for sm__inst_executed_pipe_fp64 / pipe_fp64 cycles of the same launch")
 
   # ---- CPU baseline: the reference's path on a bounded sample of the same workload ---------------------------------------------
-  try: os.sched_setaffinity(0, range(os.cpu_count()))
-  except Exception: pass
   cpu_baseline, *_ = cpu_baseline_block(scene, args.workload, args.ref_frames or REF_FRAMES.get(args.workload, 4))
 
   line = dict(metric=METRIC, value=main["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -398,7 +385,7 @@ def run_ours(args):
               config=dict(workload=args.workload, cameras=scene["C"], frames=scene["F"], boards=scene["B"], corners=main["corners"],
                           params=main["params"] if world == 1 else None, frames_per_gpu=my[1] - my[0], camera_model=scene["model"],
                           solver="TRF semantics (ftol=1e-4, x_scale=jac, max_nfev=100), exact Schur inner solve; device-resident loop (CUDA-graph WHILE)",
-                          l2="flushed between timed iterations (256 MiB write)", seed=args.seed, host_affinity=affinity,
+                          l2="flushed between timed iterations (256 MiB write)", seed=args.seed,
                           parallelism=f"frames sharded over {world} GPU(s); in-kernel NVLink peer-memory exchanges" if world > 1 else "1 GPU"),
               lm_iters_per_sec=main["lm_iters_per_sec"], nfev_plus_njev_per_step=main["nfev_plus_njev_per_step"],
               e2e=main["e2e"], gpu_launches=main["gpu_launches"], clocks=sampler.summary(), roofline=roofline, cpu_baseline=cpu_baseline)
