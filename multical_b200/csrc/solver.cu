@@ -544,7 +544,7 @@ int setup_problem(mcba_ctx* ctx, const mcba_problem_desc* desc, int64_t N, int V
     ctx->lin_split = split;
     // warps per CTA in {8, 4, 2}: the choice that keeps most warps resident per SM (shared memory: 227 KB minus ~4 KB per CTA;
     // registers: 128 per thread -> 16 warps) times how evenly the cameras spread over the CTA's warps (a warp owns cameras c == w mod warps;
-    // the CTA meets at the end of every frame).  16 cameras x 5 boards: 4 CTAs of 4 warps instead of 1 of 8.
+    // the CTA meets at the end of every frame).  16 cameras x 5 boards (11 KB per warp): 2 CTAs of 8 warps; 4 of 4 score the same.
     int warps = LIN_WARPS;
     if (split == 1) {
       double best = -1.0;
