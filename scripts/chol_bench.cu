@@ -1,11 +1,12 @@
 // Developer micro-benchmark (GPU box): the reduced-system solvers of csrc/lm_kernel.cuh on random SPD systems, one CTA, timed with clock64.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I multical_b200/csrc -o /tmp/chol_bench scripts/chol_bench.cu && /tmp/chol_bench
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I multical_b200/csrc -I scripts -o /tmp/chol_bench scripts/chol_bench.cu && /tmp/chol_bench
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cmath>
 #include <vector>
 #include "../include/mcba.h"
 #include "lm_kernel.cuh"
+#include "chol_variants.cuh"
 using namespace mcba;
 
 template <int R>
