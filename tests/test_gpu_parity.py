@@ -272,10 +272,12 @@ def test_bad_inputs_raise_like_the_reference():
     bad.bundle_adjust()
 
 
-@pytest.mark.parametrize("workload", ["cfg2", "cfg3"])
+@pytest.mark.parametrize("workload", ["cfg2", "cfg3", "cfg4", "cfg5"])
 def test_large_scene_properties(workload):
-  """BASELINE cfg2 / cfg3 (fisheye, 1M corners) sizes: size-independent properties (no oracle run): cost decreases
-  monotonically, RMS lands at sigma*sqrt(2), re-solving from the solution is a fixed point, gradient ~0 at the optimum."""
+  """BASELINE cfg2 .. cfg5 at their full sizes (cfg3: fisheye, 1 M corners; cfg4: 5.5 M corners, n_s = 286, the cooperative Cholesky;
+  cfg5: 64 cameras, 50.8 M corners, n_s = 1030): size-independent properties (no oracle run): cost decreases monotonically, RMS lands
+  at sigma*sqrt(2), re-solving from the solution is a fixed point, gradient ~0 at the optimum (dense normal equations: not at cfg5,
+  whose 13 030 x 13 030 matrix is 1.4 GB on the host)."""
   scene = synthetic.make_workload(workload)
   calib = from_scene(scene).enable(cameras=True)
   out = calib.bundle_adjust()
@@ -285,6 +287,7 @@ def test_large_scene_properties(workload):
   assert abs(rms - 0.3 * np.sqrt(2)) < 5e-3
   again = out.bundle_adjust()
   assert again.last_solve.nfev <= 3 and abs(again.last_solve.cost - out.last_solve.cost) <= 1e-6 * out.last_solve.cost
+  if workload == "cfg5": return
   eng = out._upload(out.inliers)
   JtJ, Jtr, cost = eng.linearize()
   d = np.sqrt(np.diag(JtJ)); d[d == 0] = 1
