@@ -63,6 +63,34 @@ if os.environ.get("MCBA_SIMT_FULL") == "1":      # three minutes on the interpre
   test_sixty_four_cameras_configs4_shape = gp.test_sixty_four_cameras_configs4_shape
 test_two_identical_solves_agree_bit_for_bit = gp.test_two_identical_solves_agree_bit_for_bit
 
+def test_more_views_per_frame_and_more_boards_than_the_staged_tables_hold():
+  """k_linearize stages a frame's view records (up to 96) and the board pose tables (up to 8) in shared memory and reads them from
+  global memory beyond that (csrc/linearize.cuh LIN_MAXV, LIN_MAXB).  12 cameras x 9 boards: 108 views per frame, 9 board tables --
+  both fall-backs at once.  Residuals against the oracle, normal equations against finite differences of the oracle."""
+  import numpy as np
+  from scipy.optimize._numdiff import approx_derivative, group_columns
+  from multical_b200 import synthetic
+  from multical_b200.calibration import from_scene
+  from oracle.ba_oracle import Problem
+  scene = synthetic.make_scene(C=12, F=2, vis=0.9, seed=3, boards=("charuco", 5, 4, 0.03, 9))
+  assert (scene["valid"].any(axis=-1).sum(axis=(0, 2)) > 96).all() and scene["B"] == 9
+  calib = from_scene(scene).enable(cameras=True)
+  prob = Problem.from_scene(scene, optimize=dict(cameras=True))
+  eng = calib._upload(calib.inliers)
+  x = prob.param_vec
+  assert np.abs(eng.residuals(x) - prob.residuals(x)).max() < 1e-9
+  S = prob.sparsity_matrix()
+  J = approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, group_columns(S))).toarray()
+  r = prob.residuals(x)
+  H, g = J.T @ J, J.T @ r
+  JtJ, Jtr, cost = eng.linearize(x)
+  nrm = np.sqrt(np.outer(np.diag(H), np.diag(H)))
+  live = nrm > 0
+  assert (np.abs(JtJ - H)[live] / nrm[live]).max() < 1e-6
+  assert np.abs(Jtr - g).max() < 1e-6 * np.abs(g).max()
+  assert abs(cost - 0.5 * r @ r) < 1e-12 * cost
+
+
 # ---- tests/test_gpu_table.py on the interpreter
 test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors = gt.test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors
 test_resident_adjust_outliers_equals_host_loop = gt.test_resident_adjust_outliers_equals_host_loop
