@@ -91,6 +91,35 @@ def test_more_views_per_frame_and_more_boards_than_the_staged_tables_hold():
   assert abs(cost - 0.5 * r @ r) < 1e-12 * cost
 
 
+def test_rolling_frames_with_a_frame_count_that_ends_in_a_partial_syrk_step():
+  """Rolling frames eliminate a 12 x 12 block per frame and the Schur SYRK stages 4 of them per step: 19 frames = 5 steps, the last one
+  partial, in a stage that held an earlier step (the frame-count pattern of test_frame_count_that_ends_a_syrk_chunk_in_a_partial_step for
+  FB = 12).  Residuals against the oracle, converged cost against scipy's dense exact trust region on the oracle's residuals."""
+  import numpy as np
+  from scipy import optimize
+  from scipy.optimize._numdiff import approx_derivative, group_columns
+  from multical_b200 import synthetic
+  from multical_b200.calibration import from_scene
+  from multical_b200.motion import RollingFrames
+  from oracle.ba_oracle import Problem
+  scene = synthetic.make_scene(C=2, F=19, vis=0.3, seed=5)
+  rng = np.random.default_rng(7)
+  start = scene["init"]["frame_poses"]
+  end = synthetic.to_matrix(synthetic.from_matrix(start) + 1e-3 * rng.standard_normal((scene["F"], 6)))
+  enabled = dict(cameras=True, camera_poses=True, board_poses=True, motion=True)
+  prob = Problem.from_scene(scene, optimize=enabled, motion="rolling", frame_poses_end=end, image_size=scene["image_size"])
+  calib = from_scene(scene).copy(motion=RollingFrames(start, end, scene["frame_valid"], [str(i) for i in range(scene["F"])])).enable(**enabled)
+  eng = calib._upload(calib.inliers)
+  assert eng.num_params == prob.param_vec.size
+  assert np.abs(eng.residuals(prob.param_vec) - prob.residuals(prob.param_vec)).max() < 1e-9
+  S = prob.sparsity_matrix(); groups = group_columns(S)
+  jac = lambda x: approx_derivative(prob.residuals, x, method="3-point", sparsity=(S, groups)).toarray()
+  ref = optimize.least_squares(prob.residuals, prob.param_vec, jac=jac, x_scale="jac", ftol=1e-13, xtol=1e-13, gtol=1e-13,
+                               max_nfev=200, method="trf", tr_solver="exact")
+  out = calib.bundle_adjust(tolerance=1e-13, xtol=1e-13, gtol=1e-13, max_iterations=200)
+  assert abs(out.last_solve.cost - ref.cost) <= 1e-8 * ref.cost, (out.last_solve.cost, ref.cost)
+
+
 # ---- tests/test_gpu_table.py on the interpreter
 test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors = gt.test_table_errors_ranks_and_reject_are_numpy_on_the_same_errors
 test_resident_adjust_outliers_equals_host_loop = gt.test_resident_adjust_outliers_equals_host_loop
